@@ -1,0 +1,168 @@
+/* libsimx_b200 — C ABI of the B200-native dual-encoder training step.
+ *
+ * The reference (microsoft/SimXNS) has no FFI: its hot path is reached through a Python module import
+ * (`from model.models import BiBertEncoder, HFBertEncoder, Reranker`, SimANS/co_training/co_training_marco_train.py:18).
+ * This header is the boundary a replacement `models.py` binds (simxns_b200/_lib.py does it with ctypes;
+ * INTEGRATION.md shows the stub).  Each entry point names the reference code it replaces.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; every device buffer is allocated and owned by the caller (PyTorch);
+ *     the library never allocates or frees device memory and keeps no pointer past a call;
+ *   - every function returns SIMX_OK (0) or a SIMX_ERR_* code; `simx_last_error()` returns the thread-local
+ *     message of the last failure; no C++ exception crosses the ABI;
+ *   - all work is enqueued on the caller's `stream` (a cudaStream_t passed as void*); calls are re-entrant;
+ *   - matrices are row-major; "planes" is 1 (bf16) or 3 (split-bf16, fp32-class: value = hi + mid + lo, plane p
+ *     at element offset p * plane_stride).
+ */
+#ifndef SIMX_B200_H_
+#define SIMX_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SIMX_OK 0
+#define SIMX_ERR_INVALID 1     /* bad argument / unsupported shape */
+#define SIMX_ERR_CUDA 2        /* a CUDA runtime / driver call failed */
+#define SIMX_ERR_UNSUPPORTED 3 /* feature not available (e.g. not an sm_100 device) */
+
+#define SIMX_ARCH_BERT 0       /* HF BertModel: word+position+token_type embeddings (LEAD/modeling_bert.py:181-660) */
+#define SIMX_ARCH_DISTILBERT 1 /* HF DistilBertModel: word+position embeddings (LEAD/modeling_distilbert.py:93-376) */
+
+#define SIMX_PREC_BF16 1   /* bf16 operands, fp32 accumulate (throughput mode) */
+#define SIMX_PREC_BF16X3 3 /* 3 bf16 planes per activation/weight, 6 MMA passes (fp32-class parity mode) */
+
+typedef struct simx_encoder_cfg {
+  int32_t arch;         /* SIMX_ARCH_* */
+  int32_t num_layers;   /* L */
+  int32_t hidden;       /* H, multiple of 64 */
+  int32_t heads;        /* H / heads must be 64 */
+  int32_t intermediate; /* I, multiple of 64 */
+  int32_t vocab;
+  int32_t max_pos;
+  int32_t type_vocab;   /* 0 for DistilBERT */
+  int32_t precision;    /* SIMX_PREC_* */
+  float ln_eps;
+} simx_encoder_cfg;
+
+/* ------------------------------------------------------------------------------------------------
+ * Library
+ * ---------------------------------------------------------------------------------------------- */
+const char* simx_last_error(void);
+int simx_version(void);
+/* 1 when the current CUDA device can run the kernels (compute capability 10.x), else 0. */
+int simx_device_supported(void);
+
+/* ------------------------------------------------------------------------------------------------
+ * Parameter table.  `params` / offsets use this canonical order (fp32 tensors, HF state_dict names):
+ *   BERT:  0 word_embeddings [V,H]  1 position_embeddings [P,H]  2 token_type_embeddings [Tt,H]
+ *          3 embeddings.LayerNorm.weight  4 .bias
+ *          5+16*l + {0 q.w [H,H], 1 q.b, 2 k.w, 3 k.b, 4 v.w, 5 v.b, 6 attn.out.w [H,H], 7 attn.out.b,
+ *                    8 attn.LN.w, 9 attn.LN.b, 10 intermediate.w [I,H], 11 intermediate.b,
+ *                    12 output.w [H,I], 13 output.b, 14 output.LN.w, 15 output.LN.b}
+ *          5+16*L pooler.w [H,H]   6+16*L pooler.b      (pooler is dead math in the reference:
+ *                                                         SimANS/model/models.py:80 multiplies it by 0)
+ *   DistilBERT: same table without entry 2 and without the pooler (indices shift down accordingly).
+ * ---------------------------------------------------------------------------------------------- */
+int simx_encoder_num_params(const simx_encoder_cfg* cfg);
+/* number of elements of parameter `idx` */
+int64_t simx_encoder_param_numel(const simx_encoder_cfg* cfg, int idx);
+/* element offset of parameter `idx`'s gradient inside the flat fp32 gradient buffer written by
+ * simx_encoder_backward (q/k/v weights and biases are adjacent there: the fused QKV wgrad writes them as one
+ * [3H,H] block).  Total size: simx_encoder_grad_numel(). */
+int64_t simx_encoder_grad_offset(const simx_encoder_cfg* cfg, int idx);
+int64_t simx_encoder_grad_numel(const simx_encoder_cfg* cfg);
+
+/* Buffer sizes in bytes for a batch of B sequences padded to S tokens. */
+size_t simx_encoder_weight_bytes(const simx_encoder_cfg* cfg);
+size_t simx_encoder_saved_bytes(const simx_encoder_cfg* cfg, int B, int S);
+size_t simx_encoder_workspace_bytes(const simx_encoder_cfg* cfg, int B, int S);
+
+/* fp32 master weights -> the bf16 (or split-bf16) GEMM operands in `wbuf`: fused [3H,H] QKV weight, and the
+ * transposed copies the dgrad GEMMs read.  Call after every optimizer step (or parameter load). */
+int simx_encoder_prepare_weights(const simx_encoder_cfg* cfg, const float* const* params, void* wbuf, void* stream);
+
+/* Replaces HFBertEncoder.forward -> transformers BertModel.forward
+ * (SimANS/model/models.py:77-82, LEAD/models.py:184-196; math restated in LEAD/modeling_bert.py:201-660).
+ *   ids  [B,S] int64 token ids;  mask [B,S] int64 attention mask (1 = attend, HF semantics; may be NULL = all ones)
+ *   cls_out  [B, L+1, H] fp32: the [CLS] (position 0) row of the embedding output (index 0) and of every
+ *            layer's output (index l+1) — index L is `pooled_output` of the reference wrapper, the others are
+ *            what LEAD reads from its all-layer hidden states (LEAD/util.py:605-614).
+ *   seq_out  [B,S,H] fp32 last hidden state, or NULL to skip materialising it.
+ *   saved    activations kept for backward (simx_encoder_saved_bytes); NULL = inference (nothing kept).
+ * Dropout is not applied (the reference's parity/eval configuration). */
+int simx_encoder_forward(const simx_encoder_cfg* cfg, const float* const* params, const void* wbuf,
+                         const int64_t* ids, const int64_t* mask, int B, int S, void* saved, void* workspace,
+                         float* cls_out, float* seq_out, void* stream);
+
+/* Replaces loss.backward() through the tower (co_training_marco_train.py:222).
+ *   d_cls  [B, L+1, H] fp32 cotangent of cls_out (NULL rows are not allowed; pass zeros);
+ *   d_seq  [B,S,H] fp32 cotangent of seq_out or NULL.
+ *   grads  flat fp32 buffer of simx_encoder_grad_numel() elements, OVERWRITTEN with d(loss)/d(param)
+ *          (dense for every parameter: pooler and unused token-type rows get zeros). */
+int simx_encoder_backward(const simx_encoder_cfg* cfg, const float* const* params, const void* wbuf,
+                          const int64_t* ids, const int64_t* mask, int B, int S, const void* saved,
+                          void* workspace, const float* d_cls, const float* d_seq, float* grads, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Fused score / loss / gradient step (replaces the tail of the train step:
+ * co_training_marco_train.py:199-214, SimANS/model/models.py:468-505, PROD/ProD_KD/model/models.py:669-781,
+ * MASTER/finetune/MS/co_training_model.py:249-269).  See simx_loss_cfg below.
+ * ---------------------------------------------------------------------------------------------- */
+#define SIMX_LOSS_NLL_GLOBAL 1   /* a-5  InfoNCE over the global [GQ,GC] matrix, positives at pos_idx[q] */
+#define SIMX_LOSS_KL_LOCAL 2     /* a-4  SimANS: KLDiv_batchmean(log(softmax(s)+eps), softmax(teacher/T)) on [B,1+n] */
+#define SIMX_LOSS_CE_LOCAL 4     /* a-4' / a-5': -sum p_t log(p_s+eps) / B  on [B,1+n] */
+#define SIMX_LOSS_KD_LOCAL 8     /* a-6  PROD KD_softmax: T^2 * mean_b KL(softmax(t/T) || softmax(s/T)) on [B,1+n] */
+#define SIMX_LOSS_NLL_LOCAL 16   /* a-6  hard loss of CrossBERTKDLoss: NLL of column 0 on [B,1+n] */
+
+typedef struct simx_loss_cfg {
+  int32_t terms;        /* OR of SIMX_LOSS_* */
+  int32_t GQ, GC, H;    /* global query / passage counts, embedding width */
+  int32_t q_begin, q_count; /* rows [q_begin, q_begin+q_count) of Q are this rank's queries (get dQ) */
+  int32_t c_begin, c_count; /* rows of C that are this rank's passages (get dC) */
+  int32_t group;        /* 1+n passages per local query: local passage block of query i = c_begin + i*group */
+  float w_nll_global, w_kl_local, w_ce_local, w_kd_local, w_nll_local; /* term weights */
+  float temperature;    /* T of the teacher softmax (KL/CE: softmax(t/T); KD: both sides /T, times T^2) */
+  float eps;            /* 1e-7 inside the log of KL/CE (co_training_marco_train.py:213) */
+  float score_scale;    /* multiplies student local scores (1 or 1/sqrt(H) with --scale_simmila) */
+  float grad_scale;     /* multiplies every gradient and nothing else (loss / gradient_accumulation_steps) */
+} simx_loss_cfg;
+
+/*   Q [GQ,H], C [GC,H] fp32 gathered embeddings; pos_idx [GQ] int32 positive column of each global query
+ *   (NLL_GLOBAL); teacher [q_count, group] fp32 teacher logits (KL/CE/KD terms), or NULL.
+ *   out_losses[8] fp32: {total, nll_global, kl_local, ce_local, kd_local, nll_local, n_correct_global, unused}
+ *   dQ [q_count,H], dC [c_count,H] fp32 gradients of `total * grad_scale` w.r.t. the local embeddings.
+ *   workspace: simx_score_loss_workspace_bytes(cfg). */
+size_t simx_score_loss_workspace_bytes(const simx_loss_cfg* cfg);
+int simx_score_loss(const simx_loss_cfg* cfg, const float* Q, const float* C, const int32_t* pos_idx,
+                    const float* teacher, float* out_losses, float* dQ, float* dC, void* workspace, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Operator-level entry points (used by the unit tests and by bench.py's kernel timing; the encoder calls the
+ * same kernels internally).
+ * ---------------------------------------------------------------------------------------------- */
+#define SIMX_EPI_PLAIN 0     /* out = acc */
+#define SIMX_EPI_BIAS 1      /* out = acc + bias[n]                                   (QKV projection) */
+#define SIMX_EPI_BIAS_GELU 2 /* out = acc + bias[n]; out2 = gelu_erf(out)             (BertIntermediate) */
+#define SIMX_EPI_BIAS_ADD 3  /* out = acc + bias[n] + aux[m,n]                        (BertSelfOutput/BertOutput pre-LN) */
+#define SIMX_EPI_DGELU 4     /* out = acc * gelu_erf'(aux[m,n])                       (dgrad through GELU) */
+#define SIMX_EPI_ADD 5       /* out = acc + aux[m,n]                                  (dgrad + residual grad) */
+#define SIMX_EPI_ATOMIC_F32 6 /* outf[m,n] += acc   (fp32 atomics; split-K wgrad)     */
+
+/* D[M,N] = sum_k A[m,k] * B[n,k]   on tcgen05 tensor cores (bf16 operands, fp32 accumulate in TMEM).
+ *   a_mn_major == 0: A is [M,K] row-major (lda >= K);  == 1: A is stored [K,M] row-major (lda >= M).  Same for B/N.
+ *   planes: operands, aux and bf16 outputs all carry `planes` planes; with 3 planes the 6 significant plane
+ *   pairs are accumulated.  ksplit > 1 only with SIMX_EPI_ATOMIC_F32.
+ *   out/out2/aux: bf16 [M,N] (ld*), outf: fp32 [M,N] (ATOMIC), bias: fp32 [N]. */
+int simx_gemm(int M, int N, int K, const void* A, int64_t lda, int64_t a_plane_stride, int a_mn_major,
+              const void* B, int64_t ldb, int64_t b_plane_stride, int b_mn_major, int planes, int epilogue,
+              const float* bias, const void* aux, int64_t ldaux, int64_t aux_plane_stride, void* out, void* out2,
+              int64_t ldo, int64_t out_plane_stride, float* outf, int64_t ldof, int ksplit, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SIMX_B200_H_ */

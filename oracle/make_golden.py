@@ -1,0 +1,280 @@
+"""ORACLE tooling — generates tests/golden/*.npz by running THE REFERENCE'S OWN CODE (imported unmodified from
+/root/reference, CPU fp32) on seeded synthetic weights and inputs.  Run in the build container only
+(`python oracle/make_golden.py`); the fixtures are committed because /root/reference does not exist on the GPU box.
+
+What is executed from the reference:
+  * SimANS/model/models.py        HFBertEncoder, BiBertEncoder, Reranker, BiEncoderNllLoss      (imported)
+  * PROD/ProD_KD/model/models.py  CrossBERTKDLoss                                                (imported)
+  * LEAD/models.py                HFBertEncoder / HFDistilBertEncoder over the vendored modeling files (imported via the
+                                  10-line compatibility shim of SURVEY §8c)
+  * the SimANS retriever-step loss is inline in train() (co_training_marco_train.py:199-214) and cannot be imported:
+    those lines are re-typed below verbatim in `simans_kl_loss`.
+Weights come from oracle.bert_numpy.synth_params (seeded numpy), loaded through load_state_dict, so the fixture
+does not depend on HF's init order.
+"""
+from __future__ import annotations
+
+import os
+import sys
+import types
+from pathlib import Path
+
+import numpy as np
+import torch
+import torch.nn.functional as F
+
+ROOT = Path(__file__).resolve().parents[1]
+sys.path.insert(0, str(ROOT))
+REF = Path("/root/reference")
+GOLD = ROOT / "tests" / "golden"
+
+from oracle.bert_numpy import bert_config, param_names, synth_params, synth_tokens  # noqa: E402
+
+
+def import_from(project_dir: Path, module: str):
+    """import `module` with `project_dir` first on sys.path (the reference's scripts do the same: co_training_marco_train.py:3-11)"""
+    for m in list(sys.modules):
+        if m == "model" or m.startswith("model.") or m in ("models", "modeling_bert", "modeling_distilbert"):
+            del sys.modules[m]
+    sys.path.insert(0, str(project_dir))
+    try:
+        return __import__(module, fromlist=["*"])
+    finally:
+        sys.path.pop(0)
+
+
+def hf_bert_config(cfg):
+    from transformers import BertConfig
+
+    return BertConfig(vocab_size=cfg["vocab"], hidden_size=cfg["hidden"], num_hidden_layers=cfg["num_layers"],
+                      num_attention_heads=cfg["heads"], intermediate_size=cfg["intermediate"],
+                      max_position_embeddings=cfg["max_pos"], type_vocab_size=cfg["type_vocab"],
+                      hidden_dropout_prob=0.0, attention_probs_dropout_prob=0.0, layer_norm_eps=cfg["ln_eps"])
+
+
+def load_params(module, params, prefix=""):
+    sd = {prefix + k: torch.from_numpy(v.copy()) for k, v in params.items()}
+    missing, unexpected = module.load_state_dict(sd, strict=False)
+    assert not unexpected, unexpected
+    assert all("position_ids" in m or "token_type_ids" in m for m in missing), missing
+
+
+def simans_kl_loss(local_q_vector, local_ctx_vectors, relevance_logits, temperature_distill, eps=1e-7):
+    # --- verbatim from /root/reference/SimANS/co_training/co_training_marco_train.py:199-214 (scale_simmila off) ---
+    student_local_ctx_vectors = local_ctx_vectors.reshape(local_q_vector.size(0),
+                                                          local_ctx_vectors.size(0) // local_q_vector.size(0), -1)
+    student_simila = torch.einsum("bh,bdh->bd", local_q_vector, student_local_ctx_vectors)
+    student_dist_p = F.softmax(student_simila, dim=1)
+    teacher_logits = relevance_logits / temperature_distill
+    probs = F.softmax(teacher_logits, dim=1)
+    teacher_dist_p = probs
+    loss_fct = torch.nn.KLDivLoss(reduction='batchmean')
+    distill_loss = loss_fct((student_dist_p + eps).log(), teacher_dist_p)
+    return distill_loss
+
+
+def grads_digest(named_grads):
+    """compact per-tensor fingerprint: [l2 norm, sum, abs-max] + first 16 elements"""
+    out = {}
+    for n, g in named_grads.items():
+        g = g.detach().double().reshape(-1)
+        out["gstat/" + n] = np.array([g.norm().item(), g.sum().item(), g.abs().max().item()])
+        out["ghead/" + n] = g[:16].numpy().copy()
+    return out
+
+
+# -----------------------------------------------------------------------------------------------------
+def golden_encoder_tiny(simans):
+    """tiny BERT through the reference HFBertEncoder: per-layer CLS, last hidden, ALL gradients under a random cotangent"""
+    cfg = bert_config(num_layers=2, hidden=128, heads=2, intermediate=256, vocab=512, max_pos=64)
+    params = synth_params(cfg, seed=7)
+    ids, mask = synth_tokens(3, 24, cfg["vocab"], seed=11, ragged=True)
+    enc = simans.HFBertEncoder(hf_bert_config(cfg))
+    load_params(enc, params)
+    enc.eval()
+    out = enc.forward(input_ids=torch.from_numpy(ids), attention_mask=torch.from_numpy(mask),
+                      output_hidden_states=True) if False else None
+    # the wrapper drops hidden states; call it for (sequence_output, pooled_output) and BertModel.forward for layers
+    seq, pooled, _ = enc(input_ids=torch.from_numpy(ids), attention_mask=torch.from_numpy(mask))
+    full = super(simans.HFBertEncoder, enc).forward(input_ids=torch.from_numpy(ids),
+                                                    attention_mask=torch.from_numpy(mask), output_hidden_states=True)
+    cls = torch.stack([h[:, 0, :] for h in full.hidden_states], dim=1)  # [B, L+1, H]
+    rng = np.random.RandomState(5)
+    d_cls = rng.standard_normal(cls.shape).astype(np.float32)
+    d_seq = rng.standard_normal(seq.shape).astype(np.float32)
+    (cls * torch.from_numpy(d_cls)).sum().add((seq * torch.from_numpy(d_seq)).sum()).backward()
+    res = dict(ids=ids, mask=mask, cls=cls.detach().numpy(), seq=seq.detach().numpy(), pooled=pooled.detach().numpy(),
+               d_cls=d_cls, d_seq=d_seq, cfg=np.array([2, 128, 2, 256, 512, 64, 2]), seed=np.array([7]))
+    for n, p in enc.named_parameters():
+        res["grad/" + n] = p.grad.numpy().copy()
+    np.savez_compressed(GOLD / "encoder_tiny_bert.npz", **res)
+    print("encoder_tiny_bert", {k: v.shape for k, v in res.items() if not k.startswith("grad/")})
+
+
+def golden_biencoder_cfg1(simans):
+    """BASELINE.json configs[0]: BiBertEncoder bert-base, B=2, q 32 / p 128, 1 pos + 1 hard-neg, SimANS KL loss, fp32 CPU"""
+    cfg = bert_config()
+    pq = synth_params(cfg, seed=0, perturb=False)
+    pc = synth_params(cfg, seed=1, perturb=False)
+    q_ids, q_mask = synth_tokens(2, 32, cfg["vocab"], seed=1234, ragged=True)
+    p_ids, p_mask = synth_tokens(4, 128, cfg["vocab"], seed=1235, ragged=True, min_len=16)
+    teacher = (3.0 * np.random.RandomState(99).standard_normal((2, 2))).astype(np.float32)
+    model = simans.BiBertEncoder.__new__(simans.BiBertEncoder)
+    torch.nn.Module.__init__(model)
+    model.question_model = simans.HFBertEncoder(hf_bert_config(cfg))
+    model.ctx_model = simans.HFBertEncoder(hf_bert_config(cfg))
+    load_params(model.question_model, pq)
+    load_params(model.ctx_model, pc)
+    model.eval()
+    q, a = model(torch.from_numpy(q_ids), torch.from_numpy(q_mask), torch.from_numpy(p_ids), torch.from_numpy(p_mask))
+    loss = simans_kl_loss(q, a, torch.from_numpy(teacher), temperature_distill=1.0)
+    loss.backward()
+    res = dict(q_ids=q_ids, q_mask=q_mask, p_ids=p_ids, p_mask=p_mask, teacher=teacher, q_embs=q.detach().numpy(),
+               a_embs=a.detach().numpy(), loss=np.array([loss.item()]), seeds=np.array([0, 1]))
+    res.update(grads_digest({n: p.grad for n, p in model.named_parameters()}))
+    # a few complete small tensors
+    for n, p in model.named_parameters():
+        if n.endswith("encoder.layer.0.attention.self.query.bias") or n.endswith("encoder.layer.11.output.LayerNorm.weight") \
+                or n.endswith("embeddings.LayerNorm.bias") or n.endswith("encoder.layer.5.intermediate.dense.bias"):
+            res["grad/" + n] = p.grad.numpy().copy()
+    np.savez_compressed(GOLD / "biencoder_cfg1.npz", **res)
+    print("biencoder_cfg1 loss", loss.item(), "q", q.shape, "a", a.shape)
+
+
+def golden_reranker_tiny(simans):
+    cfg = bert_config(num_layers=2, hidden=128, heads=2, intermediate=256, vocab=512, max_pos=64)
+    params = synth_params(cfg, seed=21)
+    ids, mask = synth_tokens(6, 40, cfg["vocab"], seed=22, ragged=True, min_len=8)
+    rr = simans.Reranker(simans.HFBertEncoder(hf_bert_config(cfg)), cfg["hidden"])
+    load_params(rr.encoder, params)
+    rng = np.random.RandomState(23)
+    w = (0.05 * rng.standard_normal((1, cfg["hidden"]))).astype(np.float32)
+    b = np.array([0.1], np.float32)
+    rr.qa_classifier.weight.data = torch.from_numpy(w.copy())
+    rr.qa_classifier.bias.data = torch.from_numpy(b.copy())
+    rr.eval()
+    logits = rr(torch.from_numpy(ids).view(2, 3, 40), torch.from_numpy(mask).view(2, 3, 40))
+    # co_training_marco_train.py:229-242 (teacher step): CE against column 0
+    loss = torch.nn.CrossEntropyLoss()(logits, torch.zeros(2, dtype=torch.long))
+    loss.backward()
+    res = dict(ids=ids.reshape(2, 3, 40), mask=mask.reshape(2, 3, 40), qa_w=w, qa_b=b, logits=logits.detach().numpy(),
+               loss=np.array([loss.item()]), seed=np.array([21]))
+    for n, p in rr.named_parameters():
+        res["grad/" + n] = p.grad.numpy().copy()
+    np.savez_compressed(GOLD / "reranker_tiny.npz", **res)
+    print("reranker_tiny", logits.detach().numpy())
+
+
+def golden_losses(simans, prod):
+    rng = np.random.RandomState(3)
+    GQ, group, H = 6, 4, 32
+    Q = rng.standard_normal((GQ, H)).astype(np.float32)
+    Cm = rng.standard_normal((GQ * group, H)).astype(np.float32)
+    teacher = (3 * rng.standard_normal((GQ, group))).astype(np.float32)
+    res = dict(Q=Q, C=Cm, teacher=teacher, group=np.array([group]))
+
+    def fresh():
+        return torch.from_numpy(Q.copy()).requires_grad_(True), torch.from_numpy(Cm.copy()).requires_grad_(True)
+
+    # (1) BiEncoderNllLoss.calc on the full matrix, positives at i*group  (SimANS/model/models.py:468-505)
+    q, c = fresh()
+    pos = [i * group for i in range(GQ)]
+    loss, correct = simans.BiEncoderNllLoss().calc(q, c, pos)
+    loss.backward()
+    res.update(nll_loss=np.array([loss.item()]), nll_correct=np.array([int(correct)]), nll_dQ=q.grad.numpy().copy(),
+               nll_dC=c.grad.numpy().copy(), nll_pos=np.array(pos))
+    # (2) SimANS KL (co_training_marco_train.py:199-214), T = 1 and T = 2
+    for T in (1.0, 2.0):
+        q, c = fresh()
+        loss = simans_kl_loss(q, c, torch.from_numpy(teacher), T)
+        loss.backward()
+        tag = f"kl_T{int(T)}"
+        res.update({tag + "_loss": np.array([loss.item()]), tag + "_dQ": q.grad.numpy().copy(),
+                    tag + "_dC": c.grad.numpy().copy()})
+    # (3) PROD CrossBERTKDLoss.calc, KD_softmax, CE 0.1 / KD 0.9 / T 4   (PROD/ProD_KD/model/models.py:669-781)
+    args = types.SimpleNamespace(KD_type="KD_softmax", TEMPERATURE=4.0, CE_WEIGHT=0.1, KD_WEIGHT=0.9, LwF_WEIGHT=1.0,
+                                 DKD_alpha=None, DKD_beta=None)
+    q, c = fresh()
+    loss, correct = prod.CrossBERTKDLoss().calc(args, q, c, torch.from_numpy(teacher))
+    loss.backward()
+    res.update(prod_loss=np.array([loss.item()]), prod_correct=np.array([int(correct)]), prod_dQ=q.grad.numpy().copy(),
+               prod_dC=c.grad.numpy().copy())
+    # (4) PROD prob_loss == MASTER/wiki CE-to-teacher form
+    args.KD_type = "prob_loss"
+    args.TEMPERATURE = 1.0
+    q, c = fresh()
+    loss, _ = prod.CrossBERTKDLoss().calc(args, q, c, torch.from_numpy(teacher))
+    loss.backward()
+    res.update(prob_loss=np.array([loss.item()]), prob_dQ=q.grad.numpy().copy(), prob_dC=c.grad.numpy().copy())
+    np.savez_compressed(GOLD / "losses.npz", **res)
+    print("losses", {k: float(v[0]) for k, v in res.items() if k.endswith("loss")})
+
+
+def lead_shim():
+    """make LEAD's vendored HF-4.x modeling files importable under transformers 5"""
+    import transformers
+    import transformers.pytorch_utils as pu
+
+    if not hasattr(pu, "find_pruneable_heads_and_indices"):
+        pu.find_pruneable_heads_and_indices = lambda *a, **k: (set(), None)
+    if "transformers.deepspeed" not in sys.modules:
+        m = types.ModuleType("transformers.deepspeed")
+        m.is_deepspeed_zero3_enabled = lambda: False
+        sys.modules["transformers.deepspeed"] = m
+    return transformers
+
+
+def golden_lead_distilbert():
+    """tiny DistilBERT through LEAD's vendored modeling_distilbert (the 6-layer student arch of config 5)"""
+    lead_shim()
+    try:
+        md = import_from(REF / "LEAD", "modeling_distilbert")
+    except Exception as e:  # pragma: no cover
+        print("LEAD modeling_distilbert not importable:", repr(e))
+        return
+    from transformers import DistilBertConfig
+
+    cfg = bert_config(num_layers=2, hidden=128, heads=2, intermediate=256, vocab=512, max_pos=64, arch="distilbert")
+    params = synth_params(cfg, seed=31)
+    ids, mask = synth_tokens(3, 24, cfg["vocab"], seed=32, ragged=True)
+    hcfg = DistilBertConfig(vocab_size=512, max_position_embeddings=64, n_layers=2, n_heads=2, dim=128, hidden_dim=256,
+                            dropout=0.0, attention_dropout=0.0, output_hidden_states=True)
+    if not hasattr(md.DistilBertPreTrainedModel, "get_head_mask"):
+        md.DistilBertPreTrainedModel.get_head_mask = lambda self, hm, n, *a, **k: [None] * n
+    model = md.DistilBertModel(hcfg)
+    load_params(model, params)
+    model.eval()
+    out = model(input_ids=torch.from_numpy(ids), attention_mask=torch.from_numpy(mask), output_hidden_states=True,
+                return_dict=True)
+    hs = out.hidden_states if hasattr(out, "hidden_states") and out.hidden_states is not None else out[1]
+    hs = list(hs)
+    seq = out.last_hidden_state if hasattr(out, "last_hidden_state") else out[0]
+    res = dict(ids=ids, mask=mask, seq=seq.detach().numpy(), n_hidden=np.array([len(hs)]), seed=np.array([31]),
+               hidden_cls=np.stack([h[:, 0, :].detach().numpy() for h in hs], axis=1))
+    rng = np.random.RandomState(33)
+    d_seq = rng.standard_normal(seq.shape).astype(np.float32)
+    (seq * torch.from_numpy(d_seq)).sum().backward()
+    res["d_seq"] = d_seq
+    for n, p in model.named_parameters():
+        res["grad/" + n] = p.grad.numpy().copy()
+    np.savez_compressed(GOLD / "encoder_tiny_distilbert.npz", **res)
+    print("encoder_tiny_distilbert hidden entries:", len(hs))
+
+
+def main():
+    torch.manual_seed(0)
+    torch.set_num_threads(os.cpu_count() or 1)
+    GOLD.mkdir(parents=True, exist_ok=True)
+    simans = import_from(REF / "SimANS", "model.models")
+    golden_encoder_tiny(simans)
+    golden_reranker_tiny(simans)
+    prod = import_from(REF / "PROD" / "ProD_KD", "model.models")
+    simans = import_from(REF / "SimANS", "model.models")
+    golden_losses(simans, prod)
+    golden_lead_distilbert()
+    simans = import_from(REF / "SimANS", "model.models")
+    golden_biencoder_cfg1(simans)
+
+
+if __name__ == "__main__":
+    main()

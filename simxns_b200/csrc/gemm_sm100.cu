@@ -1,0 +1,421 @@
+// Persistent warp-specialised tcgen05 GEMM for sm_100a:   D[M,N] = sum_k A[m,k] * B[n,k]
+//
+//   warp 0      : TMA producer   (cp.async.bulk.tensor, 128B-swizzled tiles, 4-stage mbarrier ring)
+//   warp 1      : MMA issuer     (one thread, tcgen05.mma kind::f16 128xBNx16, fp32 accumulator in TMEM)
+//   warp 2      : TMEM allocator
+//   warps 4..7  : epilogue       (tcgen05.ld -> registers -> bias / GELU / residual / gelu' -> global)
+//   TMEM holds two accumulators, so the epilogue of tile i overlaps the MMAs of tile i+1.
+//
+// Both operands may be K-major (activations x nn.Linear weights, the "TN" case of every forward and dgrad GEMM:
+// LEAD/modeling_bert.py:285-310,384-388,449-466) or MN-major (the wgrad GEMMs dW = dY^T X, whose contraction runs
+// over tokens; split-K with fp32 atomics into the gradient buffer).  With 3 planes per operand (fp32-class mode)
+// the producer streams the 6 significant plane pairs through the same accumulator.
+#include "common.cuh"
+#include "ptx.cuh"
+
+namespace simx {
+
+constexpr int GEMM_BM = 128;
+constexpr int GEMM_BK = 64;
+constexpr int GEMM_THREADS = 256;
+
+struct GemmParams {
+  int M, N, K;
+  int m_tiles, n_tiles, ksplit, kb_per_split, kb_total;
+  int npass;
+  int pa[6], pb[6];
+  bf16* out;
+  bf16* out2;
+  long out_ps;
+  long ldo;
+  const bf16* aux;
+  long aux_ps;
+  long ldaux;
+  const float* bias;
+  float* outf;
+  long ldof;
+};
+
+template <int BN>
+struct GemmSmem {
+  static constexpr int STAGES = (BN == 256) ? 4 : 6;
+  static constexpr uint32_t A_BYTES = GEMM_BM * GEMM_BK * 2;
+  static constexpr uint32_t B_BYTES = BN * GEMM_BK * 2;
+  static constexpr uint32_t STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr uint32_t BAR_OFF = STAGES * STAGE_BYTES;
+  static constexpr uint32_t TOTAL = BAR_OFF + 256 + 1024;  // barriers + alignment slack
+};
+
+template <int EPI, int NP>
+__device__ __forceinline__ void epilogue_chunk(const GemmParams& p, int row, int col0, const uint32_t (&acc)[32]) {
+  // this thread owns D[row, col0 .. col0+32)
+  if (row >= p.M) return;
+#pragma unroll
+  for (int g = 0; g < 4; ++g) {
+    const int col = col0 + g * 8;
+    if (col >= p.N) break;  // N % 8 == 0 is enforced on the host
+    float v[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(acc[g * 8 + i]);
+    if constexpr (EPI == SIMX_EPI_ATOMIC_F32) {
+      float* o = p.outf + (long)row * p.ldof + col;
+      asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(o), "f"(v[0]), "f"(v[1]), "f"(v[2]), "f"(v[3])
+                   : "memory");
+      asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(o + 4), "f"(v[4]), "f"(v[5]), "f"(v[6]),
+                   "f"(v[7])
+                   : "memory");
+    } else {
+      if constexpr (EPI == SIMX_EPI_BIAS || EPI == SIMX_EPI_BIAS_GELU || EPI == SIMX_EPI_BIAS_ADD) {
+        const float4 b0 = __ldg(reinterpret_cast<const float4*>(p.bias + col));
+        const float4 b1 = __ldg(reinterpret_cast<const float4*>(p.bias + col + 4));
+        v[0] += b0.x; v[1] += b0.y; v[2] += b0.z; v[3] += b0.w;
+        v[4] += b1.x; v[5] += b1.y; v[6] += b1.z; v[7] += b1.w;
+      }
+      if constexpr (EPI == SIMX_EPI_BIAS_ADD || EPI == SIMX_EPI_ADD || EPI == SIMX_EPI_DGELU) {
+        float a[8];
+        plane_load8<NP>(p.aux + (long)row * p.ldaux + col, p.aux_ps, a);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          if constexpr (EPI == SIMX_EPI_DGELU) v[i] *= gelu_erf_grad(a[i]);
+          else v[i] += a[i];
+        }
+      }
+      split_store8<NP>(p.out + (long)row * p.ldo + col, p.out_ps, v);
+      if constexpr (EPI == SIMX_EPI_BIAS_GELU) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) v[i] = gelu_erf(v[i]);
+        split_store8<NP>(p.out2 + (long)row * p.ldo + col, p.out_ps, v);
+      }
+    }
+  }
+}
+
+template <int BN, bool MN, int EPI, int NP>
+__global__ void __launch_bounds__(GEMM_THREADS, 1)
+gemm_kernel(const GemmParams p, const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB) {
+  using L = GemmSmem<BN>;
+  constexpr int STAGES = L::STAGES;
+  extern __shared__ uint8_t smem_raw[];
+  // 128B swizzle atoms need 1024-byte aligned tiles
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  uint8_t* sA = smem;
+  uint8_t* sB = smem + STAGES * L::A_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L::BAR_OFF);
+  uint64_t* full = bars;                    // [STAGES]  TMA -> MMA
+  uint64_t* empty = bars + STAGES;          // [STAGES]  MMA -> TMA
+  uint64_t* tfull = bars + 2 * STAGES;      // [2]       MMA -> epilogue
+  uint64_t* tempty = bars + 2 * STAGES + 2; // [2]       epilogue -> MMA
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&mapA);
+    tma_prefetch_desc(&mapB);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int i = 0; i < STAGES; ++i) {
+      mbar_init(&full[i], 1);
+      mbar_init(&empty[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tfull[i], 1);
+      mbar_init(&tempty[i], 4);
+    }
+    fence_mbar_init();
+  }
+  if (warp == 2) tmem_alloc<1>(tmem_slot, 2 * BN);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int total_tiles = p.m_tiles * p.n_tiles * p.ksplit;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      // ===================== TMA producer =====================
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        const int nt = tile % p.n_tiles;
+        const int mt = (tile / p.n_tiles) % p.m_tiles;
+        const int ks = tile / (p.n_tiles * p.m_tiles);
+        const int kb0 = ks * p.kb_per_split;
+        const int kb1 = min(p.kb_total, kb0 + p.kb_per_split);
+        const int m0 = mt * GEMM_BM, n0 = nt * BN;
+        for (int pass = 0; pass < p.npass; ++pass) {
+          const int pla = p.pa[pass], plb = p.pb[pass];
+          for (int kb = kb0; kb < kb1; ++kb) {
+            mbar_wait(&empty[stage], phase ^ 1);
+            mbar_arrive_expect_tx(&full[stage], L::STAGE_BYTES);
+            uint8_t* a = sA + stage * L::A_BYTES;
+            uint8_t* b = sB + stage * L::B_BYTES;
+            if constexpr (!MN) {
+              tma_load_3d(&mapA, &full[stage], a, kb * GEMM_BK, m0, pla);
+              tma_load_3d(&mapB, &full[stage], b, kb * GEMM_BK, n0, plb);
+            } else {
+              // MN-major: one [64 k-rows x 64 mn (128 B)] box per 64-wide slice of the MN extent
+#pragma unroll
+              for (int i = 0; i < GEMM_BM / 64; ++i)
+                tma_load_3d(&mapA, &full[stage], a + i * (GEMM_BK * 128), m0 + i * 64, kb * GEMM_BK, pla);
+#pragma unroll
+              for (int i = 0; i < BN / 64; ++i)
+                tma_load_3d(&mapB, &full[stage], b + i * (GEMM_BK * 128), n0 + i * 64, kb * GEMM_BK, plb);
+            }
+            if (++stage == STAGES) { stage = 0; phase ^= 1; }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      // ===================== MMA issuer =====================
+      constexpr uint32_t idesc = make_idesc_bf16(GEMM_BM, BN, MN, MN);
+      int stage = 0;
+      uint32_t phase = 0;
+      int it = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+        const int ks = tile / (p.n_tiles * p.m_tiles);
+        const int kb0 = ks * p.kb_per_split;
+        const int kb1 = min(p.kb_total, kb0 + p.kb_per_split);
+        const int nk = (kb1 - kb0) * p.npass;
+        const int acc = it & 1;
+        const uint32_t acc_phase = (it >> 1) & 1;
+        mbar_wait(&tempty[acc], acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * BN;
+        for (int i = 0; i < nk; ++i) {
+          mbar_wait(&full[stage], phase);
+          tc_fence_after();
+          const uint32_t a_addr = smem_u32(sA + stage * L::A_BYTES);
+          const uint32_t b_addr = smem_u32(sB + stage * L::B_BYTES);
+#pragma unroll
+          for (int k = 0; k < GEMM_BK / 16; ++k) {
+            uint64_t da, db;
+            if constexpr (!MN) {
+              // K-major, 128B swizzle: 8-row groups 1024 B apart; 16 k-elements = 32 B inside the swizzle atom
+              da = make_smem_desc_sw128(a_addr + k * 32, 0, 1024);
+              db = make_smem_desc_sw128(b_addr + k * 32, 0, 1024);
+            } else {
+              // MN-major, 128B swizzle: atoms of [8 k-rows x 64 mn]; next 8 k-rows +1024 B (SBO), next 64 mn
+              // +BK*128 B (LBO); 16 k-rows per MMA = 2048 B
+              da = make_smem_desc_sw128(a_addr + k * 2048, GEMM_BK * 128, 1024);
+              db = make_smem_desc_sw128(b_addr + k * 2048, GEMM_BK * 128, 1024);
+            }
+            umma_bf16<1>(d_tmem, da, db, idesc, (i | k) != 0);
+          }
+          umma_commit<1>(&empty[stage]);  // frees the smem slot when these MMAs retire
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+        umma_commit<1>(&tfull[acc]);  // accumulator complete -> epilogue
+      }
+    }
+  } else if (warp >= 4) {
+    // ===================== epilogue =====================
+    const int ew = warp - 4;  // == warp % 4: the TMEM lane quarter this warp may read
+    int it = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+      const int nt = tile % p.n_tiles;
+      const int mt = (tile / p.n_tiles) % p.m_tiles;
+      const int acc = it & 1;
+      const uint32_t acc_phase = (it >> 1) & 1;
+      const int row = mt * GEMM_BM + ew * 32 + lane;
+      mbar_wait(&tfull[acc], acc_phase);
+      tc_fence_after();
+      const uint32_t t_addr = tmem_base + acc * BN + (static_cast<uint32_t>(ew * 32) << 16);
+#pragma unroll 1
+      for (int c = 0; c < BN; c += 32) {
+        uint32_t v[32];
+        tmem_ld_32x32(t_addr + c, v);
+        tmem_ld_wait();
+        if (c + 32 == BN) {
+          // accumulator fully read: hand the TMEM buffer back before doing the global stores
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&tempty[acc]);
+        }
+        epilogue_chunk<EPI, NP>(p, row, nt * BN + c, v);
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc<1>(tmem_base, 2 * BN);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (fn) return fn;
+  void* ptr = nullptr;
+  cudaDriverEntryPointQueryResult qres;
+  if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) != cudaSuccess ||
+      qres != cudaDriverEntryPointSuccess)
+    return nullptr;
+  fn = reinterpret_cast<EncodeTiledFn>(ptr);
+  return fn;
+}
+
+// bf16 tensor [planes][outer][inner] (inner contiguous), box = [1][box_outer][64]
+int make_tmap_bf16(CUtensorMap* map, const void* ptr, uint64_t inner, uint64_t outer, uint64_t planes, uint64_t ld,
+                   uint64_t plane_stride, uint32_t box_outer) {
+  EncodeTiledFn fn = get_encode_fn();
+  SIMX_CHECK(fn != nullptr, SIMX_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
+  SIMX_CHECK((reinterpret_cast<uintptr_t>(ptr) & 15) == 0, SIMX_ERR_INVALID, "TMA operand not 16-byte aligned");
+  SIMX_CHECK((ld * 2) % 16 == 0, SIMX_ERR_INVALID, "TMA operand row stride (%llu elements) not a multiple of 8",
+             (unsigned long long)ld);
+  if (planes < 1) planes = 1;
+  if (planes == 1) plane_stride = ld * outer;  // any legal value
+  SIMX_CHECK((plane_stride * 2) % 16 == 0, SIMX_ERR_INVALID, "TMA plane stride not a multiple of 8 elements");
+  cuuint64_t gdim[3] = {inner, outer, planes};
+  cuuint64_t gstride[2] = {ld * 2, plane_stride * 2};
+  cuuint32_t box[3] = {64, box_outer, 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(ptr), gdim, gstride, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  SIMX_CHECK(r == CUDA_SUCCESS, SIMX_ERR_CUDA,
+             "cuTensorMapEncodeTiled failed (%d): inner=%llu outer=%llu planes=%llu ld=%llu box_outer=%u", (int)r,
+             (unsigned long long)inner, (unsigned long long)outer, (unsigned long long)planes, (unsigned long long)ld,
+             box_outer);
+  return SIMX_OK;
+}
+
+template <int BN, bool MN, int EPI, int NP>
+static int launch_gemm(const GemmParams& p, const CUtensorMap& ma, const CUtensorMap& mb, cudaStream_t stream) {
+  auto kern = gemm_kernel<BN, MN, EPI, NP>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    SIMX_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmSmem<BN>::TOTAL));
+    attr_set = true;
+  }
+  const int total = p.m_tiles * p.n_tiles * p.ksplit;
+  const int grid = min(total, num_sms());
+  kern<<<grid, GEMM_THREADS, GemmSmem<BN>::TOTAL, stream>>>(p, ma, mb);
+  SIMX_LAUNCH_CHECK();
+  return SIMX_OK;
+}
+
+template <int BN, bool MN, int NP>
+static int dispatch_epi(int epi, const GemmParams& p, const CUtensorMap& ma, const CUtensorMap& mb,
+                        cudaStream_t stream) {
+  if constexpr (MN) {
+    SIMX_CHECK(epi == SIMX_EPI_ATOMIC_F32 || epi == SIMX_EPI_PLAIN, SIMX_ERR_INVALID,
+               "MN-major GEMM supports the PLAIN and ATOMIC_F32 epilogues only");
+    if (epi == SIMX_EPI_ATOMIC_F32) return launch_gemm<BN, MN, SIMX_EPI_ATOMIC_F32, NP>(p, ma, mb, stream);
+    return launch_gemm<BN, MN, SIMX_EPI_PLAIN, NP>(p, ma, mb, stream);
+  } else {
+    switch (epi) {
+      case SIMX_EPI_PLAIN: return launch_gemm<BN, MN, SIMX_EPI_PLAIN, NP>(p, ma, mb, stream);
+      case SIMX_EPI_BIAS: return launch_gemm<BN, MN, SIMX_EPI_BIAS, NP>(p, ma, mb, stream);
+      case SIMX_EPI_BIAS_GELU: return launch_gemm<BN, MN, SIMX_EPI_BIAS_GELU, NP>(p, ma, mb, stream);
+      case SIMX_EPI_BIAS_ADD: return launch_gemm<BN, MN, SIMX_EPI_BIAS_ADD, NP>(p, ma, mb, stream);
+      case SIMX_EPI_DGELU: return launch_gemm<BN, MN, SIMX_EPI_DGELU, NP>(p, ma, mb, stream);
+      case SIMX_EPI_ADD: return launch_gemm<BN, MN, SIMX_EPI_ADD, NP>(p, ma, mb, stream);
+      case SIMX_EPI_ATOMIC_F32: return launch_gemm<BN, MN, SIMX_EPI_ATOMIC_F32, NP>(p, ma, mb, stream);
+    }
+    SIMX_FAIL(SIMX_ERR_INVALID, "unknown GEMM epilogue %d", epi);
+  }
+}
+
+// Internal entry used by the encoder and by simx_gemm().
+int gemm(int M, int N, int K, const bf16* A, long lda, long a_ps, bool a_mn, const bf16* B, long ldb, long b_ps,
+         bool b_mn, int planes, int epi, const float* bias, const bf16* aux, long ldaux, long aux_ps, bf16* out,
+         bf16* out2, long ldo, long out_ps, float* outf, long ldof, int ksplit, cudaStream_t stream) {
+  SIMX_CHECK(M > 0 && N > 0 && K > 0, SIMX_ERR_INVALID, "gemm: empty problem %dx%dx%d", M, N, K);
+  SIMX_CHECK(N % 8 == 0, SIMX_ERR_INVALID, "gemm: N=%d must be a multiple of 8", N);
+  SIMX_CHECK(a_mn == b_mn, SIMX_ERR_INVALID, "gemm: mixed operand majors are not instantiated");
+  SIMX_CHECK(planes == 1 || planes == 3, SIMX_ERR_INVALID, "gemm: planes must be 1 or 3");
+  SIMX_CHECK(ksplit >= 1, SIMX_ERR_INVALID, "gemm: ksplit must be >= 1");
+  SIMX_CHECK(ksplit == 1 || epi == SIMX_EPI_ATOMIC_F32, SIMX_ERR_INVALID, "gemm: split-K needs the atomic epilogue");
+  if (epi == SIMX_EPI_ATOMIC_F32) {
+    SIMX_CHECK(outf != nullptr && ldof % 4 == 0 && (reinterpret_cast<uintptr_t>(outf) & 15) == 0, SIMX_ERR_INVALID,
+               "gemm: fp32 output must be 16-byte aligned with ld %% 4 == 0");
+  } else {
+    SIMX_CHECK(out != nullptr && ldo % 8 == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0, SIMX_ERR_INVALID,
+               "gemm: bf16 output must be 16-byte aligned with ld %% 8 == 0");
+  }
+  if (epi == SIMX_EPI_BIAS || epi == SIMX_EPI_BIAS_GELU || epi == SIMX_EPI_BIAS_ADD)
+    SIMX_CHECK(bias != nullptr && (reinterpret_cast<uintptr_t>(bias) & 15) == 0, SIMX_ERR_INVALID,
+               "gemm: bias missing or misaligned");
+  if (epi == SIMX_EPI_BIAS_ADD || epi == SIMX_EPI_DGELU || epi == SIMX_EPI_ADD)
+    SIMX_CHECK(aux != nullptr && ldaux % 8 == 0 && (reinterpret_cast<uintptr_t>(aux) & 15) == 0, SIMX_ERR_INVALID,
+               "gemm: aux missing or misaligned");
+  if (epi == SIMX_EPI_BIAS_GELU) SIMX_CHECK(out2 != nullptr, SIMX_ERR_INVALID, "gemm: out2 missing");
+
+  // tile width: 256 when N fills it, else the smaller instantiations (less padding waste)
+  int BN = 256;
+  if (N <= 64) BN = 64;
+  else if (N <= 128) BN = 128;
+
+  GemmParams p;
+  p.M = M; p.N = N; p.K = K;
+  p.m_tiles = (M + GEMM_BM - 1) / GEMM_BM;
+  p.n_tiles = (N + BN - 1) / BN;
+  p.kb_total = (K + GEMM_BK - 1) / GEMM_BK;
+  if (ksplit > p.kb_total) ksplit = p.kb_total;
+  p.kb_per_split = (p.kb_total + ksplit - 1) / ksplit;
+  p.ksplit = (p.kb_total + p.kb_per_split - 1) / p.kb_per_split;
+  if (planes == 1) {
+    p.npass = 1; p.pa[0] = 0; p.pb[0] = 0;
+  } else {
+    // plane pairs ordered small -> large so the big products are added last
+    const int ia[6] = {2, 0, 1, 1, 0, 0}, ib[6] = {0, 2, 1, 0, 1, 0};
+    p.npass = 6;
+    for (int i = 0; i < 6; ++i) { p.pa[i] = ia[i]; p.pb[i] = ib[i]; }
+  }
+  p.out = out; p.out2 = out2; p.out_ps = out_ps; p.ldo = ldo;
+  p.aux = aux; p.aux_ps = aux_ps; p.ldaux = ldaux;
+  p.bias = bias; p.outf = outf; p.ldof = ldof;
+
+  CUtensorMap ma, mb;
+  if (!a_mn) {
+    SIMX_TRY(make_tmap_bf16(&ma, A, K, M, planes, lda, a_ps, GEMM_BM));
+    SIMX_TRY(make_tmap_bf16(&mb, B, K, N, planes, ldb, b_ps, BN));
+  } else {
+    SIMX_TRY(make_tmap_bf16(&ma, A, M, K, planes, lda, a_ps, GEMM_BK));
+    SIMX_TRY(make_tmap_bf16(&mb, B, N, K, planes, ldb, b_ps, GEMM_BK));
+  }
+
+#define SIMX_GEMM_DISPATCH(BN_)                                                                  \
+  if (BN == BN_) {                                                                               \
+    if (a_mn) {                                                                                  \
+      if (planes == 1) return dispatch_epi<BN_, true, 1>(epi, p, ma, mb, stream);                \
+      return dispatch_epi<BN_, true, 3>(epi, p, ma, mb, stream);                                 \
+    } else {                                                                                     \
+      if (planes == 1) return dispatch_epi<BN_, false, 1>(epi, p, ma, mb, stream);               \
+      return dispatch_epi<BN_, false, 3>(epi, p, ma, mb, stream);                                \
+    }                                                                                            \
+  }
+  SIMX_GEMM_DISPATCH(256)
+  SIMX_GEMM_DISPATCH(128)
+  SIMX_GEMM_DISPATCH(64)
+#undef SIMX_GEMM_DISPATCH
+  SIMX_FAIL(SIMX_ERR_INVALID, "gemm: no tile configuration");
+}
+
+}  // namespace simx
+
+extern "C" int simx_gemm(int M, int N, int K, const void* A, int64_t lda, int64_t a_plane_stride, int a_mn_major,
+                         const void* B, int64_t ldb, int64_t b_plane_stride, int b_mn_major, int planes, int epilogue,
+                         const float* bias, const void* aux, int64_t ldaux, int64_t aux_plane_stride, void* out,
+                         void* out2, int64_t ldo, int64_t out_plane_stride, float* outf, int64_t ldof, int ksplit,
+                         void* stream) {
+  using namespace simx;
+  return gemm(M, N, K, static_cast<const bf16*>(A), lda, a_plane_stride, a_mn_major != 0, static_cast<const bf16*>(B),
+              ldb, b_plane_stride, b_mn_major != 0, planes, epilogue, bias, static_cast<const bf16*>(aux), ldaux,
+              aux_plane_stride, static_cast<bf16*>(out), static_cast<bf16*>(out2), ldo, out_plane_stride, outf, ldof,
+              ksplit, static_cast<cudaStream_t>(stream));
+}
