@@ -244,11 +244,12 @@ def golden_lead_distilbert():
     model = md.DistilBertModel(hcfg)
     load_params(model, params)
     model.eval()
-    out = model(input_ids=torch.from_numpy(ids), attention_mask=torch.from_numpy(mask), output_hidden_states=True,
-                return_dict=True)
-    hs = out.hidden_states if hasattr(out, "hidden_states") and out.hidden_states is not None else out[1]
+    # vendored forward returns (BaseModelOutput, all_hidden_states, all_hidden_states_all_head); the hidden-state
+    # tuple has one entry per layer and EXCLUDES the embedding output (LEAD/modeling_distilbert.py:344-376)
+    result, hs, _ = model(input_ids=torch.from_numpy(ids), attention_mask=torch.from_numpy(mask),
+                          output_hidden_states=True, return_dict=True)
     hs = list(hs)
-    seq = out.last_hidden_state if hasattr(out, "last_hidden_state") else out[0]
+    seq = result.last_hidden_state
     res = dict(ids=ids, mask=mask, seq=seq.detach().numpy(), n_hidden=np.array([len(hs)]), seed=np.array([31]),
                hidden_cls=np.stack([h[:, 0, :].detach().numpy() for h in hs], axis=1))
     rng = np.random.RandomState(33)

@@ -1,0 +1,447 @@
+// Encoder tower forward / backward: the launch sequence over the kernels of this directory, plus the buffer layouts
+// of the C ABI (include/simx_b200.h).  Replaces HFBertEncoder.forward / loss.backward() through one tower
+// (SimANS/model/models.py:77-82, co_training_marco_train.py:222; math: LEAD/modeling_bert.py:201-660,
+// LEAD/modeling_distilbert.py:93-376 — the same post-LN block in both architectures).
+//
+// per layer, forward (x = layer input, all activations [T, .] as 1 or 3 bf16 planes):
+//   qkv = x Wqkv^T + b            tcgen05 GEMM, BIAS epilogue            [T,3H]
+//   ctx = softmax(q k^T/8 + m) v  attention kernel, saves lse            [T,H]
+//   z1  = ctx Wo^T + b + x        GEMM, BIAS_ADD epilogue                [T,H]
+//   x1  = LN(z1)                  row kernel                             [T,H]
+//   h   = x1 W1^T + b ; a=gelu(h) GEMM, BIAS_GELU epilogue (two outputs) [T,I] x2
+//   z2  = a W2^T + b + x1         GEMM, BIAS_ADD epilogue                [T,H]
+//   out = LN(z2)                                                         [T,H]
+// backward mirrors it: LN-bwd (also yields the bias gradient of the GEMM before it), dgrad GEMMs against the
+// pre-transposed weights with the gelu' / residual-add fused into their epilogues, split-K MN-major wgrad GEMMs
+// accumulating with fp32 atomics straight into the flat gradient buffer.
+#include "common.cuh"
+
+namespace simx {
+
+// kernels from the other translation units
+int gemm(int M, int N, int K, const bf16* A, long lda, long a_ps, bool a_mn, const bf16* B, long ldb, long b_ps,
+         bool b_mn, int planes, int epi, const float* bias, const bf16* aux, long ldaux, long aux_ps, bf16* out,
+         bf16* out2, long ldo, long out_ps, float* outf, long ldof, int ksplit, cudaStream_t stream);
+int embed_ln(int np, const int64_t* ids, int T, int S, int H, int vocab, const float* word, const float* pos,
+             const float* type0, const float* gamma, const float* beta, float eps, bf16* z0, bf16* x, long ps,
+             cudaStream_t st);
+int ln_fwd(int np, const bf16* z, int T, int H, const float* gamma, const float* beta, float eps, bf16* x, long ps,
+           cudaStream_t st);
+int ln_bwd(int np, const bf16* dy, const bf16* z, int T, int H, const float* gamma, float eps, bf16* dz, long ps,
+           float* dgamma, float* dbeta, float* dbias, cudaStream_t st);
+int colsum(int np, const bf16* x, long rows, int N, long row_stride, long ps, float* out, cudaStream_t st);
+int cls_gather(int np, const bf16* x, int B, int S, int H, long ps, float* out, long out_stride_b, cudaStream_t st);
+int cls_scatter_add(int np, bf16* dx, int B, int S, int H, long ps, const float* d, long d_stride_b, cudaStream_t st);
+int f32_to_planes(int np, const float* src, long n, bf16* dst, long ps, cudaStream_t st);
+int planes_to_f32(int np, const bf16* src, long n, long ps, float* dst, cudaStream_t st);
+int embed_scatter(int np, const int64_t* ids, const bf16* dz0, int T, int H, int vocab, long ps, float* dword,
+                  cudaStream_t st);
+int convert_weight(int np, const float* w, int R, int C, bf16* dst, long ld_dst, long ps_dst, bf16* dst_t, long ld_t,
+                   long ps_t, cudaStream_t st);
+int attention_forward(int np, const bf16* qkv, long ps_qkv, bf16* ctx, long ps_ctx, const int64_t* mask, float* lse2,
+                      int B, int S, int H, int heads, cudaStream_t st);
+int attention_backward(int np, const bf16* qkv, long ps_qkv, const bf16* ctx, const bf16* dctx, long ps_ctx, bf16* dqkv,
+                       const int64_t* mask, const float* lse2, float* delta, int B, int S, int H, int heads,
+                       cudaStream_t st);
+
+static inline size_t al(size_t x) { return (x + 255) & ~size_t(255); }
+
+static int check_cfg(const simx_encoder_cfg* c) {
+  SIMX_CHECK(c != nullptr, SIMX_ERR_INVALID, "null encoder cfg");
+  SIMX_CHECK(c->arch == SIMX_ARCH_BERT || c->arch == SIMX_ARCH_DISTILBERT, SIMX_ERR_INVALID, "unknown arch %d", c->arch);
+  SIMX_CHECK(c->num_layers >= 1 && c->num_layers <= 64, SIMX_ERR_INVALID, "num_layers=%d out of range", c->num_layers);
+  SIMX_CHECK(c->hidden >= 64 && c->hidden % 64 == 0 && c->hidden <= 1024, SIMX_ERR_INVALID,
+             "hidden=%d must be a multiple of 64 in [64,1024]", c->hidden);
+  SIMX_CHECK(c->heads * 64 == c->hidden, SIMX_ERR_INVALID, "head_dim must be 64 (hidden=%d heads=%d)", c->hidden, c->heads);
+  SIMX_CHECK(c->intermediate >= 64 && c->intermediate % 64 == 0, SIMX_ERR_INVALID, "intermediate=%d must be a multiple of 64",
+             c->intermediate);
+  SIMX_CHECK(c->vocab > 0 && c->max_pos > 0, SIMX_ERR_INVALID, "vocab / max_pos must be positive");
+  SIMX_CHECK(c->arch != SIMX_ARCH_BERT || c->type_vocab >= 1, SIMX_ERR_INVALID, "BERT needs type_vocab >= 1");
+  SIMX_CHECK(c->precision == SIMX_PREC_BF16 || c->precision == SIMX_PREC_BF16X3, SIMX_ERR_INVALID, "unknown precision %d",
+             c->precision);
+  return SIMX_OK;
+}
+
+struct ParamTable {
+  int base;      // index of layer 0's first parameter
+  int n;         // number of parameters
+  bool bert;
+};
+static ParamTable ptable(const simx_encoder_cfg* c) {
+  ParamTable t;
+  t.bert = c->arch == SIMX_ARCH_BERT;
+  t.base = t.bert ? 5 : 4;
+  t.n = t.base + 16 * c->num_layers + (t.bert ? 2 : 0);
+  return t;
+}
+static int64_t param_numel(const simx_encoder_cfg* c, int idx) {
+  const ParamTable t = ptable(c);
+  const int64_t H = c->hidden, I = c->intermediate;
+  if (idx < 0 || idx >= t.n) return -1;
+  if (idx == 0) return (int64_t)c->vocab * H;
+  if (idx == 1) return (int64_t)c->max_pos * H;
+  if (t.bert && idx == 2) return (int64_t)c->type_vocab * H;
+  if (idx < t.base) return H;
+  if (idx >= t.base + 16 * c->num_layers) return idx == t.base + 16 * c->num_layers ? H * H : H;
+  const int k = (idx - t.base) % 16;
+  switch (k) {
+    case 0: case 2: case 4: case 6: return H * H;
+    case 10: case 12: return I * H;
+    case 11: return I;
+    default: return H;
+  }
+}
+// flat gradient layout: [word, pos, (type), embLN.w, embLN.b] then per layer
+// [Wqkv(3H*H) bqkv(3H) Wo bo ln1w ln1b W1 b1 W2 b2 ln2w ln2b] then (pooler.w, pooler.b)
+static int64_t layer_grad_numel(const simx_encoder_cfg* c) {
+  const int64_t H = c->hidden, I = c->intermediate;
+  return 3 * H * H + 3 * H + H * H + H + 2 * H + I * H + I + H * I + H + 2 * H;
+}
+static int64_t emb_grad_numel(const simx_encoder_cfg* c) {
+  const int64_t H = c->hidden;
+  return ((int64_t)c->vocab + c->max_pos + (c->arch == SIMX_ARCH_BERT ? c->type_vocab : 0)) * H + 2 * H;
+}
+static int64_t grad_offset(const simx_encoder_cfg* c, int idx) {
+  const ParamTable t = ptable(c);
+  const int64_t H = c->hidden, I = c->intermediate;
+  if (idx < 0 || idx >= t.n) return -1;
+  if (idx < t.base) {
+    int64_t off = 0;
+    for (int i = 0; i < idx; ++i) off += param_numel(c, i);
+    return off;
+  }
+  const int64_t e = emb_grad_numel(c);
+  if (idx >= t.base + 16 * c->num_layers)
+    return e + layer_grad_numel(c) * c->num_layers + (idx == t.base + 16 * c->num_layers ? 0 : H * H);
+  const int l = (idx - t.base) / 16, k = (idx - t.base) % 16;
+  const int64_t lo = e + layer_grad_numel(c) * l;
+  const int64_t o_qkvb = 3 * H * H, o_wo = o_qkvb + 3 * H, o_bo = o_wo + H * H, o_ln1 = o_bo + H, o_w1 = o_ln1 + 2 * H,
+                o_b1 = o_w1 + I * H, o_w2 = o_b1 + I, o_b2 = o_w2 + H * I, o_ln2 = o_b2 + H;
+  switch (k) {
+    case 0: return lo;
+    case 2: return lo + H * H;
+    case 4: return lo + 2 * H * H;
+    case 1: return lo + o_qkvb;
+    case 3: return lo + o_qkvb + H;
+    case 5: return lo + o_qkvb + 2 * H;
+    case 6: return lo + o_wo;
+    case 7: return lo + o_bo;
+    case 8: return lo + o_ln1;
+    case 9: return lo + o_ln1 + H;
+    case 10: return lo + o_w1;
+    case 11: return lo + o_b1;
+    case 12: return lo + o_w2;
+    case 13: return lo + o_b2;
+    case 14: return lo + o_ln2;
+    default: return lo + o_ln2 + H;
+  }
+}
+
+// ---- weight buffer ------------------------------------------------------------------------------
+struct LayerW {
+  size_t wqkv, wqkvT, wo, woT, w1, w1T, w2, w2T, bqkv, total;
+};
+static LayerW layer_w(const simx_encoder_cfg* c) {
+  const size_t H = c->hidden, I = c->intermediate, np = c->precision;
+  LayerW w;
+  size_t off = 0;
+  w.wqkv = off;  off += al(np * 3 * H * H * 2);
+  w.wqkvT = off; off += al(np * 3 * H * H * 2);
+  w.wo = off;    off += al(np * H * H * 2);
+  w.woT = off;   off += al(np * H * H * 2);
+  w.w1 = off;    off += al(np * I * H * 2);
+  w.w1T = off;   off += al(np * I * H * 2);
+  w.w2 = off;    off += al(np * I * H * 2);
+  w.w2T = off;   off += al(np * I * H * 2);
+  w.bqkv = off;  off += al(3 * H * 4);
+  w.total = off;
+  return w;
+}
+
+// ---- saved activations --------------------------------------------------------------------------
+struct SavedL {
+  size_t z0, x, layer0, l_qkv, l_ctx, l_z1, l_x1, l_h, l_a, l_z2, l_lse, l_total, total;
+  size_t x_stride;
+};
+static SavedL saved_layout(const simx_encoder_cfg* c, int B, int S) {
+  const size_t T = (size_t)B * S, H = c->hidden, I = c->intermediate, np = c->precision, L = c->num_layers;
+  SavedL s;
+  size_t off = 0;
+  s.z0 = off; off += al(np * T * H * 2);
+  s.x_stride = al(np * T * H * 2);
+  s.x = off;  off += s.x_stride * (L + 1);
+  size_t lo = 0;
+  s.l_qkv = lo; lo += al(np * T * 3 * H * 2);
+  s.l_ctx = lo; lo += al(np * T * H * 2);
+  s.l_z1 = lo;  lo += al(np * T * H * 2);
+  s.l_x1 = lo;  lo += al(np * T * H * 2);
+  s.l_h = lo;   lo += al(np * T * I * 2);
+  s.l_a = lo;   lo += al(np * T * I * 2);
+  s.l_z2 = lo;  lo += al(np * T * H * 2);
+  s.l_lse = lo; lo += al((size_t)B * c->heads * S * 4);
+  s.l_total = lo;
+  s.layer0 = off;
+  off += lo * L;
+  s.total = off + 256;
+  return s;
+}
+
+// ---- workspace: backward temporaries, and one layer of activations for saved == NULL (inference) ----
+struct WsL {
+  size_t dx, dza, dxb, dh, dqkv, delta, infer, total;
+};
+static WsL ws_layout(const simx_encoder_cfg* c, int B, int S) {
+  const size_t T = (size_t)B * S, H = c->hidden, I = c->intermediate, np = c->precision;
+  WsL w;
+  size_t off = 0;
+  w.dx = off;    off += al(np * T * H * 2);
+  w.dza = off;   off += al(np * T * H * 2);
+  w.dxb = off;   off += al(np * T * H * 2);
+  w.dh = off;    off += al(np * T * I * 2);
+  w.dqkv = off;  off += al(np * T * 3 * H * 2);
+  w.delta = off; off += al((size_t)B * c->heads * S * 4);
+  // inference scratch aliases the backward temporaries (never live together): z0 + 2 x + one layer
+  const SavedL s = saved_layout(c, B, S);
+  w.infer = 0;
+  const size_t infer_bytes = al(np * T * H * 2) * 3 + s.l_total;
+  w.total = (off > infer_bytes ? off : infer_bytes) + 256;
+  return w;
+}
+
+static inline uint8_t* align_ptr(const void* p) {
+  uintptr_t u = reinterpret_cast<uintptr_t>(p);
+  return reinterpret_cast<uint8_t*>((u + 255) & ~uintptr_t(255));
+}
+
+static int wgrad_ksplit(int M, int N, int K) {
+  const int bn = N <= 64 ? 64 : (N <= 128 ? 128 : 256);
+  const int tiles = ((M + 127) / 128) * ((N + bn - 1) / bn);
+  const int kb = (K + 63) / 64;
+  int ks = (3 * num_sms() + tiles - 1) / tiles;
+  ks = min(ks, max(1, kb / 4));  // at least 4 k-blocks per split
+  return max(1, ks);
+}
+
+}  // namespace simx
+
+using namespace simx;
+
+extern "C" int simx_encoder_num_params(const simx_encoder_cfg* cfg) { return check_cfg(cfg) ? -1 : ptable(cfg).n; }
+extern "C" int64_t simx_encoder_param_numel(const simx_encoder_cfg* cfg, int idx) {
+  return check_cfg(cfg) ? -1 : param_numel(cfg, idx);
+}
+extern "C" int64_t simx_encoder_grad_offset(const simx_encoder_cfg* cfg, int idx) {
+  return check_cfg(cfg) ? -1 : grad_offset(cfg, idx);
+}
+extern "C" int64_t simx_encoder_grad_numel(const simx_encoder_cfg* cfg) {
+  if (check_cfg(cfg)) return -1;
+  const int64_t H = cfg->hidden;
+  return emb_grad_numel(cfg) + layer_grad_numel(cfg) * cfg->num_layers + (cfg->arch == SIMX_ARCH_BERT ? H * H + H : 0);
+}
+extern "C" size_t simx_encoder_weight_bytes(const simx_encoder_cfg* cfg) {
+  return check_cfg(cfg) ? 0 : layer_w(cfg).total * cfg->num_layers + 256;
+}
+extern "C" size_t simx_encoder_saved_bytes(const simx_encoder_cfg* cfg, int B, int S) {
+  return (check_cfg(cfg) || B <= 0 || S <= 0) ? 0 : saved_layout(cfg, B, S).total;
+}
+extern "C" size_t simx_encoder_workspace_bytes(const simx_encoder_cfg* cfg, int B, int S) {
+  return (check_cfg(cfg) || B <= 0 || S <= 0) ? 0 : ws_layout(cfg, B, S).total;
+}
+
+extern "C" int simx_encoder_prepare_weights(const simx_encoder_cfg* cfg, const float* const* params, void* wbuf,
+                                            void* stream) {
+  SIMX_TRY(check_cfg(cfg));
+  SIMX_CHECK(params && wbuf, SIMX_ERR_INVALID, "prepare_weights: null argument");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int np = cfg->precision, H = cfg->hidden, I = cfg->intermediate;
+  const ParamTable t = ptable(cfg);
+  const LayerW lw = layer_w(cfg);
+  uint8_t* base = align_ptr(wbuf);
+  for (int l = 0; l < cfg->num_layers; ++l) {
+    const float* const* P = params + t.base + 16 * l;
+    uint8_t* w = base + lw.total * l;
+    bf16* wqkv = reinterpret_cast<bf16*>(w + lw.wqkv);
+    bf16* wqkvT = reinterpret_cast<bf16*>(w + lw.wqkvT);
+    const long ps3 = 3L * H * H;
+    for (int j = 0; j < 3; ++j)  // q, k, v rows stacked; transposed copy [H, 3H] has them as column blocks
+      SIMX_TRY(convert_weight(np, P[2 * j], H, H, wqkv + (long)j * H * H, H, ps3, wqkvT + (long)j * H, 3L * H, ps3, st));
+    SIMX_TRY(convert_weight(np, P[6], H, H, reinterpret_cast<bf16*>(w + lw.wo), H, (long)H * H,
+                            reinterpret_cast<bf16*>(w + lw.woT), H, (long)H * H, st));
+    SIMX_TRY(convert_weight(np, P[10], I, H, reinterpret_cast<bf16*>(w + lw.w1), H, (long)I * H,
+                            reinterpret_cast<bf16*>(w + lw.w1T), I, (long)I * H, st));
+    SIMX_TRY(convert_weight(np, P[12], H, I, reinterpret_cast<bf16*>(w + lw.w2), I, (long)I * H,
+                            reinterpret_cast<bf16*>(w + lw.w2T), H, (long)I * H, st));
+    float* bqkv = reinterpret_cast<float*>(w + lw.bqkv);
+    for (int j = 0; j < 3; ++j)
+      SIMX_CUDA(cudaMemcpyAsync(bqkv + j * H, P[2 * j + 1], H * sizeof(float), cudaMemcpyDeviceToDevice, st));
+  }
+  return SIMX_OK;
+}
+
+extern "C" int simx_encoder_forward(const simx_encoder_cfg* cfg, const float* const* params, const void* wbuf,
+                                    const int64_t* ids, const int64_t* mask, int B, int S, void* saved, void* workspace,
+                                    float* cls_out, float* seq_out, void* stream) {
+  SIMX_TRY(check_cfg(cfg));
+  SIMX_CHECK(params && wbuf && ids, SIMX_ERR_INVALID, "encoder_forward: null argument");
+  SIMX_CHECK(B > 0 && S > 0 && S <= cfg->max_pos && S <= 512, SIMX_ERR_INVALID,
+             "encoder_forward: need 0 < S <= min(max_pos=%d, 512), got B=%d S=%d", cfg->max_pos, B, S);
+  SIMX_CHECK(saved != nullptr || workspace != nullptr, SIMX_ERR_INVALID, "encoder_forward: need saved or workspace");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int np = cfg->precision, H = cfg->hidden, I = cfg->intermediate, L = cfg->num_layers;
+  const int T = B * S;
+  const long psH = (long)T * H, ps3H = (long)T * 3 * H, psI = (long)T * I;
+  const ParamTable t = ptable(cfg);
+  const LayerW lw = layer_w(cfg);
+  const SavedL sl = saved_layout(cfg, B, S);
+  const uint8_t* wb = align_ptr(wbuf);
+  const bool keep = saved != nullptr;
+  uint8_t* sb = keep ? align_ptr(saved) : align_ptr(workspace);
+  // inference: [z0][xa][xb][one layer]
+  auto xbuf = [&](int l) -> bf16* {
+    if (keep) return reinterpret_cast<bf16*>(sb + sl.x + sl.x_stride * l);
+    return reinterpret_cast<bf16*>(sb + sl.x_stride * (1 + (l & 1)));
+  };
+  auto lbuf = [&](int l, size_t off) -> uint8_t* {
+    if (keep) return sb + sl.layer0 + sl.l_total * l + off;
+    return sb + sl.x_stride * 3 + off;
+  };
+  bf16* z0 = keep ? reinterpret_cast<bf16*>(sb + sl.z0) : nullptr;
+  const float* type0 = t.bert ? params[2] : nullptr;
+  const float* eg = params[t.bert ? 3 : 2];
+  const float* eb = params[t.bert ? 4 : 3];
+  SIMX_TRY(embed_ln(np, ids, T, S, H, cfg->vocab, params[0], params[1], type0, eg, eb, cfg->ln_eps, z0, xbuf(0), psH, st));
+  const long cls_stride_b = (long)(L + 1) * H;
+  if (cls_out) SIMX_TRY(cls_gather(np, xbuf(0), B, S, H, psH, cls_out, cls_stride_b, st));
+
+  for (int l = 0; l < L; ++l) {
+    const float* const* P = params + t.base + 16 * l;
+    const uint8_t* w = wb + lw.total * l;
+    const bf16* wqkv = reinterpret_cast<const bf16*>(w + lw.wqkv);
+    const bf16* wo = reinterpret_cast<const bf16*>(w + lw.wo);
+    const bf16* w1 = reinterpret_cast<const bf16*>(w + lw.w1);
+    const bf16* w2 = reinterpret_cast<const bf16*>(w + lw.w2);
+    const float* bqkv = reinterpret_cast<const float*>(w + lw.bqkv);
+    bf16* x = xbuf(l);
+    bf16* xo = xbuf(l + 1);
+    bf16* qkv = reinterpret_cast<bf16*>(lbuf(l, sl.l_qkv));
+    bf16* ctx = reinterpret_cast<bf16*>(lbuf(l, sl.l_ctx));
+    bf16* z1 = reinterpret_cast<bf16*>(lbuf(l, sl.l_z1));
+    bf16* x1 = reinterpret_cast<bf16*>(lbuf(l, sl.l_x1));
+    bf16* h = reinterpret_cast<bf16*>(lbuf(l, sl.l_h));
+    bf16* a = reinterpret_cast<bf16*>(lbuf(l, sl.l_a));
+    bf16* z2 = reinterpret_cast<bf16*>(lbuf(l, sl.l_z2));
+    float* lse = reinterpret_cast<float*>(lbuf(l, sl.l_lse));
+
+    SIMX_TRY(gemm(T, 3 * H, H, x, H, psH, false, wqkv, H, 3L * H * H, false, np, SIMX_EPI_BIAS, bqkv, nullptr, 0, 0, qkv,
+                  nullptr, 3 * H, ps3H, nullptr, 0, 1, st));
+    SIMX_TRY(attention_forward(np, qkv, ps3H, ctx, psH, mask, lse, B, S, H, cfg->heads, st));
+    SIMX_TRY(gemm(T, H, H, ctx, H, psH, false, wo, H, (long)H * H, false, np, SIMX_EPI_BIAS_ADD, P[7], x, H, psH, z1,
+                  nullptr, H, psH, nullptr, 0, 1, st));
+    SIMX_TRY(ln_fwd(np, z1, T, H, P[8], P[9], cfg->ln_eps, x1, psH, st));
+    SIMX_TRY(gemm(T, I, H, x1, H, psH, false, w1, H, (long)I * H, false, np, SIMX_EPI_BIAS_GELU, P[11], nullptr, 0, 0, h, a,
+                  I, psI, nullptr, 0, 1, st));
+    SIMX_TRY(gemm(T, H, I, a, I, psI, false, w2, I, (long)I * H, false, np, SIMX_EPI_BIAS_ADD, P[13], x1, H, psH, z2,
+                  nullptr, H, psH, nullptr, 0, 1, st));
+    SIMX_TRY(ln_fwd(np, z2, T, H, P[14], P[15], cfg->ln_eps, xo, psH, st));
+    if (cls_out) SIMX_TRY(cls_gather(np, xo, B, S, H, psH, cls_out + (long)(l + 1) * H, cls_stride_b, st));
+  }
+  if (seq_out) SIMX_TRY(planes_to_f32(np, xbuf(L), (long)T * H, psH, seq_out, st));
+  return SIMX_OK;
+}
+
+extern "C" int simx_encoder_backward(const simx_encoder_cfg* cfg, const float* const* params, const void* wbuf,
+                                     const int64_t* ids, const int64_t* mask, int B, int S, const void* saved,
+                                     void* workspace, const float* d_cls, const float* d_seq, float* grads,
+                                     void* stream) {
+  SIMX_TRY(check_cfg(cfg));
+  SIMX_CHECK(params && wbuf && ids && saved && workspace && grads, SIMX_ERR_INVALID, "encoder_backward: null argument");
+  SIMX_CHECK(d_cls != nullptr || d_seq != nullptr, SIMX_ERR_INVALID, "encoder_backward: no cotangent given");
+  SIMX_CHECK(B > 0 && S > 0 && S <= cfg->max_pos && S <= 512, SIMX_ERR_INVALID, "encoder_backward: bad B=%d S=%d", B, S);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int np = cfg->precision, H = cfg->hidden, I = cfg->intermediate, L = cfg->num_layers;
+  const int T = B * S;
+  const long psH = (long)T * H, ps3H = (long)T * 3 * H, psI = (long)T * I;
+  const ParamTable t = ptable(cfg);
+  const LayerW lw = layer_w(cfg);
+  const SavedL sl = saved_layout(cfg, B, S);
+  const WsL wl = ws_layout(cfg, B, S);
+  const uint8_t* wb = align_ptr(wbuf);
+  const uint8_t* sb = align_ptr(saved);
+  uint8_t* ws = align_ptr(workspace);
+  bf16* dx = reinterpret_cast<bf16*>(ws + wl.dx);
+  bf16* dza = reinterpret_cast<bf16*>(ws + wl.dza);
+  bf16* dxb = reinterpret_cast<bf16*>(ws + wl.dxb);
+  bf16* dh = reinterpret_cast<bf16*>(ws + wl.dh);
+  bf16* dqkv = reinterpret_cast<bf16*>(ws + wl.dqkv);
+  float* delta = reinterpret_cast<float*>(ws + wl.delta);
+  const long cls_stride_b = (long)(L + 1) * H;
+
+  const int64_t total = simx_encoder_grad_numel(cfg);
+  SIMX_CUDA(cudaMemsetAsync(grads, 0, (size_t)total * sizeof(float), st));
+  auto G = [&](int idx) -> float* { return grads + grad_offset(cfg, idx); };
+
+  // cotangent of the last hidden state
+  SIMX_TRY(f32_to_planes(np, d_seq, (long)T * H, dx, psH, st));
+  if (d_cls) SIMX_TRY(cls_scatter_add(np, dx, B, S, H, psH, d_cls + (long)L * H, cls_stride_b, st));
+
+  for (int l = L - 1; l >= 0; --l) {
+    const float* const* P = params + t.base + 16 * l;
+    const int pi = t.base + 16 * l;
+    const uint8_t* w = wb + lw.total * l;
+    const bf16* wqkvT = reinterpret_cast<const bf16*>(w + lw.wqkvT);
+    const bf16* woT = reinterpret_cast<const bf16*>(w + lw.woT);
+    const bf16* w1T = reinterpret_cast<const bf16*>(w + lw.w1T);
+    const bf16* w2T = reinterpret_cast<const bf16*>(w + lw.w2T);
+    const uint8_t* lb = sb + sl.layer0 + sl.l_total * l;
+    const bf16* x = reinterpret_cast<const bf16*>(sb + sl.x + sl.x_stride * l);
+    const bf16* qkv = reinterpret_cast<const bf16*>(lb + sl.l_qkv);
+    const bf16* ctx = reinterpret_cast<const bf16*>(lb + sl.l_ctx);
+    const bf16* z1 = reinterpret_cast<const bf16*>(lb + sl.l_z1);
+    const bf16* x1 = reinterpret_cast<const bf16*>(lb + sl.l_x1);
+    const bf16* h = reinterpret_cast<const bf16*>(lb + sl.l_h);
+    const bf16* a = reinterpret_cast<const bf16*>(lb + sl.l_a);
+    const bf16* z2 = reinterpret_cast<const bf16*>(lb + sl.l_z2);
+    const float* lse = reinterpret_cast<const float*>(lb + sl.l_lse);
+
+    // output LayerNorm -> dz2 (= d ffn-out = d residual x1), dgamma/dbeta, and db2 = colsum(dz2)
+    SIMX_TRY(ln_bwd(np, dx, z2, T, H, P[14], cfg->ln_eps, dza, psH, G(pi + 14), G(pi + 15), G(pi + 13), st));
+    // dW2 [H,I] += dz2^T a
+    SIMX_TRY(gemm(H, I, T, dza, H, psH, true, a, I, psI, true, np, SIMX_EPI_ATOMIC_F32, nullptr, nullptr, 0, 0, nullptr,
+                  nullptr, 0, 0, G(pi + 12), I, wgrad_ksplit(H, I, T), st));
+    // dh = (dz2 W2) o gelu'(h)
+    SIMX_TRY(gemm(T, I, H, dza, H, psH, false, w2T, H, (long)I * H, false, np, SIMX_EPI_DGELU, nullptr, h, I, psI, dh,
+                  nullptr, I, psI, nullptr, 0, 1, st));
+    SIMX_TRY(colsum(np, dh, T, I, I, psI, G(pi + 11), st));
+    // dW1 [I,H] += dh^T x1
+    SIMX_TRY(gemm(I, H, T, dh, I, psI, true, x1, H, psH, true, np, SIMX_EPI_ATOMIC_F32, nullptr, nullptr, 0, 0, nullptr,
+                  nullptr, 0, 0, G(pi + 10), H, wgrad_ksplit(I, H, T), st));
+    // dx1 = dh W1 + dz2
+    SIMX_TRY(gemm(T, H, I, dh, I, psI, false, w1T, I, (long)I * H, false, np, SIMX_EPI_ADD, nullptr, dza, H, psH, dxb,
+                  nullptr, H, psH, nullptr, 0, 1, st));
+    // attention-output LayerNorm -> dz1, and dbo = colsum(dz1)
+    SIMX_TRY(ln_bwd(np, dxb, z1, T, H, P[8], cfg->ln_eps, dza, psH, G(pi + 8), G(pi + 9), G(pi + 7), st));
+    // dWo [H,H] += dz1^T ctx
+    SIMX_TRY(gemm(H, H, T, dza, H, psH, true, ctx, H, psH, true, np, SIMX_EPI_ATOMIC_F32, nullptr, nullptr, 0, 0, nullptr,
+                  nullptr, 0, 0, G(pi + 6), H, wgrad_ksplit(H, H, T), st));
+    // dctx = dz1 Wo
+    SIMX_TRY(gemm(T, H, H, dza, H, psH, false, woT, H, (long)H * H, false, np, SIMX_EPI_PLAIN, nullptr, nullptr, 0, 0, dxb,
+                  nullptr, H, psH, nullptr, 0, 1, st));
+    SIMX_TRY(attention_backward(np, qkv, ps3H, ctx, dxb, psH, dqkv, mask, lse, delta, B, S, H, cfg->heads, st));
+    // fused q/k/v bias and weight gradients ([3H] and [3H,H] blocks of the flat gradient buffer)
+    SIMX_TRY(colsum(np, dqkv, T, 3 * H, 3 * H, ps3H, G(pi + 1), st));
+    SIMX_TRY(gemm(3 * H, H, T, dqkv, 3 * H, ps3H, true, x, H, psH, true, np, SIMX_EPI_ATOMIC_F32, nullptr, nullptr, 0, 0,
+                  nullptr, nullptr, 0, 0, G(pi + 0), H, wgrad_ksplit(3 * H, H, T), st));
+    // dx(layer input) = dqkv Wqkv + dz1   (+ the [CLS] cotangent LEAD injects at this depth)
+    SIMX_TRY(gemm(T, H, 3 * H, dqkv, 3 * H, ps3H, false, wqkvT, 3 * H, 3L * H * H, false, np, SIMX_EPI_ADD, nullptr, dza, H,
+                  psH, dx, nullptr, H, psH, nullptr, 0, 1, st));
+    if (d_cls) SIMX_TRY(cls_scatter_add(np, dx, B, S, H, psH, d_cls + (long)l * H, cls_stride_b, st));
+  }
+  // embeddings
+  const bf16* z0 = reinterpret_cast<const bf16*>(sb + sl.z0);
+  const int ig = t.bert ? 3 : 2;
+  SIMX_TRY(ln_bwd(np, dx, z0, T, H, params[ig], cfg->ln_eps, dza, psH, G(ig), G(ig + 1), t.bert ? G(2) : nullptr, st));
+  // position rows: dPos[s] = sum_b dz0[b*S + s]: a column sum of the [B, S*H] view
+  SIMX_TRY(colsum(np, dza, B, S * H, (long)S * H, psH, G(1), st));
+  SIMX_TRY(embed_scatter(np, ids, dza, T, H, cfg->vocab, psH, G(0), st));
+  return SIMX_OK;
+}

@@ -1,0 +1,440 @@
+// HBM-bound row kernels of the encoder: embedding gather + LayerNorm, LayerNorm forward / backward (warp-shuffle row
+// reductions), column sums (bias gradients), [CLS] gather / cotangent scatter, embedding-gradient scatter, and the
+// fp32 -> (split-)bf16 weight preparation.  One warp owns one row; a lane owns 8-element (16 B) chunks strided by
+// 256 elements, so every global access of a warp is a contiguous 512 B segment.
+//
+// Reference math: LEAD/modeling_bert.py:201-240 (BertEmbeddings), :384-388 / :462-466 (residual + LayerNorm),
+// torch.nn.LayerNorm (biased variance, eps inside the sqrt).
+#include "common.cuh"
+#include "ptx.cuh"
+
+namespace simx {
+
+constexpr int ROW_THREADS = 256;
+constexpr int ROW_WARPS = ROW_THREADS / 32;
+constexpr int MAXC = 4;  // chunks per lane: supports H <= 1024
+
+__device__ __forceinline__ void ld8f(const float* p, float (&v)[8]) {
+  const float4 a = __ldg(reinterpret_cast<const float4*>(p));
+  const float4 b = __ldg(reinterpret_cast<const float4*>(p + 4));
+  v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+}
+
+// normalise the row held in v (NC chunks of 8 per lane), write y = xhat * g + b
+template <int NP>
+__device__ __forceinline__ void ln_row_store(float (&v)[MAXC][8], int H, int lane, const float* gamma,
+                                             const float* beta, float eps, bf16* out, long ps) {
+  float s = 0.f;
+#pragma unroll
+  for (int c = 0; c < MAXC; ++c)
+    if (c * 256 + lane * 8 < H)
+#pragma unroll
+      for (int i = 0; i < 8; ++i) s += v[c][i];
+  const float mean = warp_sum(s) / H;
+  float q = 0.f;
+#pragma unroll
+  for (int c = 0; c < MAXC; ++c)
+    if (c * 256 + lane * 8 < H)
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const float d = v[c][i] - mean;
+        q += d * d;
+      }
+  const float rstd = rsqrtf(warp_sum(q) / H + eps);
+#pragma unroll
+  for (int c = 0; c < MAXC; ++c) {
+    const int col = c * 256 + lane * 8;
+    if (col < H) {
+      float g[8], b[8], y[8];
+      ld8f(gamma + col, g);
+      ld8f(beta + col, b);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) y[i] = (v[c][i] - mean) * rstd * g[i] + b[i];
+      split_store8<NP>(out + col, ps, y);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// embeddings: z0 = word[id] + pos[s] (+ type[0]);  x = LN(z0).  z0 is kept for backward.
+// ------------------------------------------------------------------------------------------------
+template <int NP>
+__global__ void __launch_bounds__(ROW_THREADS)
+embed_ln_kernel(const int64_t* __restrict__ ids, int T, int S, int H, int vocab, const float* __restrict__ word,
+                const float* __restrict__ pos, const float* __restrict__ type0, const float* __restrict__ gamma,
+                const float* __restrict__ beta, float eps, bf16* z0, bf16* x, long ps) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int row = blockIdx.x * ROW_WARPS + warp;
+  if (row >= T) return;
+  long id = ids[row];
+  if (id < 0 || id >= vocab) id = 0;  // out-of-range ids are a caller bug; stay in bounds
+  const int s = row % S;
+  float v[MAXC][8];
+#pragma unroll
+  for (int c = 0; c < MAXC; ++c) {
+    const int col = c * 256 + lane * 8;
+    if (col < H) {
+      float w[8], p[8];
+      ld8f(word + id * H + col, w);
+      ld8f(pos + (long)s * H + col, p);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) v[c][i] = w[i] + p[i];
+      if (type0 != nullptr) {
+        ld8f(type0 + col, p);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) v[c][i] += p[i];
+      }
+      if (z0 != nullptr) split_store8<NP>(z0 + (long)row * H + col, ps, v[c]);
+      if constexpr (NP == 1) {
+        // the LayerNorm input must be what backward will re-read: round through the stored representation
+        if (z0 != nullptr) {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) v[c][i] = __bfloat162float(__float2bfloat16_rn(v[c][i]));
+        }
+      }
+    }
+  }
+  ln_row_store<NP>(v, H, lane, gamma, beta, eps, x + (long)row * H, ps);
+}
+
+template <int NP>
+__global__ void __launch_bounds__(ROW_THREADS)
+ln_fwd_kernel(const bf16* __restrict__ z, int T, int H, const float* __restrict__ gamma,
+              const float* __restrict__ beta, float eps, bf16* x, long ps) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int row = blockIdx.x * ROW_WARPS + warp;
+  if (row >= T) return;
+  float v[MAXC][8];
+#pragma unroll
+  for (int c = 0; c < MAXC; ++c) {
+    const int col = c * 256 + lane * 8;
+    if (col < H) plane_load8<NP>(z + (long)row * H + col, ps, v[c]);
+  }
+  ln_row_store<NP>(v, H, lane, gamma, beta, eps, x + (long)row * H, ps);
+}
+
+// ------------------------------------------------------------------------------------------------
+// LayerNorm backward.  dz = rstd * (g*dy - mean(g*dy) - xhat * mean(g*dy*xhat));
+// dgamma += sum dy*xhat, dbeta += sum dy, and (optionally) dbias += sum dz  — the bias gradient of the GEMM that
+// produced z (BertSelfOutput.dense / BertOutput.dense), so that GEMM needs no separate column-sum pass.
+// Each block walks rows with a grid stride and keeps its partial column sums in registers.
+// ------------------------------------------------------------------------------------------------
+template <int NP>
+__global__ void __launch_bounds__(ROW_THREADS)
+ln_bwd_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ z, int T, int H, const float* __restrict__ gamma,
+              float eps, bf16* dz, long ps, float* dgamma, float* dbeta, float* dbias) {
+  __shared__ float red[ROW_WARPS][32 * 8 + 8];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  float ag[MAXC][8], ab[MAXC][8], ad[MAXC][8];
+#pragma unroll
+  for (int c = 0; c < MAXC; ++c)
+#pragma unroll
+    for (int i = 0; i < 8; ++i) ag[c][i] = ab[c][i] = ad[c][i] = 0.f;
+
+  for (int row = blockIdx.x * ROW_WARPS + warp; row < T; row += gridDim.x * ROW_WARPS) {
+    float v[MAXC][8], g[MAXC][8];
+    float s = 0.f;
+#pragma unroll
+    for (int c = 0; c < MAXC; ++c) {
+      const int col = c * 256 + lane * 8;
+      if (col < H) {
+        plane_load8<NP>(z + (long)row * H + col, ps, v[c]);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) s += v[c][i];
+      }
+    }
+    const float mean = warp_sum(s) / H;
+    float q = 0.f;
+#pragma unroll
+    for (int c = 0; c < MAXC; ++c)
+      if (c * 256 + lane * 8 < H)
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          v[c][i] -= mean;
+          q += v[c][i] * v[c][i];
+        }
+    const float rstd = rsqrtf(warp_sum(q) / H + eps);
+    float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int c = 0; c < MAXC; ++c) {
+      const int col = c * 256 + lane * 8;
+      if (col < H) {
+        float d[8], gm[8];
+        plane_load8<NP>(dy + (long)row * H + col, ps, d);
+        ld8f(gamma + col, gm);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const float xh = v[c][i] * rstd;
+          v[c][i] = xh;
+          ag[c][i] += d[i] * xh;
+          ab[c][i] += d[i];
+          g[c][i] = d[i] * gm[i];
+          s1 += g[c][i];
+          s2 += g[c][i] * xh;
+        }
+      }
+    }
+    s1 = warp_sum(s1) / H;
+    s2 = warp_sum(s2) / H;
+#pragma unroll
+    for (int c = 0; c < MAXC; ++c) {
+      const int col = c * 256 + lane * 8;
+      if (col < H) {
+        float o[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          o[i] = rstd * (g[c][i] - s1 - v[c][i] * s2);
+          ad[c][i] += o[i];
+        }
+        split_store8<NP>(dz + (long)row * H + col, ps, o);
+      }
+    }
+  }
+  // block reduction of the three column-sum vectors, then one atomic per column per block
+  float* outs[3] = {dgamma, dbeta, dbias};
+#pragma unroll
+  for (int which = 0; which < 3; ++which) {
+    if (outs[which] == nullptr) continue;
+#pragma unroll
+    for (int c = 0; c < MAXC; ++c) {
+      if (c * 256 >= H) break;
+      __syncthreads();
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+        red[warp][lane * 8 + i] = which == 0 ? ag[c][i] : (which == 1 ? ab[c][i] : ad[c][i]);
+      __syncthreads();
+      const int col = c * 256 + threadIdx.x;
+      if (col < H) {
+        float t = 0.f;
+#pragma unroll
+        for (int w = 0; w < ROW_WARPS; ++w) t += red[w][threadIdx.x];
+        atomicAdd(outs[which] + col, t);
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// out[col] += sum_{r in rows} x[r*row_stride + col]   (bias gradients; position-embedding gradient with
+// row_stride = S*H and a batch loop).  grid = (ceil(N/256), row_splits)
+// ------------------------------------------------------------------------------------------------
+template <int NP>
+__global__ void __launch_bounds__(ROW_THREADS)
+colsum_kernel(const bf16* __restrict__ x, long rows, int N, long row_stride, long ps, float* out) {
+  __shared__ float red[ROW_WARPS][32 * 8 + 8];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int col = blockIdx.x * 256 + lane * 8;
+  float acc[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) acc[i] = 0.f;
+  if (col < N) {
+    for (long r = (long)blockIdx.y * ROW_WARPS + warp; r < rows; r += (long)gridDim.y * ROW_WARPS) {
+      float v[8];
+      plane_load8<NP>(x + r * row_stride + col, ps, v);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) acc[i] += v[i];
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 8; ++i) red[warp][lane * 8 + i] = acc[i];
+  __syncthreads();
+  const int c = blockIdx.x * 256 + threadIdx.x;
+  if (c < N) {
+    float t = 0.f;
+#pragma unroll
+    for (int w = 0; w < ROW_WARPS; ++w) t += red[w][threadIdx.x];
+    atomicAdd(out + c, t);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// [CLS] rows: cls_out[b, l, :] = x[b*S, :]  and the reverse (cotangent injection into the gradient stream)
+// ------------------------------------------------------------------------------------------------
+template <int NP>
+__global__ void cls_gather_kernel(const bf16* __restrict__ x, int B, int S, int H, long ps, float* out,
+                                  long out_stride_b) {
+  const int b = blockIdx.x;
+  for (int col = threadIdx.x * 8; col < H; col += blockDim.x * 8) {
+    float v[8];
+    plane_load8<NP>(x + (long)b * S * H + col, ps, v);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) out[(long)b * out_stride_b + col + i] = v[i];
+  }
+}
+// dx[b*S, :] += d_cls[b, l, :]
+template <int NP>
+__global__ void cls_scatter_add_kernel(bf16* dx, int B, int S, int H, long ps, const float* __restrict__ d,
+                                       long d_stride_b) {
+  const int b = blockIdx.x;
+  for (int col = threadIdx.x * 8; col < H; col += blockDim.x * 8) {
+    float v[8];
+    plane_load8<NP>(dx + (long)b * S * H + col, ps, v);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v[i] += d[(long)b * d_stride_b + col + i];
+    split_store8<NP>(dx + (long)b * S * H + col, ps, v);
+  }
+}
+
+// fp32 [n] -> planes (n % 8 == 0), src may be NULL (zeros); and planes -> fp32
+template <int NP>
+__global__ void f32_to_planes_kernel(const float* __restrict__ src, long n, bf16* dst, long ps) {
+  for (long i = ((long)blockIdx.x * blockDim.x + threadIdx.x) * 8; i < n; i += (long)gridDim.x * blockDim.x * 8) {
+    float v[8];
+    if (src != nullptr) ld8f(src + i, v);
+    else
+#pragma unroll
+      for (int k = 0; k < 8; ++k) v[k] = 0.f;
+    split_store8<NP>(dst + i, ps, v);
+  }
+}
+template <int NP>
+__global__ void planes_to_f32_kernel(const bf16* __restrict__ src, long n, long ps, float* dst) {
+  for (long i = ((long)blockIdx.x * blockDim.x + threadIdx.x) * 8; i < n; i += (long)gridDim.x * blockDim.x * 8) {
+    float v[8];
+    plane_load8<NP>(src + i, ps, v);
+    *reinterpret_cast<float4*>(dst + i) = make_float4(v[0], v[1], v[2], v[3]);
+    *reinterpret_cast<float4*>(dst + i + 4) = make_float4(v[4], v[5], v[6], v[7]);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// embedding gradient: dWord[id] += dz0[row] (skipping the padding row 0: nn.Embedding(padding_idx=0))
+// ------------------------------------------------------------------------------------------------
+template <int NP>
+__global__ void __launch_bounds__(ROW_THREADS)
+embed_scatter_kernel(const int64_t* __restrict__ ids, const bf16* __restrict__ dz0, int T, int H, int vocab, long ps,
+                     float* dword) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int row = blockIdx.x * ROW_WARPS + warp;
+  if (row >= T) return;
+  const long id = ids[row];
+  if (id <= 0 || id >= vocab) return;
+  for (int col = lane * 8; col < H; col += 256) {
+    float v[8];
+    plane_load8<NP>(dz0 + (long)row * H + col, ps, v);
+    float* o = dword + id * H + col;
+    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(o), "f"(v[0]), "f"(v[1]), "f"(v[2]), "f"(v[3])
+                 : "memory");
+    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(o + 4), "f"(v[4]), "f"(v[5]), "f"(v[6]),
+                 "f"(v[7])
+                 : "memory");
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// weight preparation: fp32 [R,C] -> planes [R,C] at dst (+ optional transposed copy [C,R] at dst_t)
+// ------------------------------------------------------------------------------------------------
+template <int NP>
+__global__ void convert_weight_kernel(const float* __restrict__ w, int R, int C, bf16* dst, long ld_dst, long ps_dst,
+                                      bf16* dst_t, long ld_t, long ps_t) {
+  __shared__ float tile[32][33];
+  const int c0 = blockIdx.x * 32, r0 = blockIdx.y * 32;
+  const int tx = threadIdx.x, ty = threadIdx.y;  // 32 x 8
+  for (int j = ty; j < 32; j += 8) {
+    const int r = r0 + j, c = c0 + tx;
+    float v = 0.f;
+    if (r < R && c < C) {
+      v = w[(long)r * C + c];
+      if (dst != nullptr) split_store<NP>(dst + (long)r * ld_dst + c, ps_dst, v);
+    }
+    tile[j][tx] = v;
+  }
+  if (dst_t == nullptr) return;
+  __syncthreads();
+  for (int j = ty; j < 32; j += 8) {
+    const int c = c0 + j, r = r0 + tx;
+    if (r < R && c < C) split_store<NP>(dst_t + (long)c * ld_t + r, ps_t, tile[tx][j]);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// host wrappers
+// ------------------------------------------------------------------------------------------------
+#define SIMX_NP_DISPATCH(NP, CALL)                                      \
+  do {                                                                  \
+    if ((NP) == 1) { constexpr int kNP = 1; CALL; }                     \
+    else { constexpr int kNP = 3; CALL; }                               \
+  } while (0)
+
+int embed_ln(int np, const int64_t* ids, int T, int S, int H, int vocab, const float* word, const float* pos,
+             const float* type0, const float* gamma, const float* beta, float eps, bf16* z0, bf16* x, long ps,
+             cudaStream_t st) {
+  SIMX_CHECK(H % 8 == 0 && H <= 256 * MAXC, SIMX_ERR_INVALID, "hidden size %d unsupported (multiple of 8, <= %d)", H,
+             256 * MAXC);
+  const int grid = (T + ROW_WARPS - 1) / ROW_WARPS;
+  SIMX_NP_DISPATCH(np, (embed_ln_kernel<kNP><<<grid, ROW_THREADS, 0, st>>>(ids, T, S, H, vocab, word, pos, type0, gamma,
+                                                                           beta, eps, z0, x, ps)));
+  SIMX_LAUNCH_CHECK();
+  return SIMX_OK;
+}
+
+int ln_fwd(int np, const bf16* z, int T, int H, const float* gamma, const float* beta, float eps, bf16* x, long ps,
+           cudaStream_t st) {
+  SIMX_CHECK(H % 8 == 0 && H <= 256 * MAXC, SIMX_ERR_INVALID, "hidden size %d unsupported", H);
+  const int grid = (T + ROW_WARPS - 1) / ROW_WARPS;
+  SIMX_NP_DISPATCH(np, (ln_fwd_kernel<kNP><<<grid, ROW_THREADS, 0, st>>>(z, T, H, gamma, beta, eps, x, ps)));
+  SIMX_LAUNCH_CHECK();
+  return SIMX_OK;
+}
+
+int ln_bwd(int np, const bf16* dy, const bf16* z, int T, int H, const float* gamma, float eps, bf16* dz, long ps,
+           float* dgamma, float* dbeta, float* dbias, cudaStream_t st) {
+  SIMX_CHECK(H % 8 == 0 && H <= 256 * MAXC, SIMX_ERR_INVALID, "hidden size %d unsupported", H);
+  int grid = (T + ROW_WARPS - 1) / ROW_WARPS;
+  grid = min(grid, num_sms() * 4);
+  SIMX_NP_DISPATCH(np, (ln_bwd_kernel<kNP><<<grid, ROW_THREADS, 0, st>>>(dy, z, T, H, gamma, eps, dz, ps, dgamma, dbeta,
+                                                                         dbias)));
+  SIMX_LAUNCH_CHECK();
+  return SIMX_OK;
+}
+
+int colsum(int np, const bf16* x, long rows, int N, long row_stride, long ps, float* out, cudaStream_t st) {
+  SIMX_CHECK(N % 8 == 0, SIMX_ERR_INVALID, "colsum: N %% 8 != 0");
+  dim3 grid((N + 255) / 256, (unsigned)max(1L, min((rows + ROW_WARPS * 8 - 1) / (ROW_WARPS * 8), (long)num_sms() * 2)));
+  SIMX_NP_DISPATCH(np, (colsum_kernel<kNP><<<grid, ROW_THREADS, 0, st>>>(x, rows, N, row_stride, ps, out)));
+  SIMX_LAUNCH_CHECK();
+  return SIMX_OK;
+}
+
+int cls_gather(int np, const bf16* x, int B, int S, int H, long ps, float* out, long out_stride_b, cudaStream_t st) {
+  SIMX_NP_DISPATCH(np, (cls_gather_kernel<kNP><<<B, 128, 0, st>>>(x, B, S, H, ps, out, out_stride_b)));
+  SIMX_LAUNCH_CHECK();
+  return SIMX_OK;
+}
+int cls_scatter_add(int np, bf16* dx, int B, int S, int H, long ps, const float* d, long d_stride_b,
+                    cudaStream_t st) {
+  SIMX_NP_DISPATCH(np, (cls_scatter_add_kernel<kNP><<<B, 128, 0, st>>>(dx, B, S, H, ps, d, d_stride_b)));
+  SIMX_LAUNCH_CHECK();
+  return SIMX_OK;
+}
+int f32_to_planes(int np, const float* src, long n, bf16* dst, long ps, cudaStream_t st) {
+  SIMX_CHECK(n % 8 == 0, SIMX_ERR_INVALID, "f32_to_planes: n %% 8 != 0");
+  const int grid = (int)min((n / 8 + 255) / 256, (long)num_sms() * 8);
+  SIMX_NP_DISPATCH(np, (f32_to_planes_kernel<kNP><<<grid, 256, 0, st>>>(src, n, dst, ps)));
+  SIMX_LAUNCH_CHECK();
+  return SIMX_OK;
+}
+int planes_to_f32(int np, const bf16* src, long n, long ps, float* dst, cudaStream_t st) {
+  SIMX_CHECK(n % 8 == 0, SIMX_ERR_INVALID, "planes_to_f32: n %% 8 != 0");
+  const int grid = (int)min((n / 8 + 255) / 256, (long)num_sms() * 8);
+  SIMX_NP_DISPATCH(np, (planes_to_f32_kernel<kNP><<<grid, 256, 0, st>>>(src, n, ps, dst)));
+  SIMX_LAUNCH_CHECK();
+  return SIMX_OK;
+}
+int embed_scatter(int np, const int64_t* ids, const bf16* dz0, int T, int H, int vocab, long ps, float* dword,
+                  cudaStream_t st) {
+  const int grid = (T + ROW_WARPS - 1) / ROW_WARPS;
+  SIMX_NP_DISPATCH(np, (embed_scatter_kernel<kNP><<<grid, ROW_THREADS, 0, st>>>(ids, dz0, T, H, vocab, ps, dword)));
+  SIMX_LAUNCH_CHECK();
+  return SIMX_OK;
+}
+int convert_weight(int np, const float* w, int R, int C, bf16* dst, long ld_dst, long ps_dst, bf16* dst_t, long ld_t,
+                   long ps_t, cudaStream_t st) {
+  dim3 grid((C + 31) / 32, (R + 31) / 32), block(32, 8);
+  SIMX_NP_DISPATCH(np, (convert_weight_kernel<kNP><<<grid, block, 0, st>>>(w, R, C, dst, ld_dst, ps_dst, dst_t, ld_t,
+                                                                           ps_t)));
+  SIMX_LAUNCH_CHECK();
+  return SIMX_OK;
+}
+
+}  // namespace simx

@@ -1,0 +1,187 @@
+"""Score / loss / gradient step on libsimx_b200 (`simx_score_loss`) behind the reference's loss interfaces.
+
+  fused_score_loss(...)            the general entry: any sum of
+                                     nll_global  in-batch InfoNCE over all-gathered embeddings  (BiEncoderNllLoss.calc,
+                                                 /root/reference/SimANS/model/models.py:468-505; gathered as in
+                                                 /root/reference/MASTER/finetune/MS/run_de_model.py:180-234 and
+                                                 /root/reference/LEAD/util.py:200-204,416-451)
+                                     kl_local    SimANS KLDiv(log(softmax(s)+eps) || softmax(teacher/T))
+                                                 (/root/reference/SimANS/co_training/co_training_marco_train.py:199-214)
+                                     ce_local    -sum p_t log(p_s+eps)/B (wiki / MASTER / PROD prob_loss)
+                                     kd_local    PROD KD_softmax (/root/reference/PROD/ProD_KD/model/models.py:772-777)
+                                     nll_local   PROD hard loss, positive = column 0 (.../models.py:694-712)
+  BiEncoderNllLoss / CrossBERTKDLoss / simans_distill_loss   drop-in call signatures of the reference.
+
+The kernel returns the loss terms AND d(loss)/d(local embeddings) in the same pass; autograd only scales them by the
+incoming cotangent.  Cross-rank negatives: the local [CLS] embeddings are all-gathered with NCCL over NVLink
+(`dist.all_gather_into_tensor`), remote slices are constants, gradients reach the local rows/columns only.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional, Sequence
+
+import torch
+import torch.distributed as dist
+
+from . import _lib
+
+_TERMS = {"nll_global": _lib.LOSS_NLL_GLOBAL, "kl_local": _lib.LOSS_KL_LOCAL, "ce_local": _lib.LOSS_CE_LOCAL,
+          "kd_local": _lib.LOSS_KD_LOCAL, "nll_local": _lib.LOSS_NLL_LOCAL}
+LOSS_FIELDS = ("total", "nll_global", "kl_local", "ce_local", "kd_local", "nll_local", "n_correct")
+
+
+def gather_embeddings(local: torch.Tensor, group=None) -> torch.Tensor:
+    """[n, H] -> [world*n, H] (rank-major), every rank contributing the same n.  No autograd: gradients for the local
+    slice come from the fused kernel (the reference re-inserts the local tensor for the same effect, LEAD/util.py:200-204)."""
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+        return local
+    world = dist.get_world_size(group)
+    out = local.new_empty((world * local.shape[0],) + tuple(local.shape[1:]))
+    dist.all_gather_into_tensor(out, local.contiguous(), group=group)
+    return out
+
+
+class _ScoreLossFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, q_local, c_local, teacher, pos_idx, opts):
+        lib = _lib.lib()
+        dev = q_local.device
+        if dev.type != "cuda":
+            raise RuntimeError("fused_score_loss needs CUDA tensors (no CPU fallback)")
+        with torch.cuda.device(dev):
+            _lib.require_device()
+            q_local = q_local.detach().to(torch.float32).contiguous()
+            c_local = c_local.detach().to(torch.float32).contiguous()
+            nq, H = q_local.shape
+            nc = c_local.shape[0]
+            terms = 0
+            for t in opts["terms"]:
+                terms |= _TERMS[t]
+            use_global = bool(terms & _lib.LOSS_NLL_GLOBAL)
+            rank, world = 0, 1
+            if use_global and opts.get("gather", True) and dist.is_available() and dist.is_initialized():
+                rank, world = dist.get_rank(opts.get("group")), dist.get_world_size(opts.get("group"))
+            if world > 1:
+                Q = gather_embeddings(q_local, opts.get("group"))
+                Cm = gather_embeddings(c_local, opts.get("group"))
+            else:
+                Q, Cm = q_local, c_local
+            GQ, GC = Q.shape[0], Cm.shape[0]
+            group = opts.get("group_size") or (nc // nq)
+            w = opts.get("weights", {})
+            cfg = _lib.LossCfg(
+                terms=terms, GQ=GQ, GC=GC, H=H, q_begin=rank * nq, q_count=nq, c_begin=rank * nc, c_count=nc,
+                group=group, w_nll_global=w.get("nll_global", 1.0), w_kl_local=w.get("kl_local", 1.0),
+                w_ce_local=w.get("ce_local", 1.0), w_kd_local=w.get("kd_local", 1.0), w_nll_local=w.get("nll_local", 1.0),
+                temperature=opts.get("temperature", 1.0), eps=opts.get("eps", 1e-7),
+                score_scale=opts.get("score_scale", 1.0), grad_scale=1.0)
+            if use_global:
+                if pos_idx is None:
+                    pos_idx = torch.arange(0, GQ * group, group, device=dev, dtype=torch.int32)  # LEAD/util.py:445
+                pos_idx = pos_idx.to(device=dev, dtype=torch.int32).contiguous()
+                if pos_idx.numel() != GQ:
+                    raise ValueError(f"pos_idx has {pos_idx.numel()} entries for {GQ} global queries")
+            if teacher is not None:
+                teacher = teacher.detach().to(device=dev, dtype=torch.float32).contiguous()
+                if tuple(teacher.shape) != (nq, group):
+                    raise ValueError(f"teacher logits must be [{nq}, {group}], got {tuple(teacher.shape)}")
+            ws_bytes = lib.simx_score_loss_workspace_bytes(C.byref(cfg))
+            ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+            losses = torch.empty(8, dtype=torch.float32, device=dev)
+            dQ = torch.empty_like(q_local)
+            dC = torch.empty_like(c_local)
+            stream = torch.cuda.current_stream(dev).cuda_stream
+            _lib.check(lib.simx_score_loss(C.byref(cfg), Q.data_ptr(), Cm.data_ptr(), _lib.ptr(pos_idx), _lib.ptr(teacher),
+                                           losses.data_ptr(), dQ.data_ptr(), dC.data_ptr(), ws.data_ptr(), stream),
+                       "simx_score_loss")
+        ctx.save_for_backward(dQ, dC)
+        ctx.mark_non_differentiable(losses)
+        return losses[0].clone(), losses
+
+    @staticmethod
+    def backward(ctx, g_total, _g_losses):
+        dQ, dC = ctx.saved_tensors
+        return dQ * g_total, dC * g_total, None, None, None
+
+
+def fused_score_loss(q_local: torch.Tensor, c_local: torch.Tensor, terms: Sequence[str], *, teacher=None, pos_idx=None,
+                     weights: Optional[dict] = None, temperature: float = 1.0, eps: float = 1e-7,
+                     score_scale: float = 1.0, group_size: Optional[int] = None, gather: bool = True, group=None):
+    """-> (loss scalar with autograd into q_local / c_local, detail tensor [8] = LOSS_FIELDS + pad)"""
+    opts = dict(terms=tuple(terms), weights=dict(weights or {}), temperature=float(temperature), eps=float(eps),
+                score_scale=float(score_scale), group_size=group_size, gather=gather, group=group)
+    return _ScoreLossFn.apply(q_local, c_local, teacher, pos_idx, opts)
+
+
+# ---------------------------------------------------------------------------------------------------------
+# reference-shaped wrappers
+# ---------------------------------------------------------------------------------------------------------
+class BiEncoderNllLoss(object):
+    """SimANS/model/models.py:468-514 (identical class in MASTER / PROD / CAPSTONE).  q_vectors / ctx_vectors are the
+    ALREADY-GATHERED global embeddings in the reference's call sites (run_de_model.py:180-234), so no gather here."""
+
+    def calc(self, q_vectors, ctx_vectors, positive_idx_per_question: list, hard_negative_idx_per_question: list = None,
+             loss_scale: float = None):
+        pos = torch.as_tensor(positive_idx_per_question, dtype=torch.int32, device=q_vectors.device)
+        loss, detail = fused_score_loss(q_vectors, ctx_vectors, ["nll_global"], pos_idx=pos, gather=False,
+                                        group_size=max(1, ctx_vectors.shape[0] // q_vectors.shape[0]))
+        correct_predictions_count = detail[6].round().to(torch.int64)
+        if loss_scale:
+            loss = loss * loss_scale
+        return loss, correct_predictions_count
+
+    @staticmethod
+    def get_scores(q_vector, ctx_vectors):
+        return torch.matmul(q_vector, torch.transpose(ctx_vectors, 0, 1))
+
+    @staticmethod
+    def get_similarity_function():
+        return BiEncoderNllLoss.get_scores
+
+
+class CrossBERTKDLoss(object):
+    """PROD/ProD_KD/model/models.py:668-781: CE_WEIGHT * NLL(column 0) + KD_WEIGHT * soft [+ LwF_WEIGHT * LwF] on the
+    query's own [1+n] block.  KD_type 'KD_softmax' and 'prob_loss' run fused; LwF adds a second fused call against the
+    frozen student's scores."""
+
+    def calc(self, args, q_vectors, ctx_vectors, relevance_logits, hard_negative_idx_per_question: list = None,
+             loss_scale: float = None, LwF=False, ori_q_vector=None, ori_ctx_vectors=None):
+        nq = q_vectors.shape[0]
+        group = ctx_vectors.shape[0] // nq
+        if relevance_logits is None:
+            loss, detail = fused_score_loss(q_vectors, ctx_vectors, ["nll_local"], group_size=group, gather=False)
+        elif args.KD_type == "KD_softmax":
+            loss, detail = fused_score_loss(q_vectors, ctx_vectors, ["nll_local", "kd_local"], teacher=relevance_logits,
+                                            weights=dict(nll_local=args.CE_WEIGHT, kd_local=args.KD_WEIGHT),
+                                            temperature=args.TEMPERATURE, group_size=group, gather=False)
+        elif args.KD_type == "prob_loss":
+            loss, detail = fused_score_loss(q_vectors, ctx_vectors, ["nll_local", "ce_local"], teacher=relevance_logits,
+                                            weights=dict(nll_local=args.CE_WEIGHT, ce_local=args.KD_WEIGHT),
+                                            temperature=args.TEMPERATURE, group_size=group, gather=False)
+        else:
+            raise NotImplementedError(f"KD_type={args.KD_type!r}: fused kernel covers KD_softmax and prob_loss")
+        if LwF:
+            with torch.no_grad():
+                ori = torch.einsum("bh,bdh->bd", ori_q_vector.float(), ori_ctx_vectors.float().reshape(nq, group, -1))
+            lwf, _ = fused_score_loss(q_vectors, ctx_vectors, ["kd_local"], teacher=ori, temperature=args.TEMPERATURE,
+                                      group_size=group, gather=False)
+            loss = loss + args.LwF_WEIGHT * lwf
+        # arg-max of the local row == column 0  <=>  positive ranked first
+        with torch.no_grad():
+            s = torch.einsum("bh,bdh->bd", q_vectors.float(), ctx_vectors.float().reshape(nq, group, -1))
+            correct_predictions_count = (s.argmax(1) == 0).sum()
+        if loss_scale:
+            loss = loss * loss_scale
+        return loss, correct_predictions_count
+
+
+def simans_distill_loss(local_q_vector, local_ctx_vectors, relevance_logits, temperature_distill: float = 1.0,
+                        eps: float = 1e-7, scale_simmila: bool = False):
+    """The retriever step's loss, co_training_marco_train.py:199-214, as one fused kernel call."""
+    nq = local_q_vector.shape[0]
+    scale = 1.0 / (local_q_vector.shape[1] ** 0.5) if scale_simmila else 1.0
+    loss, _ = fused_score_loss(local_q_vector, local_ctx_vectors, ["kl_local"], teacher=relevance_logits,
+                               temperature=temperature_distill, eps=eps, score_scale=scale,
+                               group_size=local_ctx_vectors.shape[0] // nq, gather=False)
+    return loss

@@ -1,0 +1,294 @@
+"""Drop-in replacement for the reference's `model/models.py` on the dual-encoder hot path.
+
+Same class names, constructor arguments, attributes, call signatures, return values and `state_dict` layout as
+/root/reference/SimANS/model/models.py (HFBertEncoder :58-82, BiBertEncoder :85-160, Reranker :638-659,
+BiEncoderNllLoss :468-514) and /root/reference/PROD/ProD_KD/model/models.py (HFBertEncoder :13-82 with
+`role=` layer truncation, BiBertEncoder :208-298, CrossBERTKDLoss :668-781) — but every encoder forward/backward runs
+on the sm_100a kernels of libsimx_b200.  A driver switches with one import line:
+
+    from simxns_b200.models import BiBertEncoder, HFBertEncoder, Reranker, BiEncoderNllLoss
+
+There is no PyTorch/CPU fallback: parameters must live on a B200 before forward() is called.
+"""
+from __future__ import annotations
+
+import json
+import os
+from pathlib import Path
+from types import SimpleNamespace
+from typing import Optional
+
+import torch
+import torch.nn.functional as F
+from torch import Tensor as T
+from torch import nn
+
+from .encoder import B200EncoderBase, EncoderConfig
+from .losses import BiEncoderNllLoss, CrossBERTKDLoss, simans_distill_loss  # noqa: F401  (re-exported: reference names)
+
+__all__ = ["HFBertEncoder", "HFDistilBertEncoder", "BiBertEncoder", "Reranker", "BiEncoderNllLoss", "CrossBERTKDLoss",
+           "simans_distill_loss", "dot_product_scores", "init_weights"]
+
+
+# ---------------------------------------------------------------------------------------------------------
+# configuration / checkpoint helpers (stand in for transformers' from_pretrained on local files)
+# ---------------------------------------------------------------------------------------------------------
+def _load_hf_config(model_type, arch="bert"):
+    """BertConfig.from_pretrained(model_type) as the reference does (SimANS/model/models.py:69); works for local
+    directories and anything in the HF cache.  Without `transformers` only a local config.json is read."""
+    try:
+        import transformers
+
+        cls = transformers.DistilBertConfig if arch == "distilbert" else transformers.BertConfig
+        return cls.from_pretrained(model_type)
+    except ImportError:
+        with open(Path(model_type) / "config.json") as f:
+            return SimpleNamespace(**json.load(f))
+
+
+def _find_weights(model_type) -> Optional[dict]:
+    """state dict of a local HF checkpoint directory / HF-cache entry (pytorch_model.bin or model.safetensors)"""
+    cands = []
+    p = Path(str(model_type))
+    if p.is_dir():
+        cands = [p / "model.safetensors", p / "pytorch_model.bin"]
+    else:
+        try:
+            from transformers.utils import cached_file
+
+            for name in ("model.safetensors", "pytorch_model.bin"):
+                try:
+                    f = cached_file(str(model_type), name)
+                    if f:
+                        cands.append(Path(f))
+                except Exception:
+                    pass
+        except ImportError:
+            pass
+    for f in cands:
+        if f.exists():
+            if f.suffix == ".safetensors":
+                from safetensors.torch import load_file
+
+                return load_file(str(f))
+            return torch.load(str(f), map_location="cpu", weights_only=True)
+    return None
+
+
+def _strip_prefix(sd: dict, own_keys) -> dict:
+    """HF checkpoints store the encoder under `bert.` / `distilbert.` (task heads) or at top level"""
+    own = set(own_keys)
+    out = {}
+    for k, v in sd.items():
+        for pre in ("", "bert.", "distilbert.", "encoder.bert.", "model."):
+            if k.startswith(pre) and k[len(pre):] in own:
+                out[k[len(pre):]] = v
+                break
+    return out
+
+
+def init_weights(modules):
+    """SimANS/model/models.py:457-466"""
+    for module in modules:
+        if isinstance(module, (nn.Linear, nn.Embedding)):
+            module.weight.data.normal_(mean=0.0, std=0.02)
+        elif isinstance(module, nn.LayerNorm):
+            module.bias.data.zero_()
+            module.weight.data.fill_(1.0)
+        if isinstance(module, nn.Linear) and module.bias is not None:
+            module.bias.data.zero_()
+
+
+def dot_product_scores(q_vectors, ctx_vectors):
+    """SimANS/model/models.py:564-572"""
+    return torch.matmul(q_vectors, torch.transpose(ctx_vectors, 0, 1))
+
+
+# ---------------------------------------------------------------------------------------------------------
+class HFBertEncoder(B200EncoderBase):
+    """BERT tower.  `HFBertEncoder(config)` builds a randomly initialised model from an HF BertConfig (or an
+    EncoderConfig); `HFBertEncoder.init_encoder(args, dropout, model_type)` mirrors the reference classmethod.
+
+    forward(input_ids=, attention_mask=) -> (sequence_output [B,S,H], pooled_output [B,H], None) where
+    pooled_output = sequence_output[:, 0, :] (the reference multiplies BertPooler's output by 0 — its parameters
+    exist, are saved in state_dict and receive zero gradients: SimANS/model/models.py:77-82)."""
+
+    def __init__(self, config, precision: Optional[int] = None):
+        enc_cfg = config if isinstance(config, EncoderConfig) else EncoderConfig.from_hf(config)
+        assert enc_cfg.hidden > 0, "Encoder hidden_size can't be zero"
+        super().__init__(enc_cfg, precision)
+        if isinstance(config, EncoderConfig):
+            config = SimpleNamespace(hidden_size=enc_cfg.hidden, num_hidden_layers=enc_cfg.num_layers,
+                                     num_attention_heads=enc_cfg.heads, intermediate_size=enc_cfg.intermediate,
+                                     vocab_size=enc_cfg.vocab, max_position_embeddings=enc_cfg.max_pos,
+                                     type_vocab_size=enc_cfg.type_vocab, layer_norm_eps=enc_cfg.ln_eps,
+                                     hidden_dropout_prob=0.0, attention_probs_dropout_prob=0.0)
+        self.config = config
+        try:
+            import transformers
+
+            self.version = int(transformers.__version__.split('.')[0])
+        except ImportError:
+            self.version = 4
+        p_drop = max(float(getattr(config, "hidden_dropout_prob", 0.0) or 0.0),
+                     float(getattr(config, "attention_probs_dropout_prob", 0.0) or 0.0))
+        self.dropout_requested = p_drop  # kernels run the dropout-free (parity / eval) configuration, SURVEY D9
+
+    # -- reference constructor path -----------------------------------------------------------------------
+    @classmethod
+    def init_encoder(cls, args, dropout: float = 0.1, model_type=None, role: Optional[str] = None):
+        if model_type is None:
+            model_type = getattr(args, "model_type", None) or getattr(args, "pretrained_model_name", None)
+        cfg = _load_hf_config(model_type, "bert")
+        if dropout != 0:
+            cfg.attention_probs_dropout_prob = dropout
+            cfg.hidden_dropout_prob = dropout
+        cfg.gradient_checkpointing = getattr(args, "gradient_checkpointing", False)
+        # PROD: layer-truncated student / teacher (PROD/ProD_KD/model/models.py:22-40)
+        if role == "student" and getattr(args, "student_num_hidden_layers", None):
+            cfg.num_hidden_layers = args.student_num_hidden_layers
+        if role == "teacher" and getattr(args, "teacher_num_hidden_layers", None):
+            cfg.num_hidden_layers = args.teacher_num_hidden_layers
+        return cls.from_pretrained(model_type, config=cfg)
+
+    @classmethod
+    def from_pretrained(cls, model_type, config=None, **_):
+        if config is None:
+            config = _load_hf_config(model_type, "bert")
+        model = cls(config)
+        sd = _find_weights(model_type)
+        if sd is None:
+            raise FileNotFoundError(f"no pytorch_model.bin / model.safetensors found for {model_type!r}")
+        own = model.state_dict().keys()
+        missing, unexpected = model.load_state_dict(_strip_prefix(sd, own), strict=False)
+        if any("pooler" not in m for m in missing):
+            raise RuntimeError(f"checkpoint {model_type!r} lacks encoder weights: {missing[:5]} ...")
+        return model
+
+    def init_weights(self):
+        from .encoder import _hf_init_
+
+        _hf_init_(self, self.enc_cfg.init_range)
+
+    def get_input_embeddings(self):
+        return self.embeddings.word_embeddings
+
+    def gradient_checkpointing_enable(self, *a, **k):  # CAPSTONE/models/modules.py:54 calls this; accepted no-op
+        return None
+
+    def load_state_dict(self, state_dict, strict: bool = True, **kw):
+        # old HF versions persisted buffers (`embeddings.position_ids`, `token_type_ids`): ignore them as the
+        # reference's strict=False loads do (co_training_marco_train.py:355)
+        state_dict = {k: v for k, v in state_dict.items()
+                      if not k.endswith("embeddings.position_ids") and not k.endswith("embeddings.token_type_ids")}
+        return super().load_state_dict(state_dict, strict=strict, **kw)
+
+    # -- reference forward ----------------------------------------------------------------------------------
+    def forward(self, input_ids=None, attention_mask=None, token_type_ids=None, inputs_embeds=None,
+                output_attentions=None, output_hidden_states=None, _want_sequence: bool = True, **kwargs):
+        if inputs_embeds is not None:
+            raise NotImplementedError("inputs_embeds is not supported by the B200 encoder "
+                                      "(only reached from the dead forward_adv_* paths of the reference)")
+        if token_type_ids is not None and bool((token_type_ids != 0).any()):
+            raise NotImplementedError("non-zero token_type_ids: the reference never passes segment ids "
+                                      "(SimANS/model/models.py:654 'TODO: provide segment values')")
+        if output_attentions:
+            raise NotImplementedError("attention maps are never materialised by the fused attention kernel")
+        cls, seq = self.encode(input_ids, attention_mask, want_sequence=_want_sequence)
+        pooled_output = cls[:, -1, :]
+        self.last_cls_layers = cls  # [B, L+1, H]; per-layer [CLS] rows (LEAD-style consumers)
+        return seq, pooled_output, None
+
+
+class HFDistilBertEncoder(HFBertEncoder):
+    """6-layer DistilBERT student of LEAD (LEAD/models.py:31-77, LEAD/modeling_distilbert.py)."""
+
+    def __init__(self, config, precision: Optional[int] = None):
+        enc_cfg = config if isinstance(config, EncoderConfig) else EncoderConfig.from_hf(config)
+        if enc_cfg.arch != "distilbert":
+            raise ValueError("HFDistilBertEncoder needs a DistilBertConfig")
+        B200EncoderBase.__init__(self, enc_cfg, precision)
+        self.config = config if not isinstance(config, EncoderConfig) else SimpleNamespace(
+            hidden_size=enc_cfg.hidden, dim=enc_cfg.hidden, n_layers=enc_cfg.num_layers)
+        if not hasattr(self.config, "hidden_size"):
+            self.config.hidden_size = enc_cfg.hidden
+        self.version = 4
+        self.dropout_requested = 0.0
+
+    @classmethod
+    def init_encoder(cls, args, dropout: float = 0.1, pretrained_model_name=None):
+        name = pretrained_model_name or getattr(args, "pretrained_model_name", None)
+        cfg = _load_hf_config(name, "distilbert")
+        model = cls(cfg)
+        sd = _find_weights(name)
+        if sd is None:
+            raise FileNotFoundError(f"no weights found for {name!r}")
+        model.load_state_dict(_strip_prefix(sd, model.state_dict().keys()), strict=False)
+        return model
+
+
+class BiBertEncoder(nn.Module):
+    """Bi-Encoder model component. Encapsulates query/question and context/passage encoders.
+    (SimANS/model/models.py:85-118; PROD passes role='student'/'teacher', PROD/ProD_KD/model/models.py:208-256)"""
+
+    def __init__(self, args, role: Optional[str] = None, question_model: Optional[nn.Module] = None,
+                 ctx_model: Optional[nn.Module] = None):
+        super().__init__()
+        if question_model is not None:  # explicit towers (tests, random-init benchmarks)
+            self.question_model = question_model
+            self.ctx_model = ctx_model if ctx_model is not None else question_model
+            return
+        self.question_model = HFBertEncoder.init_encoder(args, role=role)
+        if hasattr(args, 'share_weight') and args.share_weight:
+            self.ctx_model = self.question_model
+        else:
+            self.ctx_model = HFBertEncoder.init_encoder(args, role=role)
+
+    def query_emb(self, input_ids, attention_mask):
+        _, pooled_output, _ = self.question_model(input_ids=input_ids, attention_mask=attention_mask,
+                                                  _want_sequence=False)
+        return pooled_output
+
+    def body_emb(self, input_ids, attention_mask):
+        _, pooled_output, _ = self.ctx_model(input_ids=input_ids, attention_mask=attention_mask, _want_sequence=False)
+        return pooled_output
+
+    def forward(self, query_ids, attention_mask_q, input_ids_a=None, attention_mask_a=None, input_ids_b=None,
+                attention_mask_b=None):
+        if input_ids_b is None:
+            q_embs = self.query_emb(query_ids, attention_mask_q)
+            a_embs = self.body_emb(input_ids_a, attention_mask_a)
+            return (q_embs, a_embs)
+        q_embs = self.query_emb(query_ids, attention_mask_q)
+        a_embs = self.body_emb(input_ids_a, attention_mask_a)
+        b_embs = self.body_emb(input_ids_b, attention_mask_b)
+        logit_matrix = torch.cat([(q_embs * a_embs).sum(-1).unsqueeze(1), (q_embs * b_embs).sum(-1).unsqueeze(1)],
+                                 dim=1)  # [B, 2]
+        lsm = F.log_softmax(logit_matrix, dim=1)
+        loss = -1.0 * lsm[:, 0]
+        return (loss.mean(),)
+
+    def forward_adv_triplet(self, *a, **k):
+        raise NotImplementedError("forward_adv_* take inputs_embeds and are unreachable from the reference drivers")
+
+    forward_adv_pairloss = forward_adv_triplet
+    forward_adv_pairloss_mse = forward_adv_triplet
+
+
+class Reranker(nn.Module):
+    """cross-encoder teacher: encoder + Linear(H,1) on [CLS] (SimANS/model/models.py:638-659)"""
+
+    def __init__(self, encoder: nn.Module, hidden_size):
+        super().__init__()
+        self.encoder = encoder
+        self.qa_classifier = nn.Linear(hidden_size, 1)
+
+    def forward(self, input_ids: T, attention_mask: T):
+        # N - number of questions in a batch, M - number of passages per question, L - sequence length
+        N, M, L = input_ids.size()
+        relevance_logits = self._forward(input_ids.view(N * M, L), attention_mask.view(N * M, L))
+        return relevance_logits.view(N, M)
+
+    def _forward(self, input_ids, attention_mask):
+        _, pooled, _ = self.encoder(input_ids=input_ids, attention_mask=attention_mask, _want_sequence=False)
+        return self.qa_classifier(pooled)  # == qa_classifier(sequence_output[:, 0, :])
