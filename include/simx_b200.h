@@ -56,6 +56,12 @@ int simx_version(void);
 /* 1 when the current CUDA device can run the kernels (compute capability 10.x), else 0. */
 int simx_device_supported(void);
 
+/* Per-launch device timing for bench.py's roofline lines: between begin and end every kernel wrapper records CUDA
+ * events on its launching stream; end synchronises and writes a JSON array aggregated by kernel label:
+ * [{"name","launches","ms","flops","bytes"}] (algorithmic FLOPs / bytes as stated in DESIGN.md). */
+int simx_profile_begin(void);
+int simx_profile_end(char* json_buf, size_t capacity);
+
 /* ------------------------------------------------------------------------------------------------
  * Parameter table.  `params` / offsets use this canonical order (fp32 tensors, HF state_dict names):
  *   BERT:  0 word_embeddings [V,H]  1 position_embeddings [P,H]  2 token_type_embeddings [Tt,H]
@@ -146,9 +152,10 @@ int simx_score_loss(const simx_loss_cfg* cfg, const float* Q, const float* C, co
  * ---------------------------------------------------------------------------------------------- */
 #define SIMX_EPI_PLAIN 0     /* out = acc */
 #define SIMX_EPI_BIAS 1      /* out = acc + bias[n]                                   (QKV projection) */
-#define SIMX_EPI_BIAS_GELU 2 /* out = acc + bias[n]; out2 = gelu_erf(out)             (BertIntermediate) */
+#define SIMX_EPI_BIAS_GELU 2 /* h = acc + bias[n]; out = gelu_erf'(h); out2 = gelu_erf(h) (BertIntermediate; out is what
+                                backward multiplies by, the pre-activation itself is never needed again) */
 #define SIMX_EPI_BIAS_ADD 3  /* out = acc + bias[n] + aux[m,n]                        (BertSelfOutput/BertOutput pre-LN) */
-#define SIMX_EPI_DGELU 4     /* out = acc * gelu_erf'(aux[m,n])                       (dgrad through GELU) */
+#define SIMX_EPI_MUL 4       /* out = acc * aux[m,n]                                  (dgrad through GELU: aux = saved gelu') */
 #define SIMX_EPI_ADD 5       /* out = acc + aux[m,n]                                  (dgrad + residual grad) */
 #define SIMX_EPI_ATOMIC_F32 6 /* outf[m,n] += acc   (fp32 atomics; split-K wgrad)     */
 

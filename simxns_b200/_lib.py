@@ -18,7 +18,7 @@ SIMX_OK = 0
 ARCH_BERT, ARCH_DISTILBERT = 0, 1
 PREC_BF16, PREC_BF16X3 = 1, 3
 
-EPI_PLAIN, EPI_BIAS, EPI_BIAS_GELU, EPI_BIAS_ADD, EPI_DGELU, EPI_ADD, EPI_ATOMIC_F32 = range(7)
+EPI_PLAIN, EPI_BIAS, EPI_BIAS_GELU, EPI_BIAS_ADD, EPI_MUL, EPI_ADD, EPI_ATOMIC_F32 = range(7)
 
 LOSS_NLL_GLOBAL, LOSS_KL_LOCAL, LOSS_CE_LOCAL, LOSS_KD_LOCAL, LOSS_NLL_LOCAL = 1, 2, 4, 8, 16
 
@@ -76,6 +76,8 @@ SIGNATURES = {
     "simx_last_error": (C.c_char_p, []),
     "simx_version": (_I, []),
     "simx_device_supported": (_I, []),
+    "simx_profile_begin": (_I, []),
+    "simx_profile_end": (_I, [C.c_char_p, C.c_size_t]),
     "simx_encoder_num_params": (_I, [_CFG]),
     "simx_encoder_param_numel": (_L, [_CFG, _I]),
     "simx_encoder_grad_offset": (_L, [_CFG, _I]),
@@ -140,6 +142,19 @@ def require_device() -> None:
     """Fail loudly unless the current CUDA device can run the sm_100a kernels."""
     if not lib().simx_device_supported():
         raise RuntimeError("libsimx_b200 needs an sm_100 (B200) CUDA device; none is current. No fallback exists.")
+
+
+def profile_begin() -> None:
+    check(lib().simx_profile_begin(), "simx_profile_begin")
+
+
+def profile_end() -> list:
+    """-> [{"name", "launches", "ms", "flops", "bytes"}] aggregated per kernel label since profile_begin()"""
+    import json
+
+    buf = C.create_string_buffer(1 << 16)
+    check(lib().simx_profile_end(buf, len(buf)), "simx_profile_end")
+    return json.loads(buf.value.decode())
 
 
 def ptr(t) -> int:

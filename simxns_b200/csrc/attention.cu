@@ -512,6 +512,7 @@ static int attn_check(int B, int S, int H, int heads) {
 int attention_forward(int np, const bf16* qkv, long ps_qkv, bf16* ctx, long ps_ctx, const int64_t* mask, float* lse2,
                       int B, int S, int H, int heads, cudaStream_t st) {
   SIMX_TRY(attn_check(B, S, H, heads));
+  ProfScope prof("attn_fwd", 4.0 * B * heads * (double)S * S * ATT_D, 2.0 * np * B * (double)S * 4 * H, st);
   if (np == 3) {
     AttnRefParams p{qkv, ctx, nullptr, nullptr, mask, lse2, nullptr, ps_qkv, ps_ctx, B, S, H, heads};
     dim3 grid((S + 127) / 128, heads, B);
@@ -536,6 +537,7 @@ int attention_backward(int np, const bf16* qkv, long ps_qkv, const bf16* ctx, co
                        const int64_t* mask, const float* lse2, float* delta, int B, int S, int H, int heads,
                        cudaStream_t st) {
   SIMX_TRY(attn_check(B, S, H, heads));
+  ProfScope prof("attn_bwd", 10.0 * B * heads * (double)S * S * ATT_D, 2.0 * np * B * (double)S * 8 * H, st);
   if (np == 3) {
     AttnRefParams p{qkv, const_cast<bf16*>(ctx), dctx, dqkv, mask, const_cast<float*>(lse2), delta, ps_qkv, ps_ctx,
                     B, S, H, heads};

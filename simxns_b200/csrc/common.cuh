@@ -47,6 +47,18 @@ void set_error(const char* fmt, ...);
 int num_sms();  // cached cudaDevAttrMultiProcessorCount of the current device
 
 // ---------------------------------------------------------------------------------------------
+// optional per-launch timing (simx_profile_begin / simx_profile_end): CUDA events recorded on the launching stream
+// around every kernel wrapper, aggregated by label.  Off by default; costs nothing when off.
+// ---------------------------------------------------------------------------------------------
+void prof_label(const char* label);  // label for the next wrapper call(s) on this thread (nullptr = wrapper default)
+struct ProfScope {
+  ProfScope(const char* default_name, double flops, double bytes, cudaStream_t st);
+  ~ProfScope();
+  int slot;
+  cudaStream_t st;
+};
+
+// ---------------------------------------------------------------------------------------------
 // Activation tensors.  Every activation is NP bf16 "planes" of the same [rows, cols] shape, plane p at
 // ptr + p * plane_stride.  NP == 1: plain bf16 (throughput mode).  NP == 3: value = hi + mid + lo with
 // hi = bf16(v), mid = bf16(v - hi), lo = bf16(v - hi - mid)  -> 24 significant bits, i.e. fp32-class storage;

@@ -8,7 +8,7 @@
 //   ctx = softmax(q k^T/8 + m) v  attention kernel, saves lse            [T,H]
 //   z1  = ctx Wo^T + b + x        GEMM, BIAS_ADD epilogue                [T,H]
 //   x1  = LN(z1)                  row kernel                             [T,H]
-//   h   = x1 W1^T + b ; a=gelu(h) GEMM, BIAS_GELU epilogue (two outputs) [T,I] x2
+//   g'  = gelu'(x1 W1^T + b) ; a = gelu(.)  GEMM, BIAS_GELU epilogue (two outputs; g' is all backward needs) [T,I] x2
 //   z2  = a W2^T + b + x1         GEMM, BIAS_ADD epilogue                [T,H]
 //   out = LN(z2)                                                         [T,H]
 // backward mirrors it: LN-bwd (also yields the bias gradient of the GEMM before it), dgrad GEMMs against the
@@ -332,16 +332,24 @@ extern "C" int simx_encoder_forward(const simx_encoder_cfg* cfg, const float* co
     bf16* z2 = reinterpret_cast<bf16*>(lbuf(l, sl.l_z2));
     float* lse = reinterpret_cast<float*>(lbuf(l, sl.l_lse));
 
+    prof_label("qkv_fwd");
     SIMX_TRY(gemm(T, 3 * H, H, x, H, psH, false, wqkv, H, 3L * H * H, false, np, SIMX_EPI_BIAS, bqkv, nullptr, 0, 0, qkv,
                   nullptr, 3 * H, ps3H, nullptr, 0, 1, st));
+    prof_label(nullptr);
     SIMX_TRY(attention_forward(np, qkv, ps3H, ctx, psH, mask, lse, B, S, H, cfg->heads, st));
+    prof_label("attnout_fwd");
     SIMX_TRY(gemm(T, H, H, ctx, H, psH, false, wo, H, (long)H * H, false, np, SIMX_EPI_BIAS_ADD, P[7], x, H, psH, z1,
                   nullptr, H, psH, nullptr, 0, 1, st));
+    prof_label(nullptr);
     SIMX_TRY(ln_fwd(np, z1, T, H, P[8], P[9], cfg->ln_eps, x1, psH, st));
+    prof_label("ffn1_fwd");
     SIMX_TRY(gemm(T, I, H, x1, H, psH, false, w1, H, (long)I * H, false, np, SIMX_EPI_BIAS_GELU, P[11], nullptr, 0, 0, h, a,
                   I, psI, nullptr, 0, 1, st));
+    prof_label(nullptr);
+    prof_label("ffn2_fwd");
     SIMX_TRY(gemm(T, H, I, a, I, psI, false, w2, I, (long)I * H, false, np, SIMX_EPI_BIAS_ADD, P[13], x1, H, psH, z2,
                   nullptr, H, psH, nullptr, 0, 1, st));
+    prof_label(nullptr);
     SIMX_TRY(ln_fwd(np, z2, T, H, P[14], P[15], cfg->ln_eps, xo, psH, st));
     if (cls_out) SIMX_TRY(cls_gather(np, xo, B, S, H, psH, cls_out + (long)(l + 1) * H, cls_stride_b, st));
   }
@@ -406,34 +414,50 @@ extern "C" int simx_encoder_backward(const simx_encoder_cfg* cfg, const float* c
     // output LayerNorm -> dz2 (= d ffn-out = d residual x1), dgamma/dbeta, and db2 = colsum(dz2)
     SIMX_TRY(ln_bwd(np, dx, z2, T, H, P[14], cfg->ln_eps, dza, psH, G(pi + 14), G(pi + 15), G(pi + 13), st));
     // dW2 [H,I] += dz2^T a
+    prof_label("ffn2_wgrad");
     SIMX_TRY(gemm(H, I, T, dza, H, psH, true, a, I, psI, true, np, SIMX_EPI_ATOMIC_F32, nullptr, nullptr, 0, 0, nullptr,
                   nullptr, 0, 0, G(pi + 12), I, wgrad_ksplit(H, I, T), st));
-    // dh = (dz2 W2) o gelu'(h)
-    SIMX_TRY(gemm(T, I, H, dza, H, psH, false, w2T, H, (long)I * H, false, np, SIMX_EPI_DGELU, nullptr, h, I, psI, dh,
+    prof_label(nullptr);
+    // dh = (dz2 W2) o gelu'(pre-activation)   (the forward epilogue saved gelu' in the `h` slot)
+    prof_label("ffn2_dgrad");
+    SIMX_TRY(gemm(T, I, H, dza, H, psH, false, w2T, H, (long)I * H, false, np, SIMX_EPI_MUL, nullptr, h, I, psI, dh,
                   nullptr, I, psI, nullptr, 0, 1, st));
+    prof_label(nullptr);
     SIMX_TRY(colsum(np, dh, T, I, I, psI, G(pi + 11), st));
     // dW1 [I,H] += dh^T x1
+    prof_label("ffn1_wgrad");
     SIMX_TRY(gemm(I, H, T, dh, I, psI, true, x1, H, psH, true, np, SIMX_EPI_ATOMIC_F32, nullptr, nullptr, 0, 0, nullptr,
                   nullptr, 0, 0, G(pi + 10), H, wgrad_ksplit(I, H, T), st));
+    prof_label(nullptr);
     // dx1 = dh W1 + dz2
+    prof_label("ffn1_dgrad");
     SIMX_TRY(gemm(T, H, I, dh, I, psI, false, w1T, I, (long)I * H, false, np, SIMX_EPI_ADD, nullptr, dza, H, psH, dxb,
                   nullptr, H, psH, nullptr, 0, 1, st));
+    prof_label(nullptr);
     // attention-output LayerNorm -> dz1, and dbo = colsum(dz1)
     SIMX_TRY(ln_bwd(np, dxb, z1, T, H, P[8], cfg->ln_eps, dza, psH, G(pi + 8), G(pi + 9), G(pi + 7), st));
     // dWo [H,H] += dz1^T ctx
+    prof_label("attnout_wgrad");
     SIMX_TRY(gemm(H, H, T, dza, H, psH, true, ctx, H, psH, true, np, SIMX_EPI_ATOMIC_F32, nullptr, nullptr, 0, 0, nullptr,
                   nullptr, 0, 0, G(pi + 6), H, wgrad_ksplit(H, H, T), st));
+    prof_label(nullptr);
     // dctx = dz1 Wo
+    prof_label("attnout_dgrad");
     SIMX_TRY(gemm(T, H, H, dza, H, psH, false, woT, H, (long)H * H, false, np, SIMX_EPI_PLAIN, nullptr, nullptr, 0, 0, dxb,
                   nullptr, H, psH, nullptr, 0, 1, st));
+    prof_label(nullptr);
     SIMX_TRY(attention_backward(np, qkv, ps3H, ctx, dxb, psH, dqkv, mask, lse, delta, B, S, H, cfg->heads, st));
     // fused q/k/v bias and weight gradients ([3H] and [3H,H] blocks of the flat gradient buffer)
     SIMX_TRY(colsum(np, dqkv, T, 3 * H, 3 * H, ps3H, G(pi + 1), st));
+    prof_label("qkv_wgrad");
     SIMX_TRY(gemm(3 * H, H, T, dqkv, 3 * H, ps3H, true, x, H, psH, true, np, SIMX_EPI_ATOMIC_F32, nullptr, nullptr, 0, 0,
                   nullptr, nullptr, 0, 0, G(pi + 0), H, wgrad_ksplit(3 * H, H, T), st));
+    prof_label(nullptr);
     // dx(layer input) = dqkv Wqkv + dz1   (+ the [CLS] cotangent LEAD injects at this depth)
+    prof_label("qkv_dgrad");
     SIMX_TRY(gemm(T, H, 3 * H, dqkv, 3 * H, ps3H, false, wqkvT, 3 * H, 3L * H * H, false, np, SIMX_EPI_ADD, nullptr, dza, H,
                   psH, dx, nullptr, H, psH, nullptr, 0, 1, st));
+    prof_label(nullptr);
     if (d_cls) SIMX_TRY(cls_scatter_add(np, dx, B, S, H, psH, d_cls + (long)l * H, cls_stride_b, st));
   }
   // embeddings

@@ -3,7 +3,7 @@
 //   warp 0      : TMA producer   (cp.async.bulk.tensor, 128B-swizzled tiles, 4-stage mbarrier ring)
 //   warp 1      : MMA issuer     (one thread, tcgen05.mma kind::f16 128xBNx16, fp32 accumulator in TMEM)
 //   warp 2      : TMEM allocator
-//   warps 4..7  : epilogue       (tcgen05.ld -> registers -> bias / GELU / residual / gelu' -> global)
+//   warps 4..11 : epilogue       (tcgen05.ld -> registers -> bias / GELU+GELU' / residual / multiply -> global)
 //   TMEM holds two accumulators, so the epilogue of tile i overlaps the MMAs of tile i+1.
 //
 // Both operands may be K-major (activations x nn.Linear weights, the "TN" case of every forward and dgrad GEMM:
@@ -17,7 +17,7 @@ namespace simx {
 
 constexpr int GEMM_BM = 128;
 constexpr int GEMM_BK = 64;
-constexpr int GEMM_THREADS = 256;
+constexpr int GEMM_THREADS = 384;  // 4 control warps + 8 epilogue warps
 
 struct GemmParams {
   int M, N, K;
@@ -46,8 +46,62 @@ struct GemmSmem {
   static constexpr uint32_t TOTAL = BAR_OFF + 256 + 1024;  // barriers + alignment slack
 };
 
+// operands the epilogue fetches from global memory for one 32-column chunk; issued BEFORE the TMEM wait so their
+// latency overlaps the tcgen05.ld in flight
 template <int EPI, int NP>
-__device__ __forceinline__ void epilogue_chunk(const GemmParams& p, int row, int col0, const uint32_t (&acc)[32]) {
+struct EpiPre {
+  static constexpr bool kBias = EPI == SIMX_EPI_BIAS || EPI == SIMX_EPI_BIAS_GELU || EPI == SIMX_EPI_BIAS_ADD;
+  static constexpr bool kAux = EPI == SIMX_EPI_BIAS_ADD || EPI == SIMX_EPI_ADD || EPI == SIMX_EPI_MUL;
+  float4 bias[kBias ? 8 : 1];
+  uint4 aux[kAux ? NP : 1][kAux ? 4 : 1];
+};
+
+template <int EPI, int NP>
+__device__ __forceinline__ void epi_prefetch(const GemmParams& p, int row, int col0, EpiPre<EPI, NP>& pre) {
+  if constexpr (EpiPre<EPI, NP>::kBias) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+      pre.bias[i] = (col0 + i * 4 < p.N) ? __ldg(reinterpret_cast<const float4*>(p.bias + col0 + i * 4))
+                                         : make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+  if constexpr (EpiPre<EPI, NP>::kAux) {
+    const bool rv = row < p.M;
+#pragma unroll
+    for (int q = 0; q < NP; ++q)
+#pragma unroll
+      for (int g = 0; g < 4; ++g)
+        pre.aux[q][g] = (rv && col0 + g * 8 < p.N)
+                            ? *reinterpret_cast<const uint4*>(p.aux + q * p.aux_ps + (long)row * p.ldaux + col0 + g * 8)
+                            : make_uint4(0u, 0u, 0u, 0u);
+  }
+}
+
+// GELU (erf form, ACT2FN["gelu"] of BERT) and its derivative from ONE exponential:
+//   Phi(x) = 1 - 0.5 * poly(t) * exp(-x^2/2) for x >= 0 (Abramowitz-Stegun 7.1.26 on z = x/sqrt(2), |err| < 1.5e-7),
+//   t = 1 / (1 + p z);  gelu = x Phi;  gelu' = Phi + x exp(-x^2/2) / sqrt(2 pi).       2 MUFU + ~15 FMA-pipe ops.
+__device__ __forceinline__ void gelu_fast(float x, float& g, float& dg) {
+  const float ax = fabsf(x);
+  float t, e;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(fmaf(0.3275911f * 0.70710678118f, ax, 1.0f)));
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(x * x * -0.72134752044f));  // exp(-x^2/2)
+  float poly = fmaf(t, 0.5f * 1.061405429f, 0.5f * -1.453152027f);
+  poly = fmaf(t, poly, 0.5f * 1.421413741f);
+  poly = fmaf(t, poly, 0.5f * -0.284496736f);
+  poly = fmaf(t, poly, 0.5f * 0.254829592f);
+  const float hp = poly * t * e;              // 0.5 * (1 - erf(|z|))
+  const float phi = x >= 0.f ? 1.0f - hp : hp;
+  g = x * phi;
+  dg = fmaf(x * e, 0.3989422804014327f, phi);
+}
+__device__ __forceinline__ void gelu_exact(float x, float& g, float& dg) {
+  const float cdf = 0.5f * (1.0f + erff(x * 0.70710678118654752440f));
+  g = x * cdf;
+  dg = cdf + x * 0.39894228040143267794f * expf(-0.5f * x * x);
+}
+
+template <int EPI, int NP>
+__device__ __forceinline__ void epilogue_chunk(const GemmParams& p, int row, int col0, const uint32_t (&acc)[32],
+                                               const EpiPre<EPI, NP>& pre) {
   // this thread owns D[row, col0 .. col0+32)
   if (row >= p.M) return;
 #pragma unroll
@@ -65,26 +119,42 @@ __device__ __forceinline__ void epilogue_chunk(const GemmParams& p, int row, int
                    "f"(v[7])
                    : "memory");
     } else {
-      if constexpr (EPI == SIMX_EPI_BIAS || EPI == SIMX_EPI_BIAS_GELU || EPI == SIMX_EPI_BIAS_ADD) {
-        const float4 b0 = __ldg(reinterpret_cast<const float4*>(p.bias + col));
-        const float4 b1 = __ldg(reinterpret_cast<const float4*>(p.bias + col + 4));
+      if constexpr (EpiPre<EPI, NP>::kBias) {
+        const float4 b0 = pre.bias[2 * g], b1 = pre.bias[2 * g + 1];
         v[0] += b0.x; v[1] += b0.y; v[2] += b0.z; v[3] += b0.w;
         v[4] += b1.x; v[5] += b1.y; v[6] += b1.z; v[7] += b1.w;
       }
-      if constexpr (EPI == SIMX_EPI_BIAS_ADD || EPI == SIMX_EPI_ADD || EPI == SIMX_EPI_DGELU) {
+      if constexpr (EpiPre<EPI, NP>::kAux) {
         float a[8];
-        plane_load8<NP>(p.aux + (long)row * p.ldaux + col, p.aux_ps, a);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) a[i] = 0.f;
+#pragma unroll
+        for (int q = 0; q < NP; ++q) {
+          const uint32_t w[4] = {pre.aux[q][g].x, pre.aux[q][g].y, pre.aux[q][g].z, pre.aux[q][g].w};
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const float2 f = unpack_bf16x2(w[i]);
+            a[2 * i] += f.x;
+            a[2 * i + 1] += f.y;
+          }
+        }
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
-          if constexpr (EPI == SIMX_EPI_DGELU) v[i] *= gelu_erf_grad(a[i]);
+          if constexpr (EPI == SIMX_EPI_MUL) v[i] *= a[i];
           else v[i] += a[i];
         }
       }
-      split_store8<NP>(p.out + (long)row * p.ldo + col, p.out_ps, v);
       if constexpr (EPI == SIMX_EPI_BIAS_GELU) {
+        float ge[8], dg[8];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) v[i] = gelu_erf(v[i]);
-        split_store8<NP>(p.out2 + (long)row * p.ldo + col, p.out_ps, v);
+        for (int i = 0; i < 8; ++i) {
+          if constexpr (NP == 1) gelu_fast(v[i], ge[i], dg[i]);
+          else gelu_exact(v[i], ge[i], dg[i]);
+        }
+        split_store8<NP>(p.out + (long)row * p.ldo + col, p.out_ps, dg);   // gelu'(pre-activation), kept for backward
+        split_store8<NP>(p.out2 + (long)row * p.ldo + col, p.out_ps, ge);  // gelu(pre-activation)
+      } else {
+        split_store8<NP>(p.out + (long)row * p.ldo + col, p.out_ps, v);
       }
     }
   }
@@ -121,7 +191,7 @@ gemm_kernel(const GemmParams p, const __grid_constant__ CUtensorMap mapA, const 
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tfull[i], 1);
-      mbar_init(&tempty[i], 4);
+      mbar_init(&tempty[i], 8);
     }
     fence_mbar_init();
   }
@@ -213,30 +283,39 @@ gemm_kernel(const GemmParams p, const __grid_constant__ CUtensorMap mapA, const 
       }
     }
   } else if (warp >= 4) {
-    // ===================== epilogue =====================
-    const int ew = warp - 4;  // == warp % 4: the TMEM lane quarter this warp may read
+    // ===================== epilogue: 8 warps, two per TMEM lane quarter, each owning half of the columns ==========
+    const int quarter = warp & 3;          // the TMEM lanes [32*quarter, +32) this warp may read
+    const int half = (warp - 4) >> 2;
+    constexpr int CPW = BN / 2;            // columns per warp
+    constexpr int NCH = CPW / 32;          // 32-column chunks per warp
     int it = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
       const int nt = tile % p.n_tiles;
       const int mt = (tile / p.n_tiles) % p.m_tiles;
       const int acc = it & 1;
       const uint32_t acc_phase = (it >> 1) & 1;
-      const int row = mt * GEMM_BM + ew * 32 + lane;
+      const int row = mt * GEMM_BM + quarter * 32 + lane;
+      const int col_base = nt * BN + half * CPW;
+      EpiPre<EPI, NP> pre;
+      epi_prefetch<EPI, NP>(p, row, col_base, pre);
       mbar_wait(&tfull[acc], acc_phase);
       tc_fence_after();
-      const uint32_t t_addr = tmem_base + acc * BN + (static_cast<uint32_t>(ew * 32) << 16);
-#pragma unroll 1
-      for (int c = 0; c < BN; c += 32) {
-        uint32_t v[32];
-        tmem_ld_32x32(t_addr + c, v);
+      const uint32_t t_addr = tmem_base + acc * BN + half * CPW + (static_cast<uint32_t>(quarter * 32) << 16);
+      uint32_t v[2][32];
+      tmem_ld_32x32(t_addr, v[0]);
+#pragma unroll
+      for (int c = 0; c < NCH; ++c) {
         tmem_ld_wait();
-        if (c + 32 == BN) {
-          // accumulator fully read: hand the TMEM buffer back before doing the global stores
+        if (c + 1 < NCH) {
+          tmem_ld_32x32(t_addr + (c + 1) * 32, v[(c + 1) & 1]);  // in flight while chunk c is processed
+        } else {
+          // accumulator fully read by this warp: hand the TMEM buffer back before the global stores
           tc_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive(&tempty[acc]);
         }
-        epilogue_chunk<EPI, NP>(p, row, nt * BN + c, v);
+        epilogue_chunk<EPI, NP>(p, row, col_base + c * 32, v[c & 1], pre);
+        if (c + 1 < NCH) epi_prefetch<EPI, NP>(p, row, col_base + (c + 1) * 32, pre);
       }
     }
   }
@@ -322,7 +401,7 @@ static int dispatch_epi(int epi, const GemmParams& p, const CUtensorMap& ma, con
       case SIMX_EPI_BIAS: return launch_gemm<BN, MN, SIMX_EPI_BIAS, NP>(p, ma, mb, stream);
       case SIMX_EPI_BIAS_GELU: return launch_gemm<BN, MN, SIMX_EPI_BIAS_GELU, NP>(p, ma, mb, stream);
       case SIMX_EPI_BIAS_ADD: return launch_gemm<BN, MN, SIMX_EPI_BIAS_ADD, NP>(p, ma, mb, stream);
-      case SIMX_EPI_DGELU: return launch_gemm<BN, MN, SIMX_EPI_DGELU, NP>(p, ma, mb, stream);
+      case SIMX_EPI_MUL: return launch_gemm<BN, MN, SIMX_EPI_MUL, NP>(p, ma, mb, stream);
       case SIMX_EPI_ADD: return launch_gemm<BN, MN, SIMX_EPI_ADD, NP>(p, ma, mb, stream);
       case SIMX_EPI_ATOMIC_F32: return launch_gemm<BN, MN, SIMX_EPI_ATOMIC_F32, NP>(p, ma, mb, stream);
     }
@@ -350,7 +429,7 @@ int gemm(int M, int N, int K, const bf16* A, long lda, long a_ps, bool a_mn, con
   if (epi == SIMX_EPI_BIAS || epi == SIMX_EPI_BIAS_GELU || epi == SIMX_EPI_BIAS_ADD)
     SIMX_CHECK(bias != nullptr && (reinterpret_cast<uintptr_t>(bias) & 15) == 0, SIMX_ERR_INVALID,
                "gemm: bias missing or misaligned");
-  if (epi == SIMX_EPI_BIAS_ADD || epi == SIMX_EPI_DGELU || epi == SIMX_EPI_ADD)
+  if (epi == SIMX_EPI_BIAS_ADD || epi == SIMX_EPI_MUL || epi == SIMX_EPI_ADD)
     SIMX_CHECK(aux != nullptr && ldaux % 8 == 0 && (reinterpret_cast<uintptr_t>(aux) & 15) == 0, SIMX_ERR_INVALID,
                "gemm: aux missing or misaligned");
   if (epi == SIMX_EPI_BIAS_GELU) SIMX_CHECK(out2 != nullptr, SIMX_ERR_INVALID, "gemm: out2 missing");
@@ -389,6 +468,8 @@ int gemm(int M, int N, int K, const bf16* A, long lda, long a_ps, bool a_mn, con
     SIMX_TRY(make_tmap_bf16(&mb, B, N, K, planes, ldb, b_ps, GEMM_BK));
   }
 
+  ProfScope prof(a_mn ? "gemm_mn" : "gemm_kk", 2.0 * M * N * (double)K * p.npass,
+                 2.0 * planes * ((double)M * K + (double)N * K) + (epi == SIMX_EPI_ATOMIC_F32 ? 4.0 : 2.0 * planes) * M * N, stream);
 #define SIMX_GEMM_DISPATCH(BN_)                                                                  \
   if (BN == BN_) {                                                                               \
     if (a_mn) {                                                                                  \

@@ -132,13 +132,13 @@ local_loss_kernel(const simx_loss_cfg cfg, const float* __restrict__ Q, const fl
 // Writes dS = w * grad_scale * (softmax - onehot) / GQ as 3 bf16 planes, accumulates loss and arg-max hits.
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
-nll_row_kernel(const float* __restrict__ S, int GQ, int GC, const int32_t* __restrict__ pos_idx, float w,
+nll_row_kernel(const float* __restrict__ S, int GQ, int GC, int ldS, const int32_t* __restrict__ pos_idx, float w,
                float grad_scale, bf16* dS, long ds_ps, float* out_losses) {
   __shared__ float red_m[8], red_s[8];
   __shared__ int red_i[8];
   __shared__ float sh_lse;
   const int row = blockIdx.x, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const float* s = S + (long)row * GC;
+  const float* s = S + (long)row * ldS;
   float m = -INFINITY, sum = 0.f;
   int am = 0;
   for (int c = threadIdx.x; c < GC; c += 256) {
@@ -185,7 +185,7 @@ nll_row_kernel(const float* __restrict__ S, int GQ, int GC, const int32_t* __res
   const float k = w * grad_scale / GQ;
   for (int c = threadIdx.x; c < GC; c += 256) {
     const float g = k * (expf(s[c] - lse) - (c == pos ? 1.f : 0.f));
-    split_store<3>(dS + (long)row * GC + c, ds_ps, g);
+    split_store<3>(dS + (long)row * ldS + c, ds_ps, g);
   }
 }
 
@@ -198,11 +198,12 @@ static LossWs loss_ws(const simx_loss_cfg* c) {
   LossWs w{};
   size_t off = 0;
   if (c->terms & SIMX_LOSS_NLL_GLOBAL) {
+    const size_t GCp = (c->GC + 7) / 8 * 8;  // score-matrix row pitch (TMA needs 16-byte row strides)
     w.qp = off;  off += align256(3ull * c->GQ * c->H * 2);
-    w.cp = off;  off += align256(3ull * c->GC * c->H * 2);
-    w.ctp = off; off += align256(3ull * c->GC * c->H * 2);
-    w.s = off;   off += align256(4ull * c->GQ * c->GC);
-    w.ds = off;  off += align256(3ull * c->GQ * c->GC * 2);
+    w.cp = off;  off += align256(3ull * GCp * c->H * 2);
+    w.ctp = off; off += align256(3ull * GCp * c->H * 2);
+    w.s = off;   off += align256(4ull * c->GQ * GCp);
+    w.ds = off;  off += align256(3ull * c->GQ * GCp * 2);
   }
   w.total = off + 256;
   return w;
@@ -237,8 +238,8 @@ extern "C" int simx_score_loss(const simx_loss_cfg* cfg, const float* Q, const f
   bool have_grads = false;
   if (cfg->terms & SIMX_LOSS_NLL_GLOBAL) {
     SIMX_CHECK(pos_idx != nullptr && workspace != nullptr, SIMX_ERR_INVALID, "score_loss: NLL_GLOBAL needs pos_idx and workspace");
-    SIMX_CHECK(cfg->GC % 8 == 0 && cfg->c_begin % 8 == 0, SIMX_ERR_INVALID,
-               "score_loss: GC=%d and c_begin=%d must be multiples of 8", cfg->GC, cfg->c_begin);
+    SIMX_CHECK(cfg->c_begin % 8 == 0, SIMX_ERR_INVALID,
+               "score_loss: c_begin=%d must be a multiple of 8 (ranks contribute multiples of 8 passages)", cfg->c_begin);
     const LossWs w = loss_ws(cfg);
     uint8_t* ws = static_cast<uint8_t*>(workspace);
     ws += (256 - (reinterpret_cast<uintptr_t>(ws) & 255)) & 255;
@@ -247,14 +248,19 @@ extern "C" int simx_score_loss(const simx_loss_cfg* cfg, const float* Q, const f
     bf16* CTp = reinterpret_cast<bf16*>(ws + w.ctp);
     float* S = reinterpret_cast<float*>(ws + w.s);
     bf16* dS = reinterpret_cast<bf16*>(ws + w.ds);
-    const int GQ = cfg->GQ, GC = cfg->GC;
-    const long q_ps = (long)GQ * H, c_ps = (long)GC * H, s_ps = (long)GQ * GC;
+    const int GQ = cfg->GQ, GC = cfg->GC, GCp = (GC + 7) / 8 * 8;
+    const long q_ps = (long)GQ * H, c_ps = (long)GCp * H, s_ps = (long)GQ * GCp;
+    if (GCp != GC) {  // zero the padding rows / columns once: they contribute nothing to any contraction
+      SIMX_CUDA(cudaMemsetAsync(Cp, 0, 3ull * GCp * H * 2, st));
+      SIMX_CUDA(cudaMemsetAsync(CTp, 0, 3ull * GCp * H * 2, st));
+      SIMX_CUDA(cudaMemsetAsync(dS, 0, 3ull * GQ * GCp * 2, st));
+    }
     SIMX_TRY(convert_weight(3, Q, GQ, H, Qp, H, q_ps, nullptr, 0, 0, st));
-    SIMX_TRY(convert_weight(3, C, GC, H, Cp, H, c_ps, CTp, GC, c_ps, st));
-    SIMX_CUDA(cudaMemsetAsync(S, 0, 4ull * GQ * GC, st));
-    SIMX_TRY(gemm(GQ, GC, H, Qp, H, q_ps, false, Cp, H, c_ps, false, 3, SIMX_EPI_ATOMIC_F32, nullptr, nullptr, 0, 0,
-                  nullptr, nullptr, 0, 0, S, GC, 1, st));
-    nll_row_kernel<<<GQ, 256, 0, st>>>(S, GQ, GC, pos_idx, cfg->w_nll_global, cfg->grad_scale, dS, s_ps, out_losses);
+    SIMX_TRY(convert_weight(3, C, GC, H, Cp, H, c_ps, CTp, GCp, c_ps, st));
+    SIMX_CUDA(cudaMemsetAsync(S, 0, 4ull * GQ * GCp, st));
+    SIMX_TRY(gemm(GQ, GCp, H, Qp, H, q_ps, false, Cp, H, c_ps, false, 3, SIMX_EPI_ATOMIC_F32, nullptr, nullptr, 0, 0,
+                  nullptr, nullptr, 0, 0, S, GCp, 1, st));
+    nll_row_kernel<<<GQ, 256, 0, st>>>(S, GQ, GC, GCp, pos_idx, cfg->w_nll_global, cfg->grad_scale, dS, s_ps, out_losses);
     SIMX_LAUNCH_CHECK();
     SIMX_CUDA(cudaMemsetAsync(dQ, 0, 4ull * cfg->q_count * H, st));
     SIMX_CUDA(cudaMemsetAsync(dC, 0, 4ull * cfg->c_count * H, st));
@@ -262,15 +268,15 @@ extern "C" int simx_score_loss(const simx_loss_cfg* cfg, const float* Q, const f
     // dQ_local = dS[local rows, :] C          (K-major x K-major against C^T)
     {
       const int tiles = ((cfg->q_count + 127) / 128) * ((H + 255) / 256);
-      const int ksplit = max(1, min((GC + 63) / 64, (sms + tiles - 1) / tiles));
-      SIMX_TRY(gemm(cfg->q_count, H, GC, dS + (long)cfg->q_begin * GC, GC, s_ps, false, CTp, GC, c_ps, false, 3,
+      const int ksplit = max(1, min((GCp + 63) / 64, (sms + tiles - 1) / tiles));
+      SIMX_TRY(gemm(cfg->q_count, H, GCp, dS + (long)cfg->q_begin * GCp, GCp, s_ps, false, CTp, GCp, c_ps, false, 3,
                     SIMX_EPI_ATOMIC_F32, nullptr, nullptr, 0, 0, nullptr, nullptr, 0, 0, dQ, H, ksplit, st));
     }
     // dC_local = dS[:, local cols]^T Q        (MN-major x MN-major, contraction over the global queries)
     {
       const int tiles = ((cfg->c_count + 127) / 128) * ((H + 255) / 256);
       const int ksplit = max(1, min((GQ + 63) / 64, (sms + tiles - 1) / tiles));
-      SIMX_TRY(gemm(cfg->c_count, H, GQ, dS + cfg->c_begin, GC, s_ps, true, Qp, H, q_ps, true, 3, SIMX_EPI_ATOMIC_F32,
+      SIMX_TRY(gemm(cfg->c_count, H, GQ, dS + cfg->c_begin, GCp, s_ps, true, Qp, H, q_ps, true, 3, SIMX_EPI_ATOMIC_F32,
                     nullptr, nullptr, 0, 0, nullptr, nullptr, 0, 0, dC, H, ksplit, st));
     }
     have_grads = true;

