@@ -3,7 +3,7 @@
 //   warp 0      : TMA producer   (cp.async.bulk.tensor, 128B-swizzled tiles, 4-stage mbarrier ring)
 //   warp 1      : MMA issuer     (one thread, tcgen05.mma kind::f16 128xBNx16, fp32 accumulator in TMEM)
 //   warp 2      : TMEM allocator
-//   warps 4..11 : epilogue       (tcgen05.ld -> registers -> bias / GELU+GELU' / residual / multiply -> global)
+//   warps 4..19 : epilogue       (tcgen05.ld -> registers -> bias / GELU+GELU' / residual / multiply -> global)
 //   TMEM holds two accumulators, so the epilogue of tile i overlaps the MMAs of tile i+1.
 //
 // Both operands may be K-major (activations x nn.Linear weights, the "TN" case of every forward and dgrad GEMM:
@@ -17,7 +17,7 @@ namespace simx {
 
 constexpr int GEMM_BM = 128;
 constexpr int GEMM_BK = 64;
-constexpr int GEMM_THREADS = 384;  // 4 control warps + 8 epilogue warps
+constexpr int GEMM_THREADS = 640;  // 4 control warps + 16 epilogue warps
 
 struct GemmParams {
   int M, N, K;
@@ -43,7 +43,9 @@ struct GemmSmem {
   static constexpr uint32_t B_BYTES = BN * GEMM_BK * 2;
   static constexpr uint32_t STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr uint32_t BAR_OFF = STAGES * STAGE_BYTES;
-  static constexpr uint32_t TOTAL = BAR_OFF + 256 + 1024;  // barriers + alignment slack
+  static constexpr uint32_t BIAS_OFF = BAR_OFF + 256;
+  static constexpr uint32_t BIAS_FLOATS = 3072;  // the whole bias vector lives in smem when N fits (else global loads)
+  static constexpr uint32_t TOTAL = BIAS_OFF + BIAS_FLOATS * 4 + 1024;  // + alignment slack
 };
 
 // operands the epilogue fetches from global memory for one 32-column chunk; issued BEFORE the TMEM wait so their
@@ -52,24 +54,17 @@ template <int EPI, int NP>
 struct EpiPre {
   static constexpr bool kBias = EPI == SIMX_EPI_BIAS || EPI == SIMX_EPI_BIAS_GELU || EPI == SIMX_EPI_BIAS_ADD;
   static constexpr bool kAux = EPI == SIMX_EPI_BIAS_ADD || EPI == SIMX_EPI_ADD || EPI == SIMX_EPI_MUL;
-  float4 bias[kBias ? 8 : 1];
   uint4 aux[kAux ? NP : 1][kAux ? 4 : 1];
 };
 
-template <int EPI, int NP>
+template <int EPI, int NP, int CW>
 __device__ __forceinline__ void epi_prefetch(const GemmParams& p, int row, int col0, EpiPre<EPI, NP>& pre) {
-  if constexpr (EpiPre<EPI, NP>::kBias) {
-#pragma unroll
-    for (int i = 0; i < 8; ++i)
-      pre.bias[i] = (col0 + i * 4 < p.N) ? __ldg(reinterpret_cast<const float4*>(p.bias + col0 + i * 4))
-                                         : make_float4(0.f, 0.f, 0.f, 0.f);
-  }
   if constexpr (EpiPre<EPI, NP>::kAux) {
     const bool rv = row < p.M;
 #pragma unroll
     for (int q = 0; q < NP; ++q)
 #pragma unroll
-      for (int g = 0; g < 4; ++g)
+      for (int g = 0; g < CW / 8; ++g)
         pre.aux[q][g] = (rv && col0 + g * 8 < p.N)
                             ? *reinterpret_cast<const uint4*>(p.aux + q * p.aux_ps + (long)row * p.ldaux + col0 + g * 8)
                             : make_uint4(0u, 0u, 0u, 0u);
@@ -99,13 +94,13 @@ __device__ __forceinline__ void gelu_exact(float x, float& g, float& dg) {
   dg = cdf + x * 0.39894228040143267794f * expf(-0.5f * x * x);
 }
 
-template <int EPI, int NP>
-__device__ __forceinline__ void epilogue_chunk(const GemmParams& p, int row, int col0, const uint32_t (&acc)[32],
-                                               const EpiPre<EPI, NP>& pre) {
-  // this thread owns D[row, col0 .. col0+32)
+template <int EPI, int NP, int CW>
+__device__ __forceinline__ void epilogue_chunk(const GemmParams& p, int row, int col0, const uint32_t (&acc)[CW],
+                                               const EpiPre<EPI, NP>& pre, const float* sbias) {
+  // this thread owns D[row, col0 .. col0+CW)
   if (row >= p.M) return;
 #pragma unroll
-  for (int g = 0; g < 4; ++g) {
+  for (int g = 0; g < CW / 8; ++g) {
     const int col = col0 + g * 8;
     if (col >= p.N) break;  // N % 8 == 0 is enforced on the host
     float v[8];
@@ -120,7 +115,10 @@ __device__ __forceinline__ void epilogue_chunk(const GemmParams& p, int row, int
                    : "memory");
     } else {
       if constexpr (EpiPre<EPI, NP>::kBias) {
-        const float4 b0 = pre.bias[2 * g], b1 = pre.bias[2 * g + 1];
+        // bias from shared memory (the epilogue's own store traffic keeps evicting it from the small L1)
+        const float* bsrc = sbias != nullptr ? sbias + col : p.bias + col;
+        const float4 b0 = *reinterpret_cast<const float4*>(bsrc);
+        const float4 b1 = *reinterpret_cast<const float4*>(bsrc + 4);
         v[0] += b0.x; v[1] += b0.y; v[2] += b0.z; v[3] += b0.w;
         v[4] += b1.x; v[5] += b1.y; v[6] += b1.z; v[7] += b1.w;
       }
@@ -176,6 +174,13 @@ gemm_kernel(const GemmParams p, const __grid_constant__ CUtensorMap mapA, const 
   uint64_t* tfull = bars + 2 * STAGES;      // [2]       MMA -> epilogue
   uint64_t* tempty = bars + 2 * STAGES + 2; // [2]       epilogue -> MMA
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
+  float* sbias = nullptr;
+  if constexpr (EpiPre<EPI, NP>::kBias) {
+    if (p.N <= (int)L::BIAS_FLOATS) {
+      sbias = reinterpret_cast<float*>(smem + L::BIAS_OFF);
+      for (int i = threadIdx.x; i < p.N; i += GEMM_THREADS) sbias[i] = p.bias[i];
+    }
+  }
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -191,7 +196,7 @@ gemm_kernel(const GemmParams p, const __grid_constant__ CUtensorMap mapA, const 
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tfull[i], 1);
-      mbar_init(&tempty[i], 8);
+      mbar_init(&tempty[i], 16);
     }
     fence_mbar_init();
   }
@@ -283,11 +288,13 @@ gemm_kernel(const GemmParams p, const __grid_constant__ CUtensorMap mapA, const 
       }
     }
   } else if (warp >= 4) {
-    // ===================== epilogue: 8 warps, two per TMEM lane quarter, each owning half of the columns ==========
+    // ===================== epilogue: 16 warps, four per TMEM lane quarter, each owning a quarter of the columns ======
+    // (the epilogue is latency-bound — TMEM load, operand fetch, MUFU — so it wants warps, not wider warps)
     const int quarter = warp & 3;          // the TMEM lanes [32*quarter, +32) this warp may read
-    const int half = (warp - 4) >> 2;
-    constexpr int CPW = BN / 2;            // columns per warp
-    constexpr int NCH = CPW / 32;          // 32-column chunks per warp
+    const int part = (warp - 4) >> 2;      // 0..3
+    constexpr int CPW = BN / 4;            // columns per warp: 64 / 32 / 16
+    constexpr int CW = CPW >= 32 ? 32 : 16;  // columns per tcgen05.ld
+    constexpr int NCH = CPW / CW;
     int it = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
       const int nt = tile % p.n_tiles;
@@ -295,27 +302,25 @@ gemm_kernel(const GemmParams p, const __grid_constant__ CUtensorMap mapA, const 
       const int acc = it & 1;
       const uint32_t acc_phase = (it >> 1) & 1;
       const int row = mt * GEMM_BM + quarter * 32 + lane;
-      const int col_base = nt * BN + half * CPW;
+      const int col_base = nt * BN + part * CPW;
       EpiPre<EPI, NP> pre;
-      epi_prefetch<EPI, NP>(p, row, col_base, pre);
+      epi_prefetch<EPI, NP, CW>(p, row, col_base, pre);
       mbar_wait(&tfull[acc], acc_phase);
       tc_fence_after();
-      const uint32_t t_addr = tmem_base + acc * BN + half * CPW + (static_cast<uint32_t>(quarter * 32) << 16);
-      uint32_t v[2][32];
-      tmem_ld_32x32(t_addr, v[0]);
+      const uint32_t t_addr = tmem_base + acc * BN + part * CPW + (static_cast<uint32_t>(quarter * 32) << 16);
 #pragma unroll
       for (int c = 0; c < NCH; ++c) {
+        uint32_t v[CW];
+        tmem_ld_cols<CW>(t_addr + c * CW, v);
         tmem_ld_wait();
-        if (c + 1 < NCH) {
-          tmem_ld_32x32(t_addr + (c + 1) * 32, v[(c + 1) & 1]);  // in flight while chunk c is processed
-        } else {
-          // accumulator fully read by this warp: hand the TMEM buffer back before the global stores
+        if (c + 1 == NCH) {
+          // accumulator fully read by this warp: hand the TMEM buffer back before the math and the global stores
           tc_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive(&tempty[acc]);
         }
-        epilogue_chunk<EPI, NP>(p, row, col_base + c * 32, v[c & 1], pre);
-        if (c + 1 < NCH) epi_prefetch<EPI, NP>(p, row, col_base + (c + 1) * 32, pre);
+        epilogue_chunk<EPI, NP, CW>(p, row, col_base + c * CW, v, pre, sbias);
+        if (c + 1 < NCH) epi_prefetch<EPI, NP, CW>(p, row, col_base + (c + 1) * CW, pre);
       }
     }
   }

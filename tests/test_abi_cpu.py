@@ -1,0 +1,110 @@
+"""CPU-side checks of the boundary: the C-ABI library loads, exports every symbol include/simx_b200.h declares,
+the ctypes signature table covers exactly those symbols, and the shape/layout queries (no GPU needed) are consistent
+with the HF parameter table.  No compute call is made."""
+import ctypes as C
+import re
+
+import pytest
+import torch
+
+from simxns_b200 import _lib
+from simxns_b200.encoder import EncoderConfig
+from simxns_b200.models import BiBertEncoder, HFBertEncoder, HFDistilBertEncoder, Reranker
+
+from conftest import ROOT
+
+
+def _declared_symbols():
+    text = (ROOT / "include" / "simx_b200.h").read_text()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(simx_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_library_exports_every_declared_symbol():
+    lib = _lib.lib()
+    declared = _declared_symbols()
+    assert len(declared) >= 15
+    for name in declared:
+        assert hasattr(lib, name), f"{name} declared in include/simx_b200.h but not exported"
+    assert sorted(_lib.SIGNATURES) == declared, "ctypes SIGNATURES and the header disagree"
+    assert lib.simx_version() >= 100
+
+
+def test_struct_mirrors_have_header_layout():
+    assert C.sizeof(_lib.EncoderCfg) == 10 * 4
+    assert C.sizeof(_lib.LossCfg) == 9 * 4 + 9 * 4
+
+
+@pytest.mark.parametrize("arch,n_expected", [("bert", 5 + 16 * 12 + 2), ("distilbert", 4 + 16 * 6)])
+def test_param_table_matches_hf_state_dict(arch, n_expected):
+    lib = _lib.lib()
+    ec = EncoderConfig(arch=arch, num_layers=12 if arch == "bert" else 6)
+    cls = HFBertEncoder if arch == "bert" else HFDistilBertEncoder
+    with torch.device("meta"):
+        m = cls(ec)
+    cfg = ec.c_struct(_lib.PREC_BF16)
+    n = lib.simx_encoder_num_params(C.byref(cfg))
+    assert n == n_expected == len(m.ordered_parameters()) == len(m.state_dict())
+    if arch == "bert":
+        assert sum(p.numel() for p in m.parameters()) == 109482240  # params per BERT-base tower
+    # every parameter has its slot in the flat gradient buffer, slots tile it exactly
+    slots = []
+    for i, p in enumerate(m.ordered_parameters()):
+        numel = lib.simx_encoder_param_numel(C.byref(cfg), i)
+        assert numel == p.numel()
+        slots.append((lib.simx_encoder_grad_offset(C.byref(cfg), i), numel))
+    slots.sort()
+    pos = 0
+    for off, numel in slots:
+        assert off == pos
+        pos += numel
+    assert pos == lib.simx_encoder_grad_numel(C.byref(cfg))
+    # q/k/v weights (and biases) are adjacent: the fused QKV wgrad writes them as one block
+    base = 5 if arch == "bert" else 4
+    H = ec.hidden
+    oq, ok, ov = (lib.simx_encoder_grad_offset(C.byref(cfg), base + j) for j in (0, 2, 4))
+    assert (ok - oq, ov - ok) == (H * H, H * H)
+
+
+def test_state_dict_keys_are_the_reference_checkpoint_layout():
+    """199 HF keys per tower, prefixed question_model. / ctx_model.; Reranker: encoder.* + qa_classifier.*"""
+    ec = EncoderConfig(num_layers=2, hidden=128, heads=2, intermediate=256, vocab=64, max_pos=32)
+    bi = BiBertEncoder(None, question_model=HFBertEncoder(ec), ctx_model=HFBertEncoder(ec))
+    keys = list(bi.state_dict())
+    assert len(keys) == 2 * (5 + 16 * 2 + 2)
+    assert "question_model.embeddings.word_embeddings.weight" in keys
+    assert "ctx_model.encoder.layer.1.attention.output.LayerNorm.bias" in keys
+    assert "ctx_model.pooler.dense.weight" in keys
+    shared = BiBertEncoder(None, question_model=HFBertEncoder(ec))
+    assert shared.ctx_model is shared.question_model
+    rr = Reranker(HFBertEncoder(ec), ec.hidden)
+    assert {"qa_classifier.weight", "qa_classifier.bias"} <= set(rr.state_dict())
+    # the optimizer's no-decay grouping keys on these substrings (co_training_marco_train.py:57-69)
+    names = [n for n, _ in bi.named_parameters()]
+    assert any("LayerNorm.weight" in n for n in names) and any(n.endswith("bias") for n in names)
+    # old checkpoints carry embeddings.position_ids: accepted and ignored
+    sd = bi.question_model.state_dict()
+    sd["embeddings.position_ids"] = torch.arange(32)[None]
+    bi.question_model.load_state_dict(sd, strict=True)
+
+
+def test_buffer_size_queries_and_invalid_configs():
+    lib = _lib.lib()
+    ec = EncoderConfig()
+    cfg = ec.c_struct(_lib.PREC_BF16)
+    per_token = (7 * 768 + 2 * 3072) * 12 + 768 * 14  # saved bf16 elements per token
+    saved = lib.simx_encoder_saved_bytes(C.byref(cfg), 2048, 128)
+    assert abs(saved - 2 * per_token * 2048 * 128) / saved < 0.01
+    cfg3 = ec.c_struct(_lib.PREC_BF16X3)
+    assert lib.simx_encoder_saved_bytes(C.byref(cfg3), 4, 32) > 2.5 * lib.simx_encoder_saved_bytes(C.byref(cfg), 4, 32)
+    bad = EncoderConfig(hidden=100, heads=2).c_struct(_lib.PREC_BF16)
+    assert lib.simx_encoder_num_params(C.byref(bad)) == -1
+    assert "hidden" in _lib.last_error()
+
+
+def test_forward_without_cuda_fails_loudly():
+    """no CPU fallback: parameters on the CPU are an error, not a slow path"""
+    ec = EncoderConfig(num_layers=1, hidden=64, heads=1, intermediate=64, vocab=32, max_pos=16)
+    m = HFBertEncoder(ec)
+    with pytest.raises(RuntimeError, match="no CPU fallback|CUDA"):
+        m(input_ids=torch.ones(1, 4, dtype=torch.long), attention_mask=torch.ones(1, 4, dtype=torch.long))

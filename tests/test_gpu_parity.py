@@ -1,0 +1,344 @@
+"""Parity tests proper (B200, `-m gpu`): the CUDA path, called through the C ABI (ctypes -> libsimx_b200.so), against
+(1) the golden fixtures produced by the reference's own code and (2) the numpy oracle on seeded inputs.
+
+Tolerances (north_star): fp32-class mode (SIMX_PREC_BF16X3) — embeddings/logits and gradients within 1e-3, loss within
+1e-4 of the reference (we assert much tighter where the data allows).  bf16 throughput mode is checked at the
+deviation the reference itself shows under bf16 autocast (~3 % on logits): 5e-2 relative on hidden
+states, 8e-2 of the per-tensor scale on gradients.
+"""
+import ctypes as C
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import bert_numpy as bn
+from oracle import losses_numpy as ln
+from simxns_b200 import _lib
+from simxns_b200.encoder import EncoderConfig
+from simxns_b200.losses import BiEncoderNllLoss, CrossBERTKDLoss, fused_score_loss, simans_distill_loss
+from simxns_b200.models import BiBertEncoder, HFBertEncoder, HFDistilBertEncoder, Reranker
+
+pytestmark = pytest.mark.gpu
+
+X3, BF16 = _lib.PREC_BF16X3, _lib.PREC_BF16
+
+
+@pytest.fixture(scope="module", autouse=True)
+def _device():
+    assert torch.cuda.is_available(), "gpu tests need a CUDA device"
+    torch.cuda.set_device(0)
+    _lib.require_device()  # fails loudly when the library cannot run here: no fallback path exists
+
+
+def cu(a, dtype=None):
+    t = torch.from_numpy(np.ascontiguousarray(a)).cuda()
+    return t.to(dtype) if dtype is not None else t
+
+
+def ec_from(cfg):
+    return EncoderConfig(arch=cfg["arch"], num_layers=cfg["num_layers"], hidden=cfg["hidden"], heads=cfg["heads"],
+                         intermediate=cfg["intermediate"], vocab=cfg["vocab"], max_pos=cfg["max_pos"],
+                         type_vocab=cfg["type_vocab"], ln_eps=cfg["ln_eps"])
+
+
+def build(cfg, params, precision):
+    cls = HFBertEncoder if cfg["arch"] == "bert" else HFDistilBertEncoder
+    m = cls(ec_from(cfg), precision=precision)
+    m.load_state_dict({k: torch.from_numpy(v) for k, v in params.items()}, strict=True)
+    return m.cuda()
+
+
+def max_rel(a, b):
+    a, b = np.asarray(a, np.float64), np.asarray(b, np.float64)
+    return float(np.abs(a - b).max() / (np.abs(b).max() + 1e-30))
+
+
+def assert_grads(model, ref_grads, tol, prefix="", zero_true=()):
+    scales = [np.abs(v).max() for v in ref_grads.values() if np.abs(v).max() > 0]
+    floor = 1e-3 * float(np.median(scales))
+    worst = ("", 0.0)
+    for name, p in model.named_parameters():
+        assert p.grad is not None, f"{name} received no gradient (DDP needs dense grads for every parameter)"
+        r = ref_grads[prefix + name]
+        # tensors whose true gradient is exactly zero (key biases: softmax shift invariance; the reranker head bias
+        # under CE: rows of softmax - onehot sum to zero) are judged on the scale of the largest gradient
+        is_zero = "key.bias" in name or "k_lin.bias" in name or name in zero_true
+        fl = max(scales) if is_zero else floor
+        e = float(np.abs(p.grad.cpu().numpy() - r).max() / max(np.abs(r).max(), fl))
+        if e > worst[1]:
+            worst = (name, e)
+    assert worst[1] < tol, f"gradient of {worst[0]} off by {worst[1]:.3e} (tol {tol})"
+
+
+# ---------------------------------------------------------------------------------------------------------
+# encoder tower vs the reference's own outputs (golden fixtures)
+# ---------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("precision,tol_h,tol_g", [(X3, 2e-5, 1e-4), (BF16, 5e-2, 8e-2)])
+def test_encoder_tiny_bert_vs_reference_golden(golden_dir, precision, tol_h, tol_g):
+    g = np.load(golden_dir / "encoder_tiny_bert.npz")
+    L, H, nh, I, V, P, Tt = [int(x) for x in g["cfg"]]
+    cfg = bn.bert_config(num_layers=L, hidden=H, heads=nh, intermediate=I, vocab=V, max_pos=P, type_vocab=Tt)
+    model = build(cfg, bn.synth_params(cfg, seed=int(g["seed"][0])), precision)
+    seq, pooled, none = model(input_ids=cu(g["ids"]), attention_mask=cu(g["mask"]))
+    assert none is None
+    cls = model.last_cls_layers
+    valid = g["mask"].astype(bool)
+    assert max_rel(seq.detach().cpu().numpy()[valid], g["seq"][valid]) < tol_h
+    assert max_rel(pooled.detach().cpu().numpy(), g["pooled"]) < tol_h
+    assert max_rel(cls.detach().cpu().numpy(), g["cls"]) < tol_h
+    if precision == X3:  # absolute bound of the north_star: 1e-3 on outputs
+        assert np.abs(pooled.detach().cpu().numpy() - g["pooled"]).max() < 1e-3
+    d_seq = g["d_seq"] * g["mask"][:, :, None]  # the reference's padded rows feed nothing downstream either
+    loss = (cls * cu(g["d_cls"])).sum() + (seq * cu(d_seq.astype(np.float32))).sum()
+    loss.backward()
+    # golden grads were taken with the unmasked d_seq: recompute the reference gradient with the oracle (pinned to the
+    # golden in tests/test_oracle_golden.py) for the masked cotangent
+    ora = bn.EncoderOracle(cfg, bn.synth_params(cfg, seed=int(g["seed"][0])))
+    ora.forward(g["ids"], g["mask"])
+    ref = ora.backward(d_cls=g["d_cls"].astype(np.float64), d_seq=d_seq.astype(np.float64))
+    assert_grads(model, ref, tol_g)
+    assert float(model.pooler.dense.weight.grad.abs().max()) == 0.0  # dead pooler: zero, not None
+
+
+def test_encoder_full_golden_gradients_fp32_class(golden_dir):
+    """every one of the reference's gradients (unmasked random cotangent on all positions), fp32-class mode"""
+    g = np.load(golden_dir / "encoder_tiny_bert.npz")
+    L, H, nh, I, V, P, Tt = [int(x) for x in g["cfg"]]
+    cfg = bn.bert_config(num_layers=L, hidden=H, heads=nh, intermediate=I, vocab=V, max_pos=P, type_vocab=Tt)
+    model = build(cfg, bn.synth_params(cfg, seed=int(g["seed"][0])), X3)
+    seq, _, _ = model(input_ids=cu(g["ids"]), attention_mask=cu(g["mask"]))
+    ((model.last_cls_layers * cu(g["d_cls"])).sum() + (seq * cu(g["d_seq"])).sum()).backward()
+    ref = {k[5:]: g[k] for k in g.files if k.startswith("grad/")}
+    assert_grads(model, ref, 1e-3)
+
+
+def test_encoder_tiny_distilbert_vs_lead_golden(golden_dir):
+    g = np.load(golden_dir / "encoder_tiny_distilbert.npz")
+    cfg = bn.bert_config(num_layers=2, hidden=128, heads=2, intermediate=256, vocab=512, max_pos=64, arch="distilbert")
+    model = build(cfg, bn.synth_params(cfg, seed=int(g["seed"][0])), X3)
+    seq, pooled, _ = model(input_ids=cu(g["ids"]), attention_mask=cu(g["mask"]))
+    valid = g["mask"].astype(bool)
+    assert max_rel(seq.detach().cpu().numpy()[valid], g["seq"][valid]) < 2e-5
+    # LEAD's all-layer hidden states (no embedding entry): layer k == cls_layers[:, k+1]
+    assert max_rel(model.last_cls_layers[:, 1:].detach().cpu().numpy(), g["hidden_cls"]) < 2e-5
+    (seq * cu(g["d_seq"])).sum().backward()
+    ref = {k[5:]: g[k] for k in g.files if k.startswith("grad/")}
+    assert_grads(model, ref, 1e-3)
+
+
+def test_reranker_teacher_step_vs_golden(golden_dir):
+    """co_training_marco_train.py:225-245 (teacher step): CE over [N, M] relevance logits, column 0 positive"""
+    g = np.load(golden_dir / "reranker_tiny.npz")
+    cfg = bn.bert_config(num_layers=2, hidden=128, heads=2, intermediate=256, vocab=512, max_pos=64)
+    enc = build(cfg, bn.synth_params(cfg, seed=int(g["seed"][0])), X3)
+    rr = Reranker(enc, cfg["hidden"]).cuda()
+    rr.qa_classifier.weight.data = cu(g["qa_w"])
+    rr.qa_classifier.bias.data = cu(g["qa_b"])
+    logits = rr(cu(g["ids"]), cu(g["mask"]))
+    assert np.abs(logits.detach().cpu().numpy() - g["logits"]).max() < 1e-4
+    loss = torch.nn.CrossEntropyLoss()(logits, torch.zeros(2, dtype=torch.long, device="cuda"))
+    assert abs(loss.item() - g["loss"][0]) < 1e-4
+    loss.backward()
+    ref = {k[5:]: g[k] for k in g.files if k.startswith("grad/")}
+    # sum_m (softmax - onehot) = 0 per query: the head bias and the last LayerNorm bias (= W^T sum of dlogits) have an
+    # exactly-zero true gradient, the reference's values for them are fp32 round-off
+    assert_grads(rr, ref, 1e-3, zero_true=("qa_classifier.bias", "encoder.encoder.layer.1.output.LayerNorm.bias"))
+
+
+def test_biencoder_cfg1_bert_base_vs_reference_golden(golden_dir):
+    """BASELINE.json configs[0]/[1]: BiBertEncoder bert-base, B=2, q 32 / p 128, 1+1 passages, SimANS KL loss:
+    embeddings within 1e-3, loss within 1e-4, gradients within 1e-3 of the tensor scale."""
+    g = np.load(golden_dir / "biencoder_cfg1.npz")
+    cfg = bn.bert_config()
+    model = BiBertEncoder(None, question_model=build(cfg, bn.synth_params(cfg, seed=0, perturb=False), X3),
+                          ctx_model=build(cfg, bn.synth_params(cfg, seed=1, perturb=False), X3))
+    q, a = model(cu(g["q_ids"]), cu(g["q_mask"]), cu(g["p_ids"]), cu(g["p_mask"]))
+    assert np.abs(q.detach().cpu().numpy() - g["q_embs"]).max() < 1e-3
+    assert np.abs(a.detach().cpu().numpy() - g["a_embs"]).max() < 1e-3
+    loss = simans_distill_loss(q, a, cu(g["teacher"]), temperature_distill=1.0)
+    assert abs(loss.item() - g["loss"][0]) < 1e-4
+    loss.backward()
+    n = 0
+    scales = [g[k][2] for k in g.files if k.startswith("gstat/") and g[k][2] > 0]
+    floor = 1e-3 * float(np.median(scales))
+    for name, p in model.named_parameters():
+        stat, head = g["gstat/" + name], g["ghead/" + name]
+        gr = p.grad.double().reshape(-1)
+        # true-zero gradients (key biases; the passage tower's last LayerNorm bias = sum_j dS_ij q_i with sum_j dS_ij = 0
+        # for a KL/softmax row): the reference's own values are fp32 round-off, judge them on the largest scale
+        zero_true = "key.bias" in name or name == "ctx_model.encoder.layer.11.output.LayerNorm.bias"
+        scale = max(scales) if zero_true else max(stat[2], floor)
+        assert abs(gr.abs().max().item() - stat[2]) <= 1e-3 * scale + 1e-12, name
+        assert np.abs(gr[:16].cpu().numpy() - head).max() <= 1e-3 * scale, name
+        assert abs(gr.norm().item() - stat[0]) <= 2e-3 * max(stat[0], floor), name
+        if ("grad/" + name) in g.files:
+            assert np.abs(p.grad.cpu().numpy() - g["grad/" + name]).max() <= 1e-3 * scale, name
+        n += 1
+    assert n == 398
+
+
+# ---------------------------------------------------------------------------------------------------------
+# encoder vs oracle: ragged / edge shapes
+# ---------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("B,S,ragged", [(1, 1, False), (2, 7, True), (3, 64, True), (2, 65, True), (5, 128, False),
+                                        (2, 160, True), (1, 300, True), (1, 512, True)])
+def test_encoder_shapes_vs_oracle(B, S, ragged):
+    cfg = bn.bert_config(num_layers=1, hidden=128, heads=2, intermediate=192, vocab=300, max_pos=512)
+    params = bn.synth_params(cfg, seed=100 + S)
+    ids, mask = bn.synth_tokens(B, S, cfg["vocab"], seed=S, ragged=ragged, min_len=1)
+    ora = bn.EncoderOracle(cfg, params)
+    out = ora.forward(ids, mask)
+    rng = np.random.RandomState(S)
+    d_cls = rng.standard_normal(out["cls"].shape)
+    ref = ora.backward(d_cls=d_cls)
+    for precision, tol_h, tol_g in ((X3, 2e-5, 2e-4), (BF16, 5e-2, 1e-1)):
+        model = build(cfg, params, precision)
+        cls, _ = model.encode(cu(ids), cu(mask))
+        assert max_rel(cls.detach().cpu().numpy(), out["cls"]) < tol_h
+        (cls * cu(d_cls, torch.float32)).sum().backward()
+        assert_grads(model, ref, tol_g)
+
+
+def test_encoder_mask_none_and_inference_mode():
+    cfg = bn.bert_config(num_layers=2, hidden=128, heads=2, intermediate=256, vocab=300, max_pos=64)
+    params = bn.synth_params(cfg, seed=3)
+    ids, mask = bn.synth_tokens(4, 32, cfg["vocab"], seed=9)
+    out = bn.EncoderOracle(cfg, params).forward(ids, mask)
+    model = build(cfg, params, X3)
+    with torch.no_grad():  # inference path: nothing saved, workspace ping-pong buffers
+        cls, seq = model.encode(cu(ids), None, want_sequence=True)
+    assert max_rel(cls.cpu().numpy(), out["cls"]) < 2e-5 and max_rel(seq.cpu().numpy(), out["seq"]) < 2e-5
+    model.eval()
+    cls2, _ = model.encode(cu(ids), cu(mask))
+    assert torch.equal(cls2.detach(), cls)  # deterministic forward
+
+
+def test_shared_tower_accumulates_both_passes():
+    """args.share_weight: one module encodes queries and passages, gradients of both passes add"""
+    cfg = bn.bert_config(num_layers=1, hidden=64, heads=1, intermediate=128, vocab=200, max_pos=64)
+    params = bn.synth_params(cfg, seed=5)
+    q_ids, q_mask = bn.synth_tokens(2, 8, cfg["vocab"], seed=1)
+    p_ids, p_mask = bn.synth_tokens(4, 24, cfg["vocab"], seed=2, ragged=True)
+    model = BiBertEncoder(None, question_model=build(cfg, params, X3))
+    q, a = model(cu(q_ids), cu(q_mask), cu(p_ids), cu(p_mask))
+    rng = np.random.RandomState(0)
+    dq, da = rng.standard_normal((2, 64)), rng.standard_normal((4, 64))
+    ((q * cu(dq, torch.float32)).sum() + (a * cu(da, torch.float32)).sum()).backward()
+    ora = bn.EncoderOracle(cfg, params)
+    total = None
+    for ids, m, d in ((q_ids, q_mask, dq), (p_ids, p_mask, da)):
+        ora.forward(ids, m)
+        dc = np.zeros((ids.shape[0], 2, 64)); dc[:, -1] = d
+        gr = ora.backward(d_cls=dc)
+        total = gr if total is None else {k: total[k] + gr[k] for k in gr}
+    assert_grads(model.question_model, total, 2e-4)
+    # gradient accumulation adds into existing .grad (the reference never uses no_sync)
+    before = model.question_model.embeddings.LayerNorm.weight.grad.clone()
+    q, a = model(cu(q_ids), cu(q_mask), cu(p_ids), cu(p_mask))
+    ((q * cu(dq, torch.float32)).sum() + (a * cu(da, torch.float32)).sum()).backward()
+    assert torch.allclose(model.question_model.embeddings.LayerNorm.weight.grad, 2 * before, rtol=1e-4, atol=1e-6)
+
+
+# ---------------------------------------------------------------------------------------------------------
+# fused score / loss / gradient kernel
+# ---------------------------------------------------------------------------------------------------------
+def test_losses_vs_reference_golden(golden_dir):
+    g = np.load(golden_dir / "losses.npz")
+    group = int(g["group"][0])
+    t = cu(g["teacher"])
+
+    def fresh():
+        return cu(g["Q"]).requires_grad_(True), cu(g["C"]).requires_grad_(True)
+
+    def check(q, c, loss, key, ref_loss):
+        assert abs(loss.item() - ref_loss) < 1e-4, key
+        loss.backward()
+        assert np.abs(q.grad.cpu().numpy() - g[key + "_dQ"]).max() < 1e-5, key
+        assert np.abs(c.grad.cpu().numpy() - g[key + "_dC"]).max() < 1e-5, key
+
+    q, c = fresh()
+    loss, correct = BiEncoderNllLoss().calc(q, c, [int(x) for x in g["nll_pos"]])
+    assert int(correct) == int(g["nll_correct"][0])
+    check(q, c, loss, "nll", g["nll_loss"][0])
+    for T in (1, 2):
+        q, c = fresh()
+        check(q, c, simans_distill_loss(q, c, t, temperature_distill=float(T)), f"kl_T{T}", g[f"kl_T{T}_loss"][0])
+
+    class A:
+        KD_type, TEMPERATURE, CE_WEIGHT, KD_WEIGHT, LwF_WEIGHT = "KD_softmax", 4.0, 0.1, 0.9, 1.0
+
+    q, c = fresh()
+    loss, correct = CrossBERTKDLoss().calc(A, q, c, t)
+    assert int(correct) == int(g["prod_correct"][0])
+    check(q, c, loss, "prod", g["prod_loss"][0])
+    A.KD_type, A.TEMPERATURE = "prob_loss", 1.0
+    q, c = fresh()
+    loss, _ = CrossBERTKDLoss().calc(A, q, c, t)
+    check(q, c, loss, "prob", g["prob_loss"][0])
+
+
+@pytest.mark.parametrize("GQ,group,H,q_begin,q_count", [(8, 4, 64, 0, 8), (6, 3, 128, 0, 6), (16, 8, 768, 4, 4),
+                                                        (1024, 16, 768, 256, 128)])
+def test_score_loss_local_slices_vs_oracle(GQ, group, H, q_begin, q_count):
+    """the global matrix with this rank owning rows [q_begin, +q_count) — multi-GPU bookkeeping without the GPUs;
+    the last case is BASELINE configs[2]'s full size: [1024, 16384] scores, rank 2's slice"""
+    rng = np.random.RandomState(GQ + group)
+    Q = (rng.standard_normal((GQ, H)) * (4.0 / np.sqrt(H))).astype(np.float32)
+    Cm = (rng.standard_normal((GQ * group, H)) * (4.0 / np.sqrt(H))).astype(np.float32)
+    t = (3 * rng.standard_normal((q_count, group))).astype(np.float32)
+    terms = ["nll_global", "kl_local"]
+    w = dict(nll_global=0.2, kl_local=1.0)
+    ref, rdQ, rdC = ln.score_loss(Q, Cm, terms=terms, q_begin=q_begin, q_count=q_count, c_begin=q_begin * group,
+                                  group=group, pos_idx=np.arange(GQ) * group, teacher=t, w=w)
+    lib = _lib.lib()
+    cfg = _lib.LossCfg(terms=_lib.LOSS_NLL_GLOBAL | _lib.LOSS_KL_LOCAL, GQ=GQ, GC=GQ * group, H=H, q_begin=q_begin,
+                       q_count=q_count, c_begin=q_begin * group, c_count=q_count * group, group=group, w_nll_global=0.2,
+                       w_kl_local=1.0, w_ce_local=0, w_kd_local=0, w_nll_local=0, temperature=1.0, eps=1e-7,
+                       score_scale=1.0, grad_scale=1.0)
+    tq, tc, tt = cu(Q), cu(Cm), cu(t)
+    pos = torch.arange(0, GQ * group, group, dtype=torch.int32, device="cuda")
+    ws = torch.empty(lib.simx_score_loss_workspace_bytes(C.byref(cfg)), dtype=torch.uint8, device="cuda")
+    out = torch.empty(8, device="cuda")
+    dQ, dC = torch.empty(q_count, H, device="cuda"), torch.empty(q_count * group, H, device="cuda")
+    _lib.check(lib.simx_score_loss(C.byref(cfg), tq.data_ptr(), tc.data_ptr(), pos.data_ptr(), tt.data_ptr(),
+                                   out.data_ptr(), dQ.data_ptr(), dC.data_ptr(), ws.data_ptr(),
+                                   torch.cuda.current_stream().cuda_stream), "simx_score_loss")
+    assert abs(out[0].item() - ref["total"]) < 1e-4
+    assert abs(out[1].item() - ref["nll_global"]) < 1e-4 and abs(out[2].item() - ref["kl_local"]) < 1e-4
+    assert out[6].item() == ref["n_correct"]
+    assert max_rel(dQ.cpu().numpy(), rdQ) < 1e-4 and max_rel(dC.cpu().numpy(), rdC) < 1e-4
+
+
+def test_score_loss_properties_full_size():
+    """size-independent properties at BASELINE's full per-rank size: gradient rows of a softmax sum to zero against
+    the all-ones direction; equal embeddings give log(GC); scaling grad via the loss cotangent is linear"""
+    GQ, group, H = 1024, 16, 768
+    q = torch.ones(GQ, H, device="cuda") * 0.03
+    c = torch.ones(GQ * group, H, device="cuda") * 0.03
+    loss, _ = fused_score_loss(q, c, ["nll_global"], group_size=group, gather=False)
+    assert abs(loss.item() - np.log(GQ * group)) < 1e-4
+    gen = torch.Generator(device="cuda").manual_seed(0)
+    q = (torch.randn(GQ, H, device="cuda", generator=gen) * 0.1).requires_grad_(True)
+    c = (torch.randn(GQ * group, H, device="cuda", generator=gen) * 0.1).requires_grad_(True)
+    loss, _ = fused_score_loss(q, c, ["nll_global"], group_size=group, gather=False)
+    (3.0 * loss).backward()
+    g3 = q.grad.clone()
+    q.grad = None
+    loss, _ = fused_score_loss(q, c, ["nll_global"], group_size=group, gather=False)
+    loss.backward()
+    assert torch.allclose(g3, 3.0 * q.grad, rtol=1e-4, atol=1e-9)
+    # d(loss)/dC summed over all passages equals -(1/GQ) sum_q (onehot - p) q = 0 contribution identity:
+    # sum_c dC[c] == sum_q (sum_c dS[q,c]) Q[q] and each dS row sums to zero
+    assert c.grad.sum(0).abs().max().item() < 1e-5
+
+
+def test_bad_arguments_raise_with_message():
+    q = torch.randn(4, 64, device="cuda")
+    c = torch.randn(9, 64, device="cuda")
+    with pytest.raises(RuntimeError, match="c_count == q_count"):
+        fused_score_loss(q, c, ["kl_local"], teacher=torch.randn(4, 2, device="cuda"), group_size=2, gather=False)
+    cfg = bn.bert_config(num_layers=1, hidden=64, heads=1, intermediate=64, vocab=50, max_pos=16)
+    m = build(cfg, bn.synth_params(cfg, seed=0), BF16)
+    with pytest.raises(ValueError, match="exceeds"):
+        m.encode(torch.ones(1, 17, dtype=torch.long, device="cuda"))
