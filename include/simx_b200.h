@@ -169,6 +169,16 @@ int simx_gemm(int M, int N, int K, const void* A, int64_t lda, int64_t a_plane_s
               const float* bias, const void* aux, int64_t ldaux, int64_t aux_plane_stride, void* out, void* out2,
               int64_t ldo, int64_t out_plane_stride, float* outf, int64_t ldof, int ksplit, void* stream);
 
+/* Self-attention of the encoder on the fused [T, 3H] projection (q | k | v column blocks, head h at columns h*64):
+ *   ctx = softmax(q k^T / 8 + (1 - mask) * -inf) v       (LEAD/modeling_bert.py:324-368), head_dim 64, S <= 512.
+ * lse2 [B, heads, S] (log2-domain log-sum-exp) is produced by forward and consumed by backward; delta [B, heads, S]
+ * is backward scratch.  planes / plane strides as for simx_gemm. */
+int simx_attention_forward(const void* qkv, void* ctx, const int64_t* mask, float* lse2, int B, int S, int H, int heads,
+                           int planes, int64_t qkv_plane_stride, int64_t ctx_plane_stride, void* stream);
+int simx_attention_backward(const void* qkv, const void* ctx, const void* dctx, void* dqkv, const int64_t* mask,
+                            const float* lse2, float* delta, int B, int S, int H, int heads, int planes,
+                            int64_t qkv_plane_stride, int64_t ctx_plane_stride, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -90,6 +90,8 @@ SIGNATURES = {
     "simx_encoder_backward": (_I, [_CFG, _P, _P, _P, _P, _I, _I, _P, _P, _P, _P, _P, _P]),
     "simx_score_loss_workspace_bytes": (C.c_size_t, [_LCFG]),
     "simx_score_loss": (_I, [_LCFG, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
+    "simx_attention_forward": (_I, [_P, _P, _P, _P, _I, _I, _I, _I, _I, _L, _L, _P]),
+    "simx_attention_backward": (_I, [_P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _L, _L, _P]),
     "simx_gemm": (
         _I,
         [_I, _I, _I, _P, _L, _L, _I, _P, _L, _L, _I, _I, _I, _P, _P, _L, _L, _P, _P, _L, _L, _P, _L, _I, _P],

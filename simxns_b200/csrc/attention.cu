@@ -10,6 +10,8 @@
 //   backward dK/dV rows = keys,    columns = queries: dV = P^T dO, dK = dS^T Q / 8   (S^T recomputed as K Q^T)
 // (legacy tensor path: the tcgen05 version of this kernel is the next step).
 // The fp32-class mode (3 planes) uses the plain FFMA kernels at the bottom of this file.
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "ptx.cuh"
 
@@ -502,6 +504,21 @@ attn_ref_kernel(const AttnRefParams p) {
 // -------------------------------------------------------------------------------------------------
 // host wrappers
 // -------------------------------------------------------------------------------------------------
+int attention_tc_forward(const bf16* qkv, bf16* ctx, const int64_t* mask, float* lse2, int B, int S, int H, int heads,
+                         cudaStream_t st);
+int attention_tc_backward(const bf16* qkv, const bf16* ctx, const bf16* dctx, bf16* dqkv, const int64_t* mask,
+                          const float* lse2, int B, int S, int H, int heads, cudaStream_t st);
+
+// single-tile sequences go to the tcgen05 kernels (attention_tc.cu); SIMX_ATTN_LEGACY=1 forces the mma.sync path
+static bool use_tc_attention(int np, int S) {
+  static int legacy = -1;
+  if (legacy < 0) {
+    const char* e = getenv("SIMX_ATTN_LEGACY");
+    legacy = (e != nullptr && e[0] == '1') ? 1 : 0;
+  }
+  return np == 1 && S <= 128 && legacy == 0;
+}
+
 static int attn_check(int B, int S, int H, int heads) {
   SIMX_CHECK(B > 0 && S > 0, SIMX_ERR_INVALID, "attention: empty batch");
   SIMX_CHECK(heads > 0 && H == heads * ATT_D, SIMX_ERR_INVALID, "attention: head_dim must be 64 (H=%d heads=%d)", H, heads);
@@ -513,6 +530,9 @@ int attention_forward(int np, const bf16* qkv, long ps_qkv, bf16* ctx, long ps_c
                       int B, int S, int H, int heads, cudaStream_t st) {
   SIMX_TRY(attn_check(B, S, H, heads));
   ProfScope prof("attn_fwd", 4.0 * B * heads * (double)S * S * ATT_D, 2.0 * np * B * (double)S * 4 * H, st);
+  if (use_tc_attention(np, S)) {
+    return attention_tc_forward(qkv, ctx, mask, lse2, B, S, H, heads, st);
+  }
   if (np == 3) {
     AttnRefParams p{qkv, ctx, nullptr, nullptr, mask, lse2, nullptr, ps_qkv, ps_ctx, B, S, H, heads};
     dim3 grid((S + 127) / 128, heads, B);
@@ -538,6 +558,7 @@ int attention_backward(int np, const bf16* qkv, long ps_qkv, const bf16* ctx, co
                        cudaStream_t st) {
   SIMX_TRY(attn_check(B, S, H, heads));
   ProfScope prof("attn_bwd", 10.0 * B * heads * (double)S * S * ATT_D, 2.0 * np * B * (double)S * 8 * H, st);
+  if (use_tc_attention(np, S)) return attention_tc_backward(qkv, ctx, dctx, dqkv, mask, lse2, B, S, H, heads, st);
   if (np == 3) {
     AttnRefParams p{qkv, const_cast<bf16*>(ctx), dctx, dqkv, mask, const_cast<float*>(lse2), delta, ps_qkv, ps_ctx,
                     B, S, H, heads};
@@ -566,3 +587,26 @@ int attention_backward(int np, const bf16* qkv, long ps_qkv, const bf16* ctx, co
 }
 
 }  // namespace simx
+
+extern "C" int simx_attention_forward(const void* qkv, void* ctx, const int64_t* mask, float* lse2, int B, int S, int H,
+                                      int heads, int planes, int64_t qkv_plane_stride, int64_t ctx_plane_stride,
+                                      void* stream) {
+  using namespace simx;
+  SIMX_CHECK(qkv && ctx && lse2, SIMX_ERR_INVALID, "attention_forward: null argument");
+  SIMX_CHECK(planes == 1 || planes == 3, SIMX_ERR_INVALID, "attention_forward: planes must be 1 or 3");
+  return attention_forward(planes, static_cast<const bf16*>(qkv), qkv_plane_stride, static_cast<bf16*>(ctx),
+                           ctx_plane_stride, mask, lse2, B, S, H, heads, static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int simx_attention_backward(const void* qkv, const void* ctx, const void* dctx, void* dqkv,
+                                       const int64_t* mask, const float* lse2, float* delta, int B, int S, int H,
+                                       int heads, int planes, int64_t qkv_plane_stride, int64_t ctx_plane_stride,
+                                       void* stream) {
+  using namespace simx;
+  SIMX_CHECK(qkv && ctx && dctx && dqkv && lse2 && delta, SIMX_ERR_INVALID, "attention_backward: null argument");
+  SIMX_CHECK(planes == 1 || planes == 3, SIMX_ERR_INVALID, "attention_backward: planes must be 1 or 3");
+  return attention_backward(planes, static_cast<const bf16*>(qkv), qkv_plane_stride, static_cast<const bf16*>(ctx),
+                            static_cast<const bf16*>(dctx), ctx_plane_stride, static_cast<bf16*>(dqkv), mask, lse2, delta,
+                            B, S, H, heads, static_cast<cudaStream_t>(stream));
+}
+

@@ -1,0 +1,380 @@
+// tcgen05 self-attention for sequences that fit one tile (S <= 128, head_dim 64, bf16 mode): the whole
+// (sequence, head) problem lives on chip.
+//
+//   forward  : TMA(Q,K,V) -> S = Q K^T in TMEM (4 MMAs) -> a thread per query row reads its row of S (tcgen05.ld),
+//              scale + key mask + softmax entirely in-thread (no shuffles), writes P (bf16, 128B-swizzled, over the dead
+//              Q/K tiles) -> O = P V (8 MMAs, V consumed MN-major straight from its [key, d] layout) -> O / l -> smem
+//              -> one TMA store.  128 TMEM columns and 48 KB smem per CTA: four CTAs per SM overlap each other's phases.
+//   backward : TMA(Q,K,V,dO) -> S = Q K^T and dP = dO V^T in TMEM -> P, dS = P o (dP - delta) per row -> smem
+//              -> dV = P^T dO, dK = dS^T Q (A operands MN-major: the transposes are free), dQ = dS K -> three TMA stores.
+//              Five matmuls, each done once; no atomics, no recomputation.  256 TMEM columns, 112 KB smem: two CTAs/SM.
+//
+// Reference math: LEAD/modeling_bert.py:324-368 (scores / sqrt(64) + extended mask, softmax, context).
+// Longer sequences and the fp32-class mode use the kernels in attention.cu.
+#include "common.cuh"
+#include "ptx.cuh"
+
+namespace simx {
+
+int make_tmap_bf16(CUtensorMap* map, const void* ptr, uint64_t inner, uint64_t outer, uint64_t planes, uint64_t ld,
+                   uint64_t plane_stride, uint32_t box_outer);
+
+constexpr float TC_LOG2E = 1.4426950408889634f;
+constexpr float TC_NEG = -1.0e30f;
+constexpr uint32_t TILE = 16384;  // [128 rows x 64 bf16] = 128 rows x 128 B
+
+struct AttnTcParams {
+  const int64_t* mask;  // [B,S] or NULL
+  float* lse2;          // [B, heads, S]
+  const bf16* ctx;      // backward: O (for delta)
+  const bf16* dctx;     // backward: dO
+  int B, S, H, heads;
+  long long* timing;  // debug: 8 clock64 stamps of one CTA (simx_debug_attention_timing), else NULL
+};
+static long long* g_attn_timing = nullptr;
+#define SIMX_STAMP(i) do { if (p.timing != nullptr && tid == 0 && blockIdx.x == 3 && blockIdx.y == gridDim.y / 2) p.timing[i] = clock64(); } while (0)
+
+__device__ __forceinline__ float ex2(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+// K-major operand tile [rows x 128 B], 16 k-elements (32 B) per MMA step
+__device__ __forceinline__ uint64_t desc_k(uint32_t tile, int kstep) { return make_smem_desc_sw128(tile + kstep * 32, 0, 1024); }
+// MN-major operand: [k rows x 128 B] per 64-wide MN atom, atoms `atom_stride` bytes apart, 16 k-rows (2048 B) per step
+__device__ __forceinline__ uint64_t desc_mn(uint32_t tile, int kstep, uint32_t atom_stride) {
+  return make_smem_desc_sw128(tile + kstep * 2048, atom_stride, 1024);
+}
+// byte offset of 16-byte chunk j (0..15: 8 columns each) of row r inside a [128 x 128] bf16 matrix stored as two
+// K-major / MN-major-compatible [128 rows x 64 cols] swizzled blocks
+__device__ __forceinline__ uint32_t p_off(int r, int j) {
+  return (j >> 3) * TILE + r * 128 + (((j & 7) ^ (r & 7)) << 4);
+}
+
+// -------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128, 4)
+attn_fwd_tc_kernel(const AttnTcParams p, const __grid_constant__ CUtensorMap map_qkv,
+                   const __grid_constant__ CUtensorMap map_ctx) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  const uint32_t sQ = smem_u32(smem), sK = sQ + TILE, sV = sK + TILE;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 3 * TILE);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 4);
+  float* bias = reinterpret_cast<float*>(smem + 3 * TILE + 64);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int h = blockIdx.x, b = blockIdx.y, S = p.S;
+
+  if (tid == 0) {
+    tma_prefetch_desc(&map_qkv);
+    tma_prefetch_desc(&map_ctx);
+    mbar_init(&bars[0], 1);
+    mbar_init(&bars[1], 1);
+    mbar_init(&bars[2], 1);
+    fence_mbar_init();
+  }
+  if (warp == 1) tmem_alloc<1>(tmem_slot, 128);
+  bias[tid] = (tid < S && (p.mask == nullptr || p.mask[(long)b * S + tid] != 0)) ? 0.f : TC_NEG;
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+
+  if (tid == 0) {
+    mbar_arrive_expect_tx(&bars[0], 3 * TILE);
+    tma_load_3d(&map_qkv, &bars[0], smem, h * 64, 0, b);
+    tma_load_3d(&map_qkv, &bars[0], smem + TILE, p.H + h * 64, 0, b);
+    tma_load_3d(&map_qkv, &bars[0], smem + 2 * TILE, 2 * p.H + h * 64, 0, b);
+    mbar_wait(&bars[0], 0);
+    tc_fence_after();
+    constexpr uint32_t idesc = make_idesc_bf16(128, 128, false, false);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) umma_bf16<1>(tmem, desc_k(sQ, k), desc_k(sK, k), idesc, k != 0);
+    umma_commit<1>(&bars[1]);
+  }
+  mbar_wait(&bars[1], 0);
+  tc_fence_after();
+
+  const int row = warp * 32 + lane;
+  const uint32_t taddr = tmem + (static_cast<uint32_t>(warp * 32) << 16);
+  const float sl2 = 0.125f * TC_LOG2E;
+  float m = TC_NEG;
+#pragma unroll 1
+  for (int c = 0; c < 4; ++c) {
+    uint32_t v[32];
+    tmem_ld_32x32(taddr + c * 32, v);
+    tmem_ld_wait();
+#pragma unroll
+    for (int i = 0; i < 32; ++i) m = fmaxf(m, fmaf(__uint_as_float(v[i]), sl2, bias[c * 32 + i]));
+  }
+  float l = 0.f;
+#pragma unroll 1
+  for (int c = 0; c < 4; ++c) {
+    uint32_t v[32];
+    tmem_ld_32x32(taddr + c * 32, v);
+    tmem_ld_wait();
+    uint32_t pk[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+      const float p0 = ex2(fmaf(__uint_as_float(v[2 * i]), sl2, bias[c * 32 + 2 * i]) - m);
+      const float p1 = ex2(fmaf(__uint_as_float(v[2 * i + 1]), sl2, bias[c * 32 + 2 * i + 1]) - m);
+      l += p0 + p1;
+      pk[i] = pack_bf16x2(p0, p1);
+    }
+    // P overwrites the Q and K tiles (both dead once S is complete)
+#pragma unroll
+    for (int g = 0; g < 4; ++g)
+      st_shared_v4(sQ + p_off(row, c * 4 + g), make_uint4(pk[4 * g], pk[4 * g + 1], pk[4 * g + 2], pk[4 * g + 3]));
+  }
+  if (row < S && p.lse2 != nullptr) p.lse2[((long)b * p.heads + h) * S + row] = m + log2f(l);
+  fence_proxy_async_smem();
+  tc_fence_before();
+  __syncthreads();
+  if (tid == 0) {
+    tc_fence_after();
+    constexpr uint32_t idesc = make_idesc_bf16(128, 64, false, true);  // A = P K-major, B = V MN-major
+#pragma unroll
+    for (int k = 0; k < 8; ++k)
+      umma_bf16<1>(tmem, desc_k(sQ + (k >> 2) * TILE, k & 3), desc_mn(sV, k, TILE), idesc, k != 0);
+    umma_commit<1>(&bars[2]);
+  }
+  mbar_wait(&bars[2], 0);
+  tc_fence_after();
+  const float inv = 1.f / l;
+#pragma unroll
+  for (int c = 0; c < 2; ++c) {
+    uint32_t v[32];
+    tmem_ld_32x32(taddr + c * 32, v);
+    tmem_ld_wait();
+#pragma unroll
+    for (int g = 0; g < 4; ++g) {
+      uint4 o;
+      o.x = pack_bf16x2(__uint_as_float(v[8 * g]) * inv, __uint_as_float(v[8 * g + 1]) * inv);
+      o.y = pack_bf16x2(__uint_as_float(v[8 * g + 2]) * inv, __uint_as_float(v[8 * g + 3]) * inv);
+      o.z = pack_bf16x2(__uint_as_float(v[8 * g + 4]) * inv, __uint_as_float(v[8 * g + 5]) * inv);
+      o.w = pack_bf16x2(__uint_as_float(v[8 * g + 6]) * inv, __uint_as_float(v[8 * g + 7]) * inv);
+      st_shared_v4(sV + p_off(row, c * 4 + g), o);  // V is dead after the second MMA group; j < 8 stays in this tile
+    }
+  }
+  fence_proxy_async_smem();
+  tc_fence_before();
+  __syncthreads();
+  if (tid == 0) {
+    tma_store_3d(&map_ctx, smem + 2 * TILE, h * 64, 0, b);  // rows >= S fall outside the [H, S, B] tensor: clipped
+    tma_store_commit();
+    tma_store_wait_read<0>();  // smem may be released once read; global visibility comes with kernel completion
+  }
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc<1>(tmem, 128);
+  }
+}
+
+// -------------------------------------------------------------------------------------------------
+// 256 threads: warps w and w+4 share TMEM lane quarter w and split the key columns, so the latency-bound
+// softmax-backward and epilogue phases have twice the warps to overlap
+__global__ void __launch_bounds__(256, 2)
+attn_bwd_tc_kernel(const AttnTcParams p, const __grid_constant__ CUtensorMap map_qkv,
+                   const __grid_constant__ CUtensorMap map_dctx, const __grid_constant__ CUtensorMap map_ctx,
+                   const __grid_constant__ CUtensorMap map_dqkv) {
+  // smem budget for two CTAs per SM is (228 KB / 2) - 1 KB = 115 712 B = 7 tiles + exactly 1 KB: the barriers and the
+  // key-mask row live in the 1 KB in front of the (1024-byte aligned) tiles.
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + 640 + ((1024u - ((smem_u32(smem_raw) + 640u) & 1023u)) & 1023u);
+  {
+    uint32_t dyn;
+    asm("mov.u32 %0, %%dynamic_smem_size;" : "=r"(dyn));
+    if (smem + 7 * TILE > smem_raw + dyn) __trap();  // would only happen if the dynamic window were not 1 KB aligned
+  }
+  // [Q][K][dO][V | P block 0][P block 1][dS block 0][dS block 1]
+  const uint32_t sQ = smem_u32(smem), sK = sQ + TILE, sdO = sK + TILE, sV = sdO + TILE, sP = sV, sdS = sP + 2 * TILE;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 4);
+  float* bias = reinterpret_cast<float*>(smem_raw + 64);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int h = blockIdx.x, b = blockIdx.y, S = p.S;
+  SIMX_STAMP(0);
+
+  if (tid == 0) {
+    tma_prefetch_desc(&map_qkv);
+    tma_prefetch_desc(&map_dctx);
+    tma_prefetch_desc(&map_ctx);
+    tma_prefetch_desc(&map_dqkv);
+    mbar_init(&bars[0], 1);
+    mbar_init(&bars[1], 1);
+    mbar_init(&bars[2], 1);
+    fence_mbar_init();
+  }
+  if (warp == 1) tmem_alloc<1>(tmem_slot, 256);
+  if (tid < 128) bias[tid] = (tid < S && (p.mask == nullptr || p.mask[(long)b * S + tid] != 0)) ? 0.f : TC_NEG;
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+  SIMX_STAMP(1);
+
+  const uint32_t sO = sdS;  // O is only needed for delta: it borrows the first dS tile until dS is written
+  if (tid == 0) {
+    mbar_arrive_expect_tx(&bars[0], 5 * TILE);
+    tma_load_3d(&map_qkv, &bars[0], smem, h * 64, 0, b);
+    tma_load_3d(&map_qkv, &bars[0], smem + TILE, p.H + h * 64, 0, b);
+    tma_load_3d(&map_qkv, &bars[0], smem + 3 * TILE, 2 * p.H + h * 64, 0, b);
+    tma_load_3d(&map_dctx, &bars[0], smem + 2 * TILE, h * 64, 0, b);
+    tma_load_3d(&map_ctx, &bars[0], smem + 5 * TILE, h * 64, 0, b);
+    mbar_wait(&bars[0], 0);
+    tc_fence_after();
+    constexpr uint32_t idesc = make_idesc_bf16(128, 128, false, false);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) umma_bf16<1>(tmem, desc_k(sQ, k), desc_k(sK, k), idesc, k != 0);             // S  = Q K^T
+#pragma unroll
+    for (int k = 0; k < 4; ++k) umma_bf16<1>(tmem + 128, desc_k(sdO, k), desc_k(sV, k), idesc, k != 0);     // dP = dO V^T
+    umma_commit<1>(&bars[1]);
+  }
+  // delta = rowsum(dO o O) from the tiles TMA just landed (rows >= S are zero-filled), while the MMAs run
+  const int quarter = warp & 3, half = warp >> 2;
+  const int row = quarter * 32 + lane;
+  mbar_wait(&bars[0], 0);
+  SIMX_STAMP(2);
+  float delta = 0.f;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const uint4 x = ld_shared_v4(sdO + p_off(row, j)), y = ld_shared_v4(sO + p_off(row, j));
+    const uint32_t xs[4] = {x.x, x.y, x.z, x.w}, ys[4] = {y.x, y.y, y.z, y.w};
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const float2 fx = unpack_bf16x2(xs[k]), fy = unpack_bf16x2(ys[k]);
+      delta += fx.x * fy.x + fx.y * fy.y;
+    }
+  }
+  const float lse = row < S ? p.lse2[((long)b * p.heads + h) * S + row] : 0.f;
+  __syncthreads();  // both column-halves have read their O row before anyone overwrites that tile with dS
+  mbar_wait(&bars[1], 0);
+  tc_fence_after();
+  SIMX_STAMP(3);
+
+  const uint32_t taddr = tmem + (static_cast<uint32_t>(quarter * 32) << 16);
+  const float sl2 = 0.125f * TC_LOG2E;
+  const bool rv = row < S;
+#pragma unroll 1
+  for (int c = half * 2; c < half * 2 + 2; ++c) {
+    uint32_t s[32], d[32];
+    tmem_ld_32x32(taddr + c * 32, s);
+    tmem_ld_32x32(taddr + 128 + c * 32, d);
+    tmem_ld_wait();
+    uint32_t pk[16], dk[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+      float p0 = ex2(fmaf(__uint_as_float(s[2 * i]), sl2, bias[c * 32 + 2 * i]) - lse);
+      float p1 = ex2(fmaf(__uint_as_float(s[2 * i + 1]), sl2, bias[c * 32 + 2 * i + 1]) - lse);
+      if (!rv) { p0 = 0.f; p1 = 0.f; }
+      pk[i] = pack_bf16x2(p0, p1);
+      dk[i] = pack_bf16x2(p0 * (__uint_as_float(d[2 * i]) - delta), p1 * (__uint_as_float(d[2 * i + 1]) - delta));
+    }
+    // P overwrites V (dead once dP is complete) and the tile after it; dS has its own two tiles
+#pragma unroll
+    for (int g = 0; g < 4; ++g) {
+      st_shared_v4(sP + p_off(row, c * 4 + g), make_uint4(pk[4 * g], pk[4 * g + 1], pk[4 * g + 2], pk[4 * g + 3]));
+      st_shared_v4(sdS + p_off(row, c * 4 + g), make_uint4(dk[4 * g], dk[4 * g + 1], dk[4 * g + 2], dk[4 * g + 3]));
+    }
+  }
+  fence_proxy_async_smem();
+  tc_fence_before();
+  __syncthreads();
+  SIMX_STAMP(4);
+  if (tid == 0) {
+    tc_fence_after();
+    constexpr uint32_t id_mnmn = make_idesc_bf16(128, 64, true, true);
+    constexpr uint32_t id_kmn = make_idesc_bf16(128, 64, false, true);
+    // dV[key,d] = sum_q P[q,key] dO[q,d]   (A = P read MN-major: M = keys contiguous, K = query rows)
+#pragma unroll
+    for (int k = 0; k < 8; ++k) umma_bf16<1>(tmem, desc_mn(sP, k, TILE), desc_mn(sdO, k, TILE), id_mnmn, k != 0);
+    // dK[key,d] = sum_q dS[q,key] Q[q,d]
+#pragma unroll
+    for (int k = 0; k < 8; ++k) umma_bf16<1>(tmem + 64, desc_mn(sdS, k, TILE), desc_mn(sQ, k, TILE), id_mnmn, k != 0);
+    // dQ[q,d] = sum_key dS[q,key] K[key,d] (A = dS K-major: two 64-key blocks; B = K MN-major)
+#pragma unroll
+    for (int k = 0; k < 8; ++k)
+      umma_bf16<1>(tmem + 128, desc_k(sdS + (k >> 2) * TILE, k & 3), desc_mn(sK, k, TILE), id_kmn, k != 0);
+    umma_commit<1>(&bars[2]);
+  }
+  mbar_wait(&bars[2], 0);
+  tc_fence_after();
+  SIMX_STAMP(5);
+  // dV -> tile 0 (Q region), dK -> tile 1 (K region), dQ -> tile 2 (dO region): every input tile is dead now
+#pragma unroll 1
+  for (int t = 0; t < 3; ++t) {
+    const float sc = t == 0 ? 1.f : 0.125f;
+    {
+      const int c = half;  // this warp's 32 of the 64 output columns
+      uint32_t v[32];
+      tmem_ld_32x32(taddr + t * 64 + c * 32, v);
+      tmem_ld_wait();
+#pragma unroll
+      for (int g = 0; g < 4; ++g) {
+        uint4 o;
+        o.x = pack_bf16x2(__uint_as_float(v[8 * g]) * sc, __uint_as_float(v[8 * g + 1]) * sc);
+        o.y = pack_bf16x2(__uint_as_float(v[8 * g + 2]) * sc, __uint_as_float(v[8 * g + 3]) * sc);
+        o.z = pack_bf16x2(__uint_as_float(v[8 * g + 4]) * sc, __uint_as_float(v[8 * g + 5]) * sc);
+        o.w = pack_bf16x2(__uint_as_float(v[8 * g + 6]) * sc, __uint_as_float(v[8 * g + 7]) * sc);
+        st_shared_v4(sQ + t * TILE + p_off(row, c * 4 + g), o);
+      }
+    }
+  }
+  fence_proxy_async_smem();
+  tc_fence_before();
+  __syncthreads();
+  SIMX_STAMP(6);
+  if (tid == 0) {
+    tma_store_3d(&map_dqkv, smem, 2 * p.H + h * 64, 0, b);             // dV
+    tma_store_3d(&map_dqkv, smem + TILE, p.H + h * 64, 0, b);          // dK
+    tma_store_3d(&map_dqkv, smem + 2 * TILE, h * 64, 0, b);            // dQ
+    tma_store_commit();
+    tma_store_wait_read<0>();  // smem may be released once read; global visibility comes with kernel completion
+  }
+  SIMX_STAMP(7);
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc<1>(tmem, 256);
+  }
+}
+
+// -------------------------------------------------------------------------------------------------
+int attention_tc_forward(const bf16* qkv, bf16* ctx, const int64_t* mask, float* lse2, int B, int S, int H, int heads,
+                         cudaStream_t st) {
+  CUtensorMap mq, mc;
+  SIMX_TRY(make_tmap_bf16(&mq, qkv, 3 * (uint64_t)H, S, B, 3 * (uint64_t)H, (uint64_t)S * 3 * H, 128));
+  SIMX_TRY(make_tmap_bf16(&mc, ctx, H, S, B, H, (uint64_t)S * H, 128));
+  constexpr int smem = 3 * TILE + 64 + 512 + 1024;
+  static bool attr = false;
+  if (!attr) {
+    SIMX_CUDA(cudaFuncSetAttribute(attn_fwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    attr = true;
+  }
+  AttnTcParams p{mask, lse2, nullptr, nullptr, B, S, H, heads, nullptr};
+  attn_fwd_tc_kernel<<<dim3(heads, B), 128, smem, st>>>(p, mq, mc);
+  SIMX_LAUNCH_CHECK();
+  return SIMX_OK;
+}
+
+int attention_tc_backward(const bf16* qkv, const bf16* ctx, const bf16* dctx, bf16* dqkv, const int64_t* mask,
+                          const float* lse2, int B, int S, int H, int heads, cudaStream_t st) {
+  CUtensorMap mq, md, mo, mg;
+  SIMX_TRY(make_tmap_bf16(&mq, qkv, 3 * (uint64_t)H, S, B, 3 * (uint64_t)H, (uint64_t)S * 3 * H, 128));
+  SIMX_TRY(make_tmap_bf16(&md, dctx, H, S, B, H, (uint64_t)S * H, 128));
+  SIMX_TRY(make_tmap_bf16(&mo, ctx, H, S, B, H, (uint64_t)S * H, 128));
+  SIMX_TRY(make_tmap_bf16(&mg, dqkv, 3 * (uint64_t)H, S, B, 3 * (uint64_t)H, (uint64_t)S * 3 * H, 128));
+  constexpr int smem = 7 * TILE + 1024;
+  static bool attr = false;
+  if (!attr) {
+    SIMX_CUDA(cudaFuncSetAttribute(attn_bwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    attr = true;
+  }
+  AttnTcParams p{mask, const_cast<float*>(lse2), ctx, dctx, B, S, H, heads, g_attn_timing};
+  attn_bwd_tc_kernel<<<dim3(heads, B), 256, smem, st>>>(p, mq, md, mo, mg);
+  SIMX_LAUNCH_CHECK();
+  return SIMX_OK;
+}
+
+}  // namespace simx
+
+// debug hook (not part of the public header): device buffer of >= 8 int64 receiving clock64 stamps of one backward CTA
+extern "C" void simx_debug_attention_timing(long long* device_buffer) { simx::g_attn_timing = device_buffer; }
