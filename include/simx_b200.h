@@ -146,6 +146,25 @@ size_t simx_score_loss_workspace_bytes(const simx_loss_cfg* cfg);
 int simx_score_loss(const simx_loss_cfg* cfg, const float* Q, const float* C, const int32_t* pos_idx,
                     const float* teacher, float* out_losses, float* dQ, float* dC, void* workspace, void* stream);
 
+/* LEAD mutual distillation between two dual encoders on the global score matrices A = Qa Ca^T (student) and
+ * B = Qb Cb^T (teacher)  — replaces the DE->DB branch of distill_loss (LEAD/util.py:594-644, 737-760) and, called once per
+ * selected layer pair on the per-layer [CLS] rows, layer_score_dis_loss (LEAD/util.py:539-559):
+ *   total = w_nll_a NLL(A) + w_nll_b NLL(B) + w_kl_b2a KL(softmax(B/T) || softmax(A)) + w_kl_a2b KL(softmax(A/T) || softmax(B))
+ * KL is `batchmean` over GQ rows; targets are NOT detached (as in the reference): both matrices receive gradients from
+ * every term.  out_losses[8] = {total, nll_a, nll_b, kl_b2a, kl_a2b, 0, 0, 0}.  dQb/dCb may be NULL (frozen teacher).
+ * Local row/column ranges as in simx_loss_cfg; gathered embeddings fp32. */
+typedef struct simx_pair_cfg {
+  int32_t GQ, GC, H;
+  int32_t q_begin, q_count, c_begin, c_count;
+  float w_nll_a, w_nll_b, w_kl_b2a, w_kl_a2b;
+  float temperature;
+  float grad_scale;
+} simx_pair_cfg;
+size_t simx_pair_distill_workspace_bytes(int GQ, int GC, int H);
+int simx_pair_distill(const simx_pair_cfg* cfg, const float* Qa, const float* Ca, const float* Qb, const float* Cb,
+                      const int32_t* pos_idx, float* out_losses, float* dQa, float* dCa, float* dQb, float* dCb,
+                      void* workspace, void* stream);
+
 /* ------------------------------------------------------------------------------------------------
  * Operator-level entry points (used by the unit tests and by bench.py's kernel timing; the encoder calls the
  * same kernels internally).

@@ -108,3 +108,65 @@ def score_loss(Q, C, *, terms, q_begin=0, q_count=None, c_begin=0, group=1, pos_
         dC += (ds[:, :, None] * Ql[:, None, :]).reshape(c_count, H)
 
     return out, dQ * grad_scale, dC * grad_scale
+
+
+def pair_distill(Qa, Ca, Qb, Cb, *, pos_idx, w_nll_a=0.0, w_nll_b=0.0, w_kl_b2a=0.0, w_kl_a2b=0.0, temperature=1.0,
+                 q_begin=0, q_count=None, c_begin=0, c_count=None, grad_scale=1.0):
+    """LEAD mutual distillation between a student (a) and a teacher (b) dual encoder on the global score matrices
+    (/root/reference/LEAD/util.py:594-644 scores, :737-760 assembly; no .detach(): targets carry gradient).
+      total = w_nll_a NLL(A) + w_nll_b NLL(B) + w_kl_b2a KL(softmax(B/T)||softmax(A)) + w_kl_a2b KL(softmax(A/T)||softmax(B))
+    Returns (losses dict, dQa, dCa, dQb, dCb) restricted to the local row / column ranges."""
+    Qa, Ca, Qb, Cb = (np.asarray(x, np.float64) for x in (Qa, Ca, Qb, Cb))
+    GQ, GC = Qa.shape[0], Ca.shape[0]
+    q_count = GQ if q_count is None else q_count
+    c_count = GC if c_count is None else c_count
+    pos = np.asarray(pos_idx, np.int64)
+    A, B = Qa @ Ca.T, Qb @ Cb.T
+    T = temperature
+    lsa, lsb = _log_softmax(A), _log_softmax(B)
+    lta, ltb = _log_softmax(A / T), _log_softmax(B / T)
+    ta, tb = np.exp(lta), np.exp(ltb)
+    rows = np.arange(GQ)
+    nll_a, nll_b = -lsa[rows, pos].mean(), -lsb[rows, pos].mean()
+    k_b2a_row = (tb * (ltb - lsa)).sum(1)
+    k_a2b_row = (ta * (lta - lsb)).sum(1)
+    kl_b2a, kl_a2b = k_b2a_row.mean(), k_a2b_row.mean()
+    total = w_nll_a * nll_a + w_nll_b * nll_b + w_kl_b2a * kl_b2a + w_kl_a2b * kl_a2b
+    oh = np.zeros_like(A)
+    oh[rows, pos] = 1.0
+    pa, pb = np.exp(lsa), np.exp(lsb)
+    dA = (w_nll_a * (pa - oh) + w_kl_b2a * (pa - tb) + w_kl_a2b / T * ta * ((lta - lsb) - k_a2b_row[:, None])) / GQ
+    dB = (w_nll_b * (pb - oh) + w_kl_a2b * (pb - ta) + w_kl_b2a / T * tb * ((ltb - lsa) - k_b2a_row[:, None])) / GQ
+    qs, cs = slice(q_begin, q_begin + q_count), slice(c_begin, c_begin + c_count)
+    out = dict(total=total, nll_a=nll_a, nll_b=nll_b, kl_b2a=kl_b2a, kl_a2b=kl_a2b)
+    g = grad_scale
+    return out, g * dA[qs] @ Ca, g * dA[:, cs].T @ Qa, g * dB[qs] @ Cb, g * dB[:, cs].T @ Qb
+
+
+def lead_de_db_loss(q_db, c_db, q_de, c_de, qL_db, cL_db, qL_de, cL_de, *, group, temperature=1.0, layer_temperature=1.0,
+                    para_db=1.0, para_de=1.0, para_dis=1.0, para_layer=1.0, reweight=True, train_de=True):
+    """The DE -> DB branch of LEAD's distill_loss incl. layer_score_dis_loss (/root/reference/LEAD/util.py:539-559,
+    594-644, 737-770) on already-gathered embeddings.  qL_*/cL_*: lists of per-selected-layer [CLS] matrices.
+    Returns (total, dict of gradients w.r.t. every input)."""
+    GQ = np.asarray(q_db).shape[0]
+    pos = np.arange(GQ) * group
+    out, dqs, dcs, dqt, dct = pair_distill(q_db, c_db, q_de, c_de, pos_idx=pos, w_nll_a=para_db,
+                                           w_nll_b=para_de if train_de else 0.0, w_kl_b2a=para_dis,
+                                           w_kl_a2b=para_dis if train_de else 0.0, temperature=temperature)
+    total = out["total"]
+    grads = dict(q_db=dqs, c_db=dcs, q_de=dqt, c_de=dct, qL_db=[], cL_db=[], qL_de=[], cL_de=[])
+    layer = [pair_distill(a, b, c, d, pos_idx=pos, w_nll_b=0.0, w_kl_b2a=1.0, temperature=temperature)
+             for a, b, c, d in zip(qL_db, cL_db, qL_de, cL_de)]
+    if layer:
+        nll_t = np.array([l[0]["nll_b"] for l in layer])
+        if reweight:  # lambda_i = softmax_i(-NLL(S_de^l) / T_layer), detached (rebuilt via torch.tensor in the reference)
+            z = -nll_t / layer_temperature
+            lam = np.exp(z - z.max())
+            lam /= lam.sum()
+        else:
+            lam = np.full(len(layer), para_layer)
+        for li, l in zip(lam, layer):
+            total += li * l[0]["kl_b2a"]
+            grads["qL_db"].append(li * l[1]); grads["cL_db"].append(li * l[2])
+            grads["qL_de"].append(li * l[3]); grads["cL_de"].append(li * l[4])
+    return total, grads

@@ -262,7 +262,45 @@ def golden_lead_distilbert():
     print("encoder_tiny_distilbert hidden entries:", len(hs))
 
 
+def golden_lead_distill():
+    """the real LEAD distill_loss (DE teacher -> DB student, both trained, per-layer score distillation with
+    re-weighting) on synthetic embeddings / per-layer [CLS] rows: loss + every gradient"""
+    lead_shim()
+    util = import_from(REF / "LEAD", "util")
+    rng = np.random.RandomState(41)
+    GQ, group, H, k = 6, 4, 32, 3
+    mk = lambda *shape: (rng.standard_normal(shape) * 0.5).astype(np.float32)
+    arrs = dict(q_db=mk(GQ, H), c_db=mk(GQ * group, H), q_de=mk(GQ, H), c_de=mk(GQ * group, H),
+                qL_db=mk(GQ, 6, 1, H), cL_db=mk(GQ * group, 6, 1, H), qL_de=mk(GQ, 12, 1, H), cL_de=mk(GQ * group, 12, 1, H))
+    sel_db, sel_de = [1, 3, 5], [7, 9, 11]
+    res = dict(arrs, sel_db=np.array(sel_db), sel_de=np.array(sel_de), group=np.array([group]))
+    for tag, train_de, reweight, T in (("both", True, True, 2.0), ("frozen", False, False, 1.0)):
+        t = {n: torch.from_numpy(v.copy()).requires_grad_(True) for n, v in arrs.items()}
+        args = types.SimpleNamespace(
+            device="cpu", local_rank=-1, distill_ce=False, distill_db=True, distill_de=True, distill_col=False,
+            train_de=train_de, temperature=T, layer_temperature=0.5, distill_de_db_layer_score=True,
+            distill_col_db_layer_score=False, distill_ce_db_layer_score=False, distill_col_db_attention=False,
+            distill_de_db_attention=False, distill_ce_db_attention=False, layer_score_reweight=reweight,
+            distill_para_db=1.0, distill_para_de=0.7, distill_para_de_db_dis=1.5, distill_para_de_db_layer_score=0.3)
+        batch = {"de_ctx_start_end": torch.zeros(GQ, group + 1, 2, dtype=torch.long)}
+        loss, loss_dict = util.distill_loss(args, None, t["q_de"], t["q_db"], None, t["c_de"], t["c_db"], None, sel_db, sel_de,
+                                            None, t["qL_de"], t["cL_de"], t["qL_db"], t["cL_db"], None, None, None, None,
+                                            None, batch)
+        loss.backward()
+        res[tag + "_loss"] = np.array([loss.item()])
+        res[tag + "_cfg"] = np.array([float(train_de), float(reweight), T, 0.5, 1.0, 0.7, 1.5, 0.3])
+        for n, v in t.items():
+            res[f"{tag}_d_{n}"] = (v.grad if v.grad is not None else torch.zeros_like(v)).numpy().copy()
+        print("lead_distill", tag, loss.item(), {k_: round(float(v_), 5) for k_, v_ in loss_dict.items()})
+    np.savez_compressed(GOLD / "lead_distill.npz", **res)
+
+
 def main():
+    only = sys.argv[1:]
+    if only == ["lead"]:
+        GOLD.mkdir(parents=True, exist_ok=True)
+        golden_lead_distill()
+        return
     torch.manual_seed(0)
     torch.set_num_threads(os.cpu_count() or 1)
     GOLD.mkdir(parents=True, exist_ok=True)
@@ -273,6 +311,8 @@ def main():
     simans = import_from(REF / "SimANS", "model.models")
     golden_losses(simans, prod)
     golden_lead_distilbert()
+    if "lead" in only or not only:
+        golden_lead_distill()
     simans = import_from(REF / "SimANS", "model.models")
     golden_biencoder_cfg1(simans)
 

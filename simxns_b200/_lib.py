@@ -65,6 +65,13 @@ class LossCfg(C.Structure):
     ]
 
 
+class PairCfg(C.Structure):
+    """mirror of `simx_pair_cfg`"""
+
+    _fields_ = [(n, C.c_int32) for n in ("GQ", "GC", "H", "q_begin", "q_count", "c_begin", "c_count")] + \
+               [(n, C.c_float) for n in ("w_nll_a", "w_nll_b", "w_kl_b2a", "w_kl_a2b", "temperature", "grad_scale")]
+
+
 _P = C.c_void_p
 _I = C.c_int
 _L = C.c_int64
@@ -90,6 +97,8 @@ SIGNATURES = {
     "simx_encoder_backward": (_I, [_CFG, _P, _P, _P, _P, _I, _I, _P, _P, _P, _P, _P, _P]),
     "simx_score_loss_workspace_bytes": (C.c_size_t, [_LCFG]),
     "simx_score_loss": (_I, [_LCFG, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
+    "simx_pair_distill_workspace_bytes": (C.c_size_t, [_I, _I, _I]),
+    "simx_pair_distill": (_I, [C.POINTER(PairCfg), _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
     "simx_attention_forward": (_I, [_P, _P, _P, _P, _I, _I, _I, _I, _I, _L, _L, _P]),
     "simx_attention_backward": (_I, [_P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _L, _L, _P]),
     "simx_gemm": (

@@ -209,6 +209,166 @@ static LossWs loss_ws(const simx_loss_cfg* c) {
   return w;
 }
 
+// ------------------------------------------------------------------------------------------------
+// LEAD-style mutual distillation between two score matrices A (student) and B (teacher), both [GQ, GC] fp32
+// (LEAD/util.py:594-644 scores, :737-760 loss assembly, no .detach() anywhere — targets carry gradient):
+//   nll_a = NLL(log_softmax(A), pos)               nll_b = NLL(log_softmax(B), pos)
+//   kl_b2a = KL_batchmean(softmax(B/T) || softmax(A))    (teacher targets, student log-probs at temperature 1)
+//   kl_a2b = KL_batchmean(softmax(A/T) || softmax(B))
+// One block per row; three sweeps over the two L2-resident rows: log-sum-exps, KL row sums, gradients.
+// dA/dB are written as 3 bf16 planes for the gradient GEMMs.
+// ------------------------------------------------------------------------------------------------
+struct PairW {
+  float nll_a, nll_b, kl_b2a, kl_a2b, T, grad_scale;
+};
+
+__device__ __forceinline__ void block_lse(const float* s, int n, float invT, float* sh, float& lse_out) {
+  // log-sum-exp of s[0..n) * invT over the block (256 threads); sh: >= 16 floats
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  float m = -INFINITY, sum = 0.f;
+  for (int c = threadIdx.x; c < n; c += 256) {
+    const float v = s[c] * invT;
+    if (v > m) { sum = sum * __expf(m - v) + 1.f; m = v; }
+    else sum += __expf(v - m);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const float m2 = __shfl_xor_sync(0xffffffffu, m, o), s2 = __shfl_xor_sync(0xffffffffu, sum, o);
+    if (m2 > -INFINITY) {
+      const float mn = fmaxf(m, m2);
+      sum = (m > -INFINITY ? sum * __expf(m - mn) : 0.f) + s2 * __expf(m2 - mn);
+      m = mn;
+    }
+  }
+  __syncthreads();
+  if (lane == 0) { sh[warp] = m; sh[8 + warp] = sum; }
+  __syncthreads();
+  float M = sh[0], Ssum = sh[8];
+  for (int k = 1; k < 8; ++k) {
+    if (!(sh[k] > -INFINITY)) continue;
+    const float mn = fmaxf(M, sh[k]);
+    Ssum = (M > -INFINITY ? Ssum * __expf(M - mn) : 0.f) + sh[8 + k] * __expf(sh[k] - mn);
+    M = mn;
+  }
+  lse_out = M + logf(Ssum);
+}
+__device__ __forceinline__ float block_sum(float v, float* sh) {
+  v = warp_sum(v);
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = v;
+  __syncthreads();
+  float t = 0.f;
+  for (int k = 0; k < 8; ++k) t += sh[k];
+  return t;
+}
+
+__global__ void __launch_bounds__(256)
+pair_row_kernel(const float* __restrict__ A, const float* __restrict__ B, int GQ, int GC, int ld,
+                const int32_t* __restrict__ pos_idx, PairW w, bf16* dA, bf16* dB, long ps, float* out_losses) {
+  __shared__ float sh[16];
+  const int row = blockIdx.x;
+  const float* a = A + (long)row * ld;
+  const float* b = B + (long)row * ld;
+  const float invT = 1.f / w.T;
+  float lse_a, lse_b, lse_aT, lse_bT;
+  block_lse(a, GC, 1.f, sh, lse_a);
+  block_lse(b, GC, 1.f, sh, lse_b);
+  block_lse(a, GC, invT, sh, lse_aT);
+  block_lse(b, GC, invT, sh, lse_bT);
+  // KL row sums
+  float k_b2a = 0.f, k_a2b = 0.f;
+  for (int c = threadIdx.x; c < GC; c += 256) {
+    const float lta = a[c] * invT - lse_aT, ltb = b[c] * invT - lse_bT;  // log softmax(./T)
+    const float lsa = a[c] - lse_a, lsb = b[c] - lse_b;
+    k_b2a += __expf(ltb) * (ltb - lsa);
+    k_a2b += __expf(lta) * (lta - lsb);
+  }
+  k_b2a = block_sum(k_b2a, sh);
+  k_a2b = block_sum(k_a2b, sh);
+  const int pos = pos_idx[row];
+  if (threadIdx.x == 0) {
+    const float na = lse_a - a[pos], nb = lse_b - b[pos], r = 1.f / GQ;
+    atomicAdd(out_losses + 1, na * r);
+    atomicAdd(out_losses + 2, nb * r);
+    atomicAdd(out_losses + 3, k_b2a * r);
+    atomicAdd(out_losses + 4, k_a2b * r);
+    atomicAdd(out_losses + 0, (w.nll_a * na + w.nll_b * nb + w.kl_b2a * k_b2a + w.kl_a2b * k_a2b) * r);
+  }
+  const float r = w.grad_scale / GQ;
+  for (int c = threadIdx.x; c < GC; c += 256) {
+    const float lta = a[c] * invT - lse_aT, ltb = b[c] * invT - lse_bT;
+    const float lsa = a[c] - lse_a, lsb = b[c] - lse_b;
+    const float pa = __expf(lsa), pb = __expf(lsb), ta = __expf(lta), tb = __expf(ltb);
+    const float oh = c == pos ? 1.f : 0.f;
+    const float ga = r * (w.nll_a * (pa - oh) + w.kl_b2a * (pa - tb) + w.kl_a2b * invT * ta * ((lta - lsb) - k_a2b));
+    const float gb = r * (w.nll_b * (pb - oh) + w.kl_a2b * (pb - ta) + w.kl_b2a * invT * tb * ((ltb - lsa) - k_b2a));
+    split_store<3>(dA + (long)row * ld + c, ps, ga);
+    if (dB != nullptr) split_store<3>(dB + (long)row * ld + c, ps, gb);
+  }
+}
+
+// shared pieces of the global-matrix paths ---------------------------------------------------------
+struct ScoreWs {  // per embedding pair (Q, C): planes, transposed planes, scores, score gradients
+  size_t qp, cp, ctp, s, ds, total;
+};
+static ScoreWs score_ws(int GQ, int GC, int H) {
+  ScoreWs w{};
+  const size_t GCp = (GC + 7) / 8 * 8;
+  size_t off = 0;
+  w.qp = off;  off += align256(3ull * GQ * H * 2);
+  w.cp = off;  off += align256(3ull * GCp * H * 2);
+  w.ctp = off; off += align256(3ull * GCp * H * 2);
+  w.s = off;   off += align256(4ull * GQ * GCp);
+  w.ds = off;  off += align256(3ull * GQ * GCp * 2);
+  w.total = off;
+  return w;
+}
+// S = Q C^T in fp32-class precision (planes of Q, C and C^T stay in the workspace for the gradient GEMMs)
+static int score_forward(const float* Q, const float* C, int GQ, int GC, int H, uint8_t* ws, const ScoreWs& w,
+                         cudaStream_t st) {
+  const int GCp = (GC + 7) / 8 * 8;
+  bf16* Qp = reinterpret_cast<bf16*>(ws + w.qp);
+  bf16* Cp = reinterpret_cast<bf16*>(ws + w.cp);
+  bf16* CTp = reinterpret_cast<bf16*>(ws + w.ctp);
+  float* S = reinterpret_cast<float*>(ws + w.s);
+  const long q_ps = (long)GQ * H, c_ps = (long)GCp * H;
+  if (GCp != GC) {
+    SIMX_CUDA(cudaMemsetAsync(Cp, 0, 3ull * GCp * H * 2, st));
+    SIMX_CUDA(cudaMemsetAsync(CTp, 0, 3ull * GCp * H * 2, st));
+    SIMX_CUDA(cudaMemsetAsync(ws + w.ds, 0, 3ull * GQ * GCp * 2, st));
+  }
+  SIMX_TRY(convert_weight(3, Q, GQ, H, Qp, H, q_ps, nullptr, 0, 0, st));
+  SIMX_TRY(convert_weight(3, C, GC, H, Cp, H, c_ps, CTp, GCp, c_ps, st));
+  SIMX_CUDA(cudaMemsetAsync(S, 0, 4ull * GQ * GCp, st));
+  return gemm(GQ, GCp, H, Qp, H, q_ps, false, Cp, H, c_ps, false, 3, SIMX_EPI_ATOMIC_F32, nullptr, nullptr, 0, 0, nullptr,
+              nullptr, 0, 0, S, GCp, 1, st);
+}
+// dQ_local = dS[local rows] C ;  dC_local = dS[:, local cols]^T Q     (both overwritten)
+static int score_backward(int GQ, int GC, int H, int q_begin, int q_count, int c_begin, int c_count, uint8_t* ws,
+                          const ScoreWs& w, float* dQ, float* dC, cudaStream_t st) {
+  const int GCp = (GC + 7) / 8 * 8;
+  bf16* Qp = reinterpret_cast<bf16*>(ws + w.qp);
+  bf16* CTp = reinterpret_cast<bf16*>(ws + w.ctp);
+  bf16* dS = reinterpret_cast<bf16*>(ws + w.ds);
+  const long q_ps = (long)GQ * H, c_ps = (long)GCp * H, s_ps = (long)GQ * GCp;
+  SIMX_CUDA(cudaMemsetAsync(dQ, 0, 4ull * q_count * H, st));
+  SIMX_CUDA(cudaMemsetAsync(dC, 0, 4ull * c_count * H, st));
+  const int sms = num_sms();
+  {
+    const int tiles = ((q_count + 127) / 128) * ((H + 255) / 256);
+    const int ksplit = max(1, min((GCp + 63) / 64, (sms + tiles - 1) / tiles));
+    SIMX_TRY(gemm(q_count, H, GCp, dS + (long)q_begin * GCp, GCp, s_ps, false, CTp, GCp, c_ps, false, 3,
+                  SIMX_EPI_ATOMIC_F32, nullptr, nullptr, 0, 0, nullptr, nullptr, 0, 0, dQ, H, ksplit, st));
+  }
+  {
+    const int tiles = ((c_count + 127) / 128) * ((H + 255) / 256);
+    const int ksplit = max(1, min((GQ + 63) / 64, (sms + tiles - 1) / tiles));
+    SIMX_TRY(gemm(c_count, H, GQ, dS + c_begin, GCp, s_ps, true, Qp, H, q_ps, true, 3, SIMX_EPI_ATOMIC_F32, nullptr,
+                  nullptr, 0, 0, nullptr, nullptr, 0, 0, dC, H, ksplit, st));
+  }
+  return SIMX_OK;
+}
+
 }  // namespace simx
 
 extern "C" size_t simx_score_loss_workspace_bytes(const simx_loss_cfg* cfg) { return simx::loss_ws(cfg).total; }
@@ -288,3 +448,40 @@ extern "C" int simx_score_loss(const simx_loss_cfg* cfg, const float* Q, const f
   }
   return SIMX_OK;
 }
+
+extern "C" size_t simx_pair_distill_workspace_bytes(int GQ, int GC, int H) {
+  return 2 * simx::score_ws(GQ, GC, H).total + 512;
+}
+
+extern "C" int simx_pair_distill(const simx_pair_cfg* cfg, const float* Qa, const float* Ca, const float* Qb,
+                                 const float* Cb, const int32_t* pos_idx, float* out_losses, float* dQa, float* dCa,
+                                 float* dQb, float* dCb, void* workspace, void* stream) {
+  using namespace simx;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  SIMX_CHECK(cfg && Qa && Ca && Qb && Cb && pos_idx && out_losses && dQa && dCa && workspace, SIMX_ERR_INVALID,
+             "pair_distill: null argument");
+  const int GQ = cfg->GQ, GC = cfg->GC, H = cfg->H;
+  SIMX_CHECK(GQ > 0 && GC > 0 && H > 0 && H % 8 == 0, SIMX_ERR_INVALID, "pair_distill: bad sizes GQ=%d GC=%d H=%d", GQ, GC, H);
+  SIMX_CHECK(cfg->q_count > 0 && cfg->q_begin >= 0 && cfg->q_begin + cfg->q_count <= GQ && cfg->c_count > 0 &&
+                 cfg->c_begin >= 0 && cfg->c_begin + cfg->c_count <= GC && cfg->c_begin % 8 == 0,
+             SIMX_ERR_INVALID, "pair_distill: bad local ranges");
+  SIMX_CHECK(cfg->temperature > 0.f, SIMX_ERR_INVALID, "pair_distill: temperature must be positive");
+  const bool train_b = dQb != nullptr && dCb != nullptr;
+  const ScoreWs w = score_ws(GQ, GC, H);
+  uint8_t* wa = static_cast<uint8_t*>(workspace);
+  wa += (256 - (reinterpret_cast<uintptr_t>(wa) & 255)) & 255;
+  uint8_t* wb = wa + w.total;
+  const int GCp = (GC + 7) / 8 * 8;
+  SIMX_CUDA(cudaMemsetAsync(out_losses, 0, 8 * sizeof(float), st));
+  SIMX_TRY(score_forward(Qa, Ca, GQ, GC, H, wa, w, st));
+  SIMX_TRY(score_forward(Qb, Cb, GQ, GC, H, wb, w, st));
+  PairW pw{cfg->w_nll_a, cfg->w_nll_b, cfg->w_kl_b2a, cfg->w_kl_a2b, cfg->temperature, cfg->grad_scale};
+  pair_row_kernel<<<GQ, 256, 0, st>>>(reinterpret_cast<const float*>(wa + w.s), reinterpret_cast<const float*>(wb + w.s), GQ,
+                                      GC, GCp, pos_idx, pw, reinterpret_cast<bf16*>(wa + w.ds),
+                                      train_b ? reinterpret_cast<bf16*>(wb + w.ds) : nullptr, (long)GQ * GCp, out_losses);
+  SIMX_LAUNCH_CHECK();
+  SIMX_TRY(score_backward(GQ, GC, H, cfg->q_begin, cfg->q_count, cfg->c_begin, cfg->c_count, wa, w, dQa, dCa, st));
+  if (train_b) SIMX_TRY(score_backward(GQ, GC, H, cfg->q_begin, cfg->q_count, cfg->c_begin, cfg->c_count, wb, w, dQb, dCb, st));
+  return SIMX_OK;
+}
+

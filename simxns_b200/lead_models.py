@@ -1,0 +1,114 @@
+"""Drop-in for /root/reference/LEAD/models.py on the dual-encoder path (HFBertEncoder :144-196, HFDistilBertEncoder
+:31-77, BiBertEncoder :198-242, Reranker :249-267): same class names, constructor / forward signatures and 5-tuple
+returns, running on libsimx_b200.
+
+Difference that matters: LEAD returns (and all-gathers, util.py:572-579) the FULL per-layer hidden states
+`all_layer_hidden [B, L, S, H]` although `distill_loss` only reads the [CLS] row `[:, l, 0, :]` of the selected layers
+(util.py:605, 631) unless the VIRT attention-map losses are on (out of scope).  Here `all_layer_hidden` is
+`[B, L, 1, H]` — the [CLS] rows only — so every `[:, l, 0, :]` read in LEAD's code keeps working and carries gradient back
+into layer l (the encoder backward accepts a cotangent on every layer's [CLS] row).  Layer indexing is LEAD's: entry k is
+the output of transformer layer k (the embedding output is not included, LEAD/modeling_bert.py:607-646).
+"""
+from __future__ import annotations
+
+from typing import Optional
+
+import torch
+from torch import Tensor as T
+from torch import nn
+
+from . import models as _m
+from .encoder import EncoderConfig
+
+
+class HFBertEncoder(_m.HFBertEncoder):
+    """LEAD/models.py:144-196"""
+
+    @classmethod
+    def init_encoder(cls, args, dropout: float = 0.1, pretrained_model_name=None):
+        name = args.pretrained_model_name
+        path = "pretrain_models/MASTER-MARCO" if name == "master" else name
+        cfg = _m._load_hf_config(path, "bert")
+        cfg.output_hidden_states = True
+        if dropout != 0:
+            cfg.attention_probs_dropout_prob = dropout
+            cfg.hidden_dropout_prob = dropout
+        cfg.gradient_checkpointing = getattr(args, "gradient_checkpointing", False)
+        return cls.from_pretrained(path, config=cfg)
+
+    init_encoder_from_my_model = init_encoder
+
+    def forward(self, input_ids=None, attention_mask=None, output_attentions=None, **kwargs):
+        if output_attentions:
+            raise NotImplementedError("attention maps (LEAD VIRT losses) are not produced by the fused attention kernel")
+        cls, seq = self.encode(input_ids, attention_mask, want_sequence=kwargs.pop("_want_sequence", False))
+        pooled_output = cls[:, -1, :]
+        all_layer_hidden = cls[:, 1:, None, :]  # [B, L, 1, H]: the [CLS] row of every transformer layer
+        return seq, pooled_output, None, None, all_layer_hidden
+
+
+class HFDistilBertEncoder(_m.HFDistilBertEncoder):
+    """LEAD/models.py:31-77 (add_linear is not supported: the shipped scripts do not set it)"""
+
+    def __init__(self, config, precision: Optional[int] = None):
+        if getattr(config, "add_linear", False):
+            raise NotImplementedError("add_linear=True (extra projection on the student) is not implemented")
+        super().__init__(config, precision)
+
+    forward = HFBertEncoder.forward
+
+
+class BiBertEncoder(nn.Module):
+    """LEAD/models.py:198-242: forward(query_ids, attention_mask_q, doc_ids, attention_mask_d) ->
+    (q_embs, d_embs, q_all_layer_hidden, d_all_layer_hidden, mask_doc)"""
+
+    def __init__(self, args, question_model: Optional[nn.Module] = None, ctx_model: Optional[nn.Module] = None):
+        super().__init__()
+        if question_model is not None:
+            self.model_type = getattr(args, "model_type", "dual_encoder") if args is not None else "dual_encoder"
+            self.question_model = question_model
+            self.ctx_model = ctx_model if ctx_model is not None else question_model
+            return
+        self.pretrained_model_name = args.pretrained_model_name
+        self.model_type = args.model_type
+        self.device = args.device
+        if 'colbert' in args.model_type:
+            raise NotImplementedError("ColBERT late interaction is out of scope (SURVEY §2.1)")
+        enc = HFDistilBertEncoder if 'distilbert' in args.model_type else HFBertEncoder
+        self.question_model = enc.init_encoder(args)
+        if hasattr(args, 'share_weight') and args.share_weight:
+            self.ctx_model = self.question_model
+        else:
+            self.ctx_model = enc.init_encoder(args)
+
+    def query_emb(self, mode, input_ids, attention_mask):
+        _, pooled_output, _, _, all_layer_hidden = self.question_model(input_ids=input_ids, attention_mask=attention_mask)
+        return pooled_output, all_layer_hidden, None
+
+    def body_emb(self, mode, input_ids, attention_mask):
+        _, pooled_output, _, _, all_layer_hidden = self.ctx_model(input_ids=input_ids, attention_mask=attention_mask)
+        return pooled_output, all_layer_hidden, None
+
+    def forward(self, query_ids, attention_mask_q, doc_ids=None, attention_mask_d=None):
+        q_embs, q_all_layer_hidden, _ = self.query_emb(self.model_type + '_query', query_ids, attention_mask_q)
+        d_embs, d_all_layer_hidden, mask_doc = self.body_emb(self.model_type + '_doc', doc_ids, attention_mask_d)
+        return q_embs, d_embs, q_all_layer_hidden, d_all_layer_hidden, mask_doc
+
+
+class Reranker(nn.Module):
+    """LEAD/models.py:249-267: also returns the per-layer relevance logits `[L, N, M]` (qa_classifier on every layer's
+    [CLS]); attention maps are returned as None."""
+
+    def __init__(self, encoder: nn.Module, hidden_size):
+        super().__init__()
+        self.encoder = encoder
+        self.qa_classifier = nn.Linear(hidden_size, 1)
+        _m.init_weights([self.qa_classifier])
+
+    def forward(self, input_ids: T, attention_mask: T):
+        N, M, L = input_ids.size()
+        seq, pooled, _, _, all_layer_hidden = self.encoder(input_ids=input_ids.view(N * M, L),
+                                                           attention_mask=attention_mask.view(N * M, L))
+        rank_logits = self.qa_classifier(pooled)
+        rank_logits_all_layer = self.qa_classifier(all_layer_hidden[:, :, 0, :])  # [N*M, L, 1]
+        return rank_logits.view(N, M), None, rank_logits_all_layer.permute([1, 0, 2]).view(rank_logits_all_layer.shape[1], N, M)

@@ -185,3 +185,90 @@ def simans_distill_loss(local_q_vector, local_ctx_vectors, relevance_logits, tem
                                temperature=temperature_distill, eps=eps, score_scale=scale,
                                group_size=local_ctx_vectors.shape[0] // nq, gather=False)
     return loss
+
+
+# ---------------------------------------------------------------------------------------------------------
+# LEAD: mutual distillation between two dual encoders on the global score matrices (simx_pair_distill)
+# ---------------------------------------------------------------------------------------------------------
+PAIR_FIELDS = ("total", "nll_a", "nll_b", "kl_b2a", "kl_a2b")
+
+
+class _PairDistillFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, q_a, c_a, q_b, c_b, opts):
+        lib = _lib.lib()
+        dev = q_a.device
+        if dev.type != "cuda":
+            raise RuntimeError("fused_pair_distill needs CUDA tensors (no CPU fallback)")
+        with torch.cuda.device(dev):
+            _lib.require_device()
+            loc = [t.detach().to(torch.float32).contiguous() for t in (q_a, c_a, q_b, c_b)]
+            nq, H = loc[0].shape
+            nc = loc[1].shape[0]
+            rank, world = 0, 1
+            if opts.get("gather", True) and dist.is_available() and dist.is_initialized():
+                rank, world = dist.get_rank(opts.get("group")), dist.get_world_size(opts.get("group"))
+            glob = [gather_embeddings(t, opts.get("group")) for t in loc] if world > 1 else loc
+            GQ, GC = glob[0].shape[0], glob[1].shape[0]
+            group = opts.get("group_size") or (nc // nq)
+            pos = torch.arange(0, GQ * group, group, device=dev, dtype=torch.int32)  # LEAD/util.py:596
+            w = opts["weights"]
+            train_b = any(ctx.needs_input_grad[2:4])
+            cfg = _lib.PairCfg(GQ=GQ, GC=GC, H=H, q_begin=rank * nq, q_count=nq, c_begin=rank * nc, c_count=nc,
+                               w_nll_a=w.get("nll_a", 0.0), w_nll_b=w.get("nll_b", 0.0), w_kl_b2a=w.get("kl_b2a", 0.0),
+                               w_kl_a2b=w.get("kl_a2b", 0.0), temperature=opts.get("temperature", 1.0), grad_scale=1.0)
+            ws = torch.empty(lib.simx_pair_distill_workspace_bytes(GQ, GC, H), dtype=torch.uint8, device=dev)
+            losses = torch.empty(8, dtype=torch.float32, device=dev)
+            grads = [torch.empty_like(loc[0]), torch.empty_like(loc[1]),
+                     torch.empty_like(loc[2]) if train_b else None, torch.empty_like(loc[3]) if train_b else None]
+            stream = torch.cuda.current_stream(dev).cuda_stream
+            _lib.check(lib.simx_pair_distill(C.byref(cfg), glob[0].data_ptr(), glob[1].data_ptr(), glob[2].data_ptr(),
+                                             glob[3].data_ptr(), pos.data_ptr(), losses.data_ptr(), grads[0].data_ptr(),
+                                             grads[1].data_ptr(), _lib.ptr(grads[2]), _lib.ptr(grads[3]), ws.data_ptr(),
+                                             stream), "simx_pair_distill")
+        ctx.grads = grads
+        ctx.mark_non_differentiable(losses)
+        return losses[0].clone(), losses
+
+    @staticmethod
+    def backward(ctx, g_total, _g):
+        return tuple(None if g is None else g * g_total for g in ctx.grads) + (None,)
+
+
+def fused_pair_distill(q_a, c_a, q_b, c_b, weights: dict, *, temperature: float = 1.0, group_size: Optional[int] = None,
+                       gather: bool = True, group=None):
+    """a = student, b = teacher (local embeddings, all-gathered inside).  weights: nll_a, nll_b, kl_b2a (teacher targets ->
+    student), kl_a2b.  -> (total with autograd into all four inputs, detail [8] = PAIR_FIELDS + pad)."""
+    opts = dict(weights=dict(weights), temperature=float(temperature), group_size=group_size, gather=gather, group=group)
+    return _PairDistillFn.apply(q_a, c_a, q_b, c_b, opts)
+
+
+def lead_distill_loss(q_db, c_db, q_de, c_de, cls_q_db=None, cls_c_db=None, cls_q_de=None, cls_c_de=None, *,
+                      selected_db: Sequence[int] = (), selected_de: Sequence[int] = (), temperature: float = 1.0,
+                      layer_temperature: float = 1.0, para_db: float = 1.0, para_de: float = 1.0, para_dis: float = 1.0,
+                      para_layer: float = 1.0, reweight: bool = True, train_de: bool = True, gather: bool = True):
+    """DE-teacher -> DB-student branch of LEAD's distill_loss with layer_score_dis_loss
+    (/root/reference/LEAD/util.py:539-559, 594-644, 737-770).
+
+    q_*/c_*: local final embeddings; cls_*: per-layer [CLS] rows `[n, L, H]` in LEAD's layer indexing (layer k =
+    `cls_layers[:, k+1]` of the encoder, i.e. pass `encoder.last_cls_layers[:, 1:]`).  Only the [CLS] rows are gathered —
+    the reference all-gathers the full [n, L, S, H] hidden states and then reads [:, l, 0, :] (util.py:572-573, 605).
+    Returns (loss, dict of detached component values)."""
+    w = dict(nll_a=para_db, nll_b=para_de if train_de else 0.0, kl_b2a=para_dis, kl_a2b=para_dis if train_de else 0.0)
+    loss, detail = fused_pair_distill(q_db, c_db, q_de, c_de, w, temperature=temperature, gather=gather)
+    parts = dict(loss_db=detail[1], loss_dual=detail[2], loss_de_db_dis=detail[3], loss_db_de_dis=detail[4])
+    if len(selected_db):
+        kls, nlls = [], []
+        for ls, lt in zip(selected_db, selected_de):
+            kl, d = fused_pair_distill(cls_q_db[:, ls], cls_c_db[:, ls], cls_q_de[:, lt], cls_c_de[:, lt],
+                                       dict(kl_b2a=1.0), temperature=temperature, gather=gather)
+            kls.append(kl)
+            nlls.append(d[2])
+        if reweight:  # lambda = softmax(-NLL(teacher layer scores) / T_layer), a constant (util.py:548-550)
+            lam = torch.softmax(-torch.stack(nlls).detach() / layer_temperature, dim=0)
+        else:
+            lam = torch.full((len(kls),), float(para_layer), device=loss.device)
+        layer_loss = sum(l * k for l, k in zip(lam, kls))
+        loss = loss + layer_loss
+        parts["loss_de_db_layer_dis"] = layer_loss.detach()
+    return loss, parts

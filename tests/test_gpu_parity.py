@@ -57,7 +57,7 @@ def max_rel(a, b):
 def assert_grads(model, ref_grads, tol, prefix="", zero_true=()):
     scales = [np.abs(v).max() for v in ref_grads.values() if np.abs(v).max() > 0]
     floor = 1e-3 * float(np.median(scales))
-    worst = ("", 0.0)
+    worst = ("", 0.0, 0.0, 0.0)
     for name, p in model.named_parameters():
         assert p.grad is not None, f"{name} received no gradient (DDP needs dense grads for every parameter)"
         r = ref_grads[prefix + name]
@@ -67,8 +67,9 @@ def assert_grads(model, ref_grads, tol, prefix="", zero_true=()):
         fl = max(scales) if is_zero else floor
         e = float(np.abs(p.grad.cpu().numpy() - r).max() / max(np.abs(r).max(), fl))
         if e > worst[1]:
-            worst = (name, e)
-    assert worst[1] < tol, f"gradient of {worst[0]} off by {worst[1]:.3e} (tol {tol})"
+            worst = (name, e, float(np.abs(r).max()), fl)
+    assert worst[1] < tol, (f"gradient of {worst[0]} off by {worst[1]:.3e} (tol {tol}); |ref|max {worst[2]:.3e}, "
+                            f"scale floor {worst[3]:.3e}, largest gradient scale {max(scales):.3e}")
 
 
 # ---------------------------------------------------------------------------------------------------------
@@ -343,3 +344,119 @@ def test_bad_arguments_raise_with_message():
     m = build(cfg, bn.synth_params(cfg, seed=0), BF16)
     with pytest.raises(ValueError, match="exceeds"):
         m.encode(torch.ones(1, 17, dtype=torch.long, device="cuda"))
+
+
+# ---------------------------------------------------------------------------------------------------------
+# LEAD mutual distillation (simx_pair_distill) vs the real LEAD distill_loss
+# ---------------------------------------------------------------------------------------------------------
+def test_lead_distill_vs_reference_golden(golden_dir):
+    from simxns_b200.losses import lead_distill_loss
+
+    g = np.load(golden_dir / "lead_distill.npz")
+    sel_db, sel_de = [int(x) for x in g["sel_db"]], [int(x) for x in g["sel_de"]]
+    for tag in ("both", "frozen"):
+        train_de, reweight, T, Tl, p_db, p_de, p_dis, p_layer = [float(x) for x in g[tag + "_cfg"]]
+        t = {n: cu(g[n]).requires_grad_(True) for n in ("q_db", "c_db", "q_de", "c_de", "qL_db", "cL_db", "qL_de", "cL_de")}
+        loss, parts = lead_distill_loss(t["q_db"], t["c_db"], t["q_de"], t["c_de"], t["qL_db"][:, :, 0], t["cL_db"][:, :, 0],
+                                        t["qL_de"][:, :, 0], t["cL_de"][:, :, 0], selected_db=sel_db, selected_de=sel_de,
+                                        temperature=T, layer_temperature=Tl, para_db=p_db, para_de=p_de, para_dis=p_dis,
+                                        para_layer=p_layer, reweight=bool(reweight), train_de=bool(train_de), gather=False)
+        assert abs(loss.item() - g[tag + "_loss"][0]) < 1e-4
+        loss.backward()
+        for n in t:
+            ref = g[f"{tag}_d_{n}"]
+            got = t[n].grad.cpu().numpy() if t[n].grad is not None else np.zeros_like(ref)
+            assert np.abs(got - ref).max() < 1e-3 * max(1e-3, np.abs(ref).max()), (tag, n)
+
+
+def test_pair_distill_local_slices_vs_oracle():
+    rng = np.random.RandomState(4)
+    GQ, group, H = 64, 8, 256
+    mk = lambda n: (rng.standard_normal((n, H)) * (3.0 / np.sqrt(H))).astype(np.float32)
+    Qa, Ca, Qb, Cb = mk(GQ), mk(GQ * group), mk(GQ), mk(GQ * group)
+    kw = dict(w_nll_a=1.0, w_nll_b=0.5, w_kl_b2a=1.5, w_kl_a2b=0.25, temperature=2.0)
+    q0, qn = 16, 16
+    ref, *rg = ln.pair_distill(Qa, Ca, Qb, Cb, pos_idx=np.arange(GQ) * group, q_begin=q0, q_count=qn, c_begin=q0 * group,
+                               c_count=qn * group, **kw)
+    lib = _lib.lib()
+    cfg = _lib.PairCfg(GQ=GQ, GC=GQ * group, H=H, q_begin=q0, q_count=qn, c_begin=q0 * group, c_count=qn * group,
+                       grad_scale=1.0, **kw)
+    ts = [cu(x) for x in (Qa, Ca, Qb, Cb)]
+    pos = torch.arange(0, GQ * group, group, dtype=torch.int32, device="cuda")
+    ws = torch.empty(lib.simx_pair_distill_workspace_bytes(GQ, GQ * group, H), dtype=torch.uint8, device="cuda")
+    out = torch.empty(8, device="cuda")
+    gs = [torch.empty(qn, H, device="cuda"), torch.empty(qn * group, H, device="cuda"), torch.empty(qn, H, device="cuda"),
+          torch.empty(qn * group, H, device="cuda")]
+    _lib.check(lib.simx_pair_distill(C.byref(cfg), *[t.data_ptr() for t in ts], pos.data_ptr(), out.data_ptr(),
+                                     *[t.data_ptr() for t in gs], ws.data_ptr(), torch.cuda.current_stream().cuda_stream),
+               "simx_pair_distill")
+    assert abs(out[0].item() - ref["total"]) < 1e-4
+    for got, want in zip(gs, rg):
+        assert max_rel(got.cpu().numpy(), want) < 1e-4
+
+
+def test_lead_end_to_end_step_vs_oracle():
+    """LEAD distillation step: 4-layer BERT teacher -> 2-layer DistilBERT student, both shared-weight dual
+    encoders, response + per-layer score distillation with lambda re-weighting; gradients enter the towers at
+    intermediate layers' [CLS] rows.  Checked end to end against the numpy oracle."""
+    from simxns_b200 import lead_models as lm
+    from simxns_b200.losses import lead_distill_loss
+
+    cfg_t = bn.bert_config(num_layers=4, hidden=64, heads=1, intermediate=128, vocab=200, max_pos=64)
+    cfg_s = bn.bert_config(num_layers=2, hidden=64, heads=1, intermediate=128, vocab=200, max_pos=64, arch="distilbert")
+    p_t, p_s = bn.synth_params(cfg_t, seed=51), bn.synth_params(cfg_s, seed=52)
+    # keep the problem well conditioned: with unit LayerNorm gains |q.c| reaches ~65 on random weights, every softmax
+    # row is one-hot to 1e-20 and the gradients are pure cancellation (fp32 round-off of the scores dominates them)
+    for p in (p_t, p_s):
+        for k in p:
+            if k.endswith("LayerNorm.weight") or k.endswith("layer_norm.weight"):
+                p[k] = (p[k] * 0.3).astype(np.float32)
+    nq, group = 4, 2
+    q_ids, q_mask = bn.synth_tokens(nq, 12, 200, seed=53, ragged=True)
+    d_ids, d_mask = bn.synth_tokens(nq * group, 40, 200, seed=54, ragged=True, min_len=6)
+    sel_s, sel_t = [0, 1], [1, 3]
+    hp = dict(temperature=2.0, layer_temperature=0.5, para_db=1.0, para_de=0.7, para_dis=1.5)
+
+    # ---- oracle
+    ot, os_ = bn.EncoderOracle(cfg_t, p_t), bn.EncoderOracle(cfg_s, p_s)
+    outs = {}
+    for name, ora, ids, m in (("tq", ot, q_ids, q_mask), ("td", ot, d_ids, d_mask), ("sq", os_, q_ids, q_mask),
+                              ("sd", os_, d_ids, d_mask)):
+        outs[name] = ora.forward(ids, m)["cls"]
+    total, gr = ln.lead_de_db_loss(outs["sq"][:, -1], outs["sd"][:, -1], outs["tq"][:, -1], outs["td"][:, -1],
+                                   [outs["sq"][:, l + 1] for l in sel_s], [outs["sd"][:, l + 1] for l in sel_s],
+                                   [outs["tq"][:, l + 1] for l in sel_t], [outs["td"][:, l + 1] for l in sel_t],
+                                   group=group, reweight=True, train_de=True, **hp)
+
+    def tower_grads(cfg, params, passes):
+        tot = None
+        for ids, m, d_final, layer_sel, d_layers in passes:
+            ora = bn.EncoderOracle(cfg, params)
+            ora.forward(ids, m)
+            d_cls = np.zeros((ids.shape[0], cfg["num_layers"] + 1, cfg["hidden"]))
+            d_cls[:, -1] += d_final
+            for l, d in zip(layer_sel, d_layers):
+                d_cls[:, l + 1] += d
+            g = ora.backward(d_cls=d_cls)
+            tot = g if tot is None else {k: tot[k] + g[k] for k in g}
+        return tot
+
+    ref_s = tower_grads(cfg_s, p_s, [(q_ids, q_mask, gr["q_db"], sel_s, gr["qL_db"]), (d_ids, d_mask, gr["c_db"], sel_s, gr["cL_db"])])
+    ref_t = tower_grads(cfg_t, p_t, [(q_ids, q_mask, gr["q_de"], sel_t, gr["qL_de"]), (d_ids, d_mask, gr["c_de"], sel_t, gr["cL_de"])])
+
+    # ---- B200
+    student = lm.BiBertEncoder(None, question_model=lm.HFDistilBertEncoder(ec_from(cfg_s), precision=X3))
+    teacher = lm.BiBertEncoder(None, question_model=lm.HFBertEncoder(ec_from(cfg_t), precision=X3))
+    student.question_model.load_state_dict({k: torch.from_numpy(v) for k, v in p_s.items()})
+    teacher.question_model.load_state_dict({k: torch.from_numpy(v) for k, v in p_t.items()})
+    student.cuda(), teacher.cuda()
+    args = (cu(q_ids), cu(q_mask), cu(d_ids), cu(d_mask))
+    q_db, d_db, qa_db, da_db, _ = student(*args)
+    q_de, d_de, qa_de, da_de, _ = teacher(*args)
+    assert qa_db.shape == (nq, 2, 1, 64) and da_de.shape == (nq * group, 4, 1, 64)
+    loss, parts = lead_distill_loss(q_db, d_db, q_de, d_de, qa_db[:, :, 0], da_db[:, :, 0], qa_de[:, :, 0], da_de[:, :, 0],
+                                    selected_db=sel_s, selected_de=sel_t, reweight=True, train_de=True, gather=False, **hp)
+    assert abs(loss.item() - total) < 1e-4
+    loss.backward()
+    assert_grads(student.question_model, ref_s, 1e-3)
+    assert_grads(teacher.question_model, ref_t, 1e-3)

@@ -148,3 +148,27 @@ def test_loss_gradients_finite_difference():
                 lm = ln.score_loss(Q, C, **kw)[0]["total"]
                 arr[off + i, j] += h
                 assert abs((lp - lm) / (2 * h) - grad[i, j]) < 1e-6
+
+
+def test_lead_distill_loss_against_reference(golden_dir):
+    """oracle lead_de_db_loss vs the real LEAD distill_loss (DE -> DB, per-layer score distillation, lambda re-weighting)"""
+    g = np.load(golden_dir / "lead_distill.npz")
+    group = int(g["group"][0])
+    sel_db, sel_de = list(g["sel_db"]), list(g["sel_de"])
+    for tag in ("both", "frozen"):
+        train_de, reweight, T, Tl, p_db, p_de, p_dis, p_layer = g[tag + "_cfg"]
+        total, grads = ln.lead_de_db_loss(
+            g["q_db"], g["c_db"], g["q_de"], g["c_de"],
+            [g["qL_db"][:, l, 0] for l in sel_db], [g["cL_db"][:, l, 0] for l in sel_db],
+            [g["qL_de"][:, l, 0] for l in sel_de], [g["cL_de"][:, l, 0] for l in sel_de],
+            group=group, temperature=T, layer_temperature=Tl, para_db=p_db, para_de=p_de, para_dis=p_dis,
+            para_layer=p_layer, reweight=bool(reweight), train_de=bool(train_de))
+        assert abs(total - g[tag + "_loss"][0]) < 2e-5
+        for n in ("q_db", "c_db", "q_de", "c_de"):
+            _close(grads[n], g[f"{tag}_d_{n}"], 2e-6)
+        for n, sel in (("qL_db", sel_db), ("cL_db", sel_db), ("qL_de", sel_de), ("cL_de", sel_de)):
+            full = g[f"{tag}_d_{n}"]
+            for i, l in enumerate(sel):
+                _close(grads[n][i], full[:, l, 0], 2e-6)
+            rest = [l for l in range(full.shape[1]) if l not in sel]
+            assert np.abs(full[:, rest]).max() == 0.0
