@@ -123,6 +123,9 @@ int simx_encoder_backward(const simx_encoder_cfg* cfg, const float* const* param
 #define SIMX_LOSS_CE_LOCAL 4     /* a-4' / a-5': -sum p_t log(p_s+eps) / B  on [B,1+n] */
 #define SIMX_LOSS_KD_LOCAL 8     /* a-6  PROD KD_softmax: T^2 * mean_b KL(softmax(t/T) || softmax(s/T)) on [B,1+n] */
 #define SIMX_LOSS_NLL_LOCAL 16   /* a-6  hard loss of CrossBERTKDLoss: NLL of column 0 on [B,1+n] */
+#define SIMX_LOSS_ADV_LOCAL 32   /* a-4' adversarial term of the wiki driver: sum_{b,j} reward_bj log(p_s+eps),
+                                    reward_bj = log(sigmoid(t_b0 - t_bj) + eps) on the raw teacher logits
+                                    (SimANS/wiki/co_training_wiki_train.py:212-225); a SUM, not a batch mean */
 
 typedef struct simx_loss_cfg {
   int32_t terms;        /* OR of SIMX_LOSS_* */
@@ -135,11 +138,13 @@ typedef struct simx_loss_cfg {
   float eps;            /* 1e-7 inside the log of KL/CE (co_training_marco_train.py:213) */
   float score_scale;    /* multiplies student local scores (1 or 1/sqrt(H) with --scale_simmila) */
   float grad_scale;     /* multiplies every gradient and nothing else (loss / gradient_accumulation_steps) */
+  float w_adv_local;    /* weight of SIMX_LOSS_ADV_LOCAL (adv_lambda) */
 } simx_loss_cfg;
 
 /*   Q [GQ,H], C [GC,H] fp32 gathered embeddings; pos_idx [GQ] int32 positive column of each global query
  *   (NLL_GLOBAL); teacher [q_count, group] fp32 teacher logits (KL/CE/KD terms), or NULL.
- *   out_losses[8] fp32: {total, nll_global, kl_local, ce_local, kd_local, nll_local, n_correct_global, unused}
+ *   out_losses[8] fp32: {total, nll_global, kl_local, ce_local, kd_local, nll_local, n_correct_global,
+ *                       n_correct_local (local rows whose column 0 has the largest score)}
  *   dQ [q_count,H], dC [c_count,H] fp32 gradients of `total * grad_scale` w.r.t. the local embeddings.
  *   workspace: simx_score_loss_workspace_bytes(cfg). */
 size_t simx_score_loss_workspace_bytes(const simx_loss_cfg* cfg);
@@ -151,7 +156,7 @@ int simx_score_loss(const simx_loss_cfg* cfg, const float* Q, const float* C, co
  * selected layer pair on the per-layer [CLS] rows, layer_score_dis_loss (LEAD/util.py:539-559):
  *   total = w_nll_a NLL(A) + w_nll_b NLL(B) + w_kl_b2a KL(softmax(B/T) || softmax(A)) + w_kl_a2b KL(softmax(A/T) || softmax(B))
  * KL is `batchmean` over GQ rows; targets are NOT detached (as in the reference): both matrices receive gradients from
- * every term.  out_losses[8] = {total, nll_a, nll_b, kl_b2a, kl_a2b, 0, 0, 0}.  dQb/dCb may be NULL (frozen teacher).
+ * every term.  out_losses[8] = {total, nll_a, nll_b, kl_b2a, kl_a2b, kd_b2a, n_correct_a, 0}.  dQb/dCb may be NULL (frozen teacher).
  * Local row/column ranges as in simx_loss_cfg; gathered embeddings fp32. */
 typedef struct simx_pair_cfg {
   int32_t GQ, GC, H;
@@ -159,6 +164,8 @@ typedef struct simx_pair_cfg {
   float w_nll_a, w_nll_b, w_kl_b2a, w_kl_a2b;
   float temperature;
   float grad_scale;
+  float w_kd_b2a; /* PROD BiEncoderKDLoss KD_softmax on the global matrix: T^2 KL(softmax(B/T) || softmax(A/T))
+                     (PROD/ProD_KD/model/models.py:971-1059) */
 } simx_pair_cfg;
 size_t simx_pair_distill_workspace_bytes(int GQ, int GC, int H);
 int simx_pair_distill(const simx_pair_cfg* cfg, const float* Qa, const float* Ca, const float* Qb, const float* Cb,

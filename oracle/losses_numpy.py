@@ -59,7 +59,7 @@ def score_loss(Q, C, *, terms, q_begin=0, q_count=None, c_begin=0, group=1, pos_
         dQ += dS[q_begin:q_begin + q_count] @ C
         dC += dS[:, c_begin:c_begin + c_count].T @ Q
 
-    local_terms = terms & {"kl_local", "ce_local", "kd_local", "nll_local"}
+    local_terms = terms & {"kl_local", "ce_local", "kd_local", "nll_local", "adv_local"}
     if local_terms:
         Ql = Q[q_begin:q_begin + q_count]
         Cl = C[c_begin:c_begin + c_count].reshape(q_count, group, H)
@@ -96,6 +96,16 @@ def score_loss(Q, C, *, terms, q_begin=0, q_count=None, c_begin=0, group=1, pos_
             out["kd_local"] = loss
             out["total"] += w.get("kd_local", 1.0) * loss
             ds += w.get("kd_local", 1.0) * (T / B) * (np.exp(lsT) - t)
+        if "adv_local" in terms:
+            # SimANS/wiki/co_training_wiki_train.py:212-225: reward = log(softmax([t_0, t_j])_0 + eps) on raw logits,
+            # adv_loss = sum(reward * log(p_s + eps))  (a sum over the batch, not a mean)
+            tr = np.asarray(teacher, np.float64)
+            reward = np.log(1.0 / (1.0 + np.exp(tr - tr[:, :1])) + eps)
+            loss = (reward * np.log(p + eps)).sum()
+            out["adv_local"] = loss
+            out["total"] += w.get("adv_local", 1.0) * loss
+            rho = reward * p / (p + eps)
+            ds += w.get("adv_local", 1.0) * (rho - p * rho.sum(-1, keepdims=True))
         if "nll_local" in terms:
             loss = -lsm[:, 0].mean()
             out["nll_local"] = loss
@@ -110,11 +120,12 @@ def score_loss(Q, C, *, terms, q_begin=0, q_count=None, c_begin=0, group=1, pos_
     return out, dQ * grad_scale, dC * grad_scale
 
 
-def pair_distill(Qa, Ca, Qb, Cb, *, pos_idx, w_nll_a=0.0, w_nll_b=0.0, w_kl_b2a=0.0, w_kl_a2b=0.0, temperature=1.0,
-                 q_begin=0, q_count=None, c_begin=0, c_count=None, grad_scale=1.0):
+def pair_distill(Qa, Ca, Qb, Cb, *, pos_idx, w_nll_a=0.0, w_nll_b=0.0, w_kl_b2a=0.0, w_kl_a2b=0.0, w_kd_b2a=0.0,
+                 temperature=1.0, q_begin=0, q_count=None, c_begin=0, c_count=None, grad_scale=1.0):
     """LEAD mutual distillation between a student (a) and a teacher (b) dual encoder on the global score matrices
     (/root/reference/LEAD/util.py:594-644 scores, :737-760 assembly; no .detach(): targets carry gradient).
       total = w_nll_a NLL(A) + w_nll_b NLL(B) + w_kl_b2a KL(softmax(B/T)||softmax(A)) + w_kl_a2b KL(softmax(A/T)||softmax(B))
+              + w_kd_b2a T^2 KL(softmax(B/T)||softmax(A/T))      (PROD BiEncoderKDLoss KD_softmax, models.py:1050-1056)
     Returns (losses dict, dQa, dCa, dQb, dCb) restricted to the local row / column ranges."""
     Qa, Ca, Qb, Cb = (np.asarray(x, np.float64) for x in (Qa, Ca, Qb, Cb))
     GQ, GC = Qa.shape[0], Ca.shape[0]
@@ -131,14 +142,19 @@ def pair_distill(Qa, Ca, Qb, Cb, *, pos_idx, w_nll_a=0.0, w_nll_b=0.0, w_kl_b2a=
     k_b2a_row = (tb * (ltb - lsa)).sum(1)
     k_a2b_row = (ta * (lta - lsb)).sum(1)
     kl_b2a, kl_a2b = k_b2a_row.mean(), k_a2b_row.mean()
-    total = w_nll_a * nll_a + w_nll_b * nll_b + w_kl_b2a * kl_b2a + w_kl_a2b * kl_a2b
+    k_kd_row = (tb * (ltb - lta)).sum(1)
+    kd_b2a = T * T * k_kd_row.mean()
+    total = w_nll_a * nll_a + w_nll_b * nll_b + w_kl_b2a * kl_b2a + w_kl_a2b * kl_a2b + w_kd_b2a * kd_b2a
     oh = np.zeros_like(A)
     oh[rows, pos] = 1.0
     pa, pb = np.exp(lsa), np.exp(lsb)
-    dA = (w_nll_a * (pa - oh) + w_kl_b2a * (pa - tb) + w_kl_a2b / T * ta * ((lta - lsb) - k_a2b_row[:, None])) / GQ
-    dB = (w_nll_b * (pb - oh) + w_kl_a2b * (pb - ta) + w_kl_b2a / T * tb * ((ltb - lsa) - k_b2a_row[:, None])) / GQ
+    dA = (w_nll_a * (pa - oh) + w_kl_b2a * (pa - tb) + w_kl_a2b / T * ta * ((lta - lsb) - k_a2b_row[:, None])
+          + w_kd_b2a * T * (ta - tb)) / GQ
+    dB = (w_nll_b * (pb - oh) + w_kl_a2b * (pb - ta) + w_kl_b2a / T * tb * ((ltb - lsa) - k_b2a_row[:, None])
+          + w_kd_b2a * T * tb * ((ltb - lta) - k_kd_row[:, None])) / GQ
     qs, cs = slice(q_begin, q_begin + q_count), slice(c_begin, c_begin + c_count)
-    out = dict(total=total, nll_a=nll_a, nll_b=nll_b, kl_b2a=kl_b2a, kl_a2b=kl_a2b)
+    out = dict(total=total, nll_a=nll_a, nll_b=nll_b, kl_b2a=kl_b2a, kl_a2b=kl_a2b, kd_b2a=kd_b2a,
+               n_correct=float((A.argmax(1) == pos).sum()))
     g = grad_scale
     return out, g * dA[qs] @ Ca, g * dA[:, cs].T @ Qa, g * dB[qs] @ Cb, g * dB[:, cs].T @ Qb
 

@@ -206,6 +206,38 @@ def golden_losses(simans, prod):
     loss, _ = prod.CrossBERTKDLoss().calc(args, q, c, torch.from_numpy(teacher))
     loss.backward()
     res.update(prob_loss=np.array([loss.item()]), prob_dQ=q.grad.numpy().copy(), prob_dC=c.grad.numpy().copy())
+    # (6) SimANS wiki retriever loss with the adversarial term, lines re-typed from wiki/co_training_wiki_train.py:198-228
+    for lam in (0.0, 0.3):
+        q, c = fresh()
+        eps_ = 1e-7
+        relevance_logits = torch.from_numpy(teacher)
+        retriever_local_ctx_vectors = c.reshape(q.size(0), c.size(0) // q.size(0), -1)
+        retriever_simila = torch.einsum("bh,bdh->bd", q, retriever_local_ctx_vectors)
+        retriever_dist_p = F.softmax(retriever_simila, dim=1)
+        reranker_dist_p = F.softmax(relevance_logits / 2.0, dim=1)
+        positive_logits = relevance_logits[:, :1]
+        negtive_logits = relevance_logits[:, :]
+        positive_logits_expand = positive_logits.expand(negtive_logits.size())
+        reward_logits = torch.stack((positive_logits_expand, negtive_logits), -1)
+        reward_prob = F.softmax(reward_logits, dim=2)
+        reward = torch.log(reward_prob[:, :, 0] + eps_)
+        normal_loss = -reranker_dist_p * torch.log(retriever_dist_p + eps_)
+        normal_loss = normal_loss.sum() / retriever_dist_p.size(0)
+        adv_loss = reward * torch.log(retriever_dist_p + eps_)
+        adv_loss = adv_loss.sum()
+        loss = lam * adv_loss + (1 - lam) * normal_loss
+        loss.backward()
+        tag = f"wiki_l{int(lam * 10)}"
+        res.update({tag + "_loss": np.array([loss.item()]), tag + "_dQ": q.grad.numpy().copy(), tag + "_dC": c.grad.numpy().copy()})
+    # (5) PROD BiEncoderKDLoss.calc: DE -> DE distillation on the global matrix (models.py:970-1059)
+    Qt = rng.standard_normal((GQ, H)).astype(np.float32)
+    Ct = rng.standard_normal((GQ * group, H)).astype(np.float32)
+    args.KD_type, args.TEMPERATURE = "KD_softmax", 4.0
+    q, c = fresh()
+    loss, correct = prod.BiEncoderKDLoss().calc(args, q, c, torch.from_numpy(Qt), torch.from_numpy(Ct), pos)
+    loss.backward()
+    res.update(Qt=Qt, Ct=Ct, bikd_loss=np.array([loss.item()]), bikd_correct=np.array([int(correct)]),
+               bikd_dQ=q.grad.numpy().copy(), bikd_dC=c.grad.numpy().copy())
     np.savez_compressed(GOLD / "losses.npz", **res)
     print("losses", {k: float(v[0]) for k, v in res.items() if k.endswith("loss")})
 

@@ -20,7 +20,7 @@ PREC_BF16, PREC_BF16X3 = 1, 3
 
 EPI_PLAIN, EPI_BIAS, EPI_BIAS_GELU, EPI_BIAS_ADD, EPI_MUL, EPI_ADD, EPI_ATOMIC_F32 = range(7)
 
-LOSS_NLL_GLOBAL, LOSS_KL_LOCAL, LOSS_CE_LOCAL, LOSS_KD_LOCAL, LOSS_NLL_LOCAL = 1, 2, 4, 8, 16
+LOSS_NLL_GLOBAL, LOSS_KL_LOCAL, LOSS_CE_LOCAL, LOSS_KD_LOCAL, LOSS_NLL_LOCAL, LOSS_ADV_LOCAL = 1, 2, 4, 8, 16, 32
 
 
 class EncoderCfg(C.Structure):
@@ -62,6 +62,7 @@ class LossCfg(C.Structure):
         ("eps", C.c_float),
         ("score_scale", C.c_float),
         ("grad_scale", C.c_float),
+        ("w_adv_local", C.c_float),
     ]
 
 
@@ -69,7 +70,7 @@ class PairCfg(C.Structure):
     """mirror of `simx_pair_cfg`"""
 
     _fields_ = [(n, C.c_int32) for n in ("GQ", "GC", "H", "q_begin", "q_count", "c_begin", "c_count")] + \
-               [(n, C.c_float) for n in ("w_nll_a", "w_nll_b", "w_kl_b2a", "w_kl_a2b", "temperature", "grad_scale")]
+               [(n, C.c_float) for n in ("w_nll_a", "w_nll_b", "w_kl_b2a", "w_kl_a2b", "temperature", "grad_scale", "w_kd_b2a")]
 
 
 _P = C.c_void_p

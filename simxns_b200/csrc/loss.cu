@@ -53,6 +53,7 @@ local_loss_kernel(const simx_loss_cfg cfg, const float* __restrict__ Q, const fl
     smax = fmaxf(smax, ds[j]);
     if (teacher) tmax = fmaxf(tmax, teacher[(long)i * G + j] / T);
   }
+  const bool pos_first = ds[0] >= smax;  // positive (column 0) ranked first; torch.max returns the first maximal index
   float ssum = 0.f, ssumT = 0.f, tsum = 0.f;
   for (int j = 0; j < G; ++j) {
     ssum += expf(ds[j] - smax);
@@ -62,8 +63,10 @@ local_loss_kernel(const simx_loss_cfg cfg, const float* __restrict__ Q, const fl
   const float lse = smax + logf(ssum);
   const float lseT = smax / T + logf(ssumT);
   const float tlse = teacher ? tmax + logf(tsum) : 0.f;
-  float l_kl = 0.f, l_ce = 0.f, l_kd = 0.f, l_nll = 0.f, rsum = 0.f;
+  float l_kl = 0.f, l_ce = 0.f, l_kd = 0.f, l_nll = 0.f, l_adv = 0.f, rsum = 0.f, rho_sum = 0.f;
   const bool want_klce = (cfg.terms & (SIMX_LOSS_KL_LOCAL | SIMX_LOSS_CE_LOCAL)) != 0;
+  const bool want_adv = (cfg.terms & SIMX_LOSS_ADV_LOCAL) != 0;
+  const float t_raw0 = teacher ? teacher[(long)i * G] : 0.f;
   for (int j = 0; j < G; ++j) {
     const float p = expf(ds[j] - lse);
     if (teacher) {
@@ -76,6 +79,12 @@ local_loss_kernel(const simx_loss_cfg cfg, const float* __restrict__ Q, const fl
         rsum += t * p / (p + cfg.eps);
       }
       if (cfg.terms & SIMX_LOSS_KD_LOCAL) l_kd += t > 0.f ? t * (tl - (ds[j] / T - lseT)) : 0.f;
+      if (want_adv) {
+        // reward_j = log(softmax([t_0, t_j])_0 + eps) on the RAW teacher logits (co_training_wiki_train.py:212-217)
+        const float reward = logf(1.f / (1.f + expf(teacher[(long)i * G + j] - t_raw0)) + cfg.eps);
+        l_adv += reward * logf(p + cfg.eps);
+        rho_sum += reward * p / (p + cfg.eps);
+      }
     }
   }
   if (cfg.terms & SIMX_LOSS_NLL_LOCAL) l_nll = -(ds[0] - lse);
@@ -91,6 +100,10 @@ local_loss_kernel(const simx_loss_cfg cfg, const float* __restrict__ Q, const fl
       const float t = expf(teacher[(long)i * G + j] / T - tlse);
       if (want_klce) g += w_klce * (-(t * p / (p + cfg.eps) - p * rsum) * invB);
       if (cfg.terms & SIMX_LOSS_KD_LOCAL) g += cfg.w_kd_local * (T * invB) * (expf(s / T - lseT) - t);
+      if (want_adv) {
+        const float reward = logf(1.f / (1.f + expf(teacher[(long)i * G + j] - t_raw0)) + cfg.eps);
+        g += cfg.w_adv_local * (reward * p / (p + cfg.eps) - p * rho_sum);  // adv_loss is a SUM over the batch
+      }
     }
     if (cfg.terms & SIMX_LOSS_NLL_LOCAL) g += cfg.w_nll_local * invB * (p - (j == 0 ? 1.f : 0.f));
     ds[j] = g * cfg.score_scale * cfg.grad_scale;
@@ -98,6 +111,7 @@ local_loss_kernel(const simx_loss_cfg cfg, const float* __restrict__ Q, const fl
   __syncwarp();
   if (lane == 0) {
     const float T2 = T * T;
+    if (pos_first) atomicAdd(out_losses + 7, 1.f);
     if (cfg.terms & SIMX_LOSS_KL_LOCAL) atomicAdd(out_losses + 2, l_kl * invB);
     if (cfg.terms & SIMX_LOSS_CE_LOCAL) atomicAdd(out_losses + 3, l_ce * invB);
     if (cfg.terms & SIMX_LOSS_KD_LOCAL) atomicAdd(out_losses + 4, l_kd * invB * T2);
@@ -107,6 +121,7 @@ local_loss_kernel(const simx_loss_cfg cfg, const float* __restrict__ Q, const fl
     if (cfg.terms & SIMX_LOSS_CE_LOCAL) tot += cfg.w_ce_local * l_ce * invB;
     if (cfg.terms & SIMX_LOSS_KD_LOCAL) tot += cfg.w_kd_local * l_kd * invB * T2;
     if (cfg.terms & SIMX_LOSS_NLL_LOCAL) tot += cfg.w_nll_local * l_nll * invB;
+    if (want_adv) tot += cfg.w_adv_local * l_adv;
     atomicAdd(out_losses + 0, tot);
   }
   // gradients: dQ_i = sum_j ds_j c_ij ; dC_ij = ds_j q_i      (this warp is the only writer of these rows)
@@ -219,7 +234,7 @@ static LossWs loss_ws(const simx_loss_cfg* c) {
 // dA/dB are written as 3 bf16 planes for the gradient GEMMs.
 // ------------------------------------------------------------------------------------------------
 struct PairW {
-  float nll_a, nll_b, kl_b2a, kl_a2b, T, grad_scale;
+  float nll_a, nll_b, kl_b2a, kl_a2b, T, grad_scale, kd_b2a;
 };
 
 __device__ __forceinline__ void block_lse(const float* s, int n, float invT, float* sh, float& lse_out) {
@@ -276,15 +291,18 @@ pair_row_kernel(const float* __restrict__ A, const float* __restrict__ B, int GQ
   block_lse(a, GC, invT, sh, lse_aT);
   block_lse(b, GC, invT, sh, lse_bT);
   // KL row sums
-  float k_b2a = 0.f, k_a2b = 0.f;
+  float k_b2a = 0.f, k_a2b = 0.f, k_kd = 0.f;
   for (int c = threadIdx.x; c < GC; c += 256) {
     const float lta = a[c] * invT - lse_aT, ltb = b[c] * invT - lse_bT;  // log softmax(./T)
     const float lsa = a[c] - lse_a, lsb = b[c] - lse_b;
-    k_b2a += __expf(ltb) * (ltb - lsa);
+    const float tb = __expf(ltb);
+    k_b2a += tb * (ltb - lsa);
     k_a2b += __expf(lta) * (lta - lsb);
+    k_kd += tb * (ltb - lta);  // PROD KD_softmax: both sides at temperature T
   }
   k_b2a = block_sum(k_b2a, sh);
   k_a2b = block_sum(k_a2b, sh);
+  k_kd = block_sum(k_kd, sh);
   const int pos = pos_idx[row];
   if (threadIdx.x == 0) {
     const float na = lse_a - a[pos], nb = lse_b - b[pos], r = 1.f / GQ;
@@ -292,7 +310,31 @@ pair_row_kernel(const float* __restrict__ A, const float* __restrict__ B, int GQ
     atomicAdd(out_losses + 2, nb * r);
     atomicAdd(out_losses + 3, k_b2a * r);
     atomicAdd(out_losses + 4, k_a2b * r);
-    atomicAdd(out_losses + 0, (w.nll_a * na + w.nll_b * nb + w.kl_b2a * k_b2a + w.kl_a2b * k_a2b) * r);
+    atomicAdd(out_losses + 5, k_kd * w.T * w.T * r);
+    atomicAdd(out_losses + 0, (w.nll_a * na + w.nll_b * nb + w.kl_b2a * k_b2a + w.kl_a2b * k_a2b +
+                               w.kd_b2a * w.T * w.T * k_kd) * r);
+  }
+  {  // arg-max of row A == positive ?  (correct_predictions_count of the reference loss classes)
+    float bv = -INFINITY;
+    int bi = 0;
+    for (int c = threadIdx.x; c < GC; c += 256)
+      if (a[c] > bv) { bv = a[c]; bi = c; }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const float v2 = __shfl_xor_sync(0xffffffffu, bv, o);
+      const int i2 = __shfl_xor_sync(0xffffffffu, bi, o);
+      if (v2 > bv || (v2 == bv && i2 < bi)) { bv = v2; bi = i2; }
+    }
+    __shared__ float sv[8];
+    __shared__ int si[8];
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) { sv[threadIdx.x >> 5] = bv; si[threadIdx.x >> 5] = bi; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      for (int k = 1; k < 8; ++k)
+        if (sv[k] > sv[0] || (sv[k] == sv[0] && si[k] < si[0])) { sv[0] = sv[k]; si[0] = si[k]; }
+      if (si[0] == pos) atomicAdd(out_losses + 6, 1.f);
+    }
   }
   const float r = w.grad_scale / GQ;
   for (int c = threadIdx.x; c < GC; c += 256) {
@@ -300,8 +342,10 @@ pair_row_kernel(const float* __restrict__ A, const float* __restrict__ B, int GQ
     const float lsa = a[c] - lse_a, lsb = b[c] - lse_b;
     const float pa = __expf(lsa), pb = __expf(lsb), ta = __expf(lta), tb = __expf(ltb);
     const float oh = c == pos ? 1.f : 0.f;
-    const float ga = r * (w.nll_a * (pa - oh) + w.kl_b2a * (pa - tb) + w.kl_a2b * invT * ta * ((lta - lsb) - k_a2b));
-    const float gb = r * (w.nll_b * (pb - oh) + w.kl_a2b * (pb - ta) + w.kl_b2a * invT * tb * ((ltb - lsa) - k_b2a));
+    const float ga = r * (w.nll_a * (pa - oh) + w.kl_b2a * (pa - tb) + w.kl_a2b * invT * ta * ((lta - lsb) - k_a2b) +
+                          w.kd_b2a * w.T * (ta - tb));
+    const float gb = r * (w.nll_b * (pb - oh) + w.kl_a2b * (pb - ta) + w.kl_b2a * invT * tb * ((ltb - lsa) - k_b2a) +
+                          w.kd_b2a * w.T * tb * ((ltb - lta) - k_kd));
     split_store<3>(dA + (long)row * ld + c, ps, ga);
     if (dB != nullptr) split_store<3>(dB + (long)row * ld + c, ps, gb);
   }
@@ -385,12 +429,13 @@ extern "C" int simx_score_loss(const simx_loss_cfg* cfg, const float* Q, const f
              "score_loss: local query range [%d,+%d) outside GQ=%d", cfg->q_begin, cfg->q_count, cfg->GQ);
   SIMX_CHECK(cfg->c_count > 0 && cfg->c_begin >= 0 && cfg->c_begin + cfg->c_count <= cfg->GC, SIMX_ERR_INVALID,
              "score_loss: local passage range [%d,+%d) outside GC=%d", cfg->c_begin, cfg->c_count, cfg->GC);
-  const int local_terms = cfg->terms & (SIMX_LOSS_KL_LOCAL | SIMX_LOSS_CE_LOCAL | SIMX_LOSS_KD_LOCAL | SIMX_LOSS_NLL_LOCAL);
-  SIMX_CHECK(cfg->terms != 0 && (cfg->terms & ~31) == 0, SIMX_ERR_INVALID, "score_loss: bad terms mask %d", cfg->terms);
+  const int local_terms = cfg->terms & (SIMX_LOSS_KL_LOCAL | SIMX_LOSS_CE_LOCAL | SIMX_LOSS_KD_LOCAL | SIMX_LOSS_NLL_LOCAL |
+                                        SIMX_LOSS_ADV_LOCAL);
+  SIMX_CHECK(cfg->terms != 0 && (cfg->terms & ~63) == 0, SIMX_ERR_INVALID, "score_loss: bad terms mask %d", cfg->terms);
   if (local_terms) {
     SIMX_CHECK(cfg->group >= 1 && cfg->group <= MAX_GROUP && cfg->c_count == cfg->q_count * cfg->group,
                SIMX_ERR_INVALID, "score_loss: local terms need c_count == q_count * group, group <= %d", MAX_GROUP);
-    if (cfg->terms & (SIMX_LOSS_KL_LOCAL | SIMX_LOSS_CE_LOCAL | SIMX_LOSS_KD_LOCAL))
+    if (cfg->terms & (SIMX_LOSS_KL_LOCAL | SIMX_LOSS_CE_LOCAL | SIMX_LOSS_KD_LOCAL | SIMX_LOSS_ADV_LOCAL))
       SIMX_CHECK(teacher != nullptr && cfg->temperature > 0.f, SIMX_ERR_INVALID,
                  "score_loss: distillation terms need teacher logits and a positive temperature");
   }
@@ -475,7 +520,7 @@ extern "C" int simx_pair_distill(const simx_pair_cfg* cfg, const float* Qa, cons
   SIMX_CUDA(cudaMemsetAsync(out_losses, 0, 8 * sizeof(float), st));
   SIMX_TRY(score_forward(Qa, Ca, GQ, GC, H, wa, w, st));
   SIMX_TRY(score_forward(Qb, Cb, GQ, GC, H, wb, w, st));
-  PairW pw{cfg->w_nll_a, cfg->w_nll_b, cfg->w_kl_b2a, cfg->w_kl_a2b, cfg->temperature, cfg->grad_scale};
+  PairW pw{cfg->w_nll_a, cfg->w_nll_b, cfg->w_kl_b2a, cfg->w_kl_a2b, cfg->temperature, cfg->grad_scale, cfg->w_kd_b2a};
   pair_row_kernel<<<GQ, 256, 0, st>>>(reinterpret_cast<const float*>(wa + w.s), reinterpret_cast<const float*>(wb + w.s), GQ,
                                       GC, GCp, pos_idx, pw, reinterpret_cast<bf16*>(wa + w.ds),
                                       train_b ? reinterpret_cast<bf16*>(wb + w.ds) : nullptr, (long)GQ * GCp, out_losses);

@@ -27,7 +27,7 @@ import torch.distributed as dist
 from . import _lib
 
 _TERMS = {"nll_global": _lib.LOSS_NLL_GLOBAL, "kl_local": _lib.LOSS_KL_LOCAL, "ce_local": _lib.LOSS_CE_LOCAL,
-          "kd_local": _lib.LOSS_KD_LOCAL, "nll_local": _lib.LOSS_NLL_LOCAL}
+          "kd_local": _lib.LOSS_KD_LOCAL, "nll_local": _lib.LOSS_NLL_LOCAL, "adv_local": _lib.LOSS_ADV_LOCAL}
 LOSS_FIELDS = ("total", "nll_global", "kl_local", "ce_local", "kd_local", "nll_local", "n_correct")
 
 
@@ -75,7 +75,7 @@ class _ScoreLossFn(torch.autograd.Function):
                 group=group, w_nll_global=w.get("nll_global", 1.0), w_kl_local=w.get("kl_local", 1.0),
                 w_ce_local=w.get("ce_local", 1.0), w_kd_local=w.get("kd_local", 1.0), w_nll_local=w.get("nll_local", 1.0),
                 temperature=opts.get("temperature", 1.0), eps=opts.get("eps", 1e-7),
-                score_scale=opts.get("score_scale", 1.0), grad_scale=1.0)
+                score_scale=opts.get("score_scale", 1.0), grad_scale=1.0, w_adv_local=w.get("adv_local", 1.0))
             if use_global:
                 if pos_idx is None:
                     pos_idx = torch.arange(0, GQ * group, group, device=dev, dtype=torch.int32)  # LEAD/util.py:445
@@ -167,13 +167,24 @@ class CrossBERTKDLoss(object):
             lwf, _ = fused_score_loss(q_vectors, ctx_vectors, ["kd_local"], teacher=ori, temperature=args.TEMPERATURE,
                                       group_size=group, gather=False)
             loss = loss + args.LwF_WEIGHT * lwf
-        # arg-max of the local row == column 0  <=>  positive ranked first
-        with torch.no_grad():
-            s = torch.einsum("bh,bdh->bd", q_vectors.float(), ctx_vectors.float().reshape(nq, group, -1))
-            correct_predictions_count = (s.argmax(1) == 0).sum()
+        correct_predictions_count = detail[7].round().to(torch.int64)  # local rows whose positive (column 0) ranks first
         if loss_scale:
             loss = loss * loss_scale
         return loss, correct_predictions_count
+
+
+def simans_wiki_loss(local_q_vector, local_ctx_vectors, relevance_logits, temperature_normal: float = 1.0,
+                     adv_lambda: float = 0.0, eps: float = 1e-7, scale_simmila: bool = False):
+    """The NQ/TQ retriever step's loss (SimANS/wiki/co_training_wiki_train.py:198-228):
+    adv_lambda * sum(reward * log(p_s+eps)) + (1 - adv_lambda) * (-sum p_t log(p_s+eps) / B), one fused kernel call."""
+    nq = local_q_vector.shape[0]
+    scale = 1.0 / (local_q_vector.shape[1] ** 0.5) if scale_simmila else 1.0
+    terms = ["ce_local"] + (["adv_local"] if adv_lambda != 0 else [])
+    loss, _ = fused_score_loss(local_q_vector, local_ctx_vectors, terms, teacher=relevance_logits,
+                               weights=dict(ce_local=1.0 - adv_lambda, adv_local=adv_lambda),
+                               temperature=temperature_normal, eps=eps, score_scale=scale,
+                               group_size=local_ctx_vectors.shape[0] // nq, gather=False)
+    return loss
 
 
 def simans_distill_loss(local_q_vector, local_ctx_vectors, relevance_logits, temperature_distill: float = 1.0,
@@ -211,12 +222,18 @@ class _PairDistillFn(torch.autograd.Function):
             glob = [gather_embeddings(t, opts.get("group")) for t in loc] if world > 1 else loc
             GQ, GC = glob[0].shape[0], glob[1].shape[0]
             group = opts.get("group_size") or (nc // nq)
-            pos = torch.arange(0, GQ * group, group, device=dev, dtype=torch.int32)  # LEAD/util.py:596
+            pos = opts.get("pos_idx")
+            if pos is None:
+                pos = torch.arange(0, GQ * group, group, device=dev, dtype=torch.int32)  # LEAD/util.py:596
+            pos = torch.as_tensor(pos, device=dev).to(torch.int32).contiguous()
+            if pos.numel() != GQ:
+                raise ValueError(f"pos_idx has {pos.numel()} entries for {GQ} global queries")
             w = opts["weights"]
             train_b = any(ctx.needs_input_grad[2:4])
             cfg = _lib.PairCfg(GQ=GQ, GC=GC, H=H, q_begin=rank * nq, q_count=nq, c_begin=rank * nc, c_count=nc,
                                w_nll_a=w.get("nll_a", 0.0), w_nll_b=w.get("nll_b", 0.0), w_kl_b2a=w.get("kl_b2a", 0.0),
-                               w_kl_a2b=w.get("kl_a2b", 0.0), temperature=opts.get("temperature", 1.0), grad_scale=1.0)
+                               w_kl_a2b=w.get("kl_a2b", 0.0), temperature=opts.get("temperature", 1.0), grad_scale=1.0,
+                               w_kd_b2a=w.get("kd_b2a", 0.0))
             ws = torch.empty(lib.simx_pair_distill_workspace_bytes(GQ, GC, H), dtype=torch.uint8, device=dev)
             losses = torch.empty(8, dtype=torch.float32, device=dev)
             grads = [torch.empty_like(loc[0]), torch.empty_like(loc[1]),
@@ -236,11 +253,31 @@ class _PairDistillFn(torch.autograd.Function):
 
 
 def fused_pair_distill(q_a, c_a, q_b, c_b, weights: dict, *, temperature: float = 1.0, group_size: Optional[int] = None,
-                       gather: bool = True, group=None):
+                       gather: bool = True, group=None, pos_idx=None):
     """a = student, b = teacher (local embeddings, all-gathered inside).  weights: nll_a, nll_b, kl_b2a (teacher targets ->
     student), kl_a2b.  -> (total with autograd into all four inputs, detail [8] = PAIR_FIELDS + pad)."""
-    opts = dict(weights=dict(weights), temperature=float(temperature), group_size=group_size, gather=gather, group=group)
+    opts = dict(weights=dict(weights), temperature=float(temperature), group_size=group_size, gather=gather, group=group,
+                pos_idx=pos_idx)
     return _PairDistillFn.apply(q_a, c_a, q_b, c_b, opts)
+
+
+class BiEncoderKDLoss(object):
+    """PROD/ProD_KD/model/models.py:970-1038: DE -> DE distillation on the (already gathered) global matrix,
+    CE_WEIGHT * NLL + KD_WEIGHT * T^2 KL(softmax(teacher/T) || softmax(student/T)); KD_type 'KD_softmax'."""
+
+    def calc(self, args, q_vectors, ctx_vectors, teacher_q_vector, teacher_ctxs_vector, positive_idx_per_question: list,
+             hard_negative_idx_per_question: list = None, loss_scale: float = None):
+        if teacher_q_vector is None or teacher_ctxs_vector is None:
+            return BiEncoderNllLoss().calc(q_vectors, ctx_vectors, positive_idx_per_question, loss_scale=loss_scale)
+        if args.KD_type != "KD_softmax":
+            raise NotImplementedError(f"KD_type={args.KD_type!r}: the fused kernel covers KD_softmax")
+        loss, detail = fused_pair_distill(q_vectors, ctx_vectors, teacher_q_vector.detach(), teacher_ctxs_vector.detach(),
+                                          dict(nll_a=args.CE_WEIGHT, kd_b2a=args.KD_WEIGHT), temperature=args.TEMPERATURE,
+                                          gather=False, pos_idx=positive_idx_per_question)
+        correct_predictions_count = detail[6].round().to(torch.int64)
+        if loss_scale:
+            loss = loss * loss_scale
+        return loss, correct_predictions_count
 
 
 def lead_distill_loss(q_db, c_db, q_de, c_de, cls_q_db=None, cls_c_db=None, cls_q_de=None, cls_c_de=None, *,

@@ -278,6 +278,18 @@ def test_losses_vs_reference_golden(golden_dir):
     q, c = fresh()
     loss, _ = CrossBERTKDLoss().calc(A, q, c, t)
     check(q, c, loss, "prob", g["prob_loss"][0])
+    # SimANS wiki retriever loss (CE-to-teacher + adversarial reward term)
+    from simxns_b200.losses import simans_wiki_loss
+    for lam, tag in ((0.0, "wiki_l0"), (0.3, "wiki_l3")):
+        q, c = fresh()
+        check(q, c, simans_wiki_loss(q, c, t, temperature_normal=2.0, adv_lambda=lam), tag, g[tag + "_loss"][0])
+    # PROD BiEncoderKDLoss: DE -> DE distillation on the global matrix
+    from simxns_b200.losses import BiEncoderKDLoss
+    A.KD_type, A.TEMPERATURE = "KD_softmax", 4.0
+    q, c = fresh()
+    loss, correct = BiEncoderKDLoss().calc(A, q, c, cu(g["Qt"]), cu(g["Ct"]), [int(x) for x in g["nll_pos"]])
+    assert int(correct) == int(g["bikd_correct"][0])
+    check(q, c, loss, "bikd", g["bikd_loss"][0])
 
 
 @pytest.mark.parametrize("GQ,group,H,q_begin,q_count", [(8, 4, 64, 0, 8), (6, 3, 128, 0, 6), (16, 8, 768, 4, 4),

@@ -172,3 +172,26 @@ def test_lead_distill_loss_against_reference(golden_dir):
                 _close(grads[n][i], full[:, l, 0], 2e-6)
             rest = [l for l in range(full.shape[1]) if l not in sel]
             assert np.abs(full[:, rest]).max() == 0.0
+
+
+def test_prod_biencoder_kd_loss_against_reference(golden_dir):
+    """PROD BiEncoderKDLoss (global DE -> DE KD_softmax, CE 0.1 / KD 0.9 / T 4)"""
+    g = np.load(golden_dir / "losses.npz")
+    out, dQ, dC, _, _ = ln.pair_distill(g["Q"], g["C"], g["Qt"], g["Ct"], pos_idx=g["nll_pos"], w_nll_a=0.1, w_kd_b2a=0.9,
+                                        temperature=4.0)
+    assert abs(out["total"] - g["bikd_loss"][0]) < 1e-5 and out["n_correct"] == g["bikd_correct"][0]
+    _close(dQ, g["bikd_dQ"], 1e-6)
+    _close(dC, g["bikd_dC"], 1e-6)
+
+
+def test_wiki_adversarial_loss_against_reference(golden_dir):
+    """SimANS NQ/TQ retriever loss: adv_lambda * sum(reward log p_s) + (1 - adv_lambda) * CE-to-teacher, T_normal = 2"""
+    g = np.load(golden_dir / "losses.npz")
+    group = int(g["group"][0])
+    for lam, tag in ((0.0, "wiki_l0"), (0.3, "wiki_l3")):
+        terms = ["ce_local"] + (["adv_local"] if lam else [])
+        out, dQ, dC = ln.score_loss(g["Q"], g["C"], terms=terms, group=group, teacher=g["teacher"], temperature=2.0,
+                                    w=dict(ce_local=1 - lam, adv_local=lam))
+        assert abs(out["total"] - g[tag + "_loss"][0]) < 2e-5
+        _close(dQ, g[tag + "_dQ"], 2e-6)
+        _close(dC, g[tag + "_dC"], 2e-6)
