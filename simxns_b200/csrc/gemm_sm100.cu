@@ -11,6 +11,7 @@
 // over tokens; split-K with fp32 atomics into the gradient buffer).  With 3 planes per operand (fp32-class mode)
 // the producer streams the 6 significant plane pairs through the same accumulator.
 #include <cuda_fp16.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 #include "ptx.cuh"
@@ -40,11 +41,13 @@ struct GemmParams {
 
 // TS: the epilogue stages its bf16 output tile in shared memory and writes it with TMA (full 128-byte lines) instead
 // of 16-byte-per-row scattered stores — those capped every K=768 GEMM at ~1.2 TB/s of half-sector L2 writes.
-template <int BN, bool TS>
+// CG = 2: a CTA pair (cta_group::2) shares one 256 x BN tile — each CTA stages its own 128 rows of A and HALF of B,
+// the leader's single tcgen05.mma covers M = 256 and reads both halves: operand bytes per flop drop by a third.
+template <int BN, bool TS, int CG>
 struct GemmSmem {
-  static constexpr int STAGES = (BN == 256) ? (TS ? 3 : 4) : (BN == 128 ? 4 : 6);
+  static constexpr int STAGES = (BN == 256) ? (CG == 2 ? (TS ? 4 : 6) : (TS ? 3 : 4)) : (BN == 128 ? 4 : 6);
   static constexpr uint32_t A_BYTES = GEMM_BM * GEMM_BK * 2;
-  static constexpr uint32_t B_BYTES = BN * GEMM_BK * 2;
+  static constexpr uint32_t B_BYTES = (BN / CG) * GEMM_BK * 2;
   static constexpr uint32_t STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr uint32_t STG_OFF = STAGES * STAGE_BYTES;
   static constexpr uint32_t STG_BYTES = TS ? 16 * 4096 : 0;  // one [32 rows x 64 cols] bf16 box per epilogue warp
@@ -189,12 +192,15 @@ __device__ __forceinline__ void epilogue_chunk(const GemmParams& p, int row, int
   }
 }
 
-template <int BN, bool MN, int EPI, int NP>
+template <int BN, bool MN, int EPI, int NP, int CG>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_kernel(const GemmParams p, const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
             const __grid_constant__ CUtensorMap mapOut, const __grid_constant__ CUtensorMap mapOut2) {
   constexpr bool TS = kTmaStore<BN, MN, EPI, NP>;
-  using L = GemmSmem<BN, TS>;
+  using L = GemmSmem<BN, TS, CG>;
+  constexpr int TILE_M = GEMM_BM * CG;  // rows of one output tile (both CTAs of a pair)
+  const uint32_t cta_rank = CG == 2 ? cluster_ctarank() : 0u;
+  const bool leader = cta_rank == 0;
   constexpr int STAGES = L::STAGES;
   extern __shared__ uint8_t smem_raw[];
   // 128B swizzle atoms need 1024-byte aligned tiles
@@ -228,53 +234,58 @@ gemm_kernel(const GemmParams p, const __grid_constant__ CUtensorMap mapA, const 
   }
   if (warp == 1 && lane == 0) {
     for (int i = 0; i < STAGES; ++i) {
-      mbar_init(&full[i], 1);
-      mbar_init(&empty[i], 1);
+      mbar_init(&full[i], CG);   // leader: arrive.expect_tx; peer: remote arrive (its bytes land on the leader's barrier)
+      mbar_init(&empty[i], 1);   // tcgen05.commit, multicast to both CTAs when CG == 2
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tfull[i], 1);
-      mbar_init(&tempty[i], 16);
+      mbar_init(&tempty[i], 16 * CG);  // every epilogue warp of the pair arrives on the LEADER's barrier
     }
     fence_mbar_init();
   }
-  if (warp == 2) tmem_alloc<1>(tmem_slot, 2 * BN);
+  if constexpr (CG == 2) cluster_sync_all();  // both CTAs alive before the pair-wide TMEM allocation
+  if (warp == 2) tmem_alloc<CG>(tmem_slot, 2 * BN);
   tc_fence_before();
-  __syncthreads();
+  if constexpr (CG == 2) cluster_sync_all();
+  else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
   const int total_tiles = p.m_tiles * p.n_tiles * p.ksplit;
+  const int first_tile = blockIdx.x / CG, tile_stride = gridDim.x / CG;  // a CTA pair walks the tiles together
 
   if (warp == 0) {
     if (lane == 0) {
       // ===================== TMA producer =====================
       int stage = 0;
       uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      for (int tile = first_tile; tile < total_tiles; tile += tile_stride) {
         const int nt = tile % p.n_tiles;
         const int mt = (tile / p.n_tiles) % p.m_tiles;
         const int ks = tile / (p.n_tiles * p.m_tiles);
         const int kb0 = ks * p.kb_per_split;
         const int kb1 = min(p.kb_total, kb0 + p.kb_per_split);
-        const int m0 = mt * GEMM_BM, n0 = nt * BN;
+        // this CTA's 128 rows of A and its BN/CG columns of B
+        const int m0 = mt * TILE_M + cta_rank * GEMM_BM, n0 = nt * BN + cta_rank * (BN / CG);
         for (int pass = 0; pass < p.npass; ++pass) {
           const int pla = p.pa[pass], plb = p.pb[pass];
           for (int kb = kb0; kb < kb1; ++kb) {
             mbar_wait(&empty[stage], phase ^ 1);
-            mbar_arrive_expect_tx(&full[stage], L::STAGE_BYTES);
+            if (leader) mbar_arrive_expect_tx(&full[stage], L::STAGE_BYTES * CG);
+            else mbar_arrive_remote(&full[stage], 0);
             uint8_t* a = sA + stage * L::A_BYTES;
             uint8_t* b = sB + stage * L::B_BYTES;
             if constexpr (!MN) {
-              tma_load_3d(&mapA, &full[stage], a, kb * GEMM_BK, m0, pla);
-              tma_load_3d(&mapB, &full[stage], b, kb * GEMM_BK, n0, plb);
+              tma_load_3d_cg<CG>(&mapA, &full[stage], a, kb * GEMM_BK, m0, pla);
+              tma_load_3d_cg<CG>(&mapB, &full[stage], b, kb * GEMM_BK, n0, plb);
             } else {
               // MN-major: one [64 k-rows x 64 mn (128 B)] box per 64-wide slice of the MN extent
 #pragma unroll
               for (int i = 0; i < GEMM_BM / 64; ++i)
-                tma_load_3d(&mapA, &full[stage], a + i * (GEMM_BK * 128), m0 + i * 64, kb * GEMM_BK, pla);
+                tma_load_3d_cg<CG>(&mapA, &full[stage], a + i * (GEMM_BK * 128), m0 + i * 64, kb * GEMM_BK, pla);
 #pragma unroll
-              for (int i = 0; i < BN / 64; ++i)
-                tma_load_3d(&mapB, &full[stage], b + i * (GEMM_BK * 128), n0 + i * 64, kb * GEMM_BK, plb);
+              for (int i = 0; i < BN / CG / 64; ++i)
+                tma_load_3d_cg<CG>(&mapB, &full[stage], b + i * (GEMM_BK * 128), n0 + i * 64, kb * GEMM_BK, plb);
             }
             if (++stage == STAGES) { stage = 0; phase ^= 1; }
           }
@@ -282,13 +293,13 @@ gemm_kernel(const GemmParams p, const __grid_constant__ CUtensorMap mapA, const 
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      // ===================== MMA issuer =====================
-      constexpr uint32_t idesc = make_idesc_bf16(GEMM_BM, BN, MN, MN);
+    if (lane == 0 && leader) {
+      // ===================== MMA issuer (leader CTA only when CG == 2) =====================
+      constexpr uint32_t idesc = make_idesc_bf16(TILE_M, BN, MN, MN);
       int stage = 0;
       uint32_t phase = 0;
       int it = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+      for (int tile = first_tile; tile < total_tiles; tile += tile_stride, ++it) {
         const int ks = tile / (p.n_tiles * p.m_tiles);
         const int kb0 = ks * p.kb_per_split;
         const int kb1 = min(p.kb_total, kb0 + p.kb_per_split);
@@ -316,12 +327,12 @@ gemm_kernel(const GemmParams p, const __grid_constant__ CUtensorMap mapA, const 
               da = make_smem_desc_sw128(a_addr + k * 2048, GEMM_BK * 128, 1024);
               db = make_smem_desc_sw128(b_addr + k * 2048, GEMM_BK * 128, 1024);
             }
-            umma_bf16<1>(d_tmem, da, db, idesc, (i | k) != 0);
+            umma_bf16<CG>(d_tmem, da, db, idesc, (i | k) != 0);
           }
-          umma_commit<1>(&empty[stage]);  // frees the smem slot when these MMAs retire
+          umma_commit<CG>(&empty[stage]);  // frees the smem slot (in both CTAs) when these MMAs retire
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
-        umma_commit<1>(&tfull[acc]);  // accumulator complete -> epilogue
+        umma_commit<CG>(&tfull[acc]);  // accumulator complete -> epilogue warps of both CTAs
       }
     }
   } else if (warp >= 4) {
@@ -333,12 +344,13 @@ gemm_kernel(const GemmParams p, const __grid_constant__ CUtensorMap mapA, const 
     constexpr int CW = CPW >= 32 ? 32 : 16;  // columns per tcgen05.ld
     constexpr int NCH = CPW / CW;
     int it = 0;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+    for (int tile = first_tile; tile < total_tiles; tile += tile_stride, ++it) {
       const int nt = tile % p.n_tiles;
       const int mt = (tile / p.n_tiles) % p.m_tiles;
       const int acc = it & 1;
       const uint32_t acc_phase = (it >> 1) & 1;
-      const int row = mt * GEMM_BM + quarter * 32 + lane;
+      const int row_base = mt * TILE_M + cta_rank * GEMM_BM + quarter * 32;
+      const int row = row_base + lane;
       const int col_base = nt * BN + part * CPW;
       EpiPre<EPI, NP> pre;
       epi_prefetch<EPI, NP, CW>(p, row, col_base, pre);
@@ -355,7 +367,7 @@ gemm_kernel(const GemmParams p, const __grid_constant__ CUtensorMap mapA, const 
             // accumulator fully read by this warp: hand the TMEM buffer back before the math and the global stores
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(&tempty[acc]);
+            if (lane == 0) { if (leader) mbar_arrive(&tempty[acc]); else mbar_arrive_remote(&tempty[acc], 0); }
           }
           epilogue_chunk<EPI, NP, CW>(p, row, col_base + c * CW, v, pre, sbias);
           if (c + 1 < NCH) epi_prefetch<EPI, NP, CW>(p, row, col_base + (c + 1) * CW, pre);
@@ -376,7 +388,7 @@ gemm_kernel(const GemmParams p, const __grid_constant__ CUtensorMap mapA, const 
           if (c + 1 == NCH) {
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(&tempty[acc]);
+            if (lane == 0) { if (leader) mbar_arrive(&tempty[acc]); else mbar_arrive_remote(&tempty[acc], 0); }
           }
 #pragma unroll
           for (int g = 0; g < 4; ++g) {
@@ -400,7 +412,6 @@ gemm_kernel(const GemmParams p, const __grid_constant__ CUtensorMap mapA, const 
         }
         fence_proxy_async_smem();
         __syncwarp();
-        const int row_base = mt * GEMM_BM + quarter * 32;
         if (lane == 0) {
           tma_store_3d(&mapOut, stg, col_base, row_base, 0);
           tma_store_commit();
@@ -425,10 +436,11 @@ gemm_kernel(const GemmParams p, const __grid_constant__ CUtensorMap mapA, const 
   }
 
   tc_fence_before();
-  __syncthreads();
+  if constexpr (CG == 2) cluster_sync_all();  // the peer may still be arriving on / reading from this CTA
+  else __syncthreads();
   if (warp == 2) {
     tc_fence_after();
-    tmem_dealloc<1>(tmem_base, 2 * BN);
+    tmem_dealloc<CG>(tmem_base, 2 * BN);
   }
 }
 
@@ -476,15 +488,35 @@ int make_tmap_bf16(CUtensorMap* map, const void* ptr, uint64_t inner, uint64_t o
   return SIMX_OK;
 }
 
-template <int BN, bool MN, int EPI, int NP>
-static int launch_gemm(const GemmParams& p, const CUtensorMap& ma, const CUtensorMap& mb, cudaStream_t stream) {
-  auto kern = gemm_kernel<BN, MN, EPI, NP>;
+// SIMX_GEMM_1CTA=1 forces the single-CTA kernels (A/B comparison, fallback)
+static bool use_cta_pairs() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("SIMX_GEMM_1CTA");
+    v = (e != nullptr && e[0] == '1') ? 0 : 1;
+  }
+  return v == 1;
+}
+
+template <int BN, bool MN, int EPI, int NP, int CG>
+static int launch_gemm_cg(GemmParams p, const bf16* A, long lda, long a_ps, const bf16* B, long ldb, long b_ps, int planes,
+                          cudaStream_t stream) {
+  auto kern = gemm_kernel<BN, MN, EPI, NP, CG>;
   constexpr bool TS = kTmaStore<BN, MN, EPI, NP>;
-  constexpr uint32_t smem_bytes = GemmSmem<BN, TS>::TOTAL;
+  constexpr uint32_t smem_bytes = GemmSmem<BN, TS, CG>::TOTAL;
   static bool attr_set = false;
   if (!attr_set) {
     SIMX_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
     attr_set = true;
+  }
+  p.m_tiles = (p.M + GEMM_BM * CG - 1) / (GEMM_BM * CG);
+  CUtensorMap ma, mb;
+  if (!MN) {
+    SIMX_TRY(make_tmap_bf16(&ma, A, p.K, p.M, planes, lda, a_ps, GEMM_BM));
+    SIMX_TRY(make_tmap_bf16(&mb, B, p.K, p.N, planes, ldb, b_ps, BN / CG));
+  } else {
+    SIMX_TRY(make_tmap_bf16(&ma, A, p.M, p.K, planes, lda, a_ps, GEMM_BK));
+    SIMX_TRY(make_tmap_bf16(&mb, B, p.N, p.K, planes, ldb, b_ps, GEMM_BK));
   }
   CUtensorMap mo = ma, mo2 = ma;  // placeholders when the epilogue stores from registers
   if constexpr (TS) {
@@ -492,29 +524,50 @@ static int launch_gemm(const GemmParams& p, const CUtensorMap& ma, const CUtenso
     if constexpr (EPI == SIMX_EPI_BIAS_GELU) SIMX_TRY(make_tmap_bf16(&mo2, p.out2, p.N, p.M, 1, p.ldo, 0, 32));
   }
   const int total = p.m_tiles * p.n_tiles * p.ksplit;
-  const int grid = min(total, num_sms());
-  kern<<<grid, GEMM_THREADS, smem_bytes, stream>>>(p, ma, mb, mo, mo2);
+  const int grid = CG * min(total, num_sms() / CG);
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(GEMM_THREADS);
+  cfg.dynamicSmemBytes = smem_bytes;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = CG;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  SIMX_CUDA(cudaLaunchKernelEx(&cfg, kern, p, ma, mb, mo, mo2));
   SIMX_LAUNCH_CHECK();
   return SIMX_OK;
 }
 
+template <int BN, bool MN, int EPI, int NP>
+static int launch_gemm(const GemmParams& p, const bf16* A, long lda, long a_ps, const bf16* B, long ldb, long b_ps, int planes,
+                       cudaStream_t stream) {
+  if constexpr (BN == 256) {
+    if (use_cta_pairs()) return launch_gemm_cg<BN, MN, EPI, NP, 2>(p, A, lda, a_ps, B, ldb, b_ps, planes, stream);
+  }
+  return launch_gemm_cg<BN, MN, EPI, NP, 1>(p, A, lda, a_ps, B, ldb, b_ps, planes, stream);
+}
+
 template <int BN, bool MN, int NP>
-static int dispatch_epi(int epi, const GemmParams& p, const CUtensorMap& ma, const CUtensorMap& mb,
-                        cudaStream_t stream) {
+static int dispatch_epi(int epi, const GemmParams& p, const bf16* A, long lda, long a_ps, const bf16* B, long ldb,
+                        long b_ps, int planes, cudaStream_t stream) {
   if constexpr (MN) {
     SIMX_CHECK(epi == SIMX_EPI_ATOMIC_F32 || epi == SIMX_EPI_PLAIN, SIMX_ERR_INVALID,
                "MN-major GEMM supports the PLAIN and ATOMIC_F32 epilogues only");
-    if (epi == SIMX_EPI_ATOMIC_F32) return launch_gemm<BN, MN, SIMX_EPI_ATOMIC_F32, NP>(p, ma, mb, stream);
-    return launch_gemm<BN, MN, SIMX_EPI_PLAIN, NP>(p, ma, mb, stream);
+    if (epi == SIMX_EPI_ATOMIC_F32) return launch_gemm<BN, MN, SIMX_EPI_ATOMIC_F32, NP>(p, A, lda, a_ps, B, ldb, b_ps, planes, stream);
+    return launch_gemm<BN, MN, SIMX_EPI_PLAIN, NP>(p, A, lda, a_ps, B, ldb, b_ps, planes, stream);
   } else {
     switch (epi) {
-      case SIMX_EPI_PLAIN: return launch_gemm<BN, MN, SIMX_EPI_PLAIN, NP>(p, ma, mb, stream);
-      case SIMX_EPI_BIAS: return launch_gemm<BN, MN, SIMX_EPI_BIAS, NP>(p, ma, mb, stream);
-      case SIMX_EPI_BIAS_GELU: return launch_gemm<BN, MN, SIMX_EPI_BIAS_GELU, NP>(p, ma, mb, stream);
-      case SIMX_EPI_BIAS_ADD: return launch_gemm<BN, MN, SIMX_EPI_BIAS_ADD, NP>(p, ma, mb, stream);
-      case SIMX_EPI_MUL: return launch_gemm<BN, MN, SIMX_EPI_MUL, NP>(p, ma, mb, stream);
-      case SIMX_EPI_ADD: return launch_gemm<BN, MN, SIMX_EPI_ADD, NP>(p, ma, mb, stream);
-      case SIMX_EPI_ATOMIC_F32: return launch_gemm<BN, MN, SIMX_EPI_ATOMIC_F32, NP>(p, ma, mb, stream);
+      case SIMX_EPI_PLAIN: return launch_gemm<BN, MN, SIMX_EPI_PLAIN, NP>(p, A, lda, a_ps, B, ldb, b_ps, planes, stream);
+      case SIMX_EPI_BIAS: return launch_gemm<BN, MN, SIMX_EPI_BIAS, NP>(p, A, lda, a_ps, B, ldb, b_ps, planes, stream);
+      case SIMX_EPI_BIAS_GELU: return launch_gemm<BN, MN, SIMX_EPI_BIAS_GELU, NP>(p, A, lda, a_ps, B, ldb, b_ps, planes, stream);
+      case SIMX_EPI_BIAS_ADD: return launch_gemm<BN, MN, SIMX_EPI_BIAS_ADD, NP>(p, A, lda, a_ps, B, ldb, b_ps, planes, stream);
+      case SIMX_EPI_MUL: return launch_gemm<BN, MN, SIMX_EPI_MUL, NP>(p, A, lda, a_ps, B, ldb, b_ps, planes, stream);
+      case SIMX_EPI_ADD: return launch_gemm<BN, MN, SIMX_EPI_ADD, NP>(p, A, lda, a_ps, B, ldb, b_ps, planes, stream);
+      case SIMX_EPI_ATOMIC_F32: return launch_gemm<BN, MN, SIMX_EPI_ATOMIC_F32, NP>(p, A, lda, a_ps, B, ldb, b_ps, planes, stream);
     }
     SIMX_FAIL(SIMX_ERR_INVALID, "unknown GEMM epilogue %d", epi);
   }
@@ -570,25 +623,16 @@ int gemm(int M, int N, int K, const bf16* A, long lda, long a_ps, bool a_mn, con
   p.aux = aux; p.aux_ps = aux_ps; p.ldaux = ldaux;
   p.bias = bias; p.outf = outf; p.ldof = ldof;
 
-  CUtensorMap ma, mb;
-  if (!a_mn) {
-    SIMX_TRY(make_tmap_bf16(&ma, A, K, M, planes, lda, a_ps, GEMM_BM));
-    SIMX_TRY(make_tmap_bf16(&mb, B, K, N, planes, ldb, b_ps, BN));
-  } else {
-    SIMX_TRY(make_tmap_bf16(&ma, A, M, K, planes, lda, a_ps, GEMM_BK));
-    SIMX_TRY(make_tmap_bf16(&mb, B, N, K, planes, ldb, b_ps, GEMM_BK));
-  }
-
   ProfScope prof(a_mn ? "gemm_mn" : "gemm_kk", 2.0 * M * N * (double)K * p.npass,
                  2.0 * planes * ((double)M * K + (double)N * K) + (epi == SIMX_EPI_ATOMIC_F32 ? 4.0 : 2.0 * planes) * M * N, stream);
 #define SIMX_GEMM_DISPATCH(BN_)                                                                  \
   if (BN == BN_) {                                                                               \
     if (a_mn) {                                                                                  \
-      if (planes == 1) return dispatch_epi<BN_, true, 1>(epi, p, ma, mb, stream);                \
-      return dispatch_epi<BN_, true, 3>(epi, p, ma, mb, stream);                                 \
+      if (planes == 1) return dispatch_epi<BN_, true, 1>(epi, p, A, lda, a_ps, B, ldb, b_ps, planes, stream);                \
+      return dispatch_epi<BN_, true, 3>(epi, p, A, lda, a_ps, B, ldb, b_ps, planes, stream);                                 \
     } else {                                                                                     \
-      if (planes == 1) return dispatch_epi<BN_, false, 1>(epi, p, ma, mb, stream);               \
-      return dispatch_epi<BN_, false, 3>(epi, p, ma, mb, stream);                                \
+      if (planes == 1) return dispatch_epi<BN_, false, 1>(epi, p, A, lda, a_ps, B, ldb, b_ps, planes, stream);               \
+      return dispatch_epi<BN_, false, 3>(epi, p, A, lda, a_ps, B, ldb, b_ps, planes, stream);                                \
     }                                                                                            \
   }
   SIMX_GEMM_DISPATCH(256)

@@ -100,6 +100,22 @@ __device__ __forceinline__ void tma_load_3d(const CUtensorMap* d, uint64_t* bar,
       "l"(reinterpret_cast<uint64_t>(d)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
       : "memory");
 }
+// CG == 2: cta_group::2 form — data lands in THIS CTA's smem, the transaction bytes are credited to the LEADER CTA's
+// mbarrier at the same offset (peer bit of the shared::cluster barrier address cleared)
+template <int CG>
+__device__ __forceinline__ void tma_load_3d_cg(const CUtensorMap* d, uint64_t* bar, void* smem, int32_t c0, int32_t c1,
+                                               int32_t c2) {
+  if constexpr (CG == 1) {
+    tma_load_3d(d, bar, smem, c0, c1, c2);
+  } else {
+    const uint32_t mbar = smem_u32(bar) & 0xFEFFFFFFu;
+    asm volatile(
+        "cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], "
+        "[%2];" ::"r"(smem_u32(smem)),
+        "l"(reinterpret_cast<uint64_t>(d)), "r"(mbar), "r"(c0), "r"(c1), "r"(c2)
+        : "memory");
+  }
+}
 // 2-CTA variant: data lands in this CTA's smem, the transaction bytes are credited to the *leader* CTA's
 // mbarrier (peer bit of the barrier address cleared).
 __device__ __forceinline__ void tma_load_2d_2sm(const CUtensorMap* d, uint64_t* bar, void* smem, int32_t c0,
