@@ -245,8 +245,15 @@ def run_b200(args):
         dom = max(gemms, key=lambda k: k["ms"]) if gemms else None
         if dom:
             peak = peaks["tflops_sustained"]
+            # DRAM bytes per launch of that kernel from the committed `ncu --set full` capture (same shape only)
+            traffic, tsrc = None, None
+            tf = ROOT / "profiles" / "ncu_traffic.json"
+            if tf.exists() and (nq, group, args.p_len) == (128, 16, 128):
+                t = json.loads(tf.read_text()).get(dom["name"])
+                if t:
+                    traffic, tsrc = t["dram_bytes_per_launch"], t["source"] + " (passage-tower launch, " + t["shape"] + ")"
             roofline = dict(kernel=dom["name"] + " (gemm_kernel, tcgen05)", bound="tensor", achieved=dom["tflops"],
-                            peak=peak, unit="TFLOP/s", frac=dom["tflops"] / peak, traffic=None,
+                            peak=peak, unit="TFLOP/s", frac=dom["tflops"] / peak, traffic=traffic, traffic_source=tsrc,
                             peak_source=peaks["source"] + ", sustained bf16 (kernel timed inside a long step)",
                             launches=dom["launches"], avg_launch_ms=dom["ms"] / dom["launches"],
                             step_share=dom["share"],
