@@ -172,6 +172,15 @@ int simx_pair_distill(const simx_pair_cfg* cfg, const float* Qa, const float* Ca
                       const int32_t* pos_idx, float* out_losses, float* dQa, float* dCa, float* dQb, float* dCb,
                       void* workspace, void* stream);
 
+/* SimANS ambiguous-negative sampling (SimANS/utils/MARCO_until_new.py:165-202, SimANS/utils/util_wiki.py:613-639):
+ * for each of NQ queries choose k of its first n_valid[q] (<= NC <= 1024) candidates, without duplicates, with probability
+ * proportional to  exp(-p0 |s - s+|)  (mode 0, p0 = tau)  or  exp(-p0 (s - s+ + p1)^2)  (mode 1, p0 = a, p1 = b); queries
+ * whose pos_score is 0 take the last k candidates.  scores [NQ,NC] fp32, pos_score [NQ], out_idx [NQ,k] int32 candidate
+ * indices.  Same rounds as the reference (k draws with replacement, keep distinct, drop them from the pool, repeat);
+ * counter-based RNG from `seed` — distribution-level parity only, the reference's stream is CPython's. */
+int simx_simans_sample(const float* scores, const int32_t* n_valid, const float* pos_score, int NQ, int NC, int k,
+                       int mode, float p0, float p1, uint64_t seed, int32_t* out_idx, void* stream);
+
 /* ------------------------------------------------------------------------------------------------
  * Operator-level entry points (used by the unit tests and by bench.py's kernel timing; the encoder calls the
  * same kernels internally).
