@@ -172,6 +172,13 @@ int simx_pair_distill(const simx_pair_cfg* cfg, const float* Qa, const float* Ca
                       const int32_t* pos_idx, float* out_losses, float* dQa, float* dCa, float* dQb, float* dCb,
                       void* workspace, void* stream);
 
+/* LEAD cross-encoder-teacher variant (--distill_ce: LEAD/util.py:669-717, 801-829): the same four terms on each query's
+ * own [1+n] block (student scores q_i . c_ij vs. the teacher's relevance logits [q_count, 1+n], positive = column 0).
+ * Uses cfg->q_count, c_count (= q_count * group), H, the four weights, temperature, grad_scale.  dT [q_count, 1+n] =
+ * d(total)/d(teacher logits) or NULL. */
+int simx_local_pair_distill(const simx_pair_cfg* cfg, const float* Q_local, const float* C_local,
+                            const float* teacher_logits, float* out_losses, float* dQ, float* dC, float* dT, void* stream);
+
 /* SimANS ambiguous-negative sampling (SimANS/utils/MARCO_until_new.py:165-202, SimANS/utils/util_wiki.py:613-639):
  * for each of NQ queries choose k of its first n_valid[q] (<= NC <= 1024) candidates, without duplicates, with probability
  * proportional to  exp(-p0 |s - s+|)  (mode 0, p0 = tau)  or  exp(-p0 (s - s+ + p1)^2)  (mode 1, p0 = a, p1 = b); queries

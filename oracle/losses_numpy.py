@@ -186,3 +186,50 @@ def lead_de_db_loss(q_db, c_db, q_de, c_de, qL_db, cL_db, qL_de, cL_de, *, group
             grads["qL_db"].append(li * l[1]); grads["cL_db"].append(li * l[2])
             grads["qL_de"].append(li * l[3]); grads["cL_de"].append(li * l[4])
     return total, grads
+
+
+def local_pair_distill(Q, C, teacher, *, group, w_nll_a=0.0, w_nll_b=0.0, w_kl_b2a=0.0, w_kl_a2b=0.0, temperature=1.0):
+    """LEAD --distill_ce variant (/root/reference/LEAD/util.py:669-717, 801-829): pair_distill's four terms on each query's
+    own [1+n] block; a = q_i . c_ij, b = the cross-encoder's relevance logits, positive = column 0.
+    Returns (losses, dQ, dC, d_teacher)."""
+    Q, C, Bm = np.asarray(Q, np.float64), np.asarray(C, np.float64), np.asarray(teacher, np.float64)
+    nq, H = Q.shape
+    Cl = C.reshape(nq, group, H)
+    A = np.einsum("bh,bdh->bd", Q, Cl)
+    T = temperature
+    lsa, lsb = _log_softmax(A), _log_softmax(Bm)
+    lta, ltb = _log_softmax(A / T), _log_softmax(Bm / T)
+    ta, tb = np.exp(lta), np.exp(ltb)
+    nll_a, nll_b = -lsa[:, 0].mean(), -lsb[:, 0].mean()
+    kb = (tb * (ltb - lsa)).sum(1)
+    ka = (ta * (lta - lsb)).sum(1)
+    total = w_nll_a * nll_a + w_nll_b * nll_b + w_kl_b2a * kb.mean() + w_kl_a2b * ka.mean()
+    oh = np.zeros_like(A)
+    oh[:, 0] = 1.0
+    pa, pb = np.exp(lsa), np.exp(lsb)
+    dA = (w_nll_a * (pa - oh) + w_kl_b2a * (pa - tb) + w_kl_a2b / T * ta * ((lta - lsb) - ka[:, None])) / nq
+    dB = (w_nll_b * (pb - oh) + w_kl_a2b * (pb - ta) + w_kl_b2a / T * tb * ((ltb - lsa) - kb[:, None])) / nq
+    out = dict(total=total, nll_a=nll_a, nll_b=nll_b, kl_b2a=kb.mean(), kl_a2b=ka.mean())
+    return out, np.einsum("bd,bdh->bh", dA, Cl), (dA[:, :, None] * Q[:, None, :]).reshape(nq * group, H), dB
+
+
+def lead_ce_db_loss(q_db, c_db, ce_logits, qL_db, cL_db, ce_layer_logits, *, group, temperature=1.0, layer_temperature=1.0,
+                    para_db=1.0, para_ce=1.0, para_dis=1.0, train_ce=True):
+    """The CE -> DB branch of LEAD's distill_loss with lambda re-weighted per-layer score distillation
+    (/root/reference/LEAD/util.py:669-717, 801-829).  ce_layer_logits: list of [B, 1+n] per-selected-layer CE logits.
+    Returns (total, grads dict)."""
+    out, dq, dc, dt = local_pair_distill(q_db, c_db, ce_logits, group=group, w_nll_a=para_db,
+                                         w_nll_b=para_ce if train_ce else 0.0, w_kl_b2a=para_dis,
+                                         w_kl_a2b=para_dis if train_ce else 0.0, temperature=temperature)
+    total = out["total"]
+    grads = dict(q_db=dq, c_db=dc, ce_logits=dt, qL_db=[], cL_db=[], ce_layers=[])
+    layer = [local_pair_distill(a, b, t, group=group, w_kl_b2a=1.0, temperature=temperature)
+             for a, b, t in zip(qL_db, cL_db, ce_layer_logits)]
+    if layer:
+        z = -np.array([l[0]["nll_b"] for l in layer]) / layer_temperature
+        lam = np.exp(z - z.max())
+        lam /= lam.sum()
+        for li, l in zip(lam, layer):
+            total += li * l[0]["kl_b2a"]
+            grads["qL_db"].append(li * l[1]); grads["cL_db"].append(li * l[2]); grads["ce_layers"].append(li * l[3])
+    return total, grads

@@ -324,6 +324,29 @@ def golden_lead_distill():
         for n, v in t.items():
             res[f"{tag}_d_{n}"] = (v.grad if v.grad is not None else torch.zeros_like(v)).numpy().copy()
         print("lead_distill", tag, loss.item(), {k_: round(float(v_), 5) for k_, v_ in loss_dict.items()})
+    # ---- cross-encoder teacher variant (--distill_ce): local [1+n] blocks, CE trained too, per-layer CE logits ----
+    ce_logits = (2.0 * rng.standard_normal((GQ, group))).astype(np.float32)
+    ce_layers = (2.0 * rng.standard_normal((12, GQ, group))).astype(np.float32)
+    res.update(ce_logits=ce_logits, ce_layers=ce_layers)
+    t = {n: torch.from_numpy(v.copy()).requires_grad_(True) for n, v in
+         dict(q_db=arrs["q_db"], c_db=arrs["c_db"], qL_db=arrs["qL_db"], cL_db=arrs["cL_db"], ce_logits=ce_logits,
+              ce_layers=ce_layers).items()}
+    args = types.SimpleNamespace(
+        device="cpu", local_rank=-1, distill_ce=True, distill_db=True, distill_de=False, distill_col=False, train_ce=True,
+        temperature=2.0, layer_temperature=0.5, distill_de_db_layer_score=False, distill_col_db_layer_score=False,
+        distill_ce_db_layer_score=True, distill_col_db_attention=False, distill_de_db_attention=False,
+        distill_ce_db_attention=False, layer_score_reweight=True, distill_para_db=1.0, distill_para_ce=0.6,
+        distill_para_ce_db_dis=1.2, distill_para_ce_db_layer_score=0.3)
+    batch = {"de_ctx_start_end": torch.zeros(GQ, group + 1, 2, dtype=torch.long)}
+    loss, loss_dict = util.distill_loss(args, None, None, t["q_db"], None, None, t["c_db"], None, sel_db, sel_de, None,
+                                        None, None, t["qL_db"], t["cL_db"], None, None, t["ce_layers"], None,
+                                        t["ce_logits"], batch)
+    loss.backward()
+    res["ce_loss"] = np.array([loss.item()])
+    res["ce_cfg"] = np.array([2.0, 0.5, 1.0, 0.6, 1.2])
+    for n, v in t.items():
+        res[f"ce_d_{n}"] = (v.grad if v.grad is not None else torch.zeros_like(v)).numpy().copy()
+    print("lead_distill ce", loss.item(), {k_: round(float(v_), 5) for k_, v_ in loss_dict.items()})
     np.savez_compressed(GOLD / "lead_distill.npz", **res)
 
 

@@ -100,6 +100,7 @@ SIGNATURES = {
     "simx_score_loss": (_I, [_LCFG, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
     "simx_pair_distill_workspace_bytes": (C.c_size_t, [_I, _I, _I]),
     "simx_pair_distill": (_I, [C.POINTER(PairCfg), _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
+    "simx_local_pair_distill": (_I, [C.POINTER(PairCfg), _P, _P, _P, _P, _P, _P, _P, _P]),
     "simx_simans_sample": (_I, [_P, _P, _P, _I, _I, _I, _I, C.c_float, C.c_float, C.c_uint64, _P, _P]),
     "simx_attention_forward": (_I, [_P, _P, _P, _P, _I, _I, _I, _I, _I, _L, _L, _P]),
     "simx_attention_backward": (_I, [_P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _L, _L, _P]),

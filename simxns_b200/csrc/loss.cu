@@ -351,6 +351,83 @@ pair_row_kernel(const float* __restrict__ A, const float* __restrict__ B, int GQ
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// LEAD cross-encoder teacher variant (--distill_ce, LEAD/util.py:669-717, 801-829): the same four terms as
+// pair_row_kernel but on the query's own [1+n] block (cross-batch negatives removed, util.py:704), a = student scores
+// q_i . c_ij, b = the teacher's relevance logits [B, 1+n], positive = column 0.  One warp per query; also returns
+// d(total)/d(teacher logits) for --train_ce.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128)
+local_pair_kernel(int q_count, int G, int H, const float* __restrict__ Q, const float* __restrict__ C,
+                  const float* __restrict__ teacher, PairW w, float* out_losses, float* dQ, float* dC, float* dT) {
+  __shared__ float sa[4][MAX_GROUP], sg[4][MAX_GROUP];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int i = blockIdx.x * 4 + warp;
+  if (i >= q_count) return;
+  const float* q = Q + (long)i * H;
+  const float* c = C + (long)i * G * H;
+  const float* b = teacher + (long)i * G;
+  float* a = sa[warp];
+  float* g = sg[warp];
+  for (int j = 0; j < G; ++j) {
+    float acc = 0.f;
+    for (int h = lane * 4; h < H; h += 128) {
+      const float4 x = __ldg(reinterpret_cast<const float4*>(q + h));
+      const float4 y = __ldg(reinterpret_cast<const float4*>(c + (long)j * H + h));
+      acc += x.x * y.x + x.y * y.y + x.z * y.z + x.w * y.w;
+    }
+    acc = warp_sum(acc);
+    if (lane == 0) a[j] = acc;
+  }
+  __syncwarp();
+  const float invT = 1.f / w.T, r = 1.f / q_count;
+  float ma = -INFINITY, mb = -INFINITY;
+  for (int j = 0; j < G; ++j) { ma = fmaxf(ma, a[j]); mb = fmaxf(mb, b[j]); }
+  float sa1 = 0.f, sb1 = 0.f, saT = 0.f, sbT = 0.f;
+  for (int j = 0; j < G; ++j) {
+    sa1 += expf(a[j] - ma); sb1 += expf(b[j] - mb);
+    saT += expf((a[j] - ma) * invT); sbT += expf((b[j] - mb) * invT);
+  }
+  const float lse_a = ma + logf(sa1), lse_b = mb + logf(sb1), lse_aT = ma * invT + logf(saT), lse_bT = mb * invT + logf(sbT);
+  float k_b2a = 0.f, k_a2b = 0.f;
+  for (int j = 0; j < G; ++j) {
+    const float lta = a[j] * invT - lse_aT, ltb = b[j] * invT - lse_bT;
+    k_b2a += expf(ltb) * (ltb - (a[j] - lse_a));
+    k_a2b += expf(lta) * (lta - (b[j] - lse_b));
+  }
+  if (lane == 0) {
+    const float na = lse_a - a[0], nb = lse_b - b[0];
+    atomicAdd(out_losses + 1, na * r);
+    atomicAdd(out_losses + 2, nb * r);
+    atomicAdd(out_losses + 3, k_b2a * r);
+    atomicAdd(out_losses + 4, k_a2b * r);
+    atomicAdd(out_losses + 0, (w.nll_a * na + w.nll_b * nb + w.kl_b2a * k_b2a + w.kl_a2b * k_a2b) * r);
+    if (a[0] >= ma) atomicAdd(out_losses + 6, 1.f);
+  }
+  const float rs = r * w.grad_scale;
+  for (int j = lane; j < G; j += 32) {
+    const float lta = a[j] * invT - lse_aT, ltb = b[j] * invT - lse_bT, lsa = a[j] - lse_a, lsb = b[j] - lse_b;
+    const float pa = expf(lsa), pb = expf(lsb), ta = expf(lta), tb = expf(ltb), oh = j == 0 ? 1.f : 0.f;
+    g[j] = rs * (w.nll_a * (pa - oh) + w.kl_b2a * (pa - tb) + w.kl_a2b * invT * ta * ((lta - lsb) - k_a2b));
+    if (dT != nullptr)
+      dT[(long)i * G + j] = rs * (w.nll_b * (pb - oh) + w.kl_a2b * (pb - ta) + w.kl_b2a * invT * tb * ((ltb - lsa) - k_b2a));
+  }
+  __syncwarp();
+  float* dq = dQ + (long)i * H;
+  float* dc = dC + (long)i * G * H;
+  for (int h = lane * 4; h < H; h += 128) {
+    const float4 x = __ldg(reinterpret_cast<const float4*>(q + h));
+    float4 accq = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int j = 0; j < G; ++j) {
+      const float gj = g[j];
+      const float4 y = __ldg(reinterpret_cast<const float4*>(c + (long)j * H + h));
+      accq.x += gj * y.x; accq.y += gj * y.y; accq.z += gj * y.z; accq.w += gj * y.w;
+      *reinterpret_cast<float4*>(dc + (long)j * H + h) = make_float4(gj * x.x, gj * x.y, gj * x.z, gj * x.w);
+    }
+    *reinterpret_cast<float4*>(dq + h) = accq;
+  }
+}
+
 // shared pieces of the global-matrix paths ---------------------------------------------------------
 struct ScoreWs {  // per embedding pair (Q, C): planes, transposed planes, scores, score gradients
   size_t qp, cp, ctp, s, ds, total;
@@ -527,6 +604,25 @@ extern "C" int simx_pair_distill(const simx_pair_cfg* cfg, const float* Qa, cons
   SIMX_LAUNCH_CHECK();
   SIMX_TRY(score_backward(GQ, GC, H, cfg->q_begin, cfg->q_count, cfg->c_begin, cfg->c_count, wa, w, dQa, dCa, st));
   if (train_b) SIMX_TRY(score_backward(GQ, GC, H, cfg->q_begin, cfg->q_count, cfg->c_begin, cfg->c_count, wb, w, dQb, dCb, st));
+  return SIMX_OK;
+}
+
+extern "C" int simx_local_pair_distill(const simx_pair_cfg* cfg, const float* Q_local, const float* C_local,
+                                       const float* teacher_logits, float* out_losses, float* dQ, float* dC, float* dT,
+                                       void* stream) {
+  using namespace simx;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  SIMX_CHECK(cfg && Q_local && C_local && teacher_logits && out_losses && dQ && dC, SIMX_ERR_INVALID,
+             "local_pair_distill: null argument");
+  SIMX_CHECK(cfg->q_count > 0 && cfg->c_count > 0 && cfg->c_count % cfg->q_count == 0 &&
+                 cfg->c_count / cfg->q_count <= MAX_GROUP, SIMX_ERR_INVALID,
+             "local_pair_distill: c_count must be q_count * group with group <= %d", MAX_GROUP);
+  SIMX_CHECK(cfg->H > 0 && cfg->H % 4 == 0 && cfg->temperature > 0.f, SIMX_ERR_INVALID, "local_pair_distill: bad H / temperature");
+  SIMX_CUDA(cudaMemsetAsync(out_losses, 0, 8 * sizeof(float), st));
+  PairW pw{cfg->w_nll_a, cfg->w_nll_b, cfg->w_kl_b2a, cfg->w_kl_a2b, cfg->temperature, cfg->grad_scale, 0.f};
+  local_pair_kernel<<<(cfg->q_count + 3) / 4, 128, 0, st>>>(cfg->q_count, cfg->c_count / cfg->q_count, cfg->H, Q_local, C_local,
+                                                            teacher_logits, pw, out_losses, dQ, dC, dT);
+  SIMX_LAUNCH_CHECK();
   return SIMX_OK;
 }
 

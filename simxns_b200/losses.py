@@ -309,3 +309,67 @@ def lead_distill_loss(q_db, c_db, q_de, c_de, cls_q_db=None, cls_c_db=None, cls_
         loss = loss + layer_loss
         parts["loss_de_db_layer_dis"] = layer_loss.detach()
     return loss, parts
+
+
+class _LocalPairFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, q, c, teacher, opts):
+        lib = _lib.lib()
+        dev = q.device
+        if dev.type != "cuda":
+            raise RuntimeError("fused_local_pair_distill needs CUDA tensors (no CPU fallback)")
+        with torch.cuda.device(dev):
+            _lib.require_device()
+            q32, c32 = q.detach().to(torch.float32).contiguous(), c.detach().to(torch.float32).contiguous()
+            t32 = teacher.detach().to(device=dev, dtype=torch.float32).contiguous()
+            nq, H = q32.shape
+            nc = c32.shape[0]
+            if nc % nq or tuple(t32.shape) != (nq, nc // nq):
+                raise ValueError(f"teacher logits must be [{nq}, {nc // max(nq, 1)}], got {tuple(t32.shape)}")
+            w = opts["weights"]
+            cfg = _lib.PairCfg(GQ=nq, GC=nc, H=H, q_begin=0, q_count=nq, c_begin=0, c_count=nc, w_nll_a=w.get("nll_a", 0.0),
+                               w_nll_b=w.get("nll_b", 0.0), w_kl_b2a=w.get("kl_b2a", 0.0), w_kl_a2b=w.get("kl_a2b", 0.0),
+                               temperature=opts["temperature"], grad_scale=1.0, w_kd_b2a=0.0)
+            losses = torch.empty(8, dtype=torch.float32, device=dev)
+            dq, dc = torch.empty_like(q32), torch.empty_like(c32)
+            dt = torch.empty_like(t32) if ctx.needs_input_grad[2] else None
+            _lib.check(lib.simx_local_pair_distill(C.byref(cfg), q32.data_ptr(), c32.data_ptr(), t32.data_ptr(),
+                                                   losses.data_ptr(), dq.data_ptr(), dc.data_ptr(), _lib.ptr(dt),
+                                                   torch.cuda.current_stream(dev).cuda_stream), "simx_local_pair_distill")
+        ctx.grads = (dq, dc, dt)
+        ctx.mark_non_differentiable(losses)
+        return losses[0].clone(), losses
+
+    @staticmethod
+    def backward(ctx, g_total, _g):
+        return tuple(None if g is None else g * g_total for g in ctx.grads) + (None,)
+
+
+def fused_local_pair_distill(q_local, c_local, teacher_logits, weights: dict, *, temperature: float = 1.0):
+    """Student dual encoder (a) vs cross-encoder relevance logits (b) on each query's own [1+n] block.
+    weights: nll_a, nll_b, kl_b2a, kl_a2b.  Gradients flow into q_local, c_local and (if it requires grad) teacher_logits."""
+    return _LocalPairFn.apply(q_local, c_local, teacher_logits, dict(weights=dict(weights), temperature=float(temperature)))
+
+
+def lead_ce_distill_loss(q_db, c_db, ce_logits, cls_q_db=None, cls_c_db=None, ce_layer_logits=None, *,
+                         selected_db: Sequence[int] = (), selected_ce: Sequence[int] = (), temperature: float = 1.0,
+                         layer_temperature: float = 1.0, para_db: float = 1.0, para_ce: float = 1.0, para_dis: float = 1.0,
+                         train_ce: bool = True):
+    """CE-teacher -> DB-student branch of LEAD's distill_loss (/root/reference/LEAD/util.py:669-717, 801-829), no
+    all-gather (util.py:567).  ce_logits [B, 1+n]; ce_layer_logits [L_t, B, 1+n] (third output of lead_models.Reranker);
+    cls_*_db: per-layer [CLS] rows [n, L, H] of the student."""
+    w = dict(nll_a=para_db, nll_b=para_ce if train_ce else 0.0, kl_b2a=para_dis, kl_a2b=para_dis if train_ce else 0.0)
+    loss, detail = fused_local_pair_distill(q_db, c_db, ce_logits, w, temperature=temperature)
+    parts = dict(loss_db=detail[1], loss_ce=detail[2], loss_ce_db_dis=detail[3], loss_db_ce_dis=detail[4])
+    if len(selected_db):
+        kls, nlls = [], []
+        for ls, lt in zip(selected_db, selected_ce):
+            kl, d = fused_local_pair_distill(cls_q_db[:, ls], cls_c_db[:, ls], ce_layer_logits[lt], dict(kl_b2a=1.0),
+                                             temperature=temperature)
+            kls.append(kl)
+            nlls.append(d[2])
+        lam = torch.softmax(-torch.stack(nlls).detach() / layer_temperature, dim=0)
+        layer_loss = sum(l * k for l, k in zip(lam, kls))
+        loss = loss + layer_loss
+        parts["loss_ce_db_layer_dis"] = layer_loss.detach()
+    return loss, parts

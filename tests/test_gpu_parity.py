@@ -472,3 +472,20 @@ def test_lead_end_to_end_step_vs_oracle():
     loss.backward()
     assert_grads(student.question_model, ref_s, 1e-3)
     assert_grads(teacher.question_model, ref_t, 1e-3)
+
+
+def test_lead_ce_teacher_distill_vs_reference_golden(golden_dir):
+    from simxns_b200.losses import lead_ce_distill_loss
+
+    g = np.load(golden_dir / "lead_distill.npz")
+    sel_db, sel_t = [int(x) for x in g["sel_db"]], [int(x) for x in g["sel_de"]]
+    T, Tl, p_db, p_ce, p_dis = [float(x) for x in g["ce_cfg"]]
+    t = {n: cu(g[n]).requires_grad_(True) for n in ("q_db", "c_db", "qL_db", "cL_db", "ce_logits", "ce_layers")}
+    loss, parts = lead_ce_distill_loss(t["q_db"], t["c_db"], t["ce_logits"], t["qL_db"][:, :, 0], t["cL_db"][:, :, 0],
+                                       t["ce_layers"], selected_db=sel_db, selected_ce=sel_t, temperature=T,
+                                       layer_temperature=Tl, para_db=p_db, para_ce=p_ce, para_dis=p_dis, train_ce=True)
+    assert abs(loss.item() - g["ce_loss"][0]) < 1e-4
+    loss.backward()
+    for n in t:
+        ref = g[f"ce_d_{n}"]
+        assert np.abs(t[n].grad.cpu().numpy() - ref).max() < 1e-3 * max(1e-3, np.abs(ref).max()), n

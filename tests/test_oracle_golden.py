@@ -195,3 +195,22 @@ def test_wiki_adversarial_loss_against_reference(golden_dir):
         assert abs(out["total"] - g[tag + "_loss"][0]) < 2e-5
         _close(dQ, g[tag + "_dQ"], 2e-6)
         _close(dC, g[tag + "_dC"], 2e-6)
+
+
+def test_lead_ce_teacher_distill_against_reference(golden_dir):
+    """oracle lead_ce_db_loss vs the real LEAD distill_loss with --distill_ce --train_ce and per-layer CE logits"""
+    g = np.load(golden_dir / "lead_distill.npz")
+    group = int(g["group"][0])
+    sel_db, sel_t = list(g["sel_db"]), list(g["sel_de"])
+    T, Tl, p_db, p_ce, p_dis = g["ce_cfg"]
+    total, grads = ln.lead_ce_db_loss(g["q_db"], g["c_db"], g["ce_logits"], [g["qL_db"][:, l, 0] for l in sel_db],
+                                      [g["cL_db"][:, l, 0] for l in sel_db], [g["ce_layers"][l] for l in sel_t], group=group,
+                                      temperature=T, layer_temperature=Tl, para_db=p_db, para_ce=p_ce, para_dis=p_dis)
+    assert abs(total - g["ce_loss"][0]) < 2e-5
+    _close(grads["q_db"], g["ce_d_q_db"], 2e-6)
+    _close(grads["c_db"], g["ce_d_c_db"], 2e-6)
+    _close(grads["ce_logits"], g["ce_d_ce_logits"], 2e-6)
+    for i, (ls, lt) in enumerate(zip(sel_db, sel_t)):
+        _close(grads["qL_db"][i], g["ce_d_qL_db"][:, ls, 0], 2e-6)
+        _close(grads["cL_db"][i], g["ce_d_cL_db"][:, ls, 0], 2e-6)
+        _close(grads["ce_layers"][i], g["ce_d_ce_layers"][lt], 2e-6)
