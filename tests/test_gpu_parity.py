@@ -489,3 +489,76 @@ def test_lead_ce_teacher_distill_vs_reference_golden(golden_dir):
     for n in t:
         ref = g[f"ce_d_{n}"]
         assert np.abs(t[n].grad.cpu().numpy() - ref).max() < 1e-3 * max(1e-3, np.abs(ref).max()), n
+
+
+# ---------------------------------------------------------------------------------------------------------
+# checkpoint layout + training-loop contract
+# ---------------------------------------------------------------------------------------------------------
+def test_checkpoint_round_trip_with_reference_model(tmp_path):
+    """north_star "same checkpoint layout": a CheckpointState file written from this model loads into the reference's
+    HF-based BiBertEncoder (oracle/ref_torch.py port of SimANS/model/models.py:58-118) and vice versa, and both produce the
+    same embeddings (SimANS/utils/dpr_utils.py:22-24,73-77; co_training_marco_train.py:310-326)."""
+    import collections
+
+    from oracle import ref_torch as rt
+
+    CheckpointState = collections.namedtuple("CheckpointState", ['model_dict', 'optimizer_dict', 'scheduler_dict', 'offset',
+                                                                 'epoch', 'encoder_params'])
+    cfg = bn.bert_config(num_layers=2, hidden=128, heads=2, intermediate=256, vocab=300, max_pos=64)
+    ours = BiBertEncoder(None, question_model=build(cfg, bn.synth_params(cfg, seed=61), X3),
+                         ctx_model=build(cfg, bn.synth_params(cfg, seed=62), X3))
+    opt = torch.optim.AdamW(ours.parameters(), lr=1e-3)
+    state = CheckpointState(ours.state_dict(), opt.state_dict(), {}, 7, 0, {})
+    torch.save(state._asdict(), tmp_path / "checkpoint-7")
+    saved = torch.load(tmp_path / "checkpoint-7", map_location="cpu", weights_only=False)
+    assert set(saved) == {'model_dict', 'optimizer_dict', 'scheduler_dict', 'offset', 'epoch', 'encoder_params'}
+    ref = rt.BiBertEncoderRef(cfg)
+    missing, unexpected = ref.load_state_dict(saved["model_dict"], strict=False)
+    assert not unexpected and all("position_ids" in m or "token_type_ids" in m for m in missing)
+    ref.eval()
+    q_ids, q_mask = bn.synth_tokens(3, 16, cfg["vocab"], seed=1, ragged=True)
+    p_ids, p_mask = bn.synth_tokens(6, 40, cfg["vocab"], seed=2, ragged=True)
+    with torch.no_grad():
+        rq, rp = ref(torch.from_numpy(q_ids), torch.from_numpy(q_mask), torch.from_numpy(p_ids), torch.from_numpy(p_mask))
+        oq, op = ours(cu(q_ids), cu(q_mask), cu(p_ids), cu(p_mask))
+    assert (oq.cpu() - rq).abs().max() < 1e-4 and (op.cpu() - rp).abs().max() < 1e-4
+    # the other direction: a reference checkpoint (with the legacy position_ids buffer) into a fresh B200 model
+    sd = {k: v.clone() for k, v in ref.state_dict().items()}
+    sd["question_model.embeddings.position_ids"] = torch.arange(64)[None]
+    fresh = BiBertEncoder(None, question_model=HFBertEncoder(ec_from(cfg), precision=X3),
+                          ctx_model=HFBertEncoder(ec_from(cfg), precision=X3))
+    fresh.load_state_dict(sd, strict=False)
+    fresh.cuda()
+    with torch.no_grad():
+        fq, _ = fresh(cu(q_ids), cu(q_mask), cu(p_ids), cu(p_mask))
+    assert (fq.cpu() - rq).abs().max() < 1e-4
+
+
+def test_training_loop_contract_adamw_clip_accumulate():
+    """the retriever loop of co_training_marco_train.py:186-263 on this model: AdamW with the bias/LayerNorm no-decay
+    grouping, gradient accumulation, clip_grad_norm_, optimizer.step, zero_grad; weights re-staged after every step
+    (the loss must go down on a fixed batch)."""
+    cfg = bn.bert_config(num_layers=2, hidden=128, heads=2, intermediate=256, vocab=300, max_pos=64)
+    model = BiBertEncoder(None, question_model=build(cfg, bn.synth_params(cfg, seed=71), BF16),
+                          ctx_model=build(cfg, bn.synth_params(cfg, seed=72), BF16))
+    no_decay = ['bias', 'LayerNorm.weight']
+    groups = [{'params': [p for n, p in model.named_parameters() if not any(nd in n for nd in no_decay)], 'weight_decay': 0.01},
+              {'params': [p for n, p in model.named_parameters() if any(nd in n for nd in no_decay)], 'weight_decay': 0.0}]
+    opt = torch.optim.AdamW(groups, lr=2e-4, eps=1e-8)
+    nq, group = 8, 4
+    q_ids, q_mask = bn.synth_tokens(nq, 16, cfg["vocab"], seed=3, ragged=True)
+    p_ids, p_mask = bn.synth_tokens(nq * group, 32, cfg["vocab"], seed=4, ragged=True)
+    teacher = cu((3 * np.random.RandomState(5).standard_normal((nq, group))).astype(np.float32))
+    batch = (cu(q_ids), cu(q_mask), cu(p_ids), cu(p_mask))
+    losses, accum = [], 2
+    for step in range(12):
+        q, a = model(*batch)
+        loss = simans_distill_loss(q, a, teacher, temperature_distill=1.0) / accum
+        loss.backward()
+        if (step + 1) % accum == 0:
+            gn = torch.nn.utils.clip_grad_norm_(model.parameters(), 2.0)
+            assert torch.isfinite(gn)
+            opt.step()
+            model.zero_grad()
+            losses.append(loss.item() * accum)
+    assert losses[-1] < losses[0] - 0.05, losses
