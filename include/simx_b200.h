@@ -189,6 +189,42 @@ int simx_simans_sample(const float* scores, const int32_t* n_valid, const float*
                        int mode, float p0, float p1, uint64_t seed, int32_t* out_idx, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
+ * Optimizer tail: torch.nn.utils.clip_grad_norm_ + AdamW.step over every parameter tensor of a model in
+ * two launches (co_training_marco_train.py:57-69,246-263; LEAD/util.py:901,  LEAD/run_LEAD.py:232-238).
+ *   SIMX_ADAMW_TORCH  torch.optim.AdamW (LEAD): p *= 1 - lr wd;  p -= lr/(1-b1^t) * m / (sqrt(v)/sqrt(1-b2^t) + eps)
+ *   SIMX_ADAMW_HF     transformers.AdamW (SimANS, PROD; transformers v4 optimization.py, not vendored):
+ *                     p -= lr sqrt(1-b2^t)/(1-b1^t) * m / (sqrt(v) + eps)   [plain lr if !correct_bias];  then p -= lr wd p
+ * The tensor table lives in DEVICE memory (the caller copies it; the library keeps nothing).  Build it on the host,
+ * call simx_opt_plan() to fill `chunk_begin` and get the grid size, then copy it to the device.
+ * ---------------------------------------------------------------------------------------------- */
+#define SIMX_ADAMW_TORCH 0
+#define SIMX_ADAMW_HF 1
+typedef struct simx_opt_tensor {
+  float* p;            /* parameter (fp32 master), updated in place */
+  float* g;            /* gradient, or NULL: the tensor is skipped (a parameter that received no gradient) */
+  float* m;            /* exp_avg */
+  float* v;            /* exp_avg_sq */
+  int64_t numel;
+  int32_t chunk_begin; /* filled by simx_opt_plan */
+  float lr;            /* the tensor's param-group learning rate at this step (the scheduler's value) */
+  float weight_decay;  /* 0 for the bias / LayerNorm.weight group */
+  int32_t reserved;
+} simx_opt_tensor;
+/* host helper: fills chunk_begin of tensors_host[0..n) and returns the number of 8192-element chunks (= grid size), or
+ * -1 on a bad table. */
+int simx_opt_plan(simx_opt_tensor* tensors_host, int n);
+/* *out_sq_dev (device, fp64) = sum over all tensors of sum(g^2): total_norm^2 of clip_grad_norm_ (L2). */
+int simx_grad_sq_norm(const simx_opt_tensor* tensors_dev, int n, int total_chunks, double* out_sq_dev, void* stream);
+/* g *= min(1, max_norm / (sqrt(*sq_norm_dev) + 1e-6)) in place — what clip_grad_norm_ leaves in .grad. */
+int simx_clip_grads(const simx_opt_tensor* tensors_dev, int n, int total_chunks, const double* sq_norm_dev,
+                    float max_norm, void* stream);
+/* One AdamW step (`step` counts from 1).  sq_norm_dev != NULL: the gradient is clipped on the fly by the coefficient
+ * above (no host round trip, no extra pass); write_clipped_grads stores the clipped gradient back as well. */
+int simx_adamw_step(const simx_opt_tensor* tensors_dev, int n, int total_chunks, int mode, float beta1, float beta2,
+                    float eps, int step, int correct_bias, const double* sq_norm_dev, float max_norm,
+                    int write_clipped_grads, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
  * Operator-level entry points (used by the unit tests and by bench.py's kernel timing; the encoder calls the
  * same kernels internally).
  * ---------------------------------------------------------------------------------------------- */
@@ -197,7 +233,9 @@ int simx_simans_sample(const float* scores, const int32_t* n_valid, const float*
 #define SIMX_EPI_BIAS_GELU 2 /* h = acc + bias[n]; out = gelu_erf'(h); out2 = gelu_erf(h) (BertIntermediate; out is what
                                 backward multiplies by, the pre-activation itself is never needed again) */
 #define SIMX_EPI_BIAS_ADD 3  /* out = acc + bias[n] + aux[m,n]                        (BertSelfOutput/BertOutput pre-LN) */
-#define SIMX_EPI_MUL 4       /* out = acc * aux[m,n]                                  (dgrad through GELU: aux = saved gelu') */
+#define SIMX_EPI_MUL 4       /* out = acc * aux[m,n]                                  (dgrad through GELU: aux = saved gelu');
+                                if outf != NULL: outf[n] += sum_m out[m,n] (fp32, [N]) — the bias gradient of the layer
+                                whose dgrad this is, reduced in the epilogue instead of by a pass over `out` */
 #define SIMX_EPI_ADD 5       /* out = acc + aux[m,n]                                  (dgrad + residual grad) */
 #define SIMX_EPI_ATOMIC_F32 6 /* outf[m,n] += acc   (fp32 atomics; split-K wgrad)     */
 
@@ -214,12 +252,13 @@ int simx_gemm(int M, int N, int K, const void* A, int64_t lda, int64_t a_plane_s
 /* Self-attention of the encoder on the fused [T, 3H] projection (q | k | v column blocks, head h at columns h*64):
  *   ctx = softmax(q k^T / 8 + (1 - mask) * -inf) v       (LEAD/modeling_bert.py:324-368), head_dim 64, S <= 512.
  * lse2 [B, heads, S] (log2-domain log-sum-exp) is produced by forward and consumed by backward; delta [B, heads, S]
- * is backward scratch.  planes / plane strides as for simx_gemm. */
+ * is backward scratch.  planes / plane strides as for simx_gemm.  dbias_qkv (optional, [3H] fp32): += column sums of dqkv,
+ * i.e. the gradient of the fused q/k/v bias (reduced from the staged output tiles by the tcgen05 kernel). */
 int simx_attention_forward(const void* qkv, void* ctx, const int64_t* mask, float* lse2, int B, int S, int H, int heads,
                            int planes, int64_t qkv_plane_stride, int64_t ctx_plane_stride, void* stream);
 int simx_attention_backward(const void* qkv, const void* ctx, const void* dctx, void* dqkv, const int64_t* mask,
                             const float* lse2, float* delta, int B, int S, int H, int heads, int planes,
-                            int64_t qkv_plane_stride, int64_t ctx_plane_stride, void* stream);
+                            int64_t qkv_plane_stride, int64_t ctx_plane_stride, float* dbias_qkv, void* stream);
 
 #ifdef __cplusplus
 }

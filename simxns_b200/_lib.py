@@ -103,7 +103,7 @@ SIGNATURES = {
     "simx_local_pair_distill": (_I, [C.POINTER(PairCfg), _P, _P, _P, _P, _P, _P, _P, _P]),
     "simx_simans_sample": (_I, [_P, _P, _P, _I, _I, _I, _I, C.c_float, C.c_float, C.c_uint64, _P, _P]),
     "simx_attention_forward": (_I, [_P, _P, _P, _P, _I, _I, _I, _I, _I, _L, _L, _P]),
-    "simx_attention_backward": (_I, [_P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _L, _L, _P]),
+    "simx_attention_backward": (_I, [_P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _L, _L, _P, _P]),
     "simx_gemm": (
         _I,
         [_I, _I, _I, _P, _L, _L, _I, _P, _L, _L, _I, _I, _I, _P, _P, _L, _L, _P, _P, _L, _L, _P, _L, _I, _P],
@@ -111,6 +111,22 @@ SIGNATURES = {
 }
 
 _lib = None
+
+
+class OptTensor(C.Structure):
+    """mirror of `simx_opt_tensor`"""
+
+    _fields_ = [("p", C.c_void_p), ("g", C.c_void_p), ("m", C.c_void_p), ("v", C.c_void_p), ("numel", C.c_int64),
+                ("chunk_begin", C.c_int32), ("lr", C.c_float), ("weight_decay", C.c_float), ("reserved", C.c_int32)]
+
+
+ADAMW_TORCH, ADAMW_HF = 0, 1
+SIGNATURES.update({
+    "simx_opt_plan": (_I, [C.POINTER(OptTensor), _I]),
+    "simx_grad_sq_norm": (_I, [_P, _I, _I, _P, _P]),
+    "simx_clip_grads": (_I, [_P, _I, _I, _P, C.c_float, _P]),
+    "simx_adamw_step": (_I, [_P, _I, _I, _I, C.c_float, C.c_float, C.c_float, _I, _I, _P, C.c_float, _I, _P]),
+})
 
 
 def build(verbose: bool = False) -> Path:

@@ -507,7 +507,8 @@ attn_ref_kernel(const AttnRefParams p) {
 int attention_tc_forward(const bf16* qkv, bf16* ctx, const int64_t* mask, float* lse2, int B, int S, int H, int heads,
                          cudaStream_t st);
 int attention_tc_backward(const bf16* qkv, const bf16* ctx, const bf16* dctx, bf16* dqkv, const int64_t* mask,
-                          const float* lse2, int B, int S, int H, int heads, cudaStream_t st);
+                          const float* lse2, int B, int S, int H, int heads, float* dbias, cudaStream_t st);
+int colsum(int np, const bf16* x, long rows, int N, long row_stride, long ps, float* out, cudaStream_t st);
 
 // single-tile sequences go to the tcgen05 kernels (attention_tc.cu); SIMX_ATTN_LEGACY=1 forces the mma.sync path
 static bool use_tc_attention(int np, int S) {
@@ -553,12 +554,29 @@ int attention_forward(int np, const bf16* qkv, long ps_qkv, bf16* ctx, long ps_c
   return SIMX_OK;
 }
 
+// dbias (optional): [3H] fp32, += column sums of dqkv — the fused q/k/v bias gradient.  The tcgen05 kernel reduces
+// its staged output tiles in shared memory; the other paths run the column-sum kernel over dqkv afterwards.
+static int attention_backward_core(int np, const bf16* qkv, long ps_qkv, const bf16* ctx, const bf16* dctx, long ps_ctx,
+                                   bf16* dqkv, const int64_t* mask, const float* lse2, float* delta, int B, int S, int H,
+                                   int heads, cudaStream_t st);
+
 int attention_backward(int np, const bf16* qkv, long ps_qkv, const bf16* ctx, const bf16* dctx, long ps_ctx, bf16* dqkv,
                        const int64_t* mask, const float* lse2, float* delta, int B, int S, int H, int heads,
-                       cudaStream_t st) {
+                       float* dbias, cudaStream_t st) {
   SIMX_TRY(attn_check(B, S, H, heads));
+  if (use_tc_attention(np, S)) {
+    ProfScope prof("attn_bwd", 10.0 * B * heads * (double)S * S * ATT_D, 2.0 * np * B * (double)S * 8 * H, st);
+    return attention_tc_backward(qkv, ctx, dctx, dqkv, mask, lse2, B, S, H, heads, dbias, st);
+  }
+  SIMX_TRY(attention_backward_core(np, qkv, ps_qkv, ctx, dctx, ps_ctx, dqkv, mask, lse2, delta, B, S, H, heads, st));
+  if (dbias != nullptr) SIMX_TRY(colsum(np, dqkv, (long)B * S, 3 * H, 3L * H, ps_qkv, dbias, st));
+  return SIMX_OK;
+}
+
+static int attention_backward_core(int np, const bf16* qkv, long ps_qkv, const bf16* ctx, const bf16* dctx, long ps_ctx,
+                                   bf16* dqkv, const int64_t* mask, const float* lse2, float* delta, int B, int S, int H,
+                                   int heads, cudaStream_t st) {
   ProfScope prof("attn_bwd", 10.0 * B * heads * (double)S * S * ATT_D, 2.0 * np * B * (double)S * 8 * H, st);
-  if (use_tc_attention(np, S)) return attention_tc_backward(qkv, ctx, dctx, dqkv, mask, lse2, B, S, H, heads, st);
   if (np == 3) {
     AttnRefParams p{qkv, const_cast<bf16*>(ctx), dctx, dqkv, mask, const_cast<float*>(lse2), delta, ps_qkv, ps_ctx,
                     B, S, H, heads};
@@ -601,12 +619,12 @@ extern "C" int simx_attention_forward(const void* qkv, void* ctx, const int64_t*
 extern "C" int simx_attention_backward(const void* qkv, const void* ctx, const void* dctx, void* dqkv,
                                        const int64_t* mask, const float* lse2, float* delta, int B, int S, int H,
                                        int heads, int planes, int64_t qkv_plane_stride, int64_t ctx_plane_stride,
-                                       void* stream) {
+                                       float* dbias_qkv, void* stream) {
   using namespace simx;
   SIMX_CHECK(qkv && ctx && dctx && dqkv && lse2 && delta, SIMX_ERR_INVALID, "attention_backward: null argument");
   SIMX_CHECK(planes == 1 || planes == 3, SIMX_ERR_INVALID, "attention_backward: planes must be 1 or 3");
   return attention_backward(planes, static_cast<const bf16*>(qkv), qkv_plane_stride, static_cast<const bf16*>(ctx),
                             static_cast<const bf16*>(dctx), ctx_plane_stride, static_cast<bf16*>(dqkv), mask, lse2, delta,
-                            B, S, H, heads, static_cast<cudaStream_t>(stream));
+                            B, S, H, heads, dbias_qkv, static_cast<cudaStream_t>(stream));
 }
 

@@ -30,6 +30,8 @@ struct AttnTcParams {
   const bf16* dctx;     // backward: dO
   int B, S, H, heads;
   long long* timing;  // debug: 8 clock64 stamps of one CTA (simx_debug_attention_timing), else NULL
+  float* dbias;       // backward: [3H] fp32 column sums of dqkv (the fused q/k/v bias gradient) accumulated with
+                      // atomics, or NULL
 };
 static long long* g_attn_timing = nullptr;
 #define SIMX_STAMP(i) do { if (p.timing != nullptr && tid == 0 && blockIdx.x == 3 && blockIdx.y == gridDim.y / 2) p.timing[i] = clock64(); } while (0)
@@ -328,8 +330,32 @@ attn_bwd_tc_kernel(const AttnTcParams p, const __grid_constant__ CUtensorMap map
     tma_store_3d(&map_dqkv, smem + TILE, p.H + h * 64, 0, b);          // dK
     tma_store_3d(&map_dqkv, smem + 2 * TILE, h * 64, 0, b);            // dQ
     tma_store_commit();
-    tma_store_wait_read<0>();  // smem may be released once read; global visibility comes with kernel completion
   }
+  if (p.dbias != nullptr && tid < 192) {
+    // q/k/v bias gradient = column sums of the three [128 x 64] tiles just staged (what a separate pass over dqkv
+    // would re-read from HBM).  A warp owns 16 column pairs of one tile; its two half-warps take the rows whose
+    // swizzle phase (row & 4) differs, so the 32 lanes of one load hit 32 different banks.
+    const int tile = warp >> 1;                          // 0 dV, 1 dK, 2 dQ
+    const int cp = (warp & 1) * 16 + (lane & 15);        // column pair inside the tile
+    const int hsel = lane >> 4;
+    const uint32_t base = sQ + tile * TILE;
+    float s0 = 0.f, s1 = 0.f;
+#pragma unroll 8
+    for (int i = 0; i < 64; ++i) {
+      const int r = ((i >> 2) << 3) + (hsel << 2) + (i & 3);
+      const float2 f = unpack_bf16x2(ld_shared_u32(base + r * 128 + (((cp >> 2) ^ (r & 7)) << 4) + ((cp & 3) << 2)));
+      s0 += f.x;
+      s1 += f.y;
+    }
+    s0 += __shfl_xor_sync(0xffffffffu, s0, 16);
+    s1 += __shfl_xor_sync(0xffffffffu, s1, 16);
+    if (hsel == 0) {
+      float* o = p.dbias + (2 - tile) * p.H + h * 64 + 2 * cp;
+      atomicAdd(o, s0);
+      atomicAdd(o + 1, s1);
+    }
+  }
+  if (tid == 0) tma_store_wait_read<0>();  // smem may be released once read; global visibility comes with kernel completion
   SIMX_STAMP(7);
   if (warp == 1) {
     tc_fence_after();
@@ -349,14 +375,14 @@ int attention_tc_forward(const bf16* qkv, bf16* ctx, const int64_t* mask, float*
     SIMX_CUDA(cudaFuncSetAttribute(attn_fwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     attr = true;
   }
-  AttnTcParams p{mask, lse2, nullptr, nullptr, B, S, H, heads, nullptr};
+  AttnTcParams p{mask, lse2, nullptr, nullptr, B, S, H, heads, nullptr, nullptr};
   attn_fwd_tc_kernel<<<dim3(heads, B), 128, smem, st>>>(p, mq, mc);
   SIMX_LAUNCH_CHECK();
   return SIMX_OK;
 }
 
 int attention_tc_backward(const bf16* qkv, const bf16* ctx, const bf16* dctx, bf16* dqkv, const int64_t* mask,
-                          const float* lse2, int B, int S, int H, int heads, cudaStream_t st) {
+                          const float* lse2, int B, int S, int H, int heads, float* dbias, cudaStream_t st) {
   CUtensorMap mq, md, mo, mg;
   SIMX_TRY(make_tmap_bf16(&mq, qkv, 3 * (uint64_t)H, S, B, 3 * (uint64_t)H, (uint64_t)S * 3 * H, 128));
   SIMX_TRY(make_tmap_bf16(&md, dctx, H, S, B, H, (uint64_t)S * H, 128));
@@ -368,7 +394,7 @@ int attention_tc_backward(const bf16* qkv, const bf16* ctx, const bf16* dctx, bf
     SIMX_CUDA(cudaFuncSetAttribute(attn_bwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     attr = true;
   }
-  AttnTcParams p{mask, const_cast<float*>(lse2), ctx, dctx, B, S, H, heads, g_attn_timing};
+  AttnTcParams p{mask, const_cast<float*>(lse2), ctx, dctx, B, S, H, heads, g_attn_timing, dbias};
   attn_bwd_tc_kernel<<<dim3(heads, B), 256, smem, st>>>(p, mq, md, mo, mg);
   SIMX_LAUNCH_CHECK();
   return SIMX_OK;

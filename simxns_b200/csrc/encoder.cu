@@ -42,7 +42,7 @@ int attention_forward(int np, const bf16* qkv, long ps_qkv, bf16* ctx, long ps_c
                       int B, int S, int H, int heads, cudaStream_t st);
 int attention_backward(int np, const bf16* qkv, long ps_qkv, const bf16* ctx, const bf16* dctx, long ps_ctx, bf16* dqkv,
                        const int64_t* mask, const float* lse2, float* delta, int B, int S, int H, int heads,
-                       cudaStream_t st);
+                       float* dbias, cudaStream_t st);
 
 static inline size_t al(size_t x) { return (x + 255) & ~size_t(255); }
 
@@ -418,12 +418,12 @@ extern "C" int simx_encoder_backward(const simx_encoder_cfg* cfg, const float* c
     SIMX_TRY(gemm(H, I, T, dza, H, psH, true, a, I, psI, true, np, SIMX_EPI_ATOMIC_F32, nullptr, nullptr, 0, 0, nullptr,
                   nullptr, 0, 0, G(pi + 12), I, wgrad_ksplit(H, I, T), st));
     prof_label(nullptr);
-    // dh = (dz2 W2) o gelu'(pre-activation)   (the forward epilogue saved gelu' in the `h` slot)
+    // dh = (dz2 W2) o gelu'(pre-activation)   (the forward epilogue saved gelu' in the `h` slot); db1 = colsum(dh)
+    // comes out of the same epilogue (a separate column-sum pass only where the staged epilogue does not run)
     prof_label("ffn2_dgrad");
     SIMX_TRY(gemm(T, I, H, dza, H, psH, false, w2T, H, (long)I * H, false, np, SIMX_EPI_MUL, nullptr, h, I, psI, dh,
-                  nullptr, I, psI, nullptr, 0, 1, st));
+                  nullptr, I, psI, G(pi + 11), 0, 1, st));
     prof_label(nullptr);
-    SIMX_TRY(colsum(np, dh, T, I, I, psI, G(pi + 11), st));
     // dW1 [I,H] += dh^T x1
     prof_label("ffn1_wgrad");
     SIMX_TRY(gemm(I, H, T, dh, I, psI, true, x1, H, psH, true, np, SIMX_EPI_ATOMIC_F32, nullptr, nullptr, 0, 0, nullptr,
@@ -446,9 +446,9 @@ extern "C" int simx_encoder_backward(const simx_encoder_cfg* cfg, const float* c
     SIMX_TRY(gemm(T, H, H, dza, H, psH, false, woT, H, (long)H * H, false, np, SIMX_EPI_PLAIN, nullptr, nullptr, 0, 0, dxb,
                   nullptr, H, psH, nullptr, 0, 1, st));
     prof_label(nullptr);
-    SIMX_TRY(attention_backward(np, qkv, ps3H, ctx, dxb, psH, dqkv, mask, lse, delta, B, S, H, cfg->heads, st));
-    // fused q/k/v bias and weight gradients ([3H] and [3H,H] blocks of the flat gradient buffer)
-    SIMX_TRY(colsum(np, dqkv, T, 3 * H, 3 * H, ps3H, G(pi + 1), st));
+    // dqkv, and the fused q/k/v bias gradient (column sums of dqkv) from the same kernel
+    SIMX_TRY(attention_backward(np, qkv, ps3H, ctx, dxb, psH, dqkv, mask, lse, delta, B, S, H, cfg->heads, G(pi + 1), st));
+    // fused q/k/v weight gradient ([3H,H] block of the flat gradient buffer)
     prof_label("qkv_wgrad");
     SIMX_TRY(gemm(3 * H, H, T, dqkv, 3 * H, ps3H, true, x, H, psH, true, np, SIMX_EPI_ATOMIC_F32, nullptr, nullptr, 0, 0,
                   nullptr, nullptr, 0, 0, G(pi + 0), H, wgrad_ksplit(3 * H, H, T), st));

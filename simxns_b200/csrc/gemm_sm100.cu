@@ -37,6 +37,8 @@ struct GemmParams {
   const float* bias;
   float* outf;
   long ldof;
+  float* colsum;  // EPI_MUL, staged epilogue: [N] fp32, += column sums of the bf16 output (bias gradient of the layer
+                  // whose dgrad this GEMM computes), or NULL
 };
 
 // TS: the epilogue stages its bf16 output tile in shared memory and writes it with TMA (full 128-byte lines) instead
@@ -218,6 +220,15 @@ gemm_kernel(const GemmParams p, const __grid_constant__ CUtensorMap mapA, const 
     if (p.N <= (int)L::BIAS_FLOATS) {
       sbias = reinterpret_cast<float*>(smem + L::BIAS_OFF);
       for (int i = threadIdx.x; i < p.N; i += GEMM_THREADS) sbias[i] = p.bias[i];
+    }
+  }
+
+  // column sums of the output (fused bias gradient): per-CTA fp32 accumulator in the (otherwise unused) bias area
+  float* scol = nullptr;
+  if constexpr (EPI == SIMX_EPI_MUL && TS) {
+    if (p.colsum != nullptr) {
+      scol = reinterpret_cast<float*>(smem + L::BIAS_OFF);
+      for (int i = threadIdx.x; i < p.N; i += GEMM_THREADS) scol[i] = 0.f;
     }
   }
 
@@ -416,6 +427,25 @@ gemm_kernel(const GemmParams p, const __grid_constant__ CUtensorMap mapA, const 
           tma_store_3d(&mapOut, stg, col_base, row_base, 0);
           tma_store_commit();
         }
+        if constexpr (EPI == SIMX_EPI_MUL) {
+          if (scol != nullptr) {
+            // lane l sums columns 2l, 2l+1 of the staged [32 x 64] box (the bf16 values being stored): for a fixed
+            // row the 32 lanes read the 32 words of one swizzled 128-byte line — conflict-free
+            float s0 = 0.f, s1 = 0.f;
+            const uint32_t sb = smem_u32(stg) + ((lane & 3) << 2);
+#pragma unroll 8
+            for (int r = 0; r < 32; ++r) {
+              const float2 f = unpack_bf16x2(ld_shared_u32(sb + r * 128 + (((lane >> 2) ^ (r & 7)) << 4)));
+              s0 += f.x;
+              s1 += f.y;
+            }
+            const int col = col_base + 2 * lane;
+            if (col < p.N) {
+              atomicAdd(&scol[col], s0);
+              atomicAdd(&scol[col + 1], s1);
+            }
+          }
+        }
         if constexpr (EPI == SIMX_EPI_BIAS_GELU) {
           if (lane == 0) tma_store_wait_read<0>();
           __syncwarp();
@@ -432,6 +462,15 @@ gemm_kernel(const GemmParams p, const __grid_constant__ CUtensorMap mapA, const 
     }
     if constexpr (TS) {
       if (lane == 0) tma_store_wait_all<0>();  // smem must outlive the last bulk store
+    }
+    if constexpr (EPI == SIMX_EPI_MUL && TS) {
+      if (scol != nullptr) {
+        named_bar_sync(1, GEMM_THREADS - 128);  // the 16 epilogue warps: every shared-memory atomic has landed
+        for (int i = threadIdx.x - 128; i < p.N; i += GEMM_THREADS - 128) {
+          const float v = scol[i];
+          if (v != 0.f) atomicAdd(p.colsum + i, v);
+        }
+      }
     }
   }
 
@@ -573,10 +612,10 @@ static int dispatch_epi(int epi, const GemmParams& p, const bf16* A, long lda, l
   }
 }
 
-// Internal entry used by the encoder and by simx_gemm().
-int gemm(int M, int N, int K, const bf16* A, long lda, long a_ps, bool a_mn, const bf16* B, long ldb, long b_ps,
-         bool b_mn, int planes, int epi, const float* bias, const bf16* aux, long ldaux, long aux_ps, bf16* out,
-         bf16* out2, long ldo, long out_ps, float* outf, long ldof, int ksplit, cudaStream_t stream) {
+static int gemm_launch(int M, int N, int K, const bf16* A, long lda, long a_ps, bool a_mn, const bf16* B, long ldb, long b_ps,
+                       bool b_mn, int planes, int epi, const float* bias, const bf16* aux, long ldaux, long aux_ps,
+                       bf16* out, bf16* out2, long ldo, long out_ps, float* outf, long ldof, int ksplit,
+                       bool* colsum_fused, cudaStream_t stream) {
   SIMX_CHECK(M > 0 && N > 0 && K > 0, SIMX_ERR_INVALID, "gemm: empty problem %dx%dx%d", M, N, K);
   SIMX_CHECK(N % 8 == 0, SIMX_ERR_INVALID, "gemm: N=%d must be a multiple of 8", N);
   SIMX_CHECK(a_mn == b_mn, SIMX_ERR_INVALID, "gemm: mixed operand majors are not instantiated");
@@ -622,6 +661,13 @@ int gemm(int M, int N, int K, const bf16* A, long lda, long a_ps, bool a_mn, con
   p.out = out; p.out2 = out2; p.out_ps = out_ps; p.ldo = ldo;
   p.aux = aux; p.aux_ps = aux_ps; p.ldaux = ldaux;
   p.bias = bias; p.outf = outf; p.ldof = ldof;
+  // EPI_MUL + outf: outf[N] += column sums of the output.  Fused into the staged epilogue when that instantiation runs
+  // (BN 256, one plane, N fits the smem accumulator); otherwise the column-sum kernel runs over `out` afterwards.
+  p.colsum = nullptr;
+  const bool want_colsum = epi == SIMX_EPI_MUL && outf != nullptr;
+  const bool fuse_colsum = want_colsum && BN == 256 && planes == 1 && !a_mn && N <= 3072;
+  if (fuse_colsum) p.colsum = outf;
+  *colsum_fused = fuse_colsum;
 
   ProfScope prof(a_mn ? "gemm_mn" : "gemm_kk", 2.0 * M * N * (double)K * p.npass,
                  2.0 * planes * ((double)M * K + (double)N * K) + (epi == SIMX_EPI_ATOMIC_F32 ? 4.0 : 2.0 * planes) * M * N, stream);
@@ -640,6 +686,20 @@ int gemm(int M, int N, int K, const bf16* A, long lda, long a_ps, bool a_mn, con
   SIMX_GEMM_DISPATCH(64)
 #undef SIMX_GEMM_DISPATCH
   SIMX_FAIL(SIMX_ERR_INVALID, "gemm: no tile configuration");
+}
+
+int colsum(int np, const bf16* x, long rows, int N, long row_stride, long ps, float* out, cudaStream_t st);
+
+// Internal entry used by the encoder and by simx_gemm(): the GEMM, plus the column-sum pass when the EPI_MUL bias
+// gradient could not ride in the epilogue.
+int gemm(int M, int N, int K, const bf16* A, long lda, long a_ps, bool a_mn, const bf16* B, long ldb, long b_ps,
+         bool b_mn, int planes, int epi, const float* bias, const bf16* aux, long ldaux, long aux_ps, bf16* out,
+         bf16* out2, long ldo, long out_ps, float* outf, long ldof, int ksplit, cudaStream_t stream) {
+  bool fused = false;
+  SIMX_TRY(gemm_launch(M, N, K, A, lda, a_ps, a_mn, B, ldb, b_ps, b_mn, planes, epi, bias, aux, ldaux, aux_ps, out, out2,
+                       ldo, out_ps, outf, ldof, ksplit, &fused, stream));
+  if (epi == SIMX_EPI_MUL && outf != nullptr && !fused) SIMX_TRY(colsum(planes, out, M, N, ldo, out_ps, outf, stream));
+  return SIMX_OK;
 }
 
 }  // namespace simx

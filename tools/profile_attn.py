@@ -33,7 +33,7 @@ def main():
 
     def bwd():
         _lib.check(lib.simx_attention_backward(qkv.data_ptr(), ctx.data_ptr(), dctx.data_ptr(), dqkv.data_ptr(), None,
-                                               lse.data_ptr(), delta.data_ptr(), a.B, a.S, H, heads, 1, 0, 0, st), "bwd")
+                                               lse.data_ptr(), delta.data_ptr(), a.B, a.S, H, heads, 1, 0, 0, None, st), "bwd")
 
     import ctypes
     tbuf = torch.zeros(8, dtype=torch.int64, device="cuda")
