@@ -127,6 +127,10 @@ int simx_encoder_backward(const simx_encoder_cfg* cfg, const float* const* param
                                     reward_bj = log(sigmoid(t_b0 - t_bj) + eps) on the raw teacher logits
                                     (SimANS/wiki/co_training_wiki_train.py:212-225); a SUM, not a batch mean */
 
+#define SIMX_LOSS_MSE_LOCAL 64   /* a-6  PROD KD_logit: 0.5 * mean_{b,j} (s - t)^2 on the raw logits (models.py:778-780) */
+#define SIMX_LOSS_DKD_LOCAL 128  /* a-6  PROD DKD: T^2/B * sum_b [alpha TCKD + beta NCKD], target = column 0
+                                    (PROD/ProD_KD/model/models.py:783-812) */
+
 typedef struct simx_loss_cfg {
   int32_t terms;        /* OR of SIMX_LOSS_* */
   int32_t GQ, GC, H;    /* global query / passage counts, embedding width */
@@ -139,12 +143,14 @@ typedef struct simx_loss_cfg {
   float score_scale;    /* multiplies student local scores (1 or 1/sqrt(H) with --scale_simmila) */
   float grad_scale;     /* multiplies every gradient and nothing else (loss / gradient_accumulation_steps) */
   float w_adv_local;    /* weight of SIMX_LOSS_ADV_LOCAL (adv_lambda) */
+  float w_mse_local, w_dkd_local; /* weights of SIMX_LOSS_MSE_LOCAL / SIMX_LOSS_DKD_LOCAL */
+  float dkd_alpha, dkd_beta;      /* args.DKD_alpha / args.DKD_beta */
 } simx_loss_cfg;
 
 /*   Q [GQ,H], C [GC,H] fp32 gathered embeddings; pos_idx [GQ] int32 positive column of each global query
  *   (NLL_GLOBAL); teacher [q_count, group] fp32 teacher logits (KL/CE/KD terms), or NULL.
- *   out_losses[8] fp32: {total, nll_global, kl_local, ce_local, kd_local, nll_local, n_correct_global,
- *                       n_correct_local (local rows whose column 0 has the largest score)}
+ *   out_losses[12] fp32: {total, nll_global, kl_local, ce_local, kd_local, nll_local, n_correct_global,
+ *                       n_correct_local (local rows whose column 0 has the largest score), mse_local, dkd_local, 0, 0}
  *   dQ [q_count,H], dC [c_count,H] fp32 gradients of `total * grad_scale` w.r.t. the local embeddings.
  *   workspace: simx_score_loss_workspace_bytes(cfg). */
 size_t simx_score_loss_workspace_bytes(const simx_loss_cfg* cfg);
@@ -156,7 +162,7 @@ int simx_score_loss(const simx_loss_cfg* cfg, const float* Q, const float* C, co
  * selected layer pair on the per-layer [CLS] rows, layer_score_dis_loss (LEAD/util.py:539-559):
  *   total = w_nll_a NLL(A) + w_nll_b NLL(B) + w_kl_b2a KL(softmax(B/T) || softmax(A)) + w_kl_a2b KL(softmax(A/T) || softmax(B))
  * KL is `batchmean` over GQ rows; targets are NOT detached (as in the reference): both matrices receive gradients from
- * every term.  out_losses[8] = {total, nll_a, nll_b, kl_b2a, kl_a2b, kd_b2a, n_correct_a, 0}.  dQb/dCb may be NULL (frozen teacher).
+ * every term.  out_losses[8] = {total, nll_a, nll_b, kl_b2a, kl_a2b, kd_b2a, n_correct_a, mse_b2a + dkd_b2a}.  dQb/dCb may be NULL (frozen teacher).
  * Local row/column ranges as in simx_loss_cfg; gathered embeddings fp32. */
 typedef struct simx_pair_cfg {
   int32_t GQ, GC, H;
@@ -166,6 +172,10 @@ typedef struct simx_pair_cfg {
   float grad_scale;
   float w_kd_b2a; /* PROD BiEncoderKDLoss KD_softmax on the global matrix: T^2 KL(softmax(B/T) || softmax(A/T))
                      (PROD/ProD_KD/model/models.py:971-1059) */
+  float w_mse_b2a; /* PROD KD_logit on the global matrix: 0.5 mean (A - B)^2                 (models.py:1057-1059) */
+  float w_dkd_b2a; /* PROD DKD on the global matrix, target = pos_idx, with dkd_alpha / dkd_beta (models.py:1070-1094).
+                      B is a constant for these two terms (PROD runs its teacher under no_grad): no dQb / dCb share. */
+  float dkd_alpha, dkd_beta;
 } simx_pair_cfg;
 size_t simx_pair_distill_workspace_bytes(int GQ, int GC, int H);
 int simx_pair_distill(const simx_pair_cfg* cfg, const float* Qa, const float* Ca, const float* Qb, const float* Cb,
@@ -178,6 +188,10 @@ int simx_pair_distill(const simx_pair_cfg* cfg, const float* Qa, const float* Ca
  * d(total)/d(teacher logits) or NULL. */
 int simx_local_pair_distill(const simx_pair_cfg* cfg, const float* Q_local, const float* C_local,
                             const float* teacher_logits, float* out_losses, float* dQ, float* dC, float* dT, void* stream);
+
+/* One half of PROD's Bi_logit (BiEncoderKDLoss.bi_logit, PROD/ProD_KD/model/models.py:1062-1067) on raw embeddings:
+ * *loss += weight * 0.5 * mean((a - b)^2) and grad[i] = weight * (a[i] - b[i]) / n   (a, b, grad: n fp32 elements). */
+int simx_embed_mse(const float* a, const float* b, int64_t n, float weight, float* loss, float* grad, void* stream);
 
 /* SimANS ambiguous-negative sampling (SimANS/utils/MARCO_until_new.py:165-202, SimANS/utils/util_wiki.py:613-639):
  * for each of NQ queries choose k of its first n_valid[q] (<= NC <= 1024) candidates, without duplicates, with probability
@@ -220,7 +234,7 @@ int simx_clip_grads(const simx_opt_tensor* tensors_dev, int n, int total_chunks,
                     float max_norm, void* stream);
 /* One AdamW step (`step` counts from 1).  sq_norm_dev != NULL: the gradient is clipped on the fly by the coefficient
  * above (no host round trip, no extra pass); write_clipped_grads stores the clipped gradient back as well. */
-int simx_adamw_step(const simx_opt_tensor* tensors_dev, int n, int total_chunks, int mode, float beta1, float beta2,
+int simx_adamw_step(const simx_opt_tensor* tensors_dev, int n, int total_chunks, int mode, double beta1, double beta2,
                     float eps, int step, int correct_bias, const double* sq_norm_dev, float max_norm,
                     int write_clipped_grads, void* stream);
 

@@ -12,6 +12,9 @@ float64 numpy restatement, with closed-form gradients, of the score/loss tail of
                                                 PROD `prob_loss` /root/reference/PROD/ProD_KD/model/models.py:735-740
   kd_local   : CrossBERTKDLoss.kd_loss KD_softmax /root/reference/PROD/ProD_KD/model/models.py:772-777
   nll_local  : CrossBERTKDLoss hard loss (positive = column 0)  .../models.py:694-712
+  mse_local / mse_b2a : kd_loss KD_logit, 0.5 MSELoss(mean)(s, t)   .../models.py:778-780, 1057-1059
+  dkd_local / dkd_b2a : dkd_loss (decoupled KD: alpha TCKD + beta NCKD)  .../models.py:783-812, 1070-1094
+  embed_mse  : BiEncoderKDLoss.bi_logit, 0.5 MSE(q_s, q_t) + 0.5 MSE(c_s, c_t)   .../models.py:1062-1067
 
 Pinned against the reference's own code by oracle/make_golden.py -> tests/golden/loss_*.npz.
 """
@@ -25,8 +28,43 @@ def _log_softmax(x):
     return x - m - np.log(np.exp(x - m).sum(-1, keepdims=True))
 
 
+def mse_logits(S, Tt):
+    """kd_loss(KD_logit): 0.5 * MSELoss(reduction='mean')(S, Tt).  -> (loss, dS)"""
+    d = S - Tt
+    return 0.5 * (d * d).mean(), d / d.size
+
+
+def dkd(S, Tt, pos, alpha, beta, T):
+    """dkd_loss (PROD/ProD_KD/model/models.py:1070-1094): with ps = softmax(S/T), pt = softmax(Tt/T), the binary
+    (target, others) KL `TCKD` plus the KL between the distributions renormalised over the non-target columns `NCKD`
+    (the reference gets the latter by subtracting 1000 from the target logit: exp(-1000) is exactly 0 in fp32), both
+    summed over rows, times T^2 / rows.  -> (alpha TCKD + beta NCKD, dS)"""
+    n = S.shape[0]
+    rows = np.arange(n)
+    ps, pt = np.exp(_log_softmax(S / T)), np.exp(_log_softmax(Tt / T))
+    gt = np.zeros_like(S, bool)
+    gt[rows, pos] = True
+    ps_t, pt_t = ps[gt], pt[gt]
+    ps_o, pt_o = (ps * ~gt).sum(1), (pt * ~gt).sum(1)
+    with np.errstate(divide="ignore", invalid="ignore"):
+        tck = np.where(pt_t > 0, pt_t * (np.log(pt_t) - np.log(ps_t)), 0.0) + \
+              np.where(pt_o > 0, pt_o * (np.log(pt_o) - np.log(ps_o)), 0.0)
+        ps2, pt2 = ps / ps_o[:, None], pt / pt_o[:, None]
+        nck = np.where(~gt & (pt2 > 0), pt2 * (np.log(pt2) - np.log(ps2)), 0.0).sum(1)
+    loss = (alpha * tck.sum() + beta * nck.sum()) * T * T / n
+    g_t = np.where(gt, (ps_t - pt_t)[:, None], ps * (pt_t - pt_o * ps_t / ps_o)[:, None])
+    g_n = np.where(gt, 0.0, ps2 - pt2)
+    return loss, (alpha * g_t + beta * g_n) * T / n
+
+
+def embed_mse(a, b):
+    """0.5 * MSELoss(mean)(a, b) on raw embeddings (one half of bi_logit).  -> (loss, d/da)"""
+    d = np.asarray(a, np.float64) - np.asarray(b, np.float64)
+    return 0.5 * (d * d).mean(), d / d.size
+
+
 def score_loss(Q, C, *, terms, q_begin=0, q_count=None, c_begin=0, group=1, pos_idx=None, teacher=None,
-               w=None, temperature=1.0, eps=1e-7, score_scale=1.0, grad_scale=1.0):
+               w=None, temperature=1.0, eps=1e-7, score_scale=1.0, grad_scale=1.0, dkd_alpha=1.0, dkd_beta=1.0):
     """Returns (losses dict, dQ_local [q_count,H], dC_local [q_count*group,H]).
 
     terms: iterable of {'nll_global','kl_local','ce_local','kd_local','nll_local'}; w: dict term -> weight (default 1).
@@ -59,7 +97,7 @@ def score_loss(Q, C, *, terms, q_begin=0, q_count=None, c_begin=0, group=1, pos_
         dQ += dS[q_begin:q_begin + q_count] @ C
         dC += dS[:, c_begin:c_begin + c_count].T @ Q
 
-    local_terms = terms & {"kl_local", "ce_local", "kd_local", "nll_local", "adv_local"}
+    local_terms = terms & {"kl_local", "ce_local", "kd_local", "nll_local", "adv_local", "mse_local", "dkd_local"}
     if local_terms:
         Ql = Q[q_begin:q_begin + q_count]
         Cl = C[c_begin:c_begin + c_count].reshape(q_count, group, H)
@@ -106,6 +144,16 @@ def score_loss(Q, C, *, terms, q_begin=0, q_count=None, c_begin=0, group=1, pos_
             out["total"] += w.get("adv_local", 1.0) * loss
             rho = reward * p / (p + eps)
             ds += w.get("adv_local", 1.0) * (rho - p * rho.sum(-1, keepdims=True))
+        if "mse_local" in terms:
+            loss, g = mse_logits(s, np.asarray(teacher, np.float64))
+            out["mse_local"] = loss
+            out["total"] += w.get("mse_local", 1.0) * loss
+            ds += w.get("mse_local", 1.0) * g
+        if "dkd_local" in terms:
+            loss, g = dkd(s, np.asarray(teacher, np.float64), np.zeros(B, np.int64), dkd_alpha, dkd_beta, temperature)
+            out["dkd_local"] = loss
+            out["total"] += w.get("dkd_local", 1.0) * loss
+            ds += w.get("dkd_local", 1.0) * g
         if "nll_local" in terms:
             loss = -lsm[:, 0].mean()
             out["nll_local"] = loss
@@ -121,11 +169,14 @@ def score_loss(Q, C, *, terms, q_begin=0, q_count=None, c_begin=0, group=1, pos_
 
 
 def pair_distill(Qa, Ca, Qb, Cb, *, pos_idx, w_nll_a=0.0, w_nll_b=0.0, w_kl_b2a=0.0, w_kl_a2b=0.0, w_kd_b2a=0.0,
-                 temperature=1.0, q_begin=0, q_count=None, c_begin=0, c_count=None, grad_scale=1.0):
+                 temperature=1.0, q_begin=0, q_count=None, c_begin=0, c_count=None, grad_scale=1.0, w_mse_b2a=0.0,
+                 w_dkd_b2a=0.0, dkd_alpha=1.0, dkd_beta=1.0):
     """LEAD mutual distillation between a student (a) and a teacher (b) dual encoder on the global score matrices
     (/root/reference/LEAD/util.py:594-644 scores, :737-760 assembly; no .detach(): targets carry gradient).
       total = w_nll_a NLL(A) + w_nll_b NLL(B) + w_kl_b2a KL(softmax(B/T)||softmax(A)) + w_kl_a2b KL(softmax(A/T)||softmax(B))
               + w_kd_b2a T^2 KL(softmax(B/T)||softmax(A/T))      (PROD BiEncoderKDLoss KD_softmax, models.py:1050-1056)
+              + w_mse_b2a 0.5 MSE(A, B) + w_dkd_b2a DKD(A | B)   (PROD KD_logit / DKD; their teacher is run under
+                no_grad, PROD/ProD_KD/run_progressive_distill_marco.py: B is a constant for these two terms)
     Returns (losses dict, dQa, dCa, dQb, dCb) restricted to the local row / column ranges."""
     Qa, Ca, Qb, Cb = (np.asarray(x, np.float64) for x in (Qa, Ca, Qb, Cb))
     GQ, GC = Qa.shape[0], Ca.shape[0]
@@ -152,9 +203,16 @@ def pair_distill(Qa, Ca, Qb, Cb, *, pos_idx, w_nll_a=0.0, w_nll_b=0.0, w_kl_b2a=
           + w_kd_b2a * T * (ta - tb)) / GQ
     dB = (w_nll_b * (pb - oh) + w_kl_a2b * (pb - ta) + w_kl_b2a / T * tb * ((ltb - lsa) - k_b2a_row[:, None])
           + w_kd_b2a * T * tb * ((ltb - lta) - k_kd_row[:, None])) / GQ
+    mse_b2a = dkd_b2a = 0.0
+    if w_mse_b2a:
+        mse_b2a, g = mse_logits(A, B)
+        total, dA = total + w_mse_b2a * mse_b2a, dA + w_mse_b2a * g
+    if w_dkd_b2a:
+        dkd_b2a, g = dkd(A, B, pos, dkd_alpha, dkd_beta, T)
+        total, dA = total + w_dkd_b2a * dkd_b2a, dA + w_dkd_b2a * g
     qs, cs = slice(q_begin, q_begin + q_count), slice(c_begin, c_begin + c_count)
     out = dict(total=total, nll_a=nll_a, nll_b=nll_b, kl_b2a=kl_b2a, kl_a2b=kl_a2b, kd_b2a=kd_b2a,
-               n_correct=float((A.argmax(1) == pos).sum()))
+               n_correct=float((A.argmax(1) == pos).sum()), mse_b2a=mse_b2a, dkd_b2a=dkd_b2a)
     g = grad_scale
     return out, g * dA[qs] @ Ca, g * dA[:, cs].T @ Qa, g * dB[qs] @ Cb, g * dB[:, cs].T @ Qb
 

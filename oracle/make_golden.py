@@ -242,6 +242,51 @@ def golden_losses(simans, prod):
     print("losses", {k: float(v[0]) for k, v in res.items() if k.endswith("loss")})
 
 
+def golden_losses_prod_kd(prod):
+    """the remaining KD_type branches of PROD's loss classes (PROD/ProD_KD/model/models.py:669-781, 970-1094):
+    CrossBERTKDLoss {KD_logit, DKD, KD_softmax + LwF, KD_logit + LwF} and BiEncoderKDLoss {KD_logit, DKD, Bi_logit}"""
+    rng = np.random.RandomState(11)
+    GQ, group, H = 6, 4, 32
+    Q = rng.standard_normal((GQ, H)).astype(np.float32)
+    Cm = rng.standard_normal((GQ * group, H)).astype(np.float32)
+    Qo = (Q + 0.3 * rng.standard_normal((GQ, H))).astype(np.float32)   # the frozen initial student of LwF
+    Co = (Cm + 0.3 * rng.standard_normal((GQ * group, H))).astype(np.float32)
+    Qt = rng.standard_normal((GQ, H)).astype(np.float32)
+    Ct = rng.standard_normal((GQ * group, H)).astype(np.float32)
+    teacher = (3 * rng.standard_normal((GQ, group))).astype(np.float32)
+    pos = [i * group for i in range(GQ)]
+    res = dict(Q=Q, C=Cm, Qo=Qo, Co=Co, Qt=Qt, Ct=Ct, teacher=teacher, group=np.array([group]), pos=np.array(pos),
+               hyper=np.array([0.1, 0.9, 4.0, 1.0, 1.0, 8.0]))  # CE_W, KD_W, T, LwF_W, DKD_alpha, DKD_beta
+    args = types.SimpleNamespace(KD_type="KD_logit", TEMPERATURE=4.0, CE_WEIGHT=0.1, KD_WEIGHT=0.9, LwF_WEIGHT=1.0,
+                                 DKD_alpha=1.0, DKD_beta=8.0)
+
+    def fresh():
+        return torch.from_numpy(Q.copy()).requires_grad_(True), torch.from_numpy(Cm.copy()).requires_grad_(True)
+
+    def put(tag, loss, correct, q, c):
+        loss.backward()
+        res.update({tag + "_loss": np.array([loss.item()]), tag + "_correct": np.array([int(correct)]),
+                    tag + "_dQ": q.grad.numpy().copy(), tag + "_dC": c.grad.numpy().copy()})
+
+    for kd in ("KD_logit", "DKD"):
+        args.KD_type = kd
+        q, c = fresh()
+        put("cross_" + kd, *prod.CrossBERTKDLoss().calc(args, q, c, torch.from_numpy(teacher)), q, c)
+        q, c = fresh()
+        put("bi_" + kd, *prod.BiEncoderKDLoss().calc(args, q, c, torch.from_numpy(Qt), torch.from_numpy(Ct), pos), q, c)
+    for kd in ("KD_softmax", "KD_logit"):
+        args.KD_type = kd
+        q, c = fresh()
+        put("lwf_" + kd, *prod.CrossBERTKDLoss().calc(args, q, c, torch.from_numpy(teacher), LwF=True,
+                                                     ori_q_vector=torch.from_numpy(Qo), ori_ctx_vectors=torch.from_numpy(Co)),
+            q, c)
+    args.KD_type = "Bi_logit"
+    q, c = fresh()
+    put("bi_Bi_logit", *prod.BiEncoderKDLoss().calc(args, q, c, torch.from_numpy(Qt), torch.from_numpy(Ct), pos), q, c)
+    np.savez_compressed(GOLD / "losses_prod_kd.npz", **res)
+    print("losses_prod_kd", {k: float(v[0]) for k, v in res.items() if k.endswith("loss")})
+
+
 def lead_shim():
     """make LEAD's vendored HF-4.x modeling files importable under transformers 5"""
     import transformers
@@ -356,6 +401,9 @@ def main():
         GOLD.mkdir(parents=True, exist_ok=True)
         golden_lead_distill()
         return
+    if only == ["prod_kd"]:
+        golden_losses_prod_kd(import_from(REF / "PROD" / "ProD_KD", "model.models"))
+        return
     torch.manual_seed(0)
     torch.set_num_threads(os.cpu_count() or 1)
     GOLD.mkdir(parents=True, exist_ok=True)
@@ -365,6 +413,7 @@ def main():
     prod = import_from(REF / "PROD" / "ProD_KD", "model.models")
     simans = import_from(REF / "SimANS", "model.models")
     golden_losses(simans, prod)
+    golden_losses_prod_kd(prod)
     golden_lead_distilbert()
     if "lead" in only or not only:
         golden_lead_distill()

@@ -21,6 +21,7 @@ PREC_BF16, PREC_BF16X3 = 1, 3
 EPI_PLAIN, EPI_BIAS, EPI_BIAS_GELU, EPI_BIAS_ADD, EPI_MUL, EPI_ADD, EPI_ATOMIC_F32 = range(7)
 
 LOSS_NLL_GLOBAL, LOSS_KL_LOCAL, LOSS_CE_LOCAL, LOSS_KD_LOCAL, LOSS_NLL_LOCAL, LOSS_ADV_LOCAL = 1, 2, 4, 8, 16, 32
+LOSS_MSE_LOCAL, LOSS_DKD_LOCAL = 64, 128
 
 
 class EncoderCfg(C.Structure):
@@ -63,6 +64,10 @@ class LossCfg(C.Structure):
         ("score_scale", C.c_float),
         ("grad_scale", C.c_float),
         ("w_adv_local", C.c_float),
+        ("w_mse_local", C.c_float),
+        ("w_dkd_local", C.c_float),
+        ("dkd_alpha", C.c_float),
+        ("dkd_beta", C.c_float),
     ]
 
 
@@ -70,7 +75,8 @@ class PairCfg(C.Structure):
     """mirror of `simx_pair_cfg`"""
 
     _fields_ = [(n, C.c_int32) for n in ("GQ", "GC", "H", "q_begin", "q_count", "c_begin", "c_count")] + \
-               [(n, C.c_float) for n in ("w_nll_a", "w_nll_b", "w_kl_b2a", "w_kl_a2b", "temperature", "grad_scale", "w_kd_b2a")]
+               [(n, C.c_float) for n in ("w_nll_a", "w_nll_b", "w_kl_b2a", "w_kl_a2b", "temperature", "grad_scale", "w_kd_b2a",
+                                    "w_mse_b2a", "w_dkd_b2a", "dkd_alpha", "dkd_beta")]
 
 
 _P = C.c_void_p
@@ -101,6 +107,7 @@ SIGNATURES = {
     "simx_pair_distill_workspace_bytes": (C.c_size_t, [_I, _I, _I]),
     "simx_pair_distill": (_I, [C.POINTER(PairCfg), _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
     "simx_local_pair_distill": (_I, [C.POINTER(PairCfg), _P, _P, _P, _P, _P, _P, _P, _P]),
+    "simx_embed_mse": (_I, [_P, _P, _L, C.c_float, _P, _P, _P]),
     "simx_simans_sample": (_I, [_P, _P, _P, _I, _I, _I, _I, C.c_float, C.c_float, C.c_uint64, _P, _P]),
     "simx_attention_forward": (_I, [_P, _P, _P, _P, _I, _I, _I, _I, _I, _L, _L, _P]),
     "simx_attention_backward": (_I, [_P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _L, _L, _P, _P]),
@@ -125,7 +132,7 @@ SIGNATURES.update({
     "simx_opt_plan": (_I, [C.POINTER(OptTensor), _I]),
     "simx_grad_sq_norm": (_I, [_P, _I, _I, _P, _P]),
     "simx_clip_grads": (_I, [_P, _I, _I, _P, C.c_float, _P]),
-    "simx_adamw_step": (_I, [_P, _I, _I, _I, C.c_float, C.c_float, C.c_float, _I, _I, _P, C.c_float, _I, _P]),
+    "simx_adamw_step": (_I, [_P, _I, _I, _I, C.c_double, C.c_double, C.c_float, _I, _I, _P, C.c_float, _I, _P]),
 })
 
 

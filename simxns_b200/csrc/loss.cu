@@ -88,6 +88,32 @@ local_loss_kernel(const simx_loss_cfg cfg, const float* __restrict__ Q, const fl
     }
   }
   if (cfg.terms & SIMX_LOSS_NLL_LOCAL) l_nll = -(ds[0] - lse);
+  // PROD KD_logit (0.5 MSE on raw logits) and DKD (decoupled KD at temperature T, target = column 0):
+  //   TCKD = KL((pt_t, pt_o) || (ps_t, ps_o)),  NCKD = KL(pt / pt_o || ps / ps_o) over the non-target columns
+  const bool want_mse = (cfg.terms & SIMX_LOSS_MSE_LOCAL) != 0 && teacher != nullptr;
+  const bool want_dkd = (cfg.terms & SIMX_LOSS_DKD_LOCAL) != 0 && teacher != nullptr && G > 1;
+  float l_mse = 0.f, l_dkd = 0.f, ps_t = 0.f, pt_t = 0.f, ps_o = 0.f, pt_o = 0.f;
+  if (want_mse)
+    for (int j = 0; j < G; ++j) {
+      const float d = ds[j] - teacher[(long)i * G + j];
+      l_mse += 0.5f * d * d;
+    }
+  if (want_dkd) {
+    ps_t = expf(ds[0] / T - lseT);
+    pt_t = expf(teacher[(long)i * G] / T - tlse);
+    for (int j = 1; j < G; ++j) {
+      ps_o += expf(ds[j] / T - lseT);
+      pt_o += expf(teacher[(long)i * G + j] / T - tlse);
+    }
+    float tck = (pt_t > 0.f ? pt_t * (logf(pt_t) - logf(ps_t)) : 0.f) + (pt_o > 0.f ? pt_o * (logf(pt_o) - logf(ps_o)) : 0.f);
+    float nck = 0.f;
+    for (int j = 1; j < G; ++j) {
+      const float ltj = teacher[(long)i * G + j] / T - tlse, lsj = ds[j] / T - lseT;
+      const float t2 = expf(ltj) / pt_o;
+      if (t2 > 0.f) nck += t2 * ((ltj - logf(pt_o)) - (lsj - logf(ps_o)));
+    }
+    l_dkd = cfg.dkd_alpha * tck + cfg.dkd_beta * nck;
+  }
   const float w_klce = ((cfg.terms & SIMX_LOSS_KL_LOCAL) ? cfg.w_kl_local : 0.f) +
                        ((cfg.terms & SIMX_LOSS_CE_LOCAL) ? cfg.w_ce_local : 0.f);
   __syncwarp();
@@ -106,6 +132,13 @@ local_loss_kernel(const simx_loss_cfg cfg, const float* __restrict__ Q, const fl
       }
     }
     if (cfg.terms & SIMX_LOSS_NLL_LOCAL) g += cfg.w_nll_local * invB * (p - (j == 0 ? 1.f : 0.f));
+    if (want_mse) g += cfg.w_mse_local * (s - teacher[(long)i * G + j]) * invB / G;
+    if (want_dkd) {
+      const float psj = expf(s / T - lseT), ptj = expf(teacher[(long)i * G + j] / T - tlse);
+      const float g_t = j == 0 ? ps_t - pt_t : psj * (pt_t - pt_o * ps_t / ps_o);
+      const float g_n = j == 0 ? 0.f : psj / ps_o - ptj / pt_o;
+      g += cfg.w_dkd_local * (T * invB) * (cfg.dkd_alpha * g_t + cfg.dkd_beta * g_n);
+    }
     ds[j] = g * cfg.score_scale * cfg.grad_scale;
   }
   __syncwarp();
@@ -122,6 +155,14 @@ local_loss_kernel(const simx_loss_cfg cfg, const float* __restrict__ Q, const fl
     if (cfg.terms & SIMX_LOSS_KD_LOCAL) tot += cfg.w_kd_local * l_kd * invB * T2;
     if (cfg.terms & SIMX_LOSS_NLL_LOCAL) tot += cfg.w_nll_local * l_nll * invB;
     if (want_adv) tot += cfg.w_adv_local * l_adv;
+    if (want_mse) {
+      atomicAdd(out_losses + 8, l_mse * invB / G);
+      tot += cfg.w_mse_local * l_mse * invB / G;
+    }
+    if (want_dkd) {
+      atomicAdd(out_losses + 9, l_dkd * invB * T2);
+      tot += cfg.w_dkd_local * l_dkd * invB * T2;
+    }
     atomicAdd(out_losses + 0, tot);
   }
   // gradients: dQ_i = sum_j ds_j c_ij ; dC_ij = ds_j q_i      (this warp is the only writer of these rows)
@@ -235,6 +276,7 @@ static LossWs loss_ws(const simx_loss_cfg* c) {
 // ------------------------------------------------------------------------------------------------
 struct PairW {
   float nll_a, nll_b, kl_b2a, kl_a2b, T, grad_scale, kd_b2a;
+  float mse_b2a, dkd_b2a, alpha, beta;
 };
 
 __device__ __forceinline__ void block_lse(const float* s, int n, float invT, float* sh, float& lse_out) {
@@ -304,8 +346,41 @@ pair_row_kernel(const float* __restrict__ A, const float* __restrict__ B, int GQ
   k_a2b = block_sum(k_a2b, sh);
   k_kd = block_sum(k_kd, sh);
   const int pos = pos_idx[row];
+  // PROD KD_logit / DKD on the global row (B is a constant for these: no share of gb)
+  float r_mse = 0.f, ps_t = 0.f, pt_t = 0.f, ps_o = 1.f, pt_o = 1.f, l_dkd = 0.f;
+  if (w.mse_b2a != 0.f) {
+    for (int c = threadIdx.x; c < GC; c += 256) {
+      const float d = a[c] - b[c];
+      r_mse += 0.5f * d * d;
+    }
+    r_mse = block_sum(r_mse, sh);
+  }
+  if (w.dkd_b2a != 0.f) {
+    float so = 0.f, to = 0.f, kx = 0.f;
+    for (int c = threadIdx.x; c < GC; c += 256) {
+      if (c == pos) continue;
+      const float lta = a[c] * invT - lse_aT, ltb = b[c] * invT - lse_bT;
+      const float tb = __expf(ltb);
+      so += __expf(lta);
+      to += tb;
+      kx += tb * (ltb - lta);
+    }
+    ps_o = block_sum(so, sh);
+    pt_o = block_sum(to, sh);
+    kx = block_sum(kx, sh);
+    ps_t = __expf(a[pos] * invT - lse_aT);
+    pt_t = __expf(b[pos] * invT - lse_bT);
+    const float tck = (pt_t > 0.f ? pt_t * (logf(pt_t) - logf(ps_t)) : 0.f) + (pt_o > 0.f ? pt_o * (logf(pt_o) - logf(ps_o)) : 0.f);
+    const float nck = pt_o > 0.f ? kx / pt_o - logf(pt_o) + logf(ps_o) : 0.f;
+    l_dkd = w.alpha * tck + w.beta * nck;
+  }
   if (threadIdx.x == 0) {
     const float na = lse_a - a[pos], nb = lse_b - b[pos], r = 1.f / GQ;
+    if (w.mse_b2a != 0.f || w.dkd_b2a != 0.f) {
+      const float mse = r_mse * r / GC, dk = l_dkd * w.T * w.T * r;
+      atomicAdd(out_losses + 7, (w.mse_b2a != 0.f ? mse : 0.f) + (w.dkd_b2a != 0.f ? dk : 0.f));
+      atomicAdd(out_losses + 0, w.mse_b2a * mse + w.dkd_b2a * dk);
+    }
     atomicAdd(out_losses + 1, na * r);
     atomicAdd(out_losses + 2, nb * r);
     atomicAdd(out_losses + 3, k_b2a * r);
@@ -342,8 +417,14 @@ pair_row_kernel(const float* __restrict__ A, const float* __restrict__ B, int GQ
     const float lsa = a[c] - lse_a, lsb = b[c] - lse_b;
     const float pa = __expf(lsa), pb = __expf(lsb), ta = __expf(lta), tb = __expf(ltb);
     const float oh = c == pos ? 1.f : 0.f;
-    const float ga = r * (w.nll_a * (pa - oh) + w.kl_b2a * (pa - tb) + w.kl_a2b * invT * ta * ((lta - lsb) - k_a2b) +
-                          w.kd_b2a * w.T * (ta - tb));
+    float ga = r * (w.nll_a * (pa - oh) + w.kl_b2a * (pa - tb) + w.kl_a2b * invT * ta * ((lta - lsb) - k_a2b) +
+                    w.kd_b2a * w.T * (ta - tb));
+    if (w.mse_b2a != 0.f) ga += r * w.mse_b2a * (a[c] - b[c]) / GC;
+    if (w.dkd_b2a != 0.f) {
+      const float g_t = c == pos ? ps_t - pt_t : ta * (pt_t - pt_o * ps_t / ps_o);
+      const float g_n = c == pos ? 0.f : ta / ps_o - tb / pt_o;
+      ga += r * w.dkd_b2a * w.T * (w.alpha * g_t + w.beta * g_n);
+    }
     const float gb = r * (w.nll_b * (pb - oh) + w.kl_a2b * (pb - ta) + w.kl_b2a * invT * tb * ((ltb - lsa) - k_b2a) +
                           w.kd_b2a * w.T * tb * ((ltb - lta) - k_kd));
     split_store<3>(dA + (long)row * ld + c, ps, ga);
@@ -428,6 +509,21 @@ local_pair_kernel(int q_count, int G, int H, const float* __restrict__ Q, const 
   }
 }
 
+// one half of PROD's Bi_logit: weight * 0.5 * mean((a - b)^2) and its gradient w.r.t. a
+__global__ void __launch_bounds__(256) embed_mse_kernel(const float* __restrict__ a, const float* __restrict__ b, long n,
+                                                        float weight, float* loss, float* grad) {
+  __shared__ float sh[16];
+  float acc = 0.f;
+  const float k = weight / (float)n;
+  for (long i = blockIdx.x * 256L + threadIdx.x; i < n; i += (long)gridDim.x * 256L) {
+    const float d = a[i] - b[i];
+    acc += d * d;
+    grad[i] = k * d;
+  }
+  acc = block_sum(acc, sh);
+  if (threadIdx.x == 0 && acc != 0.f) atomicAdd(loss, 0.5f * k * acc);
+}
+
 // shared pieces of the global-matrix paths ---------------------------------------------------------
 struct ScoreWs {  // per embedding pair (Q, C): planes, transposed planes, scores, score gradients
   size_t qp, cp, ctp, s, ds, total;
@@ -507,16 +603,17 @@ extern "C" int simx_score_loss(const simx_loss_cfg* cfg, const float* Q, const f
   SIMX_CHECK(cfg->c_count > 0 && cfg->c_begin >= 0 && cfg->c_begin + cfg->c_count <= cfg->GC, SIMX_ERR_INVALID,
              "score_loss: local passage range [%d,+%d) outside GC=%d", cfg->c_begin, cfg->c_count, cfg->GC);
   const int local_terms = cfg->terms & (SIMX_LOSS_KL_LOCAL | SIMX_LOSS_CE_LOCAL | SIMX_LOSS_KD_LOCAL | SIMX_LOSS_NLL_LOCAL |
-                                        SIMX_LOSS_ADV_LOCAL);
-  SIMX_CHECK(cfg->terms != 0 && (cfg->terms & ~63) == 0, SIMX_ERR_INVALID, "score_loss: bad terms mask %d", cfg->terms);
+                                        SIMX_LOSS_ADV_LOCAL | SIMX_LOSS_MSE_LOCAL | SIMX_LOSS_DKD_LOCAL);
+  SIMX_CHECK(cfg->terms != 0 && (cfg->terms & ~255) == 0, SIMX_ERR_INVALID, "score_loss: bad terms mask %d", cfg->terms);
   if (local_terms) {
     SIMX_CHECK(cfg->group >= 1 && cfg->group <= MAX_GROUP && cfg->c_count == cfg->q_count * cfg->group,
                SIMX_ERR_INVALID, "score_loss: local terms need c_count == q_count * group, group <= %d", MAX_GROUP);
-    if (cfg->terms & (SIMX_LOSS_KL_LOCAL | SIMX_LOSS_CE_LOCAL | SIMX_LOSS_KD_LOCAL | SIMX_LOSS_ADV_LOCAL))
+    if (cfg->terms & (SIMX_LOSS_KL_LOCAL | SIMX_LOSS_CE_LOCAL | SIMX_LOSS_KD_LOCAL | SIMX_LOSS_ADV_LOCAL | SIMX_LOSS_MSE_LOCAL |
+                      SIMX_LOSS_DKD_LOCAL))
       SIMX_CHECK(teacher != nullptr && cfg->temperature > 0.f, SIMX_ERR_INVALID,
                  "score_loss: distillation terms need teacher logits and a positive temperature");
   }
-  SIMX_CUDA(cudaMemsetAsync(out_losses, 0, 8 * sizeof(float), st));
+  SIMX_CUDA(cudaMemsetAsync(out_losses, 0, 12 * sizeof(float), st));
   bool have_grads = false;
   if (cfg->terms & SIMX_LOSS_NLL_GLOBAL) {
     SIMX_CHECK(pos_idx != nullptr && workspace != nullptr, SIMX_ERR_INVALID, "score_loss: NLL_GLOBAL needs pos_idx and workspace");
@@ -597,13 +694,24 @@ extern "C" int simx_pair_distill(const simx_pair_cfg* cfg, const float* Qa, cons
   SIMX_CUDA(cudaMemsetAsync(out_losses, 0, 8 * sizeof(float), st));
   SIMX_TRY(score_forward(Qa, Ca, GQ, GC, H, wa, w, st));
   SIMX_TRY(score_forward(Qb, Cb, GQ, GC, H, wb, w, st));
-  PairW pw{cfg->w_nll_a, cfg->w_nll_b, cfg->w_kl_b2a, cfg->w_kl_a2b, cfg->temperature, cfg->grad_scale, cfg->w_kd_b2a};
+  PairW pw{cfg->w_nll_a, cfg->w_nll_b, cfg->w_kl_b2a, cfg->w_kl_a2b, cfg->temperature, cfg->grad_scale, cfg->w_kd_b2a,
+           cfg->w_mse_b2a, cfg->w_dkd_b2a, cfg->dkd_alpha, cfg->dkd_beta};
   pair_row_kernel<<<GQ, 256, 0, st>>>(reinterpret_cast<const float*>(wa + w.s), reinterpret_cast<const float*>(wb + w.s), GQ,
                                       GC, GCp, pos_idx, pw, reinterpret_cast<bf16*>(wa + w.ds),
                                       train_b ? reinterpret_cast<bf16*>(wb + w.ds) : nullptr, (long)GQ * GCp, out_losses);
   SIMX_LAUNCH_CHECK();
   SIMX_TRY(score_backward(GQ, GC, H, cfg->q_begin, cfg->q_count, cfg->c_begin, cfg->c_count, wa, w, dQa, dCa, st));
   if (train_b) SIMX_TRY(score_backward(GQ, GC, H, cfg->q_begin, cfg->q_count, cfg->c_begin, cfg->c_count, wb, w, dQb, dCb, st));
+  return SIMX_OK;
+}
+
+extern "C" int simx_embed_mse(const float* a, const float* b, int64_t n, float weight, float* loss, float* grad,
+                              void* stream) {
+  using namespace simx;
+  SIMX_CHECK(a && b && loss && grad && n > 0, SIMX_ERR_INVALID, "embed_mse: null argument or empty tensor");
+  const int grid = (int)min((n + 255) / 256, (int64_t)num_sms() * 4);
+  embed_mse_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(a, b, (long)n, weight, loss, grad);
+  SIMX_LAUNCH_CHECK();
   return SIMX_OK;
 }
 
@@ -619,7 +727,7 @@ extern "C" int simx_local_pair_distill(const simx_pair_cfg* cfg, const float* Q_
              "local_pair_distill: c_count must be q_count * group with group <= %d", MAX_GROUP);
   SIMX_CHECK(cfg->H > 0 && cfg->H % 4 == 0 && cfg->temperature > 0.f, SIMX_ERR_INVALID, "local_pair_distill: bad H / temperature");
   SIMX_CUDA(cudaMemsetAsync(out_losses, 0, 8 * sizeof(float), st));
-  PairW pw{cfg->w_nll_a, cfg->w_nll_b, cfg->w_kl_b2a, cfg->w_kl_a2b, cfg->temperature, cfg->grad_scale, 0.f};
+  PairW pw{cfg->w_nll_a, cfg->w_nll_b, cfg->w_kl_b2a, cfg->w_kl_a2b, cfg->temperature, cfg->grad_scale, 0.f, 0.f, 0.f, 0.f, 0.f};
   local_pair_kernel<<<(cfg->q_count + 3) / 4, 128, 0, st>>>(cfg->q_count, cfg->c_count / cfg->q_count, cfg->H, Q_local, C_local,
                                                             teacher_logits, pw, out_losses, dQ, dC, dT);
   SIMX_LAUNCH_CHECK();

@@ -83,6 +83,7 @@ __global__ void __launch_bounds__(OPT_THREADS) scale_grads_kernel(const simx_opt
 struct AdamArgs {
   int mode;           // SIMX_ADAMW_TORCH / SIMX_ADAMW_HF
   float beta1, beta2, eps;
+  float omb1, omb2;     // 1 - beta, rounded from the double-precision difference (1.f - 0.999f is off by 5e-5 relative)
   float bc1, bc2_sqrt;  // 1 - beta1^t, sqrt(1 - beta2^t)
   int correct_bias;   // HF mode only
   float max_norm;
@@ -95,15 +96,15 @@ __device__ __forceinline__ void adam_one(const AdamArgs& a, float lr, float wd, 
   if (a.mode == SIMX_ADAMW_TORCH) {
     // torch.optim.AdamW (LEAD/util.py:901): decoupled decay first, bias-corrected second moment inside the denominator
     p *= 1.f - lr * wd;
-    m = m + (g - m) * (1.f - a.beta1);
-    v = v * a.beta2 + (1.f - a.beta2) * g * g;
+    m = m + (g - m) * a.omb1;
+    v = v * a.beta2 + a.omb2 * g * g;
     const float denom = sqrtf(v) / a.bc2_sqrt + a.eps;
     p -= (lr / a.bc1) * (m / denom);
   } else {
     // transformers.AdamW, the optimizer of the SimANS / PROD drivers (co_training_marco_train.py:22,67): eps is added
     // to the UN-corrected sqrt(v), the bias corrections scale the step size, decay is applied after the update
-    m = m * a.beta1 + (1.f - a.beta1) * g;
-    v = v * a.beta2 + (1.f - a.beta2) * g * g;
+    m = m * a.beta1 + a.omb1 * g;
+    v = v * a.beta2 + a.omb2 * g * g;
     const float denom = sqrtf(v) + a.eps;
     const float step = a.correct_bias ? lr * a.bc2_sqrt / a.bc1 : lr;
     p -= step * (m / denom);
@@ -196,21 +197,23 @@ extern "C" int simx_clip_grads(const simx_opt_tensor* tensors_dev, int n, int to
   return SIMX_OK;
 }
 
-extern "C" int simx_adamw_step(const simx_opt_tensor* tensors_dev, int n, int total_chunks, int mode, float beta1,
-                               float beta2, float eps, int step, int correct_bias, const double* sq_norm_dev,
+extern "C" int simx_adamw_step(const simx_opt_tensor* tensors_dev, int n, int total_chunks, int mode, double beta1,
+                               double beta2, float eps, int step, int correct_bias, const double* sq_norm_dev,
                                float max_norm, int write_clipped_grads, void* stream) {
   SIMX_CHECK(tensors_dev && n > 0 && total_chunks > 0, SIMX_ERR_INVALID, "adamw_step: bad argument");
   SIMX_CHECK(mode == SIMX_ADAMW_TORCH || mode == SIMX_ADAMW_HF, SIMX_ERR_INVALID, "adamw_step: unknown mode %d", mode);
   SIMX_CHECK(step >= 1, SIMX_ERR_INVALID, "adamw_step: step counts from 1 (got %d)", step);
-  SIMX_CHECK(beta1 >= 0.f && beta1 < 1.f && beta2 >= 0.f && beta2 < 1.f, SIMX_ERR_INVALID, "adamw_step: betas out of range");
+  SIMX_CHECK(beta1 >= 0.0 && beta1 < 1.0 && beta2 >= 0.0 && beta2 < 1.0, SIMX_ERR_INVALID, "adamw_step: betas out of range");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   AdamArgs a;
   a.mode = mode;
-  a.beta1 = beta1;
-  a.beta2 = beta2;
+  a.beta1 = (float)beta1;
+  a.beta2 = (float)beta2;
+  a.omb1 = (float)(1.0 - beta1);
+  a.omb2 = (float)(1.0 - beta2);
   a.eps = eps;
-  a.bc1 = (float)(1.0 - pow((double)beta1, (double)step));
-  a.bc2_sqrt = (float)sqrt(1.0 - pow((double)beta2, (double)step));
+  a.bc1 = (float)(1.0 - pow(beta1, (double)step));
+  a.bc2_sqrt = (float)sqrt(1.0 - pow(beta2, (double)step));
   a.correct_bias = correct_bias;
   a.max_norm = max_norm;
   a.write_grads = write_clipped_grads && sq_norm_dev != nullptr;

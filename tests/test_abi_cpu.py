@@ -32,8 +32,9 @@ def test_library_exports_every_declared_symbol():
 
 def test_struct_mirrors_have_header_layout():
     assert C.sizeof(_lib.EncoderCfg) == 10 * 4
-    assert C.sizeof(_lib.LossCfg) == 9 * 4 + 10 * 4
-    assert C.sizeof(_lib.PairCfg) == 7 * 4 + 7 * 4
+    assert C.sizeof(_lib.LossCfg) == 9 * 4 + 14 * 4
+    assert C.sizeof(_lib.PairCfg) == 7 * 4 + 11 * 4
+    assert C.sizeof(_lib.OptTensor) == 56
 
 
 @pytest.mark.parametrize("arch,n_expected", [("bert", 5 + 16 * 12 + 2), ("distilbert", 4 + 16 * 6)])
