@@ -193,6 +193,23 @@ int simx_local_pair_distill(const simx_pair_cfg* cfg, const float* Q_local, cons
  * *loss += weight * 0.5 * mean((a - b)^2) and grad[i] = weight * (a[i] - b[i]) / n   (a, b, grad: n fp32 elements). */
 int simx_embed_mse(const float* a, const float* b, int64_t n, float weight, float* loss, float* grad, void* stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * Exact inner-product top-k over a resident embedding shard — replaces, for the ANN refresh of every
+ * SimANS round, faiss.IndexFlatIP + index_cpu_to_all_gpus(shard=True).add(P) and .search(Q, 200 | 1000)
+ * (SimANS/co_training/co_training_generate.py:359-384, 412-427).
+ *   corpus_planes: caller-owned device buffer of simx_topk_corpus_bytes(N, H), 256-byte aligned, filled slab by slab with
+ *   simx_topk_add (fp32 rows [n_rows, H] at row_offset; the rows are kept as 3 bf16 planes = fp32-class operands of the
+ *   tcgen05 score GEMM).  simx_topk_search: Q [nq, H] fp32 -> out_scores [nq, k] fp32 (descending), out_idx [nq, k]
+ *   int64 row numbers inside this shard (ties: lowest row first; -1 / -inf padding when N < k).  k <= 1024, nq <= 65535,
+ *   N < 2^31, H % 64 == 0.
+ * ---------------------------------------------------------------------------------------------- */
+size_t simx_topk_corpus_bytes(int64_t N, int H);
+int simx_topk_add(const float* P, int64_t n_rows, int64_t row_offset, int64_t N_total, int H, void* corpus_planes,
+                  void* stream);
+size_t simx_topk_workspace_bytes(int nq, int64_t N, int H, int k);
+int simx_topk_search(const float* Q, int nq, const void* corpus_planes, int64_t N, int H, int k, float* out_scores,
+                     int64_t* out_idx, void* workspace, void* stream);
+
 /* SimANS ambiguous-negative sampling (SimANS/utils/MARCO_until_new.py:165-202, SimANS/utils/util_wiki.py:613-639):
  * for each of NQ queries choose k of its first n_valid[q] (<= NC <= 1024) candidates, without duplicates, with probability
  * proportional to  exp(-p0 |s - s+|)  (mode 0, p0 = tau)  or  exp(-p0 (s - s+ + p1)^2)  (mode 1, p0 = a, p1 = b); queries

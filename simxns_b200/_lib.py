@@ -108,6 +108,10 @@ SIGNATURES = {
     "simx_pair_distill": (_I, [C.POINTER(PairCfg), _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
     "simx_local_pair_distill": (_I, [C.POINTER(PairCfg), _P, _P, _P, _P, _P, _P, _P, _P]),
     "simx_embed_mse": (_I, [_P, _P, _L, C.c_float, _P, _P, _P]),
+    "simx_topk_corpus_bytes": (C.c_size_t, [_L, _I]),
+    "simx_topk_add": (_I, [_P, _L, _L, _L, _I, _P, _P]),
+    "simx_topk_workspace_bytes": (C.c_size_t, [_I, _L, _I, _I]),
+    "simx_topk_search": (_I, [_P, _I, _P, _L, _I, _I, _P, _P, _P, _P]),
     "simx_simans_sample": (_I, [_P, _P, _P, _I, _I, _I, _I, C.c_float, C.c_float, C.c_uint64, _P, _P]),
     "simx_attention_forward": (_I, [_P, _P, _P, _P, _I, _I, _I, _I, _I, _L, _L, _P]),
     "simx_attention_backward": (_I, [_P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _L, _L, _P, _P]),

@@ -1,0 +1,431 @@
+// Exact inner-product top-k over a resident passage-embedding shard: the GPU side of the ANN refresh of
+// every SimANS round — faiss.IndexFlatIP + index_cpu_to_all_gpus(shard=True) + .search(q, 200 | 1000)
+// (SimANS/co_training/co_training_generate.py:359-384, 412-427).
+//
+//   corpus  : kept in HBM as 3 bf16 planes per value (fp32-class, 6 B instead of 4 B per element) — the B operand of the
+//             tcgen05 GEMM, K-major as stored, never re-converted;
+//   scores  : S[nq, chunk] = Q P_chunk^T on the tensor cores (6 plane-pair passes, fp32 accumulation in TMEM), written
+//             once as 3 planes;
+//   select  : one CTA per (query, 32768-column segment): the segment is read ONCE from HBM into shared memory as
+//             order-preserving 32-bit keys relative to the segment minimum, a radix select over the bits the segment's
+//             range actually spans (11 bits per pass, warp-aggregated shared-memory atomics) finds the k-th largest, the winners
+//             (ties: lowest index first) go to a candidate list; candidate lists are reduced by the same kernel until one
+//             segment is left, which is also sorted (bitonic, (score desc, index asc)) and written as (fp32, int64).
+// HBM-bound: 12 B per (query, passage) pair for the score round trip; the select itself runs out of shared memory.
+#include <algorithm>
+
+#include "common.cuh"
+
+namespace simx {
+
+int gemm(int M, int N, int K, const bf16* A, long lda, long a_ps, bool a_mn, const bf16* B, long ldb, long b_ps,
+         bool b_mn, int planes, int epi, const float* bias, const bf16* aux, long ldaux, long aux_ps, bf16* out,
+         bf16* out2, long ldo, long out_ps, float* outf, long ldof, int ksplit, cudaStream_t stream);
+int convert_weight(int np, const float* w, int R, int C, bf16* dst, long ld_dst, long ps_dst, bf16* dst_t, long ld_t,
+                   long ps_t, cudaStream_t st);
+
+constexpr int TOPK_SEG = 32768;      // elements of one select segment (128 KB of keys in shared memory)
+constexpr int TOPK_THREADS = 1024;
+constexpr int TOPK_MAX_K = 1024;
+constexpr int TOPK_CHUNK = 4 * TOPK_SEG;  // passages per score GEMM
+
+__device__ __forceinline__ uint32_t float_to_key(float f) {
+  const uint32_t u = __float_as_uint(f);
+  return (u & 0x80000000u) ? ~u : (u | 0x80000000u);  // monotone: larger float <=> larger key (-0 < +0)
+}
+__device__ __forceinline__ float key_to_float(uint32_t k) {
+  return __uint_as_float((k & 0x80000000u) ? (k & 0x7fffffffu) : ~k);
+}
+
+struct SelectArgs {
+  const bf16* planes;   // phase 1 input: 3-plane scores [rows, ld] (plane stride ps), or NULL
+  long ps;
+  const float* vals;    // phase 2 input: fp32 candidates [rows, ld]
+  const int32_t* idx;   // phase 2: their passage indices
+  long ld;              // row stride of the input
+  int n;                // valid elements per row
+  int idx_base;         // phase 1: passage index of column 0
+  int k;
+  float* out_vals;      // [rows, out_ld]: segment s writes k entries at s * k
+  int32_t* out_idx;
+  long out_ld;
+  float* final_vals;    // when non-NULL (single segment): sorted results [rows, k]
+  int64_t* final_idx;
+};
+
+// position of the bin, counted from the top, in which the `want`-th largest element lies; returns the bin and how many
+// elements lie in bins above it.  One warp scans `nbins` (multiple of 32) counters.
+__device__ __forceinline__ void find_bin(const uint32_t* hist, int nbins, uint32_t want, int lane, int& bin_out,
+                                         uint32_t& above_out) {
+  const int per = nbins / 32;
+  // lane L owns bins [nbins - (L+1)*per, nbins - L*per): lane 0 holds the top bins
+  const int hi = nbins - lane * per;
+  uint32_t mine = 0;
+  for (int b = hi - per; b < hi; ++b) mine += hist[b];
+  uint32_t incl = mine;  // inclusive prefix over lanes 0..L (top-down)
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
+    if (lane >= o) incl += t;
+  }
+  const uint32_t excl = incl - mine;
+  const bool here = excl < want && want <= incl;
+  const uint32_t ballot = __ballot_sync(0xffffffffu, here);
+  const int owner = ballot ? __ffs(ballot) - 1 : 31;
+  int bin = 0;
+  uint32_t above = 0;
+  if (lane == owner) {
+    uint32_t acc = excl;
+    bin = hi - per;
+    above = incl - hist[hi - per];
+    for (int b = hi - 1; b >= hi - per; --b) {
+      if (acc + hist[b] >= want) { bin = b; above = acc; break; }
+      acc += hist[b];
+    }
+  }
+  bin_out = __shfl_sync(0xffffffffu, bin, owner);
+  above_out = __shfl_sync(0xffffffffu, above, owner);
+}
+
+__global__ void __launch_bounds__(TOPK_THREADS, 1) topk_select_kernel(const SelectArgs a) {
+  extern __shared__ uint32_t sm[];
+  uint32_t* keys = sm;                    // [TOPK_SEG]
+  uint32_t* hist = sm + TOPK_SEG;         // [2048]
+  __shared__ uint32_t s_prefix, s_want, s_count, s_ties_base, s_min, s_max;
+  __shared__ uint32_t s_scan[TOPK_THREADS / 32], s_red[2][TOPK_THREADS / 32];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int seg = blockIdx.x;
+  const long row = blockIdx.y;
+  const int begin = seg * TOPK_SEG;
+  const int m = min(TOPK_SEG, a.n - begin);
+  const int k = a.k;
+  float* ov = a.out_vals ? a.out_vals + row * a.out_ld + (long)seg * k : nullptr;
+  int32_t* oi = a.out_idx ? a.out_idx + row * a.out_ld + (long)seg * k : nullptr;
+  const bool fin = a.final_vals != nullptr;
+
+  // ---- load the segment once: HBM -> order-preserving keys in shared memory ----
+  if (a.planes != nullptr) {
+    const bf16* p = a.planes + row * a.ld + begin;
+    for (int j = tid * 2; j < m; j += TOPK_THREADS * 2) {  // ld and begin are even: 4-byte loads of bf16 pairs
+      if (j + 1 < m) {
+        const __nv_bfloat162 x0 = *reinterpret_cast<const __nv_bfloat162*>(p + j);
+        const __nv_bfloat162 x1 = *reinterpret_cast<const __nv_bfloat162*>(p + a.ps + j);
+        const __nv_bfloat162 x2 = *reinterpret_cast<const __nv_bfloat162*>(p + 2 * a.ps + j);
+        keys[j] = float_to_key(__low2float(x0) + __low2float(x1) + __low2float(x2));
+        keys[j + 1] = float_to_key(__high2float(x0) + __high2float(x1) + __high2float(x2));
+      } else {
+        keys[j] = float_to_key(__bfloat162float(p[j]) + __bfloat162float(p[a.ps + j]) + __bfloat162float(p[2 * a.ps + j]));
+      }
+    }
+  } else {
+    const float* p = a.vals + row * a.ld + begin;
+    for (int j = tid; j < m; j += TOPK_THREADS) keys[j] = float_to_key(p[j]);
+  }
+  __syncthreads();
+
+  auto index_of = [&](int j) -> int32_t {
+    return a.idx != nullptr ? a.idx[row * a.ld + begin + j] : a.idx_base + begin + j;
+  };
+
+  // number of winners this segment produces, and (radix select) the key of the last one
+  const int take = min(k, m);
+  uint32_t thr = 0;          // k-th largest key (relative to the segment minimum)
+  uint32_t n_greater = 0;    // elements with key > thr
+  uint32_t kmin = 0;
+  if (m > k) {
+    // keys relative to the segment minimum: the radix digits then cover only the bits the scores actually span, so the
+    // elements spread over the histogram bins instead of piling into the two or three bins a shared exponent would give
+    uint32_t lo = 0xffffffffu, hi = 0u;
+    for (int j = tid; j < m; j += TOPK_THREADS) {
+      const uint32_t key = keys[j];
+      lo = min(lo, key);
+      hi = max(hi, key);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      lo = min(lo, __shfl_xor_sync(0xffffffffu, lo, o));
+      hi = max(hi, __shfl_xor_sync(0xffffffffu, hi, o));
+    }
+    if (lane == 0) { s_red[0][warp] = lo; s_red[1][warp] = hi; }
+    __syncthreads();
+    if (tid == 0) {
+      for (int wv = 1; wv < TOPK_THREADS / 32; ++wv) { lo = min(lo, s_red[0][wv]); hi = max(hi, s_red[1][wv]); }
+      s_min = lo;
+      s_max = hi;
+    }
+    __syncthreads();
+    kmin = s_min;
+    const uint32_t range = s_max - kmin;
+    for (int j = tid; j < m; j += TOPK_THREADS) keys[j] -= kmin;
+    uint32_t prefix = 0, mask = 0, want = (uint32_t)k;
+    int top = 32 - __clz(range);  // number of significant bits of the relative keys (0: all elements equal)
+#pragma unroll 1
+    while (top > 0) {
+      const int wbits = min(11, top), sh = top - wbits;
+      const uint32_t dmask = (1u << wbits) - 1u;
+      for (int b = tid; b < 2048; b += TOPK_THREADS) hist[b] = 0;
+      __syncthreads();
+      for (int base = 0; base < m; base += TOPK_THREADS) {
+        const int j = base + tid;
+        const uint32_t key = j < m ? keys[j] : 0u;
+        const bool act = j < m && (key & mask) == prefix;
+        const uint32_t digit = (key >> sh) & dmask;
+        const uint32_t am = __ballot_sync(0xffffffffu, act);
+        if (act) {  // one shared-memory atomic per distinct digit per warp
+          const uint32_t peers = __match_any_sync(am, digit);
+          if (lane == __ffs(peers) - 1) atomicAdd(&hist[digit], (uint32_t)__popc(peers));
+        }
+      }
+      __syncthreads();
+      if (warp == 0) {
+        int bin;
+        uint32_t above;
+        find_bin(hist, 2048, want, lane, bin, above);
+        if (lane == 0) {
+          s_prefix = prefix | ((uint32_t)bin << sh);
+          s_want = want - above;
+        }
+      }
+      __syncthreads();
+      prefix = s_prefix;
+      want = s_want;
+      mask |= dmask << sh;
+      top = sh;
+      __syncthreads();
+    }
+    thr = prefix;
+    n_greater = (uint32_t)k - want;  // `want` of the ties at thr are still needed
+  }
+
+  // ---- emit: everything above the threshold (any order), then the ties in index order ----
+  // winners are staged in `hist` (2048 words: k keys + k positions, k <= 1024) so the final segment can sort them
+  uint32_t* w_key = hist;
+  uint32_t* w_pos = hist + TOPK_MAX_K;
+  if (tid == 0) { s_count = 0; s_ties_base = 0; }
+  __syncthreads();
+  if (m > k) {
+    for (int j = tid; j < m; j += TOPK_THREADS) {
+      const uint32_t key = keys[j];
+      if (key > thr) {
+        const uint32_t slot = atomicAdd(&s_count, 1u);
+        w_key[slot] = key;
+        w_pos[slot] = (uint32_t)j;
+      }
+    }
+    __syncthreads();
+    // ties: block-wide ordered compaction, lowest position first, until `need` are placed
+    const uint32_t need = (uint32_t)k - n_greater;
+    for (int base = 0; base < m; base += TOPK_THREADS) {
+      const int j = base + tid;
+      const bool tie = j < m && keys[j] == thr;
+      const uint32_t bal = __ballot_sync(0xffffffffu, tie);
+      if (lane == 0) s_scan[warp] = __popc(bal);
+      __syncthreads();
+      uint32_t before = s_ties_base;
+      for (int wv = 0; wv < warp; ++wv) before += s_scan[wv];
+      const uint32_t rank = before + __popc(bal & ((1u << lane) - 1u));
+      if (tie && rank < need) {
+        w_key[n_greater + rank] = thr;
+        w_pos[n_greater + rank] = (uint32_t)j;
+      }
+      __syncthreads();
+      if (tid == 0) {
+        uint32_t tot = 0;
+        for (int wv = 0; wv < TOPK_THREADS / 32; ++wv) tot += s_scan[wv];
+        s_ties_base += tot;
+      }
+      __syncthreads();
+      if (s_ties_base >= need) break;
+    }
+  } else {
+    for (int j = tid; j < m; j += TOPK_THREADS) {
+      w_key[j] = keys[j];
+      w_pos[j] = (uint32_t)j;
+    }
+  }
+  __syncthreads();
+
+  if (!fin) {
+    for (int t = tid; t < k; t += TOPK_THREADS) {
+      if (t < take) {
+        ov[t] = key_to_float(w_key[t] + kmin);
+        oi[t] = index_of((int)w_pos[t]);
+      } else {
+        ov[t] = -INFINITY;  // fewer than k elements in this segment: padding never wins a later round
+        oi[t] = -1;
+      }
+    }
+    return;
+  }
+
+  // ---- final segment: bitonic sort of (key desc, passage index asc) over 1024 slots, then write fp32 / int64 ----
+  unsigned long long* srt = reinterpret_cast<unsigned long long*>(keys);  // the keys are dead: reuse their storage
+  {
+    unsigned long long v = 0ull;  // padding sorts last
+    if (tid < take) {
+      const uint32_t key = w_key[tid] + kmin;
+      const int32_t id = index_of((int)w_pos[tid]);
+      v = ((unsigned long long)key << 32) | (uint32_t)(0x7fffffff - max(id, 0));
+      if (id < 0) v = 0ull;  // padding entries of an earlier round
+    }
+    __syncthreads();
+    srt[tid] = v;
+  }
+  __syncthreads();
+  for (int size = 2; size <= TOPK_THREADS; size <<= 1) {
+    for (int stride = size >> 1; stride > 0; stride >>= 1) {
+      const int partner = tid ^ stride;
+      if (partner > tid) {
+        const unsigned long long x = srt[tid], y = srt[partner];
+        const bool desc = (tid & size) == 0;
+        if (desc ? x < y : x > y) { srt[tid] = y; srt[partner] = x; }
+      }
+      __syncthreads();
+    }
+  }
+  if (tid < k) {
+    const unsigned long long v = srt[tid];
+    const bool valid = v != 0ull;
+    a.final_vals[row * k + tid] = valid ? key_to_float((uint32_t)(v >> 32)) : -INFINITY;
+    a.final_idx[row * k + tid] = valid ? (int64_t)(0x7fffffff - (uint32_t)(v & 0xffffffffu)) : -1;
+  }
+}
+
+struct TopkWs {
+  size_t qp, s, cand_v[2], cand_i[2], total;
+  long cand_ld;
+  int chunk;
+};
+static inline size_t al256(size_t x) { return (x + 255) & ~size_t(255); }
+static TopkWs topk_ws(int nq, int64_t N, int H, int k) {
+  TopkWs w{};
+  w.chunk = (int)std::min<int64_t>(TOPK_CHUNK, (N + 7) / 8 * 8);
+  const int64_t n_chunks = (N + w.chunk - 1) / w.chunk;
+  const int64_t segs = n_chunks * ((w.chunk + TOPK_SEG - 1) / TOPK_SEG);
+  w.cand_ld = segs * k;
+  size_t off = 0;
+  w.qp = off; off += al256(3ull * nq * H * 2);
+  w.s = off;  off += al256(3ull * nq * (size_t)w.chunk * 2);
+  for (int i = 0; i < 2; ++i) {
+    const size_t ld = i == 0 ? (size_t)w.cand_ld : (size_t)((w.cand_ld + TOPK_SEG - 1) / TOPK_SEG) * k;
+    w.cand_v[i] = off; off += al256(4ull * nq * ld);
+    w.cand_i[i] = off; off += al256(4ull * nq * ld);
+  }
+  w.total = off + 256;
+  return w;
+}
+
+}  // namespace simx
+
+using namespace simx;
+
+// rows are padded to a multiple of 8 per plane: the score GEMM wants N % 8 == 0 and may touch up to 7 rows past the end
+static inline int64_t pad8(int64_t n) { return (n + 7) / 8 * 8; }
+
+extern "C" size_t simx_topk_corpus_bytes(int64_t N, int H) {
+  return (N <= 0 || H <= 0) ? 0 : 3ull * (size_t)pad8(N) * H * 2;
+}
+
+extern "C" int simx_topk_add(const float* P, int64_t n_rows, int64_t row_offset, int64_t N_total, int H,
+                             void* corpus_planes, void* stream) {
+  SIMX_CHECK(P && corpus_planes && n_rows > 0 && row_offset >= 0 && row_offset + n_rows <= N_total, SIMX_ERR_INVALID,
+             "topk_add: bad slab [%lld, +%lld) of %lld rows", (long long)row_offset, (long long)n_rows, (long long)N_total);
+  SIMX_CHECK(H > 0 && H % 64 == 0, SIMX_ERR_INVALID, "topk_add: H=%d must be a multiple of 64", H);
+  SIMX_CHECK((reinterpret_cast<uintptr_t>(corpus_planes) & 255) == 0, SIMX_ERR_INVALID, "topk_add: corpus buffer must be 256-byte aligned");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  bf16* dst = static_cast<bf16*>(corpus_planes) + row_offset * H;
+  const long ps = (long)(pad8(N_total) * H);
+  const int64_t slab = 1 << 20;  // grid.y limit of the converter
+  for (int64_t r = 0; r < n_rows; r += slab) {
+    const int rows = (int)std::min<int64_t>(slab, n_rows - r);
+    SIMX_TRY(convert_weight(3, P + r * H, rows, H, dst + r * H, H, ps, nullptr, 0, 0, st));
+  }
+  if (row_offset + n_rows == N_total && pad8(N_total) != N_total)  // the padding rows score 0 and are never selected
+    for (int p = 0; p < 3; ++p)
+      SIMX_CUDA(cudaMemsetAsync(static_cast<bf16*>(corpus_planes) + p * ps + N_total * H, 0,
+                                (size_t)(pad8(N_total) - N_total) * H * 2, st));
+  return SIMX_OK;
+}
+
+extern "C" size_t simx_topk_workspace_bytes(int nq, int64_t N, int H, int k) {
+  if (nq <= 0 || N <= 0 || H <= 0 || k <= 0) return 0;
+  return topk_ws(nq, N, H, k).total;
+}
+
+extern "C" int simx_topk_search(const float* Q, int nq, const void* corpus_planes, int64_t N, int H, int k,
+                                float* out_scores, int64_t* out_idx, void* workspace, void* stream) {
+  SIMX_CHECK(Q && corpus_planes && out_scores && out_idx && workspace, SIMX_ERR_INVALID, "topk_search: null argument");
+  SIMX_CHECK(nq > 0 && N > 0 && N < 0x7fffffff, SIMX_ERR_INVALID, "topk_search: need 0 < nq, 0 < N < 2^31");
+  SIMX_CHECK(k >= 1 && k <= TOPK_MAX_K, SIMX_ERR_INVALID, "topk_search: k=%d outside [1, %d]", k, TOPK_MAX_K);
+  SIMX_CHECK(H > 0 && H % 64 == 0, SIMX_ERR_INVALID, "topk_search: H=%d must be a multiple of 64", H);
+  SIMX_CHECK(nq <= 65535, SIMX_ERR_INVALID, "topk_search: at most 65535 queries per call (got %d)", nq);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const TopkWs w = topk_ws(nq, N, H, k);
+  uint8_t* ws = static_cast<uint8_t*>(workspace);
+  ws += (256 - (reinterpret_cast<uintptr_t>(ws) & 255)) & 255;
+  bf16* Qp = reinterpret_cast<bf16*>(ws + w.qp);
+  bf16* S = reinterpret_cast<bf16*>(ws + w.s);
+  float* cv[2] = {reinterpret_cast<float*>(ws + w.cand_v[0]), reinterpret_cast<float*>(ws + w.cand_v[1])};
+  int32_t* ci[2] = {reinterpret_cast<int32_t*>(ws + w.cand_i[0]), reinterpret_cast<int32_t*>(ws + w.cand_i[1])};
+  const bf16* corpus = static_cast<const bf16*>(corpus_planes);
+  const size_t smem = (TOPK_SEG + 2048) * sizeof(uint32_t);
+  static bool attr = false;
+  if (!attr) {
+    SIMX_CUDA(cudaFuncSetAttribute(topk_select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr = true;
+  }
+  SIMX_TRY(convert_weight(3, Q, nq, H, Qp, H, (long)nq * H, nullptr, 0, 0, st));
+  const bool single = N <= TOPK_SEG;  // one segment: select, sort and write the results straight from the scores
+
+  const int segs_per_chunk = (w.chunk + TOPK_SEG - 1) / TOPK_SEG;
+  int chunk_i = 0;
+  for (int64_t c0 = 0; c0 < N; c0 += w.chunk, ++chunk_i) {
+    const int cols = (int)std::min<int64_t>(w.chunk, N - c0);
+    const int cols8 = (cols + 7) / 8 * 8;  // the GEMM wants N % 8 == 0: the last chunk also scores the (zero) padding
+    // rows of the corpus buffer; the select reads only `cols` columns
+    {
+      ProfScope prof("topk_scores", 12.0 * nq * (double)cols * H, 6.0 * ((double)cols * H + (double)nq * cols), st);
+      SIMX_TRY(gemm(nq, cols8, H, Qp, H, (long)nq * H, false, corpus + c0 * H, H, (long)(pad8(N) * H), false, 3, SIMX_EPI_PLAIN,
+                    nullptr, nullptr, 0, 0, S, nullptr, w.chunk, (long)nq * w.chunk, nullptr, 0, 1, st));
+    }
+    SelectArgs a{};
+    a.planes = S; a.ps = (long)nq * w.chunk; a.ld = w.chunk; a.n = cols; a.idx_base = (int)c0; a.k = k;
+    if (single) {
+      a.final_vals = out_scores; a.final_idx = out_idx;
+    } else {
+      a.out_vals = cv[0] + (long)chunk_i * segs_per_chunk * k;
+      a.out_idx = ci[0] + (long)chunk_i * segs_per_chunk * k;
+      a.out_ld = w.cand_ld;
+    }
+    const int segs = (cols + TOPK_SEG - 1) / TOPK_SEG;
+    ProfScope prof("topk_select", 0, 6.0 * nq * (double)cols, st);
+    topk_select_kernel<<<dim3(segs, nq), TOPK_THREADS, smem, st>>>(a);
+    SIMX_LAUNCH_CHECK();
+  }
+  if (!single) {
+    // candidates actually written: full chunks contribute segs_per_chunk * k each, the last chunk its own segments
+    const int64_t full_chunks = N / w.chunk;
+    const int64_t tail = N - full_chunks * w.chunk;
+    long n_cand = (long)(full_chunks * segs_per_chunk + (tail + TOPK_SEG - 1) / TOPK_SEG) * k;
+    int cur = 0;
+    long ld = w.cand_ld;
+    for (;;) {
+      const int segs = (int)((n_cand + TOPK_SEG - 1) / TOPK_SEG);
+      SelectArgs a{};
+      a.vals = cv[cur]; a.idx = ci[cur]; a.ld = ld; a.n = (int)n_cand; a.k = k;
+      if (segs == 1) {
+        a.final_vals = out_scores; a.final_idx = out_idx;
+      } else {
+        a.out_vals = cv[cur ^ 1]; a.out_idx = ci[cur ^ 1]; a.out_ld = (long)segs * k;
+      }
+      ProfScope prof("topk_reduce", 0, 8.0 * nq * (double)n_cand, st);
+      topk_select_kernel<<<dim3(segs, nq), TOPK_THREADS, smem, st>>>(a);
+      SIMX_LAUNCH_CHECK();
+      if (segs == 1) break;
+      ld = (long)segs * k;
+      n_cand = ld;
+      cur ^= 1;
+    }
+  }
+  return SIMX_OK;
+}

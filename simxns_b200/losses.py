@@ -10,6 +10,8 @@
                                      ce_local    -sum p_t log(p_s+eps)/B (wiki / MASTER / PROD prob_loss)
                                      kd_local    PROD KD_softmax (/root/reference/PROD/ProD_KD/model/models.py:772-777)
                                      nll_local   PROD hard loss, positive = column 0 (.../models.py:694-712)
+                                     mse_local   PROD KD_logit, 0.5 MSE(scores, teacher logits) (.../models.py:778-780)
+                                     dkd_local   PROD DKD, alpha TCKD + beta NCKD (.../models.py:783-812)
   BiEncoderNllLoss / CrossBERTKDLoss / simans_distill_loss   drop-in call signatures of the reference.
 
 The kernel returns the loss terms AND d(loss)/d(local embeddings) in the same pass; autograd only scales them by the
@@ -27,8 +29,10 @@ import torch.distributed as dist
 from . import _lib
 
 _TERMS = {"nll_global": _lib.LOSS_NLL_GLOBAL, "kl_local": _lib.LOSS_KL_LOCAL, "ce_local": _lib.LOSS_CE_LOCAL,
-          "kd_local": _lib.LOSS_KD_LOCAL, "nll_local": _lib.LOSS_NLL_LOCAL, "adv_local": _lib.LOSS_ADV_LOCAL}
-LOSS_FIELDS = ("total", "nll_global", "kl_local", "ce_local", "kd_local", "nll_local", "n_correct")
+          "kd_local": _lib.LOSS_KD_LOCAL, "nll_local": _lib.LOSS_NLL_LOCAL, "adv_local": _lib.LOSS_ADV_LOCAL,
+          "mse_local": _lib.LOSS_MSE_LOCAL, "dkd_local": _lib.LOSS_DKD_LOCAL}
+LOSS_FIELDS = ("total", "nll_global", "kl_local", "ce_local", "kd_local", "nll_local", "n_correct", "n_correct_local",
+               "mse_local", "dkd_local")
 
 
 def gather_embeddings(local: torch.Tensor, group=None) -> torch.Tensor:
@@ -75,7 +79,9 @@ class _ScoreLossFn(torch.autograd.Function):
                 group=group, w_nll_global=w.get("nll_global", 1.0), w_kl_local=w.get("kl_local", 1.0),
                 w_ce_local=w.get("ce_local", 1.0), w_kd_local=w.get("kd_local", 1.0), w_nll_local=w.get("nll_local", 1.0),
                 temperature=opts.get("temperature", 1.0), eps=opts.get("eps", 1e-7),
-                score_scale=opts.get("score_scale", 1.0), grad_scale=1.0, w_adv_local=w.get("adv_local", 1.0))
+                score_scale=opts.get("score_scale", 1.0), grad_scale=1.0, w_adv_local=w.get("adv_local", 1.0),
+                w_mse_local=w.get("mse_local", 1.0), w_dkd_local=w.get("dkd_local", 1.0),
+                dkd_alpha=opts.get("dkd_alpha", 1.0), dkd_beta=opts.get("dkd_beta", 1.0))
             if use_global:
                 if pos_idx is None:
                     pos_idx = torch.arange(0, GQ * group, group, device=dev, dtype=torch.int32)  # LEAD/util.py:445
@@ -88,7 +94,7 @@ class _ScoreLossFn(torch.autograd.Function):
                     raise ValueError(f"teacher logits must be [{nq}, {group}], got {tuple(teacher.shape)}")
             ws_bytes = lib.simx_score_loss_workspace_bytes(C.byref(cfg))
             ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
-            losses = torch.empty(8, dtype=torch.float32, device=dev)
+            losses = torch.empty(12, dtype=torch.float32, device=dev)
             dQ = torch.empty_like(q_local)
             dC = torch.empty_like(c_local)
             stream = torch.cuda.current_stream(dev).cuda_stream
@@ -107,10 +113,12 @@ class _ScoreLossFn(torch.autograd.Function):
 
 def fused_score_loss(q_local: torch.Tensor, c_local: torch.Tensor, terms: Sequence[str], *, teacher=None, pos_idx=None,
                      weights: Optional[dict] = None, temperature: float = 1.0, eps: float = 1e-7,
-                     score_scale: float = 1.0, group_size: Optional[int] = None, gather: bool = True, group=None):
-    """-> (loss scalar with autograd into q_local / c_local, detail tensor [8] = LOSS_FIELDS + pad)"""
+                     score_scale: float = 1.0, group_size: Optional[int] = None, gather: bool = True, group=None,
+                     dkd_alpha: float = 1.0, dkd_beta: float = 1.0):
+    """-> (loss scalar with autograd into q_local / c_local, detail tensor [12] = LOSS_FIELDS + pad)"""
     opts = dict(terms=tuple(terms), weights=dict(weights or {}), temperature=float(temperature), eps=float(eps),
-                score_scale=float(score_scale), group_size=group_size, gather=gather, group=group)
+                score_scale=float(score_scale), group_size=group_size, gather=gather, group=group,
+                dkd_alpha=float(dkd_alpha), dkd_beta=float(dkd_beta))
     return _ScoreLossFn.apply(q_local, c_local, teacher, pos_idx, opts)
 
 
@@ -142,8 +150,12 @@ class BiEncoderNllLoss(object):
 
 class CrossBERTKDLoss(object):
     """PROD/ProD_KD/model/models.py:668-781: CE_WEIGHT * NLL(column 0) + KD_WEIGHT * soft [+ LwF_WEIGHT * LwF] on the
-    query's own [1+n] block.  KD_type 'KD_softmax' and 'prob_loss' run fused; LwF adds a second fused call against the
-    frozen student's scores."""
+    query's own [1+n] block.  Every KD_type of the reference ('KD_softmax', 'KD_logit', 'DKD', 'prob_loss') runs fused;
+    LwF adds a second fused call against the frozen student's scores (kd_loss handles KD_softmax / KD_logit only there,
+    as in the reference)."""
+
+    _SOFT = {"KD_softmax": "kd_local", "KD_logit": "mse_local", "DKD": "dkd_local", "prob_loss": "ce_local"}
+
 
     def calc(self, args, q_vectors, ctx_vectors, relevance_logits, hard_negative_idx_per_question: list = None,
              loss_scale: float = None, LwF=False, ori_q_vector=None, ori_ctx_vectors=None):
@@ -151,21 +163,24 @@ class CrossBERTKDLoss(object):
         group = ctx_vectors.shape[0] // nq
         if relevance_logits is None:
             loss, detail = fused_score_loss(q_vectors, ctx_vectors, ["nll_local"], group_size=group, gather=False)
-        elif args.KD_type == "KD_softmax":
-            loss, detail = fused_score_loss(q_vectors, ctx_vectors, ["nll_local", "kd_local"], teacher=relevance_logits,
-                                            weights=dict(nll_local=args.CE_WEIGHT, kd_local=args.KD_WEIGHT),
-                                            temperature=args.TEMPERATURE, group_size=group, gather=False)
-        elif args.KD_type == "prob_loss":
-            loss, detail = fused_score_loss(q_vectors, ctx_vectors, ["nll_local", "ce_local"], teacher=relevance_logits,
-                                            weights=dict(nll_local=args.CE_WEIGHT, ce_local=args.KD_WEIGHT),
-                                            temperature=args.TEMPERATURE, group_size=group, gather=False)
+        elif args.KD_type in self._SOFT:
+            soft = self._SOFT[args.KD_type]
+            alpha, beta = getattr(args, "DKD_alpha", None), getattr(args, "DKD_beta", None)
+            if args.KD_type == "DKD" and (alpha is None or beta is None):
+                raise ValueError("DKD loss need refer DKD_alpha and DKD_beta in args")  # the reference prints this and exits
+            loss, detail = fused_score_loss(q_vectors, ctx_vectors, ["nll_local", soft], teacher=relevance_logits,
+                                            weights={"nll_local": args.CE_WEIGHT, soft: args.KD_WEIGHT},
+                                            temperature=args.TEMPERATURE, group_size=group, gather=False,
+                                            dkd_alpha=alpha or 1.0, dkd_beta=beta or 1.0)
         else:
-            raise NotImplementedError(f"KD_type={args.KD_type!r}: fused kernel covers KD_softmax and prob_loss")
+            raise ValueError("no such type of KD loss,please check KD_type")
         if LwF:
-            with torch.no_grad():
+            if args.KD_type not in ("KD_softmax", "KD_logit"):  # kd_loss has no other branch (UnboundLocalError there)
+                raise ValueError(f"LwF needs KD_type KD_softmax or KD_logit, got {args.KD_type!r}")
+            with torch.no_grad():  # the frozen copy's scores are targets only (its gradients feed no optimizer)
                 ori = torch.einsum("bh,bdh->bd", ori_q_vector.float(), ori_ctx_vectors.float().reshape(nq, group, -1))
-            lwf, _ = fused_score_loss(q_vectors, ctx_vectors, ["kd_local"], teacher=ori, temperature=args.TEMPERATURE,
-                                      group_size=group, gather=False)
+            lwf, _ = fused_score_loss(q_vectors, ctx_vectors, [self._SOFT[args.KD_type]], teacher=ori,
+                                      temperature=args.TEMPERATURE, group_size=group, gather=False)
             loss = loss + args.LwF_WEIGHT * lwf
         correct_predictions_count = detail[7].round().to(torch.int64)  # local rows whose positive (column 0) ranks first
         if loss_scale:
@@ -233,7 +248,9 @@ class _PairDistillFn(torch.autograd.Function):
             cfg = _lib.PairCfg(GQ=GQ, GC=GC, H=H, q_begin=rank * nq, q_count=nq, c_begin=rank * nc, c_count=nc,
                                w_nll_a=w.get("nll_a", 0.0), w_nll_b=w.get("nll_b", 0.0), w_kl_b2a=w.get("kl_b2a", 0.0),
                                w_kl_a2b=w.get("kl_a2b", 0.0), temperature=opts.get("temperature", 1.0), grad_scale=1.0,
-                               w_kd_b2a=w.get("kd_b2a", 0.0))
+                               w_kd_b2a=w.get("kd_b2a", 0.0), w_mse_b2a=w.get("mse_b2a", 0.0),
+                               w_dkd_b2a=w.get("dkd_b2a", 0.0), dkd_alpha=opts.get("dkd_alpha", 1.0),
+                               dkd_beta=opts.get("dkd_beta", 1.0))
             ws = torch.empty(lib.simx_pair_distill_workspace_bytes(GQ, GC, H), dtype=torch.uint8, device=dev)
             losses = torch.empty(8, dtype=torch.float32, device=dev)
             grads = [torch.empty_like(loc[0]), torch.empty_like(loc[1]),
@@ -253,27 +270,69 @@ class _PairDistillFn(torch.autograd.Function):
 
 
 def fused_pair_distill(q_a, c_a, q_b, c_b, weights: dict, *, temperature: float = 1.0, group_size: Optional[int] = None,
-                       gather: bool = True, group=None, pos_idx=None):
+                       gather: bool = True, group=None, pos_idx=None, dkd_alpha: float = 1.0, dkd_beta: float = 1.0):
     """a = student, b = teacher (local embeddings, all-gathered inside).  weights: nll_a, nll_b, kl_b2a (teacher targets ->
     student), kl_a2b.  -> (total with autograd into all four inputs, detail [8] = PAIR_FIELDS + pad)."""
     opts = dict(weights=dict(weights), temperature=float(temperature), group_size=group_size, gather=gather, group=group,
-                pos_idx=pos_idx)
+                pos_idx=pos_idx, dkd_alpha=float(dkd_alpha), dkd_beta=float(dkd_beta))
     return _PairDistillFn.apply(q_a, c_a, q_b, c_b, opts)
+
+
+class _EmbedMseFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, a, b):
+        lib = _lib.lib()
+        if a.device.type != "cuda":
+            raise RuntimeError("embed_mse needs CUDA tensors (no CPU fallback)")
+        with torch.cuda.device(a.device):
+            _lib.require_device()
+            a32 = a.detach().to(torch.float32).contiguous()
+            b32 = b.detach().to(device=a.device, dtype=torch.float32).contiguous()
+            if a32.shape != b32.shape:
+                raise ValueError(f"embed_mse: shapes differ {tuple(a32.shape)} vs {tuple(b32.shape)}")
+            loss = torch.zeros((), dtype=torch.float32, device=a.device)
+            grad = torch.empty_like(a32)
+            _lib.check(lib.simx_embed_mse(a32.data_ptr(), b32.data_ptr(), a32.numel(), 1.0, loss.data_ptr(), grad.data_ptr(),
+                                          torch.cuda.current_stream(a.device).cuda_stream), "simx_embed_mse")
+        ctx.grad = grad
+        return loss
+
+    @staticmethod
+    def backward(ctx, g):
+        return ctx.grad * g, None
+
+
+def embed_mse(student: torch.Tensor, teacher: torch.Tensor) -> torch.Tensor:
+    """0.5 * MSELoss(mean)(student, teacher) on raw embeddings, gradient into `student` only (one half of bi_logit)"""
+    return _EmbedMseFn.apply(student, teacher)
 
 
 class BiEncoderKDLoss(object):
     """PROD/ProD_KD/model/models.py:970-1038: DE -> DE distillation on the (already gathered) global matrix,
-    CE_WEIGHT * NLL + KD_WEIGHT * T^2 KL(softmax(teacher/T) || softmax(student/T)); KD_type 'KD_softmax'."""
+    CE_WEIGHT * NLL + KD_WEIGHT * soft, soft = KD_softmax (T^2 KL(softmax(teacher/T) || softmax(student/T))), KD_logit
+    (0.5 MSE of the score matrices), DKD, or Bi_logit (0.5 MSE of the raw embeddings, models.py:1062-1067)."""
 
     def calc(self, args, q_vectors, ctx_vectors, teacher_q_vector, teacher_ctxs_vector, positive_idx_per_question: list,
              hard_negative_idx_per_question: list = None, loss_scale: float = None):
         if teacher_q_vector is None or teacher_ctxs_vector is None:
             return BiEncoderNllLoss().calc(q_vectors, ctx_vectors, positive_idx_per_question, loss_scale=loss_scale)
-        if args.KD_type != "KD_softmax":
-            raise NotImplementedError(f"KD_type={args.KD_type!r}: the fused kernel covers KD_softmax")
+        if args.KD_type == "Bi_logit":
+            loss, correct_predictions_count = BiEncoderNllLoss().calc(q_vectors, ctx_vectors, positive_idx_per_question)
+            soft = embed_mse(q_vectors, teacher_q_vector) + embed_mse(ctx_vectors, teacher_ctxs_vector)
+            loss = args.CE_WEIGHT * loss + args.KD_WEIGHT * soft
+            if loss_scale:
+                loss = loss * loss_scale
+            return loss, correct_predictions_count
+        key = {"KD_softmax": "kd_b2a", "KD_logit": "mse_b2a", "DKD": "dkd_b2a"}.get(args.KD_type)
+        if key is None:
+            raise ValueError("no such type of KD loss,please check KD_type")
+        alpha, beta = getattr(args, "DKD_alpha", None), getattr(args, "DKD_beta", None)
+        if args.KD_type == "DKD" and (alpha is None or beta is None):
+            raise ValueError("DKD loss need refer DKD_alpha and DKD_beta in args")
         loss, detail = fused_pair_distill(q_vectors, ctx_vectors, teacher_q_vector.detach(), teacher_ctxs_vector.detach(),
-                                          dict(nll_a=args.CE_WEIGHT, kd_b2a=args.KD_WEIGHT), temperature=args.TEMPERATURE,
-                                          gather=False, pos_idx=positive_idx_per_question)
+                                          {"nll_a": args.CE_WEIGHT, key: args.KD_WEIGHT}, temperature=args.TEMPERATURE,
+                                          gather=False, pos_idx=positive_idx_per_question, dkd_alpha=alpha or 1.0,
+                                          dkd_beta=beta or 1.0)
         correct_predictions_count = detail[6].round().to(torch.int64)
         if loss_scale:
             loss = loss * loss_scale
