@@ -26,7 +26,8 @@ from torch import nn
 from .encoder import B200EncoderBase, EncoderConfig
 from .losses import BiEncoderNllLoss, CrossBERTKDLoss, simans_distill_loss  # noqa: F401  (re-exported: reference names)
 
-__all__ = ["HFBertEncoder", "HFDistilBertEncoder", "BiBertEncoder", "Reranker", "BiEncoderNllLoss", "CrossBERTKDLoss",
+__all__ = ["HFBertEncoder", "HFDistilBertEncoder", "BiBertEncoder", "Reranker", "ProdReranker", "BiEncoderNllLoss",
+           "CrossBERTKDLoss",
            "simans_distill_loss", "dot_product_scores", "init_weights"]
 
 
@@ -292,3 +293,25 @@ class Reranker(nn.Module):
     def _forward(self, input_ids, attention_mask):
         _, pooled, _ = self.encoder(input_ids=input_ids, attention_mask=attention_mask, _want_sequence=False)
         return self.qa_classifier(pooled)  # == qa_classifier(sequence_output[:, 0, :])
+
+
+class ProdReranker(Reranker):
+    """PROD's cross-encoder teacher (PROD/ProD_KD/model/models.py:1232-1254): the SimANS Reranker plus a 2-way `binary`
+    head on the same [CLS] row; forward returns (binary_logits [N, M, 2], relevance_logits [N, M], None).  Exported as
+    `Reranker` by simxns_b200.prod_models (the drop-in for PROD's `model/models.py`)."""
+
+    def __init__(self, encoder: nn.Module, hidden_size):
+        nn.Module.__init__(self)
+        self.encoder = encoder
+        self.binary = nn.Linear(hidden_size, 2)
+        self.qa_classifier = nn.Linear(hidden_size, 1)
+        init_weights([self.binary, self.qa_classifier])
+
+    def forward(self, input_ids: T, attention_mask: T):
+        N, M, L = input_ids.size()
+        binary_logits, relevance_logits, _ = self._forward(input_ids.view(N * M, L), attention_mask.view(N * M, L))
+        return binary_logits.view(N, M, 2), relevance_logits.view(N, M), None
+
+    def _forward(self, input_ids, attention_mask):
+        _, pooled, _ = self.encoder(input_ids=input_ids, attention_mask=attention_mask, _want_sequence=False)
+        return self.binary(pooled), self.qa_classifier(pooled), None

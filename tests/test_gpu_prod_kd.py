@@ -132,3 +132,29 @@ def test_global_mse_dkd_local_slices_vs_oracle():
     assert abs(losses[7].item() - (ref["mse_b2a"] + ref["dkd_b2a"])) < 1e-4 * max(1.0, ref["mse_b2a"] + ref["dkd_b2a"])
     assert np.abs(dq.cpu().numpy() - dQ).max() < 1e-5 * max(1.0, np.abs(dQ).max())
     assert np.abs(dc.cpu().numpy() - dC).max() < 1e-5 * max(1.0, np.abs(dC).max())
+
+
+def test_prod_reranker_binary_head_vs_oracle():
+    """PROD's Reranker (models.py:1232-1254): (binary_logits [N,M,2], relevance_logits [N,M], None) from the [CLS] row"""
+    from oracle import bert_numpy as bn
+    from simxns_b200.encoder import EncoderConfig
+    from simxns_b200.prod_models import HFBertEncoder, Reranker
+
+    cfg = bn.bert_config(num_layers=2, hidden=128, heads=2, intermediate=256, vocab=300, max_pos=64)
+    params = bn.synth_params(cfg, seed=8)
+    ec = EncoderConfig(num_layers=2, hidden=128, heads=2, intermediate=256, vocab=300, max_pos=64)
+    enc = HFBertEncoder(ec, precision=_lib.PREC_BF16X3)
+    enc.load_state_dict({k: torch.from_numpy(v) for k, v in params.items()})
+    rr = Reranker(enc, 128).cuda()
+    assert sorted(k for k in rr.state_dict() if not k.startswith("encoder.")) == [
+        "binary.bias", "binary.weight", "qa_classifier.bias", "qa_classifier.weight"]
+    ids, mask = bn.synth_tokens(6, 40, cfg["vocab"], seed=2, ragged=True, min_len=5)
+    cls = bn.EncoderOracle(cfg, params).forward(ids, mask)["cls"][:, -1]
+    b, r, none = rr(cu(ids.reshape(2, 3, 40)), cu(mask.reshape(2, 3, 40)))
+    assert none is None and tuple(b.shape) == (2, 3, 2) and tuple(r.shape) == (2, 3)
+    wb, bb = rr.binary.weight.detach().cpu().double().numpy(), rr.binary.bias.detach().cpu().double().numpy()
+    wq, bq = rr.qa_classifier.weight.detach().cpu().double().numpy(), rr.qa_classifier.bias.detach().cpu().double().numpy()
+    assert np.abs(b.detach().cpu().numpy().reshape(6, 2) - (cls @ wb.T + bb)).max() < 1e-4
+    assert np.abs(r.detach().cpu().numpy().reshape(6) - (cls @ wq.T + bq)[:, 0]).max() < 1e-4
+    (b.sum() + r.sum()).backward()
+    assert rr.binary.weight.grad is not None and enc.embeddings.word_embeddings.weight.grad is not None
