@@ -98,28 +98,6 @@ embed_ln_kernel(const int64_t* __restrict__ ids, int T, int S, int H, int vocab,
 }
 
 template <int NP>
-__global__ void __launch_bounds__(ROW_THREADS)
-ln_fwd_kernel(const bf16* __restrict__ z, int T, int H, const float* __restrict__ gamma,
-              const float* __restrict__ beta, float eps, bf16* x, long ps) {
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int row = blockIdx.x * ROW_WARPS + warp;
-  if (row >= T) return;
-  float v[MAXC][8];
-#pragma unroll
-  for (int c = 0; c < MAXC; ++c) {
-    const int col = c * 256 + lane * 8;
-    if (col < H) plane_load8<NP>(z + (long)row * H + col, ps, v[c]);
-  }
-  ln_row_store<NP>(v, H, lane, gamma, beta, eps, x + (long)row * H, ps);
-}
-
-// ------------------------------------------------------------------------------------------------
-// LayerNorm backward.  dz = rstd * (g*dy - mean(g*dy) - xhat * mean(g*dy*xhat));
-// dgamma += sum dy*xhat, dbeta += sum dy, and (optionally) dbias += sum dz  — the bias gradient of the GEMM that
-// produced z (BertSelfOutput.dense / BertOutput.dense), so that GEMM needs no separate column-sum pass.
-// Each block walks rows with a grid stride and keeps its partial column sums in registers.
-// ------------------------------------------------------------------------------------------------
-template <int NP>
 __device__ __forceinline__ void unpack8(const uint4 (&raw)[NP], float (&v)[8]) {
 #pragma unroll
   for (int q = 0; q < NP; ++q) {
@@ -133,13 +111,89 @@ __device__ __forceinline__ void unpack8(const uint4 (&raw)[NP], float (&v)[8]) {
   }
 }
 
-// NC = ceil(H / 256) chunks per lane.  The next row's z and dy are prefetched (raw 16-byte loads) while the current
-// row is reduced, so each warp keeps two rows of HBM traffic in flight.
+// A warp owns `rpw` consecutive rows: gamma / beta are read once into registers (re-reading them per row made the
+// kernel L1-bound: ncu l1tex 86 %, DRAM 55 %), and the next row's 16-byte loads are in flight while the current row is
+// reduced.  NC = ceil(H / 256) chunks per lane.
 template <int NP, int NC>
 __global__ void __launch_bounds__(ROW_THREADS)
+ln_fwd_kernel(const bf16* __restrict__ z, int T, int H, const float* __restrict__ gamma,
+              const float* __restrict__ beta, float eps, bf16* x, long ps, int rpw) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const long r0 = ((long)blockIdx.x * ROW_WARPS + warp) * rpw;
+  if (r0 >= T) return;
+  const long r1 = min((long)T, r0 + rpw);
+  float g[NC][8], b[NC][8];
+#pragma unroll
+  for (int c = 0; c < NC; ++c) {
+    const int col = c * 256 + lane * 8;
+    if (col < H) {
+      ld8f(gamma + col, g[c]);
+      ld8f(beta + col, b[c]);
+    }
+  }
+  uint4 nxt[NC][NP];
+  auto fetch = [&](long r) {
+#pragma unroll
+    for (int c = 0; c < NC; ++c) {
+      const int col = c * 256 + lane * 8;
+      if (col < H) {
+#pragma unroll
+        for (int q = 0; q < NP; ++q) nxt[c][q] = *reinterpret_cast<const uint4*>(z + q * ps + r * H + col);
+      }
+    }
+  };
+  fetch(r0);
+  const float invH = 1.f / H;
+  for (long r = r0; r < r1; ++r) {
+    float v[NC][8];
+    float s = 0.f;
+#pragma unroll
+    for (int c = 0; c < NC; ++c)
+      if (c * 256 + lane * 8 < H) {
+        unpack8<NP>(nxt[c], v[c]);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) s += v[c][i];
+      }
+    if (r + 1 < r1) fetch(r + 1);
+    const float mean = warp_sum(s) * invH;
+    float q2 = 0.f;
+#pragma unroll
+    for (int c = 0; c < NC; ++c)
+      if (c * 256 + lane * 8 < H)
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          v[c][i] -= mean;
+          q2 += v[c][i] * v[c][i];
+        }
+    const float rstd = rsqrtf(warp_sum(q2) * invH + eps);
+#pragma unroll
+    for (int c = 0; c < NC; ++c) {
+      const int col = c * 256 + lane * 8;
+      if (col < H) {
+        float y[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) y[i] = v[c][i] * rstd * g[c][i] + b[c][i];
+        split_store8<NP>(x + r * H + col, ps, y);
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// LayerNorm backward.  dz = rstd * (g*dy - mean(g*dy) - xhat * mean(g*dy*xhat));
+// dgamma += sum dy*xhat, dbeta += sum dy, and (optionally) dbias += sum dz  — the bias gradient of the GEMM that
+// produced z (BertSelfOutput.dense / BertOutput.dense), so that GEMM needs no separate column-sum pass.
+// Each block walks rows with a grid stride and keeps its partial column sums in registers.
+// ------------------------------------------------------------------------------------------------
+// NC = ceil(H / 256) chunks per lane.  The next row's z and dy are prefetched (raw 16-byte loads) while the current
+// row is reduced, so each warp keeps two rows of HBM traffic in flight.
+constexpr int LNB_THREADS = 384;  // 12 warps x ~168 registers: the whole register file of an SM (8 warps left it half idle:
+constexpr int LNB_WARPS = LNB_THREADS / 32;  // ncu warps_active 12.5 %, DRAM 53 %)
+template <int NP, int NC>
+__global__ void __launch_bounds__(LNB_THREADS)
 ln_bwd_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ z, int T, int H, const float* __restrict__ gamma,
               float eps, bf16* dz, long ps, float* dgamma, float* dbeta, float* dbias) {
-  __shared__ float red[ROW_WARPS][32 * 8 + 8];
+  __shared__ float red[LNB_WARPS][32 * 8 + 8];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   float ag[NC][8], ab[NC][8], ad[NC][8];
 #pragma unroll
@@ -147,8 +201,8 @@ ln_bwd_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ z, int T, in
 #pragma unroll
     for (int i = 0; i < 8; ++i) ag[c][i] = ab[c][i] = ad[c][i] = 0.f;
   const float invH = 1.f / H;
-  const int stride = gridDim.x * ROW_WARPS;
-  int row = blockIdx.x * ROW_WARPS + warp;
+  const int stride = gridDim.x * LNB_WARPS;
+  int row = blockIdx.x * LNB_WARPS + warp;
   uint4 zr[NC][NP], dr[NC][NP];
   auto fetch = [&](int r) {
 #pragma unroll
@@ -238,10 +292,10 @@ ln_bwd_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ z, int T, in
         red[warp][lane * 8 + i] = which == 0 ? ag[c][i] : (which == 1 ? ab[c][i] : ad[c][i]);
       __syncthreads();
       const int col = c * 256 + threadIdx.x;
-      if (col < H) {
+      if (threadIdx.x < 256 && col < H) {
         float t = 0.f;
 #pragma unroll
-        for (int w = 0; w < ROW_WARPS; ++w) t += red[w][threadIdx.x];
+        for (int w = 0; w < LNB_WARPS; ++w) t += red[w][threadIdx.x];
         atomicAdd(outs[which] + col, t);
       }
     }
@@ -407,8 +461,17 @@ int ln_fwd(int np, const bf16* z, int T, int H, const float* gamma, const float*
            cudaStream_t st) {
   ProfScope prof("ln_fwd", 0, (double)T * H * 4.0 * np, st);
   SIMX_CHECK(H % 8 == 0 && H <= 256 * MAXC, SIMX_ERR_INVALID, "hidden size %d unsupported", H);
-  const int grid = (T + ROW_WARPS - 1) / ROW_WARPS;
-  SIMX_NP_DISPATCH(np, (ln_fwd_kernel<kNP><<<grid, ROW_THREADS, 0, st>>>(z, T, H, gamma, beta, eps, x, ps)));
+  // rows per warp: up to 8 (amortises the gamma / beta loads) while keeping >= ~8 blocks per SM in the grid
+  const int rpw = (int)max(1L, min(8L, (long)T / ((long)num_sms() * 8 * ROW_WARPS)));
+  const int grid = (int)(((long)T + (long)ROW_WARPS * rpw - 1) / ((long)ROW_WARPS * rpw));
+  const int nc = (H + 255) / 256;
+#define SIMX_LN_FWD(NP_, NC_) ln_fwd_kernel<NP_, NC_><<<grid, ROW_THREADS, 0, st>>>(z, T, H, gamma, beta, eps, x, ps, rpw)
+  if (np == 1) {
+    if (nc == 1) SIMX_LN_FWD(1, 1); else if (nc == 2) SIMX_LN_FWD(1, 2); else if (nc == 3) SIMX_LN_FWD(1, 3); else SIMX_LN_FWD(1, 4);
+  } else {
+    if (nc == 1) SIMX_LN_FWD(3, 1); else if (nc == 2) SIMX_LN_FWD(3, 2); else if (nc == 3) SIMX_LN_FWD(3, 3); else SIMX_LN_FWD(3, 4);
+  }
+#undef SIMX_LN_FWD
   SIMX_LAUNCH_CHECK();
   return SIMX_OK;
 }
@@ -417,11 +480,11 @@ int ln_bwd(int np, const bf16* dy, const bf16* z, int T, int H, const float* gam
            float* dgamma, float* dbeta, float* dbias, cudaStream_t st) {
   ProfScope prof("ln_bwd", 0, (double)T * H * 6.0 * np, st);
   SIMX_CHECK(H % 8 == 0 && H <= 256 * MAXC, SIMX_ERR_INVALID, "hidden size %d unsupported", H);
-  int grid = (T + ROW_WARPS - 1) / ROW_WARPS;
-  grid = min(grid, num_sms());  // ~175 registers/thread: one resident block per SM, persistent over rows
+  int grid = (T + LNB_WARPS - 1) / LNB_WARPS;
+  grid = min(grid, num_sms());  // ~168 registers/thread: one resident block per SM, persistent over rows
   const int nc = (H + 255) / 256;
 #define SIMX_LN_BWD(NP_, NC_) \
-  ln_bwd_kernel<NP_, NC_><<<grid, ROW_THREADS, 0, st>>>(dy, z, T, H, gamma, eps, dz, ps, dgamma, dbeta, dbias)
+  ln_bwd_kernel<NP_, NC_><<<grid, LNB_THREADS, 0, st>>>(dy, z, T, H, gamma, eps, dz, ps, dgamma, dbeta, dbias)
   if (np == 1) {
     if (nc == 1) SIMX_LN_BWD(1, 1); else if (nc == 2) SIMX_LN_BWD(1, 2); else if (nc == 3) SIMX_LN_BWD(1, 3); else SIMX_LN_BWD(1, 4);
   } else {
