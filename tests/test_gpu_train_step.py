@@ -1,0 +1,121 @@
+"""B200 (`-m gpu`): the co-training loop body (simxns_b200.train: retriever_step / teacher_step — fused KL loss, fused
+clip + transformers-flavoured AdamW, linear warm-up schedule, gradient accumulation) against the same loop written with
+the reference's own torch lines for the loss (co_training_marco_train.py:199-214, 231-233) and the optimizer oracle
+(oracle/optim_numpy.py) for clip_grad_norm_ / AdamW.  fp32-class precision: parameters after 4 micro-steps within 2e-5."""
+import copy
+import types
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from oracle import bert_numpy as bn
+from oracle import optim_numpy as on
+from simxns_b200 import _lib
+from simxns_b200.encoder import EncoderConfig
+from simxns_b200.models import BiBertEncoder, HFBertEncoder, Reranker
+from simxns_b200.train import get_linear_schedule_with_warmup, get_optimizer, retriever_step, teacher_step
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module", autouse=True)
+def _device():
+    assert torch.cuda.is_available()
+    torch.cuda.set_device(0)
+    _lib.require_device()
+
+
+EC = EncoderConfig(num_layers=2, hidden=128, heads=2, intermediate=256, vocab=400, max_pos=64)
+ARGS = types.SimpleNamespace(temperature_distill=2.0, scale_simmila=False, gradient_accumulation_steps=2, max_grad_norm=0.5,
+                             optimizer="adamW")
+LR, EPS, WD, WARM, TOTAL = 1e-3, 1e-8, 0.01, 1, 4
+
+
+def make_batches(n, nq=3, group=4):
+    out = []
+    for i in range(n):
+        q_ids, q_mask = bn.synth_tokens(nq, 12, EC.vocab, seed=10 + i, ragged=True)
+        p_ids, p_mask = bn.synth_tokens(nq * group, 24, EC.vocab, seed=50 + i, ragged=True, min_len=6)
+        ce_ids, ce_mask = bn.synth_tokens(nq * group, 32, EC.vocab, seed=90 + i, ragged=True, min_len=8)
+        t = lambda a: torch.from_numpy(a)
+        scores = torch.from_numpy((2 * np.random.RandomState(i).standard_normal((nq, group))).astype(np.float32))
+        out.append(dict(student=[t(q_ids), t(q_mask), t(p_ids), t(p_mask)],
+                        teacher=[t(ce_ids).view(nq, group, 32), t(ce_mask).view(nq, group, 32), scores]))
+    return out
+
+
+def oracle_tail(model, state, step_no, lr):
+    """clip_grad_norm_ + transformers.AdamW through the numpy oracle, written back into the model"""
+    named = list(model.named_parameters())
+    grads = [p.grad.detach().cpu().double().numpy() for _, p in named]
+    _, clipped = on.clip_grad_norm(grads, ARGS.max_grad_norm)
+    for (n, p), g in zip(named, clipped):
+        m, v = state.setdefault(n, (np.zeros(g.shape), np.zeros(g.shape)))
+        wd = 0.0 if ("bias" in n or "LayerNorm.weight" in n) else WD
+        new_p, m, v = on.adamw_hf(p.detach().cpu().double().numpy(), g, m, v, step_no, lr, eps=EPS, weight_decay=wd)
+        state[n] = (m, v)
+        p.data.copy_(torch.from_numpy(new_p).to(p.dtype))
+    model.zero_grad()
+
+
+def lr_at(k):  # get_linear_schedule_with_warmup after k scheduler steps
+    return LR * (k / max(1, WARM) if k < WARM else max(0.0, (TOTAL - k) / max(1, TOTAL - WARM)))
+
+
+def assert_same_params(a, b, tol=2e-5):
+    for (n, p), (_, q) in zip(a.named_parameters(), b.named_parameters()):
+        scale = max(1e-3, q.abs().max().item())
+        assert (p - q).abs().max().item() < tol * scale, n
+
+
+def test_retriever_steps_match_reference_loop_with_oracle_optimizer():
+    torch.manual_seed(0)
+    model = BiBertEncoder(None, question_model=HFBertEncoder(EC, precision=_lib.PREC_BF16X3),
+                          ctx_model=HFBertEncoder(EC, precision=_lib.PREC_BF16X3)).cuda()
+    ref = copy.deepcopy(model)
+    opt = get_optimizer(ARGS, model, weight_decay=WD, lr=LR, eps=EPS)
+    sched = get_linear_schedule_with_warmup(opt, WARM, TOTAL)
+    assert [len(g["params"]) for g in opt.param_groups] == [2 * (3 + 6 * 2 + 1), 2 * (2 + 10 * 2 + 1)]  # decay / no-decay
+    state, updates = {}, 0
+    for step, batch in enumerate(make_batches(4), 1):
+        out = retriever_step(ARGS, model, None, batch, opt, sched, step)
+        # the reference's lines (co_training_marco_train.py:198-222) on the twin model
+        ref.train()
+        q, c = ref(*[t.cuda() for t in batch["student"]])
+        sim = torch.einsum("bh,bdh->bd", q, c.reshape(q.size(0), c.size(0) // q.size(0), -1))
+        p_s = F.softmax(sim, dim=1)
+        p_t = F.softmax(batch["teacher"][2].cuda() / ARGS.temperature_distill, dim=1)
+        distill = torch.nn.KLDivLoss(reduction="batchmean")((p_s + 1e-7).log(), p_t)
+        (distill / ARGS.gradient_accumulation_steps).backward()
+        assert abs(out["distill_loss"].item() - distill.item()) < 1e-4
+        if step % ARGS.gradient_accumulation_steps == 0:
+            updates += 1
+            oracle_tail(ref, state, updates, lr_at(updates - 1))
+            assert out["grad_norm"] is not None and out["grad_norm"].item() > ARGS.max_grad_norm  # the clip was active
+            assert_same_params(model, ref)
+            assert all(p.grad is None or float(p.grad.abs().max()) == 0.0 for p in model.parameters())
+        else:
+            assert out["grad_norm"] is None
+    assert updates == 2 and abs(opt.param_groups[0]["lr"] - lr_at(2)) < 1e-12
+
+
+def test_teacher_steps_match_reference_loop_with_oracle_optimizer():
+    torch.manual_seed(1)
+    args = copy.copy(ARGS)
+    args.gradient_accumulation_steps = 1
+    teacher = Reranker(HFBertEncoder(EC, precision=_lib.PREC_BF16X3), EC.hidden).cuda()
+    ref = copy.deepcopy(teacher)
+    opt = get_optimizer(args, teacher, weight_decay=WD, lr=LR, eps=EPS)
+    sched = get_linear_schedule_with_warmup(opt, WARM, TOTAL)
+    state = {}
+    for step, batch in enumerate(make_batches(3), 1):
+        out = teacher_step(args, teacher, batch, opt, sched, step)
+        ref.train()
+        logits = ref(batch["teacher"][0].cuda(), batch["teacher"][1].cuda())
+        loss = torch.nn.CrossEntropyLoss()(logits, torch.zeros(logits.size(0), dtype=torch.long, device="cuda"))
+        loss.backward()
+        assert abs(out["contr_loss"].item() - loss.item()) < 1e-4
+        oracle_tail(ref, state, step, lr_at(step - 1))
+        assert_same_params(teacher, ref)

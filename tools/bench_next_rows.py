@@ -176,9 +176,46 @@ def bench_optimizer(args):
                 launches_fused=2, note="torch arm = torch.nn.utils.clip_grad_norm_ + torch.optim.AdamW (foreach) on the same GPU")
 
 
+def bench_train_full(args):
+    """the whole retriever micro-step of the co-training loop INCLUDING the optimizer tail (simxns_b200.train.retriever_step:
+    both towers fwd, fused SimANS KL loss against resident teacher scores, bwd, fused clip + AdamW, scheduler, zero_grad)"""
+    import types
+
+    import torch
+
+    from simxns_b200 import _lib
+    from simxns_b200.encoder import EncoderConfig
+    from simxns_b200.models import BiBertEncoder, HFBertEncoder
+    from simxns_b200.train import get_linear_schedule_with_warmup, get_optimizer, retriever_step
+
+    ec = EncoderConfig(num_layers=args.layers)
+    torch.manual_seed(0)
+    model = BiBertEncoder(None, question_model=HFBertEncoder(ec, precision=_lib.PREC_BF16),
+                          ctx_model=HFBertEncoder(ec, precision=_lib.PREC_BF16)).cuda()
+    a = types.SimpleNamespace(temperature_distill=1.0, scale_simmila=False, gradient_accumulation_steps=1, max_grad_norm=1.0,
+                              optimizer="adamW")
+    opt = get_optimizer(a, model, weight_decay=0.01, lr=1e-5, eps=1e-8)
+    sched = get_linear_schedule_with_warmup(opt, 10, 1000)
+    nq, group = 128, 16
+    q = torch.randint(1000, ec.vocab, (nq, 32), device="cuda")
+    p = torch.randint(1000, ec.vocab, (nq * group, 128), device="cuda")
+    batch = dict(student=[q, torch.ones_like(q), p, torch.ones_like(p)],
+                 teacher=[None, None, 3 * torch.randn(nq, group, device="cuda")])
+    state = dict(step=0)
+
+    def step():
+        state["step"] += 1
+        retriever_step(a, model, None, batch, opt, sched, state["step"])
+
+    ms = timed(step, args.steps)
+    return dict(workload="train_full: retriever micro-step incl. optimizer (128 q x 16 p, q 32 / p 128, bert-base, SimANS KL loss, "
+                         "fused clip + AdamW)", ms_per_step=ms, pairs_per_s=nq * group / (ms * 1e-3),
+                note="headline bench.py excludes the optimizer (SURVEY 8d); this is the loop body end to end")
+
+
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("--only", default="encode,search,teacher,optimizer")
+    ap.add_argument("--only", default="encode,search,teacher,optimizer,train_full")
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--layers", type=int, default=12)
     ap.add_argument("--encode-batches", type=int, default=8)
@@ -195,7 +232,8 @@ def main():
     _lib.require_device()
     results = []
     for name in args.only.split(","):
-        r = dict(encode=bench_encode, search=bench_search, teacher=bench_teacher, optimizer=bench_optimizer)[name](args)
+        r = dict(encode=bench_encode, search=bench_search, teacher=bench_teacher, optimizer=bench_optimizer,
+                 train_full=bench_train_full)[name](args)
         for x in (r if isinstance(r, list) else [r]):
             print(json.dumps(x), flush=True)
             results.append(x)
