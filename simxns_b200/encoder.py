@@ -190,10 +190,14 @@ class B200EncoderBase(nn.Module):
             if p.dtype != torch.float32 or not p.is_contiguous() or p.device != dev:
                 raise RuntimeError("encoder parameters must be contiguous fp32 tensors on one CUDA device")
 
-    def _weights(self, params) -> torch.Tensor:
-        """bf16 / split-bf16 GEMM operands, rebuilt whenever a master weight changed (optimizer step, load)."""
+    def _weights(self, params, force: bool = False) -> torch.Tensor:
+        """bf16 / split-bf16 GEMM operands of the fp32 master weights.  A TRAINING forward (`force`) always rebuilds them
+        (0.7 GB of traffic per BERT-base tower, ~0.1 % of a step): optimizers that update through `p.data` — the
+        transformers.AdamW of the reference drivers does (`p.data.addcdiv_`) — never bump `p._version`, so no host-side
+        key can see their updates.  Inference forwards reuse the buffer while (data_ptr, _version) are unchanged;
+        `invalidate_weights()` drops it after an out-of-band `.data` edit."""
         key = (self.precision,) + tuple((p.data_ptr(), p._version) for p in params)
-        if self._wbuf is None or key != self._wkey:
+        if self._wbuf is None or force or key != self._wkey:
             lib = _lib.lib()
             cfg = self._c_cfg()
             nbytes = lib.simx_encoder_weight_bytes(C.byref(cfg))
@@ -204,6 +208,9 @@ class B200EncoderBase(nn.Module):
                                                         stream), "simx_encoder_prepare_weights")
             self._wkey = key
         return self._wbuf
+
+    def invalidate_weights(self) -> None:
+        self._wkey = None
 
     def grad_slices(self) -> List[Tuple[int, int]]:
         if self._grad_slices is None:
@@ -248,7 +255,7 @@ class _EncoderFn(torch.autograd.Function):
             if S > min(ec.max_pos, 512):
                 raise ValueError(f"sequence length {S} exceeds min(max_position_embeddings={ec.max_pos}, 512)")
             needs_grad = any(ctx.needs_input_grad[4:])  # grad mode is always off inside Function.forward
-            wbuf = module._weights(params)
+            wbuf = module._weights(params, force=needs_grad)
             table = module._param_table(params)
             stream = torch.cuda.current_stream(dev).cuda_stream
             cls = torch.empty(B, ec.num_layers + 1, ec.hidden, dtype=torch.float32, device=dev)
