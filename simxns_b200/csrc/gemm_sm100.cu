@@ -54,7 +54,7 @@ struct GemmSmem {
   static constexpr uint32_t STG_OFF = STAGES * STAGE_BYTES;
   static constexpr uint32_t STG_BYTES = TS ? 16 * 4096 : 0;  // one [32 rows x 64 cols] bf16 box per epilogue warp
   static constexpr uint32_t BAR_OFF = STG_OFF + STG_BYTES;
-  static constexpr uint32_t BIAS_OFF = BAR_OFF + 256;
+  static constexpr uint32_t BIAS_OFF = BAR_OFF + 512;  // ring + TMEM barriers, then one barrier per epilogue warp (aux loads)
   static constexpr uint32_t BIAS_FLOATS = 3072;  // the whole bias vector lives in smem when N fits (else global loads)
   static constexpr uint32_t TOTAL = BIAS_OFF + BIAS_FLOATS * 4 + 1024;  // + alignment slack
 };
@@ -197,7 +197,8 @@ __device__ __forceinline__ void epilogue_chunk(const GemmParams& p, int row, int
 template <int BN, bool MN, int EPI, int NP, int CG>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_kernel(const GemmParams p, const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
-            const __grid_constant__ CUtensorMap mapOut, const __grid_constant__ CUtensorMap mapOut2) {
+            const __grid_constant__ CUtensorMap mapOut, const __grid_constant__ CUtensorMap mapOut2,
+            const __grid_constant__ CUtensorMap mapAux) {
   constexpr bool TS = kTmaStore<BN, MN, EPI, NP>;
   using L = GemmSmem<BN, TS, CG>;
   constexpr int TILE_M = GEMM_BM * CG;  // rows of one output tile (both CTAs of a pair)
@@ -215,6 +216,11 @@ gemm_kernel(const GemmParams p, const __grid_constant__ CUtensorMap mapA, const 
   uint64_t* tfull = bars + 2 * STAGES;      // [2]       MMA -> epilogue
   uint64_t* tempty = bars + 2 * STAGES + 2; // [2]       epilogue -> MMA
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
+  // staged epilogue with an aux operand: the warp's [32 x 64] aux box is TMA-loaded into its staging box (a lane reading
+  // its own row straight from global touches 32 different lines per instruction: the K = 768 GEMMs with a residual /
+  // GELU' operand ran 20 % behind the plain epilogue on L1 wavefronts)
+  constexpr bool kAuxTma = TS && EpiPre<EPI, NP>::kAux;
+  uint64_t* auxbar = bars + 2 * STAGES + 6;  // [16]
   float* sbias = nullptr;
   if constexpr (EpiPre<EPI, NP>::kBias) {
     if (p.N <= (int)L::BIAS_FLOATS) {
@@ -241,6 +247,7 @@ gemm_kernel(const GemmParams p, const __grid_constant__ CUtensorMap mapA, const 
     if constexpr (TS) {
       tma_prefetch_desc(&mapOut);
       if constexpr (EPI == SIMX_EPI_BIAS_GELU) tma_prefetch_desc(&mapOut2);
+      if constexpr (kAuxTma) tma_prefetch_desc(&mapAux);
     }
   }
   if (warp == 1 && lane == 0) {
@@ -252,6 +259,8 @@ gemm_kernel(const GemmParams p, const __grid_constant__ CUtensorMap mapA, const 
       mbar_init(&tfull[i], 1);
       mbar_init(&tempty[i], 16 * CG);  // every epilogue warp of the pair arrives on the LEADER's barrier
     }
+    if constexpr (kAuxTma)
+      for (int i = 0; i < 16; ++i) mbar_init(&auxbar[i], 1);
     fence_mbar_init();
   }
   if constexpr (CG == 2) cluster_sync_all();  // both CTAs alive before the pair-wide TMEM allocation
@@ -364,7 +373,15 @@ gemm_kernel(const GemmParams p, const __grid_constant__ CUtensorMap mapA, const 
       const int row = row_base + lane;
       const int col_base = nt * BN + part * CPW;
       EpiPre<EPI, NP> pre;
-      epi_prefetch<EPI, NP, CW>(p, row, col_base, pre);
+      if constexpr (!kAuxTma) epi_prefetch<EPI, NP, CW>(p, row, col_base, pre);
+      if constexpr (kAuxTma) {
+        // the previous tile's store must have finished READING the staging box before the aux tile lands in it
+        if (lane == 0) {
+          tma_store_wait_read<0>();
+          mbar_arrive_expect_tx(&auxbar[warp - 4], 4096);
+          tma_load_3d(&mapAux, &auxbar[warp - 4], smem + L::STG_OFF + (warp - 4) * 4096, col_base, row_base, 0);
+        }
+      }
       mbar_wait(&tfull[acc], acc_phase);
       tc_fence_after();
       const uint32_t t_addr = tmem_base + acc * BN + part * CPW + (static_cast<uint32_t>(quarter * 32) << 16);
@@ -389,7 +406,11 @@ gemm_kernel(const GemmParams p, const __grid_constant__ CUtensorMap mapA, const 
         const uint32_t stg_row = smem_u32(stg) + lane * 128;
         uint4 o2[EPI == SIMX_EPI_BIAS_GELU ? 8 : 1];
         // the previous tile's store must have finished READING the staging box before it is overwritten
-        if (lane == 0) tma_store_wait_read<0>();
+        if constexpr (kAuxTma) {
+          mbar_wait(&auxbar[warp - 4], it & 1);  // this tile's aux box has landed (one phase per tile)
+        } else {
+          if (lane == 0) tma_store_wait_read<0>();
+        }
         __syncwarp();
 #pragma unroll
         for (int c = 0; c < NCH; ++c) {
@@ -404,6 +425,7 @@ gemm_kernel(const GemmParams p, const __grid_constant__ CUtensorMap mapA, const 
 #pragma unroll
           for (int g = 0; g < 4; ++g) {
             const int j = c * 4 + g;  // 16-byte chunk index inside the 128-byte row
+            if constexpr (kAuxTma) pre.aux[0][g] = ld_shared_v4(stg_row + ((j ^ (lane & 7)) << 4));
             float f[8];
             epi_values<EPI, NP>(p, min(col_base + j * 8, p.N - 8), &v[g * 8], pre, g, sbias, f);
             uint4 o;
@@ -419,7 +441,9 @@ gemm_kernel(const GemmParams p, const __grid_constant__ CUtensorMap mapA, const 
             }
             st_shared_v4(stg_row + ((j ^ (lane & 7)) << 4), o);
           }
-          if (c + 1 < NCH) epi_prefetch<EPI, NP, CW>(p, row, col_base + (c + 1) * CW, pre);
+          if constexpr (!kAuxTma) {
+            if (c + 1 < NCH) epi_prefetch<EPI, NP, CW>(p, row, col_base + (c + 1) * CW, pre);
+          }
         }
         fence_proxy_async_smem();
         __syncwarp();
@@ -557,10 +581,11 @@ static int launch_gemm_cg(GemmParams p, const bf16* A, long lda, long a_ps, cons
     SIMX_TRY(make_tmap_bf16(&ma, A, p.M, p.K, planes, lda, a_ps, GEMM_BK));
     SIMX_TRY(make_tmap_bf16(&mb, B, p.N, p.K, planes, ldb, b_ps, GEMM_BK));
   }
-  CUtensorMap mo = ma, mo2 = ma;  // placeholders when the epilogue stores from registers
+  CUtensorMap mo = ma, mo2 = ma, mx = ma;  // placeholders when the epilogue stores from registers
   if constexpr (TS) {
     SIMX_TRY(make_tmap_bf16(&mo, p.out, p.N, p.M, 1, p.ldo, 0, 32));
     if constexpr (EPI == SIMX_EPI_BIAS_GELU) SIMX_TRY(make_tmap_bf16(&mo2, p.out2, p.N, p.M, 1, p.ldo, 0, 32));
+    if constexpr (EpiPre<EPI, NP>::kAux) SIMX_TRY(make_tmap_bf16(&mx, p.aux, p.N, p.M, 1, p.ldaux, 0, 32));
   }
   const int total = p.m_tiles * p.n_tiles * p.ksplit;
   const int grid = CG * min(total, num_sms() / CG);
@@ -576,7 +601,7 @@ static int launch_gemm_cg(GemmParams p, const bf16* A, long lda, long a_ps, cons
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  SIMX_CUDA(cudaLaunchKernelEx(&cfg, kern, p, ma, mb, mo, mo2));
+  SIMX_CUDA(cudaLaunchKernelEx(&cfg, kern, p, ma, mb, mo, mo2, mx));
   SIMX_LAUNCH_CHECK();
   return SIMX_OK;
 }

@@ -27,8 +27,11 @@ def main():
     ap.add_argument("case")
     ap.add_argument("--tokens", type=int, default=65536)
     ap.add_argument("--iters", type=int, default=3)
+    ap.add_argument("--epi", type=int, default=-1, help="override the epilogue (SIMX_EPI_*) of the case's shape")
     a = ap.parse_args()
     M, N, K, mn, epi = [a.tokens if v == "T" else v for v in CASES[a.case]]
+    if a.epi >= 0:
+        epi = a.epi
     lib = _lib.lib()
     dev = "cuda"
     A = torch.randn(K, M, device=dev).to(torch.bfloat16) if mn else torch.randn(M, K, device=dev).to(torch.bfloat16)
@@ -37,7 +40,7 @@ def main():
     aux = torch.randn(M, N, device=dev).to(torch.bfloat16)
     out = torch.empty(M, N, device=dev, dtype=torch.bfloat16)
     out2 = torch.empty(M, N, device=dev, dtype=torch.bfloat16)
-    outf = torch.zeros(M, N, device=dev) if epi == _lib.EPI_ATOMIC_F32 else torch.zeros(8, device=dev)
+    outf = torch.zeros(M, N, device=dev) if epi == _lib.EPI_ATOMIC_F32 else torch.zeros(N, device=dev)  # EPI_MUL: column sums
     lda, ldb = (M, N) if mn else (K, K)
     ks = 1
     if mn:
@@ -54,7 +57,7 @@ def main():
     evs[1].record()
     torch.cuda.synchronize()
     ms = evs[0].elapsed_time(evs[1]) / a.iters
-    print(f"{a.case}: M={M} N={N} K={K} {ms:.3f} ms  {2.0 * M * N * K / ms / 1e9:.1f} TFLOP/s")
+    print(f"{a.case} epi={epi}: M={M} N={N} K={K} {ms:.3f} ms  {2.0 * M * N * K / ms / 1e9:.1f} TFLOP/s")
 
 
 if __name__ == "__main__":
