@@ -172,6 +172,134 @@ attn_fwd_tc_kernel(const AttnTcParams p, const __grid_constant__ CUtensorMap map
 }
 
 // -------------------------------------------------------------------------------------------------
+// Forward for 128 < S <= 256 (cross-encoder inputs of 160 tokens, PROD's 144-token passages): one CTA per
+// (head, sequence, 128-query tile); both 128-key tiles of K and V are resident, S[128, 256] lives in 256 TMEM columns and
+// O re-uses the first 64 of them once P has been staged.  smem: [Q][K0][K1][pad][V0][V1] = 96 KB, P (128 x 256 bf16)
+// overwrites the first four tiles -> two CTAs per SM.
+__global__ void __launch_bounds__(128, 2)
+attn_fwd_tc2_kernel(const AttnTcParams p, const __grid_constant__ CUtensorMap map_qkv,
+                    const __grid_constant__ CUtensorMap map_ctx) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  const uint32_t sQ = smem_u32(smem), sK = sQ + TILE, sV = sQ + 4 * TILE;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 6 * TILE);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 4);
+  float* bias = reinterpret_cast<float*>(smem + 6 * TILE + 64);  // [256]
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int h = blockIdx.x, b = blockIdx.y, q0 = blockIdx.z * 128, S = p.S;
+
+  if (tid == 0) {
+    tma_prefetch_desc(&map_qkv);
+    tma_prefetch_desc(&map_ctx);
+    mbar_init(&bars[0], 1);
+    mbar_init(&bars[1], 1);
+    mbar_init(&bars[2], 1);
+    fence_mbar_init();
+  }
+  if (warp == 1) tmem_alloc<1>(tmem_slot, 256);
+  for (int k = tid; k < 256; k += 128)
+    bias[k] = (k < S && (p.mask == nullptr || p.mask[(long)b * S + k] != 0)) ? 0.f : TC_NEG;
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+
+  if (tid == 0) {
+    mbar_arrive_expect_tx(&bars[0], 5 * TILE);
+    tma_load_3d(&map_qkv, &bars[0], smem, h * 64, q0, b);                            // Q rows q0 ..
+    tma_load_3d(&map_qkv, &bars[0], smem + TILE, p.H + h * 64, 0, b);                // K keys 0..127
+    tma_load_3d(&map_qkv, &bars[0], smem + 2 * TILE, p.H + h * 64, 128, b);          // K keys 128..255 (zero-filled >= S)
+    tma_load_3d(&map_qkv, &bars[0], smem + 4 * TILE, 2 * p.H + h * 64, 0, b);        // V
+    tma_load_3d(&map_qkv, &bars[0], smem + 5 * TILE, 2 * p.H + h * 64, 128, b);
+    mbar_wait(&bars[0], 0);
+    tc_fence_after();
+    constexpr uint32_t idesc = make_idesc_bf16(128, 128, false, false);
+#pragma unroll
+    for (int t = 0; t < 2; ++t)
+#pragma unroll
+      for (int k = 0; k < 4; ++k) umma_bf16<1>(tmem + t * 128, desc_k(sQ, k), desc_k(sK + t * TILE, k), idesc, k != 0);
+    umma_commit<1>(&bars[1]);
+  }
+  mbar_wait(&bars[1], 0);
+  tc_fence_after();
+
+  const int row = warp * 32 + lane;
+  const uint32_t taddr = tmem + (static_cast<uint32_t>(warp * 32) << 16);
+  const float sl2 = 0.125f * TC_LOG2E;
+  float m = TC_NEG;
+#pragma unroll 1
+  for (int c = 0; c < 8; ++c) {
+    uint32_t v[32];
+    tmem_ld_32x32(taddr + c * 32, v);
+    tmem_ld_wait();
+#pragma unroll
+    for (int i = 0; i < 32; ++i) m = fmaxf(m, fmaf(__uint_as_float(v[i]), sl2, bias[c * 32 + i]));
+  }
+  float l = 0.f;
+  // thread r only ever reads TMEM lane r and writes smem row r; the tiles P overwrites (Q, K0, K1, pad) were consumed by
+  // the S MMAs, which completed before bars[1] fired
+#pragma unroll 1
+  for (int c = 0; c < 8; ++c) {
+    uint32_t v[32];
+    tmem_ld_32x32(taddr + c * 32, v);
+    tmem_ld_wait();
+    uint32_t pk[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+      const float p0 = ex2(fmaf(__uint_as_float(v[2 * i]), sl2, bias[c * 32 + 2 * i]) - m);
+      const float p1 = ex2(fmaf(__uint_as_float(v[2 * i + 1]), sl2, bias[c * 32 + 2 * i + 1]) - m);
+      l += p0 + p1;
+      pk[i] = pack_bf16x2(p0, p1);
+    }
+#pragma unroll
+    for (int g = 0; g < 4; ++g)
+      st_shared_v4(sQ + p_off(row, c * 4 + g), make_uint4(pk[4 * g], pk[4 * g + 1], pk[4 * g + 2], pk[4 * g + 3]));
+  }
+  if (q0 + row < S && p.lse2 != nullptr) p.lse2[((long)b * p.heads + h) * S + q0 + row] = m + log2f(l);
+  fence_proxy_async_smem();
+  tc_fence_before();
+  __syncthreads();
+  if (tid == 0) {
+    tc_fence_after();
+    constexpr uint32_t idesc = make_idesc_bf16(128, 64, false, true);  // A = P K-major (4 tiles of 64 keys), B = V MN-major
+#pragma unroll
+    for (int k = 0; k < 16; ++k)
+      umma_bf16<1>(tmem, desc_k(sQ + (k >> 2) * TILE, k & 3), desc_mn(sV + (k >> 3) * TILE, k & 7, TILE), idesc, k != 0);
+    umma_commit<1>(&bars[2]);
+  }
+  mbar_wait(&bars[2], 0);
+  tc_fence_after();
+  const float inv = 1.f / l;
+#pragma unroll
+  for (int c = 0; c < 2; ++c) {
+    uint32_t v[32];
+    tmem_ld_32x32(taddr + c * 32, v);
+    tmem_ld_wait();
+#pragma unroll
+    for (int g = 0; g < 4; ++g) {
+      uint4 o;
+      o.x = pack_bf16x2(__uint_as_float(v[8 * g]) * inv, __uint_as_float(v[8 * g + 1]) * inv);
+      o.y = pack_bf16x2(__uint_as_float(v[8 * g + 2]) * inv, __uint_as_float(v[8 * g + 3]) * inv);
+      o.z = pack_bf16x2(__uint_as_float(v[8 * g + 4]) * inv, __uint_as_float(v[8 * g + 5]) * inv);
+      o.w = pack_bf16x2(__uint_as_float(v[8 * g + 6]) * inv, __uint_as_float(v[8 * g + 7]) * inv);
+      st_shared_v4(sV + p_off(row, c * 4 + g), o);  // V0 is dead after the PV MMAs
+    }
+  }
+  fence_proxy_async_smem();
+  tc_fence_before();
+  __syncthreads();
+  if (tid == 0) {
+    tma_store_3d(&map_ctx, smem + 4 * TILE, h * 64, q0, b);  // rows >= S fall outside the tensor: clipped
+    tma_store_commit();
+    tma_store_wait_read<0>();
+  }
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc<1>(tmem, 256);
+  }
+}
+
+// -------------------------------------------------------------------------------------------------
 // 256 threads: warps w and w+4 share TMEM lane quarter w and split the key columns, so the latency-bound
 // softmax-backward and epilogue phases have twice the warps to overlap
 __global__ void __launch_bounds__(256, 2)
@@ -376,6 +504,17 @@ int attention_tc_forward(const bf16* qkv, bf16* ctx, const int64_t* mask, float*
     attr = true;
   }
   AttnTcParams p{mask, lse2, nullptr, nullptr, B, S, H, heads, nullptr, nullptr};
+  if (S > 128) {
+    constexpr int smem2 = 6 * TILE + 64 + 1024 + 1024;
+    static bool attr2 = false;
+    if (!attr2) {
+      SIMX_CUDA(cudaFuncSetAttribute(attn_fwd_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem2));
+      attr2 = true;
+    }
+    attn_fwd_tc2_kernel<<<dim3(heads, B, (S + 127) / 128), 128, smem2, st>>>(p, mq, mc);
+    SIMX_LAUNCH_CHECK();
+    return SIMX_OK;
+  }
   attn_fwd_tc_kernel<<<dim3(heads, B), 128, smem, st>>>(p, mq, mc);
   SIMX_LAUNCH_CHECK();
   return SIMX_OK;

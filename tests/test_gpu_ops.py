@@ -132,7 +132,7 @@ def attention_reference(qkv, mask, dctx, heads):
 
 
 @pytest.mark.parametrize("B,S,heads,ragged", [(3, 128, 2, False), (5, 128, 12, True), (4, 32, 3, True), (2, 77, 2, True),
-                                              (2, 160, 2, True), (1, 512, 1, True)])
+                                              (2, 160, 2, True), (3, 200, 2, True), (2, 256, 3, False), (1, 512, 1, True)])
 def test_attention_forward_backward_and_bias_gradient(B, S, heads, ragged):
     lib = _lib.lib()
     H = heads * 64
