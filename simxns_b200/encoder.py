@@ -57,6 +57,21 @@ class EncoderConfig:
                              ln_eps=cfg.layer_norm_eps, init_range=getattr(cfg, "initializer_range", 0.02))
 
 
+# Every torch.optim.Optimizer.step() — including subclasses that write through `p.data` and therefore never bump
+# `p._version`, like the transformers.AdamW of the reference drivers — advances this counter; the bf16 operand cache of
+# each tower is keyed on it (and on the parameters' data pointers / versions).
+_OPTIMIZER_STEPS = [0]
+
+
+def _count_optimizer_step(optimizer, args, kwargs):
+    _OPTIMIZER_STEPS[0] += 1
+
+
+from torch.optim.optimizer import register_optimizer_step_post_hook  # noqa: E402
+
+register_optimizer_step_post_hook(_count_optimizer_step)
+
+
 def default_precision() -> int:
     """SIMX_PRECISION=bf16 (default, throughput) | bf16x3 / fp32 (3-plane split-bf16, fp32-class parity mode)"""
     v = os.environ.get("SIMX_PRECISION", "bf16").lower()
@@ -190,14 +205,14 @@ class B200EncoderBase(nn.Module):
             if p.dtype != torch.float32 or not p.is_contiguous() or p.device != dev:
                 raise RuntimeError("encoder parameters must be contiguous fp32 tensors on one CUDA device")
 
-    def _weights(self, params, force: bool = False) -> torch.Tensor:
-        """bf16 / split-bf16 GEMM operands of the fp32 master weights.  A TRAINING forward (`force`) always rebuilds them
-        (0.7 GB of traffic per BERT-base tower, ~0.1 % of a step): optimizers that update through `p.data` — the
-        transformers.AdamW of the reference drivers does (`p.data.addcdiv_`) — never bump `p._version`, so no host-side
-        key can see their updates.  Inference forwards reuse the buffer while (data_ptr, _version) are unchanged;
-        `invalidate_weights()` drops it after an out-of-band `.data` edit."""
-        key = (self.precision,) + tuple((p.data_ptr(), p._version) for p in params)
-        if self._wbuf is None or force or key != self._wkey:
+    def _weights(self, params) -> torch.Tensor:
+        """bf16 / split-bf16 GEMM operands of the fp32 master weights, rebuilt when a master weight may have changed:
+        a parameter's (data_ptr, _version) moved, or ANY optimizer stepped since the last build (optimizers that update
+        through `p.data` — the transformers.AdamW of the reference drivers does, `p.data.addcdiv_` — never bump
+        `_version`; the global step hook above sees them).  An out-of-band `p.data` edit outside an optimizer needs
+        `invalidate_weights()`."""
+        key = (self.precision, _OPTIMIZER_STEPS[0]) + tuple((p.data_ptr(), p._version) for p in params)
+        if self._wbuf is None or key != self._wkey:
             lib = _lib.lib()
             cfg = self._c_cfg()
             nbytes = lib.simx_encoder_weight_bytes(C.byref(cfg))
@@ -255,7 +270,7 @@ class _EncoderFn(torch.autograd.Function):
             if S > min(ec.max_pos, 512):
                 raise ValueError(f"sequence length {S} exceeds min(max_position_embeddings={ec.max_pos}, 512)")
             needs_grad = any(ctx.needs_input_grad[4:])  # grad mode is always off inside Function.forward
-            wbuf = module._weights(params, force=needs_grad)
+            wbuf = module._weights(params)
             table = module._param_table(params)
             stream = torch.cuda.current_stream(dev).cuda_stream
             cls = torch.empty(B, ec.num_layers + 1, ec.hidden, dtype=torch.float32, device=dev)

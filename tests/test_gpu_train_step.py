@@ -56,8 +56,11 @@ def oracle_tail(model, state, step_no, lr):
         wd = 0.0 if ("bias" in n or "LayerNorm.weight" in n) else WD
         new_p, m, v = on.adamw_hf(p.detach().cpu().double().numpy(), g, m, v, step_no, lr, eps=EPS, weight_decay=wd)
         state[n] = (m, v)
-        p.data.copy_(torch.from_numpy(new_p).to(p.dtype))
+        p.data.copy_(torch.from_numpy(new_p).to(p.dtype))  # through .data, as transformers.AdamW does: no _version bump
     model.zero_grad()
+    for m in model.modules():  # this hand-written update is not a torch Optimizer: tell the towers their weights moved
+        if hasattr(m, "invalidate_weights"):
+            m.invalidate_weights()
 
 
 def lr_at(k):  # get_linear_schedule_with_warmup after k scheduler steps
@@ -129,3 +132,37 @@ def test_teacher_steps_match_reference_loop_with_oracle_optimizer():
         assert abs(out["contr_loss"].item() - loss.item()) < 1e-4
         oracle_tail(ref, state, step, lr_at(step - 1))
         assert_same_params(teacher, ref)
+
+
+def test_data_style_optimizer_updates_reach_the_kernels():
+    """an optimizer that writes through `p.data` (transformers.AdamW v4 does) never bumps `p._version`; the towers' bf16
+    operand cache must still see its update (global optimizer-step hook)"""
+
+    class DataSGD(torch.optim.Optimizer):
+        def __init__(self, params):
+            super().__init__(params, dict(lr=0.5))
+
+        def step(self, closure=None):
+            for g in self.param_groups:
+                for p in g["params"]:
+                    if p.grad is not None:
+                        p.data.add_(p.grad.data, alpha=-g["lr"])
+
+    torch.manual_seed(2)
+    enc = HFBertEncoder(EC, precision=_lib.PREC_BF16X3).cuda()
+    ids, mask = bn.synth_tokens(3, 16, EC.vocab, seed=1)
+    ids, mask = torch.from_numpy(ids).cuda(), torch.from_numpy(mask).cuda()
+    opt = DataSGD(enc.parameters())
+    _, pooled, _ = enc(input_ids=ids, attention_mask=mask)
+    pooled.square().sum().backward()
+    v0 = enc.embeddings.word_embeddings.weight._version
+    opt.step()
+    assert enc.embeddings.word_embeddings.weight._version == v0  # the hazard: nothing visible on the tensor
+    with torch.no_grad():
+        _, after, _ = enc(input_ids=ids, attention_mask=mask)
+    fresh = HFBertEncoder(EC, precision=_lib.PREC_BF16X3).cuda()
+    fresh.load_state_dict(enc.state_dict())
+    with torch.no_grad():
+        _, want, _ = fresh(input_ids=ids, attention_mask=mask)
+    assert (after - pooled.detach()).abs().max().item() > 1e-3  # the step moved the output ...
+    assert torch.equal(after, want)                              # ... exactly to what the new weights give
