@@ -118,12 +118,13 @@ def merge_shard_results(D: torch.Tensor, I: torch.Tensor, k: int, group=None) ->
     """all-gather the per-rank [nq, k] results and keep the best k per query, (score desc, id asc).  The gathered
     candidates are only world*k per query, so the merge is a sort of a tiny matrix."""
     world = dist.get_world_size(group)
-    Dg = D.new_empty((world,) + tuple(D.shape))
-    Ig = I.new_empty((world,) + tuple(I.shape))
+    nq = D.shape[0]
+    Dg = D.new_empty((world * nq, k))  # rank-major concatenation along dim 0 (the layout every backend accepts)
+    Ig = I.new_empty((world * nq, k))
     dist.all_gather_into_tensor(Dg, D.contiguous(), group=group)
     dist.all_gather_into_tensor(Ig, I.contiguous(), group=group)
-    Dc = Dg.permute(1, 0, 2).reshape(D.shape[0], world * k)
-    Ic = Ig.permute(1, 0, 2).reshape(D.shape[0], world * k)
+    Dc = Dg.view(world, nq, k).permute(1, 0, 2).reshape(nq, world * k)
+    Ic = Ig.view(world, nq, k).permute(1, 0, 2).reshape(nq, world * k)
     return merge_candidates(Dc, Ic, k)
 
 

@@ -55,3 +55,38 @@ def test_two_rank_gather_and_gradient_ownership(tmp_path):
     assert abs(full["total"] - r[0]["loss"]) < 1e-12
     assert np.allclose(np.concatenate([r[0]["dQ"], r[1]["dQ"]]), dQ, atol=1e-12)
     assert np.allclose(np.concatenate([r[0]["dC"], r[1]["dC"]]), dC, atol=1e-12)
+
+
+def _search_worker(rank, world, port, out_dir):
+    """sharded index merge (faiss co.shard=True): each rank holds rows [cut_r, cut_{r+1}) and its local top-k (from the
+    oracle here — the kernel needs a GPU); merge_shard_results must reproduce the global top-k on every rank"""
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from oracle import search_numpy as sn
+    from simxns_b200.search import merge_shard_results
+
+    rng = np.random.RandomState(7)
+    # integer-valued embeddings: every inner product is exact in float64 whatever the BLAS blocking, so ties are real ties
+    P, Q = rng.randint(-8, 9, (500, 32)).astype(np.float64), rng.randint(-8, 9, (5, 32)).astype(np.float64)
+    P[300:320] = P[10:30]  # exact ties across the shard boundary: the lower global row must win
+    cuts = [0, 260, 500]
+    k = 40
+    D, I, _ = sn.flat_ip_search(P[cuts[rank]:cuts[rank + 1]], Q, k)
+    I = I + cuts[rank]
+    Dm, Im = merge_shard_results(torch.from_numpy(D), torch.from_numpy(I), k)
+    np.savez(os.path.join(out_dir, f"s{rank}.npz"), D=Dm.numpy(), I=Im.numpy(), P=P, Q=Q)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_two_rank_sharded_search_merge(tmp_path):
+    from oracle import search_numpy as sn
+
+    world = 2
+    mp.spawn(_search_worker, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
+    r = [np.load(tmp_path / f"s{i}.npz") for i in range(world)]
+    D, I, _ = sn.flat_ip_search(r[0]["P"], r[0]["Q"], 40)
+    for x in r:
+        assert np.array_equal(x["I"], I)        # bit-exact ids (ties -> lowest global row) on every rank
+        assert np.allclose(x["D"], D, atol=1e-12)
