@@ -562,3 +562,52 @@ def test_training_loop_contract_adamw_clip_accumulate():
             model.zero_grad()
             losses.append(loss.item() * accum)
     assert losses[-1] < losses[0] - 0.05, losses
+
+
+# ---------------------------------------------------------------------------------------------------------
+# the encoder at the full per-GPU size of BASELINE configs[2] (bert-base, 2048 passages x 128 tokens, bf16):
+# size-independent properties — the oracle cannot run this size
+# ---------------------------------------------------------------------------------------------------------
+def test_encoder_full_size_properties_bert_base():
+    """(1) batch-permutation equivariance, bit-exact: a sequence's embedding does not depend on where it sits in the
+    batch (tile scheduling, CTA pairs, persistent loops); (2) padding invariance: appending masked pad tokens to a
+    sequence leaves its [CLS] embedding unchanged up to bf16 round-off of the different tile shapes; (3) the gradient is
+    linear in the cotangent and the gradient of padded positions' word rows is exactly zero."""
+    ec = EncoderConfig()  # bert-base
+    torch.manual_seed(0)
+    enc = HFBertEncoder(ec, precision=BF16).cuda()
+    gen = torch.Generator(device="cuda").manual_seed(1)
+    B, S = 2048, 128
+    ids = torch.randint(1000, ec.vocab, (B, S), device="cuda", generator=gen)
+    ids[:, 0] = 101
+    lens = torch.randint(16, S + 1, (B,), device="cuda", generator=gen)
+    mask = (torch.arange(S, device="cuda")[None, :] < lens[:, None]).long()
+    ids = ids * mask
+    with torch.no_grad():
+        cls, _ = enc.encode(ids, mask)
+        perm = torch.randperm(B, device="cuda", generator=gen)
+        cls_p, _ = enc.encode(ids[perm], mask[perm])
+    assert torch.equal(cls_p, cls[perm])
+    assert torch.isfinite(cls).all()
+    # padding invariance on a slice (S 96 -> 128 with masked tail)
+    short = lens <= 96
+    sub = short.nonzero().flatten()[:256]
+    with torch.no_grad():
+        cls_s, _ = enc.encode(ids[sub, :96].contiguous(), mask[sub, :96].contiguous())
+    rel = ((cls_s[:, -1] - cls[sub, -1]).abs().max() / cls[sub, -1].abs().max()).item()
+    assert rel < 3e-2, rel
+    # backward on a 256-sequence slice: linearity in the cotangent, zero gradient for the pad row (id 0 is only ever masked)
+    sl = slice(0, 256)
+    d = torch.randn(256, ec.hidden, device="cuda", generator=gen)
+    out, _ = enc.encode(ids[sl], mask[sl])
+    (out[:, -1] * d).sum().backward()
+    g1 = enc.encoder.layer[5].intermediate.dense.weight.grad.clone()
+    gw = enc.embeddings.word_embeddings.weight.grad.clone()
+    enc.zero_grad()
+    out, _ = enc.encode(ids[sl], mask[sl])
+    (out[:, -1] * (2.0 * d)).sum().backward()
+    g2 = enc.encoder.layer[5].intermediate.dense.weight.grad
+    assert ((g2 - 2.0 * g1).abs().max() / g1.abs().max()).item() < 2e-2  # bf16 activations: rounding is not linear
+    used = torch.zeros(ec.vocab, dtype=torch.bool, device="cuda")
+    used[ids[sl].flatten()] = True
+    assert float(gw[~used].abs().max()) == 0.0  # rows of tokens that never occur get exactly nothing
