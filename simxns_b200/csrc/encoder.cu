@@ -38,6 +38,11 @@ int embed_scatter(int np, const int64_t* ids, const bf16* dz0, int T, int H, int
                   cudaStream_t st);
 int convert_weight(int np, const float* w, int R, int C, bf16* dst, long ld_dst, long ps_dst, bf16* dst_t, long ld_t,
                    long ps_t, cudaStream_t st);
+// batched form: every job queued between begin and end goes out in one launch per 56 jobs (C == 0: fp32 copy of R values)
+int conv_begin(void** handle);
+int conv_add(void* handle, int np, const float* w, int R, int C, bf16* dst, long ld_dst, long ps_dst, bf16* dst_t, long ld_t,
+             long ps_t, cudaStream_t st);
+int conv_end(void* handle, int np, cudaStream_t st);
 int attention_forward(int np, const bf16* qkv, long ps_qkv, bf16* ctx, long ps_ctx, const int64_t* mask, float* lse2,
                       int B, int S, int H, int heads, cudaStream_t st);
 int attention_backward(int np, const bf16* qkv, long ps_qkv, const bf16* ctx, const bf16* dctx, long ps_ctx, bf16* dqkv,
@@ -257,24 +262,33 @@ extern "C" int simx_encoder_prepare_weights(const simx_encoder_cfg* cfg, const f
   const ParamTable t = ptable(cfg);
   const LayerW lw = layer_w(cfg);
   uint8_t* base = align_ptr(wbuf);
-  for (int l = 0; l < cfg->num_layers; ++l) {
+  void* batch = nullptr;
+  SIMX_TRY(conv_begin(&batch));
+  int rc = SIMX_OK;
+  for (int l = 0; l < cfg->num_layers && rc == SIMX_OK; ++l) {
     const float* const* P = params + t.base + 16 * l;
     uint8_t* w = base + lw.total * l;
     bf16* wqkv = reinterpret_cast<bf16*>(w + lw.wqkv);
     bf16* wqkvT = reinterpret_cast<bf16*>(w + lw.wqkvT);
     const long ps3 = 3L * H * H;
-    for (int j = 0; j < 3; ++j)  // q, k, v rows stacked; transposed copy [H, 3H] has them as column blocks
-      SIMX_TRY(convert_weight(np, P[2 * j], H, H, wqkv + (long)j * H * H, H, ps3, wqkvT + (long)j * H, 3L * H, ps3, st));
-    SIMX_TRY(convert_weight(np, P[6], H, H, reinterpret_cast<bf16*>(w + lw.wo), H, (long)H * H,
-                            reinterpret_cast<bf16*>(w + lw.woT), H, (long)H * H, st));
-    SIMX_TRY(convert_weight(np, P[10], I, H, reinterpret_cast<bf16*>(w + lw.w1), H, (long)I * H,
-                            reinterpret_cast<bf16*>(w + lw.w1T), I, (long)I * H, st));
-    SIMX_TRY(convert_weight(np, P[12], H, I, reinterpret_cast<bf16*>(w + lw.w2), I, (long)I * H,
-                            reinterpret_cast<bf16*>(w + lw.w2T), H, (long)I * H, st));
+    for (int j = 0; j < 3 && rc == SIMX_OK; ++j)  // q, k, v rows stacked; transposed copy [H, 3H] has them as column blocks
+      rc = conv_add(batch, np, P[2 * j], H, H, wqkv + (long)j * H * H, H, ps3, wqkvT + (long)j * H, 3L * H, ps3, st);
+    if (rc == SIMX_OK)
+      rc = conv_add(batch, np, P[6], H, H, reinterpret_cast<bf16*>(w + lw.wo), H, (long)H * H,
+                    reinterpret_cast<bf16*>(w + lw.woT), H, (long)H * H, st);
+    if (rc == SIMX_OK)
+      rc = conv_add(batch, np, P[10], I, H, reinterpret_cast<bf16*>(w + lw.w1), H, (long)I * H,
+                    reinterpret_cast<bf16*>(w + lw.w1T), I, (long)I * H, st);
+    if (rc == SIMX_OK)
+      rc = conv_add(batch, np, P[12], H, I, reinterpret_cast<bf16*>(w + lw.w2), I, (long)I * H,
+                    reinterpret_cast<bf16*>(w + lw.w2T), H, (long)I * H, st);
     float* bqkv = reinterpret_cast<float*>(w + lw.bqkv);
-    for (int j = 0; j < 3; ++j)
-      SIMX_CUDA(cudaMemcpyAsync(bqkv + j * H, P[2 * j + 1], H * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    for (int j = 0; j < 3 && rc == SIMX_OK; ++j)  // fused [3H] bias: fp32 copies ride in the same launch
+      rc = conv_add(batch, np, P[2 * j + 1], H, 0, reinterpret_cast<bf16*>(bqkv + j * H), 0, 0, nullptr, 0, 0, st);
   }
+  const int rc_end = conv_end(batch, np, st);
+  SIMX_TRY(rc);
+  SIMX_TRY(rc_end);
   return SIMX_OK;
 }
 

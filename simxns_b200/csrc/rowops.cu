@@ -435,6 +435,49 @@ __global__ void convert_weight_kernel(const float* __restrict__ w, int R, int C,
   }
 }
 
+// All weight matrices of a tower in one launch (blockIdx.z = job): the per-matrix launches of prepare_weights were
+// 84 launches of ~7 us per tower after every optimizer step.  A job with C == 0 copies R fp32 values (the fused qkv bias).
+struct ConvJob {
+  const float* w;
+  bf16* dst;
+  bf16* dst_t;
+  int R, C;
+  long ld_dst, ps_dst, ld_t, ps_t;
+};
+constexpr int CONV_MAX_JOBS = 56;  // 56 x 64 B of kernel parameters
+struct ConvJobs {
+  ConvJob j[CONV_MAX_JOBS];
+};
+template <int NP>
+__global__ void convert_weights_batched_kernel(const ConvJobs jobs) {
+  __shared__ float tile[32][33];
+  const ConvJob jb = jobs.j[blockIdx.z];
+  const int tx = threadIdx.x, ty = threadIdx.y;
+  if (jb.C == 0) {  // plain fp32 copy of R values into `dst` (reinterpreted)
+    if (blockIdx.y != 0) return;
+    float* d = reinterpret_cast<float*>(jb.dst);
+    for (int i = blockIdx.x * 256 + ty * 32 + tx; i < jb.R; i += gridDim.x * 256) d[i] = jb.w[i];
+    return;
+  }
+  const int c0 = blockIdx.x * 32, r0 = blockIdx.y * 32;
+  if (c0 >= jb.C || r0 >= jb.R) return;
+  for (int j = ty; j < 32; j += 8) {
+    const int r = r0 + j, c = c0 + tx;
+    float v = 0.f;
+    if (r < jb.R && c < jb.C) {
+      v = jb.w[(long)r * jb.C + c];
+      if (jb.dst != nullptr) split_store<NP>(jb.dst + (long)r * jb.ld_dst + c, jb.ps_dst, v);
+    }
+    tile[j][tx] = v;
+  }
+  if (jb.dst_t == nullptr) return;
+  __syncthreads();
+  for (int j = ty; j < 32; j += 8) {
+    const int c = c0 + j, r = r0 + tx;
+    if (r < jb.R && c < jb.C) split_store<NP>(jb.dst_t + (long)c * jb.ld_t + r, jb.ps_t, tile[tx][j]);
+  }
+}
+
 // ------------------------------------------------------------------------------------------------
 // host wrappers
 // ------------------------------------------------------------------------------------------------
@@ -539,6 +582,48 @@ int embed_scatter(int np, const int64_t* ids, const bf16* dz0, int T, int H, int
   SIMX_LAUNCH_CHECK();
   return SIMX_OK;
 }
+// queue of conversion jobs, flushed as one launch per CONV_MAX_JOBS
+struct ConvBatch {
+  ConvJobs jobs;
+  int n = 0, max_r = 0, max_c = 0;
+  double bytes = 0;
+};
+static int conv_flush(int np, ConvBatch& b, cudaStream_t st) {
+  if (b.n == 0) return SIMX_OK;
+  ProfScope prof("convert_weight", 0, b.bytes, st);
+  dim3 grid((b.max_c + 31) / 32, (b.max_r + 31) / 32, b.n), block(32, 8);
+  SIMX_NP_DISPATCH(np, (convert_weights_batched_kernel<kNP><<<grid, block, 0, st>>>(b.jobs)));
+  SIMX_LAUNCH_CHECK();
+  b.n = 0; b.max_r = 0; b.max_c = 0; b.bytes = 0;
+  return SIMX_OK;
+}
+int conv_begin(void** handle) {
+  *handle = new ConvBatch();
+  return SIMX_OK;
+}
+int conv_add(void* handle, int np, const float* w, int R, int C, bf16* dst, long ld_dst, long ps_dst, bf16* dst_t, long ld_t,
+             long ps_t, cudaStream_t st) {
+  ConvBatch& b = *static_cast<ConvBatch*>(handle);
+  if (b.n == CONV_MAX_JOBS) SIMX_TRY(conv_flush(np, b, st));
+  b.jobs.j[b.n++] = ConvJob{w, dst, dst_t, R, C, ld_dst, ps_dst, ld_t, ps_t};
+  if (C == 0) {
+    b.max_c = max(b.max_c, 32 * 4);  // a few blocks in x for the copy loop
+    b.max_r = max(b.max_r, 1);
+    b.bytes += 8.0 * R;
+  } else {
+    b.max_r = max(b.max_r, R);
+    b.max_c = max(b.max_c, C);
+    b.bytes += (double)R * C * (4.0 + 2.0 * np * (dst_t ? 2 : 1));
+  }
+  return SIMX_OK;
+}
+int conv_end(void* handle, int np, cudaStream_t st) {
+  ConvBatch* b = static_cast<ConvBatch*>(handle);
+  const int rc = conv_flush(np, *b, st);
+  delete b;
+  return rc;
+}
+
 int convert_weight(int np, const float* w, int R, int C, bf16* dst, long ld_dst, long ps_dst, bf16* dst_t, long ld_t,
                    long ps_t, cudaStream_t st) {
   ProfScope prof("convert_weight", 0, (double)R * C * (4.0 + 2.0 * np * (dst_t ? 2 : 1)), st);
