@@ -269,6 +269,8 @@ int simx_adamw_step(const simx_opt_tensor* tensors_dev, int n, int total_chunks,
                                 whose dgrad this is, reduced in the epilogue instead of by a pass over `out` */
 #define SIMX_EPI_ADD 5       /* out = acc + aux[m,n]                                  (dgrad + residual grad) */
 #define SIMX_EPI_ATOMIC_F32 6 /* outf[m,n] += acc   (fp32 atomics; split-K wgrad)     */
+#define SIMX_EPI_BIAS_GELU_FWD 7 /* out = gelu_erf(acc + bias[n])                     (BertIntermediate at inference: nothing is
+                                    kept for a backward pass, so the derivative is neither computed nor stored) */
 
 /* D[M,N] = sum_k A[m,k] * B[n,k]   on tcgen05 tensor cores (bf16 operands, fp32 accumulate in TMEM).
  *   a_mn_major == 0: A is [M,K] row-major (lda >= K);  == 1: A is stored [K,M] row-major (lda >= M).  Same for B/N.

@@ -18,7 +18,7 @@ SIMX_OK = 0
 ARCH_BERT, ARCH_DISTILBERT = 0, 1
 PREC_BF16, PREC_BF16X3 = 1, 3
 
-EPI_PLAIN, EPI_BIAS, EPI_BIAS_GELU, EPI_BIAS_ADD, EPI_MUL, EPI_ADD, EPI_ATOMIC_F32 = range(7)
+EPI_PLAIN, EPI_BIAS, EPI_BIAS_GELU, EPI_BIAS_ADD, EPI_MUL, EPI_ADD, EPI_ATOMIC_F32, EPI_BIAS_GELU_FWD = range(8)
 
 LOSS_NLL_GLOBAL, LOSS_KL_LOCAL, LOSS_CE_LOCAL, LOSS_KD_LOCAL, LOSS_NLL_LOCAL, LOSS_ADV_LOCAL = 1, 2, 4, 8, 16, 32
 LOSS_MSE_LOCAL, LOSS_DKD_LOCAL = 64, 128

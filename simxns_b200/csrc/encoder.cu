@@ -357,8 +357,12 @@ extern "C" int simx_encoder_forward(const simx_encoder_cfg* cfg, const float* co
     prof_label(nullptr);
     SIMX_TRY(ln_fwd(np, z1, T, H, P[8], P[9], cfg->ln_eps, x1, psH, st));
     prof_label("ffn1_fwd");
-    SIMX_TRY(gemm(T, I, H, x1, H, psH, false, w1, H, (long)I * H, false, np, SIMX_EPI_BIAS_GELU, P[11], nullptr, 0, 0, h, a,
-                  I, psI, nullptr, 0, 1, st));
+    if (keep)
+      SIMX_TRY(gemm(T, I, H, x1, H, psH, false, w1, H, (long)I * H, false, np, SIMX_EPI_BIAS_GELU, P[11], nullptr, 0, 0, h, a,
+                    I, psI, nullptr, 0, 1, st));
+    else  // inference: gelu only, one [T, I] output instead of two
+      SIMX_TRY(gemm(T, I, H, x1, H, psH, false, w1, H, (long)I * H, false, np, SIMX_EPI_BIAS_GELU_FWD, P[11], nullptr, 0, 0, a,
+                    nullptr, I, psI, nullptr, 0, 1, st));
     prof_label(nullptr);
     prof_label("ffn2_fwd");
     SIMX_TRY(gemm(T, H, I, a, I, psI, false, w2, I, (long)I * H, false, np, SIMX_EPI_BIAS_ADD, P[13], x1, H, psH, z2,

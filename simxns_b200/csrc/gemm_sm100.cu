@@ -65,7 +65,8 @@ constexpr bool kTmaStore = (BN == 256) && (NP == 1) && !MN && (EPI != SIMX_EPI_A
 // latency overlaps the tcgen05.ld in flight
 template <int EPI, int NP>
 struct EpiPre {
-  static constexpr bool kBias = EPI == SIMX_EPI_BIAS || EPI == SIMX_EPI_BIAS_GELU || EPI == SIMX_EPI_BIAS_ADD;
+  static constexpr bool kBias = EPI == SIMX_EPI_BIAS || EPI == SIMX_EPI_BIAS_GELU || EPI == SIMX_EPI_BIAS_ADD ||
+                                EPI == SIMX_EPI_BIAS_GELU_FWD;
   static constexpr bool kAux = EPI == SIMX_EPI_BIAS_ADD || EPI == SIMX_EPI_ADD || EPI == SIMX_EPI_MUL;
   uint4 aux[kAux ? NP : 1][kAux ? 4 : 1];
 };
@@ -113,6 +114,22 @@ __device__ __forceinline__ void gelu_pair_f16(float x0, float x1, uint32_t& g_ou
   const float2 gf = __half22float2(g), df = __half22float2(dg);
   g_out = pack_bf16x2(gf.x, gf.y);
   dg_out = pack_bf16x2(df.x, df.y);
+}
+// forward-only variant (inference): gelu alone, same tanh-form fit
+__device__ __forceinline__ uint32_t gelu_only_pair_f16(float x0, float x1) {
+  const __half2 x = __floats2half2_rn(x0, x1);
+  const __half2 lim = __float2half2_rn(8.0f);
+  const __half2 xc = __hmax2(__hmin2(x, lim), __hneg2(lim));
+  const __half2 x2 = __hmul2(xc, xc);
+  __half2 p = __hfma2(x2, __float2half2_rn(-3.47550486e-04f), __float2half2_rn(3.70038725e-02f));
+  p = __hfma2(x2, p, __float2half2_rn(7.97422816e-01f));
+  const __half2 u = __hmul2(xc, p);
+  uint32_t tu;
+  asm("tanh.approx.f16x2 %0, %1;" : "=r"(tu) : "r"(*reinterpret_cast<const uint32_t*>(&u)));
+  const __half2 t = *reinterpret_cast<const __half2*>(&tu);
+  const __half2 half = __float2half2_rn(0.5f);
+  const float2 gf = __half22float2(__hmul2(x, __hfma2(t, half, half)));
+  return pack_bf16x2(gf.x, gf.y);
 }
 __device__ __forceinline__ void gelu_exact(float x, float& g, float& dg) {
   const float cdf = 0.5f * (1.0f + erff(x * 0.70710678118654752440f));
@@ -187,6 +204,17 @@ __device__ __forceinline__ void epilogue_chunk(const GemmParams& p, int row, int
         for (int i = 0; i < 8; ++i) gelu_exact(v[i], ge[i], dg[i]);
         split_store8<NP>(p.out + (long)row * p.ldo + col, p.out_ps, dg);   // gelu'(pre-activation), kept for backward
         split_store8<NP>(p.out2 + (long)row * p.ldo + col, p.out_ps, ge);  // gelu(pre-activation)
+      }
+    } else if constexpr (EPI == SIMX_EPI_BIAS_GELU_FWD) {
+      if constexpr (NP == 1) {
+        *reinterpret_cast<uint4*>(p.out + (long)row * p.ldo + col) =
+            make_uint4(gelu_only_pair_f16(v[0], v[1]), gelu_only_pair_f16(v[2], v[3]), gelu_only_pair_f16(v[4], v[5]),
+                       gelu_only_pair_f16(v[6], v[7]));
+      } else {
+        float ge[8], dg;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) gelu_exact(v[i], ge[i], dg);
+        split_store8<NP>(p.out + (long)row * p.ldo + col, p.out_ps, ge);
       }
     } else {
       split_store8<NP>(p.out + (long)row * p.ldo + col, p.out_ps, v);
@@ -435,6 +463,9 @@ gemm_kernel(const GemmParams p, const __grid_constant__ CUtensorMap mapA, const 
               for (int i = 0; i < 4; ++i) gelu_pair_f16(f[2 * i], f[2 * i + 1], ge[i], dg[i]);
               o = make_uint4(dg[0], dg[1], dg[2], dg[3]);
               o2[j] = make_uint4(ge[0], ge[1], ge[2], ge[3]);
+            } else if constexpr (EPI == SIMX_EPI_BIAS_GELU_FWD) {
+              o = make_uint4(gelu_only_pair_f16(f[0], f[1]), gelu_only_pair_f16(f[2], f[3]), gelu_only_pair_f16(f[4], f[5]),
+                             gelu_only_pair_f16(f[6], f[7]));
             } else {
               o = make_uint4(pack_bf16x2(f[0], f[1]), pack_bf16x2(f[2], f[3]), pack_bf16x2(f[4], f[5]),
                              pack_bf16x2(f[6], f[7]));
@@ -632,6 +663,7 @@ static int dispatch_epi(int epi, const GemmParams& p, const bf16* A, long lda, l
       case SIMX_EPI_MUL: return launch_gemm<BN, MN, SIMX_EPI_MUL, NP>(p, A, lda, a_ps, B, ldb, b_ps, planes, stream);
       case SIMX_EPI_ADD: return launch_gemm<BN, MN, SIMX_EPI_ADD, NP>(p, A, lda, a_ps, B, ldb, b_ps, planes, stream);
       case SIMX_EPI_ATOMIC_F32: return launch_gemm<BN, MN, SIMX_EPI_ATOMIC_F32, NP>(p, A, lda, a_ps, B, ldb, b_ps, planes, stream);
+      case SIMX_EPI_BIAS_GELU_FWD: return launch_gemm<BN, MN, SIMX_EPI_BIAS_GELU_FWD, NP>(p, A, lda, a_ps, B, ldb, b_ps, planes, stream);
     }
     SIMX_FAIL(SIMX_ERR_INVALID, "unknown GEMM epilogue %d", epi);
   }
@@ -654,7 +686,7 @@ static int gemm_launch(int M, int N, int K, const bf16* A, long lda, long a_ps, 
     SIMX_CHECK(out != nullptr && ldo % 8 == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0, SIMX_ERR_INVALID,
                "gemm: bf16 output must be 16-byte aligned with ld %% 8 == 0");
   }
-  if (epi == SIMX_EPI_BIAS || epi == SIMX_EPI_BIAS_GELU || epi == SIMX_EPI_BIAS_ADD)
+  if (epi == SIMX_EPI_BIAS || epi == SIMX_EPI_BIAS_GELU || epi == SIMX_EPI_BIAS_ADD || epi == SIMX_EPI_BIAS_GELU_FWD)
     SIMX_CHECK(bias != nullptr && (reinterpret_cast<uintptr_t>(bias) & 15) == 0, SIMX_ERR_INVALID,
                "gemm: bias missing or misaligned");
   if (epi == SIMX_EPI_BIAS_ADD || epi == SIMX_EPI_MUL || epi == SIMX_EPI_ADD)

@@ -32,7 +32,7 @@ def run_gemm(M, N, K, mn, planes, epi, ksplit, seed, colsum=False):
     lib = _lib.lib()
     torch.manual_seed(seed)
     dev = "cuda"
-    A32 = torch.randn(M, K, device=dev) * (0.05 if epi == _lib.EPI_BIAS_GELU else 1.0)
+    A32 = torch.randn(M, K, device=dev) * (0.05 if epi in (_lib.EPI_BIAS_GELU, _lib.EPI_BIAS_GELU_FWD) else 1.0)
     B32 = torch.randn(N, K, device=dev)
     bias = torch.randn(N, device=dev)
     aux32 = torch.randn(M, N, device=dev)
@@ -52,8 +52,10 @@ def run_gemm(M, N, K, mn, planes, epi, ksplit, seed, colsum=False):
     else:
         outf = torch.full((N,), 0.25, device=dev) if colsum else None  # column sums ACCUMULATE into outf
     ref = Af.double() @ Bf.double().t()
-    if epi in (_lib.EPI_BIAS, _lib.EPI_BIAS_GELU, _lib.EPI_BIAS_ADD):
+    if epi in (_lib.EPI_BIAS, _lib.EPI_BIAS_GELU, _lib.EPI_BIAS_ADD, _lib.EPI_BIAS_GELU_FWD):
         ref = ref + bias.double()
+    if epi == _lib.EPI_BIAS_GELU_FWD:  # inference epilogue: gelu only
+        ref = torch.nn.functional.gelu(ref)
     if epi in (_lib.EPI_BIAS_ADD, _lib.EPI_ADD):
         ref = ref + auxf.double()
     ref2 = None
@@ -91,6 +93,7 @@ GEMM_CASES = [
     (512, 3072, 768, 0, 1, 4, 1), (512, 768, 2304, 0, 1, 5, 1), (512, 768, 768, 0, 1, 6, 3), (8192, 3072, 768, 0, 1, 2, 1),
     (2304, 768, 4096, 1, 1, 6, 1), (768, 3072, 8192, 1, 1, 6, 8), (768, 768, 1000, 1, 1, 6, 4), (192, 64, 520, 1, 1, 6, 2),
     (384, 768, 768, 0, 3, 1, 1), (256, 3072, 768, 0, 3, 2, 1), (768, 768, 2048, 1, 3, 6, 4),
+    (512, 3072, 768, 0, 1, 7, 1), (300, 128, 192, 0, 1, 7, 1), (256, 3072, 768, 0, 3, 7, 1), (1000, 328, 128, 0, 1, 7, 1),
 ]
 
 
@@ -98,7 +101,8 @@ GEMM_CASES = [
 def test_gemm_epilogues_vs_torch(case):
     M, N, K, mn, planes, epi, ksplit = case
     err, err2, _ = run_gemm(M, N, K, mn, planes, epi, ksplit, seed=M + N + K)
-    tol = 1e-5 if planes == 3 else (2e-5 if epi == _lib.EPI_ATOMIC_F32 else (1e-2 if epi == _lib.EPI_BIAS_GELU else 6e-3))
+    gelu = epi in (_lib.EPI_BIAS_GELU, _lib.EPI_BIAS_GELU_FWD)
+    tol = 1e-5 if planes == 3 else (2e-5 if epi == _lib.EPI_ATOMIC_F32 else (1e-2 if gelu else 6e-3))
     assert err < tol, (case, err)
     if err2 is not None:
         assert err2 < tol, (case, err2)
