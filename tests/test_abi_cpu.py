@@ -110,3 +110,77 @@ def test_forward_without_cuda_fails_loudly():
     m = HFBertEncoder(ec)
     with pytest.raises(RuntimeError, match="no CPU fallback|CUDA"):
         m(input_ids=torch.ones(1, 4, dtype=torch.long), attention_mask=torch.ones(1, 4, dtype=torch.long))
+
+
+def test_widened_rows_refuse_cpu_tensors_and_bad_arguments():
+    """no CPU fallback anywhere: the optimizer, the clip, the index and the MSE helper raise on CPU tensors"""
+    from simxns_b200 import optim as sx
+    from simxns_b200.losses import embed_mse
+    from simxns_b200.search import FlatIPIndex
+
+    p = torch.nn.Parameter(torch.zeros(4))
+    p.grad = torch.ones(4)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        sx.AdamW([p]).step()
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        sx.clip_grad_norm_([p], 1.0)
+    with pytest.raises(NotImplementedError):
+        sx.clip_grad_norm_([p], 1.0, norm_type=1.0)
+    with pytest.raises(ValueError):
+        sx.AdamW([p], flavor="lion")
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        embed_mse(torch.zeros(2, 8), torch.zeros(2, 8))
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        FlatIPIndex(64, device="cpu")
+    with pytest.raises(ValueError):
+        FlatIPIndex(100, device="cuda:0")
+
+
+def test_opt_plan_chunks_the_tensor_table():
+    """simx_opt_plan is host-only: 8192-element chunks, prefix in chunk_begin, -1 on a bad row"""
+    lib = _lib.lib()
+    rows = (_lib.OptTensor * 3)()
+    for i, n in enumerate((1, 8192, 8193)):
+        rows[i].p, rows[i].numel = 16 * (i + 1), n
+    assert lib.simx_opt_plan(rows, 3) == 1 + 1 + 2
+    assert [rows[i].chunk_begin for i in range(3)] == [0, 1, 2]
+    rows[1].numel = 0
+    assert lib.simx_opt_plan(rows, 3) == -1 and b"tensor 1" in lib.simx_last_error()
+
+
+def test_linear_schedule_and_optimizer_groups_host_logic():
+    """get_linear_schedule_with_warmup values and get_optimizer's bias / LayerNorm.weight no-decay split
+    (co_training_marco_train.py:57-69, 129-134) — pure host logic"""
+    import types
+
+    from simxns_b200.train import get_linear_schedule_with_warmup, get_optimizer
+
+    ec = EncoderConfig(num_layers=1, hidden=64, heads=1, intermediate=128, vocab=50, max_pos=16)
+    m = HFBertEncoder(ec)
+    opt = get_optimizer(types.SimpleNamespace(optimizer="adamW"), m, weight_decay=0.01, lr=2e-5, eps=1e-8)
+    decay, no_decay = opt.param_groups
+    names = {id(p): n for n, p in m.named_parameters()}
+    assert all("bias" in names[id(p)] or "LayerNorm.weight" in names[id(p)] for p in no_decay["params"])
+    assert not any("bias" in names[id(p)] or "LayerNorm.weight" in names[id(p)] for p in decay["params"])
+    assert decay["weight_decay"] == 0.01 and no_decay["weight_decay"] == 0.0
+    assert len(decay["params"]) + len(no_decay["params"]) == len(list(m.parameters()))
+    with pytest.raises(Exception, match="not recognized"):
+        get_optimizer(types.SimpleNamespace(optimizer="sgd"), m)
+    sched = get_linear_schedule_with_warmup(opt, num_warmup_steps=2, num_training_steps=10)
+    lrs = []
+    for _ in range(11):
+        lrs.append(opt.param_groups[0]["lr"])
+        sched.step()  # (stepping the scheduler alone is fine for reading the schedule)
+    want = [2e-5 * (k / 2 if k < 2 else max(0.0, (10 - k) / 8)) for k in range(11)]
+    assert all(abs(a - b) < 1e-12 for a, b in zip(lrs, want))
+
+
+def test_merge_candidates_orders_by_score_then_id():
+    from simxns_b200.search import merge_candidates
+
+    D = torch.tensor([[1.0, 3.0, 3.0, float("-inf"), 2.0, 3.0]])
+    I = torch.tensor([[7, 9, 4, -1, 5, 6]])
+    d, i = merge_candidates(D, I, 4)
+    assert i.tolist() == [[4, 6, 9, 5]] and d.tolist() == [[3.0, 3.0, 3.0, 2.0]]
+    d, i = merge_candidates(D, I, 6)
+    assert i.tolist()[0][-1] == -1 and d.tolist()[0][-1] == float("-inf")
