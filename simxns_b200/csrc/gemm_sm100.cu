@@ -403,7 +403,9 @@ gemm_kernel(const GemmParams p, const __grid_constant__ CUtensorMap mapA, const 
       EpiPre<EPI, NP> pre;
       if constexpr (!kAuxTma) epi_prefetch<EPI, NP, CW>(p, row, col_base, pre);
       if constexpr (kAuxTma) {
-        // the previous tile's store must have finished READING the staging box before the aux tile lands in it
+        // the previous tile's store must have finished READING the staging box before the aux tile lands in it (and
+        // every lane must be done with its own reads of the box: the column-sum sweep of EPI_MUL)
+        __syncwarp();
         if (lane == 0) {
           tma_store_wait_read<0>();
           mbar_arrive_expect_tx(&auxbar[warp - 4], 4096);
