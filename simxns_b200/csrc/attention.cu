@@ -533,7 +533,7 @@ int attention_forward(int np, const bf16* qkv, long ps_qkv, bf16* ctx, long ps_c
   ProfScope prof("attn_fwd", 4.0 * B * heads * (double)S * S * ATT_D, 2.0 * np * B * (double)S * 4 * H, st);
   // forward also has a two-key-tile tcgen05 kernel for S <= 256; it always works on 2 x 128 queries x 256 keys, so it
   // only beats the mma.sync kernel on the longer half of that range (measured at 2048 sequences x 12 heads: S = 256
-  // 1.25 vs 1.71 ms, S = 160 1.21 vs 1.16 ms); backward for those lengths stays on mma.sync
+  // 1.25 vs 1.71 ms, S = 160 1.21 vs 1.16 ms).  Both forwards write the same lse2, which is all the backward needs.
   if (use_tc_attention(np, S) || (S > 176 && use_tc_attention(np, S - 128))) {
     return attention_tc_forward(qkv, ctx, mask, lse2, B, S, H, heads, st);
   }
@@ -567,7 +567,7 @@ int attention_backward(int np, const bf16* qkv, long ps_qkv, const bf16* ctx, co
                        const int64_t* mask, const float* lse2, float* delta, int B, int S, int H, int heads,
                        float* dbias, cudaStream_t st) {
   SIMX_TRY(attn_check(B, S, H, heads));
-  if (use_tc_attention(np, S)) {
+  if (use_tc_attention(np, S) || use_tc_attention(np, S - 128)) {  // S <= 256: one or 2 x 2 tcgen05 blocks
     ProfScope prof("attn_bwd", 10.0 * B * heads * (double)S * S * ATT_D, 2.0 * np * B * (double)S * 8 * H, st);
     return attention_tc_backward(qkv, ctx, dctx, dqkv, mask, lse2, B, S, H, heads, dbias, st);
   }

@@ -9,8 +9,12 @@
 //              -> dV = P^T dO, dK = dS^T Q (A operands MN-major: the transposes are free), dQ = dS K -> three TMA stores.
 //              Five matmuls, each done once; no atomics, no recomputation.  256 TMEM columns, 112 KB smem: two CTAs/SM.
 //
+//   128 < S <= 256 : forward = attn_fwd_tc2_kernel (two key tiles resident, S[128,256] in TMEM); backward = the same
+//              single-tile kernel run on the 2 x 2 (query tile, key tile) blocks — P of a block needs only the forward's
+//              row log-sum-exp — with TMA reduce-add (bf16) of the dQ / dK / dV contributions into a zeroed dqkv.
+//
 // Reference math: LEAD/modeling_bert.py:324-368 (scores / sqrt(64) + extended mask, softmax, context).
-// Longer sequences and the fp32-class mode use the kernels in attention.cu.
+// Longer sequences (<= 512) and the fp32-class mode use the kernels in attention.cu.
 #include "common.cuh"
 #include "ptx.cuh"
 
@@ -322,6 +326,11 @@ attn_bwd_tc_kernel(const AttnTcParams p, const __grid_constant__ CUtensorMap map
   float* bias = reinterpret_cast<float*>(smem_raw + 64);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int h = blockIdx.x, b = blockIdx.y, S = p.S;
+  // 128 < S <= 256: the (sequence, head) problem is cut into 2 x 2 blocks of (128 queries) x (128 keys); P of a block
+  // needs only the forward's row log-sum-exp, so blocks are independent and their dQ / dK / dV contributions are
+  // accumulated in global memory with TMA reduce-add (dqkv zeroed by the host wrapper).  S <= 128: one block, plain stores.
+  const int kt = (S + 127) >> 7;
+  const int q0 = (blockIdx.z / kt) * 128, k0 = (blockIdx.z % kt) * 128;
   SIMX_STAMP(0);
 
   if (tid == 0) {
@@ -335,7 +344,7 @@ attn_bwd_tc_kernel(const AttnTcParams p, const __grid_constant__ CUtensorMap map
     fence_mbar_init();
   }
   if (warp == 1) tmem_alloc<1>(tmem_slot, 256);
-  if (tid < 128) bias[tid] = (tid < S && (p.mask == nullptr || p.mask[(long)b * S + tid] != 0)) ? 0.f : TC_NEG;
+  if (tid < 128) bias[tid] = (k0 + tid < S && (p.mask == nullptr || p.mask[(long)b * S + k0 + tid] != 0)) ? 0.f : TC_NEG;
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -345,11 +354,11 @@ attn_bwd_tc_kernel(const AttnTcParams p, const __grid_constant__ CUtensorMap map
   const uint32_t sO = sdS;  // O is only needed for delta: it borrows the first dS tile until dS is written
   if (tid == 0) {
     mbar_arrive_expect_tx(&bars[0], 5 * TILE);
-    tma_load_3d(&map_qkv, &bars[0], smem, h * 64, 0, b);
-    tma_load_3d(&map_qkv, &bars[0], smem + TILE, p.H + h * 64, 0, b);
-    tma_load_3d(&map_qkv, &bars[0], smem + 3 * TILE, 2 * p.H + h * 64, 0, b);
-    tma_load_3d(&map_dctx, &bars[0], smem + 2 * TILE, h * 64, 0, b);
-    tma_load_3d(&map_ctx, &bars[0], smem + 5 * TILE, h * 64, 0, b);
+    tma_load_3d(&map_qkv, &bars[0], smem, h * 64, q0, b);
+    tma_load_3d(&map_qkv, &bars[0], smem + TILE, p.H + h * 64, k0, b);
+    tma_load_3d(&map_qkv, &bars[0], smem + 3 * TILE, 2 * p.H + h * 64, k0, b);
+    tma_load_3d(&map_dctx, &bars[0], smem + 2 * TILE, h * 64, q0, b);
+    tma_load_3d(&map_ctx, &bars[0], smem + 5 * TILE, h * 64, q0, b);
     mbar_wait(&bars[0], 0);
     tc_fence_after();
     constexpr uint32_t idesc = make_idesc_bf16(128, 128, false, false);
@@ -375,7 +384,7 @@ attn_bwd_tc_kernel(const AttnTcParams p, const __grid_constant__ CUtensorMap map
       delta += fx.x * fy.x + fx.y * fy.y;
     }
   }
-  const float lse = row < S ? p.lse2[((long)b * p.heads + h) * S + row] : 0.f;
+  const float lse = q0 + row < S ? p.lse2[((long)b * p.heads + h) * S + q0 + row] : 0.f;
   __syncthreads();  // both column-halves have read their O row before anyone overwrites that tile with dS
   mbar_wait(&bars[1], 0);
   tc_fence_after();
@@ -383,7 +392,7 @@ attn_bwd_tc_kernel(const AttnTcParams p, const __grid_constant__ CUtensorMap map
 
   const uint32_t taddr = tmem + (static_cast<uint32_t>(quarter * 32) << 16);
   const float sl2 = 0.125f * TC_LOG2E;
-  const bool rv = row < S;
+  const bool rv = q0 + row < S;
 #pragma unroll 1
   for (int c = half * 2; c < half * 2 + 2; ++c) {
     uint32_t s[32], d[32];
@@ -454,9 +463,15 @@ attn_bwd_tc_kernel(const AttnTcParams p, const __grid_constant__ CUtensorMap map
   __syncthreads();
   SIMX_STAMP(6);
   if (tid == 0) {
-    tma_store_3d(&map_dqkv, smem, 2 * p.H + h * 64, 0, b);             // dV
-    tma_store_3d(&map_dqkv, smem + TILE, p.H + h * 64, 0, b);          // dK
-    tma_store_3d(&map_dqkv, smem + 2 * TILE, h * 64, 0, b);            // dQ
+    if (kt == 1) {
+      tma_store_3d(&map_dqkv, smem, 2 * p.H + h * 64, 0, b);             // dV
+      tma_store_3d(&map_dqkv, smem + TILE, p.H + h * 64, 0, b);          // dK
+      tma_store_3d(&map_dqkv, smem + 2 * TILE, h * 64, 0, b);            // dQ
+    } else {  // this block's share of the sums over the other tile index
+      tma_reduce_add_3d(&map_dqkv, smem, 2 * p.H + h * 64, k0, b);       // dV[k-tile] += P^T dO   (over q-tiles)
+      tma_reduce_add_3d(&map_dqkv, smem + TILE, p.H + h * 64, k0, b);    // dK[k-tile] += dS^T Q
+      tma_reduce_add_3d(&map_dqkv, smem + 2 * TILE, h * 64, q0, b);      // dQ[q-tile] += dS K     (over k-tiles)
+    }
     tma_store_commit();
   }
   if (p.dbias != nullptr && tid < 192) {
@@ -534,7 +549,9 @@ int attention_tc_backward(const bf16* qkv, const bf16* ctx, const bf16* dctx, bf
     attr = true;
   }
   AttnTcParams p{mask, const_cast<float*>(lse2), ctx, dctx, B, S, H, heads, g_attn_timing, dbias};
-  attn_bwd_tc_kernel<<<dim3(heads, B), 256, smem, st>>>(p, mq, md, mo, mg);
+  const int kt = (S + 127) / 128;
+  if (kt > 1) SIMX_CUDA(cudaMemsetAsync(dqkv, 0, (size_t)B * S * 3 * H * sizeof(bf16), st));  // blocks reduce-add into it
+  attn_bwd_tc_kernel<<<dim3(heads, B, kt * kt), 256, smem, st>>>(p, mq, md, mo, mg);
   SIMX_LAUNCH_CHECK();
   return SIMX_OK;
 }

@@ -158,6 +158,12 @@ __device__ __forceinline__ void tma_reduce_add_2d(const CUtensorMap* d, const vo
                "r"(smem_u32(smem)), "r"(c0), "r"(c1)
                : "memory");
 }
+__device__ __forceinline__ void tma_reduce_add_3d(const CUtensorMap* d, const void* smem, int32_t c0, int32_t c1, int32_t c2) {
+  asm volatile("cp.reduce.async.bulk.tensor.3d.global.shared::cta.add.bulk_group [%0, {%2, %3, %4}], [%1];" ::"l"(
+                   reinterpret_cast<uint64_t>(d)),
+               "r"(smem_u32(smem)), "r"(c0), "r"(c1), "r"(c2)
+               : "memory");
+}
 __device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 template <int N>
 __device__ __forceinline__ void tma_store_wait_read() {
