@@ -531,10 +531,9 @@ int attention_forward(int np, const bf16* qkv, long ps_qkv, bf16* ctx, long ps_c
                       int B, int S, int H, int heads, cudaStream_t st) {
   SIMX_TRY(attn_check(B, S, H, heads));
   ProfScope prof("attn_fwd", 4.0 * B * heads * (double)S * S * ATT_D, 2.0 * np * B * (double)S * 4 * H, st);
-  // forward also has a two-key-tile tcgen05 kernel for S <= 256; it always works on 2 x 128 queries x 256 keys, so it
-  // only beats the mma.sync kernel on the longer half of that range (measured at 2048 sequences x 12 heads: S = 256
-  // 1.25 vs 1.71 ms, S = 160 1.21 vs 1.16 ms).  Both forwards write the same lse2, which is all the backward needs.
-  if (use_tc_attention(np, S) || (S > 176 && use_tc_attention(np, S - 128))) {
+  // 128 < S <= 256: the two-key-tile tcgen05 kernel (2048 sequences x 12 heads: S = 160 0.97 vs 1.16 ms for the mma.sync
+  // kernel, S = 256 1.31 vs 1.71 ms)
+  if (use_tc_attention(np, S) || use_tc_attention(np, S - 128)) {
     return attention_tc_forward(qkv, ctx, mask, lse2, B, S, H, heads, st);
   }
   if (np == 3) {

@@ -230,9 +230,14 @@ attn_fwd_tc2_kernel(const AttnTcParams p, const __grid_constant__ CUtensorMap ma
   const int row = warp * 32 + lane;
   const uint32_t taddr = tmem + (static_cast<uint32_t>(warp * 32) << 16);
   const float sl2 = 0.125f * TC_LOG2E;
+  // ragged lengths: only the 32-key chunks that hold a real key are touched (the PV product stops at ceil(S / 16) key
+  // steps, so P beyond them is never read), and a warp whose 32 query rows all lie beyond S skips the softmax
+  // altogether — its rows of P / O are garbage that the clipped TMA store never writes
+  const int nch = (S + 31) >> 5;
+  const bool warp_valid = q0 + warp * 32 < S;
   float m = TC_NEG;
 #pragma unroll 1
-  for (int c = 0; c < 8; ++c) {
+  for (int c = 0; c < (warp_valid ? nch : 0); ++c) {
     uint32_t v[32];
     tmem_ld_32x32(taddr + c * 32, v);
     tmem_ld_wait();
@@ -243,7 +248,7 @@ attn_fwd_tc2_kernel(const AttnTcParams p, const __grid_constant__ CUtensorMap ma
   // thread r only ever reads TMEM lane r and writes smem row r; the tiles P overwrites (Q, K0, K1, pad) were consumed by
   // the S MMAs, which completed before bars[1] fired
 #pragma unroll 1
-  for (int c = 0; c < 8; ++c) {
+  for (int c = 0; c < (warp_valid ? nch : 0); ++c) {
     uint32_t v[32];
     tmem_ld_32x32(taddr + c * 32, v);
     tmem_ld_wait();
@@ -266,8 +271,9 @@ attn_fwd_tc2_kernel(const AttnTcParams p, const __grid_constant__ CUtensorMap ma
   if (tid == 0) {
     tc_fence_after();
     constexpr uint32_t idesc = make_idesc_bf16(128, 64, false, true);  // A = P K-major (4 tiles of 64 keys), B = V MN-major
-#pragma unroll
-    for (int k = 0; k < 16; ++k)
+    const int ksteps = (S + 15) >> 4;  // 16 keys per MMA
+#pragma unroll 1
+    for (int k = 0; k < ksteps; ++k)
       umma_bf16<1>(tmem, desc_k(sQ + (k >> 2) * TILE, k & 3), desc_mn(sV + (k >> 3) * TILE, k & 7, TILE), idesc, k != 0);
     umma_commit<1>(&bars[2]);
   }
