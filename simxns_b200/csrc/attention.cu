@@ -566,7 +566,7 @@ int attention_backward(int np, const bf16* qkv, long ps_qkv, const bf16* ctx, co
                        const int64_t* mask, const float* lse2, float* delta, int B, int S, int H, int heads,
                        float* dbias, cudaStream_t st) {
   SIMX_TRY(attn_check(B, S, H, heads));
-  if (use_tc_attention(np, S) || use_tc_attention(np, S - 128)) {  // S <= 256: one or 2 x 2 tcgen05 blocks
+  if (use_tc_attention(np, min(S, 128))) {  // bf16 mode, any S <= 512: ceil(S/128)^2 independent tcgen05 blocks
     ProfScope prof("attn_bwd", 10.0 * B * heads * (double)S * S * ATT_D, 2.0 * np * B * (double)S * 8 * H, st);
     return attention_tc_backward(qkv, ctx, dctx, dqkv, mask, lse2, B, S, H, heads, dbias, st);
   }

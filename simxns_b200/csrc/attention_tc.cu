@@ -9,9 +9,10 @@
 //              -> dV = P^T dO, dK = dS^T Q (A operands MN-major: the transposes are free), dQ = dS K -> three TMA stores.
 //              Five matmuls, each done once; no atomics, no recomputation.  256 TMEM columns, 112 KB smem: two CTAs/SM.
 //
-//   128 < S <= 256 : forward = attn_fwd_tc2_kernel (two key tiles resident, S[128,256] in TMEM); backward = the same
-//              single-tile kernel run on the 2 x 2 (query tile, key tile) blocks — P of a block needs only the forward's
-//              row log-sum-exp — with TMA reduce-add (bf16) of the dQ / dK / dV contributions into a zeroed dqkv.
+//   S > 128  : forward (S <= 256) = attn_fwd_tc2_kernel (two key tiles resident, S[128,256] in TMEM); backward (S <= 512)
+//              = the same single-tile kernel run on the ceil(S/128)^2 (query tile, key tile) blocks — P of a block needs
+//              only the forward's row log-sum-exp — with TMA reduce-add (bf16) of the dQ / dK / dV contributions into a
+//              zeroed dqkv.
 //
 // Reference math: LEAD/modeling_bert.py:324-368 (scores / sqrt(64) + extended mask, softmax, context).
 // Longer sequences (<= 512) and the fp32-class mode use the kernels in attention.cu.
@@ -332,9 +333,10 @@ attn_bwd_tc_kernel(const AttnTcParams p, const __grid_constant__ CUtensorMap map
   float* bias = reinterpret_cast<float*>(smem_raw + 64);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int h = blockIdx.x, b = blockIdx.y, S = p.S;
-  // 128 < S <= 256: the (sequence, head) problem is cut into 2 x 2 blocks of (128 queries) x (128 keys); P of a block
-  // needs only the forward's row log-sum-exp, so blocks are independent and their dQ / dK / dV contributions are
-  // accumulated in global memory with TMA reduce-add (dqkv zeroed by the host wrapper).  S <= 128: one block, plain stores.
+  // S > 128: the (sequence, head) problem is cut into kt x kt blocks of (128 queries) x (128 keys), kt = ceil(S / 128) <= 4;
+  // P of a block needs only the forward's row log-sum-exp, so blocks are independent and their dQ / dK / dV contributions
+  // are accumulated in global memory with TMA reduce-add (dqkv zeroed by the host wrapper).  S <= 128: one block, plain
+  // stores.
   const int kt = (S + 127) >> 7;
   const int q0 = (blockIdx.z / kt) * 128, k0 = (blockIdx.z % kt) * 128;
   SIMX_STAMP(0);
