@@ -132,6 +132,11 @@ class AdamW(torch.optim.Optimizer):
                                                     group["lr"], group["weight_decay"]))
         while len(self._tables) < len(buckets):
             self._tables.append(_Table())
+        if max_grad_norm is not None and len(buckets) > 1:
+            # parameters that differ in betas / eps / step count / device need several launches: the norm must still be
+            # the global one, so clip first (one table over every gradient), then update without the fused clip
+            self.last_grad_norm = clip_grad_norm_([r[0] for rows in buckets.values() for r in rows], max_grad_norm)
+            max_grad_norm = None
         touched = []
         for tab, ((dev, betas, eps, correct_bias, step), rows) in zip(self._tables, buckets.items()):
             with torch.cuda.device(dev):
@@ -140,9 +145,6 @@ class AdamW(torch.optim.Optimizer):
                 st = torch.cuda.current_stream(dev).cuda_stream
                 sq_ptr = None
                 if max_grad_norm is not None:
-                    if len(buckets) != 1:
-                        raise RuntimeError("step(max_grad_norm=...) needs all parameters in one launch (same betas / eps / "
-                                           "step count on one device); call optim.clip_grad_norm_ first instead")
                     sq = torch.empty((), dtype=torch.float64, device=dev)
                     _lib.check(lib.simx_grad_sq_norm(tab.dev.data_ptr(), tab.n, tab.chunks, sq.data_ptr(), st),
                                "simx_grad_sq_norm")
