@@ -611,3 +611,39 @@ def test_encoder_full_size_properties_bert_base():
     used = torch.zeros(ec.vocab, dtype=torch.bool, device="cuda")
     used[ids[sl].flatten()] = True
     assert float(gw[~used].abs().max()) == 0.0  # rows of tokens that never occur get exactly nothing
+
+
+def test_bf16_mode_tracks_fp32_class_mode_at_bert_base_width():
+    """the throughput mode against the fp32-class mode of the SAME kernels (itself pinned to the reference fixtures and
+    the oracle above) at the real width — H 768, 12 heads, I 3072, 512 passages x 128 tokens, 2 layers — where the oracle
+    is too slow: [CLS] embeddings within 3e-2 of their scale, every parameter gradient within 8e-2 of its tensor's scale
+    (the tolerances of the small-shape bf16 tests; SURVEY D6: the reference itself moves 3 % under bf16 autocast)"""
+    ec = EncoderConfig(num_layers=2)
+    torch.manual_seed(0)
+    ref = HFBertEncoder(ec, precision=X3).cuda()
+    fast = HFBertEncoder(ec, precision=BF16).cuda()
+    fast.load_state_dict(ref.state_dict())
+    gen = torch.Generator(device="cuda").manual_seed(5)
+    B, S = 512, 128
+    ids = torch.randint(1000, ec.vocab, (B, S), device="cuda", generator=gen)
+    ids[:, 0] = 101
+    lens = torch.randint(8, S + 1, (B,), device="cuda", generator=gen)
+    mask = (torch.arange(S, device="cuda")[None, :] < lens[:, None]).long()
+    ids = ids * mask
+    d = torch.randn(B, ec.hidden, device="cuda", generator=gen)
+    outs = []
+    for m in (ref, fast):
+        cls, _ = m.encode(ids, mask)
+        (cls[:, -1] * d).sum().backward()
+        outs.append(cls[:, -1].detach())
+    assert ((outs[1] - outs[0]).abs().max() / outs[0].abs().max()).item() < 3e-2
+    scales = [p.grad.abs().max().item() for p in ref.parameters()]
+    floor = 1e-3 * float(np.median([s for s in scales if s > 0]))
+    worst = ("", 0.0)
+    for (n, p), (_, q) in zip(ref.named_parameters(), fast.named_parameters()):
+        if "key.bias" in n:  # true-zero gradient (softmax shift invariance): round-off only in both modes
+            continue
+        e = ((q.grad - p.grad).abs().max() / max(p.grad.abs().max().item(), floor)).item()
+        if e > worst[1]:
+            worst = (n, e)
+    assert worst[1] < 8e-2, worst
