@@ -30,9 +30,28 @@ except Exception:  # pragma: no cover
 # configuration + canonical parameter naming (HF state_dict names)
 # ---------------------------------------------------------------------------------------------------------
 def bert_config(num_layers=12, hidden=768, heads=12, intermediate=3072, vocab=30522, max_pos=512, type_vocab=2,
-                ln_eps=1e-12, arch="bert"):
+                ln_eps=1e-12, arch="bert", pad_token_id=0, roberta_positions=False):
+    """roberta_positions: HF RobertaModel's position ids (transformers modeling_roberta.create_position_ids_from_input_ids,
+    used through /root/reference/SimANS/model/models.py:168-192 HFRobertaEncoder and :333-352 RobertaDot):
+    pad + cumsum(ids != pad) for real tokens, pad for padding; the pad row of BOTH embedding tables gets no gradient."""
     return dict(arch=arch, num_layers=num_layers, hidden=hidden, heads=heads, intermediate=intermediate, vocab=vocab,
-                max_pos=max_pos, type_vocab=(type_vocab if arch == "bert" else 0), ln_eps=ln_eps)
+                max_pos=max_pos, type_vocab=(type_vocab if arch == "bert" else 0), ln_eps=ln_eps,
+                pad_token_id=pad_token_id, roberta_positions=roberta_positions)
+
+
+def roberta_config(num_layers=12, hidden=768, heads=12, intermediate=3072, vocab=50265, max_pos=514, ln_eps=1e-5):
+    """RobertaConfig defaults of roberta-base: one token type, pad id 1, positions offset by the pad id"""
+    return bert_config(num_layers, hidden, heads, intermediate, vocab, max_pos, type_vocab=1, ln_eps=ln_eps,
+                       pad_token_id=1, roberta_positions=True)
+
+
+def position_ids(cfg, ids):
+    ids = np.asarray(ids)
+    if not cfg.get("roberta_positions", False):
+        return np.broadcast_to(np.arange(ids.shape[1]), ids.shape)
+    pad = cfg["pad_token_id"]
+    m = (ids != pad).astype(np.int64)
+    return np.cumsum(m, axis=1) * m + pad
 
 
 def param_names(cfg):
@@ -164,14 +183,15 @@ class EncoderOracle:
         if mask is None:
             mask = np.ones_like(ids)
         word, pos = self.p[0], self.p[1]
-        emb = word[ids] + pos[np.arange(S)][None]
+        pos_ids = position_ids(cfg, ids)
+        emb = word[ids] + pos[pos_ids]
         if cfg["arch"] == "bert":
             emb = emb + self.p[2][0][None, None]
             g, b = self.p[3], self.p[4]
         else:
             g, b = self.p[2], self.p[3]
         x, ln0 = layer_norm(emb, g, b, cfg["ln_eps"])
-        self.cache = dict(ids=ids, mask=mask, ln0=ln0, layers=[])
+        self.cache = dict(ids=ids, mask=mask, ln0=ln0, layers=[], pos_ids=pos_ids)
         hidden = [x]
         neg = np.where(mask[:, None, None, :] > 0, 0.0, -np.inf)
         for l in range(cfg["num_layers"]):
@@ -254,7 +274,12 @@ class EncoderOracle:
         else:
             g = self.p[2]
             demb, grads[2], grads[3] = layer_norm_bwd(dx, g, c["ln0"])
-        grads[1][:S] = demb.sum(0)
+        pad = cfg.get("pad_token_id", 0)
+        if cfg.get("roberta_positions", False):
+            np.add.at(grads[1], c["pos_ids"].reshape(-1), demb.reshape(-1, H))
+            grads[1][pad] = 0.0  # RobertaEmbeddings: position_embeddings has padding_idx too
+        else:
+            grads[1][:S] = demb.sum(0)
         np.add.at(grads[0], ids.reshape(-1), demb.reshape(-1, H))
-        grads[0][0] = 0.0  # nn.Embedding(padding_idx=0) in both archs: the pad row never receives gradient
+        grads[0][pad] = 0.0  # nn.Embedding(padding_idx=pad): the pad row never receives gradient
         return {n: g_ for n, g_ in zip(self.names, grads)}

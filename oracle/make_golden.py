@@ -287,6 +287,70 @@ def golden_losses_prod_kd(prod):
     print("losses_prod_kd", {k: float(v[0]) for k, v in res.items() if k.endswith("loss")})
 
 
+def roberta_tokens(B, S, vocab, seed, pad=1, min_len=3):
+    """right-padded RoBERTa-style rows: <s>=0 first, </s>=2 last valid, pad=1; mask = ids != pad"""
+    rng = np.random.RandomState(seed)
+    ids = rng.randint(3, vocab, size=(B, S)).astype(np.int64)
+    ids[:, 0] = 0
+    lens = rng.randint(min_len, S + 1, size=B)
+    for b in range(B):
+        ids[b, lens[b] - 1] = 2
+        ids[b, lens[b]:] = pad
+    return ids, (ids != pad).astype(np.int64)
+
+
+def golden_roberta(simans):
+    """SimANS MS-Doc towers (SimANS/model/models.py): HFRobertaEncoder :168-192 (RobertaModel with the dead pooler) and
+    RobertaDot :333-352 (RobertaModel without pooler + embeddingHead + LayerNorm on the first token), run unmodified on
+    CPU fp32 with seeded weights; position ids come from HF's create_position_ids_from_input_ids (pad id 1)."""
+    from transformers import RobertaConfig
+
+    from oracle.bert_numpy import roberta_config
+
+    cfg = roberta_config(num_layers=2, hidden=128, heads=2, intermediate=256, vocab=300, max_pos=66)
+    hf = RobertaConfig(vocab_size=cfg["vocab"], hidden_size=cfg["hidden"], num_hidden_layers=cfg["num_layers"],
+                       num_attention_heads=cfg["heads"], intermediate_size=cfg["intermediate"],
+                       max_position_embeddings=cfg["max_pos"], type_vocab_size=1, hidden_dropout_prob=0.0,
+                       attention_probs_dropout_prob=0.0, layer_norm_eps=cfg["ln_eps"], pad_token_id=1)
+    import copy
+
+    hf_dot = copy.deepcopy(hf)
+    hf_dot.return_dict = False  # what RobertaDot.__init__ sets under transformers 4 (models.py:337-338)
+    params = synth_params(cfg, seed=31)
+    ids, mask = roberta_tokens(5, 40, cfg["vocab"], seed=32)
+    rng = np.random.RandomState(33)
+    res = dict(ids=ids, mask=mask, seed=np.array([31]))
+    # (1) HFRobertaEncoder: (sequence_output, pooled = sequence_output[:, 0], None)
+    enc = simans.HFRobertaEncoder(hf)
+    load_params(enc, params)
+    enc.eval()
+    seq, pooled, _ = enc(input_ids=torch.from_numpy(ids), attention_mask=torch.from_numpy(mask))
+    d_seq = (rng.standard_normal(seq.shape) * mask[:, :, None]).astype(np.float32)
+    (seq * torch.from_numpy(d_seq)).sum().backward()
+    res.update(enc_seq=seq.detach().numpy(), enc_pooled=pooled.detach().numpy(), enc_d_seq=d_seq)
+    for n, p in enc.named_parameters():
+        res["enc_grad/" + n] = p.grad.numpy().copy()
+    # (2) RobertaDot.query_emb: norm(embeddingHead(first token))
+    dot = simans.RobertaDot(hf_dot)
+    load_params(dot.roberta, {k: v for k, v in params.items() if not k.startswith("pooler.")})
+    head_w = (0.05 * rng.standard_normal((cfg["hidden"], cfg["hidden"]))).astype(np.float32)
+    head_b = (0.02 * rng.standard_normal(cfg["hidden"])).astype(np.float32)
+    norm_w = (1 + 0.1 * rng.standard_normal(cfg["hidden"])).astype(np.float32)
+    norm_b = (0.02 * rng.standard_normal(cfg["hidden"])).astype(np.float32)
+    with torch.no_grad():
+        dot.embeddingHead.weight.copy_(torch.from_numpy(head_w)); dot.embeddingHead.bias.copy_(torch.from_numpy(head_b))
+        dot.norm.weight.copy_(torch.from_numpy(norm_w)); dot.norm.bias.copy_(torch.from_numpy(norm_b))
+    dot.eval()
+    emb = dot.query_emb(torch.from_numpy(ids), torch.from_numpy(mask))
+    d_emb = rng.standard_normal(emb.shape).astype(np.float32)
+    (emb * torch.from_numpy(d_emb)).sum().backward()
+    res.update(dot_emb=emb.detach().numpy(), dot_d_emb=d_emb, head_w=head_w, head_b=head_b, norm_w=norm_w, norm_b=norm_b)
+    for n, p in dot.named_parameters():
+        res["dot_grad/" + n] = p.grad.numpy().copy()
+    np.savez_compressed(GOLD / "roberta_tiny.npz", **res)
+    print("roberta_tiny", float(np.abs(res["enc_pooled"]).max()), float(np.abs(res["dot_emb"]).max()))
+
+
 def lead_shim():
     """make LEAD's vendored HF-4.x modeling files importable under transformers 5"""
     import transformers
@@ -401,6 +465,9 @@ def main():
         GOLD.mkdir(parents=True, exist_ok=True)
         golden_lead_distill()
         return
+    if only == ["roberta"]:
+        golden_roberta(import_from(REF / "SimANS", "model.models"))
+        return
     if only == ["prod_kd"]:
         golden_losses_prod_kd(import_from(REF / "PROD" / "ProD_KD", "model.models"))
         return
@@ -419,6 +486,7 @@ def main():
         golden_lead_distill()
     simans = import_from(REF / "SimANS", "model.models")
     golden_biencoder_cfg1(simans)
+    golden_roberta(simans)
 
 
 if __name__ == "__main__":
