@@ -113,6 +113,19 @@ int simx_encoder_backward(const simx_encoder_cfg* cfg, const float* const* param
                           const int64_t* ids, const int64_t* mask, int B, int S, const void* saved,
                           void* workspace, const float* d_cls, const float* d_seq, float* grads, void* stream);
 
+/* RoBERTa towers (SimANS MS-Doc: HFRobertaEncoder SimANS/model/models.py:168-192, RobertaDot :333-352 over HF
+ * RobertaModel) are BERT towers (type_vocab 1, ln_eps 1e-5, max_pos 514) whose position rows are chosen by the caller:
+ * pos_ids [B,S] int64 = pad + cumsum(ids != pad) for real tokens, pad for padding (HF create_position_ids_from_input_ids).
+ * Backward scatters the position gradient by pos_ids, and row `pad_token_id` of BOTH embedding tables receives none
+ * (nn.Embedding(padding_idx = pad) on both; the plain entry points above use pad id 0 for the word table, BERT's). */
+int simx_encoder_forward_pos(const simx_encoder_cfg* cfg, const float* const* params, const void* wbuf,
+                             const int64_t* ids, const int64_t* mask, const int64_t* pos_ids, int B, int S, void* saved,
+                             void* workspace, float* cls_out, float* seq_out, void* stream);
+int simx_encoder_backward_pos(const simx_encoder_cfg* cfg, const float* const* params, const void* wbuf,
+                              const int64_t* ids, const int64_t* mask, const int64_t* pos_ids, int pad_token_id, int B,
+                              int S, const void* saved, void* workspace, const float* d_cls, const float* d_seq,
+                              float* grads, void* stream);
+
 /* ------------------------------------------------------------------------------------------------
  * Fused score / loss / gradient step (replaces the tail of the train step:
  * co_training_marco_train.py:199-214, SimANS/model/models.py:468-505, PROD/ProD_KD/model/models.py:669-781,

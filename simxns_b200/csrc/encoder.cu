@@ -22,9 +22,9 @@ namespace simx {
 int gemm(int M, int N, int K, const bf16* A, long lda, long a_ps, bool a_mn, const bf16* B, long ldb, long b_ps,
          bool b_mn, int planes, int epi, const float* bias, const bf16* aux, long ldaux, long aux_ps, bf16* out,
          bf16* out2, long ldo, long out_ps, float* outf, long ldof, int ksplit, cudaStream_t stream);
-int embed_ln(int np, const int64_t* ids, int T, int S, int H, int vocab, const float* word, const float* pos,
-             const float* type0, const float* gamma, const float* beta, float eps, bf16* z0, bf16* x, long ps,
-             cudaStream_t st);
+int embed_ln(int np, const int64_t* ids, const int64_t* pos_ids, int max_pos, int T, int S, int H, int vocab,
+             const float* word, const float* pos, const float* type0, const float* gamma, const float* beta, float eps,
+             bf16* z0, bf16* x, long ps, cudaStream_t st);
 int ln_fwd(int np, const bf16* z, int T, int H, const float* gamma, const float* beta, float eps, bf16* x, long ps,
            cudaStream_t st);
 int ln_bwd(int np, const bf16* dy, const bf16* z, int T, int H, const float* gamma, float eps, bf16* dz, long ps,
@@ -34,7 +34,7 @@ int cls_gather(int np, const bf16* x, int B, int S, int H, long ps, float* out, 
 int cls_scatter_add(int np, bf16* dx, int B, int S, int H, long ps, const float* d, long d_stride_b, cudaStream_t st);
 int f32_to_planes(int np, const float* src, long n, bf16* dst, long ps, cudaStream_t st);
 int planes_to_f32(int np, const bf16* src, long n, long ps, float* dst, cudaStream_t st);
-int embed_scatter(int np, const int64_t* ids, const bf16* dz0, int T, int H, int vocab, long ps, float* dword,
+int embed_scatter(int np, const int64_t* ids, const bf16* dz0, int T, int H, int vocab, int pad_id, long ps, float* dword,
                   cudaStream_t st);
 int convert_weight(int np, const float* w, int R, int C, bf16* dst, long ld_dst, long ps_dst, bf16* dst_t, long ld_t,
                    long ps_t, cudaStream_t st);
@@ -292,9 +292,9 @@ extern "C" int simx_encoder_prepare_weights(const simx_encoder_cfg* cfg, const f
   return SIMX_OK;
 }
 
-extern "C" int simx_encoder_forward(const simx_encoder_cfg* cfg, const float* const* params, const void* wbuf,
-                                    const int64_t* ids, const int64_t* mask, int B, int S, void* saved, void* workspace,
-                                    float* cls_out, float* seq_out, void* stream) {
+static int encoder_forward_impl(const simx_encoder_cfg* cfg, const float* const* params, const void* wbuf,
+                                const int64_t* ids, const int64_t* mask, const int64_t* pos_ids, int B, int S, void* saved,
+                                void* workspace, float* cls_out, float* seq_out, void* stream) {
   SIMX_TRY(check_cfg(cfg));
   SIMX_CHECK(params && wbuf && ids, SIMX_ERR_INVALID, "encoder_forward: null argument");
   SIMX_CHECK(B > 0 && S > 0 && S <= cfg->max_pos && S <= 512, SIMX_ERR_INVALID,
@@ -323,7 +323,8 @@ extern "C" int simx_encoder_forward(const simx_encoder_cfg* cfg, const float* co
   const float* type0 = t.bert ? params[2] : nullptr;
   const float* eg = params[t.bert ? 3 : 2];
   const float* eb = params[t.bert ? 4 : 3];
-  SIMX_TRY(embed_ln(np, ids, T, S, H, cfg->vocab, params[0], params[1], type0, eg, eb, cfg->ln_eps, z0, xbuf(0), psH, st));
+  SIMX_TRY(embed_ln(np, ids, pos_ids, cfg->max_pos, T, S, H, cfg->vocab, params[0], params[1], type0, eg, eb, cfg->ln_eps, z0,
+                    xbuf(0), psH, st));
   const long cls_stride_b = (long)(L + 1) * H;
   if (cls_out) SIMX_TRY(cls_gather(np, xbuf(0), B, S, H, psH, cls_out, cls_stride_b, st));
 
@@ -375,10 +376,22 @@ extern "C" int simx_encoder_forward(const simx_encoder_cfg* cfg, const float* co
   return SIMX_OK;
 }
 
-extern "C" int simx_encoder_backward(const simx_encoder_cfg* cfg, const float* const* params, const void* wbuf,
-                                     const int64_t* ids, const int64_t* mask, int B, int S, const void* saved,
-                                     void* workspace, const float* d_cls, const float* d_seq, float* grads,
-                                     void* stream) {
+extern "C" int simx_encoder_forward(const simx_encoder_cfg* cfg, const float* const* params, const void* wbuf,
+                                    const int64_t* ids, const int64_t* mask, int B, int S, void* saved, void* workspace,
+                                    float* cls_out, float* seq_out, void* stream) {
+  return encoder_forward_impl(cfg, params, wbuf, ids, mask, nullptr, B, S, saved, workspace, cls_out, seq_out, stream);
+}
+extern "C" int simx_encoder_forward_pos(const simx_encoder_cfg* cfg, const float* const* params, const void* wbuf,
+                                        const int64_t* ids, const int64_t* mask, const int64_t* pos_ids, int B, int S,
+                                        void* saved, void* workspace, float* cls_out, float* seq_out, void* stream) {
+  SIMX_CHECK(pos_ids != nullptr, SIMX_ERR_INVALID, "encoder_forward_pos: null position ids");
+  return encoder_forward_impl(cfg, params, wbuf, ids, mask, pos_ids, B, S, saved, workspace, cls_out, seq_out, stream);
+}
+
+static int encoder_backward_impl(const simx_encoder_cfg* cfg, const float* const* params, const void* wbuf,
+                                 const int64_t* ids, const int64_t* mask, const int64_t* pos_ids, int pad_id, int B, int S,
+                                 const void* saved, void* workspace, const float* d_cls, const float* d_seq, float* grads,
+                                 void* stream) {
   SIMX_TRY(check_cfg(cfg));
   SIMX_CHECK(params && wbuf && ids && saved && workspace && grads, SIMX_ERR_INVALID, "encoder_backward: null argument");
   SIMX_CHECK(d_cls != nullptr || d_seq != nullptr, SIMX_ERR_INVALID, "encoder_backward: no cotangent given");
@@ -482,8 +495,28 @@ extern "C" int simx_encoder_backward(const simx_encoder_cfg* cfg, const float* c
   const bf16* z0 = reinterpret_cast<const bf16*>(sb + sl.z0);
   const int ig = t.bert ? 3 : 2;
   SIMX_TRY(ln_bwd(np, dx, z0, T, H, params[ig], cfg->ln_eps, dza, psH, G(ig), G(ig + 1), t.bert ? G(2) : nullptr, st));
-  // position rows: dPos[s] = sum_b dz0[b*S + s]: a column sum of the [B, S*H] view
-  SIMX_TRY(colsum(np, dza, B, S * H, (long)S * H, psH, G(1), st));
-  SIMX_TRY(embed_scatter(np, ids, dza, T, H, cfg->vocab, psH, G(0), st));
+  if (pos_ids == nullptr) {
+    // position rows: dPos[s] = sum_b dz0[b*S + s]: a column sum of the [B, S*H] view
+    SIMX_TRY(colsum(np, dza, B, S * H, (long)S * H, psH, G(1), st));
+  } else {
+    // caller-supplied position ids (RoBERTa): scatter-add like the word rows; the pad position row gets nothing
+    SIMX_TRY(embed_scatter(np, pos_ids, dza, T, H, cfg->max_pos, pad_id, psH, G(1), st));
+  }
+  SIMX_TRY(embed_scatter(np, ids, dza, T, H, cfg->vocab, pad_id, psH, G(0), st));
   return SIMX_OK;
+}
+
+extern "C" int simx_encoder_backward(const simx_encoder_cfg* cfg, const float* const* params, const void* wbuf,
+                                     const int64_t* ids, const int64_t* mask, int B, int S, const void* saved,
+                                     void* workspace, const float* d_cls, const float* d_seq, float* grads,
+                                     void* stream) {
+  return encoder_backward_impl(cfg, params, wbuf, ids, mask, nullptr, 0, B, S, saved, workspace, d_cls, d_seq, grads, stream);
+}
+extern "C" int simx_encoder_backward_pos(const simx_encoder_cfg* cfg, const float* const* params, const void* wbuf,
+                                         const int64_t* ids, const int64_t* mask, const int64_t* pos_ids, int pad_token_id,
+                                         int B, int S, const void* saved, void* workspace, const float* d_cls,
+                                         const float* d_seq, float* grads, void* stream) {
+  SIMX_CHECK(pos_ids != nullptr, SIMX_ERR_INVALID, "encoder_backward_pos: null position ids");
+  return encoder_backward_impl(cfg, params, wbuf, ids, mask, pos_ids, pad_token_id, B, S, saved, workspace, d_cls, d_seq,
+                               grads, stream);
 }

@@ -60,15 +60,22 @@ __device__ __forceinline__ void ln_row_store(float (&v)[MAXC][8], int H, int lan
 // ------------------------------------------------------------------------------------------------
 template <int NP>
 __global__ void __launch_bounds__(ROW_THREADS)
-embed_ln_kernel(const int64_t* __restrict__ ids, int T, int S, int H, int vocab, const float* __restrict__ word,
-                const float* __restrict__ pos, const float* __restrict__ type0, const float* __restrict__ gamma,
-                const float* __restrict__ beta, float eps, bf16* z0, bf16* x, long ps) {
+embed_ln_kernel(const int64_t* __restrict__ ids, const int64_t* __restrict__ pos_ids, int max_pos, int T, int S, int H,
+                int vocab, const float* __restrict__ word, const float* __restrict__ pos,
+                const float* __restrict__ type0, const float* __restrict__ gamma, const float* __restrict__ beta, float eps,
+                bf16* z0, bf16* x, long ps) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int row = blockIdx.x * ROW_WARPS + warp;
   if (row >= T) return;
   long id = ids[row];
   if (id < 0 || id >= vocab) id = 0;  // out-of-range ids are a caller bug; stay in bounds
-  const int s = row % S;
+  // position row: the token's index in its sequence (BERT), or the caller's position ids (RoBERTa: pad + running count
+  // of real tokens)
+  long s = row % S;
+  if (pos_ids != nullptr) {
+    s = pos_ids[row];
+    if (s < 0 || s >= max_pos) s = 0;
+  }
   float v[MAXC][8];
 #pragma unroll
   for (int c = 0; c < MAXC; ++c) {
@@ -76,7 +83,7 @@ embed_ln_kernel(const int64_t* __restrict__ ids, int T, int S, int H, int vocab,
     if (col < H) {
       float w[8], p[8];
       ld8f(word + id * H + col, w);
-      ld8f(pos + (long)s * H + col, p);
+      ld8f(pos + s * H + col, p);
 #pragma unroll
       for (int i = 0; i < 8; ++i) v[c][i] = w[i] + p[i];
       if (type0 != nullptr) {
@@ -390,13 +397,13 @@ __global__ void planes_to_f32_kernel(const bf16* __restrict__ src, long n, long 
 // ------------------------------------------------------------------------------------------------
 template <int NP>
 __global__ void __launch_bounds__(ROW_THREADS)
-embed_scatter_kernel(const int64_t* __restrict__ ids, const bf16* __restrict__ dz0, int T, int H, int vocab, long ps,
-                     float* dword) {
+embed_scatter_kernel(const int64_t* __restrict__ ids, const bf16* __restrict__ dz0, int T, int H, int vocab, int pad_id,
+                     long ps, float* dword) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int row = blockIdx.x * ROW_WARPS + warp;
   if (row >= T) return;
   const long id = ids[row];
-  if (id <= 0 || id >= vocab) return;
+  if (id < 0 || id >= vocab || id == pad_id) return;  // nn.Embedding(padding_idx): the pad row never receives gradient
   for (int col = lane * 8; col < H; col += 256) {
     float v[8];
     plane_load8<NP>(dz0 + (long)row * H + col, ps, v);
@@ -487,15 +494,15 @@ __global__ void convert_weights_batched_kernel(const ConvJobs jobs) {
     else { constexpr int kNP = 3; CALL; }                               \
   } while (0)
 
-int embed_ln(int np, const int64_t* ids, int T, int S, int H, int vocab, const float* word, const float* pos,
-             const float* type0, const float* gamma, const float* beta, float eps, bf16* z0, bf16* x, long ps,
-             cudaStream_t st) {
+int embed_ln(int np, const int64_t* ids, const int64_t* pos_ids, int max_pos, int T, int S, int H, int vocab,
+             const float* word, const float* pos, const float* type0, const float* gamma, const float* beta, float eps,
+             bf16* z0, bf16* x, long ps, cudaStream_t st) {
   ProfScope prof("embed_ln", 0, (double)T * H * (8.0 + 4.0 * np), st);
   SIMX_CHECK(H % 8 == 0 && H <= 256 * MAXC, SIMX_ERR_INVALID, "hidden size %d unsupported (multiple of 8, <= %d)", H,
              256 * MAXC);
   const int grid = (T + ROW_WARPS - 1) / ROW_WARPS;
-  SIMX_NP_DISPATCH(np, (embed_ln_kernel<kNP><<<grid, ROW_THREADS, 0, st>>>(ids, T, S, H, vocab, word, pos, type0, gamma,
-                                                                           beta, eps, z0, x, ps)));
+  SIMX_NP_DISPATCH(np, (embed_ln_kernel<kNP><<<grid, ROW_THREADS, 0, st>>>(ids, pos_ids, max_pos, T, S, H, vocab, word, pos,
+                                                                           type0, gamma, beta, eps, z0, x, ps)));
   SIMX_LAUNCH_CHECK();
   return SIMX_OK;
 }
@@ -574,11 +581,11 @@ int planes_to_f32(int np, const bf16* src, long n, long ps, float* dst, cudaStre
   SIMX_LAUNCH_CHECK();
   return SIMX_OK;
 }
-int embed_scatter(int np, const int64_t* ids, const bf16* dz0, int T, int H, int vocab, long ps, float* dword,
+int embed_scatter(int np, const int64_t* ids, const bf16* dz0, int T, int H, int vocab, int pad_id, long ps, float* dword,
                   cudaStream_t st) {
   ProfScope prof("embed_scatter", 0, (double)T * H * (2.0 * np + 8.0), st);
   const int grid = (T + ROW_WARPS - 1) / ROW_WARPS;
-  SIMX_NP_DISPATCH(np, (embed_scatter_kernel<kNP><<<grid, ROW_THREADS, 0, st>>>(ids, dz0, T, H, vocab, ps, dword)));
+  SIMX_NP_DISPATCH(np, (embed_scatter_kernel<kNP><<<grid, ROW_THREADS, 0, st>>>(ids, dz0, T, H, vocab, pad_id, ps, dword)));
   SIMX_LAUNCH_CHECK();
   return SIMX_OK;
 }

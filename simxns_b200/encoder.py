@@ -31,6 +31,9 @@ class EncoderConfig:
     type_vocab: int = 2
     ln_eps: float = 1e-12
     init_range: float = 0.02
+    pad_token_id: int = 0            # row of the embedding tables that never receives gradient (nn.Embedding padding_idx)
+    roberta_positions: bool = False  # HF RobertaModel position ids: pad + cumsum(ids != pad), pad for padding
+    pooler: bool = True              # False: RobertaModel(add_pooling_layer=False) — no `pooler.*` parameters exposed
 
     def c_struct(self, precision: int) -> _lib.EncoderCfg:
         return _lib.EncoderCfg(
@@ -46,6 +49,7 @@ class EncoderConfig:
             return EncoderConfig(arch="distilbert", num_layers=cfg.n_layers, hidden=cfg.dim, heads=cfg.n_heads,
                                  intermediate=cfg.hidden_dim, vocab=cfg.vocab_size, max_pos=cfg.max_position_embeddings,
                                  type_vocab=0, ln_eps=1e-12, init_range=getattr(cfg, "initializer_range", 0.02))
+        roberta = getattr(cfg, "model_type", "bert") in ("roberta", "xlm-roberta")
         act = getattr(cfg, "hidden_act", "gelu")
         if act not in ("gelu",):
             raise NotImplementedError(f"hidden_act={act!r}: only the exact erf GELU of BERT is implemented")
@@ -54,7 +58,8 @@ class EncoderConfig:
         return EncoderConfig(arch="bert", num_layers=cfg.num_hidden_layers, hidden=cfg.hidden_size,
                              heads=cfg.num_attention_heads, intermediate=cfg.intermediate_size, vocab=cfg.vocab_size,
                              max_pos=cfg.max_position_embeddings, type_vocab=cfg.type_vocab_size,
-                             ln_eps=cfg.layer_norm_eps, init_range=getattr(cfg, "initializer_range", 0.02))
+                             ln_eps=cfg.layer_norm_eps, init_range=getattr(cfg, "initializer_range", 0.02),
+                             pad_token_id=(cfg.pad_token_id if roberta else 0), roberta_positions=roberta)
 
 
 # Every torch.optim.Optimizer.step() — including subclasses that write through `p.data` and therefore never bump
@@ -96,8 +101,9 @@ def _container(**children) -> nn.Module:
 
 def _build_bert_skeleton(owner: nn.Module, c: EncoderConfig) -> List[nn.Parameter]:
     H, I = c.hidden, c.intermediate
-    emb = _container(word_embeddings=nn.Embedding(c.vocab, H, padding_idx=0),
-                     position_embeddings=nn.Embedding(c.max_pos, H),
+    emb = _container(word_embeddings=nn.Embedding(c.vocab, H, padding_idx=c.pad_token_id),
+                     position_embeddings=nn.Embedding(c.max_pos, H,
+                                                      padding_idx=c.pad_token_id if c.roberta_positions else None),
                      token_type_embeddings=nn.Embedding(c.type_vocab, H),
                      LayerNorm=nn.LayerNorm(H, eps=c.ln_eps))
     layers = nn.ModuleList()
@@ -119,7 +125,14 @@ def _build_bert_skeleton(owner: nn.Module, c: EncoderConfig) -> List[nn.Paramete
     order += [pooler.dense.weight, pooler.dense.bias]
     owner.add_module("embeddings", emb)
     owner.add_module("encoder", _container(layer=layers))
-    owner.add_module("pooler", pooler)
+    if c.pooler:
+        owner.add_module("pooler", pooler)
+    else:
+        # the kernel's parameter table always has the two (dead) pooler slots: keep zero placeholders that follow the
+        # module between devices but are neither parameters nor part of the state_dict
+        owner.register_buffer("_no_pooler_w", torch.zeros(H, H), persistent=False)
+        owner.register_buffer("_no_pooler_b", torch.zeros(H), persistent=False)
+        order[-2:] = [owner._no_pooler_w, owner._no_pooler_b]
     return order
 
 
@@ -185,7 +198,10 @@ class B200EncoderBase(nn.Module):
 
     def _apply(self, fn, *a, **k):  # .to() / .cuda() replace parameter storage: drop cached device state
         self._wbuf, self._wkey = None, None
-        return super()._apply(fn, *a, **k)
+        out = super()._apply(fn, *a, **k)
+        if not self.enc_cfg.pooler and self.enc_cfg.arch == "bert":  # buffers are re-created by _apply: re-link the table
+            self._ordered[-2:] = [self._no_pooler_w, self._no_pooler_b]
+        return out
 
     def _c_cfg(self) -> _lib.EncoderCfg:
         return self.enc_cfg.c_struct(self.precision)
@@ -269,6 +285,14 @@ class _EncoderFn(torch.autograd.Function):
             ec = module.enc_cfg
             if S > min(ec.max_pos, 512):
                 raise ValueError(f"sequence length {S} exceeds min(max_position_embeddings={ec.max_pos}, 512)")
+            pos_ids = None
+            if ec.roberta_positions:
+                # transformers create_position_ids_from_input_ids: pad + running count of real tokens, pad for padding
+                if S + ec.pad_token_id >= ec.max_pos:
+                    raise ValueError(f"sequence length {S} needs position {S + ec.pad_token_id} >= "
+                                     f"max_position_embeddings={ec.max_pos}")
+                real = (ids != ec.pad_token_id).to(torch.int64)
+                pos_ids = (torch.cumsum(real, dim=1) * real + ec.pad_token_id).contiguous()
             needs_grad = any(ctx.needs_input_grad[4:])  # grad mode is always off inside Function.forward
             wbuf = module._weights(params)
             table = module._param_table(params)
@@ -279,12 +303,17 @@ class _EncoderFn(torch.autograd.Function):
             saved = None
             if needs_grad:
                 saved = torch.empty(lib.simx_encoder_saved_bytes(C.byref(cfg), B, S), dtype=torch.uint8, device=dev)
-            _lib.check(lib.simx_encoder_forward(C.byref(cfg), table, wbuf.data_ptr(), ids.data_ptr(), _lib.ptr(mask), B, S,
-                                                _lib.ptr(saved), ws.data_ptr(), cls.data_ptr(), _lib.ptr(seq), stream),
-                       "simx_encoder_forward")
+            if pos_ids is None:
+                _lib.check(lib.simx_encoder_forward(C.byref(cfg), table, wbuf.data_ptr(), ids.data_ptr(), _lib.ptr(mask), B, S,
+                                                    _lib.ptr(saved), ws.data_ptr(), cls.data_ptr(), _lib.ptr(seq), stream),
+                           "simx_encoder_forward")
+            else:
+                _lib.check(lib.simx_encoder_forward_pos(C.byref(cfg), table, wbuf.data_ptr(), ids.data_ptr(), _lib.ptr(mask),
+                                                        pos_ids.data_ptr(), B, S, _lib.ptr(saved), ws.data_ptr(),
+                                                        cls.data_ptr(), _lib.ptr(seq), stream), "simx_encoder_forward_pos")
         ctx.module = module
         ctx.saved_act = saved
-        ctx.ids, ctx.mask, ctx.shape = ids, mask, (B, S)
+        ctx.ids, ctx.mask, ctx.shape, ctx.pos_ids = ids, mask, (B, S), pos_ids
         ctx.want_seq = want_seq
         ctx.wbuf = wbuf
         ctx.params = params
@@ -317,10 +346,17 @@ class _EncoderFn(torch.autograd.Function):
                 d_seq = None
             ws = torch.empty(lib.simx_encoder_workspace_bytes(C.byref(cfg), B, S), dtype=torch.uint8, device=dev)
             flat = torch.empty(lib.simx_encoder_grad_numel(C.byref(cfg)), dtype=torch.float32, device=dev)
-            _lib.check(lib.simx_encoder_backward(C.byref(cfg), module._param_table(params), ctx.wbuf.data_ptr(),
-                                                 ctx.ids.data_ptr(), _lib.ptr(ctx.mask), B, S, ctx.saved_act.data_ptr(),
-                                                 ws.data_ptr(), _lib.ptr(d_cls), _lib.ptr(d_seq), flat.data_ptr(), stream),
-                       "simx_encoder_backward")
+            if ctx.pos_ids is None:
+                _lib.check(lib.simx_encoder_backward(C.byref(cfg), module._param_table(params), ctx.wbuf.data_ptr(),
+                                                     ctx.ids.data_ptr(), _lib.ptr(ctx.mask), B, S, ctx.saved_act.data_ptr(),
+                                                     ws.data_ptr(), _lib.ptr(d_cls), _lib.ptr(d_seq), flat.data_ptr(), stream),
+                           "simx_encoder_backward")
+            else:
+                _lib.check(lib.simx_encoder_backward_pos(C.byref(cfg), module._param_table(params), ctx.wbuf.data_ptr(),
+                                                         ctx.ids.data_ptr(), _lib.ptr(ctx.mask), ctx.pos_ids.data_ptr(),
+                                                         module.enc_cfg.pad_token_id, B, S, ctx.saved_act.data_ptr(),
+                                                         ws.data_ptr(), _lib.ptr(d_cls), _lib.ptr(d_seq), flat.data_ptr(),
+                                                         stream), "simx_encoder_backward_pos")
         ctx.saved_act = None
         grads = []
         for p, (off, n), need in zip(params, module.grad_slices(), ctx.needs_input_grad[n_lead:]):

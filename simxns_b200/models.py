@@ -12,6 +12,7 @@ There is no PyTorch/CPU fallback: parameters must live on a B200 before forward(
 """
 from __future__ import annotations
 
+import dataclasses
 import json
 import os
 from pathlib import Path
@@ -26,7 +27,8 @@ from torch import nn
 from .encoder import B200EncoderBase, EncoderConfig
 from .losses import BiEncoderNllLoss, CrossBERTKDLoss, simans_distill_loss  # noqa: F401  (re-exported: reference names)
 
-__all__ = ["HFBertEncoder", "HFDistilBertEncoder", "BiBertEncoder", "Reranker", "ProdReranker", "BiEncoderNllLoss",
+__all__ = ["HFBertEncoder", "HFDistilBertEncoder", "HFRobertaEncoder", "BiBertEncoder", "BiRobertaEncoder", "RobertaDot",
+           "Reranker", "ProdReranker", "BiEncoderNllLoss",
            "CrossBERTKDLoss",
            "simans_distill_loss", "dot_product_scores", "init_weights"]
 
@@ -40,7 +42,8 @@ def _load_hf_config(model_type, arch="bert"):
     try:
         import transformers
 
-        cls = transformers.DistilBertConfig if arch == "distilbert" else transformers.BertConfig
+        cls = {"distilbert": transformers.DistilBertConfig, "roberta": transformers.RobertaConfig}.get(
+            arch, transformers.BertConfig)
         return cls.from_pretrained(model_type)
     except ImportError:
         with open(Path(model_type) / "config.json") as f:
@@ -315,3 +318,107 @@ class ProdReranker(Reranker):
     def _forward(self, input_ids, attention_mask):
         _, pooled, _ = self.encoder(input_ids=input_ids, attention_mask=attention_mask, _want_sequence=False)
         return self.binary(pooled), self.qa_classifier(pooled), None
+
+
+# ---------------------------------------------------------------------------------------------------------
+# SimANS MS-Doc towers (RoBERTa): SimANS/model/models.py:168-232 (HFRobertaEncoder, BiRobertaEncoder), :262-352
+# (EmbeddingMixin, BaseModelDot, RobertaDot)
+# ---------------------------------------------------------------------------------------------------------
+class HFRobertaEncoder(HFBertEncoder):
+    """HF RobertaModel on the B200 kernels: the BERT block with one token type, LayerNorm eps 1e-5 and RoBERTa's position
+    ids (pad + running count of real tokens; pad id 1 on both embedding tables).  Same forward contract as
+    HFBertEncoder: (sequence_output, sequence_output[:, 0], None); `add_pooling_layer=False` drops the (dead) pooler
+    parameters from the module, as RobertaDot's backbone does."""
+
+    def __init__(self, config, precision: Optional[int] = None, add_pooling_layer: bool = True):
+        if isinstance(config, EncoderConfig):
+            enc_cfg = config
+        else:
+            enc_cfg = EncoderConfig.from_hf(config)
+            if not enc_cfg.roberta_positions:  # a plain namespace without model_type: this class means RoBERTa
+                enc_cfg.roberta_positions, enc_cfg.pad_token_id = True, getattr(config, "pad_token_id", 1)
+        enc_cfg = dataclasses.replace(enc_cfg, pooler=bool(add_pooling_layer))
+        super().__init__(enc_cfg, precision)
+        if not isinstance(config, EncoderConfig):
+            self.config = config
+
+    @classmethod
+    def init_encoder(cls, args, dropout: float = 0.1, model_type=None):
+        if model_type is None:
+            model_type = args.model_type
+        cfg = _load_hf_config(model_type, "roberta")
+        if dropout != 0:
+            cfg.attention_probs_dropout_prob = dropout
+            cfg.hidden_dropout_prob = dropout
+        cfg.gradient_checkpointing = getattr(args, "gradient_checkpointing", False)
+        return cls.from_pretrained(model_type, config=cfg)
+
+    @classmethod
+    def from_pretrained(cls, model_type, config=None, **kw):
+        if config is None:
+            config = _load_hf_config(model_type, "roberta")
+        model = cls(config, **kw)
+        sd = _find_weights(model_type)
+        if sd is None:
+            raise FileNotFoundError(f"no pytorch_model.bin / model.safetensors found for {model_type!r}")
+        own = model.state_dict().keys()
+        stripped = {}
+        for k, v in sd.items():
+            for pre in ("", "roberta.", "model.roberta."):
+                if k.startswith(pre) and k[len(pre):] in own:
+                    stripped[k[len(pre):]] = v
+                    break
+        missing, _ = model.load_state_dict(stripped, strict=False)
+        if any("pooler" not in m for m in missing):
+            raise RuntimeError(f"checkpoint {model_type!r} lacks encoder weights: {missing[:5]} ...")
+        return model
+
+
+class BiRobertaEncoder(BiBertEncoder):
+    """SimANS/model/models.py:194-232: two HFRobertaEncoder towers behind the BiBertEncoder interface"""
+
+    def __init__(self, args, question_model: Optional[nn.Module] = None, ctx_model: Optional[nn.Module] = None):
+        nn.Module.__init__(self)
+        if question_model is not None:
+            self.question_model = question_model
+            self.ctx_model = ctx_model if ctx_model is not None else question_model
+            return
+        self.question_model = HFRobertaEncoder.init_encoder(args)
+        if hasattr(args, 'share_weight') and args.share_weight:
+            self.ctx_model = self.question_model
+        else:
+            self.ctx_model = HFRobertaEncoder.init_encoder(args)
+
+
+class RobertaDot(nn.Module):
+    """SimANS/model/models.py:333-352 (+ BaseModelDot :316-331, EmbeddingMixin :262-313): one shared RoBERTa tower
+    (`self.roberta`, no pooler), `embeddingHead = Linear(H, output_embedding_size)` and `norm = LayerNorm` on the first
+    token (or the masked mean when `model_argobj.use_mean`).  state_dict keys: roberta.*, embeddingHead.*, norm.*"""
+
+    def __init__(self, config, model_argobj=None, precision: Optional[int] = None):
+        super().__init__()
+        self.use_mean = False if model_argobj is None else bool(model_argobj.use_mean)
+        self.roberta = HFRobertaEncoder(config, precision=precision, add_pooling_layer=False)
+        hidden = self.roberta.enc_cfg.hidden
+        self.output_embedding_size = getattr(config, "output_embedding_size", hidden)
+        self.embeddingHead = nn.Linear(hidden, self.output_embedding_size)
+        self.norm = nn.LayerNorm(self.output_embedding_size)
+        for m in (self.embeddingHead,):  # EmbeddingMixin._init_weights: N(0, 0.02) weights (biases keep torch's default)
+            m.weight.data.normal_(mean=0.0, std=0.02)
+
+    def masked_mean(self, t, mask):
+        s = torch.sum(t * mask.unsqueeze(-1).float(), axis=1)
+        d = mask.sum(axis=1, keepdim=True).float()
+        return s / d
+
+    def query_emb(self, input_ids, attention_mask):
+        seq, first, _ = self.roberta(input_ids=input_ids, attention_mask=attention_mask, _want_sequence=self.use_mean)
+        full_emb = self.masked_mean(seq, attention_mask) if self.use_mean else first
+        return self.norm(self.embeddingHead(full_emb))
+
+    def body_emb(self, input_ids, attention_mask):
+        return self.query_emb(input_ids, attention_mask)
+
+    def forward(self, input_ids, attention_mask, is_query, *args):
+        assert len(args) == 0
+        return self.query_emb(input_ids, attention_mask) if is_query else self.body_emb(input_ids, attention_mask)

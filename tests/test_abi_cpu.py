@@ -184,3 +184,22 @@ def test_merge_candidates_orders_by_score_then_id():
     assert i.tolist() == [[4, 6, 9, 5]] and d.tolist() == [[3.0, 3.0, 3.0, 2.0]]
     d, i = merge_candidates(D, I, 6)
     assert i.tolist()[0][-1] == -1 and d.tolist()[0][-1] == float("-inf")
+
+
+def test_roberta_modules_have_the_reference_key_sets():
+    """HFRobertaEncoder == HF RobertaModel keys (with the dead pooler); RobertaDot == roberta.* without pooler +
+    embeddingHead / norm (SimANS/model/models.py:168-192, 333-352); the two pooler slots of the kernel's parameter
+    table are non-persistent zero buffers there"""
+    from simxns_b200.models import HFRobertaEncoder, RobertaDot
+
+    ec = EncoderConfig(num_layers=1, hidden=64, heads=1, intermediate=128, vocab=50, max_pos=20, type_vocab=1, ln_eps=1e-5,
+                       pad_token_id=1, roberta_positions=True)
+    enc = HFRobertaEncoder(ec)
+    assert "pooler.dense.weight" in enc.state_dict() and len(enc.state_dict()) == 5 + 16 + 2
+    assert enc.embeddings.word_embeddings.padding_idx == 1 and enc.embeddings.position_embeddings.padding_idx == 1
+    dot = RobertaDot(ec)
+    keys = list(dot.state_dict())
+    assert not any("pooler" in k for k in keys) and len(keys) == 5 + 16 + 4
+    assert {"embeddingHead.weight", "embeddingHead.bias", "norm.weight", "norm.bias"} <= set(keys)
+    assert len(dot.roberta.ordered_parameters()) == 5 + 16 + 2  # the table still has the two pooler slots
+    assert ec.pooler is True  # the caller's config object is not modified
