@@ -19,7 +19,6 @@ import os
 import subprocess
 import sys
 import threading
-import time
 from pathlib import Path
 
 ROOT = Path(__file__).resolve().parent

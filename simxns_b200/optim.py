@@ -13,7 +13,6 @@ There is no CPU path: parameters and gradients must be fp32 CUDA tensors on a B2
 """
 from __future__ import annotations
 
-import ctypes as C
 from typing import Iterable, List, Optional, Union
 
 import torch
