@@ -14,7 +14,6 @@ from __future__ import annotations
 
 import dataclasses
 import json
-import os
 from pathlib import Path
 from types import SimpleNamespace
 from typing import Optional
