@@ -351,6 +351,80 @@ def golden_roberta(simans):
     print("roberta_tiny", float(np.abs(res["enc_pooled"]).max()), float(np.abs(res["dot_emb"]).max()))
 
 
+def golden_batch_layout():
+    """the reference's own Rocketqa_v2Dataset.__getitem__ and collate (SimANS/utils/MARCO_until_new.py:165-260) run on a
+    tiny synthetic corpus with a deterministic whitespace tokenizer: records the token lists the tokenizer returned (the
+    inputs of simxns_b200.data.pack_example) and the tensors the reference built from them"""
+    import random
+    import tempfile
+
+    sys.path.insert(0, str(REF / "SimANS"))
+    for m in [m for m in sys.modules if m == "utils" or m.startswith("utils.")]:
+        del sys.modules[m]
+    from utils.MARCO_until_new import Rocketqa_v2Dataset
+
+    class Tok:
+        pad_token_id, sep_token_id, cls_token_id = 0, 102, 101
+
+        def __init__(self):
+            self.calls = []
+
+        def _ids(self, text):
+            return [1000 + (sum(ord(ch) for ch in w) % 700) for w in text.split()]
+
+        def encode(self, text, text_pair=None, add_special_tokens=True, max_length=128, truncation=True,
+                   pad_to_max_length=False):
+            a = self._ids(text)
+            if text_pair is None:
+                ids = [self.cls_token_id] + a[:max_length - 2] + [self.sep_token_id]
+            else:
+                b = self._ids(text_pair)
+                while len(a) + len(b) + 3 > max_length:  # longest_first
+                    (a if len(a) > len(b) else b).pop()
+                ids = [self.cls_token_id] + a + [self.sep_token_id] + b + [self.sep_token_id]
+            self.calls.append(ids)
+            return ids
+
+    rng = np.random.RandomState(5)
+    words = ["w%d" % i for i in range(400)]
+    sent = lambda n: " ".join(rng.choice(words, n))
+    tmp = Path(tempfile.mkdtemp())
+    n_pass = 40
+    with open(tmp / "para.txt", "w") as f:
+        for i in range(n_pass):
+            f.write(f"{i}\t{sent(rng.randint(5, 200))}\n")  # some passages overflow 128 tokens and are truncated
+    with open(tmp / "para.title.txt", "w") as f:
+        for i in range(0, n_pass, 2):  # half of the passages have no title -> '-'
+            f.write(f"{i}\t{sent(rng.randint(1, 6))}\n")
+    with open(tmp / "train.tsv", "w") as f:
+        for q in range(4):
+            pos = f"{q} {75 + q}"
+            negs = ",".join(f"{p} {74.5 - 0.3 * j}" for j, p in enumerate(range(10, 30)))
+            f.write(f"{q}\t{sent(rng.randint(3, 50))}\t{pos}\t{negs}\n")  # one query overflows 32 tokens
+    tok = Tok()
+    ds = Rocketqa_v2Dataset(str(tmp / "train.tsv"), tok, num_hard_negatives=3, corpus_path=str(tmp))
+    random.seed(0)
+    feats, res = [], {}
+    for i in range(len(ds)):
+        tok.calls = []
+        q, ctx, ce = ds[i]
+        feats.append((q, ctx, ce))
+        ctx_lists, q_list = tok.calls[:-1], tok.calls[-1]  # __getitem__ tokenises the passages first, then the query
+        res[f"ex{i}_q_tokens"] = np.array(q_list)
+        res[f"ex{i}_ctx_lens"] = np.array([len(c) for c in ctx_lists])
+        res[f"ex{i}_ctx_tokens"] = np.concatenate([np.array(c) for c in ctx_lists])
+        res[f"ex{i}_q"], res[f"ex{i}_ctx"], res[f"ex{i}_ce"] = q.numpy(), ctx.numpy(), ce.numpy()
+    batch = Rocketqa_v2Dataset.get_collate_fn(None)(feats)
+    for k, v in zip(("q", "q_mask", "d", "d_mask"), batch["student"][:4]):
+        res["batch_" + k] = v.numpy()
+    res["batch_pos"] = np.array(batch["student"][4])
+    for k, v in zip(("ce", "ce_mask", "tgt"), batch["teacher"]):
+        res["batch_" + k] = v.numpy()
+    res["n_examples"] = np.array([len(ds)])
+    np.savez_compressed(GOLD / "batch_layout.npz", **res)
+    print("batch_layout", {k: v.shape for k, v in res.items() if k.startswith("batch_")})
+
+
 def lead_shim():
     """make LEAD's vendored HF-4.x modeling files importable under transformers 5"""
     import transformers
@@ -465,6 +539,9 @@ def main():
         GOLD.mkdir(parents=True, exist_ok=True)
         golden_lead_distill()
         return
+    if only == ["data"]:
+        golden_batch_layout()
+        return
     if only == ["roberta"]:
         golden_roberta(import_from(REF / "SimANS", "model.models"))
         return
@@ -487,6 +564,7 @@ def main():
     simans = import_from(REF / "SimANS", "model.models")
     golden_biencoder_cfg1(simans)
     golden_roberta(simans)
+    golden_batch_layout()
 
 
 if __name__ == "__main__":
