@@ -421,6 +421,27 @@ def golden_batch_layout():
     for k, v in zip(("ce", "ce_mask", "tgt"), batch["teacher"]):
         res["batch_" + k] = v.numpy()
     res["n_examples"] = np.array([len(ds)])
+    # the NQ / TriviaQA collate (SimANS/utils/util_wiki.py:665-698) on ragged synthetic features: pads to the batch maximum
+    from utils.util_wiki import TraditionDataset
+
+    wrng = np.random.RandomState(9)
+    wfeats = []
+    for i in range(3):
+        q = [101] + wrng.randint(1000, 2000, wrng.randint(3, 40)).tolist() + [102]
+        ctxs = [[101] + wrng.randint(1000, 2000, wrng.randint(5, 120)).tolist() + [102] for _ in range(3)]
+        ces = [q + c[1:-1] for c in ctxs]
+        wfeats.append((q, ctxs, ces, [[7, 8]], [[len(q), len(c)] for c in ces]))
+    wb = TraditionDataset.get_collate_fn(None)(wfeats)
+    res["wiki_q_flat"] = np.concatenate([np.array(f[0]) for f in wfeats])
+    res["wiki_q_lens"] = np.array([len(f[0]) for f in wfeats])
+    res["wiki_ctx_flat"] = np.concatenate([np.array(c) for f in wfeats for c in f[1]])
+    res["wiki_ctx_lens"] = np.array([len(c) for f in wfeats for c in f[1]])
+    for k, v in zip(("ce", "ce_mask", "tgt"), wb["reranker"]):
+        res["wiki_" + k] = v.numpy()
+    for k, v in zip(("q", "q_mask", "d", "d_mask"), wb["retriever"][:4]):
+        res["wiki_" + k] = v.numpy()
+    res["wiki_pos"] = np.array(wb["retriever"][4])
+    res["wiki_start_end"] = np.array(wb["reranker_ctx_start_end"])
     np.savez_compressed(GOLD / "batch_layout.npz", **res)
     print("batch_layout", {k: v.shape for k, v in res.items() if k.startswith("batch_")})
 

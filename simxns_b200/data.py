@@ -7,6 +7,10 @@ workers produce them, so the dict drops into `train()` / `simxns_b200.train.retr
     batch = collate([ (q_ids, ctx_ids, ce_ids), ... ])
     batch == {'student': [q [B,32], q_mask, d [B*(1+n),128], d_mask, positive_ctx_indices],
               'teacher': [ce [B,1+n,160], ce_mask, tgt [B,1+n]]}
+
+`collate_wiki` is the NQ / TriviaQA variant (/root/reference/SimANS/utils/util_wiki.py:665-698): ragged token lists padded
+to the BATCH maximum (queries are not truncated there), keys 'retriever' / 'reranker' / 'answers' /
+'reranker_ctx_start_end' — the reason the kernels take any S <= 512.
 """
 from __future__ import annotations
 
@@ -54,3 +58,30 @@ def collate(features: List[Tuple[torch.Tensor, torch.Tensor, torch.Tensor]]) -> 
     tgt_tensor = tgt_tensor.reshape(q_num, d_num // q_num)
     return {'student': [q_tensor, (q_tensor != 0).long(), doc_tensor, (doc_tensor != 0).long(), positive_ctx_indices],
             'teacher': [ctx_tensor_out, (ctx_tensor_out != 0).long(), tgt_tensor]}
+
+
+def collate_wiki(features) -> dict:
+    """TraditionDataset.get_collate_fn (util_wiki.py:665-698).  feature = (question_token_ids, ctx_token_ids,
+    c_e_token_ids, answers, start_end) with plain Python lists of token ids."""
+    q_list, d_list, c_e_input_list, positive_ctx_indices, c_e_ctx_start_end = [], [], [], [], []
+    for feature in features:
+        positive_ctx_indices.append(len(d_list))
+        q_list.append(feature[0])
+        d_list.extend(feature[1])
+        c_e_input_list.extend(feature[2])
+        c_e_ctx_start_end.append(feature[4])
+    max_q_len = max(len(q) for q in q_list)
+    max_d_len = max(len(d) for d in d_list)
+    max_c_e_len = max(len(d) for d in c_e_input_list)
+    q_tensor = torch.LongTensor([q + [0] * (max_q_len - len(q)) for q in q_list])
+    doc_tensor = torch.LongTensor([d + [0] * (max_d_len - len(d)) for d in d_list])
+    ctx_tensor_out = torch.LongTensor([c + [0] * (max_c_e_len - len(c)) for c in c_e_input_list])
+    q_num, d_num = len(q_list), len(d_list)
+    tgt_tensor = torch.zeros((len(c_e_input_list)), dtype=torch.long)
+    tgt_tensor[positive_ctx_indices] = 1
+    ctx_tensor_out = ctx_tensor_out.reshape(q_num, d_num // q_num, -1)
+    tgt_tensor = tgt_tensor.reshape(q_num, d_num // q_num)
+    return {'reranker': [ctx_tensor_out, (ctx_tensor_out != 0).long(), tgt_tensor],
+            'retriever': [q_tensor, (q_tensor != 0).long(), doc_tensor, (doc_tensor != 0).long(), positive_ctx_indices],
+            "answers": [feature[3] for feature in features],
+            "reranker_ctx_start_end": c_e_ctx_start_end}

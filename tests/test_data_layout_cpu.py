@@ -45,3 +45,25 @@ def test_pack_example_edge_cases():
     assert q.shape == (32,) and ctx.shape == (2, 128) and ce.shape == (2, 160)
     with pytest.raises(ValueError):
         pack_example(list(range(1, 40)), [[101, 5, 102]])
+
+
+def test_wiki_collate_matches_the_reference_bit_exactly(golden_dir):
+    """TraditionDataset.get_collate_fn (SimANS/utils/util_wiki.py:665-698): everything padded to the batch maximum"""
+    from simxns_b200.data import collate_wiki
+
+    g = np.load(golden_dir / "batch_layout.npz")
+    qs = [a.tolist() for a in np.split(g["wiki_q_flat"], np.cumsum(g["wiki_q_lens"])[:-1])]
+    ctxs = [a.tolist() for a in np.split(g["wiki_ctx_flat"], np.cumsum(g["wiki_ctx_lens"])[:-1])]
+    feats = []
+    for i, q in enumerate(qs):
+        c = ctxs[3 * i:3 * i + 3]
+        ces = [q + x[1:-1] for x in c]
+        feats.append((q, c, ces, [[7, 8]], [[len(q), len(x)] for x in ces]))
+    b = collate_wiki(feats)
+    for k, v in zip(("ce", "ce_mask", "tgt"), b["reranker"]):
+        assert np.array_equal(v.numpy(), g["wiki_" + k]), k
+    for k, v in zip(("q", "q_mask", "d", "d_mask"), b["retriever"][:4]):
+        assert np.array_equal(v.numpy(), g["wiki_" + k]), k
+    assert b["retriever"][4] == g["wiki_pos"].tolist()
+    assert np.array_equal(np.array(b["reranker_ctx_start_end"]), g["wiki_start_end"])
+    assert b["retriever"][0].shape[1] == max(g["wiki_q_lens"]) and b["retriever"][2].shape[1] == max(g["wiki_ctx_lens"])
