@@ -446,6 +446,32 @@ def golden_batch_layout():
     print("batch_layout", {k: v.shape for k, v in res.items() if k.startswith("batch_")})
 
 
+def golden_lead_select_layer():
+    """LEAD/util.py:206-254 select_layer, the reference function itself, over every branch (seeded `random`)"""
+    import contextlib
+    import io
+    import json
+    import random
+
+    lead_shim()
+    util = import_from(REF / "LEAD", "util")
+    cases = []
+    for mode in ("random", "last", "skip"):
+        for name in ("distilbert-base-uncased", "bert-large-uncased"):
+            for add_linear in (False, True):
+                for train_file in ("data/ms/train.tsv", "data/nq/train.json"):
+                    for k in (3, 5):
+                        a = dict(layer_selection_random=mode == "random", layer_selection_last=mode == "last",
+                                 layer_selection_skip=mode == "skip", pretrained_model_name=name, add_linear=add_linear,
+                                 train_file=train_file, disitll_layer_num=k)
+                        random.seed(len(cases))
+                        with contextlib.redirect_stdout(io.StringIO()):
+                            db, te = util.select_layer(types.SimpleNamespace(**a))
+                        cases.append(dict(args=a, seed=len(cases), db=db, teacher=te))
+    (GOLD / "lead_select_layer.json").write_text(json.dumps(cases))
+    print("lead_select_layer", len(cases), "cases")
+
+
 def lead_shim():
     """make LEAD's vendored HF-4.x modeling files importable under transformers 5"""
     import transformers
@@ -560,6 +586,9 @@ def main():
         GOLD.mkdir(parents=True, exist_ok=True)
         golden_lead_distill()
         return
+    if only == ["select_layer"]:
+        golden_lead_select_layer()
+        return
     if only == ["data"]:
         golden_batch_layout()
         return
@@ -586,6 +615,7 @@ def main():
     golden_biencoder_cfg1(simans)
     golden_roberta(simans)
     golden_batch_layout()
+    golden_lead_select_layer()
 
 
 if __name__ == "__main__":

@@ -432,3 +432,30 @@ def lead_ce_distill_loss(q_db, c_db, ce_logits, cls_q_db=None, cls_c_db=None, ce
         loss = loss + layer_loss
         parts["loss_ce_db_layer_dis"] = layer_loss.detach()
     return loss, parts
+
+
+def select_layer(args):
+    """LEAD's choice of the layer pairs whose [CLS] scores are distilled (/root/reference/LEAD/util.py:206-254), re-drawn
+    every `save_steps` by run_LEAD.py.  Returns (selected_index_list_db, selected_index_list_teacher) for
+    lead_distill_loss / lead_ce_distill_loss.  `layer_selection_random` consumes Python's global `random` stream exactly
+    as the reference does (student list first, then the teacher list)."""
+    from random import sample
+
+    selected_index_list_db, selected_index_list_teacher = None, None
+    if args.layer_selection_random:
+        large = 'large' in args.pretrained_model_name
+        extra = 1 if args.add_linear else 0
+        n_db, n_teacher = (12, 24) if large else (6, 12)
+        selected_index_list_db = sorted(sample([i for i in range(n_db + extra)], args.disitll_layer_num))
+        selected_index_list_teacher = sorted(sample([i for i in range(n_teacher + extra)], args.disitll_layer_num))
+    elif args.layer_selection_last:
+        if 'ms' in args.train_file:  # passage distillation: 5 layers, document distillation: 6
+            selected_index_list_db, selected_index_list_teacher = [1, 2, 3, 4, 5], [7, 8, 9, 10, 11]
+        else:
+            selected_index_list_db, selected_index_list_teacher = [0, 1, 2, 3, 4, 5], [6, 7, 8, 9, 10, 11]
+    elif args.layer_selection_skip:
+        if 'ms' in args.train_file:
+            selected_index_list_db, selected_index_list_teacher = [1, 2, 3, 4, 5], [0, 2, 4, 6, 8]
+        else:
+            selected_index_list_db, selected_index_list_teacher = [0, 1, 2, 3, 4, 5], [0, 2, 4, 6, 8, 10]
+    return selected_index_list_db, selected_index_list_teacher
