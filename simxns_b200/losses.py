@@ -459,3 +459,28 @@ def select_layer(args):
         else:
             selected_index_list_db, selected_index_list_teacher = [0, 1, 2, 3, 4, 5], [0, 2, 4, 6, 8, 10]
     return selected_index_list_db, selected_index_list_teacher
+
+
+def global_positive_indices(local_positive_idxs, n_local_ctx: int, device=None, group=None) -> torch.Tensor:
+    """positives of ALL ranks' queries as columns of the rank-major gathered passage matrix: rank r's local index v
+    becomes v + (number of passages of ranks < r) — the bookkeeping of `caculate_cont_loss`
+    (/root/reference/MASTER/finetune/MS/run_de_model.py:203-220; same loop in PROD run_progressive_distill_marco.py:371-447).
+    Every rank must contribute the same number of queries and passages (the gathered matrices are dense)."""
+    idx = torch.as_tensor(list(local_positive_idxs), dtype=torch.int64, device=device)
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+        return idx.to(torch.int32)
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    out = idx.new_empty(world * idx.numel())
+    dist.all_gather_into_tensor(out, idx + rank * int(n_local_ctx), group=group)
+    return out.to(torch.int32)
+
+
+def caculate_cont_loss(args, local_q_vector, local_ctx_vectors, local_positive_idxs):
+    """Drop-in for `caculate_cont_loss` (run_de_model.py:180-234, spelling as in the reference): in-batch InfoNCE over the
+    embeddings of every rank.  The reference pickles the vectors, all-reduces a 640 MB byte buffer and rebuilds the
+    matrices on every rank; here the [CLS] rows are all-gathered over NCCL inside the fused loss and only the positive
+    indices travel separately.  -> (loss, is_correct)"""
+    pos = global_positive_indices(local_positive_idxs, local_ctx_vectors.shape[0], device=local_q_vector.device)
+    loss, detail = fused_score_loss(local_q_vector, local_ctx_vectors, ["nll_global"], pos_idx=pos, gather=True,
+                                    group_size=max(1, local_ctx_vectors.shape[0] // local_q_vector.shape[0]))
+    return loss, detail[6].round().to(torch.int64)

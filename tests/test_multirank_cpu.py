@@ -90,3 +90,29 @@ def test_two_rank_sharded_search_merge(tmp_path):
     for x in r:
         assert np.array_equal(x["I"], I)        # bit-exact ids (ties -> lowest global row) on every rank
         assert np.allclose(x["D"], D, atol=1e-12)
+
+
+def _posidx_worker(rank, world, port, out_dir):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from simxns_b200.losses import global_positive_indices
+
+    n_local_ctx = 12
+    local = [0, 5, 9] if rank == 0 else [2, 4, 11]  # positives need not sit at i*(1+n) (run_de_model.py:203-220)
+    g = global_positive_indices(local, n_local_ctx)
+    np.save(os.path.join(out_dir, f"p{rank}.npy"), g.numpy())
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_two_rank_positive_index_bookkeeping(tmp_path):
+    """the reference's loop: positive_idx_per_question.extend([v + total_ctxs for v in positive_idx]); total_ctxs += n"""
+    world = 2
+    mp.spawn(_posidx_worker, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
+    want, total = [], 0
+    for positive_idx in ([0, 5, 9], [2, 4, 11]):
+        want.extend([v + total for v in positive_idx])
+        total += 12
+    for r in range(world):
+        assert np.load(tmp_path / f"p{r}.npy").tolist() == want
