@@ -175,11 +175,18 @@ class EncoderOracle:
         return self.p[self.base + 16 * l: self.base + 16 * (l + 1)]
 
     # ---- forward ---------------------------------------------------------------------------------------
-    def forward(self, ids, mask=None):
+    def forward(self, ids, mask=None, dropout=None):
+        """dropout: None (eval / parity configuration) or dict(p_hidden=, p_attn=, seed=): the masks of
+        oracle/dropout_numpy.py at the HF sites (LEAD/modeling_bert.py:239, :358, :386, :464; DistilBERT has no dropout
+        after the attention output projection, LEAD/modeling_distilbert.py:254-319)."""
         cfg = self.cfg
         B, S = ids.shape
         H, nh = cfg["hidden"], cfg["heads"]
         d = H // nh
+        from oracle import dropout_numpy as dn
+        dr = dropout or dict(p_hidden=0.0, p_attn=0.0, seed=0)
+        ph, pa, seed = float(dr.get("p_hidden", 0.0)), float(dr.get("p_attn", 0.0)), int(dr.get("seed", 0))
+        hmask = lambda site, layer: dn.hidden_mask(seed, site, layer, B * S, H, ph).reshape(B, S, H)
         if mask is None:
             mask = np.ones_like(ids)
         word, pos = self.p[0], self.p[1]
@@ -191,7 +198,9 @@ class EncoderOracle:
         else:
             g, b = self.p[2], self.p[3]
         x, ln0 = layer_norm(emb, g, b, cfg["ln_eps"])
-        self.cache = dict(ids=ids, mask=mask, ln0=ln0, layers=[], pos_ids=pos_ids)
+        m0 = hmask(dn.SITE_EMBED, 0)
+        x = x * m0
+        self.cache = dict(ids=ids, mask=mask, ln0=ln0, layers=[], pos_ids=pos_ids, m0=m0)
         hidden = [x]
         neg = np.where(mask[:, None, None, :] > 0, 0.0, -np.inf)
         for l in range(cfg["num_layers"]):
@@ -203,14 +212,18 @@ class EncoderOracle:
             s = s - s.max(-1, keepdims=True)
             e = np.exp(s)
             p = e / e.sum(-1, keepdims=True)
-            ctx = (p @ v).transpose(0, 2, 1, 3).reshape(B, S, H)
-            z1 = ctx @ wo.T + bo + x
+            ma = dn.attn_mask(seed, l, B, nh, S, pa)
+            m2 = hmask(dn.SITE_ATTN_OUT, l) if cfg["arch"] == "bert" else np.ones((B, S, H))
+            m3 = hmask(dn.SITE_FFN_OUT, l)
+            ctx = ((p * ma) @ v).transpose(0, 2, 1, 3).reshape(B, S, H)
+            z1 = (ctx @ wo.T + bo) * m2 + x
             x1, ln1 = layer_norm(z1, g1, b1, cfg["ln_eps"])
             h = x1 @ wi.T + bi
             a = gelu(h)
-            z2 = a @ w2.T + b2 + x1
+            z2 = (a @ w2.T + b2) * m3 + x1
             x2, ln2 = layer_norm(z2, g2, bb2, cfg["ln_eps"])
-            self.cache["layers"].append(dict(x=x, q=q, k=k, v=v, p=p, ctx=ctx, ln1=ln1, x1=x1, h=h, a=a, ln2=ln2))
+            self.cache["layers"].append(dict(x=x, q=q, k=k, v=v, p=p, ctx=ctx, ln1=ln1, x1=x1, h=h, a=a, ln2=ln2,
+                                             ma=ma, m2=m2, m3=m3))
             x = x2
             hidden.append(x)
         self.hidden = hidden
@@ -238,22 +251,24 @@ class EncoderOracle:
             lc = c["layers"][l]
             gi = self.base + 16 * l
             dz2, grads[gi + 14], grads[gi + 15] = layer_norm_bwd(dx, g2, lc["ln2"])
-            f2 = dz2.reshape(-1, H)
+            dz2m = dz2 * lc["m3"]  # into the dense output (dropout sits between the dense and the residual add)
+            f2 = dz2m.reshape(-1, H)
             grads[gi + 13] = f2.sum(0)
             grads[gi + 12] = f2.T @ lc["a"].reshape(-1, lc["a"].shape[-1])
-            dh = (dz2 @ w2) * gelu_grad(lc["h"])
+            dh = (dz2m @ w2) * gelu_grad(lc["h"])
             fh = dh.reshape(-1, dh.shape[-1])
             grads[gi + 11] = fh.sum(0)
             grads[gi + 10] = fh.T @ lc["x1"].reshape(-1, H)
             dx1 = dh @ wi + dz2
             dz1, grads[gi + 8], grads[gi + 9] = layer_norm_bwd(dx1, g1, lc["ln1"])
-            f1 = dz1.reshape(-1, H)
+            dz1m = dz1 * lc["m2"]
+            f1 = dz1m.reshape(-1, H)
             grads[gi + 7] = f1.sum(0)
             grads[gi + 6] = f1.T @ lc["ctx"].reshape(-1, H)
-            dctx = (dz1 @ wo).reshape(B, S, nh, d).transpose(0, 2, 1, 3)
+            dctx = (dz1m @ wo).reshape(B, S, nh, d).transpose(0, 2, 1, 3)
             p, q, k, v = lc["p"], lc["q"], lc["k"], lc["v"]
-            dv = p.transpose(0, 1, 3, 2) @ dctx
-            dp = dctx @ v.transpose(0, 1, 3, 2)
+            dv = (p * lc["ma"]).transpose(0, 1, 3, 2) @ dctx
+            dp = (dctx @ v.transpose(0, 1, 3, 2)) * lc["ma"]
             ds = p * (dp - (dp * p).sum(-1, keepdims=True)) / math.sqrt(d)
             dq = ds @ k
             dk = ds.transpose(0, 1, 3, 2) @ q
@@ -267,6 +282,7 @@ class EncoderOracle:
             dx = dxl
             if d_cls is not None:
                 dx[:, 0, :] += d_cls[:, l, :]
+        dx = dx * c["m0"]
         if cfg["arch"] == "bert":
             g = self.p[3]
             demb, grads[3], grads[4] = layer_norm_bwd(dx, g, c["ln0"])

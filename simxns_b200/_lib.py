@@ -16,6 +16,7 @@ CSRC = _PKG / "csrc"
 
 SIMX_OK = 0
 ARCH_BERT, ARCH_DISTILBERT = 0, 1
+SAVE_ALL, SAVE_LAYER_INPUTS = 0, 1
 PREC_BF16, PREC_BF16X3 = 1, 3
 
 EPI_PLAIN, EPI_BIAS, EPI_BIAS_GELU, EPI_BIAS_ADD, EPI_MUL, EPI_ADD, EPI_ATOMIC_F32, EPI_BIAS_GELU_FWD = range(8)
@@ -38,6 +39,11 @@ class EncoderCfg(C.Structure):
         ("type_vocab", C.c_int32),
         ("precision", C.c_int32),
         ("ln_eps", C.c_float),
+        ("hidden_dropout", C.c_float),
+        ("attn_dropout", C.c_float),
+        ("dropout_seed", C.c_uint64),
+        ("save_policy", C.c_int32),
+        ("id_bytes", C.c_int32),
     ]
 
 
@@ -104,6 +110,7 @@ SIGNATURES = {
     "simx_encoder_backward": (_I, [_CFG, _P, _P, _P, _P, _I, _I, _P, _P, _P, _P, _P, _P]),
     "simx_encoder_forward_pos": (_I, [_CFG, _P, _P, _P, _P, _P, _I, _I, _P, _P, _P, _P, _P]),
     "simx_encoder_backward_pos": (_I, [_CFG, _P, _P, _P, _P, _P, _I, _I, _I, _P, _P, _P, _P, _P, _P]),
+    "simx_encoder_backward_layers": (_I, [_CFG, _P, _P, _P, _P, _P, _I, _I, _I, _P, _P, _P, _P, _P, _I, _I, _P]),
     "simx_score_loss_workspace_bytes": (C.c_size_t, [_LCFG]),
     "simx_score_loss": (_I, [_LCFG, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
     "simx_pair_distill_workspace_bytes": (C.c_size_t, [_I, _I, _I]),

@@ -124,11 +124,14 @@ struct AttnParams {
   bf16* ctx;        // [T, H]       (forward out / backward in: O)
   const bf16* dctx; // [T, H]
   bf16* dqkv;       // [T, 3H]
-  const int64_t* mask;  // [B, S] or NULL
+  const void* mask;  // [B, S] int64 / int32 (mask_w bytes per entry) or NULL
   float* lse2;      // [B, heads, S]  log2-domain log-sum-exp of the scaled, masked scores
   float* delta;     // [B, heads, S]
   int B, S, H, heads, s_pad;
+  int mask_w;
+  DropSpec drop;    // attention-probability dropout (forward kernel only; the mma.sync backward is a legacy path)
 };
+__device__ __forceinline__ uint32_t u4_word_rt(const uint4& r, int i) { return i == 0 ? r.x : (i == 1 ? r.y : (i == 2 ? r.z : r.w)); }
 
 // -------------------------------------------------------------------------------------------------
 // forward
@@ -151,7 +154,7 @@ attn_fwd_kernel(const AttnParams p) {
   load_tile(k_tile, base + p.H, ld, S, SP);
   load_tile(v_tile, base + 2 * p.H, ld, S, SP);
   for (int c = threadIdx.x; c < SP; c += ATT_THREADS)
-    bias[c] = (c < S && (p.mask == nullptr || p.mask[(long)b * S + c] != 0)) ? 0.f : NEG_BIG;
+    bias[c] = (c < S && (p.mask == nullptr || ld_id(p.mask, (long)b * S + c, p.mask_w) != 0)) ? 0.f : NEG_BIG;
   cp_async_wait_all();
   __syncthreads();
 
@@ -196,6 +199,19 @@ attn_fwd_kernel(const AttnParams p) {
       for (int j = 0; j < 8; ++j) {
         o[j][0] *= corr_lo; o[j][1] *= corr_lo; o[j][2] *= corr_hi; o[j][3] *= corr_hi;
       }
+      if (p.drop.thr_hi != 0u) {
+        // this thread holds keys c0 + 8j + 2t, +1 of rows r_lo / r_hi: word t of the 8-key group's Philox block
+        const uint32_t plane = b * p.heads + h, q_lo = row0 + warp * 16 + g;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const uint32_t w_lo = u4_word_rt(drop_bits(p.drop, (c0 >> 3) + j, q_lo, plane), t);
+          const uint32_t w_hi = u4_word_rt(drop_bits(p.drop, (c0 >> 3) + j, q_lo + 8, plane), t);
+          if ((w_lo << 16) < p.drop.thr_hi) s[j][0] = 0.f;
+          if (w_lo < p.drop.thr_hi) s[j][1] = 0.f;
+          if ((w_hi << 16) < p.drop.thr_hi) s[j][2] = 0.f;
+          if (w_hi < p.drop.thr_hi) s[j][3] = 0.f;
+        }
+      }
       mma_p_z(o, s, v_tile, lane, c0);
     }
     l_lo += __shfl_xor_sync(0xffffffffu, l_lo, 1);
@@ -208,7 +224,8 @@ attn_fwd_kernel(const AttnParams p) {
       if (r_lo < S) L[r_lo] = m_lo + log2f(l_lo);
       if (r_hi < S) L[r_hi] = m_hi + log2f(l_hi);
     }
-    store_rows(o, 1.f / l_lo, 1.f / l_hi, q_tile, q_ptr, warp, lane, p.ctx + (long)b * S * p.H + h * ATT_D, p.H, row0, S);
+    const float ksc = p.drop.thr_hi != 0u ? p.drop.scale : 1.f;
+    store_rows(o, ksc / l_lo, ksc / l_hi, q_tile, q_ptr, warp, lane, p.ctx + (long)b * S * p.H + h * ATT_D, p.H, row0, S);
   }
 }
 
@@ -239,7 +256,7 @@ attn_bwd_dq_kernel(const AttnParams p) {
   load_tile(k_tile, base + p.H, ld, S, SP);
   load_tile(v_tile, base + 2 * p.H, ld, S, SP);
   for (int c = threadIdx.x; c < SP; c += ATT_THREADS)
-    bias[c] = (c < S && (p.mask == nullptr || p.mask[(long)b * S + c] != 0)) ? 0.f : NEG_BIG;
+    bias[c] = (c < S && (p.mask == nullptr || ld_id(p.mask, (long)b * S + c, p.mask_w) != 0)) ? 0.f : NEG_BIG;
   {
     // delta[row] = sum_d dO[row,d] * O[row,d]: two lanes per row, 32 elements each
     const int r = warp * 16 + (lane >> 1), half = lane & 1;
@@ -333,8 +350,8 @@ attn_bwd_dkv_kernel(const AttnParams p) {
   if (row0 + warp * 16 >= S) return;
   const float sl2 = 0.125f * LOG2E;
   const int r_lo = row0 + warp * 16 + g, r_hi = r_lo + 8;
-  const float kb_lo = (r_lo < S && (p.mask == nullptr || p.mask[(long)b * S + r_lo] != 0)) ? 0.f : NEG_BIG;
-  const float kb_hi = (r_hi < S && (p.mask == nullptr || p.mask[(long)b * S + r_hi] != 0)) ? 0.f : NEG_BIG;
+  const float kb_lo = (r_lo < S && (p.mask == nullptr || ld_id(p.mask, (long)b * S + r_lo, p.mask_w) != 0)) ? 0.f : NEG_BIG;
+  const float kb_hi = (r_hi < S && (p.mask == nullptr || ld_id(p.mask, (long)b * S + r_hi, p.mask_w) != 0)) ? 0.f : NEG_BIG;
   float dk[8][4], dv[8][4];
 #pragma unroll
   for (int j = 0; j < 8; ++j)
@@ -370,9 +387,11 @@ attn_bwd_dkv_kernel(const AttnParams p) {
 constexpr int REF_CHUNK = 64;
 
 struct AttnRefParams {
-  const bf16* qkv; bf16* ctx; const bf16* dctx; bf16* dqkv; const int64_t* mask; float* lse2; float* delta;
+  const bf16* qkv; bf16* ctx; const bf16* dctx; bf16* dqkv; const void* mask; float* lse2; float* delta;
   long ps_qkv, ps_ctx;
   int B, S, H, heads;
+  int mask_w;
+  DropSpec drop;
 };
 
 // mode 0: forward; 1: dQ (+delta); 2: dK/dV
@@ -415,7 +434,7 @@ attn_ref_kernel(const AttnRefParams p) {
         x[d] = plane_load<3>(qkv + p.H + (long)r * ld + d, p.ps_qkv);      // k
         y[d] = plane_load<3>(qkv + 2 * p.H + (long)r * ld + d, p.ps_qkv);  // v
       }
-      kbias = (p.mask == nullptr || p.mask[(long)b * S + r] != 0) ? 0.f : NEG_BIG;
+      kbias = (p.mask == nullptr || ld_id(p.mask, (long)b * S + r, p.mask_w) != 0) ? 0.f : NEG_BIG;
     }
   }
   const float sl2 = 0.125f * LOG2E;
@@ -438,7 +457,7 @@ attn_ref_kernel(const AttnRefParams p) {
     }
     for (int c = threadIdx.x; c < REF_CHUNK; c += 128) {
       const int cc = c0 + c;
-      cbias[c] = (cc < S && (p.mask == nullptr || p.mask[(long)b * S + cc] != 0)) ? 0.f : NEG_BIG;
+      cbias[c] = (cc < S && (p.mask == nullptr || ld_id(p.mask, (long)b * S + cc, p.mask_w) != 0)) ? 0.f : NEG_BIG;
       if (MODE == 2) {
         clse[c] = cc < S ? p.lse2[lrow + cc] : 1.0e30f;
         cdelta[c] = cc < S ? p.delta[lrow + cc] : 0.f;
@@ -446,24 +465,39 @@ attn_ref_kernel(const AttnRefParams p) {
     }
     __syncthreads();
     if (!valid) continue;
+    const bool dropping = p.drop.thr_hi != 0u;
+    const uint32_t plane = b * p.heads + h;
+    uint4 rb = make_uint4(0u, 0u, 0u, 0u);
     for (int c = 0; c < REF_CHUNK; ++c) {
       float s = 0.f;
 #pragma unroll
       for (int d = 0; d < ATT_D; ++d) s += x[d] * cA[c][d];
+      // keep-multiplier of P[query, key]: MODE 0 / 1 walk the keys of one query row (one Philox block per 8 keys),
+      // MODE 2 walks the queries of one key (the block of (query cc, key group r >> 3), element r & 7)
+      float km = 1.f;
+      if (dropping) {
+        if (MODE == 2) {
+          km = drop_mult(drop_bits(p.drop, static_cast<uint32_t>(r) >> 3, c0 + c, plane), r & 7, p.drop.thr_hi, p.drop.scale);
+        } else {
+          if ((c & 7) == 0) rb = drop_bits(p.drop, static_cast<uint32_t>(c0 + c) >> 3, r, plane);
+          km = drop_mult(rb, c & 7, p.drop.thr_hi, p.drop.scale);
+        }
+      }
       if (MODE == 0) {
         s = s * sl2 + cbias[c];
         const float mn = fmaxf(m, s);
         const float corr = exp2f(m - mn), pe = exp2f(s - mn);
         m = mn;
         l = l * corr + pe;
+        const float pd = pe * km;
 #pragma unroll
-        for (int d = 0; d < ATT_D; ++d) acc0[d] = acc0[d] * corr + pe * cB[c][d];
+        for (int d = 0; d < ATT_D; ++d) acc0[d] = acc0[d] * corr + pd * cB[c][d];
       } else if (MODE == 1) {
         const float pe = exp2f(s * sl2 + cbias[c] - lse);
         float dp = 0.f;
 #pragma unroll
         for (int d = 0; d < ATT_D; ++d) dp += y[d] * cB[c][d];
-        const float ds = pe * (dp - delta);
+        const float ds = pe * (km * dp - delta);
 #pragma unroll
         for (int d = 0; d < ATT_D; ++d) acc0[d] += ds * cA[c][d];
       } else {
@@ -471,11 +505,12 @@ attn_ref_kernel(const AttnRefParams p) {
         float dp = 0.f;
 #pragma unroll
         for (int d = 0; d < ATT_D; ++d) dp += y[d] * cB[c][d];
-        const float ds = pe * (dp - cdelta[c]);
+        const float ds = pe * (km * dp - cdelta[c]);
+        const float pd = pe * km;
 #pragma unroll
         for (int d = 0; d < ATT_D; ++d) {
           acc0[d] += ds * cA[c][d];  // dK
-          acc1[d] += pe * cB[c][d];  // dV
+          acc1[d] += pd * cB[c][d];  // dV
         }
       }
     }
@@ -504,10 +539,11 @@ attn_ref_kernel(const AttnRefParams p) {
 // -------------------------------------------------------------------------------------------------
 // host wrappers
 // -------------------------------------------------------------------------------------------------
-int attention_tc_forward(const bf16* qkv, bf16* ctx, const int64_t* mask, float* lse2, int B, int S, int H, int heads,
-                         cudaStream_t st);
-int attention_tc_backward(const bf16* qkv, const bf16* ctx, const bf16* dctx, bf16* dqkv, const int64_t* mask,
-                          const float* lse2, int B, int S, int H, int heads, float* dbias, cudaStream_t st);
+int attention_tc_forward(const bf16* qkv, bf16* ctx, const void* mask, int mask_w, float* lse2, int B, int S, int H,
+                         int heads, const DropSpec& drop, cudaStream_t st);
+int attention_tc_backward(const bf16* qkv, const bf16* ctx, const bf16* dctx, bf16* dqkv, const void* mask, int mask_w,
+                          const float* lse2, int B, int S, int H, int heads, float* dbias, const DropSpec& drop,
+                          cudaStream_t st);
 int colsum(int np, const bf16* x, long rows, int N, long row_stride, long ps, float* out, cudaStream_t st);
 
 // single-tile sequences go to the tcgen05 kernels (attention_tc.cu); SIMX_ATTN_LEGACY=1 forces the mma.sync path
@@ -527,23 +563,23 @@ static int attn_check(int B, int S, int H, int heads) {
   return SIMX_OK;
 }
 
-int attention_forward(int np, const bf16* qkv, long ps_qkv, bf16* ctx, long ps_ctx, const int64_t* mask, float* lse2,
-                      int B, int S, int H, int heads, cudaStream_t st) {
+int attention_forward(int np, const bf16* qkv, long ps_qkv, bf16* ctx, long ps_ctx, const void* mask, int mask_w,
+                      float* lse2, int B, int S, int H, int heads, const DropSpec& drop, cudaStream_t st) {
   SIMX_TRY(attn_check(B, S, H, heads));
   ProfScope prof("attn_fwd", 4.0 * B * heads * (double)S * S * ATT_D, 2.0 * np * B * (double)S * 4 * H, st);
   // 128 < S <= 256: the two-key-tile tcgen05 kernel (2048 sequences x 12 heads: S = 160 0.97 vs 1.16 ms for the mma.sync
   // kernel, S = 256 1.31 vs 1.71 ms)
   if (use_tc_attention(np, S) || use_tc_attention(np, S - 128)) {
-    return attention_tc_forward(qkv, ctx, mask, lse2, B, S, H, heads, st);
+    return attention_tc_forward(qkv, ctx, mask, mask_w, lse2, B, S, H, heads, drop, st);
   }
   if (np == 3) {
-    AttnRefParams p{qkv, ctx, nullptr, nullptr, mask, lse2, nullptr, ps_qkv, ps_ctx, B, S, H, heads};
+    AttnRefParams p{qkv, ctx, nullptr, nullptr, mask, lse2, nullptr, ps_qkv, ps_ctx, B, S, H, heads, mask_w, drop};
     dim3 grid((S + 127) / 128, heads, B);
     attn_ref_kernel<0><<<grid, 128, 0, st>>>(p);
     SIMX_LAUNCH_CHECK();
     return SIMX_OK;
   }
-  AttnParams p{qkv, ctx, nullptr, nullptr, mask, lse2, nullptr, B, S, H, heads, (S + 63) / 64 * 64};
+  AttnParams p{qkv, ctx, nullptr, nullptr, mask, lse2, nullptr, B, S, H, heads, (S + 63) / 64 * 64, mask_w, drop};
   const size_t smem = ATT_ROWS * 128 + 2 * (size_t)p.s_pad * 128 + p.s_pad * sizeof(float);
   static bool attr = false;
   if (!attr) {
@@ -559,29 +595,30 @@ int attention_forward(int np, const bf16* qkv, long ps_qkv, bf16* ctx, long ps_c
 // dbias (optional): [3H] fp32, += column sums of dqkv — the fused q/k/v bias gradient.  The tcgen05 kernel reduces
 // its staged output tiles in shared memory; the other paths run the column-sum kernel over dqkv afterwards.
 static int attention_backward_core(int np, const bf16* qkv, long ps_qkv, const bf16* ctx, const bf16* dctx, long ps_ctx,
-                                   bf16* dqkv, const int64_t* mask, const float* lse2, float* delta, int B, int S, int H,
-                                   int heads, cudaStream_t st);
+                                   bf16* dqkv, const void* mask, int mask_w, const float* lse2, float* delta, int B, int S,
+                                   int H, int heads, const DropSpec& drop, cudaStream_t st);
 
 int attention_backward(int np, const bf16* qkv, long ps_qkv, const bf16* ctx, const bf16* dctx, long ps_ctx, bf16* dqkv,
-                       const int64_t* mask, const float* lse2, float* delta, int B, int S, int H, int heads,
-                       float* dbias, cudaStream_t st) {
+                       const void* mask, int mask_w, const float* lse2, float* delta, int B, int S, int H, int heads,
+                       float* dbias, const DropSpec& drop, cudaStream_t st) {
   SIMX_TRY(attn_check(B, S, H, heads));
   if (use_tc_attention(np, min(S, 128))) {  // bf16 mode, any S <= 512: ceil(S/128)^2 independent tcgen05 blocks
     ProfScope prof("attn_bwd", 10.0 * B * heads * (double)S * S * ATT_D, 2.0 * np * B * (double)S * 8 * H, st);
-    return attention_tc_backward(qkv, ctx, dctx, dqkv, mask, lse2, B, S, H, heads, dbias, st);
+    return attention_tc_backward(qkv, ctx, dctx, dqkv, mask, mask_w, lse2, B, S, H, heads, dbias, drop, st);
   }
-  SIMX_TRY(attention_backward_core(np, qkv, ps_qkv, ctx, dctx, ps_ctx, dqkv, mask, lse2, delta, B, S, H, heads, st));
+  SIMX_TRY(attention_backward_core(np, qkv, ps_qkv, ctx, dctx, ps_ctx, dqkv, mask, mask_w, lse2, delta, B, S, H, heads, drop,
+                                   st));
   if (dbias != nullptr) SIMX_TRY(colsum(np, dqkv, (long)B * S, 3 * H, 3L * H, ps_qkv, dbias, st));
   return SIMX_OK;
 }
 
 static int attention_backward_core(int np, const bf16* qkv, long ps_qkv, const bf16* ctx, const bf16* dctx, long ps_ctx,
-                                   bf16* dqkv, const int64_t* mask, const float* lse2, float* delta, int B, int S, int H,
-                                   int heads, cudaStream_t st) {
+                                   bf16* dqkv, const void* mask, int mask_w, const float* lse2, float* delta, int B, int S,
+                                   int H, int heads, const DropSpec& drop, cudaStream_t st) {
   ProfScope prof("attn_bwd", 10.0 * B * heads * (double)S * S * ATT_D, 2.0 * np * B * (double)S * 8 * H, st);
   if (np == 3) {
     AttnRefParams p{qkv, const_cast<bf16*>(ctx), dctx, dqkv, mask, const_cast<float*>(lse2), delta, ps_qkv, ps_ctx,
-                    B, S, H, heads};
+                    B, S, H, heads, mask_w, drop};
     dim3 grid((S + 127) / 128, heads, B);
     attn_ref_kernel<1><<<grid, 128, 0, st>>>(p);
     SIMX_LAUNCH_CHECK();
@@ -589,8 +626,10 @@ static int attention_backward_core(int np, const bf16* qkv, long ps_qkv, const b
     SIMX_LAUNCH_CHECK();
     return SIMX_OK;
   }
+  SIMX_CHECK(drop.thr_hi == 0u, SIMX_ERR_UNSUPPORTED,
+             "attention dropout is not implemented in the legacy mma.sync backward (unset SIMX_ATTN_LEGACY)");
   AttnParams p{qkv, const_cast<bf16*>(ctx), dctx, dqkv, mask, const_cast<float*>(lse2), delta, B, S, H, heads,
-               (S + 63) / 64 * 64};
+               (S + 63) / 64 * 64, mask_w, no_drop()};
   const size_t smem = 2 * ATT_ROWS * 128 + 2 * (size_t)p.s_pad * 128 + (2 * p.s_pad + ATT_ROWS) * sizeof(float);
   static bool attr = false;
   if (!attr) {
@@ -615,7 +654,7 @@ extern "C" int simx_attention_forward(const void* qkv, void* ctx, const int64_t*
   SIMX_CHECK(qkv && ctx && lse2, SIMX_ERR_INVALID, "attention_forward: null argument");
   SIMX_CHECK(planes == 1 || planes == 3, SIMX_ERR_INVALID, "attention_forward: planes must be 1 or 3");
   return attention_forward(planes, static_cast<const bf16*>(qkv), qkv_plane_stride, static_cast<bf16*>(ctx),
-                           ctx_plane_stride, mask, lse2, B, S, H, heads, static_cast<cudaStream_t>(stream));
+                           ctx_plane_stride, mask, 8, lse2, B, S, H, heads, no_drop(), static_cast<cudaStream_t>(stream));
 }
 
 extern "C" int simx_attention_backward(const void* qkv, const void* ctx, const void* dctx, void* dqkv,
@@ -626,7 +665,7 @@ extern "C" int simx_attention_backward(const void* qkv, const void* ctx, const v
   SIMX_CHECK(qkv && ctx && dctx && dqkv && lse2 && delta, SIMX_ERR_INVALID, "attention_backward: null argument");
   SIMX_CHECK(planes == 1 || planes == 3, SIMX_ERR_INVALID, "attention_backward: planes must be 1 or 3");
   return attention_backward(planes, static_cast<const bf16*>(qkv), qkv_plane_stride, static_cast<const bf16*>(ctx),
-                            static_cast<const bf16*>(dctx), ctx_plane_stride, static_cast<bf16*>(dqkv), mask, lse2, delta,
-                            B, S, H, heads, dbias_qkv, static_cast<cudaStream_t>(stream));
+                            static_cast<const bf16*>(dctx), ctx_plane_stride, static_cast<bf16*>(dqkv), mask, 8, lse2, delta,
+                            B, S, H, heads, dbias_qkv, no_drop(), static_cast<cudaStream_t>(stream));
 }
 

@@ -29,7 +29,7 @@ constexpr float TC_NEG = -1.0e30f;
 constexpr uint32_t TILE = 16384;  // [128 rows x 64 bf16] = 128 rows x 128 B
 
 struct AttnTcParams {
-  const int64_t* mask;  // [B,S] or NULL
+  const void* mask;     // [B,S] int64 / int32 (mask_w bytes per entry) or NULL
   float* lse2;          // [B, heads, S]
   const bf16* ctx;      // backward: O (for delta)
   const bf16* dctx;     // backward: dO
@@ -37,7 +37,16 @@ struct AttnTcParams {
   long long* timing;  // debug: 8 clock64 stamps of one CTA (simx_debug_attention_timing), else NULL
   float* dbias;       // backward: [3H] fp32 column sums of dqkv (the fused q/k/v bias gradient) accumulated with
                       // atomics, or NULL
+  int mask_w;         // 8 or 4
+  DropSpec drop;      // attention-probability dropout (LEAD/modeling_bert.py:358); thr_hi == 0: off
 };
+// keep / drop decision of the two probabilities packed in one bf16x2 word: elements 2i (low half of the Philox word) and
+// 2i+1 (high half) of an 8-key group
+__device__ __forceinline__ void drop_pair(float& p0, float& p1, uint32_t w, uint32_t thr_hi) {
+  if ((w << 16) < thr_hi) p0 = 0.f;
+  if (w < thr_hi) p1 = 0.f;
+}
+__device__ __forceinline__ uint32_t u4_word(const uint4& r, int i) { return i == 0 ? r.x : (i == 1 ? r.y : (i == 2 ? r.z : r.w)); }
 static long long* g_attn_timing = nullptr;
 #define SIMX_STAMP(i) do { if (p.timing != nullptr && tid == 0 && blockIdx.x == 3 && blockIdx.y == gridDim.y / 2) p.timing[i] = clock64(); } while (0)
 
@@ -59,6 +68,7 @@ __device__ __forceinline__ uint32_t p_off(int r, int j) {
 }
 
 // -------------------------------------------------------------------------------------------------
+template <bool DROP>
 __global__ void __launch_bounds__(128, 4)
 attn_fwd_tc_kernel(const AttnTcParams p, const __grid_constant__ CUtensorMap map_qkv,
                    const __grid_constant__ CUtensorMap map_ctx) {
@@ -80,7 +90,7 @@ attn_fwd_tc_kernel(const AttnTcParams p, const __grid_constant__ CUtensorMap map
     fence_mbar_init();
   }
   if (warp == 1) tmem_alloc<1>(tmem_slot, 128);
-  bias[tid] = (tid < S && (p.mask == nullptr || p.mask[(long)b * S + tid] != 0)) ? 0.f : TC_NEG;
+  bias[tid] = (tid < S && (p.mask == nullptr || ld_id(p.mask, (long)b * S + tid, p.mask_w) != 0)) ? 0.f : TC_NEG;
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -121,11 +131,18 @@ attn_fwd_tc_kernel(const AttnTcParams p, const __grid_constant__ CUtensorMap map
     tmem_ld_wait();
     uint32_t pk[16];
 #pragma unroll
-    for (int i = 0; i < 16; ++i) {
-      const float p0 = ex2(fmaf(__uint_as_float(v[2 * i]), sl2, bias[c * 32 + 2 * i]) - m);
-      const float p1 = ex2(fmaf(__uint_as_float(v[2 * i + 1]), sl2, bias[c * 32 + 2 * i + 1]) - m);
-      l += p0 + p1;
-      pk[i] = pack_bf16x2(p0, p1);
+    for (int g8 = 0; g8 < 4; ++g8) {
+      uint4 rb = make_uint4(0u, 0u, 0u, 0u);
+      if constexpr (DROP) rb = drop_bits(p.drop, c * 4 + g8, row, b * p.heads + h);
+#pragma unroll
+      for (int ii = 0; ii < 4; ++ii) {
+        const int i = g8 * 4 + ii;
+        float p0 = ex2(fmaf(__uint_as_float(v[2 * i]), sl2, bias[c * 32 + 2 * i]) - m);
+        float p1 = ex2(fmaf(__uint_as_float(v[2 * i + 1]), sl2, bias[c * 32 + 2 * i + 1]) - m);
+        l += p0 + p1;  // the softmax normaliser is that of the un-dropped probabilities
+        if constexpr (DROP) drop_pair(p0, p1, u4_word(rb, ii), p.drop.thr_hi);
+        pk[i] = pack_bf16x2(p0, p1);
+      }
     }
     // P overwrites the Q and K tiles (both dead once S is complete)
 #pragma unroll
@@ -146,7 +163,7 @@ attn_fwd_tc_kernel(const AttnTcParams p, const __grid_constant__ CUtensorMap map
   }
   mbar_wait(&bars[2], 0);
   tc_fence_after();
-  const float inv = 1.f / l;
+  const float inv = (DROP ? p.drop.scale : 1.f) / l;
 #pragma unroll
   for (int c = 0; c < 2; ++c) {
     uint32_t v[32];
@@ -181,6 +198,7 @@ attn_fwd_tc_kernel(const AttnTcParams p, const __grid_constant__ CUtensorMap map
 // (head, sequence, 128-query tile); both 128-key tiles of K and V are resident, S[128, 256] lives in 256 TMEM columns and
 // O re-uses the first 64 of them once P has been staged.  smem: [Q][K0][K1][pad][V0][V1] = 96 KB, P (128 x 256 bf16)
 // overwrites the first four tiles -> two CTAs per SM.
+template <bool DROP>
 __global__ void __launch_bounds__(128, 2)
 attn_fwd_tc2_kernel(const AttnTcParams p, const __grid_constant__ CUtensorMap map_qkv,
                     const __grid_constant__ CUtensorMap map_ctx) {
@@ -203,7 +221,7 @@ attn_fwd_tc2_kernel(const AttnTcParams p, const __grid_constant__ CUtensorMap ma
   }
   if (warp == 1) tmem_alloc<1>(tmem_slot, 256);
   for (int k = tid; k < 256; k += 128)
-    bias[k] = (k < S && (p.mask == nullptr || p.mask[(long)b * S + k] != 0)) ? 0.f : TC_NEG;
+    bias[k] = (k < S && (p.mask == nullptr || ld_id(p.mask, (long)b * S + k, p.mask_w) != 0)) ? 0.f : TC_NEG;
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -255,11 +273,18 @@ attn_fwd_tc2_kernel(const AttnTcParams p, const __grid_constant__ CUtensorMap ma
     tmem_ld_wait();
     uint32_t pk[16];
 #pragma unroll
-    for (int i = 0; i < 16; ++i) {
-      const float p0 = ex2(fmaf(__uint_as_float(v[2 * i]), sl2, bias[c * 32 + 2 * i]) - m);
-      const float p1 = ex2(fmaf(__uint_as_float(v[2 * i + 1]), sl2, bias[c * 32 + 2 * i + 1]) - m);
-      l += p0 + p1;
-      pk[i] = pack_bf16x2(p0, p1);
+    for (int g8 = 0; g8 < 4; ++g8) {
+      uint4 rb = make_uint4(0u, 0u, 0u, 0u);
+      if constexpr (DROP) rb = drop_bits(p.drop, c * 4 + g8, q0 + row, b * p.heads + h);
+#pragma unroll
+      for (int ii = 0; ii < 4; ++ii) {
+        const int i = g8 * 4 + ii;
+        float p0 = ex2(fmaf(__uint_as_float(v[2 * i]), sl2, bias[c * 32 + 2 * i]) - m);
+        float p1 = ex2(fmaf(__uint_as_float(v[2 * i + 1]), sl2, bias[c * 32 + 2 * i + 1]) - m);
+        l += p0 + p1;
+        if constexpr (DROP) drop_pair(p0, p1, u4_word(rb, ii), p.drop.thr_hi);
+        pk[i] = pack_bf16x2(p0, p1);
+      }
     }
 #pragma unroll
     for (int g = 0; g < 4; ++g)
@@ -280,7 +305,7 @@ attn_fwd_tc2_kernel(const AttnTcParams p, const __grid_constant__ CUtensorMap ma
   }
   mbar_wait(&bars[2], 0);
   tc_fence_after();
-  const float inv = 1.f / l;
+  const float inv = (DROP ? p.drop.scale : 1.f) / l;
 #pragma unroll
   for (int c = 0; c < 2; ++c) {
     uint32_t v[32];
@@ -313,6 +338,7 @@ attn_fwd_tc2_kernel(const AttnTcParams p, const __grid_constant__ CUtensorMap ma
 // -------------------------------------------------------------------------------------------------
 // 256 threads: warps w and w+4 share TMEM lane quarter w and split the key columns, so the latency-bound
 // softmax-backward and epilogue phases have twice the warps to overlap
+template <bool DROP>
 __global__ void __launch_bounds__(256, 2)
 attn_bwd_tc_kernel(const AttnTcParams p, const __grid_constant__ CUtensorMap map_qkv,
                    const __grid_constant__ CUtensorMap map_dctx, const __grid_constant__ CUtensorMap map_ctx,
@@ -352,7 +378,8 @@ attn_bwd_tc_kernel(const AttnTcParams p, const __grid_constant__ CUtensorMap map
     fence_mbar_init();
   }
   if (warp == 1) tmem_alloc<1>(tmem_slot, 256);
-  if (tid < 128) bias[tid] = (k0 + tid < S && (p.mask == nullptr || p.mask[(long)b * S + k0 + tid] != 0)) ? 0.f : TC_NEG;
+  if (tid < 128)
+    bias[tid] = (k0 + tid < S && (p.mask == nullptr || ld_id(p.mask, (long)b * S + k0 + tid, p.mask_w) != 0)) ? 0.f : TC_NEG;
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -409,12 +436,26 @@ attn_bwd_tc_kernel(const AttnTcParams p, const __grid_constant__ CUtensorMap map
     tmem_ld_wait();
     uint32_t pk[16], dk[16];
 #pragma unroll
-    for (int i = 0; i < 16; ++i) {
-      float p0 = ex2(fmaf(__uint_as_float(s[2 * i]), sl2, bias[c * 32 + 2 * i]) - lse);
-      float p1 = ex2(fmaf(__uint_as_float(s[2 * i + 1]), sl2, bias[c * 32 + 2 * i + 1]) - lse);
-      if (!rv) { p0 = 0.f; p1 = 0.f; }
-      pk[i] = pack_bf16x2(p0, p1);
-      dk[i] = pack_bf16x2(p0 * (__uint_as_float(d[2 * i]) - delta), p1 * (__uint_as_float(d[2 * i + 1]) - delta));
+    for (int g8 = 0; g8 < 4; ++g8) {
+      uint4 rb = make_uint4(0u, 0u, 0u, 0u);
+      if constexpr (DROP) rb = drop_bits(p.drop, (k0 >> 3) + c * 4 + g8, q0 + row, b * p.heads + h);
+#pragma unroll
+      for (int ii = 0; ii < 4; ++ii) {
+        const int i = g8 * 4 + ii;
+        float p0 = ex2(fmaf(__uint_as_float(s[2 * i]), sl2, bias[c * 32 + 2 * i]) - lse);
+        float p1 = ex2(fmaf(__uint_as_float(s[2 * i + 1]), sl2, bias[c * 32 + 2 * i + 1]) - lse);
+        if (!rv) { p0 = 0.f; p1 = 0.f; }
+        if constexpr (DROP) {
+          // forward used P~ = P o mask * scale: dV = P~^T dO, dS = P o (mask * scale * dP - delta), delta = rowsum(dO o O)
+          float m0 = p.drop.scale, m1 = p.drop.scale;
+          drop_pair(m0, m1, u4_word(rb, ii), p.drop.thr_hi);
+          pk[i] = pack_bf16x2(p0 * m0, p1 * m1);
+          dk[i] = pack_bf16x2(p0 * (m0 * __uint_as_float(d[2 * i]) - delta), p1 * (m1 * __uint_as_float(d[2 * i + 1]) - delta));
+        } else {
+          pk[i] = pack_bf16x2(p0, p1);
+          dk[i] = pack_bf16x2(p0 * (__uint_as_float(d[2 * i]) - delta), p1 * (__uint_as_float(d[2 * i + 1]) - delta));
+        }
+      }
     }
     // P overwrites V (dead once dP is complete) and the tile after it; dS has its own two tiles
 #pragma unroll
@@ -515,36 +556,42 @@ attn_bwd_tc_kernel(const AttnTcParams p, const __grid_constant__ CUtensorMap map
 }
 
 // -------------------------------------------------------------------------------------------------
-int attention_tc_forward(const bf16* qkv, bf16* ctx, const int64_t* mask, float* lse2, int B, int S, int H, int heads,
-                         cudaStream_t st) {
+int attention_tc_forward(const bf16* qkv, bf16* ctx, const void* mask, int mask_w, float* lse2, int B, int S, int H,
+                         int heads, const DropSpec& drop, cudaStream_t st) {
   CUtensorMap mq, mc;
   SIMX_TRY(make_tmap_bf16(&mq, qkv, 3 * (uint64_t)H, S, B, 3 * (uint64_t)H, (uint64_t)S * 3 * H, 128));
   SIMX_TRY(make_tmap_bf16(&mc, ctx, H, S, B, H, (uint64_t)S * H, 128));
   constexpr int smem = 3 * TILE + 64 + 512 + 1024;
   static bool attr = false;
   if (!attr) {
-    SIMX_CUDA(cudaFuncSetAttribute(attn_fwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    SIMX_CUDA(cudaFuncSetAttribute(attn_fwd_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    SIMX_CUDA(cudaFuncSetAttribute(attn_fwd_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     attr = true;
   }
-  AttnTcParams p{mask, lse2, nullptr, nullptr, B, S, H, heads, nullptr, nullptr};
+  AttnTcParams p{mask, lse2, nullptr, nullptr, B, S, H, heads, nullptr, nullptr, mask_w, drop};
+  const bool dr = drop.thr_hi != 0u;
   if (S > 128) {
     constexpr int smem2 = 6 * TILE + 64 + 1024 + 1024;
     static bool attr2 = false;
     if (!attr2) {
-      SIMX_CUDA(cudaFuncSetAttribute(attn_fwd_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem2));
+      SIMX_CUDA(cudaFuncSetAttribute(attn_fwd_tc2_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem2));
+      SIMX_CUDA(cudaFuncSetAttribute(attn_fwd_tc2_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem2));
       attr2 = true;
     }
-    attn_fwd_tc2_kernel<<<dim3(heads, B, (S + 127) / 128), 128, smem2, st>>>(p, mq, mc);
+    if (dr) attn_fwd_tc2_kernel<true><<<dim3(heads, B, (S + 127) / 128), 128, smem2, st>>>(p, mq, mc);
+    else attn_fwd_tc2_kernel<false><<<dim3(heads, B, (S + 127) / 128), 128, smem2, st>>>(p, mq, mc);
     SIMX_LAUNCH_CHECK();
     return SIMX_OK;
   }
-  attn_fwd_tc_kernel<<<dim3(heads, B), 128, smem, st>>>(p, mq, mc);
+  if (dr) attn_fwd_tc_kernel<true><<<dim3(heads, B), 128, smem, st>>>(p, mq, mc);
+  else attn_fwd_tc_kernel<false><<<dim3(heads, B), 128, smem, st>>>(p, mq, mc);
   SIMX_LAUNCH_CHECK();
   return SIMX_OK;
 }
 
-int attention_tc_backward(const bf16* qkv, const bf16* ctx, const bf16* dctx, bf16* dqkv, const int64_t* mask,
-                          const float* lse2, int B, int S, int H, int heads, float* dbias, cudaStream_t st) {
+int attention_tc_backward(const bf16* qkv, const bf16* ctx, const bf16* dctx, bf16* dqkv, const void* mask, int mask_w,
+                          const float* lse2, int B, int S, int H, int heads, float* dbias, const DropSpec& drop,
+                          cudaStream_t st) {
   CUtensorMap mq, md, mo, mg;
   SIMX_TRY(make_tmap_bf16(&mq, qkv, 3 * (uint64_t)H, S, B, 3 * (uint64_t)H, (uint64_t)S * 3 * H, 128));
   SIMX_TRY(make_tmap_bf16(&md, dctx, H, S, B, H, (uint64_t)S * H, 128));
@@ -553,13 +600,15 @@ int attention_tc_backward(const bf16* qkv, const bf16* ctx, const bf16* dctx, bf
   constexpr int smem = 7 * TILE + 1024;
   static bool attr = false;
   if (!attr) {
-    SIMX_CUDA(cudaFuncSetAttribute(attn_bwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    SIMX_CUDA(cudaFuncSetAttribute(attn_bwd_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    SIMX_CUDA(cudaFuncSetAttribute(attn_bwd_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     attr = true;
   }
-  AttnTcParams p{mask, const_cast<float*>(lse2), ctx, dctx, B, S, H, heads, g_attn_timing, dbias};
+  AttnTcParams p{mask, const_cast<float*>(lse2), ctx, dctx, B, S, H, heads, g_attn_timing, dbias, mask_w, drop};
   const int kt = (S + 127) / 128;
   if (kt > 1) SIMX_CUDA(cudaMemsetAsync(dqkv, 0, (size_t)B * S * 3 * H * sizeof(bf16), st));  // blocks reduce-add into it
-  attn_bwd_tc_kernel<<<dim3(heads, B, kt * kt), 256, smem, st>>>(p, mq, md, mo, mg);
+  if (drop.thr_hi != 0u) attn_bwd_tc_kernel<true><<<dim3(heads, B, kt * kt), 256, smem, st>>>(p, mq, md, mo, mg);
+  else attn_bwd_tc_kernel<false><<<dim3(heads, B, kt * kt), 256, smem, st>>>(p, mq, md, mo, mg);
   SIMX_LAUNCH_CHECK();
   return SIMX_OK;
 }

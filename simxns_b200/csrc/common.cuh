@@ -8,10 +8,15 @@
 #include <stdio.h>
 
 #include "../../include/simx_b200.h"
+#include "dropout.cuh"
 
 namespace simx {
 
 typedef __nv_bfloat16 bf16;
+
+// internal GEMM epilogue (not reachable through simx_gemm: it needs a DropSpec):
+//   out = dropout(acc + bias[n]) + aux[m,n]   (BertSelfOutput / BertOutput in training: LEAD/modeling_bert.py:384-388, 462-466)
+constexpr int EPI_BIAS_DROP_ADD = 8;
 
 // ---------------------------------------------------------------------------------------------
 // error plumbing (no C++ exceptions cross the ABI; see include/simx_b200.h)
@@ -45,6 +50,12 @@ void set_error(const char* fmt, ...);
   } while (0)
 
 int num_sms();  // cached cudaDevAttrMultiProcessorCount of the current device
+
+// the tcgen05 GEMM (gemm_sm100.cu); `drop` turns SIMX_EPI_BIAS_ADD into out = dropout(acc + bias) + aux
+int gemm(int M, int N, int K, const __nv_bfloat16* A, long lda, long a_ps, bool a_mn, const __nv_bfloat16* B, long ldb,
+         long b_ps, bool b_mn, int planes, int epi, const float* bias, const __nv_bfloat16* aux, long ldaux, long aux_ps,
+         __nv_bfloat16* out, __nv_bfloat16* out2, long ldo, long out_ps, float* outf, long ldof, int ksplit,
+         cudaStream_t stream, const DropSpec* drop = nullptr);
 
 // ---------------------------------------------------------------------------------------------
 // optional per-launch timing (simx_profile_begin / simx_profile_end): CUDA events recorded on the launching stream
@@ -139,6 +150,12 @@ __device__ __forceinline__ void split_store8(bf16* p, long ps, const float (&v)[
     for (int i = 0; i < 4; ++i) h[i] = __floats2bfloat162_rn(r[2 * i], r[2 * i + 1]);
     *reinterpret_cast<uint4*>(p + 2 * ps) = u;
   }
+}
+
+// token ids / attention masks / position ids arrive as int64 (the reference's collate, MARCO_until_new.py:240-260) or
+// int32 (simx_encoder_cfg.id_bytes = 4: half the host->device bytes)
+__device__ __forceinline__ long ld_id(const void* p, long i, int id_bytes) {
+  return id_bytes == 4 ? (long)static_cast<const int32_t*>(p)[i] : (long)static_cast<const int64_t*>(p)[i];
 }
 
 __device__ __forceinline__ float warp_sum(float v) {

@@ -19,23 +19,20 @@
 namespace simx {
 
 // kernels from the other translation units
-int gemm(int M, int N, int K, const bf16* A, long lda, long a_ps, bool a_mn, const bf16* B, long ldb, long b_ps,
-         bool b_mn, int planes, int epi, const float* bias, const bf16* aux, long ldaux, long aux_ps, bf16* out,
-         bf16* out2, long ldo, long out_ps, float* outf, long ldof, int ksplit, cudaStream_t stream);
-int embed_ln(int np, const int64_t* ids, const int64_t* pos_ids, int max_pos, int T, int S, int H, int vocab,
+int embed_ln(int np, const void* ids, const void* pos_ids, int id_bytes, int max_pos, int T, int S, int H, int vocab,
              const float* word, const float* pos, const float* type0, const float* gamma, const float* beta, float eps,
-             bf16* z0, bf16* x, long ps, cudaStream_t st);
+             bf16* z0, bf16* x, long ps, const DropSpec& drop, cudaStream_t st);
 int ln_fwd(int np, const bf16* z, int T, int H, const float* gamma, const float* beta, float eps, bf16* x, long ps,
            cudaStream_t st);
 int ln_bwd(int np, const bf16* dy, const bf16* z, int T, int H, const float* gamma, float eps, bf16* dz, long ps,
-           float* dgamma, float* dbeta, float* dbias, cudaStream_t st);
+           float* dgamma, float* dbeta, float* dbias, bf16* dzm, int drop_mode, const DropSpec& drop, cudaStream_t st);
 int colsum(int np, const bf16* x, long rows, int N, long row_stride, long ps, float* out, cudaStream_t st);
 int cls_gather(int np, const bf16* x, int B, int S, int H, long ps, float* out, long out_stride_b, cudaStream_t st);
 int cls_scatter_add(int np, bf16* dx, int B, int S, int H, long ps, const float* d, long d_stride_b, cudaStream_t st);
 int f32_to_planes(int np, const float* src, long n, bf16* dst, long ps, cudaStream_t st);
 int planes_to_f32(int np, const bf16* src, long n, long ps, float* dst, cudaStream_t st);
-int embed_scatter(int np, const int64_t* ids, const bf16* dz0, int T, int H, int vocab, int pad_id, long ps, float* dword,
-                  cudaStream_t st);
+int embed_scatter(int np, const void* ids, int id_bytes, const bf16* dz0, int T, int H, int vocab, int pad_id, long ps,
+                  float* dword, cudaStream_t st);
 int convert_weight(int np, const float* w, int R, int C, bf16* dst, long ld_dst, long ps_dst, bf16* dst_t, long ld_t,
                    long ps_t, cudaStream_t st);
 // batched form: every job queued between begin and end goes out in one launch per 56 jobs (C == 0: fp32 copy of R values)
@@ -43,11 +40,11 @@ int conv_begin(void** handle);
 int conv_add(void* handle, int np, const float* w, int R, int C, bf16* dst, long ld_dst, long ps_dst, bf16* dst_t, long ld_t,
              long ps_t, cudaStream_t st);
 int conv_end(void* handle, int np, cudaStream_t st);
-int attention_forward(int np, const bf16* qkv, long ps_qkv, bf16* ctx, long ps_ctx, const int64_t* mask, float* lse2,
-                      int B, int S, int H, int heads, cudaStream_t st);
+int attention_forward(int np, const bf16* qkv, long ps_qkv, bf16* ctx, long ps_ctx, const void* mask, int mask_w,
+                      float* lse2, int B, int S, int H, int heads, const DropSpec& drop, cudaStream_t st);
 int attention_backward(int np, const bf16* qkv, long ps_qkv, const bf16* ctx, const bf16* dctx, long ps_ctx, bf16* dqkv,
-                       const int64_t* mask, const float* lse2, float* delta, int B, int S, int H, int heads,
-                       float* dbias, cudaStream_t st);
+                       const void* mask, int mask_w, const float* lse2, float* delta, int B, int S, int H, int heads,
+                       float* dbias, const DropSpec& drop, cudaStream_t st);
 
 static inline size_t al(size_t x) { return (x + 255) & ~size_t(255); }
 
@@ -64,7 +61,23 @@ static int check_cfg(const simx_encoder_cfg* c) {
   SIMX_CHECK(c->arch != SIMX_ARCH_BERT || c->type_vocab >= 1, SIMX_ERR_INVALID, "BERT needs type_vocab >= 1");
   SIMX_CHECK(c->precision == SIMX_PREC_BF16 || c->precision == SIMX_PREC_BF16X3, SIMX_ERR_INVALID, "unknown precision %d",
              c->precision);
+  SIMX_CHECK(c->hidden_dropout >= 0.f && c->hidden_dropout < 1.f && c->attn_dropout >= 0.f && c->attn_dropout < 1.f,
+             SIMX_ERR_INVALID, "dropout probabilities must lie in [0, 1): hidden %g, attention %g", c->hidden_dropout,
+             c->attn_dropout);
+  SIMX_CHECK(c->save_policy == SIMX_SAVE_ALL || c->save_policy == SIMX_SAVE_LAYER_INPUTS, SIMX_ERR_INVALID,
+             "unknown save_policy %d", c->save_policy);
+  SIMX_CHECK(c->id_bytes == 0 || c->id_bytes == 4 || c->id_bytes == 8, SIMX_ERR_INVALID, "id_bytes must be 4 or 8 (0 = 8), got %d",
+             c->id_bytes);
   return SIMX_OK;
+}
+static inline int id_bytes(const simx_encoder_cfg* c) { return c->id_bytes == 4 ? 4 : 8; }
+static inline bool ckpt(const simx_encoder_cfg* c) { return c->save_policy == SIMX_SAVE_LAYER_INPUTS; }
+// dropout masks of this call: sites as in LEAD/modeling_bert.py (:239, :358, :386, :464); DistilBERT has no dropout after
+// the attention output projection (LEAD/modeling_distilbert.py:260-319)
+static inline DropSpec drop_at(const simx_encoder_cfg* c, uint32_t site, int layer) {
+  float p = site == DROP_SITE_ATTN ? c->attn_dropout : c->hidden_dropout;
+  if (site == DROP_SITE_ATTN_OUT && c->arch == SIMX_ARCH_DISTILBERT) p = 0.f;
+  return p > 0.f ? make_drop(p, c->dropout_seed, site, layer) : no_drop();
 }
 
 struct ParamTable {
@@ -186,14 +199,16 @@ static SavedL saved_layout(const simx_encoder_cfg* c, int B, int S) {
   s.l_lse = lo; lo += al((size_t)B * c->heads * S * 4);
   s.l_total = lo;
   s.layer0 = off;
-  off += lo * L;
+  // SIMX_SAVE_LAYER_INPUTS (the reference's --gradient_checkpointing): only z0 and the layer inputs x[0..L] are kept;
+  // backward recomputes one layer at a time into the workspace
+  if (!ckpt(c)) off += lo * L;
   s.total = off + 256;
   return s;
 }
 
 // ---- workspace: backward temporaries, and one layer of activations for saved == NULL (inference) ----
 struct WsL {
-  size_t dx, dza, dxb, dh, dqkv, delta, infer, total;
+  size_t dx, dza, dxb, dzm, dh, dqkv, delta, scratch, infer, total;
 };
 static WsL ws_layout(const simx_encoder_cfg* c, int B, int S) {
   const size_t T = (size_t)B * S, H = c->hidden, I = c->intermediate, np = c->precision;
@@ -202,11 +217,15 @@ static WsL ws_layout(const simx_encoder_cfg* c, int B, int S) {
   w.dx = off;    off += al(np * T * H * 2);
   w.dza = off;   off += al(np * T * H * 2);
   w.dxb = off;   off += al(np * T * H * 2);
+  w.dzm = off;   off += c->hidden_dropout > 0.f ? al(np * T * H * 2) : 0;  // dropout-masked copy of the LayerNorm-backward output
   w.dh = off;    off += al(np * T * I * 2);
   w.dqkv = off;  off += al(np * T * 3 * H * 2);
   w.delta = off; off += al((size_t)B * c->heads * S * 4);
-  // inference scratch aliases the backward temporaries (never live together): z0 + 2 x + one layer
   const SavedL s = saved_layout(c, B, S);
+  // layer-input checkpointing: one layer of activations, written by the training forward and re-written by backward
+  w.scratch = off;
+  if (ckpt(c)) off += s.l_total;
+  // inference scratch aliases the backward temporaries (never live together): z0 + 2 x + one layer
   w.infer = 0;
   const size_t infer_bytes = al(np * T * H * 2) * 3 + s.l_total;
   w.total = (off > infer_bytes ? off : infer_bytes) + 256;
@@ -292,8 +311,70 @@ extern "C" int simx_encoder_prepare_weights(const simx_encoder_cfg* cfg, const f
   return SIMX_OK;
 }
 
+// one layer's activation buffers (in `saved`, or in the workspace scratch when they are recomputed / not kept)
+struct LayerBufs {
+  bf16 *qkv, *ctx, *z1, *x1, *h, *a, *z2;
+  float* lse;
+};
+static LayerBufs layer_bufs(uint8_t* base, const SavedL& sl) {
+  LayerBufs b;
+  b.qkv = reinterpret_cast<bf16*>(base + sl.l_qkv);
+  b.ctx = reinterpret_cast<bf16*>(base + sl.l_ctx);
+  b.z1 = reinterpret_cast<bf16*>(base + sl.l_z1);
+  b.x1 = reinterpret_cast<bf16*>(base + sl.l_x1);
+  b.h = reinterpret_cast<bf16*>(base + sl.l_h);
+  b.a = reinterpret_cast<bf16*>(base + sl.l_a);
+  b.z2 = reinterpret_cast<bf16*>(base + sl.l_z2);
+  b.lse = reinterpret_cast<float*>(base + sl.l_lse);
+  return b;
+}
+
+// forward of layer l: x -> (lb.*) -> xo = LN(z2) (xo == NULL: stop at z2 — the recomputation inside backward).
+// train: the FFN-up epilogue also stores gelu' for backward.
+static int layer_forward(const simx_encoder_cfg* cfg, const float* const* P, const uint8_t* w, const LayerW& lw, int l,
+                         const bf16* x, bf16* xo, const LayerBufs& lb, const void* mask, int B, int S, bool train,
+                         cudaStream_t st) {
+  const int np = cfg->precision, H = cfg->hidden, I = cfg->intermediate;
+  const int T = B * S;
+  const long psH = (long)T * H, ps3H = (long)T * 3 * H, psI = (long)T * I;
+  const bf16* wqkv = reinterpret_cast<const bf16*>(w + lw.wqkv);
+  const bf16* wo = reinterpret_cast<const bf16*>(w + lw.wo);
+  const bf16* w1 = reinterpret_cast<const bf16*>(w + lw.w1);
+  const bf16* w2 = reinterpret_cast<const bf16*>(w + lw.w2);
+  const float* bqkv = reinterpret_cast<const float*>(w + lw.bqkv);
+  // dropout follows the cfg probabilities (the caller zeroes them in eval mode), whether or not activations are kept:
+  // the reference's model.train() + torch.no_grad() still drops
+  const DropSpec d_attn = drop_at(cfg, DROP_SITE_ATTN, l);
+  const DropSpec d_ao = drop_at(cfg, DROP_SITE_ATTN_OUT, l);
+  const DropSpec d_fo = drop_at(cfg, DROP_SITE_FFN_OUT, l);
+
+  prof_label("qkv_fwd");
+  SIMX_TRY(gemm(T, 3 * H, H, x, H, psH, false, wqkv, H, 3L * H * H, false, np, SIMX_EPI_BIAS, bqkv, nullptr, 0, 0, lb.qkv,
+                nullptr, 3 * H, ps3H, nullptr, 0, 1, st));
+  prof_label(nullptr);
+  SIMX_TRY(attention_forward(np, lb.qkv, ps3H, lb.ctx, psH, mask, id_bytes(cfg), lb.lse, B, S, H, cfg->heads, d_attn, st));
+  prof_label("attnout_fwd");
+  SIMX_TRY(gemm(T, H, H, lb.ctx, H, psH, false, wo, H, (long)H * H, false, np, SIMX_EPI_BIAS_ADD, P[7], x, H, psH, lb.z1,
+                nullptr, H, psH, nullptr, 0, 1, st, &d_ao));
+  prof_label(nullptr);
+  SIMX_TRY(ln_fwd(np, lb.z1, T, H, P[8], P[9], cfg->ln_eps, lb.x1, psH, st));
+  prof_label("ffn1_fwd");
+  if (train)
+    SIMX_TRY(gemm(T, I, H, lb.x1, H, psH, false, w1, H, (long)I * H, false, np, SIMX_EPI_BIAS_GELU, P[11], nullptr, 0, 0, lb.h,
+                  lb.a, I, psI, nullptr, 0, 1, st));
+  else  // inference: gelu only, one [T, I] output instead of two
+    SIMX_TRY(gemm(T, I, H, lb.x1, H, psH, false, w1, H, (long)I * H, false, np, SIMX_EPI_BIAS_GELU_FWD, P[11], nullptr, 0, 0,
+                  lb.a, nullptr, I, psI, nullptr, 0, 1, st));
+  prof_label("ffn2_fwd");
+  SIMX_TRY(gemm(T, H, I, lb.a, I, psI, false, w2, I, (long)I * H, false, np, SIMX_EPI_BIAS_ADD, P[13], lb.x1, H, psH, lb.z2,
+                nullptr, H, psH, nullptr, 0, 1, st, &d_fo));
+  prof_label(nullptr);
+  if (xo != nullptr) SIMX_TRY(ln_fwd(np, lb.z2, T, H, P[14], P[15], cfg->ln_eps, xo, psH, st));
+  return SIMX_OK;
+}
+
 static int encoder_forward_impl(const simx_encoder_cfg* cfg, const float* const* params, const void* wbuf,
-                                const int64_t* ids, const int64_t* mask, const int64_t* pos_ids, int B, int S, void* saved,
+                                const void* ids, const void* mask, const void* pos_ids, int B, int S, void* saved,
                                 void* workspace, float* cls_out, float* seq_out, void* stream) {
   SIMX_TRY(check_cfg(cfg));
   SIMX_CHECK(params && wbuf && ids, SIMX_ERR_INVALID, "encoder_forward: null argument");
@@ -301,103 +382,76 @@ static int encoder_forward_impl(const simx_encoder_cfg* cfg, const float* const*
              "encoder_forward: need 0 < S <= min(max_pos=%d, 512), got B=%d S=%d", cfg->max_pos, B, S);
   SIMX_CHECK(saved != nullptr || workspace != nullptr, SIMX_ERR_INVALID, "encoder_forward: need saved or workspace");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  const int np = cfg->precision, H = cfg->hidden, I = cfg->intermediate, L = cfg->num_layers;
+  const int np = cfg->precision, H = cfg->hidden, L = cfg->num_layers;
   const int T = B * S;
-  const long psH = (long)T * H, ps3H = (long)T * 3 * H, psI = (long)T * I;
+  const long psH = (long)T * H;
   const ParamTable t = ptable(cfg);
   const LayerW lw = layer_w(cfg);
   const SavedL sl = saved_layout(cfg, B, S);
+  const WsL wl = ws_layout(cfg, B, S);
   const uint8_t* wb = align_ptr(wbuf);
-  const bool keep = saved != nullptr;
+  const bool keep = saved != nullptr;   // a backward pass will follow: activations (or layer inputs) are kept
+  SIMX_CHECK(!(keep && ckpt(cfg)) || workspace != nullptr, SIMX_ERR_INVALID,
+             "encoder_forward: SIMX_SAVE_LAYER_INPUTS needs the workspace for the layer scratch");
   uint8_t* sb = keep ? align_ptr(saved) : align_ptr(workspace);
-  // inference: [z0][xa][xb][one layer]
+  // inference: [z0][xa][xb][one layer] inside the workspace
   auto xbuf = [&](int l) -> bf16* {
     if (keep) return reinterpret_cast<bf16*>(sb + sl.x + sl.x_stride * l);
     return reinterpret_cast<bf16*>(sb + sl.x_stride * (1 + (l & 1)));
   };
-  auto lbuf = [&](int l, size_t off) -> uint8_t* {
-    if (keep) return sb + sl.layer0 + sl.l_total * l + off;
-    return sb + sl.x_stride * 3 + off;
+  auto lbase = [&](int l) -> uint8_t* {
+    if (keep && ckpt(cfg)) return align_ptr(workspace) + wl.scratch;
+    if (keep) return sb + sl.layer0 + sl.l_total * l;
+    return sb + sl.x_stride * 3;
   };
   bf16* z0 = keep ? reinterpret_cast<bf16*>(sb + sl.z0) : nullptr;
   const float* type0 = t.bert ? params[2] : nullptr;
   const float* eg = params[t.bert ? 3 : 2];
   const float* eb = params[t.bert ? 4 : 3];
-  SIMX_TRY(embed_ln(np, ids, pos_ids, cfg->max_pos, T, S, H, cfg->vocab, params[0], params[1], type0, eg, eb, cfg->ln_eps, z0,
-                    xbuf(0), psH, st));
+  SIMX_TRY(embed_ln(np, ids, pos_ids, id_bytes(cfg), cfg->max_pos, T, S, H, cfg->vocab, params[0], params[1], type0, eg, eb,
+                    cfg->ln_eps, z0, xbuf(0), psH, drop_at(cfg, DROP_SITE_EMBED, 0), st));
   const long cls_stride_b = (long)(L + 1) * H;
   if (cls_out) SIMX_TRY(cls_gather(np, xbuf(0), B, S, H, psH, cls_out, cls_stride_b, st));
 
   for (int l = 0; l < L; ++l) {
-    const float* const* P = params + t.base + 16 * l;
-    const uint8_t* w = wb + lw.total * l;
-    const bf16* wqkv = reinterpret_cast<const bf16*>(w + lw.wqkv);
-    const bf16* wo = reinterpret_cast<const bf16*>(w + lw.wo);
-    const bf16* w1 = reinterpret_cast<const bf16*>(w + lw.w1);
-    const bf16* w2 = reinterpret_cast<const bf16*>(w + lw.w2);
-    const float* bqkv = reinterpret_cast<const float*>(w + lw.bqkv);
-    bf16* x = xbuf(l);
-    bf16* xo = xbuf(l + 1);
-    bf16* qkv = reinterpret_cast<bf16*>(lbuf(l, sl.l_qkv));
-    bf16* ctx = reinterpret_cast<bf16*>(lbuf(l, sl.l_ctx));
-    bf16* z1 = reinterpret_cast<bf16*>(lbuf(l, sl.l_z1));
-    bf16* x1 = reinterpret_cast<bf16*>(lbuf(l, sl.l_x1));
-    bf16* h = reinterpret_cast<bf16*>(lbuf(l, sl.l_h));
-    bf16* a = reinterpret_cast<bf16*>(lbuf(l, sl.l_a));
-    bf16* z2 = reinterpret_cast<bf16*>(lbuf(l, sl.l_z2));
-    float* lse = reinterpret_cast<float*>(lbuf(l, sl.l_lse));
-
-    prof_label("qkv_fwd");
-    SIMX_TRY(gemm(T, 3 * H, H, x, H, psH, false, wqkv, H, 3L * H * H, false, np, SIMX_EPI_BIAS, bqkv, nullptr, 0, 0, qkv,
-                  nullptr, 3 * H, ps3H, nullptr, 0, 1, st));
-    prof_label(nullptr);
-    SIMX_TRY(attention_forward(np, qkv, ps3H, ctx, psH, mask, lse, B, S, H, cfg->heads, st));
-    prof_label("attnout_fwd");
-    SIMX_TRY(gemm(T, H, H, ctx, H, psH, false, wo, H, (long)H * H, false, np, SIMX_EPI_BIAS_ADD, P[7], x, H, psH, z1,
-                  nullptr, H, psH, nullptr, 0, 1, st));
-    prof_label(nullptr);
-    SIMX_TRY(ln_fwd(np, z1, T, H, P[8], P[9], cfg->ln_eps, x1, psH, st));
-    prof_label("ffn1_fwd");
-    if (keep)
-      SIMX_TRY(gemm(T, I, H, x1, H, psH, false, w1, H, (long)I * H, false, np, SIMX_EPI_BIAS_GELU, P[11], nullptr, 0, 0, h, a,
-                    I, psI, nullptr, 0, 1, st));
-    else  // inference: gelu only, one [T, I] output instead of two
-      SIMX_TRY(gemm(T, I, H, x1, H, psH, false, w1, H, (long)I * H, false, np, SIMX_EPI_BIAS_GELU_FWD, P[11], nullptr, 0, 0, a,
-                    nullptr, I, psI, nullptr, 0, 1, st));
-    prof_label(nullptr);
-    prof_label("ffn2_fwd");
-    SIMX_TRY(gemm(T, H, I, a, I, psI, false, w2, I, (long)I * H, false, np, SIMX_EPI_BIAS_ADD, P[13], x1, H, psH, z2,
-                  nullptr, H, psH, nullptr, 0, 1, st));
-    prof_label(nullptr);
-    SIMX_TRY(ln_fwd(np, z2, T, H, P[14], P[15], cfg->ln_eps, xo, psH, st));
-    if (cls_out) SIMX_TRY(cls_gather(np, xo, B, S, H, psH, cls_out + (long)(l + 1) * H, cls_stride_b, st));
+    const LayerBufs lb = layer_bufs(lbase(l), sl);
+    SIMX_TRY(layer_forward(cfg, params + t.base + 16 * l, wb + lw.total * l, lw, l, xbuf(l), xbuf(l + 1), lb, mask, B, S, keep,
+                           st));
+    if (cls_out) SIMX_TRY(cls_gather(np, xbuf(l + 1), B, S, H, psH, cls_out + (long)(l + 1) * H, cls_stride_b, st));
   }
   if (seq_out) SIMX_TRY(planes_to_f32(np, xbuf(L), (long)T * H, psH, seq_out, st));
   return SIMX_OK;
 }
 
 extern "C" int simx_encoder_forward(const simx_encoder_cfg* cfg, const float* const* params, const void* wbuf,
-                                    const int64_t* ids, const int64_t* mask, int B, int S, void* saved, void* workspace,
+                                    const void* ids, const void* mask, int B, int S, void* saved, void* workspace,
                                     float* cls_out, float* seq_out, void* stream) {
   return encoder_forward_impl(cfg, params, wbuf, ids, mask, nullptr, B, S, saved, workspace, cls_out, seq_out, stream);
 }
 extern "C" int simx_encoder_forward_pos(const simx_encoder_cfg* cfg, const float* const* params, const void* wbuf,
-                                        const int64_t* ids, const int64_t* mask, const int64_t* pos_ids, int B, int S,
+                                        const void* ids, const void* mask, const void* pos_ids, int B, int S,
                                         void* saved, void* workspace, float* cls_out, float* seq_out, void* stream) {
   SIMX_CHECK(pos_ids != nullptr, SIMX_ERR_INVALID, "encoder_forward_pos: null position ids");
   return encoder_forward_impl(cfg, params, wbuf, ids, mask, pos_ids, B, S, saved, workspace, cls_out, seq_out, stream);
 }
 
+// Backward through layers [layer_lo, layer_hi) in descending order.  layer_hi == L starts the pass (the running cotangent
+// dx in the workspace is initialised from d_seq / d_cls[:, L]); layer_lo == -1 finishes it with the embedding backward.
+// Between calls the cotangent lives in the workspace, so a caller that splits the pass (one call per layer: gradients of
+// layer l are complete — and can be handed to DDP's reducer — while layer l-1 is still being computed) must pass the
+// same workspace to every call.
 static int encoder_backward_impl(const simx_encoder_cfg* cfg, const float* const* params, const void* wbuf,
-                                 const int64_t* ids, const int64_t* mask, const int64_t* pos_ids, int pad_id, int B, int S,
+                                 const void* ids, const void* mask, const void* pos_ids, int pad_id, int B, int S,
                                  const void* saved, void* workspace, const float* d_cls, const float* d_seq, float* grads,
-                                 void* stream) {
+                                 int layer_lo, int layer_hi, void* stream) {
   SIMX_TRY(check_cfg(cfg));
   SIMX_CHECK(params && wbuf && ids && saved && workspace && grads, SIMX_ERR_INVALID, "encoder_backward: null argument");
-  SIMX_CHECK(d_cls != nullptr || d_seq != nullptr, SIMX_ERR_INVALID, "encoder_backward: no cotangent given");
   SIMX_CHECK(B > 0 && S > 0 && S <= cfg->max_pos && S <= 512, SIMX_ERR_INVALID, "encoder_backward: bad B=%d S=%d", B, S);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const int np = cfg->precision, H = cfg->hidden, I = cfg->intermediate, L = cfg->num_layers;
+  SIMX_CHECK(layer_lo >= -1 && layer_lo < layer_hi && layer_hi <= L, SIMX_ERR_INVALID,
+             "encoder_backward: bad layer range [%d, %d) for %d layers", layer_lo, layer_hi, L);
+  SIMX_CHECK(layer_hi < L || d_cls != nullptr || d_seq != nullptr, SIMX_ERR_INVALID, "encoder_backward: no cotangent given");
   const int T = B * S;
   const long psH = (long)T * H, ps3H = (long)T * 3 * H, psI = (long)T * I;
   const ParamTable t = ptable(cfg);
@@ -405,25 +459,36 @@ static int encoder_backward_impl(const simx_encoder_cfg* cfg, const float* const
   const SavedL sl = saved_layout(cfg, B, S);
   const WsL wl = ws_layout(cfg, B, S);
   const uint8_t* wb = align_ptr(wbuf);
-  const uint8_t* sb = align_ptr(saved);
+  uint8_t* sb = align_ptr(saved);
   uint8_t* ws = align_ptr(workspace);
   bf16* dx = reinterpret_cast<bf16*>(ws + wl.dx);
   bf16* dza = reinterpret_cast<bf16*>(ws + wl.dza);
   bf16* dxb = reinterpret_cast<bf16*>(ws + wl.dxb);
+  bf16* dzm = reinterpret_cast<bf16*>(ws + wl.dzm);
   bf16* dh = reinterpret_cast<bf16*>(ws + wl.dh);
   bf16* dqkv = reinterpret_cast<bf16*>(ws + wl.dqkv);
   float* delta = reinterpret_cast<float*>(ws + wl.delta);
   const long cls_stride_b = (long)(L + 1) * H;
+  const int idw = id_bytes(cfg);
 
-  const int64_t total = simx_encoder_grad_numel(cfg);
-  SIMX_CUDA(cudaMemsetAsync(grads, 0, (size_t)total * sizeof(float), st));
   auto G = [&](int idx) -> float* { return grads + grad_offset(cfg, idx); };
+  // the gradient slices this call produces are accumulated into (split-K wgrads, atomics): zero them first
+  {
+    const int l0 = layer_lo < 0 ? 0 : layer_lo;
+    SIMX_CUDA(cudaMemsetAsync(grads + emb_grad_numel(cfg) + layer_grad_numel(cfg) * l0, 0,
+                              (size_t)layer_grad_numel(cfg) * (layer_hi - l0) * sizeof(float), st));
+    if (layer_lo < 0) SIMX_CUDA(cudaMemsetAsync(grads, 0, (size_t)emb_grad_numel(cfg) * sizeof(float), st));
+    if (layer_hi == L && t.bert)  // pooler: dead math in the reference (x 0), dense zero gradients
+      SIMX_CUDA(cudaMemsetAsync(grads + emb_grad_numel(cfg) + layer_grad_numel(cfg) * L, 0, ((size_t)H * H + H) * sizeof(float),
+                                st));
+  }
 
-  // cotangent of the last hidden state
-  SIMX_TRY(f32_to_planes(np, d_seq, (long)T * H, dx, psH, st));
-  if (d_cls) SIMX_TRY(cls_scatter_add(np, dx, B, S, H, psH, d_cls + (long)L * H, cls_stride_b, st));
+  if (layer_hi == L) {  // cotangent of the last hidden state
+    SIMX_TRY(f32_to_planes(np, d_seq, (long)T * H, dx, psH, st));
+    if (d_cls) SIMX_TRY(cls_scatter_add(np, dx, B, S, H, psH, d_cls + (long)L * H, cls_stride_b, st));
+  }
 
-  for (int l = L - 1; l >= 0; --l) {
+  for (int l = layer_hi - 1; l >= 0 && l >= layer_lo; --l) {
     const float* const* P = params + t.base + 16 * l;
     const int pi = t.base + 16 * l;
     const uint8_t* w = wb + lw.total * l;
@@ -431,59 +496,59 @@ static int encoder_backward_impl(const simx_encoder_cfg* cfg, const float* const
     const bf16* woT = reinterpret_cast<const bf16*>(w + lw.woT);
     const bf16* w1T = reinterpret_cast<const bf16*>(w + lw.w1T);
     const bf16* w2T = reinterpret_cast<const bf16*>(w + lw.w2T);
-    const uint8_t* lb = sb + sl.layer0 + sl.l_total * l;
     const bf16* x = reinterpret_cast<const bf16*>(sb + sl.x + sl.x_stride * l);
-    const bf16* qkv = reinterpret_cast<const bf16*>(lb + sl.l_qkv);
-    const bf16* ctx = reinterpret_cast<const bf16*>(lb + sl.l_ctx);
-    const bf16* z1 = reinterpret_cast<const bf16*>(lb + sl.l_z1);
-    const bf16* x1 = reinterpret_cast<const bf16*>(lb + sl.l_x1);
-    const bf16* h = reinterpret_cast<const bf16*>(lb + sl.l_h);
-    const bf16* a = reinterpret_cast<const bf16*>(lb + sl.l_a);
-    const bf16* z2 = reinterpret_cast<const bf16*>(lb + sl.l_z2);
-    const float* lse = reinterpret_cast<const float*>(lb + sl.l_lse);
+    LayerBufs lb;
+    if (ckpt(cfg)) {  // recompute this layer's activations from its saved input (same dropout masks: counter-based)
+      lb = layer_bufs(ws + wl.scratch, sl);
+      SIMX_TRY(layer_forward(cfg, P, w, lw, l, x, nullptr, lb, mask, B, S, true, st));
+    } else {
+      lb = layer_bufs(sb + sl.layer0 + sl.l_total * l, sl);
+    }
+    const DropSpec d_attn = drop_at(cfg, DROP_SITE_ATTN, l);
+    const DropSpec d_ao = drop_at(cfg, DROP_SITE_ATTN_OUT, l);
+    const DropSpec d_fo = drop_at(cfg, DROP_SITE_FFN_OUT, l);
 
-    // output LayerNorm -> dz2 (= d ffn-out = d residual x1), dgamma/dbeta, and db2 = colsum(dz2)
-    SIMX_TRY(ln_bwd(np, dx, z2, T, H, P[14], cfg->ln_eps, dza, psH, G(pi + 14), G(pi + 15), G(pi + 13), st));
-    // dW2 [H,I] += dz2^T a
+    // output LayerNorm -> dz2 (= d residual x1); dz2m = dz2 o mask flows into the FFN-down dense (dz2m == dz2 without
+    // dropout); dgamma/dbeta, and db2 = colsum(dz2m)
+    const bf16* dz2m = d_fo.thr_hi ? dzm : dza;
+    SIMX_TRY(ln_bwd(np, dx, lb.z2, T, H, P[14], cfg->ln_eps, dza, psH, G(pi + 14), G(pi + 15), G(pi + 13), dzm, 2, d_fo, st));
+    // dW2 [H,I] += dz2m^T a
     prof_label("ffn2_wgrad");
-    SIMX_TRY(gemm(H, I, T, dza, H, psH, true, a, I, psI, true, np, SIMX_EPI_ATOMIC_F32, nullptr, nullptr, 0, 0, nullptr,
+    SIMX_TRY(gemm(H, I, T, dz2m, H, psH, true, lb.a, I, psI, true, np, SIMX_EPI_ATOMIC_F32, nullptr, nullptr, 0, 0, nullptr,
                   nullptr, 0, 0, G(pi + 12), I, wgrad_ksplit(H, I, T), st));
-    prof_label(nullptr);
-    // dh = (dz2 W2) o gelu'(pre-activation)   (the forward epilogue saved gelu' in the `h` slot); db1 = colsum(dh)
+    // dh = (dz2m W2) o gelu'(pre-activation)   (the forward epilogue saved gelu' in the `h` slot); db1 = colsum(dh)
     // comes out of the same epilogue (a separate column-sum pass only where the staged epilogue does not run)
     prof_label("ffn2_dgrad");
-    SIMX_TRY(gemm(T, I, H, dza, H, psH, false, w2T, H, (long)I * H, false, np, SIMX_EPI_MUL, nullptr, h, I, psI, dh,
+    SIMX_TRY(gemm(T, I, H, dz2m, H, psH, false, w2T, H, (long)I * H, false, np, SIMX_EPI_MUL, nullptr, lb.h, I, psI, dh,
                   nullptr, I, psI, G(pi + 11), 0, 1, st));
-    prof_label(nullptr);
     // dW1 [I,H] += dh^T x1
     prof_label("ffn1_wgrad");
-    SIMX_TRY(gemm(I, H, T, dh, I, psI, true, x1, H, psH, true, np, SIMX_EPI_ATOMIC_F32, nullptr, nullptr, 0, 0, nullptr,
+    SIMX_TRY(gemm(I, H, T, dh, I, psI, true, lb.x1, H, psH, true, np, SIMX_EPI_ATOMIC_F32, nullptr, nullptr, 0, 0, nullptr,
                   nullptr, 0, 0, G(pi + 10), H, wgrad_ksplit(I, H, T), st));
-    prof_label(nullptr);
-    // dx1 = dh W1 + dz2
+    // dx1 = dh W1 + dz2 (the residual path carries the un-masked dz2)
     prof_label("ffn1_dgrad");
     SIMX_TRY(gemm(T, H, I, dh, I, psI, false, w1T, I, (long)I * H, false, np, SIMX_EPI_ADD, nullptr, dza, H, psH, dxb,
                   nullptr, H, psH, nullptr, 0, 1, st));
     prof_label(nullptr);
-    // attention-output LayerNorm -> dz1, and dbo = colsum(dz1)
-    SIMX_TRY(ln_bwd(np, dxb, z1, T, H, P[8], cfg->ln_eps, dza, psH, G(pi + 8), G(pi + 9), G(pi + 7), st));
-    // dWo [H,H] += dz1^T ctx
+    // attention-output LayerNorm -> dz1 (+ masked copy for the dense), and dbo = colsum(dz1m)
+    const bf16* dz1m = d_ao.thr_hi ? dzm : dza;
+    SIMX_TRY(ln_bwd(np, dxb, lb.z1, T, H, P[8], cfg->ln_eps, dza, psH, G(pi + 8), G(pi + 9), G(pi + 7), dzm, 2, d_ao, st));
+    // dWo [H,H] += dz1m^T ctx
     prof_label("attnout_wgrad");
-    SIMX_TRY(gemm(H, H, T, dza, H, psH, true, ctx, H, psH, true, np, SIMX_EPI_ATOMIC_F32, nullptr, nullptr, 0, 0, nullptr,
+    SIMX_TRY(gemm(H, H, T, dz1m, H, psH, true, lb.ctx, H, psH, true, np, SIMX_EPI_ATOMIC_F32, nullptr, nullptr, 0, 0, nullptr,
                   nullptr, 0, 0, G(pi + 6), H, wgrad_ksplit(H, H, T), st));
-    prof_label(nullptr);
-    // dctx = dz1 Wo
+    // dctx = dz1m Wo
     prof_label("attnout_dgrad");
-    SIMX_TRY(gemm(T, H, H, dza, H, psH, false, woT, H, (long)H * H, false, np, SIMX_EPI_PLAIN, nullptr, nullptr, 0, 0, dxb,
+    SIMX_TRY(gemm(T, H, H, dz1m, H, psH, false, woT, H, (long)H * H, false, np, SIMX_EPI_PLAIN, nullptr, nullptr, 0, 0, dxb,
                   nullptr, H, psH, nullptr, 0, 1, st));
     prof_label(nullptr);
     // dqkv, and the fused q/k/v bias gradient (column sums of dqkv) from the same kernel
-    SIMX_TRY(attention_backward(np, qkv, ps3H, ctx, dxb, psH, dqkv, mask, lse, delta, B, S, H, cfg->heads, G(pi + 1), st));
+    SIMX_TRY(attention_backward(np, lb.qkv, ps3H, lb.ctx, dxb, psH, dqkv, mask, idw, lb.lse, delta, B, S, H, cfg->heads,
+                                G(pi + 1), d_attn, st));
     // fused q/k/v weight gradient ([3H,H] block of the flat gradient buffer)
     prof_label("qkv_wgrad");
     SIMX_TRY(gemm(3 * H, H, T, dqkv, 3 * H, ps3H, true, x, H, psH, true, np, SIMX_EPI_ATOMIC_F32, nullptr, nullptr, 0, 0,
                   nullptr, nullptr, 0, 0, G(pi + 0), H, wgrad_ksplit(3 * H, H, T), st));
-    prof_label(nullptr);
     // dx(layer input) = dqkv Wqkv + dz1   (+ the [CLS] cotangent LEAD injects at this depth)
     prof_label("qkv_dgrad");
     SIMX_TRY(gemm(T, H, 3 * H, dqkv, 3 * H, ps3H, false, wqkvT, 3 * H, 3L * H * H, false, np, SIMX_EPI_ADD, nullptr, dza, H,
@@ -491,32 +556,44 @@ static int encoder_backward_impl(const simx_encoder_cfg* cfg, const float* const
     prof_label(nullptr);
     if (d_cls) SIMX_TRY(cls_scatter_add(np, dx, B, S, H, psH, d_cls + (long)l * H, cls_stride_b, st));
   }
-  // embeddings
+  if (layer_lo >= 0) return SIMX_OK;
+  // embeddings: x0 = dropout(LN(z0)); the mask is re-applied to the cotangent on load
   const bf16* z0 = reinterpret_cast<const bf16*>(sb + sl.z0);
   const int ig = t.bert ? 3 : 2;
-  SIMX_TRY(ln_bwd(np, dx, z0, T, H, params[ig], cfg->ln_eps, dza, psH, G(ig), G(ig + 1), t.bert ? G(2) : nullptr, st));
+  SIMX_TRY(ln_bwd(np, dx, z0, T, H, params[ig], cfg->ln_eps, dza, psH, G(ig), G(ig + 1), t.bert ? G(2) : nullptr, nullptr, 1,
+                  drop_at(cfg, DROP_SITE_EMBED, 0), st));
   if (pos_ids == nullptr) {
     // position rows: dPos[s] = sum_b dz0[b*S + s]: a column sum of the [B, S*H] view
     SIMX_TRY(colsum(np, dza, B, S * H, (long)S * H, psH, G(1), st));
   } else {
     // caller-supplied position ids (RoBERTa): scatter-add like the word rows; the pad position row gets nothing
-    SIMX_TRY(embed_scatter(np, pos_ids, dza, T, H, cfg->max_pos, pad_id, psH, G(1), st));
+    SIMX_TRY(embed_scatter(np, pos_ids, idw, dza, T, H, cfg->max_pos, pad_id, psH, G(1), st));
   }
-  SIMX_TRY(embed_scatter(np, ids, dza, T, H, cfg->vocab, pad_id, psH, G(0), st));
+  SIMX_TRY(embed_scatter(np, ids, idw, dza, T, H, cfg->vocab, pad_id, psH, G(0), st));
   return SIMX_OK;
 }
 
 extern "C" int simx_encoder_backward(const simx_encoder_cfg* cfg, const float* const* params, const void* wbuf,
-                                     const int64_t* ids, const int64_t* mask, int B, int S, const void* saved,
+                                     const void* ids, const void* mask, int B, int S, const void* saved,
                                      void* workspace, const float* d_cls, const float* d_seq, float* grads,
                                      void* stream) {
-  return encoder_backward_impl(cfg, params, wbuf, ids, mask, nullptr, 0, B, S, saved, workspace, d_cls, d_seq, grads, stream);
+  SIMX_TRY(check_cfg(cfg));
+  return encoder_backward_impl(cfg, params, wbuf, ids, mask, nullptr, 0, B, S, saved, workspace, d_cls, d_seq, grads, -1,
+                               cfg->num_layers, stream);
 }
 extern "C" int simx_encoder_backward_pos(const simx_encoder_cfg* cfg, const float* const* params, const void* wbuf,
-                                         const int64_t* ids, const int64_t* mask, const int64_t* pos_ids, int pad_token_id,
+                                         const void* ids, const void* mask, const void* pos_ids, int pad_token_id,
                                          int B, int S, const void* saved, void* workspace, const float* d_cls,
                                          const float* d_seq, float* grads, void* stream) {
+  SIMX_TRY(check_cfg(cfg));
   SIMX_CHECK(pos_ids != nullptr, SIMX_ERR_INVALID, "encoder_backward_pos: null position ids");
   return encoder_backward_impl(cfg, params, wbuf, ids, mask, pos_ids, pad_token_id, B, S, saved, workspace, d_cls, d_seq,
-                               grads, stream);
+                               grads, -1, cfg->num_layers, stream);
+}
+extern "C" int simx_encoder_backward_layers(const simx_encoder_cfg* cfg, const float* const* params, const void* wbuf,
+                                            const void* ids, const void* mask, const void* pos_ids, int pad_token_id,
+                                            int B, int S, const void* saved, void* workspace, const float* d_cls,
+                                            const float* d_seq, float* grads, int layer_lo, int layer_hi, void* stream) {
+  return encoder_backward_impl(cfg, params, wbuf, ids, mask, pos_ids, pad_token_id, B, S, saved, workspace, d_cls, d_seq,
+                               grads, layer_lo, layer_hi, stream);
 }

@@ -39,6 +39,7 @@ struct GemmParams {
   long ldof;
   float* colsum;  // EPI_MUL, staged epilogue: [N] fp32, += column sums of the bf16 output (bias gradient of the layer
                   // whose dgrad this GEMM computes), or NULL
+  DropSpec drop;  // EPI_BIAS_DROP_ADD: the dropout mask of (acc + bias), row = m, column = n
 };
 
 // TS: the epilogue stages its bf16 output tile in shared memory and writes it with TMA (full 128-byte lines) instead
@@ -55,7 +56,7 @@ struct GemmSmem {
   static constexpr uint32_t STG_BYTES = TS ? 16 * 4096 : 0;  // one [32 rows x 64 cols] bf16 box per epilogue warp
   static constexpr uint32_t BAR_OFF = STG_OFF + STG_BYTES;
   static constexpr uint32_t BIAS_OFF = BAR_OFF + 512;  // ring + TMEM barriers, then one barrier per epilogue warp (aux loads)
-  static constexpr uint32_t BIAS_FLOATS = 3072;  // the whole bias vector lives in smem when N fits (else global loads)
+  static constexpr uint32_t BIAS_FLOATS = 4096;  // the whole bias vector lives in smem when N fits (else global loads)
   static constexpr uint32_t TOTAL = BIAS_OFF + BIAS_FLOATS * 4 + 1024;  // + alignment slack
 };
 template <int BN, bool MN, int EPI, int NP>
@@ -66,8 +67,9 @@ constexpr bool kTmaStore = (BN == 256) && (NP == 1) && !MN && (EPI != SIMX_EPI_A
 template <int EPI, int NP>
 struct EpiPre {
   static constexpr bool kBias = EPI == SIMX_EPI_BIAS || EPI == SIMX_EPI_BIAS_GELU || EPI == SIMX_EPI_BIAS_ADD ||
-                                EPI == SIMX_EPI_BIAS_GELU_FWD;
-  static constexpr bool kAux = EPI == SIMX_EPI_BIAS_ADD || EPI == SIMX_EPI_ADD || EPI == SIMX_EPI_MUL;
+                                EPI == SIMX_EPI_BIAS_GELU_FWD || EPI == EPI_BIAS_DROP_ADD;
+  static constexpr bool kAux = EPI == SIMX_EPI_BIAS_ADD || EPI == SIMX_EPI_ADD || EPI == SIMX_EPI_MUL ||
+                               EPI == EPI_BIAS_DROP_ADD;
   uint4 aux[kAux ? NP : 1][kAux ? 4 : 1];
 };
 
@@ -139,7 +141,7 @@ __device__ __forceinline__ void gelu_exact(float x, float& g, float& dg) {
 
 // values of D[row, col .. col+8) after the fused epilogue: v (and for BIAS_GELU: v = gelu', v2 = gelu) in fp32
 template <int EPI, int NP>
-__device__ __forceinline__ void epi_values(const GemmParams& p, int col, const uint32_t* acc8,
+__device__ __forceinline__ void epi_values(const GemmParams& p, int row, int col, const uint32_t* acc8,
                                            const EpiPre<EPI, NP>& pre, int g, const float* sbias, float (&v)[8]) {
 #pragma unroll
   for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(acc8[i]);
@@ -151,6 +153,9 @@ __device__ __forceinline__ void epi_values(const GemmParams& p, int col, const u
     v[0] += b0.x; v[1] += b0.y; v[2] += b0.z; v[3] += b0.w;
     v[4] += b1.x; v[5] += b1.y; v[6] += b1.z; v[7] += b1.w;
   }
+  if constexpr (EPI == EPI_BIAS_DROP_ADD)  // dropout sits between the dense layer and the residual add
+    drop_apply8(v, drop_bits(p.drop, static_cast<uint32_t>(col) >> 3, static_cast<uint32_t>(row), 0u), p.drop.thr_hi,
+                p.drop.scale);
   if constexpr (EpiPre<EPI, NP>::kAux) {
     float a[8];
 #pragma unroll
@@ -183,7 +188,7 @@ __device__ __forceinline__ void epilogue_chunk(const GemmParams& p, int row, int
     const int col = col0 + g * 8;
     if (col >= p.N) break;  // N % 8 == 0 is enforced on the host
     float v[8];
-    epi_values<EPI, NP>(p, col, &acc[g * 8], pre, g, sbias, v);
+    epi_values<EPI, NP>(p, row, col, &acc[g * 8], pre, g, sbias, v);
     if constexpr (EPI == SIMX_EPI_ATOMIC_F32) {
       float* o = p.outf + (long)row * p.ldof + col;
       asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(o), "f"(v[0]), "f"(v[1]), "f"(v[2]), "f"(v[3])
@@ -457,7 +462,7 @@ gemm_kernel(const GemmParams p, const __grid_constant__ CUtensorMap mapA, const 
             const int j = c * 4 + g;  // 16-byte chunk index inside the 128-byte row
             if constexpr (kAuxTma) pre.aux[0][g] = ld_shared_v4(stg_row + ((j ^ (lane & 7)) << 4));
             float f[8];
-            epi_values<EPI, NP>(p, min(col_base + j * 8, p.N - 8), &v[g * 8], pre, g, sbias, f);
+            epi_values<EPI, NP>(p, row, min(col_base + j * 8, p.N - 8), &v[g * 8], pre, g, sbias, f);
             uint4 o;
             if constexpr (EPI == SIMX_EPI_BIAS_GELU) {
               uint32_t ge[4], dg[4];
@@ -666,6 +671,7 @@ static int dispatch_epi(int epi, const GemmParams& p, const bf16* A, long lda, l
       case SIMX_EPI_ADD: return launch_gemm<BN, MN, SIMX_EPI_ADD, NP>(p, A, lda, a_ps, B, ldb, b_ps, planes, stream);
       case SIMX_EPI_ATOMIC_F32: return launch_gemm<BN, MN, SIMX_EPI_ATOMIC_F32, NP>(p, A, lda, a_ps, B, ldb, b_ps, planes, stream);
       case SIMX_EPI_BIAS_GELU_FWD: return launch_gemm<BN, MN, SIMX_EPI_BIAS_GELU_FWD, NP>(p, A, lda, a_ps, B, ldb, b_ps, planes, stream);
+      case EPI_BIAS_DROP_ADD: return launch_gemm<BN, MN, EPI_BIAS_DROP_ADD, NP>(p, A, lda, a_ps, B, ldb, b_ps, planes, stream);
     }
     SIMX_FAIL(SIMX_ERR_INVALID, "unknown GEMM epilogue %d", epi);
   }
@@ -674,7 +680,7 @@ static int dispatch_epi(int epi, const GemmParams& p, const bf16* A, long lda, l
 static int gemm_launch(int M, int N, int K, const bf16* A, long lda, long a_ps, bool a_mn, const bf16* B, long ldb, long b_ps,
                        bool b_mn, int planes, int epi, const float* bias, const bf16* aux, long ldaux, long aux_ps,
                        bf16* out, bf16* out2, long ldo, long out_ps, float* outf, long ldof, int ksplit,
-                       bool* colsum_fused, cudaStream_t stream) {
+                       bool* colsum_fused, const DropSpec* drop, cudaStream_t stream) {
   SIMX_CHECK(M > 0 && N > 0 && K > 0, SIMX_ERR_INVALID, "gemm: empty problem %dx%dx%d", M, N, K);
   SIMX_CHECK(N % 8 == 0, SIMX_ERR_INVALID, "gemm: N=%d must be a multiple of 8", N);
   SIMX_CHECK(a_mn == b_mn, SIMX_ERR_INVALID, "gemm: mixed operand majors are not instantiated");
@@ -688,10 +694,12 @@ static int gemm_launch(int M, int N, int K, const bf16* A, long lda, long a_ps, 
     SIMX_CHECK(out != nullptr && ldo % 8 == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0, SIMX_ERR_INVALID,
                "gemm: bf16 output must be 16-byte aligned with ld %% 8 == 0");
   }
-  if (epi == SIMX_EPI_BIAS || epi == SIMX_EPI_BIAS_GELU || epi == SIMX_EPI_BIAS_ADD || epi == SIMX_EPI_BIAS_GELU_FWD)
+  if (epi == SIMX_EPI_BIAS_ADD && drop != nullptr && drop->thr_hi != 0u) epi = EPI_BIAS_DROP_ADD;
+  if (epi == SIMX_EPI_BIAS || epi == SIMX_EPI_BIAS_GELU || epi == SIMX_EPI_BIAS_ADD || epi == SIMX_EPI_BIAS_GELU_FWD ||
+      epi == EPI_BIAS_DROP_ADD)
     SIMX_CHECK(bias != nullptr && (reinterpret_cast<uintptr_t>(bias) & 15) == 0, SIMX_ERR_INVALID,
                "gemm: bias missing or misaligned");
-  if (epi == SIMX_EPI_BIAS_ADD || epi == SIMX_EPI_MUL || epi == SIMX_EPI_ADD)
+  if (epi == SIMX_EPI_BIAS_ADD || epi == SIMX_EPI_MUL || epi == SIMX_EPI_ADD || epi == EPI_BIAS_DROP_ADD)
     SIMX_CHECK(aux != nullptr && ldaux % 8 == 0 && (reinterpret_cast<uintptr_t>(aux) & 15) == 0, SIMX_ERR_INVALID,
                "gemm: aux missing or misaligned");
   if (epi == SIMX_EPI_BIAS_GELU) SIMX_CHECK(out2 != nullptr, SIMX_ERR_INVALID, "gemm: out2 missing");
@@ -722,9 +730,10 @@ static int gemm_launch(int M, int N, int K, const bf16* A, long lda, long a_ps, 
   p.bias = bias; p.outf = outf; p.ldof = ldof;
   // EPI_MUL + outf: outf[N] += column sums of the output.  Fused into the staged epilogue when that instantiation runs
   // (BN 256, one plane, N fits the smem accumulator); otherwise the column-sum kernel runs over `out` afterwards.
+  p.drop = (epi == EPI_BIAS_DROP_ADD) ? *drop : no_drop();
   p.colsum = nullptr;
   const bool want_colsum = epi == SIMX_EPI_MUL && outf != nullptr;
-  const bool fuse_colsum = want_colsum && BN == 256 && planes == 1 && !a_mn && N <= 3072;
+  const bool fuse_colsum = want_colsum && BN == 256 && planes == 1 && !a_mn && N <= 4096;
   if (fuse_colsum) p.colsum = outf;
   *colsum_fused = fuse_colsum;
 
@@ -751,12 +760,14 @@ int colsum(int np, const bf16* x, long rows, int N, long row_stride, long ps, fl
 
 // Internal entry used by the encoder and by simx_gemm(): the GEMM, plus the column-sum pass when the EPI_MUL bias
 // gradient could not ride in the epilogue.
+// drop (optional): turns SIMX_EPI_BIAS_ADD into out = dropout(acc + bias) + aux.
 int gemm(int M, int N, int K, const bf16* A, long lda, long a_ps, bool a_mn, const bf16* B, long ldb, long b_ps,
          bool b_mn, int planes, int epi, const float* bias, const bf16* aux, long ldaux, long aux_ps, bf16* out,
-         bf16* out2, long ldo, long out_ps, float* outf, long ldof, int ksplit, cudaStream_t stream) {
+         bf16* out2, long ldo, long out_ps, float* outf, long ldof, int ksplit, cudaStream_t stream,
+         const DropSpec* drop) {
   bool fused = false;
   SIMX_TRY(gemm_launch(M, N, K, A, lda, a_ps, a_mn, B, ldb, b_ps, b_mn, planes, epi, bias, aux, ldaux, aux_ps, out, out2,
-                       ldo, out_ps, outf, ldof, ksplit, &fused, stream));
+                       ldo, out_ps, outf, ldof, ksplit, &fused, drop, stream));
   if (epi == SIMX_EPI_MUL && outf != nullptr && !fused) SIMX_TRY(colsum(planes, out, M, N, ldo, out_ps, outf, stream));
   return SIMX_OK;
 }
@@ -769,8 +780,10 @@ extern "C" int simx_gemm(int M, int N, int K, const void* A, int64_t lda, int64_
                          void* out2, int64_t ldo, int64_t out_plane_stride, float* outf, int64_t ldof, int ksplit,
                          void* stream) {
   using namespace simx;
+  SIMX_CHECK(epilogue >= SIMX_EPI_PLAIN && epilogue <= SIMX_EPI_BIAS_GELU_FWD, SIMX_ERR_INVALID, "unknown GEMM epilogue %d",
+             epilogue);
   return gemm(M, N, K, static_cast<const bf16*>(A), lda, a_plane_stride, a_mn_major != 0, static_cast<const bf16*>(B),
               ldb, b_plane_stride, b_mn_major != 0, planes, epilogue, bias, static_cast<const bf16*>(aux), ldaux,
               aux_plane_stride, static_cast<bf16*>(out), static_cast<bf16*>(out2), ldo, out_plane_stride, outf, ldof,
-              ksplit, static_cast<cudaStream_t>(stream));
+              ksplit, static_cast<cudaStream_t>(stream), nullptr);
 }

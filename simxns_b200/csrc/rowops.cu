@@ -23,7 +23,8 @@ __device__ __forceinline__ void ld8f(const float* p, float (&v)[8]) {
 // normalise the row held in v (NC chunks of 8 per lane), write y = xhat * g + b
 template <int NP>
 __device__ __forceinline__ void ln_row_store(float (&v)[MAXC][8], int H, int lane, const float* gamma,
-                                             const float* beta, float eps, bf16* out, long ps) {
+                                             const float* beta, float eps, bf16* out, long ps, const DropSpec& drop,
+                                             int row) {
   float s = 0.f;
 #pragma unroll
   for (int c = 0; c < MAXC; ++c)
@@ -50,6 +51,7 @@ __device__ __forceinline__ void ln_row_store(float (&v)[MAXC][8], int H, int lan
       ld8f(beta + col, b);
 #pragma unroll
       for (int i = 0; i < 8; ++i) y[i] = (v[c][i] - mean) * rstd * g[i] + b[i];
+      if (drop.thr_hi != 0u) drop_apply8(y, drop_bits(drop, col >> 3, row, 0u), drop.thr_hi, drop.scale);  // embeddings dropout
       split_store8<NP>(out + col, ps, y);
     }
   }
@@ -60,20 +62,20 @@ __device__ __forceinline__ void ln_row_store(float (&v)[MAXC][8], int H, int lan
 // ------------------------------------------------------------------------------------------------
 template <int NP>
 __global__ void __launch_bounds__(ROW_THREADS)
-embed_ln_kernel(const int64_t* __restrict__ ids, const int64_t* __restrict__ pos_ids, int max_pos, int T, int S, int H,
-                int vocab, const float* __restrict__ word, const float* __restrict__ pos,
+embed_ln_kernel(const void* __restrict__ ids, const void* __restrict__ pos_ids, int id_bytes, int max_pos, int T, int S,
+                int H, int vocab, const float* __restrict__ word, const float* __restrict__ pos,
                 const float* __restrict__ type0, const float* __restrict__ gamma, const float* __restrict__ beta, float eps,
-                bf16* z0, bf16* x, long ps) {
+                bf16* z0, bf16* x, long ps, const DropSpec drop) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int row = blockIdx.x * ROW_WARPS + warp;
   if (row >= T) return;
-  long id = ids[row];
+  long id = ld_id(ids, row, id_bytes);
   if (id < 0 || id >= vocab) id = 0;  // out-of-range ids are a caller bug; stay in bounds
   // position row: the token's index in its sequence (BERT), or the caller's position ids (RoBERTa: pad + running count
   // of real tokens)
   long s = row % S;
   if (pos_ids != nullptr) {
-    s = pos_ids[row];
+    s = ld_id(pos_ids, row, id_bytes);
     if (s < 0 || s >= max_pos) s = 0;
   }
   float v[MAXC][8];
@@ -101,7 +103,7 @@ embed_ln_kernel(const int64_t* __restrict__ ids, const int64_t* __restrict__ pos
       }
     }
   }
-  ln_row_store<NP>(v, H, lane, gamma, beta, eps, x + (long)row * H, ps);
+  ln_row_store<NP>(v, H, lane, gamma, beta, eps, x + (long)row * H, ps, drop, row);
 }
 
 template <int NP>
@@ -196,10 +198,13 @@ ln_fwd_kernel(const bf16* __restrict__ z, int T, int H, const float* __restrict_
 // row is reduced, so each warp keeps two rows of HBM traffic in flight.
 constexpr int LNB_THREADS = 384;  // 12 warps x ~168 registers: the whole register file of an SM (8 warps left it half idle:
 constexpr int LNB_WARPS = LNB_THREADS / 32;  // ncu warps_active 12.5 %, DRAM 53 %)
-template <int NP, int NC>
+// DM: 0 no dropout; 1 the cotangent dy is masked on load (the LayerNorm output was dropped: embeddings); 2 a second,
+// masked copy dzm = dz o mask is written (what flows into the dense layer whose dropped output was added to the
+// residual: dz itself continues down the residual path) and dbias sums the masked values.
+template <int NP, int NC, int DM>
 __global__ void __launch_bounds__(LNB_THREADS)
 ln_bwd_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ z, int T, int H, const float* __restrict__ gamma,
-              float eps, bf16* dz, long ps, float* dgamma, float* dbeta, float* dbias) {
+              float eps, bf16* dz, long ps, float* dgamma, float* dbeta, float* dbias, bf16* dzm, const DropSpec drop) {
   __shared__ float red[LNB_WARPS][32 * 8 + 8];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   float ag[NC][8], ab[NC][8], ad[NC][8];
@@ -233,6 +238,8 @@ ln_bwd_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ z, int T, in
       if (c * 256 + lane * 8 < H) {
         unpack8<NP>(zr[c], v[c]);
         unpack8<NP>(dr[c], g[c]);
+        if constexpr (DM == 1)
+          drop_apply8(g[c], drop_bits(drop, (c * 256 + lane * 8) >> 3, row, 0u), drop.thr_hi, drop.scale);
 #pragma unroll
         for (int i = 0; i < 8; ++i) s += v[c][i];
       }
@@ -277,11 +284,14 @@ ln_bwd_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ z, int T, in
       if (col < H) {
         float o[8];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          o[i] = rstd * (g[c][i] - s1 - v[c][i] * s2);
-          ad[c][i] += o[i];
-        }
+        for (int i = 0; i < 8; ++i) o[i] = rstd * (g[c][i] - s1 - v[c][i] * s2);
         split_store8<NP>(dz + (long)row * H + col, ps, o);
+        if constexpr (DM == 2) {
+          drop_apply8(o, drop_bits(drop, col >> 3, row, 0u), drop.thr_hi, drop.scale);
+          split_store8<NP>(dzm + (long)row * H + col, ps, o);
+        }
+#pragma unroll
+        for (int i = 0; i < 8; ++i) ad[c][i] += o[i];
       }
     }
   }
@@ -397,12 +407,12 @@ __global__ void planes_to_f32_kernel(const bf16* __restrict__ src, long n, long 
 // ------------------------------------------------------------------------------------------------
 template <int NP>
 __global__ void __launch_bounds__(ROW_THREADS)
-embed_scatter_kernel(const int64_t* __restrict__ ids, const bf16* __restrict__ dz0, int T, int H, int vocab, int pad_id,
-                     long ps, float* dword) {
+embed_scatter_kernel(const void* __restrict__ ids, int id_bytes, const bf16* __restrict__ dz0, int T, int H, int vocab,
+                     int pad_id, long ps, float* dword) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int row = blockIdx.x * ROW_WARPS + warp;
   if (row >= T) return;
-  const long id = ids[row];
+  const long id = ld_id(ids, row, id_bytes);
   if (id < 0 || id >= vocab || id == pad_id) return;  // nn.Embedding(padding_idx): the pad row never receives gradient
   for (int col = lane * 8; col < H; col += 256) {
     float v[8];
@@ -494,15 +504,15 @@ __global__ void convert_weights_batched_kernel(const ConvJobs jobs) {
     else { constexpr int kNP = 3; CALL; }                               \
   } while (0)
 
-int embed_ln(int np, const int64_t* ids, const int64_t* pos_ids, int max_pos, int T, int S, int H, int vocab,
+int embed_ln(int np, const void* ids, const void* pos_ids, int id_bytes, int max_pos, int T, int S, int H, int vocab,
              const float* word, const float* pos, const float* type0, const float* gamma, const float* beta, float eps,
-             bf16* z0, bf16* x, long ps, cudaStream_t st) {
+             bf16* z0, bf16* x, long ps, const DropSpec& drop, cudaStream_t st) {
   ProfScope prof("embed_ln", 0, (double)T * H * (8.0 + 4.0 * np), st);
   SIMX_CHECK(H % 8 == 0 && H <= 256 * MAXC, SIMX_ERR_INVALID, "hidden size %d unsupported (multiple of 8, <= %d)", H,
              256 * MAXC);
   const int grid = (T + ROW_WARPS - 1) / ROW_WARPS;
-  SIMX_NP_DISPATCH(np, (embed_ln_kernel<kNP><<<grid, ROW_THREADS, 0, st>>>(ids, pos_ids, max_pos, T, S, H, vocab, word, pos,
-                                                                           type0, gamma, beta, eps, z0, x, ps)));
+  SIMX_NP_DISPATCH(np, (embed_ln_kernel<kNP><<<grid, ROW_THREADS, 0, st>>>(ids, pos_ids, id_bytes, max_pos, T, S, H, vocab, word,
+                                                                           pos, type0, gamma, beta, eps, z0, x, ps, drop)));
   SIMX_LAUNCH_CHECK();
   return SIMX_OK;
 }
@@ -526,21 +536,33 @@ int ln_fwd(int np, const bf16* z, int T, int H, const float* gamma, const float*
   return SIMX_OK;
 }
 
+// drop_mode 0: plain; 1: dy is masked on load (`drop` = the mask that was applied to this LayerNorm's output);
+// 2: dzm (same shape as dz) receives dz o mask and dbias sums the masked values (`drop` = the mask of the dense output
+// that was added to the residual to form z)
 int ln_bwd(int np, const bf16* dy, const bf16* z, int T, int H, const float* gamma, float eps, bf16* dz, long ps,
-           float* dgamma, float* dbeta, float* dbias, cudaStream_t st) {
-  ProfScope prof("ln_bwd", 0, (double)T * H * 6.0 * np, st);
+           float* dgamma, float* dbeta, float* dbias, bf16* dzm, int drop_mode, const DropSpec& drop, cudaStream_t st) {
+  ProfScope prof("ln_bwd", 0, (double)T * H * (drop_mode == 2 ? 8.0 : 6.0) * np, st);
+  if (drop.thr_hi == 0u) drop_mode = 0;
+  SIMX_CHECK(drop_mode != 2 || dzm != nullptr, SIMX_ERR_INVALID, "ln_bwd: masked output buffer missing");
   SIMX_CHECK(H % 8 == 0 && H <= 256 * MAXC, SIMX_ERR_INVALID, "hidden size %d unsupported", H);
   int grid = (T + LNB_WARPS - 1) / LNB_WARPS;
   grid = min(grid, num_sms());  // ~168 registers/thread: one resident block per SM, persistent over rows
   const int nc = (H + 255) / 256;
-#define SIMX_LN_BWD(NP_, NC_) \
-  ln_bwd_kernel<NP_, NC_><<<grid, LNB_THREADS, 0, st>>>(dy, z, T, H, gamma, eps, dz, ps, dgamma, dbeta, dbias)
+#define SIMX_LN_BWD_DM(NP_, NC_, DM_) \
+  ln_bwd_kernel<NP_, NC_, DM_><<<grid, LNB_THREADS, 0, st>>>(dy, z, T, H, gamma, eps, dz, ps, dgamma, dbeta, dbias, dzm, drop)
+#define SIMX_LN_BWD(NP_, NC_)                                       \
+  do {                                                              \
+    if (drop_mode == 0) SIMX_LN_BWD_DM(NP_, NC_, 0);                \
+    else if (drop_mode == 1) SIMX_LN_BWD_DM(NP_, NC_, 1);           \
+    else SIMX_LN_BWD_DM(NP_, NC_, 2);                               \
+  } while (0)
   if (np == 1) {
     if (nc == 1) SIMX_LN_BWD(1, 1); else if (nc == 2) SIMX_LN_BWD(1, 2); else if (nc == 3) SIMX_LN_BWD(1, 3); else SIMX_LN_BWD(1, 4);
   } else {
     if (nc == 1) SIMX_LN_BWD(3, 1); else if (nc == 2) SIMX_LN_BWD(3, 2); else if (nc == 3) SIMX_LN_BWD(3, 3); else SIMX_LN_BWD(3, 4);
   }
 #undef SIMX_LN_BWD
+#undef SIMX_LN_BWD_DM
   SIMX_LAUNCH_CHECK();
   return SIMX_OK;
 }
@@ -581,11 +603,12 @@ int planes_to_f32(int np, const bf16* src, long n, long ps, float* dst, cudaStre
   SIMX_LAUNCH_CHECK();
   return SIMX_OK;
 }
-int embed_scatter(int np, const int64_t* ids, const bf16* dz0, int T, int H, int vocab, int pad_id, long ps, float* dword,
-                  cudaStream_t st) {
+int embed_scatter(int np, const void* ids, int id_bytes, const bf16* dz0, int T, int H, int vocab, int pad_id, long ps,
+                  float* dword, cudaStream_t st) {
   ProfScope prof("embed_scatter", 0, (double)T * H * (2.0 * np + 8.0), st);
   const int grid = (T + ROW_WARPS - 1) / ROW_WARPS;
-  SIMX_NP_DISPATCH(np, (embed_scatter_kernel<kNP><<<grid, ROW_THREADS, 0, st>>>(ids, dz0, T, H, vocab, pad_id, ps, dword)));
+  SIMX_NP_DISPATCH(np, (embed_scatter_kernel<kNP><<<grid, ROW_THREADS, 0, st>>>(ids, id_bytes, dz0, T, H, vocab, pad_id, ps,
+                                                                                dword)));
   SIMX_LAUNCH_CHECK();
   return SIMX_OK;
 }

@@ -19,9 +19,6 @@
 
 namespace simx {
 
-int gemm(int M, int N, int K, const bf16* A, long lda, long a_ps, bool a_mn, const bf16* B, long ldb, long b_ps,
-         bool b_mn, int planes, int epi, const float* bias, const bf16* aux, long ldaux, long aux_ps, bf16* out,
-         bf16* out2, long ldo, long out_ps, float* outf, long ldof, int ksplit, cudaStream_t stream);
 int convert_weight(int np, const float* w, int R, int C, bf16* dst, long ld_dst, long ps_dst, bf16* dst_t, long ld_t,
                    long ps_t, cudaStream_t st);
 

@@ -35,12 +35,14 @@ class EncoderConfig:
     roberta_positions: bool = False  # HF RobertaModel position ids: pad + cumsum(ids != pad), pad for padding
     pooler: bool = True              # False: RobertaModel(add_pooling_layer=False) — no `pooler.*` parameters exposed
 
-    def c_struct(self, precision: int) -> _lib.EncoderCfg:
+    def c_struct(self, precision: int, hidden_dropout: float = 0.0, attn_dropout: float = 0.0, dropout_seed: int = 0,
+                 save_policy: int = 0, id_bytes: int = 8) -> _lib.EncoderCfg:
         return _lib.EncoderCfg(
             arch=_lib.ARCH_BERT if self.arch == "bert" else _lib.ARCH_DISTILBERT,
             num_layers=self.num_layers, hidden=self.hidden, heads=self.heads, intermediate=self.intermediate,
             vocab=self.vocab, max_pos=self.max_pos, type_vocab=self.type_vocab if self.arch == "bert" else 0,
-            precision=precision, ln_eps=self.ln_eps)
+            precision=precision, ln_eps=self.ln_eps, hidden_dropout=hidden_dropout, attn_dropout=attn_dropout,
+            dropout_seed=dropout_seed, save_policy=save_policy, id_bytes=id_bytes)
 
     @staticmethod
     def from_hf(cfg) -> "EncoderConfig":
@@ -75,6 +77,27 @@ def _count_optimizer_step(optimizer, args, kwargs):
 from torch.optim.optimizer import register_optimizer_step_post_hook  # noqa: E402
 
 register_optimizer_step_post_hook(_count_optimizer_step)
+
+
+# Dropout seeds: one 64-bit seed per tower call, derived from torch's seed (the drivers' `set_seed(args)` ->
+# torch.manual_seed), the rank, and a per-process call counter; masks are a counter-based function of the seed
+# (csrc/dropout.cuh), so backward — and the recomputation under gradient checkpointing — regenerates them.
+_DROPOUT_CALLS = [0]
+
+
+def _mix64(x: int) -> int:
+    x &= 0xFFFFFFFFFFFFFFFF
+    x = ((x ^ (x >> 30)) * 0xBF58476D1CE4E5B9) & 0xFFFFFFFFFFFFFFFF
+    x = ((x ^ (x >> 27)) * 0x94D049BB133111EB) & 0xFFFFFFFFFFFFFFFF
+    return x ^ (x >> 31)
+
+
+def next_dropout_seed() -> int:
+    _DROPOUT_CALLS[0] += 1
+    rank = 0
+    if torch.distributed.is_available() and torch.distributed.is_initialized():
+        rank = torch.distributed.get_rank()
+    return _mix64(torch.initial_seed() * 0x9E3779B97F4A7C15 + _DROPOUT_CALLS[0] * 0xD1B54A32D192ED03 + (rank << 48) + 1)
 
 
 def default_precision() -> int:
@@ -190,6 +213,13 @@ class B200EncoderBase(nn.Module):
         self._wbuf: Optional[torch.Tensor] = None
         self._wkey = None
         self._grad_slices = None
+        # training-time behaviour of the reference's config (SimANS/model/models.py:66-74): dropout probabilities (applied
+        # only while self.training) and --gradient_checkpointing (keep layer inputs only, recompute inside backward)
+        self.hidden_dropout_prob = 0.0
+        self.attention_probs_dropout_prob = 0.0
+        self.gradient_checkpointing = False
+        self.forced_dropout_seed: Optional[int] = None  # tests: fixed masks (compared with oracle/dropout_numpy.py)
+        self.last_dropout_seed: Optional[int] = None
 
     # ---- parameter plumbing ---------------------------------------------------------------------------
     def ordered_parameters(self) -> List[nn.Parameter]:
@@ -203,8 +233,13 @@ class B200EncoderBase(nn.Module):
             self._ordered[-2:] = [self._no_pooler_w, self._no_pooler_b]
         return out
 
-    def _c_cfg(self) -> _lib.EncoderCfg:
-        return self.enc_cfg.c_struct(self.precision)
+    def _c_cfg(self, dropout_seed: int = 0, id_bytes: int = 8, train: Optional[bool] = None) -> _lib.EncoderCfg:
+        train = self.training if train is None else train
+        ph = float(self.hidden_dropout_prob) if train else 0.0
+        pa = float(self.attention_probs_dropout_prob) if train else 0.0
+        return self.enc_cfg.c_struct(self.precision, hidden_dropout=ph, attn_dropout=pa, dropout_seed=dropout_seed,
+                                     save_policy=_lib.SAVE_LAYER_INPUTS if self.gradient_checkpointing else _lib.SAVE_ALL,
+                                     id_bytes=id_bytes)
 
     def _param_table(self, params) -> "C.Array":
         arr = (C.c_void_p * len(params))()
@@ -230,7 +265,7 @@ class B200EncoderBase(nn.Module):
         key = (self.precision, _OPTIMIZER_STEPS[0]) + tuple((p.data_ptr(), p._version) for p in params)
         if self._wbuf is None or key != self._wkey:
             lib = _lib.lib()
-            cfg = self._c_cfg()
+            cfg = self._c_cfg(train=False)
             nbytes = lib.simx_encoder_weight_bytes(C.byref(cfg))
             if self._wbuf is None or self._wbuf.numel() != nbytes or self._wbuf.device != params[0].device:
                 self._wbuf = torch.empty(nbytes, dtype=torch.uint8, device=params[0].device)
@@ -246,7 +281,7 @@ class B200EncoderBase(nn.Module):
     def grad_slices(self) -> List[Tuple[int, int]]:
         if self._grad_slices is None:
             lib = _lib.lib()
-            cfg = self._c_cfg()
+            cfg = self._c_cfg(train=False)
             n = lib.simx_encoder_num_params(C.byref(cfg))
             assert n == len(self._ordered), (n, len(self._ordered))
             self._grad_slices = [(lib.simx_encoder_grad_offset(C.byref(cfg), i),
@@ -254,6 +289,14 @@ class B200EncoderBase(nn.Module):
         return self._grad_slices
 
     # ---- compute ------------------------------------------------------------------------------------------
+    def param_groups(self) -> List[List[nn.Parameter]]:
+        """[embedding params, layer 0 params, ..., layer L-1 params, pooler params ([] without one)] in the canonical order:
+        the granularity at which backward hands gradients to autograd (and thereby to DDP's reducer)"""
+        base = 5 if self.enc_cfg.arch == "bert" else 4
+        L = self.enc_cfg.num_layers
+        o = self._ordered
+        return [o[:base]] + [o[base + 16 * l: base + 16 * (l + 1)] for l in range(L)] + [o[base + 16 * L:]]
+
     def encode(self, input_ids: torch.Tensor, attention_mask: Optional[torch.Tensor] = None,
                want_sequence: bool = False):
         """-> (cls_layers [B, L+1, H] fp32, sequence_output [B,S,H] fp32 or None).
@@ -261,28 +304,43 @@ class B200EncoderBase(nn.Module):
         if input_ids.dim() != 2:
             raise ValueError("input_ids must be [B, S]")
         params = self._ordered
-        cls, seq = _EncoderFn.apply(self, input_ids, attention_mask, bool(want_sequence), *params)
+        needs_grad = torch.is_grad_enabled() and any(p.requires_grad for p in params)
+        st = _TowerPass(self, input_ids, attention_mask, bool(want_sequence), needs_grad)
+        if not needs_grad:
+            return st.cls, (st.seq if want_sequence else None)
+        # autograd graph: embeddings -> layer 0 -> ... -> layer L-1 -> outputs, chained through a dummy token.  Each node's
+        # backward runs ONE slice of the tower's backward pass (simx_encoder_backward_layers) and returns that slice's
+        # parameter gradients, so DDP's bucket all-reduces start while the lower layers are still being computed.
+        groups = self.param_groups()
+        token = _EmbedNode.apply(st, *groups[0])
+        for l in range(self.enc_cfg.num_layers):
+            token = _LayerNode.apply(st, l, token, *groups[1 + l])
+        cls, seq = _TopNode.apply(st, token, *groups[-1])
         return cls, (seq if want_sequence else None)
 
 
-class _EncoderFn(torch.autograd.Function):
-    @staticmethod
-    def forward(ctx, module: B200EncoderBase, ids, mask, want_seq, *params):
+class _TowerPass:
+    """State of one forward/backward pass of one tower: runs the forward at construction, owns the saved activations, and
+    runs the backward slice by slice on behalf of the autograd nodes below."""
+
+    def __init__(self, module: B200EncoderBase, ids, mask, want_seq: bool, needs_grad: bool):
         lib = _lib.lib()
+        params = module._ordered
         module._check_params(params)
         dev = params[0].device
         if ids.device != dev:
             raise RuntimeError(f"input_ids on {ids.device}, parameters on {dev}")
-        with torch.cuda.device(dev):
+        ec = module.enc_cfg
+        with torch.no_grad(), torch.cuda.device(dev):
             _lib.require_device()
-            ids = ids.to(torch.int64).contiguous()
+            # int32 batches stay int32 (half the host->device bytes); anything else is the reference's int64
+            idt = torch.int32 if ids.dtype == torch.int32 else torch.int64
+            ids = ids.to(idt).contiguous()
             if mask is not None:
-                mask = mask.to(device=dev, dtype=torch.int64).contiguous()
+                mask = mask.to(device=dev, dtype=idt).contiguous()
                 if mask.shape != ids.shape:
                     raise ValueError("attention_mask must have the shape of input_ids")
             B, S = ids.shape
-            cfg = module._c_cfg()
-            ec = module.enc_cfg
             if S > min(ec.max_pos, 512):
                 raise ValueError(f"sequence length {S} exceeds min(max_position_embeddings={ec.max_pos}, 512)")
             pos_ids = None
@@ -291,74 +349,146 @@ class _EncoderFn(torch.autograd.Function):
                 if S + ec.pad_token_id >= ec.max_pos:
                     raise ValueError(f"sequence length {S} needs position {S + ec.pad_token_id} >= "
                                      f"max_position_embeddings={ec.max_pos}")
-                real = (ids != ec.pad_token_id).to(torch.int64)
-                pos_ids = (torch.cumsum(real, dim=1) * real + ec.pad_token_id).contiguous()
-            needs_grad = any(ctx.needs_input_grad[4:])  # grad mode is always off inside Function.forward
+                real = (ids != ec.pad_token_id).to(idt)
+                pos_ids = (torch.cumsum(real, dim=1) * real + ec.pad_token_id).to(idt).contiguous()
+            dropping = module.training and (module.hidden_dropout_prob > 0 or module.attention_probs_dropout_prob > 0)
+            seed = 0
+            if dropping:
+                seed = module.forced_dropout_seed if module.forced_dropout_seed is not None else next_dropout_seed()
+                module.last_dropout_seed = seed
+            cfg = module._c_cfg(dropout_seed=seed, id_bytes=4 if idt == torch.int32 else 8)
             wbuf = module._weights(params)
             table = module._param_table(params)
             stream = torch.cuda.current_stream(dev).cuda_stream
             cls = torch.empty(B, ec.num_layers + 1, ec.hidden, dtype=torch.float32, device=dev)
             seq = torch.empty(B, S, ec.hidden, dtype=torch.float32, device=dev) if want_seq else None
-            ws = torch.empty(lib.simx_encoder_workspace_bytes(C.byref(cfg), B, S), dtype=torch.uint8, device=dev)
-            saved = None
+            saved, ws = None, None
             if needs_grad:
                 saved = torch.empty(lib.simx_encoder_saved_bytes(C.byref(cfg), B, S), dtype=torch.uint8, device=dev)
+            if not needs_grad or module.gradient_checkpointing:
+                ws = torch.empty(lib.simx_encoder_workspace_bytes(C.byref(cfg), B, S), dtype=torch.uint8, device=dev)
             if pos_ids is None:
                 _lib.check(lib.simx_encoder_forward(C.byref(cfg), table, wbuf.data_ptr(), ids.data_ptr(), _lib.ptr(mask), B, S,
-                                                    _lib.ptr(saved), ws.data_ptr(), cls.data_ptr(), _lib.ptr(seq), stream),
+                                                    _lib.ptr(saved), _lib.ptr(ws), cls.data_ptr(), _lib.ptr(seq), stream),
                            "simx_encoder_forward")
             else:
                 _lib.check(lib.simx_encoder_forward_pos(C.byref(cfg), table, wbuf.data_ptr(), ids.data_ptr(), _lib.ptr(mask),
-                                                        pos_ids.data_ptr(), B, S, _lib.ptr(saved), ws.data_ptr(),
+                                                        pos_ids.data_ptr(), B, S, _lib.ptr(saved), _lib.ptr(ws),
                                                         cls.data_ptr(), _lib.ptr(seq), stream), "simx_encoder_forward_pos")
-        ctx.module = module
-        ctx.saved_act = saved
-        ctx.ids, ctx.mask, ctx.shape, ctx.pos_ids = ids, mask, (B, S), pos_ids
-        ctx.want_seq = want_seq
-        ctx.wbuf = wbuf
-        ctx.params = params
-        ctx.set_materialize_grads(False)
-        if seq is None:
-            seq = cls.new_empty(0)
-            ctx.mark_non_differentiable(seq)
-        return cls, seq
+        self.module, self.cfg, self.dev = module, cfg, dev
+        self.ids, self.mask, self.pos_ids, self.shape = ids, mask, pos_ids, (B, S)
+        self.cls, self.seq, self.want_seq = cls, seq, want_seq
+        self.saved, self.wbuf, self.params = saved, wbuf, params
+        self.ws = None      # backward workspace: holds the running cotangent between slices
+        self.flat = None    # flat fp32 gradient buffer of this pass
+        self.d_cls = self.d_seq = None
+        self.next_hi = ec.num_layers  # the slice that must run next is [.., next_hi)
+
+    def begin_backward(self, d_cls, d_seq) -> bool:
+        """called by the top node; False when no cotangent reaches the tower"""
+        if self.saved is None:
+            raise RuntimeError("encoder backward without saved activations (already freed by an earlier backward, or the "
+                               "forward ran under no_grad)")
+        if d_cls is None and (d_seq is None or not self.want_seq):
+            return False
+        lib = _lib.lib()
+        B, S = self.shape
+        with torch.cuda.device(self.dev):
+            self.d_cls = None if d_cls is None else d_cls.to(torch.float32).contiguous()
+            self.d_seq = d_seq.to(torch.float32).contiguous() if (d_seq is not None and self.want_seq) else None
+            self.ws = torch.empty(lib.simx_encoder_workspace_bytes(C.byref(self.cfg), B, S), dtype=torch.uint8,
+                                  device=self.dev)
+            self.flat = torch.empty(lib.simx_encoder_grad_numel(C.byref(self.cfg)), dtype=torch.float32, device=self.dev)
+        return True
+
+    def run_slice(self, lo: int, hi: int) -> None:
+        """backward through layers [lo, hi) (lo == -1: down to and including the embeddings)"""
+        if self.flat is None:
+            return
+        if hi != self.next_hi:
+            raise RuntimeError(f"encoder backward slices out of order: expected [.., {self.next_hi}), got [{lo}, {hi})")
+        lib = _lib.lib()
+        B, S = self.shape
+        m = self.module
+        with torch.cuda.device(self.dev):
+            stream = torch.cuda.current_stream(self.dev).cuda_stream
+            _lib.check(lib.simx_encoder_backward_layers(
+                C.byref(self.cfg), m._param_table(self.params), self.wbuf.data_ptr(), self.ids.data_ptr(), _lib.ptr(self.mask),
+                _lib.ptr(self.pos_ids), m.enc_cfg.pad_token_id if self.pos_ids is not None else 0, B, S,
+                self.saved.data_ptr(), self.ws.data_ptr(), _lib.ptr(self.d_cls), _lib.ptr(self.d_seq), self.flat.data_ptr(),
+                lo, hi, stream), "simx_encoder_backward_layers")
+        self.next_hi = lo
+        if lo < 0:  # pass complete: release everything but the gradient buffer (kept alive by the views handed out)
+            self.saved = self.ws = self.d_cls = self.d_seq = None
+
+    def grads_for(self, params, needs) -> tuple:
+        if self.flat is None:
+            return (None,) * len(params)
+        slices = self.module.grad_slices()
+        index = {id(p): i for i, p in enumerate(self.params)}
+        out = []
+        for p, need in zip(params, needs):
+            off, n = slices[index[id(p)]]
+            out.append(self.flat[off:off + n].view(p.shape) if need else None)
+        return tuple(out)
+
+
+class _EmbedNode(torch.autograd.Function):
+    """bottom of the chain: owns the embedding parameters; its backward finishes the pass"""
 
     @staticmethod
+    def forward(ctx, st: _TowerPass, *params):
+        ctx.st, ctx.params = st, params
+        return st.cls.new_zeros(1)
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, _token_grad):
+        st: _TowerPass = ctx.st
+        if st.flat is not None and st.next_hi > 0:  # layers whose nodes were pruned (nothing trainable between) still run
+            st.run_slice(0, st.next_hi)
+        st.run_slice(-1, 0)
+        return (None,) + st.grads_for(ctx.params, ctx.needs_input_grad[1:])
+
+
+class _LayerNode(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, st: _TowerPass, layer: int, token, *params):
+        ctx.st, ctx.layer, ctx.params = st, layer, params
+        return st.cls.new_zeros(1)
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, _token_grad):
+        st: _TowerPass = ctx.st
+        l = ctx.layer
+        if st.flat is not None:
+            st.run_slice(l, st.next_hi)  # normally [l, l+1); wider when the nodes above were pruned
+        token_grad = _token_grad.new_zeros(1) if ctx.needs_input_grad[2] else None
+        return (None, None, token_grad) + st.grads_for(ctx.params, ctx.needs_input_grad[3:])
+
+
+class _TopNode(torch.autograd.Function):
+    """hands out the tower's outputs; its backward receives the cotangents and opens the pass"""
+
+    @staticmethod
+    def forward(ctx, st: _TowerPass, token, *params):
+        ctx.st, ctx.params = st, params
+        ctx.set_materialize_grads(False)
+        seq = st.seq
+        if seq is None:
+            seq = st.cls.new_empty(0)
+            ctx.mark_non_differentiable(seq)
+        return st.cls, seq
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
     def backward(ctx, d_cls, d_seq):
-        module: B200EncoderBase = ctx.module
-        params = ctx.params
-        n_lead = 4
-        if ctx.saved_act is None:
-            raise RuntimeError("encoder backward without saved activations (forward ran under no_grad)")
-        if d_cls is None and (d_seq is None or not ctx.want_seq):
-            return (None,) * (n_lead + len(params))
-        lib = _lib.lib()
-        dev = params[0].device
-        B, S = ctx.shape
-        with torch.cuda.device(dev):
-            cfg = module._c_cfg()
-            stream = torch.cuda.current_stream(dev).cuda_stream
-            if d_cls is not None:
-                d_cls = d_cls.to(torch.float32).contiguous()
-            if d_seq is not None and ctx.want_seq:
-                d_seq = d_seq.to(torch.float32).contiguous()
-            else:
-                d_seq = None
-            ws = torch.empty(lib.simx_encoder_workspace_bytes(C.byref(cfg), B, S), dtype=torch.uint8, device=dev)
-            flat = torch.empty(lib.simx_encoder_grad_numel(C.byref(cfg)), dtype=torch.float32, device=dev)
-            if ctx.pos_ids is None:
-                _lib.check(lib.simx_encoder_backward(C.byref(cfg), module._param_table(params), ctx.wbuf.data_ptr(),
-                                                     ctx.ids.data_ptr(), _lib.ptr(ctx.mask), B, S, ctx.saved_act.data_ptr(),
-                                                     ws.data_ptr(), _lib.ptr(d_cls), _lib.ptr(d_seq), flat.data_ptr(), stream),
-                           "simx_encoder_backward")
-            else:
-                _lib.check(lib.simx_encoder_backward_pos(C.byref(cfg), module._param_table(params), ctx.wbuf.data_ptr(),
-                                                         ctx.ids.data_ptr(), _lib.ptr(ctx.mask), ctx.pos_ids.data_ptr(),
-                                                         module.enc_cfg.pad_token_id, B, S, ctx.saved_act.data_ptr(),
-                                                         ws.data_ptr(), _lib.ptr(d_cls), _lib.ptr(d_seq), flat.data_ptr(),
-                                                         stream), "simx_encoder_backward_pos")
-        ctx.saved_act = None
-        grads = []
-        for p, (off, n), need in zip(params, module.grad_slices(), ctx.needs_input_grad[n_lead:]):
-            grads.append(flat[off:off + n].view(p.shape) if need else None)
-        return (None,) * n_lead + tuple(grads)
+        st: _TowerPass = ctx.st
+        live = st.begin_backward(d_cls, d_seq)
+        token_grad = st.cls.new_zeros(1) if (live and ctx.needs_input_grad[1]) else None
+        # pooler parameters: dead math in the reference (multiplied by 0), dense zero gradients (SURVEY H7).  Their slice of
+        # the flat buffer is zeroed by the first backward slice, which has not run yet — hand out fresh zeros instead.
+        grads = tuple(torch.zeros_like(p) if (live and need) else None
+                      for p, need in zip(ctx.params, ctx.needs_input_grad[2:]))
+        return (None, token_grad) + grads

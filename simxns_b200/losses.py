@@ -162,7 +162,9 @@ class CrossBERTKDLoss(object):
         nq = q_vectors.shape[0]
         group = ctx_vectors.shape[0] // nq
         if relevance_logits is None:
-            loss, detail = fused_score_loss(q_vectors, ctx_vectors, ["nll_local"], group_size=group, gather=False)
+            # no teacher: the bare hard loss — weighted by CE_WEIGHT only on the LwF branch (models.py:768-774)
+            loss, detail = fused_score_loss(q_vectors, ctx_vectors, ["nll_local"], group_size=group, gather=False,
+                                            weights={"nll_local": args.CE_WEIGHT if LwF else 1.0})
         elif args.KD_type in self._SOFT:
             soft = self._SOFT[args.KD_type]
             alpha, beta = getattr(args, "DKD_alpha", None), getattr(args, "DKD_beta", None)
@@ -171,7 +173,8 @@ class CrossBERTKDLoss(object):
             loss, detail = fused_score_loss(q_vectors, ctx_vectors, ["nll_local", soft], teacher=relevance_logits,
                                             weights={"nll_local": args.CE_WEIGHT, soft: args.KD_WEIGHT},
                                             temperature=args.TEMPERATURE, group_size=group, gather=False,
-                                            dkd_alpha=alpha or 1.0, dkd_beta=beta or 1.0)
+                                            dkd_alpha=1.0 if alpha is None else alpha,
+                                            dkd_beta=1.0 if beta is None else beta)
         else:
             raise ValueError("no such type of KD loss,please check KD_type")
         if LwF:
@@ -331,8 +334,9 @@ class BiEncoderKDLoss(object):
             raise ValueError("DKD loss need refer DKD_alpha and DKD_beta in args")
         loss, detail = fused_pair_distill(q_vectors, ctx_vectors, teacher_q_vector.detach(), teacher_ctxs_vector.detach(),
                                           {"nll_a": args.CE_WEIGHT, key: args.KD_WEIGHT}, temperature=args.TEMPERATURE,
-                                          gather=False, pos_idx=positive_idx_per_question, dkd_alpha=alpha or 1.0,
-                                          dkd_beta=beta or 1.0)
+                                          gather=False, pos_idx=positive_idx_per_question,
+                                          dkd_alpha=1.0 if alpha is None else alpha,
+                                          dkd_beta=1.0 if beta is None else beta)
         correct_predictions_count = detail[6].round().to(torch.int64)
         if loss_scale:
             loss = loss * loss_scale

@@ -133,9 +133,12 @@ class HFBertEncoder(B200EncoderBase):
             self.version = int(transformers.__version__.split('.')[0])
         except ImportError:
             self.version = 4
-        p_drop = max(float(getattr(config, "hidden_dropout_prob", 0.0) or 0.0),
-                     float(getattr(config, "attention_probs_dropout_prob", 0.0) or 0.0))
-        self.dropout_requested = p_drop  # kernels run the dropout-free (parity / eval) configuration, SURVEY D9
+        # training-time configuration of the reference (SimANS/model/models.py:66-74): nn.Dropout(p) at the HF sites while
+        # the module is in train() mode, and --gradient_checkpointing.  Both run inside the kernels (csrc/dropout.cuh,
+        # SIMX_SAVE_LAYER_INPUTS); model.eval() — the teacher under no_grad, evaluation, the parity fixtures — disables dropout.
+        self.hidden_dropout_prob = float(getattr(config, "hidden_dropout_prob", 0.0) or 0.0)
+        self.attention_probs_dropout_prob = float(getattr(config, "attention_probs_dropout_prob", 0.0) or 0.0)
+        self.gradient_checkpointing = bool(getattr(config, "gradient_checkpointing", False))
 
     # -- reference constructor path -----------------------------------------------------------------------
     @classmethod
@@ -176,15 +179,23 @@ class HFBertEncoder(B200EncoderBase):
     def get_input_embeddings(self):
         return self.embeddings.word_embeddings
 
-    def gradient_checkpointing_enable(self, *a, **k):  # CAPSTONE/models/modules.py:54 calls this; accepted no-op
-        return None
+    def gradient_checkpointing_enable(self, *a, **k):
+        """HF PreTrainedModel API (CAPSTONE/models/modules.py:54): keep layer inputs only, recompute inside backward"""
+        self.gradient_checkpointing = True
 
-    def load_state_dict(self, state_dict, strict: bool = True, **kw):
-        # old HF versions persisted buffers (`embeddings.position_ids`, `token_type_ids`): ignore them as the
-        # reference's strict=False loads do (co_training_marco_train.py:355)
-        state_dict = {k: v for k, v in state_dict.items()
-                      if not k.endswith("embeddings.position_ids") and not k.endswith("embeddings.token_type_ids")}
-        return super().load_state_dict(state_dict, strict=strict, **kw)
+    def gradient_checkpointing_disable(self):
+        self.gradient_checkpointing = False
+
+    def _load_from_state_dict(self, state_dict, prefix, local_metadata, strict, missing_keys, unexpected_keys, error_msgs):
+        # Checkpoints written with older transformers persist two buffers (`embeddings.position_ids`,
+        # `embeddings.token_type_ids`) that this module does not have.  nn.Module.load_state_dict on a PARENT
+        # (BiBertEncoder, Reranker, RobertaDot — the way every reference driver loads, several with strict=True:
+        # wiki/co_training_wiki_train.py:364, PROD run_progressive_distill_*.py) recurses through this hook with the
+        # parent's prefix and never calls a child's load_state_dict, so the keys are dropped here.
+        for k in (prefix + "embeddings.position_ids", prefix + "embeddings.token_type_ids"):
+            state_dict.pop(k, None)
+        return super()._load_from_state_dict(state_dict, prefix, local_metadata, strict, missing_keys, unexpected_keys,
+                                             error_msgs)
 
     # -- reference forward ----------------------------------------------------------------------------------
     def forward(self, input_ids=None, attention_mask=None, token_type_ids=None, inputs_embeds=None,
@@ -216,12 +227,18 @@ class HFDistilBertEncoder(HFBertEncoder):
         if not hasattr(self.config, "hidden_size"):
             self.config.hidden_size = enc_cfg.hidden
         self.version = 4
-        self.dropout_requested = 0.0
+        # DistilBertModel reads `dropout` / `attention_dropout` (LEAD/modeling_distilbert.py:104, :143, :240); LEAD's
+        # init_encoder sets the BERT-named fields, which DistilBERT ignores (LEAD/models.py:45-47) — so the values in force
+        # are those of the checkpoint's config.json (0.1 / 0.1 for distilbert-base-uncased)
+        self.hidden_dropout_prob = float(getattr(config, "dropout", 0.0) or 0.0)
+        self.attention_probs_dropout_prob = float(getattr(config, "attention_dropout", 0.0) or 0.0)
+        self.gradient_checkpointing = bool(getattr(config, "gradient_checkpointing", False))
 
     @classmethod
     def init_encoder(cls, args, dropout: float = 0.1, pretrained_model_name=None):
         name = pretrained_model_name or getattr(args, "pretrained_model_name", None)
         cfg = _load_hf_config(name, "distilbert")
+        cfg.gradient_checkpointing = getattr(args, "gradient_checkpointing", False)
         model = cls(cfg)
         sd = _find_weights(name)
         if sd is None:
@@ -340,6 +357,9 @@ class HFRobertaEncoder(HFBertEncoder):
         super().__init__(enc_cfg, precision)
         if not isinstance(config, EncoderConfig):
             self.config = config
+            self.hidden_dropout_prob = float(getattr(config, "hidden_dropout_prob", 0.0) or 0.0)
+            self.attention_probs_dropout_prob = float(getattr(config, "attention_probs_dropout_prob", 0.0) or 0.0)
+            self.gradient_checkpointing = bool(getattr(config, "gradient_checkpointing", False))
 
     @classmethod
     def init_encoder(cls, args, dropout: float = 0.1, model_type=None):

@@ -88,8 +88,15 @@ def retriever_step(args, model, teacher_model, batch, optimizer, scheduler, step
         teacher_model.eval()
         with torch.no_grad():
             relevance_logits = teacher_model(input_ids=batch_teacher[0].long(), attention_mask=batch_teacher[1].long())
-    else:  # pre-computed teacher scores [B, 1+n] as the third element of batch['teacher'] (collate layout)
-        relevance_logits = batch['teacher'][2].to(dev)
+    else:
+        # pre-computed teacher scores [B, 1+n] under their own key.  (batch['teacher'][2] of the collate layout is
+        # tgt_tensor — the 0/1 positive labels, MARCO_until_new.py:255 — never scores: it is not read here.)
+        relevance_logits = batch.get('teacher_scores') if hasattr(batch, "get") else None
+        if relevance_logits is None:
+            raise ValueError("retriever_step(teacher_model=None) needs batch['teacher_scores'] [B, 1+n] (float logits)")
+        if not torch.is_floating_point(relevance_logits):
+            raise TypeError(f"batch['teacher_scores'] must be floating-point logits, got {relevance_logits.dtype}")
+        relevance_logits = relevance_logits.to(dev)
     distill_loss = simans_distill_loss(local_q_vector, local_ctx_vectors, relevance_logits,
                                        temperature_distill=args.temperature_distill, eps=1e-7,
                                        scale_simmila=getattr(args, "scale_simmila", False))

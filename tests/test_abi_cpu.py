@@ -31,7 +31,8 @@ def test_library_exports_every_declared_symbol():
 
 
 def test_struct_mirrors_have_header_layout():
-    assert C.sizeof(_lib.EncoderCfg) == 10 * 4
+    assert C.sizeof(_lib.EncoderCfg) == 10 * 4 + 2 * 4 + 8 + 2 * 4  # + dropout probabilities, seed, save_policy, id_bytes
+    assert _lib.EncoderCfg.dropout_seed.offset == 48 and _lib.EncoderCfg.id_bytes.offset == 60
     assert C.sizeof(_lib.LossCfg) == 9 * 4 + 14 * 4
     assert C.sizeof(_lib.PairCfg) == 7 * 4 + 11 * 4
     assert C.sizeof(_lib.OptTensor) == 56

@@ -1,0 +1,195 @@
+"""B200 (`-m gpu`): the training-time behaviour of the reference's towers that round 1 left out — nn.Dropout at the HF
+sites (SimANS/model/models.py:66-72; LEAD/modeling_bert.py:239, :358, :386, :464; DistilBERT
+LEAD/modeling_distilbert.py:133, :221, :254), --gradient_checkpointing (SimANS/model/models.py:73-74), and int32 token
+batches — against the numpy oracle with the SAME masks (oracle/dropout_numpy.py restates csrc/dropout.cuh).
+
+With the seed fixed the masked forward / backward is deterministic, so the fp32-class mode is held to the north_star
+tolerances (embeddings / gradients 1e-3; asserted tighter) exactly like the dropout-free parity tests: this proves that the
+mask applied in forward is the mask re-generated in backward at every site, in every kernel variant (tcgen05 single-tile,
+two-key-tile, blocked backward, mma.sync forward, FFMA reference kernels, GEMM epilogue, LayerNorm backward)."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import bert_numpy as bn
+from oracle import dropout_numpy as dn
+from simxns_b200 import _lib
+from test_gpu_parity import X3, BF16, assert_grads, build, cu, max_rel
+
+pytestmark = pytest.mark.gpu
+
+SEED = 0x5EED0123456789AB
+
+
+@pytest.fixture(scope="module", autouse=True)
+def _device():
+    assert torch.cuda.is_available(), "gpu tests need a CUDA device"
+    torch.cuda.set_device(0)
+    _lib.require_device()
+
+
+def _with_dropout(model, ph, pa, seed=SEED):
+    model.hidden_dropout_prob, model.attention_probs_dropout_prob, model.forced_dropout_seed = ph, pa, seed
+    return model.train()
+
+
+@pytest.mark.parametrize("arch", ["bert", "distilbert"])
+@pytest.mark.parametrize("B,S", [(3, 40), (2, 128), (2, 160), (1, 300)])
+def test_dropout_forward_backward_vs_oracle_same_masks(arch, B, S):
+    cfg = bn.bert_config(num_layers=2, hidden=128, heads=2, intermediate=192, vocab=300, max_pos=512, arch=arch)
+    params = bn.synth_params(cfg, seed=7 + S)
+    ids, mask = bn.synth_tokens(B, S, cfg["vocab"], seed=S, ragged=True, min_len=3)
+    dr = dict(p_hidden=0.1, p_attn=0.15, seed=SEED)
+    ora = bn.EncoderOracle(cfg, params)
+    out = ora.forward(ids, mask, dropout=dr)
+    plain = bn.EncoderOracle(cfg, params).forward(ids, mask)
+    assert max_rel(out["cls"], plain["cls"]) > 1e-2  # the masks do something
+    rng = np.random.RandomState(S)
+    d_cls = rng.standard_normal(out["cls"].shape)
+    ref = ora.backward(d_cls=d_cls)
+    for precision, tol_h, tol_g in ((X3, 2e-5, 2e-4), (BF16, 6e-2, 1.2e-1)):
+        model = _with_dropout(build(cfg, params, precision), dr["p_hidden"], dr["p_attn"])
+        cls, _ = model.encode(cu(ids), cu(mask))
+        assert model.last_dropout_seed == SEED
+        assert max_rel(cls.detach().cpu().numpy(), out["cls"]) < tol_h, (precision, "forward")
+        (cls * cu(d_cls, torch.float32)).sum().backward()
+        assert_grads(model, ref, tol_g)
+
+
+def test_sites_are_independent_and_eval_disables_dropout():
+    cfg = bn.bert_config(num_layers=2, hidden=128, heads=2, intermediate=256, vocab=300, max_pos=64)
+    params = bn.synth_params(cfg, seed=3)
+    ids, mask = bn.synth_tokens(4, 32, cfg["vocab"], seed=9, ragged=True)
+    base = bn.EncoderOracle(cfg, params).forward(ids, mask)["cls"]
+    model = build(cfg, params, X3)
+    # each probability alone, against the oracle with only that site active
+    for ph, pa in ((0.2, 0.0), (0.0, 0.3)):
+        want = bn.EncoderOracle(cfg, params).forward(ids, mask, dropout=dict(p_hidden=ph, p_attn=pa, seed=SEED))["cls"]
+        _with_dropout(model, ph, pa)
+        with torch.no_grad():  # model.train() + no_grad still drops, as nn.Dropout does
+            got, _ = model.encode(cu(ids), cu(mask))
+        assert max_rel(got.cpu().numpy(), want) < 2e-5, (ph, pa)
+        assert max_rel(want, base) > 1e-2
+    # eval(): the probabilities stay configured, nothing is dropped
+    model.eval()
+    got, _ = model.encode(cu(ids), cu(mask))
+    assert max_rel(got.detach().cpu().numpy(), base) < 2e-5
+    # train() without a forced seed: fresh masks per call, same statistics
+    model.train()
+    model.forced_dropout_seed = None
+    with torch.no_grad():
+        a, _ = model.encode(cu(ids), cu(mask))
+        s1 = model.last_dropout_seed
+        b, _ = model.encode(cu(ids), cu(mask))
+    assert s1 != model.last_dropout_seed and not torch.equal(a, b)
+
+
+def test_dropout_mask_statistics_on_device():
+    """keep rate and scaling measured THROUGH the kernels, with torch-drawn seeds: row 0 of the [CLS] stack is the
+    embedding output LN(z0) o mask, so the mask is visible directly — 90 % of the elements survive, survivors are scaled by
+    1 / keep, and the average over many masks returns the eval value"""
+    cfg = bn.bert_config(num_layers=1, hidden=256, heads=4, intermediate=256, vocab=500, max_pos=64)
+    params = bn.synth_params(cfg, seed=11)
+    ids, mask = bn.synth_tokens(8, 16, cfg["vocab"], seed=2)
+    model = build(cfg, params, X3)
+    model.hidden_dropout_prob, model.attention_probs_dropout_prob = 0.1, 0.1
+    model.eval()
+    with torch.no_grad():
+        ref, _ = model.encode(cu(ids), cu(mask))
+    model.train()
+    acc = torch.zeros_like(ref)
+    n = 64
+    with torch.no_grad():
+        for _ in range(n):
+            out, _ = model.encode(cu(ids), cu(mask))
+            acc += out
+    mean = acc / n
+    # the embedding row (index 0 of the [CLS] stack) is LN(z0) o mask: its mask-average is exactly the eval value
+    e = (mean[:, 0] - ref[:, 0]).abs().max().item() / ref[:, 0].abs().max().item()
+    assert e < 0.25, e  # per-element std of the mean = sqrt(p/(1-p)/n) = 0.042 of the value
+    kept = (out[:, 0] != 0).float().mean().item()
+    assert abs(kept - 0.9) < 0.03, kept
+    scale = (out[:, 0][out[:, 0] != 0] / ref[:, 0][out[:, 0] != 0]).median().item()
+    assert abs(scale - dn.keep_scale(0.1)) < 1e-3, scale
+
+
+@pytest.mark.parametrize("drop", [False, True])
+def test_gradient_checkpointing_matches_full_saving(drop):
+    """--gradient_checkpointing keeps the layer inputs only and recomputes each layer inside backward (with the same
+    dropout masks): same outputs bit for bit, same gradients up to the order of the split-K atomics"""
+    cfg = bn.bert_config(num_layers=3, hidden=128, heads=2, intermediate=256, vocab=300, max_pos=256)
+    params = bn.synth_params(cfg, seed=21)
+    ids, mask = bn.synth_tokens(6, 130, cfg["vocab"], seed=4, ragged=True)
+    d = torch.randn(6, 4, 128, device="cuda", generator=torch.Generator(device="cuda").manual_seed(1))
+    for precision, tol in ((X3, 1e-5), (BF16, 2e-2)):
+        outs, grads, saved_bytes = [], [], []
+        for ck in (False, True):
+            model = build(cfg, params, precision)
+            if drop:
+                _with_dropout(model, 0.1, 0.1)
+            if ck:
+                model.gradient_checkpointing_enable()
+            cls, _ = model.encode(cu(ids), cu(mask))
+            (cls * d).sum().backward()
+            outs.append(cls.detach().clone())
+            grads.append({n: p.grad.clone() for n, p in model.named_parameters()})
+            c = model._c_cfg()
+            saved_bytes.append(_lib.lib().simx_encoder_saved_bytes(__import__("ctypes").byref(c), 6, 130))
+        assert torch.equal(outs[0], outs[1])
+        assert saved_bytes[1] < 0.25 * saved_bytes[0]
+        gmax = max(g.abs().max().item() for g in grads[0].values())
+        for n in grads[0]:
+            e = (grads[0][n] - grads[1][n]).abs().max().item() / max(grads[0][n].abs().max().item(), 1e-3 * gmax)
+            assert e < tol, (n, e)
+
+
+def test_int32_token_batches_are_bit_identical_to_int64():
+    cfg = bn.bert_config(num_layers=2, hidden=128, heads=2, intermediate=256, vocab=300, max_pos=256)
+    params = bn.synth_params(cfg, seed=8)
+    d = torch.randn(5, 3, 128, device="cuda", generator=torch.Generator(device="cuda").manual_seed(2))
+    for S in (48, 150):
+        ids, mask = bn.synth_tokens(5, S, cfg["vocab"], seed=S, ragged=True)
+        res = []
+        for dt in (torch.int64, torch.int32):
+            model = _with_dropout(build(cfg, params, BF16), 0.1, 0.1)
+            cls, seq = model.encode(cu(ids).to(dt), cu(mask).to(dt), want_sequence=True)
+            (cls * d).sum().backward()
+            res.append((cls.detach().clone(), seq.detach().clone(), model.embeddings.word_embeddings.weight.grad.clone(),
+                        model.encoder.layer[0].attention.self.query.bias.grad.clone()))
+        assert torch.equal(res[0][0], res[1][0]) and torch.equal(res[0][1], res[1][1])
+        assert torch.allclose(res[0][2], res[1][2], rtol=1e-5, atol=1e-7)  # scatter atomics: order only
+        assert torch.allclose(res[0][3], res[1][3], rtol=1e-4, atol=1e-6)
+
+
+def test_partial_freezing_through_the_layer_chain():
+    """backward is cut into per-layer autograd nodes (gradients reach DDP layer by layer); freezing the embeddings and the
+    lower layer must leave the upper layer's gradients unchanged and the frozen ones absent"""
+    cfg = bn.bert_config(num_layers=2, hidden=128, heads=2, intermediate=256, vocab=300, max_pos=64)
+    params = bn.synth_params(cfg, seed=13)
+    ids, mask = bn.synth_tokens(4, 20, cfg["vocab"], seed=3, ragged=True)
+    d = torch.randn(4, 3, 128, device="cuda", generator=torch.Generator(device="cuda").manual_seed(3))
+    full = build(cfg, params, X3)
+    cls, _ = full.encode(cu(ids), cu(mask))
+    (cls * d).sum().backward()
+    part = build(cfg, params, X3)
+    for n, p in part.named_parameters():
+        if n.startswith("embeddings.") or n.startswith("encoder.layer.0."):
+            p.requires_grad_(False)
+    cls2, _ = part.encode(cu(ids), cu(mask))
+    assert torch.equal(cls.detach(), cls2.detach())
+    (cls2 * d).sum().backward()
+    for (n, p), (_, q) in zip(full.named_parameters(), part.named_parameters()):
+        if q.requires_grad:
+            assert q.grad is not None and torch.allclose(p.grad, q.grad, rtol=1e-4, atol=1e-7), n
+        else:
+            assert q.grad is None, n
+    # only the lower half trainable: the chain still runs through the frozen upper layer
+    low = build(cfg, params, X3)
+    for n, p in low.named_parameters():
+        if n.startswith("encoder.layer.1.") or n.startswith("pooler."):
+            p.requires_grad_(False)
+    cls3, _ = low.encode(cu(ids), cu(mask))
+    (cls3 * d).sum().backward()
+    for (n, p), (_, q) in zip(full.named_parameters(), low.named_parameters()):
+        if q.requires_grad:
+            assert q.grad is not None and torch.allclose(p.grad, q.grad, rtol=1e-4, atol=1e-7), n

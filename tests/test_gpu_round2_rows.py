@@ -1,0 +1,78 @@
+"""B200 (`-m gpu`): the holes VERDICT r01 listed — MASTER's `normal + 0.2 * InfoNCE` as the exact term pair
+(MASTER/finetune/MS/co_training_model.py:249-269: CE-to-teacher on the local block + 0.2 x in-batch NLL), and LEAD's
+Reranker with per-layer relevance logits (LEAD/models.py:249-267), forward and backward against the oracle."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import bert_numpy as bn
+from oracle import losses_numpy as ln
+from simxns_b200 import _lib, lead_models
+from simxns_b200.encoder import EncoderConfig
+from simxns_b200.losses import fused_score_loss
+from test_gpu_parity import X3, assert_grads, cu, max_rel
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module", autouse=True)
+def _device():
+    assert torch.cuda.is_available(), "gpu tests need a CUDA device"
+    torch.cuda.set_device(0)
+    _lib.require_device()
+
+
+def test_master_ce_local_plus_02_nll_global_pair():
+    rng = np.random.RandomState(0)
+    nq, group, H = 24, 16, 768
+    Q = rng.standard_normal((nq, H)).astype(np.float32) * 0.3
+    Cm = rng.standard_normal((nq * group, H)).astype(np.float32) * 0.3
+    teacher = (3 * rng.standard_normal((nq, group))).astype(np.float32)
+    w = dict(ce_local=1.0, nll_global=0.2)
+    ref, dQ, dC = ln.score_loss(Q, Cm, terms=["ce_local", "nll_global"], group=group, pos_idx=np.arange(nq) * group,
+                                teacher=teacher, w=w, temperature=1.0)
+    q, c = cu(Q).requires_grad_(True), cu(Cm).requires_grad_(True)
+    loss, detail = fused_score_loss(q, c, ["ce_local", "nll_global"], teacher=cu(teacher), weights=w, group_size=group,
+                                    gather=False)
+    assert abs(loss.item() - ref["total"]) < 1e-4
+    assert abs(detail[3].item() - ref["ce_local"]) < 1e-4 and abs(detail[1].item() - ref["nll_global"]) < 1e-4
+    loss.backward()
+    assert np.abs(q.grad.cpu().numpy() - dQ).max() < 1e-5 and np.abs(c.grad.cpu().numpy() - dC).max() < 1e-5
+
+
+def test_lead_reranker_per_layer_logits_forward_backward():
+    cfg = bn.bert_config(num_layers=3, hidden=128, heads=2, intermediate=256, vocab=300, max_pos=64)
+    params = bn.synth_params(cfg, seed=17)
+    N, M, S = 3, 4, 40
+    ids, mask = bn.synth_tokens(N * M, S, cfg["vocab"], seed=5, ragged=True, min_len=6)
+    enc = lead_models.HFBertEncoder(EncoderConfig(num_layers=3, hidden=128, heads=2, intermediate=256, vocab=300, max_pos=64),
+                                    precision=X3)
+    enc.load_state_dict({k: torch.from_numpy(v) for k, v in params.items()})
+    model = lead_models.Reranker(enc, 128).cuda()
+    rng = np.random.RandomState(3)
+    hw = (0.05 * rng.standard_normal((1, 128))).astype(np.float32)
+    hb = np.asarray([0.01], np.float32)
+    with torch.no_grad():
+        model.qa_classifier.weight.copy_(cu(hw))
+        model.qa_classifier.bias.copy_(cu(hb))
+    logits, attn, layer_logits = model(cu(ids).view(N, M, S), cu(mask).view(N, M, S))
+    assert attn is None and tuple(logits.shape) == (N, M) and tuple(layer_logits.shape) == (3, N, M)
+
+    ora = bn.EncoderOracle(cfg, params)
+    out = ora.forward(ids, mask)
+    cls = out["cls"]                                    # [NM, L+1, H]
+    want_layers = (cls[:, 1:] @ hw.T.astype(np.float64) + hb).transpose(1, 0, 2).reshape(3, N, M)
+    assert max_rel(layer_logits.detach().cpu().numpy(), want_layers) < 2e-5
+    assert max_rel(logits.detach().cpu().numpy(), want_layers[-1]) < 2e-5
+    assert torch.equal(logits, layer_logits[-1])
+
+    # a loss that reads every layer's logits (what LEAD's CE-teacher distillation does): cotangents on every layer's [CLS]
+    cw = rng.standard_normal((3, N, M))
+    (layer_logits * cu(cw, torch.float32)).sum().backward()
+    d_logit = cw.reshape(3, N * M).T                    # [NM, L]
+    d_cls = np.zeros_like(cls)
+    d_cls[:, 1:] = d_logit[:, :, None] * hw.astype(np.float64)[None]
+    grads = {"encoder." + k: v for k, v in ora.backward(d_cls=d_cls).items()}
+    grads["qa_classifier.weight"] = np.einsum("nl,nlh->h", d_logit, cls[:, 1:])[None]
+    grads["qa_classifier.bias"] = d_logit.sum().reshape(1)
+    assert_grads(model, grads, 2e-4)

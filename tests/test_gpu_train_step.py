@@ -42,7 +42,9 @@ def make_batches(n, nq=3, group=4):
         t = lambda a: torch.from_numpy(a)
         scores = torch.from_numpy((2 * np.random.RandomState(i).standard_normal((nq, group))).astype(np.float32))
         out.append(dict(student=[t(q_ids), t(q_mask), t(p_ids), t(p_mask)],
-                        teacher=[t(ce_ids).view(nq, group, 32), t(ce_mask).view(nq, group, 32), scores]))
+                        teacher=[t(ce_ids).view(nq, group, 32), t(ce_mask).view(nq, group, 32),
+                                 torch.zeros(nq, group, dtype=torch.long)],  # [2] = tgt_tensor of the collate layout
+                        teacher_scores=scores))
     return out
 
 
@@ -99,7 +101,7 @@ def test_retriever_steps_match_reference_loop_with_oracle_optimizer():
         q, c = ref(*[t.cuda() for t in batch["student"]])
         sim = torch.einsum("bh,bdh->bd", q, c.reshape(q.size(0), c.size(0) // q.size(0), -1))
         p_s = F.softmax(sim, dim=1)
-        p_t = F.softmax(batch["teacher"][2].cuda() / ARGS.temperature_distill, dim=1)
+        p_t = F.softmax(batch["teacher_scores"].cuda() / ARGS.temperature_distill, dim=1)
         distill = torch.nn.KLDivLoss(reduction="batchmean")((p_s + 1e-7).log(), p_t)
         (distill / ARGS.gradient_accumulation_steps).backward()
         assert abs(out["distill_loss"].item() - distill.item()) < 1e-4

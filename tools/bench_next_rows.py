@@ -203,7 +203,7 @@ def bench_train_full(args):
     q = torch.randint(1000, ec.vocab, (nq, 32), device="cuda")
     p = torch.randint(1000, ec.vocab, (nq * group, 128), device="cuda")
     batch = dict(student=[q, torch.ones_like(q), p, torch.ones_like(p)],
-                 teacher=[None, None, 3 * torch.randn(nq, group, device="cuda")])
+                 teacher=[None, None, None], teacher_scores=3 * torch.randn(nq, group, device="cuda"))
     state = dict(step=0)
 
     def step():

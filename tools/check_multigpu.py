@@ -69,12 +69,22 @@ def main():
         q, c = ddp(*[t(a) for a in batches[rank]])
         loss, _ = fused_score_loss(q, c, ["nll_global"], group_size=group, gather=True)
         loss.backward()
-        if step == 0:  # single-process loss on the concatenated batch, same initial weights
+        if step == 0:  # single-process loss AND gradients on the concatenated batch, same initial weights
             ref = make()
             cat = [np.concatenate([b[i] for b in batches]) for i in range(4)]
             qr, cr = ref(*[t(a) for a in cat])
             lr_, _ = fused_score_loss(qr, cr, ["nll_global"], group_size=group, gather=False)
             assert abs(lr_.item() - loss.item()) < 1e-4, (lr_.item(), loss.item())
+            lr_.backward()
+            # every rank differentiates the same global loss w.r.t. its own rows only, DDP averages: world * ddp grad == grad
+            worst = 0.0
+            gmax = max(p.grad.abs().max().item() for p in ref.parameters())
+            for (n, p), (_, q) in zip(ref.named_parameters(), model.named_parameters()):
+                e = (world * q.grad - p.grad).abs().max().item() / max(p.grad.abs().max().item(), 1e-3 * gmax)
+                worst = max(worst, e)
+            assert worst < 1e-3, f"DDP gradient differs from the single-process gradient by {worst:.2e}"
+            if rank == 0:
+                print(f"world x DDP-averaged gradient == single-process gradient of the global loss: worst {worst:.1e}: OK")
         opt.step(max_grad_norm=1.0)
         ddp.zero_grad()
         losses.append(loss.item())
@@ -84,6 +94,36 @@ def main():
     assert all(torch.equal(gathered[0], x) for x in gathered), "ranks diverged after DDP + fused AdamW"
     if rank == 0:
         print(f"DDP + all-gathered InfoNCE + fused clip/AdamW on {world} ranks: parameters identical, losses {losses}: OK")
+
+    # ---- 3. the training configuration: dropout + gradient checkpointing + bf16 under DDP (ranks must stay in lock-step) ----
+    torch.manual_seed(1)
+    m2 = BiBertEncoder(None, question_model=HFBertEncoder(ec, precision=_lib.PREC_BF16),
+                       ctx_model=HFBertEncoder(ec, precision=_lib.PREC_BF16)).to(dev)
+    for tower in (m2.question_model, m2.ctx_model):
+        tower.hidden_dropout_prob = tower.attention_probs_dropout_prob = 0.1
+        tower.gradient_checkpointing_enable()
+    ddp2 = torch.nn.parallel.DistributedDataParallel(m2, device_ids=[local], gradient_as_bucket_view=True)
+    opt2 = AdamW(m2.parameters(), lr=1e-3, eps=1e-8, weight_decay=0.01)
+    seeds = []
+    for step in range(2):
+        q_ids, q_mask = bn.synth_tokens(nq, 12, ec.vocab, seed=500 + 10 * step + rank, ragged=True)
+        p_ids, p_mask = bn.synth_tokens(nq * group, 24, ec.vocab, seed=600 + 10 * step + rank, ragged=True, min_len=6)
+        q, c = ddp2(t(q_ids), t(q_mask), t(p_ids), t(p_mask))
+        seeds.append(m2.ctx_model.last_dropout_seed)
+        loss, _ = fused_score_loss(q, c, ["nll_global"], group_size=group, gather=True)
+        loss.backward()
+        opt2.step(max_grad_norm=1.0)
+        ddp2.zero_grad()
+    flat = torch.cat([p.detach().reshape(-1) for p in m2.parameters()])
+    gathered = [torch.empty_like(flat) for _ in range(world)]
+    dist.all_gather(gathered, flat)
+    assert all(torch.equal(gathered[0], x) for x in gathered), "ranks diverged with dropout + checkpointing"
+    all_seeds = [None] * world
+    dist.all_gather_object(all_seeds, seeds)
+    assert len({tuple(s) for s in all_seeds}) == world, "ranks drew the same dropout seeds"
+    if rank == 0:
+        print(f"dropout 0.1 + gradient checkpointing + bf16 under DDP on {world} ranks: parameters identical, "
+              f"per-rank dropout seeds distinct: OK")
     dist.destroy_process_group()
 
 
