@@ -182,7 +182,7 @@ def run_gpu_bar(args, dev, batch):
         model = BiBertEncoderRef(bert_base_cfg(args.layers)).to(dev).train()
         b = tuple(t.to(dev) for t in batch)
         tgt = torch.arange(0, args.queries * args.group, args.group, device=dev)
-        for mode in ("bf16_autocast", "fp32"):
+        for mode in ("fp32", "bf16_autocast"):
             try:
                 def step():
                     with torch.autocast("cuda", dtype=torch.bfloat16, enabled=(mode == "bf16_autocast")):
@@ -207,7 +207,8 @@ def run_gpu_bar(args, dev, batch):
                                  peak_mem_gb=torch.cuda.max_memory_allocated() / 2 ** 30)
             except torch.cuda.OutOfMemoryError:
                 out[mode] = dict(error="OOM")
-                torch.cuda.empty_cache()
+            model.zero_grad(set_to_none=True)
+            torch.cuda.empty_cache()
         out["what"] = "reference model code (transformers BertModel, PyTorch eager) on the same GPU, dropout 0"
     except Exception as e:
         out["error"] = f"{type(e).__name__}: {e}"[:300]

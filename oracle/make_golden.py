@@ -141,6 +141,37 @@ def golden_biencoder_cfg1(simans):
     print("biencoder_cfg1 loss", loss.item(), "q", q.shape, "a", a.shape)
 
 
+def golden_biencoder_cfg1_bf16_autocast(simans):
+    """The same cfg1 step run by the reference's own classes under torch.autocast(bfloat16) — the reference's reduced-precision
+    behaviour (SimANS drivers: apex O1 / --fp16; the B200 configs of BASELINE.json name bf16).  Stored next to the fp32
+    fixture so the bf16 throughput mode of the kernels can be held to the deviation the reference itself shows."""
+    cfg = bert_config()
+    pq = synth_params(cfg, seed=0, perturb=False)
+    pc = synth_params(cfg, seed=1, perturb=False)
+    q_ids, q_mask = synth_tokens(2, 32, cfg["vocab"], seed=1234, ragged=True)
+    p_ids, p_mask = synth_tokens(4, 128, cfg["vocab"], seed=1235, ragged=True, min_len=16)
+    teacher = (3.0 * np.random.RandomState(99).standard_normal((2, 2))).astype(np.float32)
+    model = simans.BiBertEncoder.__new__(simans.BiBertEncoder)
+    torch.nn.Module.__init__(model)
+    model.question_model = simans.HFBertEncoder(hf_bert_config(cfg))
+    model.ctx_model = simans.HFBertEncoder(hf_bert_config(cfg))
+    load_params(model.question_model, pq)
+    load_params(model.ctx_model, pc)
+    model.eval()
+    with torch.autocast("cpu", dtype=torch.bfloat16):
+        q, a = model(torch.from_numpy(q_ids), torch.from_numpy(q_mask), torch.from_numpy(p_ids), torch.from_numpy(p_mask))
+    loss = simans_kl_loss(q.float(), a.float(), torch.from_numpy(teacher), temperature_distill=1.0)
+    loss.backward()
+    res = dict(q_embs=q.detach().float().numpy(), a_embs=a.detach().float().numpy(), loss=np.array([loss.item()]))
+    res.update(grads_digest({n: p.grad for n, p in model.named_parameters()}))
+    for n, p in model.named_parameters():
+        if n.endswith("encoder.layer.0.attention.self.query.bias") or n.endswith("encoder.layer.11.output.LayerNorm.weight") \
+                or n.endswith("embeddings.LayerNorm.bias") or n.endswith("encoder.layer.5.intermediate.dense.bias"):
+            res["grad/" + n] = p.grad.float().numpy().copy()
+    np.savez_compressed(GOLD / "biencoder_cfg1_bf16_autocast.npz", **res)
+    print("biencoder_cfg1_bf16_autocast loss", loss.item())
+
+
 def golden_reranker_tiny(simans):
     cfg = bert_config(num_layers=2, hidden=128, heads=2, intermediate=256, vocab=512, max_pos=64)
     params = synth_params(cfg, seed=21)
@@ -595,6 +626,10 @@ def main():
     if only == ["roberta"]:
         golden_roberta(import_from(REF / "SimANS", "model.models"))
         return
+    if only == ["cfg1_bf16"]:
+        torch.manual_seed(0)
+        golden_biencoder_cfg1_bf16_autocast(import_from(REF / "SimANS", "model.models"))
+        return
     if only == ["prod_kd"]:
         golden_losses_prod_kd(import_from(REF / "PROD" / "ProD_KD", "model.models"))
         return
@@ -613,6 +648,7 @@ def main():
         golden_lead_distill()
     simans = import_from(REF / "SimANS", "model.models")
     golden_biencoder_cfg1(simans)
+    golden_biencoder_cfg1_bf16_autocast(simans)
     golden_roberta(simans)
     golden_batch_layout()
     golden_lead_select_layer()

@@ -62,7 +62,13 @@ def test_ernie_large_width_teacher_step_vs_oracle(large_case, precision, tol_h, 
     loss = torch.nn.functional.cross_entropy(logits, torch.zeros(2, dtype=torch.long, device="cuda"))
     assert abs(loss.item() - loss_ref) < tol_l * max(1.0, abs(loss_ref))
     loss.backward()
-    assert_grads(model, grads, tol_g, zero_true=("qa_classifier.bias",))
+    # true-zero gradients: the head bias and the last LayerNorm's bias both receive sum_b (softmax - onehot)_b = 0; the last
+    # FFN-output bias is the same sum pushed through six different LayerNorm Jacobians — 1e-3 of the largest gradient, all
+    # cancellation — so the bf16 mode is judged on the global scale there (the fp32-class mode holds it to 2e-4 of itself)
+    zero_true = ("qa_classifier.bias", "encoder.encoder.layer.1.output.LayerNorm.bias")
+    if precision == BF16:
+        zero_true += ("encoder.encoder.layer.1.output.dense.bias",)
+    assert_grads(model, grads, tol_g, zero_true=zero_true)
 
 
 def test_ernie_large_width_with_checkpointing_and_dropout_runs_and_matches_itself():

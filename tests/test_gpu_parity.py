@@ -647,3 +647,52 @@ def test_bf16_mode_tracks_fp32_class_mode_at_bert_base_width():
         if e > worst[1]:
             worst = (n, e)
     assert worst[1] < 8e-2, worst
+
+
+def test_bf16_mode_deviates_no_more_than_the_reference_under_bf16_autocast(golden_dir):
+    """The throughput mode pinned to the reference's OWN reduced-precision behaviour: tests/golden/biencoder_cfg1_bf16_autocast.npz
+    holds the cfg1 step (BASELINE configs[0]/[1]: bert-base, 2 queries, 1+1 passages, SimANS KL loss) run by the reference's
+    classes under torch.autocast(bfloat16) (oracle/make_golden.py cfg1_bf16).  For every quantity — embeddings, loss,
+    per-tensor gradient norms of all 398 tensors, four complete gradient tensors — the bf16 kernels must sit no further from the
+    reference's fp32 result than 1.5 x the reference's own bf16 run does (plus a small absolute floor)."""
+    g32 = np.load(golden_dir / "biencoder_cfg1.npz")
+    g16 = np.load(golden_dir / "biencoder_cfg1_bf16_autocast.npz")
+    cfg = bn.bert_config()
+    pq, pc = bn.synth_params(cfg, seed=0, perturb=False), bn.synth_params(cfg, seed=1, perturb=False)
+    model = BiBertEncoder(None, question_model=build(cfg, pq, BF16), ctx_model=build(cfg, pc, BF16))
+    q, a = model(cu(g32["q_ids"]), cu(g32["q_mask"]), cu(g32["p_ids"]), cu(g32["p_mask"]))
+    loss = simans_distill_loss(q, a, cu(g32["teacher"]), temperature_distill=1.0)
+    loss.backward()
+    ours = dict(q_embs=q.detach().cpu().numpy(), a_embs=a.detach().cpu().numpy())
+    report = {}
+    for k in ("q_embs", "a_embs"):
+        d_ref = np.abs(g16[k] - g32[k]).max() / np.abs(g32[k]).max()
+        d_us = np.abs(ours[k] - g32[k]).max() / np.abs(g32[k]).max()
+        report[k] = (d_us, d_ref)
+        assert d_us <= 1.5 * d_ref + 1e-3, (k, d_us, d_ref)
+    d_ref, d_us = abs(float(g16["loss"][0] - g32["loss"][0])), abs(loss.item() - float(g32["loss"][0]))
+    report["loss"] = (d_us, d_ref)
+    assert d_us <= 1.5 * d_ref + 1e-3, ("loss", d_us, d_ref)
+    grads = {n: p.grad.detach().cpu().numpy() for n, p in model.named_parameters()}
+    # complete tensors
+    for k in [k for k in g32.files if k.startswith("grad/")]:
+        n = k[5:]
+        scale = np.abs(g32[k]).max()
+        d_ref, d_us = np.abs(g16[k] - g32[k]).max() / scale, np.abs(grads[n] - g32[k]).max() / scale
+        report[n] = (d_us, d_ref)
+        assert d_us <= 1.5 * d_ref + 5e-3, (n, d_us, d_ref)
+    # gradient norms of every tensor (true-zero gradients — key biases, pooler — excluded: both runs hold round-off only)
+    norms = [(k[6:], g32[k][0], g16[k][0]) for k in g32.files if k.startswith("gstat/")]
+    big = max(v for _, v, _ in norms)
+    rel_us, rel_ref = [], []
+    for n, v32, v16 in norms:
+        if v32 < 1e-6 * big:
+            continue
+        rel_ref.append(abs(v16 - v32) / v32)
+        rel_us.append(abs(float(np.linalg.norm(grads[n].astype(np.float64))) - v32) / v32)
+    rel_us, rel_ref = np.asarray(rel_us), np.asarray(rel_ref)
+    report["grad-norm median / max"] = ((float(np.median(rel_us)), float(rel_us.max())),
+                                        (float(np.median(rel_ref)), float(rel_ref.max())))
+    print("bf16 kernels vs reference-under-autocast, deviation from the fp32 reference (ours, reference's):", report)
+    assert np.median(rel_us) <= 1.5 * np.median(rel_ref) + 1e-3
+    assert rel_us.max() <= 1.5 * rel_ref.max() + 1e-2
