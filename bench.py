@@ -234,8 +234,8 @@ def run_b200(args):
     dev = torch.device("cuda", local)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
-            os.environ["NCCL_DEBUG"] = "WARN"  # keep NCCL's version banner off stdout: rank 0 prints ONE JSON line
+        if os.environ.get("NCCL_DEBUG", "").upper() in ("VERSION", "WARN"):
+            os.environ.pop("NCCL_DEBUG")  # both levels print NCCL's version banner on stdout: rank 0 prints ONE JSON line
         dist.init_process_group("nccl", device_id=dev)
     _lib.require_device()
 
@@ -244,12 +244,21 @@ def run_b200(args):
     model = BiBertEncoder(None, question_model=HFBertEncoder(ec, precision=_lib.PREC_BF16),
                           ctx_model=HFBertEncoder(ec, precision=_lib.PREC_BF16)).to(dev)
     step_model = model
-    if world > 1:
+    exchange = "none"
+    if world > 1 and os.environ.get("SIMX_BENCH_DDP", "0") == "1":
         # the reference's wrap (co_training_marco_train.py:109-114) plus bucket views: .grad aliases the all-reduce
         # buckets, so the 876 MB of gradients are not copied back out of them (2 GPUs: 165.3 -> 159.1 ms per step)
         step_model = torch.nn.parallel.DistributedDataParallel(
             model, device_ids=[local], find_unused_parameters=False, gradient_as_bucket_view=True,
             bucket_cap_mb=int(os.environ.get("SIMX_DDP_BUCKET_MB", "25")))
+        exchange = "torch DistributedDataParallel (25 MB buckets)"
+    elif world > 1:
+        # same contract as the DDP wrap, laid out for these towers: one in-place fp32 all-reduce (AVG) of each tower's flat
+        # gradient buffer, issued when that tower's backward completes (simxns_b200/gradsync.py)
+        from simxns_b200.gradsync import FlatGradSync
+
+        step_model = FlatGradSync(model, compress=os.environ.get("SIMX_GRAD_COMPRESS") or None)
+        exchange = "FlatGradSync: one fp32 NCCL all-reduce per tower over its flat gradient buffer"
 
     nq, group = args.queries, args.group
     gen = torch.Generator().manual_seed(1234 + rank)
@@ -406,7 +415,7 @@ def run_b200(args):
         fpp = flops_per_pair(args.layers, args.q_len, args.p_len, group)
         line = dict(metric=METRIC, value=value, unit=UNIT, n_gpus=world, steps=args.steps, warmup=args.warmup,
                     ms_per_step=ms_step, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="bf16",
-                    data="synthetic", config=workload_config(args, nq), e2e=e2e,
+                    data="synthetic", config=dict(workload_config(args, nq), gradient_exchange=exchange), e2e=e2e,
                     gpu_launches=(launches_per_step * args.steps if launches_per_step else None), clocks=clocks,
                     roofline=roofline, cpu_baseline=cpu_baseline, dropout=dropout, parity_mode=parity_mode,
                     gpu_bar=gpu_bar, model_tflops_per_gpu=value / world * fpp / 1e12, kernels=kernels)

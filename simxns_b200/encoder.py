@@ -220,6 +220,8 @@ class B200EncoderBase(nn.Module):
         self.gradient_checkpointing = False
         self.forced_dropout_seed: Optional[int] = None  # tests: fixed masks (compared with oracle/dropout_numpy.py)
         self.last_dropout_seed: Optional[int] = None
+        self.grad_delivery = os.environ.get("SIMX_GRAD_SLICES", "tower")  # "tower" | "layer" (see encode())
+        self._grad_sink = None  # gradsync.FlatGradSync: receives (tower, pass) instead of autograd receiving gradients
 
     # ---- parameter plumbing ---------------------------------------------------------------------------
     def ordered_parameters(self) -> List[nn.Parameter]:
@@ -308,14 +310,22 @@ class B200EncoderBase(nn.Module):
         st = _TowerPass(self, input_ids, attention_mask, bool(want_sequence), needs_grad)
         if not needs_grad:
             return st.cls, (st.seq if want_sequence else None)
-        # autograd graph: embeddings -> layer 0 -> ... -> layer L-1 -> outputs, chained through a dummy token.  Each node's
-        # backward runs ONE slice of the tower's backward pass (simx_encoder_backward_layers) and returns that slice's
-        # parameter gradients, so DDP's bucket all-reduces start while the lower layers are still being computed.
+        # autograd graph.  "tower" (default): one node per tower pass returns all gradients when the pass is complete.
+        # "layer": embeddings -> layer 0 -> ... -> layer L-1 -> outputs chained through a dummy token, each node running ONE
+        # slice of the backward pass (simx_encoder_backward_layers) and returning that slice's parameter gradients, so a
+        # reducer sees them layer by layer.  (Under stock DDP that is SLOWER here: NCCL's kernels cannot share an SM with
+        # the persistent one-CTA-per-SM GEMMs, so every bucket all-reduce launched mid-backward stalls a GEMM wave —
+        # 2 GPUs: 170.7 vs 159.1 ms per step.  gradsync.FlatGradSync reduces each tower's flat gradient buffer in one
+        # call after its pass instead.)
         groups = self.param_groups()
-        token = _EmbedNode.apply(st, *groups[0])
-        for l in range(self.enc_cfg.num_layers):
-            token = _LayerNode.apply(st, l, token, *groups[1 + l])
-        cls, seq = _TopNode.apply(st, token, *groups[-1])
+        if self.grad_delivery == "layer":
+            token = _EmbedNode.apply(st, *groups[0])
+            for l in range(self.enc_cfg.num_layers):
+                token = _LayerNode.apply(st, l, token, *groups[1 + l])
+            cls, seq = _TopNode.apply(st, token, *groups[-1])
+        else:
+            st.monolithic = True
+            cls, seq = _TopNode.apply(st, None, *params)
         return cls, (seq if want_sequence else None)
 
 
@@ -383,6 +393,8 @@ class _TowerPass:
         self.flat = None    # flat fp32 gradient buffer of this pass
         self.d_cls = self.d_seq = None
         self.next_hi = ec.num_layers  # the slice that must run next is [.., next_hi)
+        self.monolithic = False
+        self.sink = module._grad_sink if needs_grad else None
 
     def begin_backward(self, d_cls, d_seq) -> bool:
         """called by the top node; False when no cotangent reaches the tower"""
@@ -421,8 +433,13 @@ class _TowerPass:
         if lo < 0:  # pass complete: release everything but the gradient buffer (kept alive by the views handed out)
             self.saved = self.ws = self.d_cls = self.d_seq = None
 
+    def finish(self) -> None:
+        """the last slice of this pass has run: hand the flat buffer to the gradient sink, if one is attached"""
+        if self.sink is not None and self.flat is not None:
+            self.sink(self.module, self)
+
     def grads_for(self, params, needs) -> tuple:
-        if self.flat is None:
+        if self.flat is None or self.sink is not None:  # with a sink, parameters get their gradients from it, not from autograd
             return (None,) * len(params)
         slices = self.module.grad_slices()
         index = {id(p): i for i, p in enumerate(self.params)}
@@ -439,7 +456,7 @@ class _EmbedNode(torch.autograd.Function):
     @staticmethod
     def forward(ctx, st: _TowerPass, *params):
         ctx.st, ctx.params = st, params
-        return st.cls.new_zeros(1)
+        return st.cls.new_empty(0)
 
     @staticmethod
     @torch.autograd.function.once_differentiable
@@ -448,6 +465,7 @@ class _EmbedNode(torch.autograd.Function):
         if st.flat is not None and st.next_hi > 0:  # layers whose nodes were pruned (nothing trainable between) still run
             st.run_slice(0, st.next_hi)
         st.run_slice(-1, 0)
+        st.finish()
         return (None,) + st.grads_for(ctx.params, ctx.needs_input_grad[1:])
 
 
@@ -455,7 +473,7 @@ class _LayerNode(torch.autograd.Function):
     @staticmethod
     def forward(ctx, st: _TowerPass, layer: int, token, *params):
         ctx.st, ctx.layer, ctx.params = st, layer, params
-        return st.cls.new_zeros(1)
+        return st.cls.new_empty(0)
 
     @staticmethod
     @torch.autograd.function.once_differentiable
@@ -464,7 +482,9 @@ class _LayerNode(torch.autograd.Function):
         l = ctx.layer
         if st.flat is not None:
             st.run_slice(l, st.next_hi)  # normally [l, l+1); wider when the nodes above were pruned
-        token_grad = _token_grad.new_zeros(1) if ctx.needs_input_grad[2] else None
+        token_grad = st.cls.new_empty(0) if ctx.needs_input_grad[2] else None
+        if token_grad is None:  # nothing trainable below: this node is the bottom of the chain
+            st.finish()
         return (None, None, token_grad) + st.grads_for(ctx.params, ctx.needs_input_grad[3:])
 
 
@@ -486,9 +506,17 @@ class _TopNode(torch.autograd.Function):
     def backward(ctx, d_cls, d_seq):
         st: _TowerPass = ctx.st
         live = st.begin_backward(d_cls, d_seq)
-        token_grad = st.cls.new_zeros(1) if (live and ctx.needs_input_grad[1]) else None
+        if st.monolithic:  # the whole pass in this node: every parameter is an input here
+            if live:
+                st.run_slice(-1, st.next_hi)
+                st.finish()
+            return (None, None) + st.grads_for(ctx.params, ctx.needs_input_grad[2:])
+        token_grad = st.cls.new_empty(0) if (live and ctx.needs_input_grad[1]) else None
         # pooler parameters: dead math in the reference (multiplied by 0), dense zero gradients.  Their slice of
         # the flat buffer is zeroed by the first backward slice, which has not run yet — hand out fresh zeros instead.
-        grads = tuple(torch.zeros_like(p) if (live and need) else None
+        grads = tuple(torch.zeros_like(p) if (live and need and st.sink is None) else None
                       for p, need in zip(ctx.params, ctx.needs_input_grad[2:]))
+        if live and token_grad is None:  # nothing trainable below the outputs: only the (dead) pooler gets zeros
+            st.flat.zero_()
+            st.finish()
         return (None, token_grad) + grads

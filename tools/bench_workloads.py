@@ -59,15 +59,19 @@ class Runner:
         self.dev = torch.device("cuda", self.local)
         if self.world > 1:
             os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-            if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
-                os.environ["NCCL_DEBUG"] = "WARN"
+            if os.environ.get("NCCL_DEBUG", "").upper() in ("VERSION", "WARN"):
+                os.environ.pop("NCCL_DEBUG")
             dist.init_process_group("nccl", device_id=self.dev)
 
     def ddp(self, model):
         if self.world == 1:
             return model
-        return self.torch.nn.parallel.DistributedDataParallel(model, device_ids=[self.local], find_unused_parameters=False,
-                                                              gradient_as_bucket_view=True)
+        if os.environ.get("SIMX_BENCH_DDP", "0") == "1":
+            return self.torch.nn.parallel.DistributedDataParallel(model, device_ids=[self.local], find_unused_parameters=False,
+                                                                  gradient_as_bucket_view=True)
+        from simxns_b200.gradsync import FlatGradSync
+
+        return FlatGradSync(model)
 
     def barrier(self):
         if self.world > 1:

@@ -95,6 +95,43 @@ def main():
     if rank == 0:
         print(f"DDP + all-gathered InfoNCE + fused clip/AdamW on {world} ranks: parameters identical, losses {losses}: OK")
 
+    # ---- 2b. FlatGradSync (one all-reduce per tower over its flat gradient buffer) == DDP, incl. a shared tower used twice
+    #          per step, a head outside the towers, and gradient accumulation over two micro-steps ----
+    from simxns_b200.gradsync import FlatGradSync
+    from simxns_b200.models import Reranker
+
+    class Both(torch.nn.Module):
+        def __init__(self):
+            super().__init__()
+            torch.manual_seed(3)
+            self.bi = BiBertEncoder(None, question_model=HFBertEncoder(ec, precision=_lib.PREC_BF16X3))  # share_weight
+            self.rr = Reranker(HFBertEncoder(ec, precision=_lib.PREC_BF16X3), ec.hidden)
+
+        def forward(self, q, qm, p, pm):
+            qe, ce = self.bi(q, qm, p, pm)
+            return qe, ce, self.rr(p.view(nq, group, -1), pm.view(nq, group, -1))
+
+    def run(wrapper):
+        m = Both().to(dev)
+        w = wrapper(m)
+        for micro in range(2):
+            q_ids, q_mask = bn.synth_tokens(nq, 12, ec.vocab, seed=700 + 10 * micro + rank, ragged=True)
+            p_ids, p_mask = bn.synth_tokens(nq * group, 24, ec.vocab, seed=800 + 10 * micro + rank, ragged=True, min_len=6)
+            qe, ce, logits = w(t(q_ids), t(q_mask), t(p_ids), t(p_mask))
+            loss, _ = fused_score_loss(qe, ce, ["nll_global"], group_size=group, gather=True)
+            loss = loss + torch.nn.functional.cross_entropy(logits, torch.zeros(nq, dtype=torch.long, device=dev))
+            loss.backward()
+        torch.cuda.synchronize()
+        return {n: p.grad.clone() for n, p in m.named_parameters()}
+
+    g_ddp = run(lambda m: torch.nn.parallel.DistributedDataParallel(m, device_ids=[local]))
+    g_flat = run(lambda m: FlatGradSync(m))
+    gmax = max(v.abs().max().item() for v in g_ddp.values())
+    worst = max((g_flat[n] - g_ddp[n]).abs().max().item() / max(g_ddp[n].abs().max().item(), 1e-3 * gmax) for n in g_ddp)
+    assert worst < 1e-4, f"FlatGradSync gradients differ from DDP's by {worst:.2e}"
+    if rank == 0:
+        print(f"FlatGradSync == DistributedDataParallel (shared tower, reranker head, 2 accumulated micro-steps): worst {worst:.1e}: OK")
+
     # ---- 3. the training configuration: dropout + gradient checkpointing + bf16 under DDP (ranks must stay in lock-step) ----
     torch.manual_seed(1)
     m2 = BiBertEncoder(None, question_model=HFBertEncoder(ec, precision=_lib.PREC_BF16),
@@ -102,7 +139,7 @@ def main():
     for tower in (m2.question_model, m2.ctx_model):
         tower.hidden_dropout_prob = tower.attention_probs_dropout_prob = 0.1
         tower.gradient_checkpointing_enable()
-    ddp2 = torch.nn.parallel.DistributedDataParallel(m2, device_ids=[local], gradient_as_bucket_view=True)
+    ddp2 = FlatGradSync(m2)
     opt2 = AdamW(m2.parameters(), lr=1e-3, eps=1e-8, weight_decay=0.01)
     seeds = []
     for step in range(2):
@@ -122,7 +159,7 @@ def main():
     dist.all_gather_object(all_seeds, seeds)
     assert len({tuple(s) for s in all_seeds}) == world, "ranks drew the same dropout seeds"
     if rank == 0:
-        print(f"dropout 0.1 + gradient checkpointing + bf16 under DDP on {world} ranks: parameters identical, "
+        print(f"dropout 0.1 + gradient checkpointing + bf16 under FlatGradSync on {world} ranks: parameters identical, "
               f"per-rank dropout seeds distinct: OK")
     dist.destroy_process_group()
 
