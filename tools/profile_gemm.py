@@ -19,6 +19,8 @@ CASES = {  # name: (M, N, K, mn_major, epilogue)   M == 'T' means the token coun
     "ffn2_dgrad": ("T", I, H, 0, _lib.EPI_MUL),
     "ffn1_dgrad": ("T", H, I, 0, _lib.EPI_ADD),
     "ffn1_wgrad": (I, H, "T", 1, _lib.EPI_ATOMIC_F32),
+    "attnout_dgrad": ("T", H, H, 0, _lib.EPI_PLAIN),
+    "qkv_dgrad": ("T", H, 3 * H, 0, _lib.EPI_ADD),
 }
 
 
