@@ -325,6 +325,40 @@ def run_b200(args):
     e2e = dict(value=pairs_step / (e2e_ms * 1e-3), unit=UNIT, h2d_bytes_per_step=h2d_bytes * world,
                d2h_bytes_per_step=4 * world, ms_per_step=e2e_ms, last_loss=last)
 
+    # ---------------- N > 1: what each GPU needs for the same step WITHOUT any cross-rank exchange ----------------
+    # A synchronous data-parallel step runs at the pace of the slowest GPU; under the 1 kW cap the eight GPUs of a box differ
+    # by several percent.  step(N) - max(per-rank compute) is the exposed cost of the exchange itself.
+    rank_compute = None
+    if world > 1 and hasattr(step_model, "detach_sinks"):
+        step_model.detach_sinks()
+
+        def local_step(batch):
+            q, c = model(*batch)
+            loss, _ = fused_score_loss(q, c, ["nll_global"], group_size=group, gather=False)
+            loss.backward()
+            model.zero_grad(set_to_none=True)
+
+        for i in range(2):
+            local_step(resident[i % n_batches])
+        barrier()
+        n_local = 5
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(n_local):
+            local_step(resident[i % n_batches])
+        e1.record()
+        torch.cuda.synchronize()
+        mine = torch.tensor([e0.elapsed_time(e1) / n_local], device=dev, dtype=torch.float64)
+        every = [torch.zeros_like(mine) for _ in range(world)]
+        dist.all_gather(every, mine)
+        per_rank = [round(float(t.item()), 2) for t in every]
+        rank_compute = dict(ms_per_step_by_rank=per_rank, slowest=max(per_rank), fastest=min(per_rank),
+                            exchange_exposed_ms=round(ms_step - max(per_rank), 2),
+                            note="same step per rank with no all-gather / gradient exchange (5 steps); the synchronous step "
+                                 "cannot beat `slowest`")
+        step_model.attach_sinks()
+        barrier()
+
     # ---------------- the reference's training configuration: dropout 0.1 at every HF site ----------------
     # (SimANS/model/models.py:66-72.  The headline above runs dropout-free like the reference arm's CPU port and the parity
     # fixtures; this is the same step with the Philox masks generated inside the attention kernels / GEMM epilogues.)
@@ -417,7 +451,8 @@ def run_b200(args):
                     ms_per_step=ms_step, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="bf16",
                     data="synthetic", config=dict(workload_config(args, nq), gradient_exchange=exchange), e2e=e2e,
                     gpu_launches=(launches_per_step * args.steps if launches_per_step else None), clocks=clocks,
-                    roofline=roofline, cpu_baseline=cpu_baseline, dropout=dropout, parity_mode=parity_mode,
+                    roofline=roofline, cpu_baseline=cpu_baseline, dropout=dropout, rank_compute=rank_compute,
+                    parity_mode=parity_mode,
                     gpu_bar=gpu_bar, model_tflops_per_gpu=value / world * fpp / 1e12, kernels=kernels)
         print(json.dumps(line), flush=True)
     if world > 1:

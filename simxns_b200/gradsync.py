@@ -105,5 +105,10 @@ class FlatGradSync(nn.Module):
                 off += p.numel()
 
     def detach_sinks(self) -> None:
+        """towers hand their gradients to autograd again (no exchange) until attach_sinks()"""
         for m in self._towers:
             m._grad_sink = None
+
+    def attach_sinks(self) -> None:
+        for m in self._towers:
+            m._grad_sink = self._sink
