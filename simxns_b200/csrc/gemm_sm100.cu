@@ -253,7 +253,7 @@ gemm_kernel(const GemmParams p, const __grid_constant__ CUtensorMap mapA, const 
   // its own row straight from global touches 32 different lines per instruction: the K = 768 GEMMs with a residual /
   // GELU' operand ran 20 % behind the plain epilogue on L1 wavefronts)
   constexpr bool kAuxTma = TS && EpiPre<EPI, NP>::kAux;
-  uint64_t* auxbar = bars + 2 * STAGES + 6;  // [16]
+  uint64_t* auxbar = bars + 2 * STAGES + 6;  // [16 warps][2 half boxes]
   float* sbias = nullptr;
   if constexpr (EpiPre<EPI, NP>::kBias) {
     if (p.N <= (int)L::BIAS_FLOATS) {
@@ -293,7 +293,7 @@ gemm_kernel(const GemmParams p, const __grid_constant__ CUtensorMap mapA, const 
       mbar_init(&tempty[i], 16 * CG);  // every epilogue warp of the pair arrives on the LEADER's barrier
     }
     if constexpr (kAuxTma)
-      for (int i = 0; i < 16; ++i) mbar_init(&auxbar[i], 1);
+      for (int i = 0; i < 32; ++i) mbar_init(&auxbar[i], 1);
     fence_mbar_init();
   }
   if constexpr (CG == 2) cluster_sync_all();  // both CTAs alive before the pair-wide TMEM allocation
@@ -406,21 +406,11 @@ gemm_kernel(const GemmParams p, const __grid_constant__ CUtensorMap mapA, const 
       const int row = row_base + lane;
       const int col_base = nt * BN + part * CPW;
       EpiPre<EPI, NP> pre;
-      if constexpr (!kAuxTma) epi_prefetch<EPI, NP, CW>(p, row, col_base, pre);
-      if constexpr (kAuxTma) {
-        // the previous tile's store must have finished READING the staging box before the aux tile lands in it (and
-        // every lane must be done with its own reads of the box: the column-sum sweep of EPI_MUL)
-        __syncwarp();
-        if (lane == 0) {
-          tma_store_wait_read<0>();
-          mbar_arrive_expect_tx(&auxbar[warp - 4], 4096);
-          tma_load_3d(&mapAux, &auxbar[warp - 4], smem + L::STG_OFF + (warp - 4) * 4096, col_base, row_base, 0);
-        }
-      }
-      mbar_wait(&tfull[acc], acc_phase);
-      tc_fence_after();
-      const uint32_t t_addr = tmem_base + acc * BN + part * CPW + (static_cast<uint32_t>(quarter * 32) << 16);
       if constexpr (!TS) {
+        epi_prefetch<EPI, NP, CW>(p, row, col_base, pre);
+        mbar_wait(&tfull[acc], acc_phase);
+        tc_fence_after();
+        const uint32_t t_addr = tmem_base + acc * BN + part * CPW + (static_cast<uint32_t>(quarter * 32) << 16);
 #pragma unroll
         for (int c = 0; c < NCH; ++c) {
           uint32_t v[CW];
@@ -436,88 +426,123 @@ gemm_kernel(const GemmParams p, const __grid_constant__ CUtensorMap mapA, const 
           if (c + 1 < NCH) epi_prefetch<EPI, NP, CW>(p, row, col_base + (c + 1) * CW, pre);
         }
       } else {
-        // ---- staged epilogue: registers -> 128B-swizzled smem box [32 rows x 64 cols] -> one TMA store per output ----
+        // ---- staged epilogue (BN = 256, one plane): the warp's [32 rows x 64 cols] block goes out as two half boxes of
+        // [32 x 32] bf16 (64-byte rows, 64B swizzle) through TMA stores.  Chunk c of a tile uses half box c, so the store of
+        // one half drains while the other half is being computed, and an aux half (residual / GELU' / addend) is TMA-loaded
+        // into its box one chunk of work ahead.  (One [32 x 64] box per warp serialised load -> math -> store: ncu r02 showed
+        // 16 % of the FFN-up epilogue's samples on cp.async.bulk.wait_group.read and the K = 768 GEMMs at 53-69 % tensor
+        // pipe.)  BIAS_GELU has two outputs per chunk (gelu' -> half 0, gelu -> half 1), stored together.
+        static_assert(CW == 32 && NCH == 2, "staged epilogue: two 32-column chunks per warp");
         uint8_t* stg = smem + L::STG_OFF + (warp - 4) * 4096;
-        const uint32_t stg_row = smem_u32(stg) + lane * 128;
-        uint4 o2[EPI == SIMX_EPI_BIAS_GELU ? 8 : 1];
-        // the previous tile's store must have finished READING the staging box before it is overwritten
+        uint64_t* abar = auxbar + 2 * (warp - 4);
+        constexpr bool kGelu2 = EPI == SIMX_EPI_BIAS_GELU;
         if constexpr (kAuxTma) {
-          mbar_wait(&auxbar[warp - 4], it & 1);  // this tile's aux box has landed (one phase per tile)
-        } else {
-          if (lane == 0) tma_store_wait_read<0>();
+          // aux of chunk 1 -> half 1: that half's last store (previous tile, chunk 1) is the most recent one
+          __syncwarp();
+          if (lane == 0) {
+            if (it == 0) {  // first tile of this CTA: nothing was prefetched yet
+              mbar_arrive_expect_tx(&abar[0], 2048);
+              tma_load_3d(&mapAux, &abar[0], stg, col_base, row_base, 0);
+            }
+            tma_store_wait_read<0>();
+            mbar_arrive_expect_tx(&abar[1], 2048);
+            tma_load_3d(&mapAux, &abar[1], stg + 2048, col_base + 32, row_base, 0);
+          }
         }
-        __syncwarp();
+        mbar_wait(&tfull[acc], acc_phase);
+        tc_fence_after();
+        const uint32_t t_addr = tmem_base + acc * BN + part * CPW + (static_cast<uint32_t>(quarter * 32) << 16);
+        const uint32_t sw = (lane >> 1) & 3;  // 64B swizzle: 16-byte chunk q of row r sits at q ^ ((r >> 1) & 3)
 #pragma unroll
-        for (int c = 0; c < NCH; ++c) {
+        for (int c = 0; c < 2; ++c) {
           uint32_t v[CW];
           tmem_ld_cols<CW>(t_addr + c * CW, v);
           tmem_ld_wait();
-          if (c + 1 == NCH) {
+          if (c == 1) {
             tc_fence_before();
             __syncwarp();
             if (lane == 0) { if (leader) mbar_arrive(&tempty[acc]); else mbar_arrive_remote(&tempty[acc], 0); }
           }
+          uint8_t* box = stg + (kGelu2 ? 0 : c * 2048);
+          const uint32_t box_row = smem_u32(box) + lane * 64;
+          if constexpr (kAuxTma) mbar_wait(&abar[c], it & 1);  // this chunk's aux half has landed (one phase per tile)
+          uint4 o[4], o2[kGelu2 ? 4 : 1];
 #pragma unroll
           for (int g = 0; g < 4; ++g) {
-            const int j = c * 4 + g;  // 16-byte chunk index inside the 128-byte row
-            if constexpr (kAuxTma) pre.aux[0][g] = ld_shared_v4(stg_row + ((j ^ (lane & 7)) << 4));
+            if constexpr (kAuxTma) pre.aux[0][g] = ld_shared_v4(box_row + ((g ^ sw) << 4));
             float f[8];
-            epi_values<EPI, NP>(p, row, min(col_base + j * 8, p.N - 8), &v[g * 8], pre, g, sbias, f);
-            uint4 o;
-            if constexpr (EPI == SIMX_EPI_BIAS_GELU) {
+            epi_values<EPI, NP>(p, row, min(col_base + c * 32 + g * 8, p.N - 8), &v[g * 8], pre, g, sbias, f);
+            if constexpr (kGelu2) {
               uint32_t ge[4], dg[4];
 #pragma unroll
               for (int i = 0; i < 4; ++i) gelu_pair_f16(f[2 * i], f[2 * i + 1], ge[i], dg[i]);
-              o = make_uint4(dg[0], dg[1], dg[2], dg[3]);
-              o2[j] = make_uint4(ge[0], ge[1], ge[2], ge[3]);
+              o[g] = make_uint4(dg[0], dg[1], dg[2], dg[3]);
+              o2[g] = make_uint4(ge[0], ge[1], ge[2], ge[3]);
             } else if constexpr (EPI == SIMX_EPI_BIAS_GELU_FWD) {
-              o = make_uint4(gelu_only_pair_f16(f[0], f[1]), gelu_only_pair_f16(f[2], f[3]), gelu_only_pair_f16(f[4], f[5]),
-                             gelu_only_pair_f16(f[6], f[7]));
+              o[g] = make_uint4(gelu_only_pair_f16(f[0], f[1]), gelu_only_pair_f16(f[2], f[3]), gelu_only_pair_f16(f[4], f[5]),
+                                gelu_only_pair_f16(f[6], f[7]));
             } else {
-              o = make_uint4(pack_bf16x2(f[0], f[1]), pack_bf16x2(f[2], f[3]), pack_bf16x2(f[4], f[5]),
-                             pack_bf16x2(f[6], f[7]));
+              o[g] = make_uint4(pack_bf16x2(f[0], f[1]), pack_bf16x2(f[2], f[3]), pack_bf16x2(f[4], f[5]),
+                                pack_bf16x2(f[6], f[7]));
             }
-            st_shared_v4(stg_row + ((j ^ (lane & 7)) << 4), o);
           }
+          // the box must be free: its previous store has finished READING shared memory.  Those stores were issued one
+          // chunk of math ago (with an aux operand the wait already happened before the aux load went into the box).
           if constexpr (!kAuxTma) {
-            if (c + 1 < NCH) epi_prefetch<EPI, NP, CW>(p, row, col_base + (c + 1) * CW, pre);
-          }
-        }
-        fence_proxy_async_smem();
-        __syncwarp();
-        if (lane == 0) {
-          tma_store_3d(&mapOut, stg, col_base, row_base, 0);
-          tma_store_commit();
-        }
-        if constexpr (EPI == SIMX_EPI_MUL) {
-          if (scol != nullptr) {
-            // lane l sums columns 2l, 2l+1 of the staged [32 x 64] box (the bf16 values being stored): for a fixed
-            // row the 32 lanes read the 32 words of one swizzled 128-byte line — conflict-free
-            float s0 = 0.f, s1 = 0.f;
-            const uint32_t sb = smem_u32(stg) + ((lane & 3) << 2);
-#pragma unroll 8
-            for (int r = 0; r < 32; ++r) {
-              const float2 f = unpack_bf16x2(ld_shared_u32(sb + r * 128 + (((lane >> 2) ^ (r & 7)) << 4)));
-              s0 += f.x;
-              s1 += f.y;
+            if (lane == 0) {
+              if constexpr (kGelu2) tma_store_wait_read<0>();
+              else tma_store_wait_read<1>();
             }
-            const int col = col_base + 2 * lane;
-            if (col < p.N) {
-              atomicAdd(&scol[col], s0);
-              atomicAdd(&scol[col + 1], s1);
-            }
+            __syncwarp();
           }
-        }
-        if constexpr (EPI == SIMX_EPI_BIAS_GELU) {
-          if (lane == 0) tma_store_wait_read<0>();
-          __syncwarp();
 #pragma unroll
-          for (int j = 0; j < 8; ++j) st_shared_v4(stg_row + ((j ^ (lane & 7)) << 4), o2[j]);
+          for (int g = 0; g < 4; ++g) {
+            st_shared_v4(box_row + ((g ^ sw) << 4), o[g]);
+            if constexpr (kGelu2) st_shared_v4(box_row + 2048 + ((g ^ sw) << 4), o2[g]);
+          }
           fence_proxy_async_smem();
           __syncwarp();
           if (lane == 0) {
-            tma_store_3d(&mapOut2, stg, col_base, row_base, 0);
+            tma_store_3d(&mapOut, box, col_base + c * 32, row_base, 0);
+            if constexpr (kGelu2) tma_store_3d(&mapOut2, box + 2048, col_base + c * 32, row_base, 0);
             tma_store_commit();
+          }
+          if constexpr (EPI == SIMX_EPI_MUL) {
+            if (scol != nullptr) {
+              // column sums of the bf16 values being stored: lane l takes column pair l & 15 over 16 of the 32 rows (the two
+              // half-warps start one row apart so that their 64-byte rows fall into different bank halves)
+              const int pr = lane & 15, hsel = lane >> 4;
+              const uint32_t sb = smem_u32(box) + ((pr & 3) << 2);
+              float s0 = 0.f, s1 = 0.f;
+#pragma unroll 8
+              for (int k = 0; k < 16; ++k) {
+                const int r = hsel * 16 + ((k + hsel) & 15);
+                const float2 f2 = unpack_bf16x2(ld_shared_u32(sb + r * 64 + ((((pr >> 2) ^ (r >> 1)) & 3) << 4)));
+                s0 += f2.x;
+                s1 += f2.y;
+              }
+              s0 += __shfl_xor_sync(0xffffffffu, s0, 16);
+              s1 += __shfl_xor_sync(0xffffffffu, s1, 16);
+              const int col = col_base + c * 32 + 2 * pr;
+              if (hsel == 0 && col < p.N) {
+                atomicAdd(&scol[col], s0);
+                atomicAdd(&scol[col + 1], s1);
+              }
+              __syncwarp();  // every lane is done reading the box before the next aux half may land in it
+            }
+          }
+          if constexpr (kAuxTma) {
+            if (c == 1) {
+              // prefetch the NEXT tile's chunk-0 aux half into half 0: its store (chunk 0 of this tile) was issued a chunk
+              // of math ago; only the chunk-1 store just issued may still be pending
+              const int nxt = tile + tile_stride;
+              if (nxt < total_tiles && lane == 0) {
+                const int nnt = nxt % p.n_tiles, nmt = (nxt / p.n_tiles) % p.m_tiles;
+                tma_store_wait_read<1>();
+                mbar_arrive_expect_tx(&abar[0], 2048);
+                tma_load_3d(&mapAux, &abar[0], stg, nnt * BN + part * CPW, nmt * TILE_M + cta_rank * GEMM_BM + quarter * 32, 0);
+              }
+            }
           }
         }
       }
@@ -565,8 +590,16 @@ static EncodeTiledFn get_encode_fn() {
 }
 
 // bf16 tensor [planes][outer][inner] (inner contiguous), box = [1][box_outer][64]
+static int make_tmap_bf16_box(CUtensorMap* map, const void* ptr, uint64_t inner, uint64_t outer, uint64_t planes, uint64_t ld,
+                              uint64_t plane_stride, uint32_t box_outer, uint32_t box_inner);
 int make_tmap_bf16(CUtensorMap* map, const void* ptr, uint64_t inner, uint64_t outer, uint64_t planes, uint64_t ld,
                    uint64_t plane_stride, uint32_t box_outer) {
+  return make_tmap_bf16_box(map, ptr, inner, outer, planes, ld, plane_stride, box_outer, 64);
+}
+// box_inner = 64 elements (128-byte rows, 128B swizzle: operand tiles) or 32 (64-byte rows, 64B swizzle: the epilogue's
+// half boxes)
+static int make_tmap_bf16_box(CUtensorMap* map, const void* ptr, uint64_t inner, uint64_t outer, uint64_t planes, uint64_t ld,
+                              uint64_t plane_stride, uint32_t box_outer, uint32_t box_inner) {
   EncodeTiledFn fn = get_encode_fn();
   SIMX_CHECK(fn != nullptr, SIMX_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
   SIMX_CHECK((reinterpret_cast<uintptr_t>(ptr) & 15) == 0, SIMX_ERR_INVALID, "TMA operand not 16-byte aligned");
@@ -577,11 +610,11 @@ int make_tmap_bf16(CUtensorMap* map, const void* ptr, uint64_t inner, uint64_t o
   SIMX_CHECK((plane_stride * 2) % 16 == 0, SIMX_ERR_INVALID, "TMA plane stride not a multiple of 8 elements");
   cuuint64_t gdim[3] = {inner, outer, planes};
   cuuint64_t gstride[2] = {ld * 2, plane_stride * 2};
-  cuuint32_t box[3] = {64, box_outer, 1};
+  cuuint32_t box[3] = {box_inner, box_outer, 1};
   cuuint32_t estr[3] = {1, 1, 1};
   CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(ptr), gdim, gstride, box, estr,
-                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, box_inner == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B,
+                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   SIMX_CHECK(r == CUDA_SUCCESS, SIMX_ERR_CUDA,
              "cuTensorMapEncodeTiled failed (%d): inner=%llu outer=%llu planes=%llu ld=%llu box_outer=%u", (int)r,
              (unsigned long long)inner, (unsigned long long)outer, (unsigned long long)planes, (unsigned long long)ld,
@@ -621,9 +654,9 @@ static int launch_gemm_cg(GemmParams p, const bf16* A, long lda, long a_ps, cons
   }
   CUtensorMap mo = ma, mo2 = ma, mx = ma;  // placeholders when the epilogue stores from registers
   if constexpr (TS) {
-    SIMX_TRY(make_tmap_bf16(&mo, p.out, p.N, p.M, 1, p.ldo, 0, 32));
-    if constexpr (EPI == SIMX_EPI_BIAS_GELU) SIMX_TRY(make_tmap_bf16(&mo2, p.out2, p.N, p.M, 1, p.ldo, 0, 32));
-    if constexpr (EpiPre<EPI, NP>::kAux) SIMX_TRY(make_tmap_bf16(&mx, p.aux, p.N, p.M, 1, p.ldaux, 0, 32));
+    SIMX_TRY(make_tmap_bf16_box(&mo, p.out, p.N, p.M, 1, p.ldo, 0, 32, 32));
+    if constexpr (EPI == SIMX_EPI_BIAS_GELU) SIMX_TRY(make_tmap_bf16_box(&mo2, p.out2, p.N, p.M, 1, p.ldo, 0, 32, 32));
+    if constexpr (EpiPre<EPI, NP>::kAux) SIMX_TRY(make_tmap_bf16_box(&mx, p.aux, p.N, p.M, 1, p.ldaux, 0, 32, 32));
   }
   const int total = p.m_tiles * p.n_tiles * p.ksplit;
   const int grid = CG * min(total, num_sms() / CG);
