@@ -175,11 +175,16 @@ class EncoderOracle:
         return self.p[self.base + 16 * l: self.base + 16 * (l + 1)]
 
     # ---- forward ---------------------------------------------------------------------------------------
-    def forward(self, ids, mask=None, dropout=None):
+    def forward(self, ids, mask=None, dropout=None, inputs_embeds=None):
         """dropout: None (eval / parity configuration) or dict(p_hidden=, p_attn=, seed=): the masks of
         oracle/dropout_numpy.py at the HF sites (LEAD/modeling_bert.py:239, :358, :386, :464; DistilBERT has no dropout
         after the attention output projection, LEAD/modeling_distilbert.py:254-319)."""
         cfg = self.cfg
+        if inputs_embeds is not None:
+            # HF BertEmbeddings.forward(inputs_embeds=...): the caller's [B,S,H] rows replace word_embeddings(input_ids)
+            # (LEAD/modeling_bert.py:222-227); `ids` is only used for its shape
+            inputs_embeds = np.asarray(inputs_embeds, dtype=self.dtype)
+            ids = np.zeros(inputs_embeds.shape[:2], dtype=np.int64)
         B, S = ids.shape
         H, nh = cfg["hidden"], cfg["heads"]
         d = H // nh
@@ -191,7 +196,7 @@ class EncoderOracle:
             mask = np.ones_like(ids)
         word, pos = self.p[0], self.p[1]
         pos_ids = position_ids(cfg, ids)
-        emb = word[ids] + pos[pos_ids]
+        emb = (word[ids] if inputs_embeds is None else inputs_embeds) + pos[pos_ids]
         if cfg["arch"] == "bert":
             emb = emb + self.p[2][0][None, None]
             g, b = self.p[3], self.p[4]
@@ -200,7 +205,7 @@ class EncoderOracle:
         x, ln0 = layer_norm(emb, g, b, cfg["ln_eps"])
         m0 = hmask(dn.SITE_EMBED, 0)
         x = x * m0
-        self.cache = dict(ids=ids, mask=mask, ln0=ln0, layers=[], pos_ids=pos_ids, m0=m0)
+        self.cache = dict(ids=ids, mask=mask, ln0=ln0, layers=[], pos_ids=pos_ids, m0=m0, embeds=inputs_embeds is not None)
         hidden = [x]
         neg = np.where(mask[:, None, None, :] > 0, 0.0, -np.inf)
         for l in range(cfg["num_layers"]):
@@ -296,6 +301,8 @@ class EncoderOracle:
             grads[1][pad] = 0.0  # RobertaEmbeddings: position_embeddings has padding_idx too
         else:
             grads[1][:S] = demb.sum(0)
-        np.add.at(grads[0], ids.reshape(-1), demb.reshape(-1, H))
+        self.d_inputs_embeds = demb if c["embeds"] else None
+        if not c["embeds"]:
+            np.add.at(grads[0], ids.reshape(-1), demb.reshape(-1, H))
         grads[0][pad] = 0.0  # nn.Embedding(padding_idx=pad): the pad row never receives gradient
         return {n: g_ for n, g_ in zip(self.names, grads)}

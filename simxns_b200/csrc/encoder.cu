@@ -19,9 +19,9 @@
 namespace simx {
 
 // kernels from the other translation units
-int embed_ln(int np, const void* ids, const void* pos_ids, int id_bytes, int max_pos, int T, int S, int H, int vocab,
-             const float* word, const float* pos, const float* type0, const float* gamma, const float* beta, float eps,
-             bf16* z0, bf16* x, long ps, const DropSpec& drop, cudaStream_t st);
+int embed_ln(int np, const void* ids, const float* embeds, const void* pos_ids, int id_bytes, int max_pos, int T, int S, int H,
+             int vocab, const float* word, const float* pos, const float* type0, const float* gamma, const float* beta,
+             float eps, bf16* z0, bf16* x, long ps, const DropSpec& drop, cudaStream_t st);
 int ln_fwd(int np, const bf16* z, int T, int H, const float* gamma, const float* beta, float eps, bf16* x, long ps,
            cudaStream_t st);
 int ln_bwd(int np, const bf16* dy, const bf16* z, int T, int H, const float* gamma, float eps, bf16* dz, long ps,
@@ -374,10 +374,10 @@ static int layer_forward(const simx_encoder_cfg* cfg, const float* const* P, con
 }
 
 static int encoder_forward_impl(const simx_encoder_cfg* cfg, const float* const* params, const void* wbuf,
-                                const void* ids, const void* mask, const void* pos_ids, int B, int S, void* saved,
-                                void* workspace, float* cls_out, float* seq_out, void* stream) {
+                                const void* ids, const float* embeds, const void* mask, const void* pos_ids, int B, int S,
+                                void* saved, void* workspace, float* cls_out, float* seq_out, void* stream) {
   SIMX_TRY(check_cfg(cfg));
-  SIMX_CHECK(params && wbuf && ids, SIMX_ERR_INVALID, "encoder_forward: null argument");
+  SIMX_CHECK(params && wbuf && (ids || embeds), SIMX_ERR_INVALID, "encoder_forward: null argument");
   SIMX_CHECK(B > 0 && S > 0 && S <= cfg->max_pos && S <= 512, SIMX_ERR_INVALID,
              "encoder_forward: need 0 < S <= min(max_pos=%d, 512), got B=%d S=%d", cfg->max_pos, B, S);
   SIMX_CHECK(saved != nullptr || workspace != nullptr, SIMX_ERR_INVALID, "encoder_forward: need saved or workspace");
@@ -408,8 +408,8 @@ static int encoder_forward_impl(const simx_encoder_cfg* cfg, const float* const*
   const float* type0 = t.bert ? params[2] : nullptr;
   const float* eg = params[t.bert ? 3 : 2];
   const float* eb = params[t.bert ? 4 : 3];
-  SIMX_TRY(embed_ln(np, ids, pos_ids, id_bytes(cfg), cfg->max_pos, T, S, H, cfg->vocab, params[0], params[1], type0, eg, eb,
-                    cfg->ln_eps, z0, xbuf(0), psH, drop_at(cfg, DROP_SITE_EMBED, 0), st));
+  SIMX_TRY(embed_ln(np, ids, embeds, pos_ids, id_bytes(cfg), cfg->max_pos, T, S, H, cfg->vocab, params[0], params[1], type0, eg,
+                    eb, cfg->ln_eps, z0, xbuf(0), psH, drop_at(cfg, DROP_SITE_EMBED, 0), st));
   const long cls_stride_b = (long)(L + 1) * H;
   if (cls_out) SIMX_TRY(cls_gather(np, xbuf(0), B, S, H, psH, cls_out, cls_stride_b, st));
 
@@ -426,13 +426,20 @@ static int encoder_forward_impl(const simx_encoder_cfg* cfg, const float* const*
 extern "C" int simx_encoder_forward(const simx_encoder_cfg* cfg, const float* const* params, const void* wbuf,
                                     const void* ids, const void* mask, int B, int S, void* saved, void* workspace,
                                     float* cls_out, float* seq_out, void* stream) {
-  return encoder_forward_impl(cfg, params, wbuf, ids, mask, nullptr, B, S, saved, workspace, cls_out, seq_out, stream);
+  return encoder_forward_impl(cfg, params, wbuf, ids, nullptr, mask, nullptr, B, S, saved, workspace, cls_out, seq_out, stream);
 }
 extern "C" int simx_encoder_forward_pos(const simx_encoder_cfg* cfg, const float* const* params, const void* wbuf,
                                         const void* ids, const void* mask, const void* pos_ids, int B, int S,
                                         void* saved, void* workspace, float* cls_out, float* seq_out, void* stream) {
   SIMX_CHECK(pos_ids != nullptr, SIMX_ERR_INVALID, "encoder_forward_pos: null position ids");
-  return encoder_forward_impl(cfg, params, wbuf, ids, mask, pos_ids, B, S, saved, workspace, cls_out, seq_out, stream);
+  return encoder_forward_impl(cfg, params, wbuf, ids, nullptr, mask, pos_ids, B, S, saved, workspace, cls_out, seq_out, stream);
+}
+extern "C" int simx_encoder_forward_embeds(const simx_encoder_cfg* cfg, const float* const* params, const void* wbuf,
+                                           const float* inputs_embeds, const void* mask, const void* pos_ids, int B, int S,
+                                           void* saved, void* workspace, float* cls_out, float* seq_out, void* stream) {
+  SIMX_CHECK(inputs_embeds != nullptr, SIMX_ERR_INVALID, "encoder_forward_embeds: null inputs_embeds");
+  return encoder_forward_impl(cfg, params, wbuf, nullptr, inputs_embeds, mask, pos_ids, B, S, saved, workspace, cls_out, seq_out,
+                              stream);
 }
 
 // Backward through layers [layer_lo, layer_hi) in descending order.  layer_hi == L starts the pass (the running cotangent
@@ -443,9 +450,10 @@ extern "C" int simx_encoder_forward_pos(const simx_encoder_cfg* cfg, const float
 static int encoder_backward_impl(const simx_encoder_cfg* cfg, const float* const* params, const void* wbuf,
                                  const void* ids, const void* mask, const void* pos_ids, int pad_id, int B, int S,
                                  const void* saved, void* workspace, const float* d_cls, const float* d_seq, float* grads,
-                                 int layer_lo, int layer_hi, void* stream) {
+                                 int layer_lo, int layer_hi, void* stream, float* d_embeds = nullptr) {
   SIMX_TRY(check_cfg(cfg));
-  SIMX_CHECK(params && wbuf && ids && saved && workspace && grads, SIMX_ERR_INVALID, "encoder_backward: null argument");
+  SIMX_CHECK(params && wbuf && (ids || d_embeds) && saved && workspace && grads, SIMX_ERR_INVALID,
+             "encoder_backward: null argument");
   SIMX_CHECK(B > 0 && S > 0 && S <= cfg->max_pos && S <= 512, SIMX_ERR_INVALID, "encoder_backward: bad B=%d S=%d", B, S);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const int np = cfg->precision, H = cfg->hidden, I = cfg->intermediate, L = cfg->num_layers;
@@ -569,7 +577,9 @@ static int encoder_backward_impl(const simx_encoder_cfg* cfg, const float* const
     // caller-supplied position ids (RoBERTa): scatter-add like the word rows; the pad position row gets nothing
     SIMX_TRY(embed_scatter(np, pos_ids, idw, dza, T, H, cfg->max_pos, pad_id, psH, G(1), st));
   }
-  SIMX_TRY(embed_scatter(np, ids, idw, dza, T, H, cfg->vocab, pad_id, psH, G(0), st));
+  if (ids != nullptr) SIMX_TRY(embed_scatter(np, ids, idw, dza, T, H, cfg->vocab, pad_id, psH, G(0), st));
+  // caller-supplied input embeddings: their cotangent is dz0 itself (the word table took no part: its gradient stays zero)
+  if (d_embeds != nullptr) SIMX_TRY(planes_to_f32(np, dza, (long)T * H, psH, d_embeds, st));
   return SIMX_OK;
 }
 
@@ -589,6 +599,15 @@ extern "C" int simx_encoder_backward_pos(const simx_encoder_cfg* cfg, const floa
   SIMX_CHECK(pos_ids != nullptr, SIMX_ERR_INVALID, "encoder_backward_pos: null position ids");
   return encoder_backward_impl(cfg, params, wbuf, ids, mask, pos_ids, pad_token_id, B, S, saved, workspace, d_cls, d_seq,
                                grads, -1, cfg->num_layers, stream);
+}
+extern "C" int simx_encoder_backward_embeds(const simx_encoder_cfg* cfg, const float* const* params, const void* wbuf,
+                                            const void* mask, const void* pos_ids, int pad_token_id, int B, int S,
+                                            const void* saved, void* workspace, const float* d_cls, const float* d_seq,
+                                            float* grads, float* d_inputs_embeds, void* stream) {
+  SIMX_TRY(check_cfg(cfg));
+  SIMX_CHECK(d_inputs_embeds != nullptr, SIMX_ERR_INVALID, "encoder_backward_embeds: null d_inputs_embeds");
+  return encoder_backward_impl(cfg, params, wbuf, nullptr, mask, pos_ids, pad_token_id, B, S, saved, workspace, d_cls, d_seq,
+                               grads, -1, cfg->num_layers, stream, d_inputs_embeds);
 }
 extern "C" int simx_encoder_backward_layers(const simx_encoder_cfg* cfg, const float* const* params, const void* wbuf,
                                             const void* ids, const void* mask, const void* pos_ids, int pad_token_id,

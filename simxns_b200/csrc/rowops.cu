@@ -62,15 +62,18 @@ __device__ __forceinline__ void ln_row_store(float (&v)[MAXC][8], int H, int lan
 // ------------------------------------------------------------------------------------------------
 template <int NP>
 __global__ void __launch_bounds__(ROW_THREADS)
-embed_ln_kernel(const void* __restrict__ ids, const void* __restrict__ pos_ids, int id_bytes, int max_pos, int T, int S,
-                int H, int vocab, const float* __restrict__ word, const float* __restrict__ pos,
+embed_ln_kernel(const void* __restrict__ ids, const float* __restrict__ embeds, const void* __restrict__ pos_ids, int id_bytes,
+                int max_pos, int T, int S, int H, int vocab, const float* __restrict__ word, const float* __restrict__ pos,
                 const float* __restrict__ type0, const float* __restrict__ gamma, const float* __restrict__ beta, float eps,
                 bf16* z0, bf16* x, long ps, const DropSpec drop) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int row = blockIdx.x * ROW_WARPS + warp;
   if (row >= T) return;
-  long id = ld_id(ids, row, id_bytes);
-  if (id < 0 || id >= vocab) id = 0;  // out-of-range ids are a caller bug; stay in bounds
+  // the word row of this token — or, with caller-supplied `inputs_embeds` (HF BertEmbeddings.forward(inputs_embeds=...),
+  // LEAD/modeling_bert.py:222-227), row `row` of that [T, H] fp32 tensor
+  long id = embeds != nullptr ? row : ld_id(ids, row, id_bytes);
+  if (embeds == nullptr && (id < 0 || id >= vocab)) id = 0;  // out-of-range ids are a caller bug; stay in bounds
+  const float* wsrc = embeds != nullptr ? embeds : word;
   // position row: the token's index in its sequence (BERT), or the caller's position ids (RoBERTa: pad + running count
   // of real tokens)
   long s = row % S;
@@ -84,7 +87,7 @@ embed_ln_kernel(const void* __restrict__ ids, const void* __restrict__ pos_ids, 
     const int col = c * 256 + lane * 8;
     if (col < H) {
       float w[8], p[8];
-      ld8f(word + id * H + col, w);
+      ld8f(wsrc + id * H + col, w);
       ld8f(pos + s * H + col, p);
 #pragma unroll
       for (int i = 0; i < 8; ++i) v[c][i] = w[i] + p[i];
@@ -504,15 +507,15 @@ __global__ void convert_weights_batched_kernel(const ConvJobs jobs) {
     else { constexpr int kNP = 3; CALL; }                               \
   } while (0)
 
-int embed_ln(int np, const void* ids, const void* pos_ids, int id_bytes, int max_pos, int T, int S, int H, int vocab,
-             const float* word, const float* pos, const float* type0, const float* gamma, const float* beta, float eps,
-             bf16* z0, bf16* x, long ps, const DropSpec& drop, cudaStream_t st) {
+int embed_ln(int np, const void* ids, const float* embeds, const void* pos_ids, int id_bytes, int max_pos, int T, int S, int H,
+             int vocab, const float* word, const float* pos, const float* type0, const float* gamma, const float* beta,
+             float eps, bf16* z0, bf16* x, long ps, const DropSpec& drop, cudaStream_t st) {
   ProfScope prof("embed_ln", 0, (double)T * H * (8.0 + 4.0 * np), st);
   SIMX_CHECK(H % 8 == 0 && H <= 256 * MAXC, SIMX_ERR_INVALID, "hidden size %d unsupported (multiple of 8, <= %d)", H,
              256 * MAXC);
   const int grid = (T + ROW_WARPS - 1) / ROW_WARPS;
-  SIMX_NP_DISPATCH(np, (embed_ln_kernel<kNP><<<grid, ROW_THREADS, 0, st>>>(ids, pos_ids, id_bytes, max_pos, T, S, H, vocab, word,
-                                                                           pos, type0, gamma, beta, eps, z0, x, ps, drop)));
+  SIMX_NP_DISPATCH(np, (embed_ln_kernel<kNP><<<grid, ROW_THREADS, 0, st>>>(ids, embeds, pos_ids, id_bytes, max_pos, T, S, H, vocab,
+                                                                           word, pos, type0, gamma, beta, eps, z0, x, ps, drop)));
   SIMX_LAUNCH_CHECK();
   return SIMX_OK;
 }

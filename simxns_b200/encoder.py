@@ -299,13 +299,29 @@ class B200EncoderBase(nn.Module):
         o = self._ordered
         return [o[:base]] + [o[base + 16 * l: base + 16 * (l + 1)] for l in range(L)] + [o[base + 16 * L:]]
 
-    def encode(self, input_ids: torch.Tensor, attention_mask: Optional[torch.Tensor] = None,
-               want_sequence: bool = False):
+    def encode(self, input_ids: Optional[torch.Tensor], attention_mask: Optional[torch.Tensor] = None,
+               want_sequence: bool = False, inputs_embeds: Optional[torch.Tensor] = None):
         """-> (cls_layers [B, L+1, H] fp32, sequence_output [B,S,H] fp32 or None).
-        cls_layers[:, -1] is the reference's pooled_output; cls_layers[:, l+1] the [CLS] row of layer l."""
+        cls_layers[:, -1] is the reference's pooled_output; cls_layers[:, l+1] the [CLS] row of layer l.
+        inputs_embeds [B,S,H] (instead of input_ids): HF's `inputs_embeds=` — the word-embedding rows supplied by the caller,
+        differentiable (the forward_adv_* paths of BiBertEncoder)."""
+        params = self._ordered
+        if inputs_embeds is not None:
+            if input_ids is not None:
+                raise ValueError("You cannot specify both input_ids and inputs_embeds at the same time")  # HF's message
+            if inputs_embeds.dim() != 3 or inputs_embeds.shape[-1] != self.enc_cfg.hidden:
+                raise ValueError(f"inputs_embeds must be [B, S, {self.enc_cfg.hidden}]")
+            if self.enc_cfg.roberta_positions:
+                raise NotImplementedError("inputs_embeds with RoBERTa position ids is not implemented")
+            needs_grad = torch.is_grad_enabled() and (inputs_embeds.requires_grad or any(p.requires_grad for p in params))
+            st = _TowerPass(self, None, attention_mask, bool(want_sequence), needs_grad, inputs_embeds=inputs_embeds)
+            if not needs_grad:
+                return st.cls, (st.seq if want_sequence else None)
+            st.monolithic = True
+            cls, seq = _TopNode.apply(st, inputs_embeds, *params)
+            return cls, (seq if want_sequence else None)
         if input_ids.dim() != 2:
             raise ValueError("input_ids must be [B, S]")
-        params = self._ordered
         needs_grad = torch.is_grad_enabled() and any(p.requires_grad for p in params)
         st = _TowerPass(self, input_ids, attention_mask, bool(want_sequence), needs_grad)
         if not needs_grad:
@@ -333,24 +349,31 @@ class _TowerPass:
     """State of one forward/backward pass of one tower: runs the forward at construction, owns the saved activations, and
     runs the backward slice by slice on behalf of the autograd nodes below."""
 
-    def __init__(self, module: B200EncoderBase, ids, mask, want_seq: bool, needs_grad: bool):
+    def __init__(self, module: B200EncoderBase, ids, mask, want_seq: bool, needs_grad: bool, inputs_embeds=None):
         lib = _lib.lib()
         params = module._ordered
         module._check_params(params)
         dev = params[0].device
-        if ids.device != dev:
-            raise RuntimeError(f"input_ids on {ids.device}, parameters on {dev}")
+        src = ids if inputs_embeds is None else inputs_embeds
+        if src.device != dev:
+            raise RuntimeError(f"inputs on {src.device}, parameters on {dev}")
         ec = module.enc_cfg
         with torch.no_grad(), torch.cuda.device(dev):
             _lib.require_device()
-            # int32 batches stay int32 (half the host->device bytes); anything else is the reference's int64
-            idt = torch.int32 if ids.dtype == torch.int32 else torch.int64
-            ids = ids.to(idt).contiguous()
+            embeds = None
+            if inputs_embeds is not None:
+                embeds = inputs_embeds.detach().to(torch.float32).contiguous()
+                idt = torch.int64 if mask is None or mask.dtype != torch.int32 else torch.int32
+                B, S = embeds.shape[:2]
+            else:
+                # int32 batches stay int32 (half the host->device bytes); anything else is the reference's int64
+                idt = torch.int32 if ids.dtype == torch.int32 else torch.int64
+                ids = ids.to(idt).contiguous()
+                B, S = ids.shape
             if mask is not None:
                 mask = mask.to(device=dev, dtype=idt).contiguous()
-                if mask.shape != ids.shape:
+                if tuple(mask.shape) != (B, S):
                     raise ValueError("attention_mask must have the shape of input_ids")
-            B, S = ids.shape
             if S > min(ec.max_pos, 512):
                 raise ValueError(f"sequence length {S} exceeds min(max_position_embeddings={ec.max_pos}, 512)")
             pos_ids = None
@@ -377,7 +400,12 @@ class _TowerPass:
                 saved = torch.empty(lib.simx_encoder_saved_bytes(C.byref(cfg), B, S), dtype=torch.uint8, device=dev)
             if not needs_grad or module.gradient_checkpointing:
                 ws = torch.empty(lib.simx_encoder_workspace_bytes(C.byref(cfg), B, S), dtype=torch.uint8, device=dev)
-            if pos_ids is None:
+            if embeds is not None:
+                _lib.check(lib.simx_encoder_forward_embeds(C.byref(cfg), table, wbuf.data_ptr(), embeds.data_ptr(),
+                                                           _lib.ptr(mask), None, B, S, _lib.ptr(saved), _lib.ptr(ws),
+                                                           cls.data_ptr(), _lib.ptr(seq), stream),
+                           "simx_encoder_forward_embeds")
+            elif pos_ids is None:
                 _lib.check(lib.simx_encoder_forward(C.byref(cfg), table, wbuf.data_ptr(), ids.data_ptr(), _lib.ptr(mask), B, S,
                                                     _lib.ptr(saved), _lib.ptr(ws), cls.data_ptr(), _lib.ptr(seq), stream),
                            "simx_encoder_forward")
@@ -387,6 +415,8 @@ class _TowerPass:
                                                         cls.data_ptr(), _lib.ptr(seq), stream), "simx_encoder_forward_pos")
         self.module, self.cfg, self.dev = module, cfg, dev
         self.ids, self.mask, self.pos_ids, self.shape = ids, mask, pos_ids, (B, S)
+        self.embeds = embeds is not None  # backward also produces d(loss)/d(inputs_embeds)
+        self.d_embeds = None
         self.cls, self.seq, self.want_seq = cls, seq, want_seq
         self.saved, self.wbuf, self.params = saved, wbuf, params
         self.ws = None      # backward workspace: holds the running cotangent between slices
@@ -422,6 +452,19 @@ class _TowerPass:
         lib = _lib.lib()
         B, S = self.shape
         m = self.module
+        if self.embeds:
+            if (lo, hi) != (-1, m.enc_cfg.num_layers):
+                raise RuntimeError("inputs_embeds passes run their backward in one slice")
+            with torch.cuda.device(self.dev):
+                stream = torch.cuda.current_stream(self.dev).cuda_stream
+                self.d_embeds = torch.empty(B, S, m.enc_cfg.hidden, dtype=torch.float32, device=self.dev)
+                _lib.check(lib.simx_encoder_backward_embeds(
+                    C.byref(self.cfg), m._param_table(self.params), self.wbuf.data_ptr(), _lib.ptr(self.mask), None, 0, B, S,
+                    self.saved.data_ptr(), self.ws.data_ptr(), _lib.ptr(self.d_cls), _lib.ptr(self.d_seq), self.flat.data_ptr(),
+                    self.d_embeds.data_ptr(), stream), "simx_encoder_backward_embeds")
+            self.next_hi = -1
+            self.saved = self.ws = self.d_cls = self.d_seq = None
+            return
         with torch.cuda.device(self.dev):
             stream = torch.cuda.current_stream(self.dev).cuda_stream
             _lib.check(lib.simx_encoder_backward_layers(
@@ -510,7 +553,8 @@ class _TopNode(torch.autograd.Function):
             if live:
                 st.run_slice(-1, st.next_hi)
                 st.finish()
-            return (None, None) + st.grads_for(ctx.params, ctx.needs_input_grad[2:])
+            d_in = st.d_embeds if (st.embeds and ctx.needs_input_grad[1]) else None  # `token` slot = inputs_embeds here
+            return (None, d_in) + st.grads_for(ctx.params, ctx.needs_input_grad[2:])
         token_grad = st.cls.new_empty(0) if (live and ctx.needs_input_grad[1]) else None
         # pooler parameters: dead math in the reference (multiplied by 0), dense zero gradients.  Their slice of
         # the flat buffer is zeroed by the first backward slice, which has not run yet — hand out fresh zeros instead.

@@ -200,15 +200,12 @@ class HFBertEncoder(B200EncoderBase):
     # -- reference forward ----------------------------------------------------------------------------------
     def forward(self, input_ids=None, attention_mask=None, token_type_ids=None, inputs_embeds=None,
                 output_attentions=None, output_hidden_states=None, _want_sequence: bool = True, **kwargs):
-        if inputs_embeds is not None:
-            raise NotImplementedError("inputs_embeds is not supported by the B200 encoder "
-                                      "(only reached from the dead forward_adv_* paths of the reference)")
         if token_type_ids is not None and bool((token_type_ids != 0).any()):
             raise NotImplementedError("non-zero token_type_ids: the reference never passes segment ids "
                                       "(SimANS/model/models.py:654 'TODO: provide segment values')")
         if output_attentions:
             raise NotImplementedError("attention maps are never materialised by the fused attention kernel")
-        cls, seq = self.encode(input_ids, attention_mask, want_sequence=_want_sequence)
+        cls, seq = self.encode(input_ids, attention_mask, want_sequence=_want_sequence, inputs_embeds=inputs_embeds)
         pooled_output = cls[:, -1, :]
         self.last_cls_layers = cls  # [B, L+1, H]; per-layer [CLS] rows (LEAD-style consumers)
         return seq, pooled_output, None
@@ -288,11 +285,45 @@ class BiBertEncoder(nn.Module):
         loss = -1.0 * lsm[:, 0]
         return (loss.mean(),)
 
-    def forward_adv_triplet(self, *a, **k):
-        raise NotImplementedError("forward_adv_* take inputs_embeds and are unreachable from the reference drivers")
+    # the adversarial-embedding variants (SimANS/model/models.py:120-160): the hard negatives arrive as input EMBEDDINGS
+    # (`inputs_embeds=`), differentiable, through the same kernels (simx_encoder_forward_embeds)
+    def _adv_embs(self, query_ids, attention_mask_q, input_ids_a, attention_mask_a, input_ids_embed_b, attention_mask_b):
+        q_embs = self.query_emb(query_ids, attention_mask_q)
+        a_embs = self.body_emb(input_ids_a, attention_mask_a)
+        _, b_embs, _ = self.ctx_model(inputs_embeds=input_ids_embed_b, attention_mask=attention_mask_b, _want_sequence=False)
+        return q_embs, a_embs, b_embs
 
-    forward_adv_pairloss = forward_adv_triplet
-    forward_adv_pairloss_mse = forward_adv_triplet
+    def forward_adv_triplet(self, query_ids, attention_mask_q, input_ids_a=None, attention_mask_a=None,
+                            input_ids_embed_b=None, attention_mask_b=None):
+        q_embs, a_embs, b_embs = self._adv_embs(query_ids, attention_mask_q, input_ids_a, attention_mask_a,
+                                                input_ids_embed_b, attention_mask_b)
+        logit_matrix = torch.cat([(q_embs * a_embs).sum(-1).unsqueeze(1), (q_embs * b_embs).sum(-1).unsqueeze(1)], dim=1)
+        lsm = F.log_softmax(logit_matrix, dim=1)
+        loss = -1.0 * lsm[:, 0]
+        return (loss.mean(),)
+
+    def _adv_pair_logits(self, *args):
+        q_embs, a_embs, b_embs = self._adv_embs(*args)
+        question_num = q_embs.size(0)
+        neg_local_ctx_vectors = b_embs.reshape(question_num, b_embs.size(0) // question_num, -1)
+        neg_simila = torch.einsum("bh,bdh->bd", [q_embs, neg_local_ctx_vectors])
+        pos_simil = (q_embs * a_embs).sum(-1).unsqueeze(1)
+        return pos_simil, neg_simila
+
+    def forward_adv_pairloss(self, query_ids, attention_mask_q, input_ids_a=None, attention_mask_a=None,
+                             input_ids_embed_b=None, attention_mask_b=None):
+        pos_simil, neg_simila = self._adv_pair_logits(query_ids, attention_mask_q, input_ids_a, attention_mask_a,
+                                                      input_ids_embed_b, attention_mask_b)
+        lsm = F.log_softmax(torch.cat([pos_simil, neg_simila], dim=1), dim=1)
+        loss = -1.0 * lsm[:, 1]  # column 1, as in the reference (:144)
+        return (loss.mean(), lsm)
+
+    def forward_adv_pairloss_mse(self, query_ids, attention_mask_q, input_ids_a=None, attention_mask_a=None,
+                                 input_ids_embed_b=None, attention_mask_b=None):
+        pos_simil, neg_simila = self._adv_pair_logits(query_ids, attention_mask_q, input_ids_a, attention_mask_a,
+                                                      input_ids_embed_b, attention_mask_b)
+        loss = nn.MSELoss()(neg_simila, pos_simil)
+        return (loss.mean(), 0)
 
 
 class Reranker(nn.Module):

@@ -76,3 +76,80 @@ def test_lead_reranker_per_layer_logits_forward_backward():
     grads["qa_classifier.weight"] = np.einsum("nl,nlh->h", d_logit, cls[:, 1:])[None]
     grads["qa_classifier.bias"] = d_logit.sum().reshape(1)
     assert_grads(model, grads, 2e-4)
+
+
+def test_inputs_embeds_and_forward_adv_paths_vs_oracle():
+    """`inputs_embeds=` through the kernels (simx_encoder_forward_embeds / _backward_embeds) and the three forward_adv_*
+    methods of BiBertEncoder (SimANS/model/models.py:120-160) built on it: values and gradients — including the gradient
+    with respect to the supplied embeddings — against the oracle."""
+    import torch.nn.functional as F
+    from simxns_b200.models import BiBertEncoder
+    from test_gpu_parity import build
+
+    cfg = bn.bert_config(num_layers=2, hidden=128, heads=2, intermediate=256, vocab=300, max_pos=64)
+    pq, pc = bn.synth_params(cfg, seed=31), bn.synth_params(cfg, seed=32)
+    nq, nneg, S = 3, 2, 24
+    q_ids, q_mask = bn.synth_tokens(nq, 12, cfg["vocab"], seed=1, ragged=True)
+    a_ids, a_mask = bn.synth_tokens(nq, S, cfg["vocab"], seed=2, ragged=True, min_len=6)
+    b_ids, b_mask = bn.synth_tokens(nq * nneg, S, cfg["vocab"], seed=3, ragged=True, min_len=6)
+    rng = np.random.RandomState(4)
+    b_emb = (pc["embeddings.word_embeddings.weight"][b_ids] + 0.01 * rng.standard_normal((nq * nneg, S, 128))).astype(np.float32)
+
+    model = BiBertEncoder(None, question_model=build(cfg, pq, X3), ctx_model=build(cfg, pc, X3))
+    # plain encode with inputs_embeds == word rows reproduces the id path bit for bit
+    ctx = model.ctx_model
+    with torch.no_grad():
+        via_ids, _ = ctx.encode(cu(b_ids), cu(b_mask))
+        via_emb, _ = ctx.encode(None, cu(b_mask), inputs_embeds=ctx.embeddings.word_embeddings.weight[cu(b_ids)])
+    assert torch.equal(via_ids, via_emb)
+
+    # oracle for the pair loss: -log_softmax([pos, negs])[:, 1]
+    oq, oa, ob = bn.EncoderOracle(cfg, pq), bn.EncoderOracle(cfg, pc), bn.EncoderOracle(cfg, pc)
+    q = oq.forward(q_ids, q_mask)["cls"][:, -1]
+    a = oa.forward(a_ids, a_mask)["cls"][:, -1]
+    b = ob.forward(None, b_mask, inputs_embeds=b_emb)["cls"][:, -1]
+    bb = b.reshape(nq, nneg, -1)
+    logits = np.concatenate([(q * a).sum(-1, keepdims=True), np.einsum("bh,bdh->bd", q, bb)], axis=1)
+    z = logits - logits.max(1, keepdims=True)
+    lsm = z - np.log(np.exp(z).sum(1, keepdims=True))
+    loss_ref = float(-lsm[:, 1].mean())
+    dlog = np.exp(lsm)
+    dlog[:, 1] -= 1.0
+    dlog /= nq
+    dq = dlog[:, :1] * a + np.einsum("bd,bdh->bh", dlog[:, 1:], bb)
+    da = dlog[:, :1] * q
+    db = (dlog[:, 1:, None] * q[:, None, :]).reshape(nq * nneg, -1)
+
+    def dcls(d):
+        out = np.zeros((d.shape[0], 3, 128))
+        out[:, -1] = d
+        return out
+
+    gq = oq.backward(d_cls=dcls(dq))
+    ga = oa.backward(d_cls=dcls(da))
+    gb = ob.backward(d_cls=dcls(db))
+    gc = {k: ga[k] + gb[k] for k in ga}
+
+    emb_t = cu(b_emb).requires_grad_(True)
+    loss, lsm_t = model.forward_adv_pairloss(cu(q_ids), cu(q_mask), cu(a_ids), cu(a_mask), emb_t, cu(b_mask))
+    assert abs(loss.item() - loss_ref) < 1e-5
+    assert max_rel(lsm_t.detach().cpu().numpy(), lsm) < 1e-5
+    loss.backward()
+    assert_grads(model.question_model, gq, 2e-4)
+    assert_grads(model.ctx_model, gc, 2e-4)
+    assert max_rel(emb_t.grad.cpu().numpy(), ob.d_inputs_embeds) < 2e-4
+    # padded positions of the supplied embeddings still receive the LayerNorm-path gradient of their own (masked) token:
+    # it must be finite and, for tokens no query attends to, independent of the loss only through zero cotangent rows
+    assert torch.isfinite(emb_t.grad).all()
+
+    # the two sibling methods: same embeddings, their own loss heads (checked against torch on the kernel's embeddings)
+    with torch.no_grad():
+        (l3,) = model.forward_adv_triplet(cu(q_ids), cu(q_mask), cu(a_ids), cu(a_mask), cu(b_emb[::nneg].copy()), cu(b_mask[::nneg].copy()))
+        l2, zero = model.forward_adv_pairloss_mse(cu(q_ids), cu(q_mask), cu(a_ids), cu(a_mask), cu(b_emb), cu(b_mask))
+    b1 = ob.forward(None, b_mask[::nneg], inputs_embeds=b_emb[::nneg])["cls"][:, -1]
+    lm = np.stack([(q * a).sum(-1), (q * b1).sum(-1)], 1)
+    lm = lm - lm.max(1, keepdims=True)
+    want3 = float(-(lm - np.log(np.exp(lm).sum(1, keepdims=True)))[:, 0].mean())
+    assert abs(l3.item() - want3) < 1e-5
+    want2 = float(((logits[:, 1:] - logits[:, :1]) ** 2).mean())
+    assert abs(l2.item() - want2) < 1e-4 * max(1.0, want2) and zero == 0
