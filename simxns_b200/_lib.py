@@ -23,6 +23,7 @@ EPI_PLAIN, EPI_BIAS, EPI_BIAS_GELU, EPI_BIAS_ADD, EPI_MUL, EPI_ADD, EPI_ATOMIC_F
 
 LOSS_NLL_GLOBAL, LOSS_KL_LOCAL, LOSS_CE_LOCAL, LOSS_KD_LOCAL, LOSS_NLL_LOCAL, LOSS_ADV_LOCAL = 1, 2, 4, 8, 16, 32
 LOSS_MSE_LOCAL, LOSS_DKD_LOCAL = 64, 128
+LOSS_GLOBAL_UNFUSED = 256
 
 
 class EncoderCfg(C.Structure):

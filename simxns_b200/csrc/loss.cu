@@ -7,6 +7,8 @@
 //    runs S = Q C^T, dQ = dS C and dC = dS^T Q on the tcgen05 GEMM in fp32-class (3-plane) precision, with one
 //    row kernel in between doing log-sum-exp, NLL, arg-max and dS = (softmax - onehot) / GQ in place.
 // Gradients reach only the local rows/columns; remote slices are constants (LEAD/util.py:200-204).
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "ptx.cuh"
 
@@ -14,6 +16,20 @@ namespace simx {
 
 int convert_weight(int np, const float* w, int R, int C, bf16* dst, long ld_dst, long ps_dst, bf16* dst_t, long ld_t,
                    long ps_t, cudaStream_t st);
+// loss_fused.cu: the global InfoNCE as one cooperative launch (no score matrix in memory)
+size_t nll_fused_workspace_bytes(int GQ, int GC);
+int nll_global_fused(const simx_loss_cfg* cfg, const float* Q, const float* C, const int32_t* pos_idx, float* out_losses,
+                     float* dQ, float* dC, void* workspace, cudaStream_t st);
+// SIMX_LOSS_UNFUSED=1: the round-1 path (tcgen05 score GEMM in split-bf16 planes, S and dS in memory, two gradient GEMMs) —
+// kept as the checker of the fused kernel
+static bool use_unfused_global_loss() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("SIMX_LOSS_UNFUSED");
+    v = (e != nullptr && e[0] == '1') ? 1 : 0;
+  }
+  return v == 1;
+}
 
 constexpr int MAX_GROUP = 64;
 
@@ -257,6 +273,8 @@ static LossWs loss_ws(const simx_loss_cfg* c) {
     w.ctp = off; off += align256(3ull * GCp * c->H * 2);
     w.s = off;   off += align256(4ull * c->GQ * GCp);
     w.ds = off;  off += align256(3ull * c->GQ * GCp * 2);
+    if (!use_unfused_global_loss() && !(c->terms & SIMX_LOSS_GLOBAL_UNFUSED))
+      off = nll_fused_workspace_bytes(c->GQ, c->GC);  // the fused kernel's small tables only
   }
   w.total = off + 256;
   return w;
@@ -601,7 +619,8 @@ extern "C" int simx_score_loss(const simx_loss_cfg* cfg, const float* Q, const f
              "score_loss: local passage range [%d,+%d) outside GC=%d", cfg->c_begin, cfg->c_count, cfg->GC);
   const int local_terms = cfg->terms & (SIMX_LOSS_KL_LOCAL | SIMX_LOSS_CE_LOCAL | SIMX_LOSS_KD_LOCAL | SIMX_LOSS_NLL_LOCAL |
                                         SIMX_LOSS_ADV_LOCAL | SIMX_LOSS_MSE_LOCAL | SIMX_LOSS_DKD_LOCAL);
-  SIMX_CHECK(cfg->terms != 0 && (cfg->terms & ~255) == 0, SIMX_ERR_INVALID, "score_loss: bad terms mask %d", cfg->terms);
+  SIMX_CHECK((cfg->terms & 255) != 0 && (cfg->terms & ~511) == 0, SIMX_ERR_INVALID, "score_loss: bad terms mask %d", cfg->terms);
+  const bool unfused = use_unfused_global_loss() || (cfg->terms & SIMX_LOSS_GLOBAL_UNFUSED) != 0;
   if (local_terms) {
     SIMX_CHECK(cfg->group >= 1 && cfg->group <= MAX_GROUP && cfg->c_count == cfg->q_count * cfg->group,
                SIMX_ERR_INVALID, "score_loss: local terms need c_count == q_count * group, group <= %d", MAX_GROUP);
@@ -614,6 +633,11 @@ extern "C" int simx_score_loss(const simx_loss_cfg* cfg, const float* Q, const f
   bool have_grads = false;
   if (cfg->terms & SIMX_LOSS_NLL_GLOBAL) {
     SIMX_CHECK(pos_idx != nullptr && workspace != nullptr, SIMX_ERR_INVALID, "score_loss: NLL_GLOBAL needs pos_idx and workspace");
+  }
+  if ((cfg->terms & SIMX_LOSS_NLL_GLOBAL) && !unfused) {
+    SIMX_TRY(nll_global_fused(cfg, Q, C, pos_idx, out_losses, dQ, dC, workspace, st));
+    have_grads = true;
+  } else if (cfg->terms & SIMX_LOSS_NLL_GLOBAL) {
     SIMX_CHECK(cfg->c_begin % 8 == 0, SIMX_ERR_INVALID,
                "score_loss: c_begin=%d must be a multiple of 8 (ranks contribute multiples of 8 passages)", cfg->c_begin);
     const LossWs w = loss_ws(cfg);

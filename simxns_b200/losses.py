@@ -63,6 +63,8 @@ class _ScoreLossFn(torch.autograd.Function):
             for t in opts["terms"]:
                 terms |= _TERMS[t]
             use_global = bool(terms & _lib.LOSS_NLL_GLOBAL)
+            if opts.get("unfused_check"):
+                terms |= _lib.LOSS_GLOBAL_UNFUSED
             rank, world = 0, 1
             if use_global and opts.get("gather", True) and dist.is_available() and dist.is_initialized():
                 rank, world = dist.get_rank(opts.get("group")), dist.get_world_size(opts.get("group"))
@@ -114,11 +116,12 @@ class _ScoreLossFn(torch.autograd.Function):
 def fused_score_loss(q_local: torch.Tensor, c_local: torch.Tensor, terms: Sequence[str], *, teacher=None, pos_idx=None,
                      weights: Optional[dict] = None, temperature: float = 1.0, eps: float = 1e-7,
                      score_scale: float = 1.0, group_size: Optional[int] = None, gather: bool = True, group=None,
-                     dkd_alpha: float = 1.0, dkd_beta: float = 1.0):
-    """-> (loss scalar with autograd into q_local / c_local, detail tensor [12] = LOSS_FIELDS + pad)"""
+                     dkd_alpha: float = 1.0, dkd_beta: float = 1.0, unfused_check: bool = False):
+    """-> (loss scalar with autograd into q_local / c_local, detail tensor [12] = LOSS_FIELDS + pad).
+    unfused_check: evaluate the global term through the 3-GEMM checker path instead of the fused launch."""
     opts = dict(terms=tuple(terms), weights=dict(weights or {}), temperature=float(temperature), eps=float(eps),
                 score_scale=float(score_scale), group_size=group_size, gather=gather, group=group,
-                dkd_alpha=float(dkd_alpha), dkd_beta=float(dkd_beta))
+                dkd_alpha=float(dkd_alpha), dkd_beta=float(dkd_beta), unfused_check=bool(unfused_check))
     return _ScoreLossFn.apply(q_local, c_local, teacher, pos_idx, opts)
 
 

@@ -153,3 +153,55 @@ def test_inputs_embeds_and_forward_adv_paths_vs_oracle():
     assert abs(l3.item() - want3) < 1e-5
     want2 = float(((logits[:, 1:] - logits[:, :1]) ** 2).mean())
     assert abs(l2.item() - want2) < 1e-4 * max(1.0, want2) and zero == 0
+
+
+@pytest.mark.parametrize("GQ,GC,H,q_begin,q_count,c_begin,c_count", [
+    (5, 37, 64, 0, 5, 0, 37),              # tiny, nothing aligned to the tile edge
+    (130, 1000, 128, 3, 70, 8, 504),       # ranges straddling 64-wide tiles, ragged tails in both dimensions
+    (256, 4096, 768, 64, 64, 1024, 1024),  # the 64-wide instantiation, several row tiles
+    (1024, 16384, 768, 256, 128, 4096, 2048),  # BASELINE configs[2] full size (128-wide tiles), rank 2 of 8
+])
+def test_fused_global_nll_launch_vs_unfused_checker_and_oracle(GQ, GC, H, q_begin, q_count, c_begin, c_count):
+    """the single cooperative launch (csrc/loss_fused.cu) against (1) the round-1 path kept as its checker (tcgen05 score
+    GEMM + row kernel + two gradient GEMMs, SIMX_LOSS_GLOBAL_UNFUSED) and (2) the fp64 oracle: loss, hit count, dQ, dC"""
+    import ctypes as C
+    rng = np.random.RandomState(GQ + GC)
+    Q = (rng.standard_normal((GQ, H)) * (4.0 / np.sqrt(H))).astype(np.float32)
+    Cm = (rng.standard_normal((GC, H)) * (4.0 / np.sqrt(H))).astype(np.float32)
+    pos = rng.randint(0, GC, size=GQ).astype(np.int32)
+    Cm[pos[: GQ // 2]] += 0.5 * Q[: GQ // 2]  # make about half of the positives win their row
+    lib = _lib.lib()
+    tq, tc, tp = cu(Q), cu(Cm), cu(pos)
+    res = {}
+    for name, extra in (("fused", 0), ("unfused", _lib.LOSS_GLOBAL_UNFUSED)):
+        if extra and c_begin % 8:
+            continue  # the checker path needs 8-aligned column offsets (TMA row pitch); the fused kernel does not
+        cfg = _lib.LossCfg(terms=_lib.LOSS_NLL_GLOBAL | extra, GQ=GQ, GC=GC, H=H, q_begin=q_begin, q_count=q_count,
+                           c_begin=c_begin, c_count=c_count, group=1, w_nll_global=0.7, temperature=1.0, eps=1e-7,
+                           score_scale=1.0, grad_scale=2.0)
+        ws = torch.empty(lib.simx_score_loss_workspace_bytes(C.byref(cfg)), dtype=torch.uint8, device="cuda")
+        out = torch.empty(12, device="cuda")
+        dQ, dC = torch.full((q_count, H), 7.0, device="cuda"), torch.full((c_count, H), 7.0, device="cuda")
+        _lib.check(lib.simx_score_loss(C.byref(cfg), tq.data_ptr(), tc.data_ptr(), tp.data_ptr(), None, out.data_ptr(),
+                                       dQ.data_ptr(), dC.data_ptr(), ws.data_ptr(), torch.cuda.current_stream().cuda_stream),
+                   "simx_score_loss")
+        res[name] = (out.cpu().numpy(), dQ.cpu().numpy(), dC.cpu().numpy(), ws.numel())
+    # oracle (fp64): full matrices, then this rank's slices
+    S = Q.astype(np.float64) @ Cm.astype(np.float64).T
+    m = S.max(1, keepdims=True)
+    lse = m + np.log(np.exp(S - m).sum(1, keepdims=True))
+    nll = float((lse[:, 0] - S[np.arange(GQ), pos]).mean())
+    dS = np.exp(S - lse)
+    dS[np.arange(GQ), pos] -= 1.0
+    dS *= 0.7 * 2.0 / GQ
+    want_dQ = dS[q_begin:q_begin + q_count] @ Cm.astype(np.float64)
+    want_dC = dS[:, c_begin:c_begin + c_count].T @ Q.astype(np.float64)
+    hits = float((S.argmax(1) == pos).sum())
+    out, dQ, dC, ws_bytes = res["fused"]
+    assert abs(out[1] - nll) < 1e-4 and abs(out[0] - 0.7 * nll) < 1e-4 and out[6] == hits
+    assert max_rel(dQ, want_dQ) < 1e-4 and max_rel(dC, want_dC) < 1e-4
+    assert ws_bytes < 0.05 * 4 * GQ * GC + 4096, "the fused path must not reserve room for the score matrix"
+    if "unfused" in res:
+        o2, dQ2, dC2, _ = res["unfused"]
+        assert abs(o2[1] - out[1]) < 1e-5 and o2[6] == out[6]
+        assert max_rel(dQ, dQ2) < 1e-4 and max_rel(dC, dC2) < 1e-4
