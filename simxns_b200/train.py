@@ -59,8 +59,11 @@ def _unwrap(model):
 
 def _finish(args, model, optimizer, scheduler, step: int) -> Optional[torch.Tensor]:
     """:246-263 — every `gradient_accumulation_steps` micro-steps: clip, optimizer.step, scheduler.step, zero_grad.
-    The clip is folded into the fused AdamW launch (the norm never visits the host); returns the gradient norm."""
-    if step % args.gradient_accumulation_steps != 0:
+    The clip is folded into the fused AdamW launch (the norm never visits the host); returns the gradient norm.
+    The reference tests `(step + 1) % gradient_accumulation_steps == 0` with `step` counted from 1 (:192, :246): with the
+    shipped MS-Pas setting of 2 (train_MS_Pas_AR2.sh:11) the optimizer steps after micro-steps 1, 3, 5, ... — the first
+    update sees a single micro-batch.  Kept as is: same updates as the reference driver."""
+    if (step + 1) % args.gradient_accumulation_steps != 0:
         return None
     if isinstance(optimizer, sx_optim.AdamW):
         optimizer.step(max_grad_norm=args.max_grad_norm)

@@ -94,7 +94,7 @@ def test_retriever_steps_match_reference_loop_with_oracle_optimizer():
     sched = get_linear_schedule_with_warmup(opt, WARM, TOTAL)
     assert [len(g["params"]) for g in opt.param_groups] == [2 * (3 + 6 * 2 + 1), 2 * (2 + 10 * 2 + 1)]  # decay / no-decay
     state, updates = {}, 0
-    for step, batch in enumerate(make_batches(4), 1):
+    for step, batch in enumerate(make_batches(5), 1):
         out = retriever_step(ARGS, model, None, batch, opt, sched, step)
         # the reference's lines (co_training_marco_train.py:198-222) on the twin model
         ref.train()
@@ -105,7 +105,7 @@ def test_retriever_steps_match_reference_loop_with_oracle_optimizer():
         distill = torch.nn.KLDivLoss(reduction="batchmean")((p_s + 1e-7).log(), p_t)
         (distill / ARGS.gradient_accumulation_steps).backward()
         assert abs(out["distill_loss"].item() - distill.item()) < 1e-4
-        if step % ARGS.gradient_accumulation_steps == 0:
+        if (step + 1) % ARGS.gradient_accumulation_steps == 0:  # the reference's test (:246): micro-steps 1, 3, 5
             updates += 1
             oracle_tail(ref, state, updates, lr_at(updates - 1))
             assert out["grad_norm"] is not None and out["grad_norm"].item() > ARGS.max_grad_norm  # the clip was active
@@ -113,7 +113,7 @@ def test_retriever_steps_match_reference_loop_with_oracle_optimizer():
             assert all(p.grad is None or float(p.grad.abs().max()) == 0.0 for p in model.parameters())
         else:
             assert out["grad_norm"] is None
-    assert updates == 2 and abs(opt.param_groups[0]["lr"] - lr_at(2)) < 1e-12
+    assert updates == 3 and abs(opt.param_groups[0]["lr"] - lr_at(3)) < 1e-12
 
 
 def test_teacher_steps_match_reference_loop_with_oracle_optimizer():
