@@ -97,12 +97,12 @@ __device__ __forceinline__ void epi_prefetch(const GemmParams& p, int row, int c
 // results (3e-3 rms); the fp32-class mode keeps the exact erf path below.
 __device__ __forceinline__ void gelu_pair_f16(float x0, float x1, uint32_t& g_out, uint32_t& dg_out) {
   const __half2 x = __floats2half2_rn(x0, x1);
-  const __half2 lim = __float2half2_rn(8.0f);
-  const __half2 xc = __hmax2(__hmin2(x, lim), __hneg2(lim));  // the odd polynomial is only monotone on [-8, 8]
-  const __half2 x2 = __hmul2(xc, xc);
+  // the odd polynomial u(x) is only monotone on [-8, 8]: clamp x^2 (one instruction instead of a two-sided clamp of x);
+  // beyond 8 the polynomial factor freezes, u = x p(64) keeps growing linearly and tanh saturates: Phi -> 0 / 1, gelu' -> Phi
+  const __half2 x2 = __hmin2(__hmul2(x, x), __float2half2_rn(64.0f));
   __half2 p = __hfma2(x2, __float2half2_rn(-3.47550486e-04f), __float2half2_rn(3.70038725e-02f));
   p = __hfma2(x2, p, __float2half2_rn(7.97422816e-01f));
-  const __half2 u = __hmul2(xc, p);
+  const __half2 u = __hmul2(x, p);
   uint32_t tu;
   asm("tanh.approx.f16x2 %0, %1;" : "=r"(tu) : "r"(*reinterpret_cast<const uint32_t*>(&u)));
   const __half2 t = *reinterpret_cast<const __half2*>(&tu);
@@ -112,7 +112,8 @@ __device__ __forceinline__ void gelu_pair_f16(float x0, float x1, uint32_t& g_ou
   const __half2 w = __hfma2(__hneg2(t), t, __float2half2_rn(1.0f));  // 1 - tanh^2
   __half2 q = __hfma2(x2, __float2half2_rn(2.5f * -3.47550486e-04f), __float2half2_rn(1.5f * 3.70038725e-02f));
   q = __hfma2(x2, q, __float2half2_rn(0.5f * 7.97422816e-01f));      // 0.5 u'
-  const __half2 dg = __hfma2(__hmul2(xc, w), q, phi);
+  // |x| > 8: tanh is saturated (t = +-1 exactly in f16), w = 0 and the product vanishes for every finite x
+  const __half2 dg = __hfma2(__hmul2(x, w), q, phi);
   const float2 gf = __half22float2(g), df = __half22float2(dg);
   g_out = pack_bf16x2(gf.x, gf.y);
   dg_out = pack_bf16x2(df.x, df.y);
@@ -120,12 +121,10 @@ __device__ __forceinline__ void gelu_pair_f16(float x0, float x1, uint32_t& g_ou
 // forward-only variant (inference): gelu alone, same tanh-form fit
 __device__ __forceinline__ uint32_t gelu_only_pair_f16(float x0, float x1) {
   const __half2 x = __floats2half2_rn(x0, x1);
-  const __half2 lim = __float2half2_rn(8.0f);
-  const __half2 xc = __hmax2(__hmin2(x, lim), __hneg2(lim));
-  const __half2 x2 = __hmul2(xc, xc);
+  const __half2 x2 = __hmin2(__hmul2(x, x), __float2half2_rn(64.0f));  // see gelu_pair_f16
   __half2 p = __hfma2(x2, __float2half2_rn(-3.47550486e-04f), __float2half2_rn(3.70038725e-02f));
   p = __hfma2(x2, p, __float2half2_rn(7.97422816e-01f));
-  const __half2 u = __hmul2(xc, p);
+  const __half2 u = __hmul2(x, p);
   uint32_t tu;
   asm("tanh.approx.f16x2 %0, %1;" : "=r"(tu) : "r"(*reinterpret_cast<const uint32_t*>(&u)));
   const __half2 t = *reinterpret_cast<const __half2*>(&tu);

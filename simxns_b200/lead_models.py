@@ -48,14 +48,32 @@ class HFBertEncoder(_m.HFBertEncoder):
 
 
 class HFDistilBertEncoder(_m.HFDistilBertEncoder):
-    """LEAD/models.py:31-77 (add_linear is not supported: the shipped scripts do not set it)"""
+    """LEAD/models.py:31-77.  `config.add_linear` (--add_linear): an extra `linear = nn.Linear(hidden, 768)` on the last
+    hidden state; its output becomes the sequence / pooled output and is appended to the per-layer stack as one more
+    "layer" (models.py:64-70) — here applied to the [CLS] rows, the only rows LEAD's losses read."""
 
     def __init__(self, config, precision: Optional[int] = None):
-        if getattr(config, "add_linear", False):
-            raise NotImplementedError("add_linear=True (extra projection on the student) is not implemented")
         super().__init__(config, precision)
+        self.add_linear = bool(getattr(config, "add_linear", False))
+        if self.add_linear:
+            self.linear = nn.Linear(self.enc_cfg.hidden, 768)
+            _m.init_weights([self.linear])
 
-    forward = HFBertEncoder.forward
+    def forward(self, input_ids=None, attention_mask=None, output_attentions=None, **kwargs):
+        if output_attentions:
+            raise NotImplementedError("attention maps (LEAD VIRT losses) are not produced by the fused attention kernel")
+        want_seq = kwargs.pop("_want_sequence", False)
+        cls, seq = self.encode(input_ids, attention_mask, want_sequence=want_seq)
+        pooled_output = cls[:, -1, :]
+        all_layer_hidden = cls[:, 1:, None, :]
+        if self.add_linear:
+            if seq is not None:
+                seq = self.linear(seq)
+            pooled_output = self.linear(pooled_output)
+            if self.enc_cfg.hidden != 768:
+                raise NotImplementedError("add_linear with hidden != 768: the appended layer has another width than the stack")
+            all_layer_hidden = torch.cat([all_layer_hidden, pooled_output[:, None, None, :]], dim=1)  # [B, L+1, 1, 768]
+        return seq, pooled_output, None, None, all_layer_hidden
 
 
 class BiBertEncoder(nn.Module):

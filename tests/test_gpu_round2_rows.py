@@ -205,3 +205,23 @@ def test_fused_global_nll_launch_vs_unfused_checker_and_oracle(GQ, GC, H, q_begi
         o2, dQ2, dC2, _ = res["unfused"]
         assert abs(o2[1] - out[1]) < 1e-5 and o2[6] == out[6]
         assert max_rel(dQ, dQ2) < 1e-4 and max_rel(dC, dC2) < 1e-4
+
+
+def test_lead_distilbert_add_linear_appends_projected_layer():
+    """--add_linear (LEAD/models.py:31-77): `linear(hidden -> 768)` on the last hidden state becomes the pooled output and one
+    more entry of the per-layer stack; gradients reach the projection and the tower"""
+    from types import SimpleNamespace
+    cfg = SimpleNamespace(model_type="distilbert", n_layers=2, dim=768, n_heads=12, hidden_dim=1536, vocab_size=300,
+                          max_position_embeddings=64, dropout=0.0, attention_dropout=0.0, add_linear=True)
+    torch.manual_seed(0)
+    enc = lead_models.HFDistilBertEncoder(cfg, precision=X3).cuda()
+    ids, mask = bn.synth_tokens(4, 20, 300, seed=2, ragged=True)
+    seq, pooled, _, _, layers = enc(input_ids=cu(ids), attention_mask=cu(mask), _want_sequence=True)
+    assert tuple(layers.shape) == (4, 3, 1, 768) and tuple(pooled.shape) == (4, 768) and tuple(seq.shape) == (4, 20, 768)
+    assert torch.equal(layers[:, -1, 0], pooled)
+    raw = enc.last_cls_layers if hasattr(enc, "last_cls_layers") else None
+    want = torch.nn.functional.linear(layers[:, 1, 0], enc.linear.weight, enc.linear.bias)  # layer index 1 = last transformer layer
+    assert torch.allclose(pooled, want, rtol=1e-5, atol=1e-6)
+    assert torch.allclose(seq[:, 0], pooled, rtol=1e-4, atol=1e-5)
+    (pooled.square().sum() + layers[:, 0].sum()).backward()
+    assert enc.linear.weight.grad.abs().max() > 0 and enc.transformer.layer[0].ffn.lin1.weight.grad.abs().max() > 0
