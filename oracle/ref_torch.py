@@ -3,7 +3,7 @@
 The reference's train step as the reference itself runs it on a CPU: its thin wrapper classes restated over the
 installed `transformers.BertModel` (the un-vendored dependency that holds the reference's arithmetic), PyTorch CPU
 ops, all host threads.  /root/reference does not exist on the GPU box, so these ~40 lines are a "port"
-(`cpu_baseline.kind = "port"`); in the build container tests/test_ref_torch_matches_reference.py checks them against
+(`cpu_baseline.kind = "port"`); in the build container tests/test_ref_torch_port.py checks them against
 the real classes imported from /root/reference.
 
   HFBertEncoderRef  <- /root/reference/SimANS/model/models.py:58-82
