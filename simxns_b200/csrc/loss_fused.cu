@@ -185,7 +185,7 @@ __device__ __forceinline__ void red_add4(float* p, float a, float b, float c, fl
 }
 
 template <int TM>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256)  // one CTA per SM at 187 registers (capping at 128 for two CTAs/SM spills: 2.93 vs 2.60 ms)
 nll_global_fused_kernel(const FusedNllParams p) {
   using T = FusedTile<TM>;
   constexpr int BT = T::BT, LD = T::LD;
