@@ -440,7 +440,10 @@ class _TowerPass:
             self.d_seq = d_seq.to(torch.float32).contiguous() if (d_seq is not None and self.want_seq) else None
             self.ws = torch.empty(lib.simx_encoder_workspace_bytes(C.byref(self.cfg), B, S), dtype=torch.uint8,
                                   device=self.dev)
-            self.flat = torch.empty(lib.simx_encoder_grad_numel(C.byref(self.cfg)), dtype=torch.float32, device=self.dev)
+            numel = lib.simx_encoder_grad_numel(C.byref(self.cfg))
+            # a sharded gradient exchange (gradsync.FlatGradSync(shard=True)) reduce-scatters equal chunks: room for the tail pad
+            self.flat = torch.empty(max(numel, int(getattr(self.module, "_flat_padded_numel", 0))), dtype=torch.float32,
+                                    device=self.dev)
         return True
 
     def run_slice(self, lo: int, hi: int) -> None:

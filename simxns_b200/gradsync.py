@@ -16,6 +16,12 @@ Same contract as DDP for the loop body: gradients are averaged over ranks and re
 order), `model.module` is the wrapped module, parameters are broadcast from rank 0 at construction, gradient accumulation
 over micro-steps adds.  `compress="bf16"` halves the bytes on the wire (gradients are rounded to bf16 for the exchange
 only — a deviation from the reference's fp32 all-reduce, off by default).
+
+`shard=True` (second half) turns the exchange into ZeRO-1 over the same flat layout: each tower's parameters
+are moved into ONE flat fp32 buffer laid out like its gradient buffer (`p.data` become views: names, shapes and
+`state_dict()` are unchanged), the gradient buffer is REDUCE-SCATTERED in place (rank r ends up with the averaged chunk r
+only), `optim.ShardedAdamW` updates chunk r of the parameters with rank-local Adam moments (1/world of the optimizer state
+and of the update work) and all-gathers the flat parameter buffer in place.  Tower parameters then carry no `.grad`.
 """
 from __future__ import annotations
 
@@ -29,16 +35,21 @@ from .encoder import B200EncoderBase
 
 
 class FlatGradSync(nn.Module):
-    def __init__(self, module: nn.Module, process_group=None, compress: Optional[str] = None, broadcast: bool = True):
+    def __init__(self, module: nn.Module, process_group=None, compress: Optional[str] = None, broadcast: bool = True,
+                 shard: bool = False):
         super().__init__()
         if not (dist.is_available() and dist.is_initialized()):
             raise RuntimeError("FlatGradSync needs an initialised torch.distributed process group")
         if compress not in (None, "bf16"):
             raise ValueError("compress must be None or 'bf16'")
+        if shard and compress:
+            raise ValueError("shard=True exchanges fp32 chunks; compress is not combined with it")
         self.module = module
         self.group = process_group
         self.compress = compress
+        self.shard = bool(shard)
         self.world = dist.get_world_size(process_group)
+        self.rank = dist.get_rank(process_group)
         self._towers: List[B200EncoderBase] = []
         seen = set()
         tower_params = set()
@@ -59,6 +70,27 @@ class FlatGradSync(nn.Module):
                                    group=process_group)
             for m in self._towers:
                 m.invalidate_weights()
+        if self.shard:
+            for m in self._towers:
+                self._flatten_tower(m)
+
+    # ---- shard=True: parameters of a tower live in one flat buffer with the layout of its gradient buffer -----------
+    def _flatten_tower(self, tower: B200EncoderBase) -> None:
+        slices = tower.grad_slices()
+        numel = max(off + n for off, n in slices)
+        chunk = (-(-numel // self.world) + 63) // 64 * 64          # per-rank chunk, a multiple of 64 elements
+        padded = chunk * self.world
+        params = tower.ordered_parameters()
+        flat = torch.zeros(padded, dtype=torch.float32, device=params[0].device)
+        with torch.no_grad():
+            for p, (off, n) in zip(params, slices):
+                flat[off:off + n].copy_(p.detach().reshape(-1))
+                p.data = flat[off:off + n].view(p.shape)
+        tower._flat_param = flat
+        tower._flat_padded_numel = padded
+        tower._shard_range = (self.rank * chunk, min((self.rank + 1) * chunk, numel), chunk)  # [lo, hi), chunk size
+        tower._grad_shard = None
+        tower.invalidate_weights()
 
     def forward(self, *args, **kwargs):
         return self.module(*args, **kwargs)
@@ -67,7 +99,13 @@ class FlatGradSync(nn.Module):
     def _sink(self, tower: B200EncoderBase, st) -> None:
         flat = st.flat
         work, wire = None, None
-        if self.world > 1:
+        if self.shard:
+            lo, _, chunk = tower._shard_range
+            padded = tower._flat_padded_numel
+            if self.world > 1:  # in place: rank r's chunk of the buffer receives the average of everybody's chunk r
+                work = dist.reduce_scatter_tensor(flat[lo:lo + chunk], flat[:padded], op=dist.ReduceOp.AVG, group=self.group,
+                                                  async_op=True)
+        elif self.world > 1:
             if self.compress == "bf16":
                 wire = flat.to(torch.bfloat16)
                 work = dist.all_reduce(wire, op=dist.ReduceOp.AVG, group=self.group, async_op=True)
@@ -87,6 +125,16 @@ class FlatGradSync(nn.Module):
                 work.wait()  # stream-level: the current stream waits for the collective, the host does not
             if wire is not None:
                 flat.copy_(wire)
+            if self.shard:  # keep this rank's chunk only (accumulated over micro-steps); tower parameters get no .grad
+                lo, _, chunk = tower._shard_range
+                mine = flat[lo:lo + chunk]
+                if tower._grad_shard is None:
+                    if getattr(tower, "_grad_shard_buf", None) is None:
+                        tower._grad_shard_buf = torch.empty_like(mine)  # persistent: the optimizer's kernel table keeps its address
+                    tower._grad_shard = tower._grad_shard_buf.copy_(mine)
+                else:
+                    tower._grad_shard.add_(mine)
+                continue
             for p, (off, n) in zip(params, tower.grad_slices()):
                 if not isinstance(p, nn.Parameter) or not p.requires_grad:
                     continue

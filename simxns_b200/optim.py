@@ -157,3 +157,127 @@ class AdamW(torch.optim.Optimizer):
         if touched:
             torch.autograd.graph.increment_version(touched)
         return loss
+
+
+class ShardedAdamW(AdamW):
+    """AdamW with the optimizer state and the update sharded over the data-parallel ranks (ZeRO-1) for models wrapped in
+    `gradsync.FlatGradSync(model, shard=True)` — the second half of SURVEY §8f N3 (the reference keeps a full replica of
+    exp_avg / exp_avg_sq on every GPU and all-reduces every gradient: co_training_marco_train.py:57-69, 107-114).
+
+    Per tower, rank r owns elements [lo, hi) of the flat parameter / gradient layout: `step()` builds the kernel table from
+    the intersections of that range with the parameter tensors (so every element keeps its parameter's lr / weight decay),
+    runs the same fused norm + AdamW kernels on 1/world of the elements with rank-local moments, and all-gathers the flat
+    parameter buffer in place.  The gradient norm for clipping is the global one (partial sums of squares are all-reduced).
+    Parameters outside the towers (a reranker head) are updated on every rank as usual.  `param_groups` (and therefore LR
+    schedulers) behave as with `AdamW`; `state_dict()` holds this rank's shard of the moments only."""
+
+    def __init__(self, sync, params, lr: float = 1e-3, betas=(0.9, 0.999), eps: float = 1e-6, weight_decay: float = 0.0,
+                 correct_bias: bool = True, flavor: str = "hf"):
+        super().__init__(params, lr=lr, betas=betas, eps=eps, weight_decay=weight_decay, correct_bias=correct_bias,
+                         flavor=flavor)
+        if not getattr(sync, "shard", False):
+            raise ValueError("ShardedAdamW needs gradsync.FlatGradSync(model, shard=True)")
+        self.sync = sync
+        self._step_count = 0
+        self._shards = {}  # id(tower) -> (exp_avg, exp_avg_sq) of this rank's chunk
+        self._tab_shard, self._tab_loose = _Table(), _Table()
+
+    @torch.no_grad()
+    def step(self, closure=None, max_grad_norm: Optional[float] = None):
+        import torch.distributed as dist
+
+        loss = None
+        if closure is not None:
+            with torch.enable_grad():
+                loss = closure()
+        lib = _lib.lib()
+        mode = _lib.ADAMW_HF if self.flavor == "hf" else _lib.ADAMW_TORCH
+        group_of = {}
+        for group in self.param_groups:
+            for p in group["params"]:
+                group_of[id(p)] = group
+        g0 = self.param_groups[0]
+        betas, eps, correct_bias = tuple(g0["betas"]), float(g0["eps"]), bool(g0.get("correct_bias", True))
+        for g in self.param_groups:
+            if (tuple(g["betas"]), float(g["eps"]), bool(g.get("correct_bias", True))) != (betas, eps, correct_bias):
+                raise NotImplementedError("ShardedAdamW: all groups must share betas / eps / correct_bias")
+        self._step_count += 1
+        rows, towers, dev = [], [], None
+        for tower in self.sync._towers:
+            if tower._grad_shard is None:
+                continue
+            lo, hi, chunk = tower._shard_range
+            dev = tower._flat_param.device
+            if id(tower) not in self._shards:
+                self._shards[id(tower)] = (torch.zeros(chunk, dtype=torch.float32, device=dev),
+                                           torch.zeros(chunk, dtype=torch.float32, device=dev))
+            m, v = self._shards[id(tower)]
+            for p, (off, n) in zip(tower.ordered_parameters(), tower.grad_slices()):
+                a, b = max(off, lo), min(off + n, hi)
+                group = group_of.get(id(p))
+                if a >= b or group is None or not p.requires_grad:
+                    continue
+                rows.append((tower._flat_param[a:b], tower._grad_shard[a - lo:b - lo], m[a - lo:b - lo], v[a - lo:b - lo],
+                             b - a, group["lr"], group["weight_decay"]))
+            towers.append(tower)
+        loose = []
+        for p in self.sync._loose:
+            group = group_of.get(id(p))
+            if p.grad is None or group is None:
+                continue
+            _check(p, "parameter")
+            _check(p.grad, "gradient")
+            state = self.state[p]
+            if not state:
+                state["exp_avg"] = torch.zeros_like(p, memory_format=torch.preserve_format)
+                state["exp_avg_sq"] = torch.zeros_like(p, memory_format=torch.preserve_format)
+            state["step"] = self._step_count
+            loose.append((p, p.grad, state["exp_avg"], state["exp_avg_sq"], p.numel(), group["lr"], group["weight_decay"]))
+            dev = p.device
+        if dev is None:
+            return loss
+        with torch.cuda.device(dev):
+            _lib.require_device()
+            st = torch.cuda.current_stream(dev).cuda_stream
+            sq = torch.zeros((), dtype=torch.float64, device=dev)
+            sq_ptr = None
+            tabs = []
+            if rows:
+                self._tab_shard.update(rows, dev)
+                tabs.append(self._tab_shard)
+            if loose:
+                self._tab_loose.update(loose, dev)
+                tabs.append(self._tab_loose)
+            if max_grad_norm is not None:
+                if rows:  # this rank's chunk of the global sum of squares; the chunks partition the towers
+                    _lib.check(lib.simx_grad_sq_norm(self._tab_shard.dev.data_ptr(), self._tab_shard.n, self._tab_shard.chunks,
+                                                     sq.data_ptr(), st), "simx_grad_sq_norm")
+                if self.sync.world > 1:
+                    dist.all_reduce(sq, group=self.sync.group)
+                if loose:  # replicated gradients: counted once
+                    sq_l = torch.zeros((), dtype=torch.float64, device=dev)
+                    _lib.check(lib.simx_grad_sq_norm(self._tab_loose.dev.data_ptr(), self._tab_loose.n, self._tab_loose.chunks,
+                                                     sq_l.data_ptr(), st), "simx_grad_sq_norm")
+                    sq += sq_l
+                self.last_grad_norm = sq.sqrt().to(torch.float32)
+                sq_ptr = sq.data_ptr()
+            for tab in tabs:
+                _lib.check(lib.simx_adamw_step(tab.dev.data_ptr(), tab.n, tab.chunks, mode, betas[0], betas[1], eps,
+                                               self._step_count, int(correct_bias), sq_ptr, float(max_grad_norm or 0.0), 0, st),
+                           "simx_adamw_step")
+            touched = [p for p, *_ in loose]
+            for tower in towers:  # every rank now needs everybody's updated chunk
+                lo, hi, chunk = tower._shard_range
+                if self.sync.world > 1:
+                    dist.all_gather_into_tensor(tower._flat_param[:tower._flat_padded_numel], tower._flat_param[lo:lo + chunk],
+                                                group=self.sync.group)
+                tower._grad_shard = None
+                touched.extend(p for p in tower.ordered_parameters() if isinstance(p, torch.nn.Parameter))
+        if touched:
+            torch.autograd.graph.increment_version(touched)
+        return loss
+
+    def zero_grad(self, set_to_none: bool = True):
+        super().zero_grad(set_to_none=set_to_none)
+        for tower in self.sync._towers:
+            tower._grad_shard = None

@@ -26,9 +26,11 @@ from .losses import simans_distill_loss
 
 
 def get_optimizer(args, model: nn.Module, weight_decay: float = 0.0, lr: float = 0.0, eps: float = 0.0,
-                  flavor: str = "hf") -> torch.optim.Optimizer:
+                  flavor: str = "hf", sync=None) -> torch.optim.Optimizer:
     """co_training_marco_train.py:57-69 — two groups, `bias` / `LayerNorm.weight` without decay; transformers.AdamW
-    semantics by default (`flavor="torch"` gives LEAD's torch.optim.AdamW, LEAD/util.py:889-901)."""
+    semantics by default (`flavor="torch"` gives LEAD's torch.optim.AdamW, LEAD/util.py:889-901).
+    sync: a `gradsync.FlatGradSync(model, shard=True)` wrapper -> the sharded optimizer (optimizer state / update split
+    over the ranks)."""
     no_decay = ['bias', 'LayerNorm.weight']
     optimizer_grouped_parameters = [
         {'params': [p for n, p in model.named_parameters() if p.requires_grad and not any(nd in n for nd in no_decay)],
@@ -38,6 +40,8 @@ def get_optimizer(args, model: nn.Module, weight_decay: float = 0.0, lr: float =
     ]
     if getattr(args, "optimizer", "adamW") != "adamW":
         raise Exception("optimizer {0} not recognized! Can only be adamW".format(args.optimizer))
+    if sync is not None:
+        return sx_optim.ShardedAdamW(sync, optimizer_grouped_parameters, lr=lr, eps=eps, flavor=flavor)
     return sx_optim.AdamW(optimizer_grouped_parameters, lr=lr, eps=eps, flavor=flavor)
 
 

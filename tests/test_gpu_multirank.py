@@ -37,4 +37,4 @@ def test_two_rank_nccl_parity():
     out_dir.mkdir(exist_ok=True)
     (out_dir / "multigpu_2rank.log").write_text(log)
     assert proc.returncode == 0, log[-4000:]
-    assert log.count(": OK") >= 5, log[-4000:]
+    assert log.count(": OK") >= 6, log[-4000:]

@@ -133,6 +133,51 @@ def main():
     if rank == 0:
         print(f"FlatGradSync == DistributedDataParallel (shared tower, reranker head, 2 accumulated micro-steps): worst {worst:.1e}: OK")
 
+    # ---- 2c. sharded optimizer (ZeRO-1 on the flat layout): FlatGradSync(shard=True) + ShardedAdamW == FlatGradSync + AdamW ----
+    from simxns_b200.train import get_optimizer
+    import types
+
+    oargs = types.SimpleNamespace(optimizer="adamW")
+
+    def train3(shard):
+        m = Both().to(dev)
+        w = FlatGradSync(m, shard=shard)
+        opt = get_optimizer(oargs, m, weight_decay=0.01, lr=1e-3, eps=1e-8, sync=w if shard else None)
+        norms = []
+        for step in range(3):
+            for micro in range(2):  # two accumulated micro-steps per update
+                q_ids, q_mask = bn.synth_tokens(nq, 12, ec.vocab, seed=900 + 20 * step + 10 * micro + rank, ragged=True)
+                p_ids, p_mask = bn.synth_tokens(nq * group, 24, ec.vocab, seed=950 + 20 * step + 10 * micro + rank, ragged=True,
+                                                min_len=6)
+                qe, ce, logits = w(t(q_ids), t(q_mask), t(p_ids), t(p_mask))
+                loss, _ = fused_score_loss(qe, ce, ["nll_global"], group_size=group, gather=True)
+                loss = loss + torch.nn.functional.cross_entropy(logits, torch.zeros(nq, dtype=torch.long, device=dev))
+                loss.backward()
+            opt.step(max_grad_norm=0.5)
+            norms.append(opt.last_grad_norm.item())
+            opt.zero_grad()
+        torch.cuda.synchronize()
+        state_bytes = sum(t_.numel() * 4 for st_ in opt.state.values() for t_ in st_.values() if torch.is_tensor(t_))
+        state_bytes += sum(a.numel() * 4 + b.numel() * 4 for a, b in getattr(opt, "_shards", {}).values())
+        return {n: p.detach().clone() for n, p in m.named_parameters()}, norms, state_bytes
+
+    p_full, n_full, b_full = train3(False)
+    p_shard, n_shard, b_shard = train3(True)
+    assert all(abs(a - b) < 1e-4 * max(1.0, abs(a)) for a, b in zip(n_full, n_shard)), (n_full, n_shard)
+    worst = 0.0
+    for n in p_full:
+        # Adam normalises: elements with ~zero gradient move by +-lr on round-off in either run; compare the bulk
+        d = (p_full[n] - p_shard[n]).abs()
+        worst = max(worst, d.mean().item() / 1e-3)
+    assert worst < 2e-2, f"sharded optimizer diverges from the replicated one: mean |dp| / lr = {worst:.2e}"
+    flat = torch.cat([p.reshape(-1) for p in p_shard.values()])
+    gathered = [torch.empty_like(flat) for _ in range(world)]
+    dist.all_gather(gathered, flat)
+    assert all(torch.equal(gathered[0], x) for x in gathered), "ranks diverged under the sharded optimizer"
+    if rank == 0:
+        print(f"ShardedAdamW (reduce-scatter + 1/{world} of the Adam state: {b_shard / 2**20:.1f} vs {b_full / 2**20:.1f} MiB per rank) == "
+              f"replicated AdamW after 3 clipped updates: gradient norms {['%.4f' % x for x in n_shard]}, mean |dp|/lr {worst:.1e}: OK")
+
     # ---- 3. the training configuration: dropout + gradient checkpointing + bf16 under DDP (ranks must stay in lock-step) ----
     torch.manual_seed(1)
     m2 = BiBertEncoder(None, question_model=HFBertEncoder(ec, precision=_lib.PREC_BF16),
