@@ -153,7 +153,7 @@ def main():
                 loss, _ = fused_score_loss(qe, ce, ["nll_global"], group_size=group, gather=True)
                 loss = loss + torch.nn.functional.cross_entropy(logits, torch.zeros(nq, dtype=torch.long, device=dev))
                 loss.backward()
-            opt.step(max_grad_norm=0.5)
+            opt.step(max_grad_norm=0.1)  # below every norm of this run: the clip is active
             norms.append(opt.last_grad_norm.item())
             opt.zero_grad()
         torch.cuda.synchronize()
@@ -164,12 +164,18 @@ def main():
     p_full, n_full, b_full = train3(False)
     p_shard, n_shard, b_shard = train3(True)
     assert all(abs(a - b) < 1e-4 * max(1.0, abs(a)) for a, b in zip(n_full, n_shard)), (n_full, n_shard)
-    worst = 0.0
+    worst, worst_name = 0.0, ""
     for n in p_full:
-        # Adam normalises: elements with ~zero gradient move by +-lr on round-off in either run; compare the bulk
-        d = (p_full[n] - p_shard[n]).abs()
-        worst = max(worst, d.mean().item() / 1e-3)
-    assert worst < 2e-2, f"sharded optimizer diverges from the replicated one: mean |dp| / lr = {worst:.2e}"
+        # Adam normalises: tensors whose true gradient is zero (key biases: softmax shift invariance; the last LayerNorm bias
+        # of a tower feeding a softmax-row loss; the head bias) move by +-lr on fp32 round-off in either run — skip them and
+        # compare the bulk of every other tensor
+        if "key.bias" in n or n.endswith(f"layer.{ec.num_layers - 1}.output.LayerNorm.bias") or n.endswith("qa_classifier.bias") \
+                or "pooler" in n:
+            continue
+        d = (p_full[n] - p_shard[n]).abs().mean().item() / 1e-3
+        if d > worst:
+            worst, worst_name = d, n
+    assert worst < 2e-2, f"sharded optimizer diverges from the replicated one: mean |dp| / lr = {worst:.2e} at {worst_name}"
     flat = torch.cat([p.reshape(-1) for p in p_shard.values()])
     gathered = [torch.empty_like(flat) for _ in range(world)]
     dist.all_gather(gathered, flat)
