@@ -161,16 +161,24 @@ def test_int32_token_batches_are_bit_identical_to_int64():
         assert torch.allclose(res[0][3], res[1][3], rtol=1e-4, atol=1e-6)
 
 
-def test_partial_freezing_through_the_layer_chain():
-    """backward is cut into per-layer autograd nodes (gradients reach DDP layer by layer); freezing the embeddings and the
-    lower layer must leave the upper layer's gradients unchanged and the frozen ones absent"""
+@pytest.mark.parametrize("delivery", ["tower", "layer"])
+def test_partial_freezing_through_the_layer_chain(delivery, monkeypatch):
+    """gradient delivery per tower (one autograd node) or per layer (`SIMX_GRAD_SLICES=layer`: the backward pass cut into
+    simx_encoder_backward_layers slices, one node per layer): freezing the embeddings and the lower layer must leave the
+    upper layer's gradients unchanged and the frozen ones absent; both deliveries give the same gradients"""
+    monkeypatch.setenv("SIMX_GRAD_SLICES", delivery)
     cfg = bn.bert_config(num_layers=2, hidden=128, heads=2, intermediate=256, vocab=300, max_pos=64)
     params = bn.synth_params(cfg, seed=13)
     ids, mask = bn.synth_tokens(4, 20, cfg["vocab"], seed=3, ragged=True)
     d = torch.randn(4, 3, 128, device="cuda", generator=torch.Generator(device="cuda").manual_seed(3))
     full = build(cfg, params, X3)
+    assert full.grad_delivery == delivery
+    ora = bn.EncoderOracle(cfg, params)
+    ora.forward(ids, mask)
+    want = ora.backward(d_cls=d.cpu().numpy().astype(np.float64))
     cls, _ = full.encode(cu(ids), cu(mask))
     (cls * d).sum().backward()
+    assert_grads(full, want, 2e-4)
     part = build(cfg, params, X3)
     for n, p in part.named_parameters():
         if n.startswith("embeddings.") or n.startswith("encoder.layer.0."):
