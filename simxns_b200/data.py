@@ -43,9 +43,11 @@ def pack_example(question_token_ids: Sequence[int], ctx_token_ids: Sequence[Sequ
     return q_t, ctx_t, ce_t
 
 
-def collate(features: List[Tuple[torch.Tensor, torch.Tensor, torch.Tensor]]) -> dict:
+def collate(features: List[Tuple[torch.Tensor, torch.Tensor, torch.Tensor]], dtype: torch.dtype = torch.int64) -> dict:
     """Rocketqa_v2Dataset.get_collate_fn (MARCO_until_new.py:240-260): passages of query i occupy rows
-    i*(1+n) .. i*(1+n)+n of the student's passage tensor, positive first; masks are `ids != 0`."""
+    i*(1+n) .. i*(1+n)+n of the student's passage tensor, positive first; masks are `ids != 0`.
+    dtype=torch.int32 halves the bytes of every id / mask tensor on the host->device wire (the kernels read either width:
+    simx_encoder_cfg.id_bytes); the default is the reference's int64."""
     doc_per_question = features[0][1].size(0)
     q_tensor = torch.stack([feature[0] for feature in features], dim=0)
     doc_tensor = torch.cat([feature[1] for feature in features])
@@ -56,8 +58,9 @@ def collate(features: List[Tuple[torch.Tensor, torch.Tensor, torch.Tensor]]) -> 
     tgt_tensor[positive_ctx_indices] = 1
     ctx_tensor_out = ctx_tensor_out.reshape(q_num, d_num // q_num, -1)
     tgt_tensor = tgt_tensor.reshape(q_num, d_num // q_num)
-    return {'student': [q_tensor, (q_tensor != 0).long(), doc_tensor, (doc_tensor != 0).long(), positive_ctx_indices],
-            'teacher': [ctx_tensor_out, (ctx_tensor_out != 0).long(), tgt_tensor]}
+    c = lambda t: t.to(dtype)
+    return {'student': [c(q_tensor), c(q_tensor != 0), c(doc_tensor), c(doc_tensor != 0), positive_ctx_indices],
+            'teacher': [c(ctx_tensor_out), c(ctx_tensor_out != 0), tgt_tensor]}
 
 
 def collate_wiki(features) -> dict:

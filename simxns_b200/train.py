@@ -57,6 +57,12 @@ def get_linear_schedule_with_warmup(optimizer, num_warmup_steps, num_training_st
     return torch.optim.lr_scheduler.LambdaLR(optimizer, lr_lambda, last_epoch)
 
 
+def _ids(t, dev):
+    """the driver casts every id / mask tensor with .long() (:189-194); int32 batches (data.collate(dtype=torch.int32)) keep
+    their width — the kernels read both"""
+    return (t if t.dtype == torch.int32 else t.long()).to(dev)
+
+
 def _unwrap(model):
     return model.module if hasattr(model, "module") else model
 
@@ -86,15 +92,14 @@ def retriever_step(args, model, teacher_model, batch, optimizer, scheduler, step
     KLDiv(log(softmax(q.c)+eps) || softmax(teacher / T)), backward through both towers, then the optimizer tail."""
     dev = next(_unwrap(model).parameters()).device
     batch_student = batch['student']
-    inputs_student = {"query_ids": batch_student[0].long().to(dev), "attention_mask_q": batch_student[1].long().to(dev),
-                      "input_ids_a": batch_student[2].long().to(dev), "attention_mask_a": batch_student[3].long().to(dev)}
+    inputs_student = {"query_ids": _ids(batch_student[0], dev), "attention_mask_q": _ids(batch_student[1], dev),
+                      "input_ids_a": _ids(batch_student[2], dev), "attention_mask_a": _ids(batch_student[3], dev)}
     model.train()
     local_q_vector, local_ctx_vectors = model(**inputs_student)
     if teacher_model is not None:
-        batch_teacher = tuple(t.to(dev) for t in batch['teacher'])
         teacher_model.eval()
         with torch.no_grad():
-            relevance_logits = teacher_model(input_ids=batch_teacher[0].long(), attention_mask=batch_teacher[1].long())
+            relevance_logits = teacher_model(input_ids=_ids(batch['teacher'][0], dev), attention_mask=_ids(batch['teacher'][1], dev))
     else:
         # pre-computed teacher scores [B, 1+n] under their own key.  (batch['teacher'][2] of the collate layout is
         # tgt_tensor — the 0/1 positive labels, MARCO_until_new.py:255 — never scores: it is not read here.)
@@ -116,9 +121,8 @@ def retriever_step(args, model, teacher_model, batch, optimizer, scheduler, step
 def teacher_step(args, teacher_model, batch, teacher_optimizer, teacher_scheduler, step: int) -> Dict[str, torch.Tensor]:
     """train_flag == 1 (:225-245): cross-encoder CE over the [B, 1+n] relevance logits with the positive in column 0."""
     dev = next(_unwrap(teacher_model).parameters()).device
-    batch_teacher = tuple(t.to(dev) for t in batch['teacher'])
     teacher_model.train()
-    relevance_logits = teacher_model(input_ids=batch_teacher[0].long(), attention_mask=batch_teacher[1].long())
+    relevance_logits = teacher_model(input_ids=_ids(batch['teacher'][0], dev), attention_mask=_ids(batch['teacher'][1], dev))
     relevance_target = torch.zeros(relevance_logits.size(0), dtype=torch.long, device=dev)
     contr_loss = torch.nn.functional.cross_entropy(relevance_logits, relevance_target)
     loss = contr_loss / args.gradient_accumulation_steps

@@ -67,3 +67,16 @@ def test_wiki_collate_matches_the_reference_bit_exactly(golden_dir):
     assert b["retriever"][4] == g["wiki_pos"].tolist()
     assert np.array_equal(np.array(b["reranker_ctx_start_end"]), g["wiki_start_end"])
     assert b["retriever"][0].shape[1] == max(g["wiki_q_lens"]) and b["retriever"][2].shape[1] == max(g["wiki_ctx_lens"])
+
+
+def test_collate_int32_option_has_the_same_values():
+    import torch
+    from simxns_b200.data import collate, pack_example
+
+    feats = [pack_example([101, 7, 8, 102], [[101, 5, 6, 102], [101, 9, 102]]) for _ in range(3)]
+    a, b = collate(feats), collate(feats, dtype=torch.int32)
+    for key in ("student", "teacher"):
+        for x, y in zip(a[key], b[key]):
+            if torch.is_tensor(x) and x is not a["teacher"][2]:
+                assert y.dtype == torch.int32 and torch.equal(x, y.long())
+    assert b["teacher"][2].dtype == torch.int64  # tgt_tensor keeps the reference's dtype (labels, never sent to the kernels)
