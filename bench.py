@@ -388,7 +388,7 @@ def run_b200(args):
     kernels, roofline, launches_per_step = None, None, None
     if not args.no_profile:
         barrier()
-        prof_steps = 3  # several steps: one step's per-kernel times swing +-10 % with the power-capped clock
+        prof_steps = 6  # several steps: one step's per-kernel times swing +-10 % with the power-capped clock
         _lib.profile_begin()
         for i in range(prof_steps):
             step(resident[i % n_batches])
