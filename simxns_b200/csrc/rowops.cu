@@ -131,9 +131,6 @@ __global__ void __launch_bounds__(ROW_THREADS)
 ln_fwd_kernel(const bf16* __restrict__ z, int T, int H, const float* __restrict__ gamma,
               const float* __restrict__ beta, float eps, bf16* x, long ps, int rpw) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const long r0 = ((long)blockIdx.x * ROW_WARPS + warp) * rpw;
-  if (r0 >= T) return;
-  const long r1 = min((long)T, r0 + rpw);
   float g[NC][8], b[NC][8];
 #pragma unroll
   for (int c = 0; c < NC; ++c) {
@@ -154,38 +151,46 @@ ln_fwd_kernel(const bf16* __restrict__ z, int T, int H, const float* __restrict_
       }
     }
   };
-  fetch(r0);
   const float invH = 1.f / H;
-  for (long r = r0; r < r1; ++r) {
-    float v[NC][8];
-    float s = 0.f;
+  // persistent over groups of `rpw` consecutive rows (grid = a couple of blocks per SM): gamma / beta are loaded once per
+  // warp for the whole launch, no wave tail, and the next group's first row is already in flight when a group ends
+  const long stride = (long)gridDim.x * ROW_WARPS * rpw;
+  long r0 = ((long)blockIdx.x * ROW_WARPS + warp) * rpw;
+  if (r0 < T) fetch(r0);
+  for (; r0 < T; r0 += stride) {
+    const long r1 = min((long)T, r0 + rpw);
+    for (long r = r0; r < r1; ++r) {
+      float v[NC][8];
+      float s = 0.f;
 #pragma unroll
-    for (int c = 0; c < NC; ++c)
-      if (c * 256 + lane * 8 < H) {
-        unpack8<NP>(nxt[c], v[c]);
+      for (int c = 0; c < NC; ++c)
+        if (c * 256 + lane * 8 < H) {
+          unpack8<NP>(nxt[c], v[c]);
 #pragma unroll
-        for (int i = 0; i < 8; ++i) s += v[c][i];
-      }
-    if (r + 1 < r1) fetch(r + 1);
-    const float mean = warp_sum(s) * invH;
-    float q2 = 0.f;
-#pragma unroll
-    for (int c = 0; c < NC; ++c)
-      if (c * 256 + lane * 8 < H)
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          v[c][i] -= mean;
-          q2 += v[c][i] * v[c][i];
+          for (int i = 0; i < 8; ++i) s += v[c][i];
         }
-    const float rstd = rsqrtf(warp_sum(q2) * invH + eps);
+      if (r + 1 < r1) fetch(r + 1);
+      else if (r0 + stride < T) fetch(r0 + stride);
+      const float mean = warp_sum(s) * invH;
+      float q2 = 0.f;
 #pragma unroll
-    for (int c = 0; c < NC; ++c) {
-      const int col = c * 256 + lane * 8;
-      if (col < H) {
-        float y[8];
+      for (int c = 0; c < NC; ++c)
+        if (c * 256 + lane * 8 < H)
 #pragma unroll
-        for (int i = 0; i < 8; ++i) y[i] = v[c][i] * rstd * g[c][i] + b[c][i];
-        split_store8<NP>(x + r * H + col, ps, y);
+          for (int i = 0; i < 8; ++i) {
+            v[c][i] -= mean;
+            q2 += v[c][i] * v[c][i];
+          }
+      const float rstd = rsqrtf(warp_sum(q2) * invH + eps);
+#pragma unroll
+      for (int c = 0; c < NC; ++c) {
+        const int col = c * 256 + lane * 8;
+        if (col < H) {
+          float y[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) y[i] = v[c][i] * rstd * g[c][i] + b[c][i];
+          split_store8<NP>(x + r * H + col, ps, y);
+        }
       }
     }
   }
@@ -526,7 +531,8 @@ int ln_fwd(int np, const bf16* z, int T, int H, const float* gamma, const float*
   SIMX_CHECK(H % 8 == 0 && H <= 256 * MAXC, SIMX_ERR_INVALID, "hidden size %d unsupported", H);
   // rows per warp: up to 8 (amortises the gamma / beta loads) while keeping >= ~8 blocks per SM in the grid
   const int rpw = (int)max(1L, min(8L, (long)T / ((long)num_sms() * 8 * ROW_WARPS)));
-  const int grid = (int)(((long)T + (long)ROW_WARPS * rpw - 1) / ((long)ROW_WARPS * rpw));
+  const long groups = ((long)T + (long)ROW_WARPS * rpw - 1) / ((long)ROW_WARPS * rpw);
+  const int grid = (int)min(groups, (long)num_sms() * 2);  // persistent: two 256-thread blocks per SM (111 registers per thread)
   const int nc = (H + 255) / 256;
 #define SIMX_LN_FWD(NP_, NC_) ln_fwd_kernel<NP_, NC_><<<grid, ROW_THREADS, 0, st>>>(z, T, H, gamma, beta, eps, x, ps, rpw)
   if (np == 1) {
