@@ -116,3 +116,53 @@ def test_two_rank_positive_index_bookkeeping(tmp_path):
         total += 12
     for r in range(world):
         assert np.load(tmp_path / f"p{r}.npy").tolist() == want
+
+
+def _flat_worker(rank, world, port, out_dir):
+    """gradsync.FlatGradSync host logic without a GPU: the constructor's broadcast and the shard=True parameter layout"""
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from simxns_b200.encoder import EncoderConfig
+    from simxns_b200.gradsync import FlatGradSync
+    from simxns_b200.models import BiBertEncoder, HFBertEncoder
+
+    torch.manual_seed(100 + rank)  # different initial weights per rank: the constructor must make them equal
+    cfg = EncoderConfig(vocab=97, hidden=64, num_layers=2, heads=1, intermediate=128, max_pos=40, type_vocab=2)
+    model = BiBertEncoder(None, question_model=HFBertEncoder(cfg), ctx_model=HFBertEncoder(cfg))
+    before = {k: v.clone() for k, v in model.state_dict().items()}
+    sync = FlatGradSync(model, shard=True)
+    after = model.state_dict()
+    assert list(after.keys()) == list(before.keys())            # names and order survive the flattening
+    out = {"keys": np.array(len(after))}
+    for i, tower in enumerate((model.question_model, model.ctx_model)):
+        flat, padded = tower._flat_param, tower._flat_padded_numel
+        lo, hi, chunk = tower._shard_range
+        slices = tower.grad_slices()
+        numel = max(off + n for off, n in slices)
+        assert padded == chunk * world and chunk % 64 == 0 and padded >= numel
+        assert lo == rank * chunk and hi == min((rank + 1) * chunk, numel)
+        for p, (off, n) in zip(tower.ordered_parameters(), slices):
+            assert p.data_ptr() == flat[off:off + n].data_ptr() and p.numel() == n    # parameters ARE views of the buffer
+        covered = np.zeros(numel, dtype=np.int32)
+        for off, n in slices:
+            covered[off:off + n] += 1
+        assert covered.max() == 1                                # slices never overlap
+        out[f"flat{i}"] = flat.numpy().copy()
+        out[f"range{i}"] = np.array([lo, hi, chunk, numel])
+    out["sum"] = np.array(sum(float(v.double().sum()) for v in after.values()))
+    np.savez(os.path.join(out_dir, f"f{rank}.npz"), **out)
+    assert sync.module is model
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_two_rank_flat_gradsync_layout(tmp_path):
+    world = 2
+    mp.spawn(_flat_worker, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
+    r = [np.load(tmp_path / f"f{i}.npz") for i in range(world)]
+    for i in range(2):
+        assert np.array_equal(r[0][f"flat{i}"], r[1][f"flat{i}"])   # rank 0's weights everywhere after construction
+        (lo0, hi0, chunk, numel), (lo1, hi1, _, _) = r[0][f"range{i}"], r[1][f"range{i}"]
+        assert lo0 == 0 and hi0 == lo1 and hi1 == numel              # the two chunks tile [0, numel)
+    assert r[0]["sum"] == r[1]["sum"]
