@@ -236,8 +236,10 @@ class EncoderOracle:
         return dict(cls=cls, seq=x, hidden=hidden)
 
     # ---- backward --------------------------------------------------------------------------------------
-    def backward(self, d_cls=None, d_seq=None):
-        """d_cls [B, L+1, H] cotangent of forward()['cls']; d_seq [B,S,H] cotangent of the last hidden state.
+    def backward(self, d_cls=None, d_seq=None, d_hidden=None):
+        """d_cls [B, L+1, H] cotangent of forward()['cls']; d_seq [B,S,H] cotangent of the last hidden state; d_hidden
+        [B, L+1, S, H] cotangent of forward()['hidden'] stacked on axis 1 (HF output_hidden_states: what LEAD's ColBERT
+        layer scores and attention maps differentiate through, LEAD/util.py:504-529, :657-660).
         Returns dict HF-name -> gradient (dense for every parameter; pooler gradients are zeros)."""
         cfg = self.cfg
         c = self.cache
@@ -251,6 +253,8 @@ class EncoderOracle:
             dx += d_seq
         if d_cls is not None:
             dx[:, 0, :] += d_cls[:, L, :]
+        if d_hidden is not None:
+            dx += d_hidden[:, L]
         for l in range(L - 1, -1, -1):
             (wq, bq, wk, bk, wv, bv, wo, bo, g1, b1, wi, bi, w2, b2, g2, bb2) = self._layer_params(l)
             lc = c["layers"][l]
@@ -287,6 +291,8 @@ class EncoderOracle:
             dx = dxl
             if d_cls is not None:
                 dx[:, 0, :] += d_cls[:, l, :]
+            if d_hidden is not None:
+                dx = dx + d_hidden[:, l]
         dx = dx * c["m0"]
         if cfg["arch"] == "bert":
             g = self.p[3]

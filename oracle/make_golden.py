@@ -611,8 +611,89 @@ def golden_lead_distill():
     np.savez_compressed(GOLD / "lead_distill.npz", **res)
 
 
+def golden_lead_col_distill():
+    """the real LEAD distill_loss with a ColBERT teacher (--distill_col --distill_db --distill_col_db_layer_score: the
+    shipped distill_from_12cb_to_6de.sh), late-interaction scores from colbert_score on final and per-layer token states"""
+    lead_shim()
+    util = import_from(REF / "LEAD", "util")
+    rng = np.random.RandomState(43)
+    GQ, group, H, Sq, Sd = 4, 3, 16, 5, 7
+    mk = lambda *shape: (rng.standard_normal(shape) * 0.5).astype(np.float32)
+    unit = lambda a: a / np.linalg.norm(a, axis=-1, keepdims=True)
+    arrs = dict(q_db=mk(GQ, H), c_db=mk(GQ * group, H), q_col=unit(mk(GQ, Sq, H)), c_col=unit(mk(GQ * group, Sd, H)),
+                qL_db=mk(GQ, 6, 1, H), cL_db=mk(GQ * group, 6, 1, H), qL_col=mk(GQ, 12, Sq, H), cL_col=mk(GQ * group, 12, Sd, H))
+    lens = rng.randint(2, Sd + 1, size=GQ * group)
+    doc_mask = (np.arange(Sd)[None, :] < lens[:, None]).astype(np.int64)
+    sel_db, sel_col = [0, 2, 5], [3, 8, 11]
+    res = dict(arrs, doc_mask=doc_mask, sel_db=np.array(sel_db), sel_col=np.array(sel_col), group=np.array([group]))
+    for tag, train_col, reweight, T in (("both", True, True, 2.0), ("frozen", False, False, 1.0)):
+        t = {n: torch.from_numpy(v.copy()).requires_grad_(True) for n, v in arrs.items()}
+        args = types.SimpleNamespace(
+            device="cpu", local_rank=-1, distill_ce=False, distill_db=True, distill_de=False, distill_col=True,
+            train_col=train_col, temperature=T, layer_temperature=0.5, distill_de_db_layer_score=False,
+            distill_col_db_layer_score=True, distill_ce_db_layer_score=False, distill_col_db_attention=False,
+            distill_de_db_attention=False, distill_ce_db_attention=False, layer_score_reweight=reweight,
+            distill_para_db=1.0, distill_para_col=0.8, distill_para_col_db_dis=1.3, distill_para_col_db_layer_score=0.4)
+        batch = {"de_ctx_start_end": torch.zeros(GQ, group + 1, 2, dtype=torch.long)}
+        loss, loss_dict = util.distill_loss(args, t["q_col"], None, t["q_db"], t["c_col"], None, t["c_db"], None, sel_db,
+                                            sel_col, None, None, None, t["qL_db"], t["cL_db"], t["qL_col"], t["cL_col"],
+                                            None, torch.from_numpy(doc_mask), None, batch)
+        loss.backward()
+        res[tag + "_loss"] = np.array([loss.item()])
+        res[tag + "_cfg"] = np.array([float(train_col), float(reweight), T, 0.5, 1.0, 0.8, 1.3, 0.4])
+        for n, v in t.items():
+            res[f"{tag}_d_{n}"] = (v.grad if v.grad is not None else torch.zeros_like(v)).numpy().copy()
+        print("lead_col_distill", tag, loss.item(), {k_: round(float(v_), 5) for k_, v_ in loss_dict.items()})
+    np.savez_compressed(GOLD / "lead_col_distill.npz", **res)
+
+
+def golden_lead_colbert():
+    """LEAD/models.py HFColBertEncoder (the ColBERT teacher tower) on a tiny BERT: normalised token embeddings, every
+    layer's FULL hidden state, and the gradients of a loss built from the reference's own colbert_score on the final
+    output and on an intermediate layer (what --distill_col_db_layer_score differentiates through)."""
+    lead_shim()
+    models = import_from(REF / "LEAD", "models")
+    util = sys.modules.get("util") or import_from(REF / "LEAD", "util")
+    mb = sys.modules["modeling_bert"]
+    if not hasattr(mb.BertPreTrainedModel, "get_head_mask"):
+        mb.BertPreTrainedModel.get_head_mask = lambda self, hm, n, *a, **k: [None] * n
+    cfg = bert_config(num_layers=3, hidden=128, heads=2, intermediate=256, vocab=512, max_pos=64)
+    params = synth_params(cfg, seed=51)
+    hcfg = hf_bert_config(cfg)
+    hcfg.add_linear = False
+    hcfg.output_hidden_states = True
+    model = models.HFColBertEncoder(hcfg, mask_punctuation=False)
+    load_params(model, params)
+    model.eval()
+    q_ids, q_mask = synth_tokens(2, 8, cfg["vocab"], seed=52, ragged=True, min_len=3)
+    d_ids, d_mask = synth_tokens(6, 24, cfg["vocab"], seed=53, ragged=True, min_len=5)
+    tq, td = (torch.from_numpy(q_ids), torch.from_numpy(q_mask)), (torch.from_numpy(d_ids), torch.from_numpy(d_mask))
+    q_out, q_hid, _ = model("colbert_query", "cpu", input_ids=tq[0], attention_mask=tq[1])
+    d_out, d_hid, _ = model("colbert_doc", "cpu", input_ids=td[0], attention_mask=td[1])
+    target = torch.tensor([0, 3])
+    scores = util.colbert_score(q_out, d_out, td[1], 2)
+    layer = 1
+    layer_scores = util.colbert_score(q_hid[:, layer], d_hid[:, layer], td[1], 2) / 64.0
+    lsm = torch.nn.functional.log_softmax
+    loss = torch.nn.functional.nll_loss(lsm(scores, dim=-1), target) + \
+        0.5 * torch.nn.functional.nll_loss(lsm(layer_scores, dim=-1), target)
+    loss.backward()
+    res = dict(q_ids=q_ids, q_mask=q_mask, d_ids=d_ids, d_mask=d_mask, seed=np.array([51]), layer=np.array([layer]),
+               q_out=q_out.detach().numpy(), d_out=d_out.detach().numpy(), q_hid=q_hid.detach().numpy(),
+               d_hid=d_hid.detach().numpy(), scores=scores.detach().numpy(), layer_scores=layer_scores.detach().numpy(),
+               loss=np.array([loss.item()]))
+    for n, p_ in model.named_parameters():
+        res["grad/" + n] = (p_.grad if p_.grad is not None else torch.zeros_like(p_)).numpy().copy()
+    np.savez_compressed(GOLD / "lead_colbert_tiny.npz", **res)
+    print("lead_colbert_tiny loss", loss.item(), "hidden", tuple(q_hid.shape), tuple(d_hid.shape))
+
+
 def main():
     only = sys.argv[1:]
+    if only == ["lead_col"]:
+        golden_lead_col_distill()
+        golden_lead_colbert()
+        return
     if only == ["lead"]:
         GOLD.mkdir(parents=True, exist_ok=True)
         golden_lead_distill()
@@ -652,6 +733,8 @@ def main():
     golden_roberta(simans)
     golden_batch_layout()
     golden_lead_select_layer()
+    golden_lead_col_distill()
+    golden_lead_colbert()
 
 
 if __name__ == "__main__":

@@ -114,6 +114,8 @@ SIGNATURES = {
     "simx_encoder_forward_embeds": (_I, [_CFG, _P, _P, _P, _P, _P, _I, _I, _P, _P, _P, _P, _P]),
     "simx_encoder_backward_embeds": (_I, [_CFG, _P, _P, _P, _P, _I, _I, _I, _P, _P, _P, _P, _P, _P, _P]),
     "simx_encoder_backward_layers": (_I, [_CFG, _P, _P, _P, _P, _P, _I, _I, _I, _P, _P, _P, _P, _P, _I, _I, _P]),
+    "simx_encoder_hidden_state": (_I, [_CFG, _P, _I, _I, _I, _P, _L, _P]),
+    "simx_encoder_add_cotangent": (_I, [_CFG, _P, _I, _I, _P, _L, _P]),
     "simx_score_loss_workspace_bytes": (C.c_size_t, [_LCFG]),
     "simx_score_loss": (_I, [_LCFG, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
     "simx_pair_distill_workspace_bytes": (C.c_size_t, [_I, _I, _I]),

@@ -31,6 +31,8 @@ int cls_gather(int np, const bf16* x, int B, int S, int H, long ps, float* out, 
 int cls_scatter_add(int np, bf16* dx, int B, int S, int H, long ps, const float* d, long d_stride_b, cudaStream_t st);
 int f32_to_planes(int np, const float* src, long n, bf16* dst, long ps, cudaStream_t st);
 int planes_to_f32(int np, const bf16* src, long n, long ps, float* dst, cudaStream_t st);
+int planes_to_f32_strided(int np, const bf16* src, int B, long SH, long ps, float* dst, long dst_stride_b, cudaStream_t st);
+int planes_add_f32(int np, bf16* dx, int B, long SH, long ps, const float* d, long d_stride_b, cudaStream_t st);
 int embed_scatter(int np, const void* ids, int id_bytes, const bf16* dz0, int T, int H, int vocab, int pad_id, long ps,
                   float* dword, cudaStream_t st);
 int convert_weight(int np, const float* w, int R, int C, bf16* dst, long ld_dst, long ps_dst, bf16* dst_t, long ld_t,
@@ -581,6 +583,32 @@ static int encoder_backward_impl(const simx_encoder_cfg* cfg, const float* const
   // caller-supplied input embeddings: their cotangent is dz0 itself (the word table took no part: its gradient stays zero)
   if (d_embeds != nullptr) SIMX_TRY(planes_to_f32(np, dza, (long)T * H, psH, d_embeds, st));
   return SIMX_OK;
+}
+
+extern "C" int simx_encoder_hidden_state(const simx_encoder_cfg* cfg, const void* saved, int B, int S, int index, float* out,
+                                         int64_t out_stride_b, void* stream) {
+  SIMX_TRY(check_cfg(cfg));
+  SIMX_CHECK(saved && out && B > 0 && S > 0 && S <= 512, SIMX_ERR_INVALID, "encoder_hidden_state: bad argument");
+  SIMX_CHECK(index >= 0 && index <= cfg->num_layers, SIMX_ERR_INVALID, "encoder_hidden_state: index %d outside [0, %d]", index,
+             cfg->num_layers);
+  SIMX_CHECK(out_stride_b >= (long)S * cfg->hidden, SIMX_ERR_INVALID, "encoder_hidden_state: out_stride_b %ld < S*H", out_stride_b);
+  const SavedL sl = saved_layout(cfg, B, S);
+  const uint8_t* sb = align_ptr(saved);
+  const long T = (long)B * S;
+  return planes_to_f32_strided(cfg->precision, reinterpret_cast<const bf16*>(sb + sl.x + sl.x_stride * index), B,
+                               (long)S * cfg->hidden, T * cfg->hidden, out, out_stride_b, static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int simx_encoder_add_cotangent(const simx_encoder_cfg* cfg, void* workspace, int B, int S, const float* d_hidden,
+                                          int64_t d_stride_b, void* stream) {
+  SIMX_TRY(check_cfg(cfg));
+  SIMX_CHECK(workspace && d_hidden && B > 0 && S > 0 && S <= 512, SIMX_ERR_INVALID, "encoder_add_cotangent: bad argument");
+  SIMX_CHECK(d_stride_b >= (long)S * cfg->hidden, SIMX_ERR_INVALID, "encoder_add_cotangent: d_stride_b %ld < S*H", d_stride_b);
+  const WsL wl = ws_layout(cfg, B, S);
+  uint8_t* ws = align_ptr(workspace);
+  const long T = (long)B * S;
+  return planes_add_f32(cfg->precision, reinterpret_cast<bf16*>(ws + wl.dx), B, (long)S * cfg->hidden, T * cfg->hidden, d_hidden,
+                        d_stride_b, static_cast<cudaStream_t>(stream));
 }
 
 extern "C" int simx_encoder_backward(const simx_encoder_cfg* cfg, const float* const* params, const void* wbuf,

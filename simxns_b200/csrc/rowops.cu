@@ -410,6 +410,32 @@ __global__ void planes_to_f32_kernel(const bf16* __restrict__ src, long n, long 
   }
 }
 
+// per-sequence strided variants: planes [B][SH] <-> fp32 with a batch stride (one layer of a [B, L, S, H] tensor)
+template <int NP>
+__global__ void planes_to_f32_strided_kernel(const bf16* __restrict__ src, long SH, long ps, float* dst, long dst_stride_b) {
+  const long b = blockIdx.y;
+  for (long i = ((long)blockIdx.x * blockDim.x + threadIdx.x) * 8; i < SH; i += (long)gridDim.x * blockDim.x * 8) {
+    float v[8];
+    plane_load8<NP>(src + b * SH + i, ps, v);
+    float* o = dst + b * dst_stride_b + i;
+    *reinterpret_cast<float4*>(o) = make_float4(v[0], v[1], v[2], v[3]);
+    *reinterpret_cast<float4*>(o + 4) = make_float4(v[4], v[5], v[6], v[7]);
+  }
+}
+// dx[b, :] += d[b, :]  (the running cotangent takes an extra term at a layer boundary)
+template <int NP>
+__global__ void planes_add_f32_kernel(bf16* dx, long SH, long ps, const float* __restrict__ d, long d_stride_b) {
+  const long b = blockIdx.y;
+  for (long i = ((long)blockIdx.x * blockDim.x + threadIdx.x) * 8; i < SH; i += (long)gridDim.x * blockDim.x * 8) {
+    float v[8], a[8];
+    plane_load8<NP>(dx + b * SH + i, ps, v);
+    ld8f(d + b * d_stride_b + i, a);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) v[k] += a[k];
+    split_store8<NP>(dx + b * SH + i, ps, v);
+  }
+}
+
 // ------------------------------------------------------------------------------------------------
 // embedding gradient: dWord[id] += dz0[row] (skipping the padding row 0: nn.Embedding(padding_idx=0))
 // ------------------------------------------------------------------------------------------------
@@ -609,6 +635,22 @@ int planes_to_f32(int np, const bf16* src, long n, long ps, float* dst, cudaStre
   SIMX_CHECK(n % 8 == 0, SIMX_ERR_INVALID, "planes_to_f32: n %% 8 != 0");
   const int grid = (int)min((n / 8 + 255) / 256, (long)num_sms() * 8);
   SIMX_NP_DISPATCH(np, (planes_to_f32_kernel<kNP><<<grid, 256, 0, st>>>(src, n, ps, dst)));
+  SIMX_LAUNCH_CHECK();
+  return SIMX_OK;
+}
+int planes_to_f32_strided(int np, const bf16* src, int B, long SH, long ps, float* dst, long dst_stride_b, cudaStream_t st) {
+  ProfScope prof("planes_to_f32", 0, (double)B * SH * (4.0 + 2.0 * np), st);
+  SIMX_CHECK(SH % 8 == 0 && dst_stride_b % 4 == 0, SIMX_ERR_INVALID, "planes_to_f32_strided: S*H %% 8 or stride %% 4 != 0");
+  const dim3 grid((unsigned)min((SH / 8 + 255) / 256, 64L), (unsigned)B);
+  SIMX_NP_DISPATCH(np, (planes_to_f32_strided_kernel<kNP><<<grid, 256, 0, st>>>(src, SH, ps, dst, dst_stride_b)));
+  SIMX_LAUNCH_CHECK();
+  return SIMX_OK;
+}
+int planes_add_f32(int np, bf16* dx, int B, long SH, long ps, const float* d, long d_stride_b, cudaStream_t st) {
+  ProfScope prof("planes_add_f32", 0, (double)B * SH * (4.0 + 4.0 * np), st);
+  SIMX_CHECK(SH % 8 == 0 && d_stride_b % 4 == 0, SIMX_ERR_INVALID, "planes_add_f32: S*H %% 8 or stride %% 4 != 0");
+  const dim3 grid((unsigned)min((SH / 8 + 255) / 256, 64L), (unsigned)B);
+  SIMX_NP_DISPATCH(np, (planes_add_f32_kernel<kNP><<<grid, 256, 0, st>>>(dx, SH, ps, d, d_stride_b)));
   SIMX_LAUNCH_CHECK();
   return SIMX_OK;
 }

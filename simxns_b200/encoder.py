@@ -300,9 +300,11 @@ class B200EncoderBase(nn.Module):
         return [o[:base]] + [o[base + 16 * l: base + 16 * (l + 1)] for l in range(L)] + [o[base + 16 * L:]]
 
     def encode(self, input_ids: Optional[torch.Tensor], attention_mask: Optional[torch.Tensor] = None,
-               want_sequence: bool = False, inputs_embeds: Optional[torch.Tensor] = None):
-        """-> (cls_layers [B, L+1, H] fp32, sequence_output [B,S,H] fp32 or None).
+               want_sequence: bool = False, inputs_embeds: Optional[torch.Tensor] = None, want_hidden: bool = False):
+        """-> (cls_layers [B, L+1, H] fp32, sequence_output [B,S,H] fp32 or None[, hidden [B, L+1, S, H] fp32]).
         cls_layers[:, -1] is the reference's pooled_output; cls_layers[:, l+1] the [CLS] row of layer l.
+        want_hidden: a third output, every depth's full hidden state (index 0 = embedding output, l+1 = layer l) with
+        gradients — HF `output_hidden_states`, what LEAD's towers return as `all_layer_hidden` (LEAD/models.py:125-138).
         inputs_embeds [B,S,H] (instead of input_ids): HF's `inputs_embeds=` — the word-embedding rows supplied by the caller,
         differentiable (the forward_adv_* paths of BiBertEncoder)."""
         params = self._ordered
@@ -313,19 +315,21 @@ class B200EncoderBase(nn.Module):
                 raise ValueError(f"inputs_embeds must be [B, S, {self.enc_cfg.hidden}]")
             if self.enc_cfg.roberta_positions:
                 raise NotImplementedError("inputs_embeds with RoBERTa position ids is not implemented")
+            if want_hidden:
+                raise NotImplementedError("want_hidden with inputs_embeds is not implemented")
             needs_grad = torch.is_grad_enabled() and (inputs_embeds.requires_grad or any(p.requires_grad for p in params))
             st = _TowerPass(self, None, attention_mask, bool(want_sequence), needs_grad, inputs_embeds=inputs_embeds)
             if not needs_grad:
                 return st.cls, (st.seq if want_sequence else None)
             st.monolithic = True
-            cls, seq = _TopNode.apply(st, inputs_embeds, *params)
+            cls, seq, _ = _TopNode.apply(st, inputs_embeds, *params)
             return cls, (seq if want_sequence else None)
         if input_ids.dim() != 2:
             raise ValueError("input_ids must be [B, S]")
         needs_grad = torch.is_grad_enabled() and any(p.requires_grad for p in params)
-        st = _TowerPass(self, input_ids, attention_mask, bool(want_sequence), needs_grad)
+        st = _TowerPass(self, input_ids, attention_mask, bool(want_sequence), needs_grad, want_hidden=bool(want_hidden))
         if not needs_grad:
-            return st.cls, (st.seq if want_sequence else None)
+            return (st.cls, (st.seq if want_sequence else None)) + ((st.hidden,) if want_hidden else ())
         # autograd graph.  "tower" (default): one node per tower pass returns all gradients when the pass is complete.
         # "layer": embeddings -> layer 0 -> ... -> layer L-1 -> outputs chained through a dummy token, each node running ONE
         # slice of the backward pass (simx_encoder_backward_layers) and returning that slice's parameter gradients, so a
@@ -338,18 +342,19 @@ class B200EncoderBase(nn.Module):
             token = _EmbedNode.apply(st, *groups[0])
             for l in range(self.enc_cfg.num_layers):
                 token = _LayerNode.apply(st, l, token, *groups[1 + l])
-            cls, seq = _TopNode.apply(st, token, *groups[-1])
+            cls, seq, hidden = _TopNode.apply(st, token, *groups[-1])
         else:
             st.monolithic = True
-            cls, seq = _TopNode.apply(st, None, *params)
-        return cls, (seq if want_sequence else None)
+            cls, seq, hidden = _TopNode.apply(st, None, *params)
+        return (cls, (seq if want_sequence else None)) + ((hidden,) if want_hidden else ())
 
 
 class _TowerPass:
     """State of one forward/backward pass of one tower: runs the forward at construction, owns the saved activations, and
     runs the backward slice by slice on behalf of the autograd nodes below."""
 
-    def __init__(self, module: B200EncoderBase, ids, mask, want_seq: bool, needs_grad: bool, inputs_embeds=None):
+    def __init__(self, module: B200EncoderBase, ids, mask, want_seq: bool, needs_grad: bool, inputs_embeds=None,
+                 want_hidden: bool = False):
         lib = _lib.lib()
         params = module._ordered
         module._check_params(params)
@@ -390,13 +395,15 @@ class _TowerPass:
                 seed = module.forced_dropout_seed if module.forced_dropout_seed is not None else next_dropout_seed()
                 module.last_dropout_seed = seed
             cfg = module._c_cfg(dropout_seed=seed, id_bytes=4 if idt == torch.int32 else 8)
+            if want_hidden and not needs_grad:
+                cfg.save_policy = _lib.SAVE_LAYER_INPUTS  # the hidden states are the layer inputs: keep those and nothing else
             wbuf = module._weights(params)
             table = module._param_table(params)
             stream = torch.cuda.current_stream(dev).cuda_stream
             cls = torch.empty(B, ec.num_layers + 1, ec.hidden, dtype=torch.float32, device=dev)
             seq = torch.empty(B, S, ec.hidden, dtype=torch.float32, device=dev) if want_seq else None
             saved, ws = None, None
-            if needs_grad:
+            if needs_grad or want_hidden:
                 saved = torch.empty(lib.simx_encoder_saved_bytes(C.byref(cfg), B, S), dtype=torch.uint8, device=dev)
             if not needs_grad or module.gradient_checkpointing:
                 ws = torch.empty(lib.simx_encoder_workspace_bytes(C.byref(cfg), B, S), dtype=torch.uint8, device=dev)
@@ -413,6 +420,16 @@ class _TowerPass:
                 _lib.check(lib.simx_encoder_forward_pos(C.byref(cfg), table, wbuf.data_ptr(), ids.data_ptr(), _lib.ptr(mask),
                                                         pos_ids.data_ptr(), B, S, _lib.ptr(saved), _lib.ptr(ws),
                                                         cls.data_ptr(), _lib.ptr(seq), stream), "simx_encoder_forward_pos")
+            hidden = None
+            if want_hidden:  # [B, L+1, S, H]: depth l of every sequence is one strided slab
+                Lh = ec.num_layers + 1
+                hidden = torch.empty(B, Lh, S, ec.hidden, dtype=torch.float32, device=dev)
+                for l in range(Lh):
+                    _lib.check(lib.simx_encoder_hidden_state(C.byref(cfg), saved.data_ptr(), B, S, l, hidden[:, l].data_ptr(),
+                                                             Lh * S * ec.hidden, stream), "simx_encoder_hidden_state")
+                if not needs_grad:
+                    saved = None
+        self.hidden, self.d_hidden = hidden, None
         self.module, self.cfg, self.dev = module, cfg, dev
         self.ids, self.mask, self.pos_ids, self.shape = ids, mask, pos_ids, (B, S)
         self.embeds = embeds is not None  # backward also produces d(loss)/d(inputs_embeds)
@@ -426,18 +443,26 @@ class _TowerPass:
         self.monolithic = False
         self.sink = module._grad_sink if needs_grad else None
 
-    def begin_backward(self, d_cls, d_seq) -> bool:
+    def begin_backward(self, d_cls, d_seq, d_hidden=None) -> bool:
         """called by the top node; False when no cotangent reaches the tower"""
         if self.saved is None:
             raise RuntimeError("encoder backward without saved activations (already freed by an earlier backward, or the "
                                "forward ran under no_grad)")
-        if d_cls is None and (d_seq is None or not self.want_seq):
+        if d_hidden is not None and self.hidden is None:
+            d_hidden = None
+        if d_cls is None and (d_seq is None or not self.want_seq) and d_hidden is None:
             return False
         lib = _lib.lib()
         B, S = self.shape
         with torch.cuda.device(self.dev):
             self.d_cls = None if d_cls is None else d_cls.to(torch.float32).contiguous()
             self.d_seq = d_seq.to(torch.float32).contiguous() if (d_seq is not None and self.want_seq) else None
+            if d_hidden is not None:
+                # the cotangent of the last hidden state is the sequence output's; the other depths are added to the running
+                # cotangent at their layer boundary (run_slice)
+                self.d_hidden = d_hidden.to(torch.float32).contiguous()
+                top = self.d_hidden[:, -1]
+                self.d_seq = top.contiguous() if self.d_seq is None else self.d_seq + top
             self.ws = torch.empty(lib.simx_encoder_workspace_bytes(C.byref(self.cfg), B, S), dtype=torch.uint8,
                                   device=self.dev)
             numel = lib.simx_encoder_grad_numel(C.byref(self.cfg))
@@ -470,14 +495,29 @@ class _TowerPass:
             return
         with torch.cuda.device(self.dev):
             stream = torch.cuda.current_stream(self.dev).cuda_stream
-            _lib.check(lib.simx_encoder_backward_layers(
-                C.byref(self.cfg), m._param_table(self.params), self.wbuf.data_ptr(), self.ids.data_ptr(), _lib.ptr(self.mask),
-                _lib.ptr(self.pos_ids), m.enc_cfg.pad_token_id if self.pos_ids is not None else 0, B, S,
-                self.saved.data_ptr(), self.ws.data_ptr(), _lib.ptr(self.d_cls), _lib.ptr(self.d_seq), self.flat.data_ptr(),
-                lo, hi, stream), "simx_encoder_backward_layers")
+            table = m._param_table(self.params)
+
+            def layers(a: int, b: int) -> None:
+                _lib.check(lib.simx_encoder_backward_layers(
+                    C.byref(self.cfg), table, self.wbuf.data_ptr(), self.ids.data_ptr(), _lib.ptr(self.mask),
+                    _lib.ptr(self.pos_ids), m.enc_cfg.pad_token_id if self.pos_ids is not None else 0, B, S,
+                    self.saved.data_ptr(), self.ws.data_ptr(), _lib.ptr(self.d_cls), _lib.ptr(self.d_seq),
+                    self.flat.data_ptr(), a, b, stream), "simx_encoder_backward_layers")
+
+            if self.d_hidden is None:
+                layers(lo, hi)
+            else:  # one layer at a time: the cotangent of hidden state l joins the running one between layer l and l - 1
+                Lh, H = m.enc_cfg.num_layers + 1, m.enc_cfg.hidden
+                for l in range(hi - 1, max(lo, 0) - 1, -1):
+                    layers(l, l + 1)
+                    _lib.check(lib.simx_encoder_add_cotangent(C.byref(self.cfg), self.ws.data_ptr(), B, S,
+                                                              self.d_hidden[:, l].data_ptr(), Lh * S * H, stream),
+                               "simx_encoder_add_cotangent")
+                if lo < 0:
+                    layers(-1, 0)
         self.next_hi = lo
         if lo < 0:  # pass complete: release everything but the gradient buffer (kept alive by the views handed out)
-            self.saved = self.ws = self.d_cls = self.d_seq = None
+            self.saved = self.ws = self.d_cls = self.d_seq = self.d_hidden = None
 
     def finish(self) -> None:
         """the last slice of this pass has run: hand the flat buffer to the gradient sink, if one is attached"""
@@ -541,17 +581,23 @@ class _TopNode(torch.autograd.Function):
     def forward(ctx, st: _TowerPass, token, *params):
         ctx.st, ctx.params = st, params
         ctx.set_materialize_grads(False)
-        seq = st.seq
+        seq, hidden = st.seq, st.hidden
+        dead = []
         if seq is None:
             seq = st.cls.new_empty(0)
-            ctx.mark_non_differentiable(seq)
-        return st.cls, seq
+            dead.append(seq)
+        if hidden is None:
+            hidden = st.cls.new_empty(0)
+            dead.append(hidden)
+        if dead:
+            ctx.mark_non_differentiable(*dead)
+        return st.cls, seq, hidden
 
     @staticmethod
     @torch.autograd.function.once_differentiable
-    def backward(ctx, d_cls, d_seq):
+    def backward(ctx, d_cls, d_seq, d_hidden):
         st: _TowerPass = ctx.st
-        live = st.begin_backward(d_cls, d_seq)
+        live = st.begin_backward(d_cls, d_seq, d_hidden)
         if st.monolithic:  # the whole pass in this node: every parameter is an input here
             if live:
                 st.run_slice(-1, st.next_hi)

@@ -441,6 +441,123 @@ def lead_ce_distill_loss(q_db, c_db, ce_logits, cls_q_db=None, cls_c_db=None, ce
     return loss, parts
 
 
+def gather_tensor(local: torch.Tensor, group=None) -> torch.Tensor:
+    """LEAD/util.py:200-204 `gather_tensor`: all-gather along dim 0 with the LOCAL slice re-inserted, so gradients reach the
+    local rows only and remote rows are constants.  One NCCL all-gather into a flat buffer instead of a list of tensors."""
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+        return local
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    n = local.shape[0]
+    out = local.new_empty((world * n,) + tuple(local.shape[1:]))
+    dist.all_gather_into_tensor(out, local.detach().contiguous(), group=group)
+    return torch.cat([out[:rank * n], local, out[(rank + 1) * n:]], dim=0)
+
+
+class _ColbertScoreFn(torch.autograd.Function):
+    """late-interaction scores in document chunks: the reference materialises the whole [Q*Sq, D*Sd] token-pair matrix
+    (4.3 GB fp32 at 128 queries x 2048 passages); here a chunk of it lives at a time and backward rebuilds the one-hot
+    routing of each chunk from the saved arg-max positions"""
+
+    @staticmethod
+    def forward(ctx, q, d, keep, chunk):
+        Q, Sq, H = q.shape
+        D, Sd, _ = d.shape
+        qf = q.reshape(Q * Sq, H)
+        out = q.new_empty(Q, D)
+        idx = torch.empty(Q, Sq, D, dtype=torch.int64, device=q.device)
+        for lo in range(0, D, chunk):
+            hi = min(lo + chunk, D)
+            logits = torch.matmul(qf, d[lo:hi].reshape(-1, H).t()).view(Q, Sq, hi - lo, Sd)
+            logits.masked_fill_(~keep[lo:hi][None, None], -9e9)
+            mx, ix = logits.max(3)
+            out[:, lo:hi] = mx.sum(1)
+            idx[:, :, lo:hi] = ix
+        ctx.save_for_backward(q, d, keep, idx)
+        ctx.chunk = chunk
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        q, d, keep, idx = ctx.saved_tensors
+        Q, Sq, H = q.shape
+        D, Sd, _ = d.shape
+        qf = q.reshape(Q * Sq, H)
+        dq = torch.zeros_like(qf)
+        dd = torch.empty_like(d)
+        for lo in range(0, D, ctx.chunk):
+            hi = min(lo + ctx.chunk, D)
+            w = q.new_zeros(Q, Sq, hi - lo, Sd)
+            w.scatter_(3, idx[:, :, lo:hi, None], g[:, None, lo:hi, None].expand(Q, Sq, hi - lo, 1))
+            w.mul_(keep[lo:hi][None, None])  # a filled position passes no gradient (index_fill_ in the reference)
+            wf = w.view(Q * Sq, (hi - lo) * Sd)
+            dq.addmm_(wf, d[lo:hi].reshape(-1, H))
+            dd[lo:hi] = torch.matmul(wf.t(), qf).view(hi - lo, Sd, H)
+        return dq.view(Q, Sq, H), dd, None, None
+
+
+def colbert_score(q_embs_col, d_embs_col, attention_mask, q_num, chunk: int = 256):
+    """LEAD/util.py:459-465: MaxSim late interaction.  q_embs_col [Q, Sq, H], d_embs_col [D, Sd, H], attention_mask [D, Sd]
+    of the documents -> scores [q_num, D * Q / q_num]: sum over ALL query positions (padded ones included, as in the
+    reference) of the maximum over the un-masked document tokens of q_i . d_j."""
+    keep = attention_mask.reshape(d_embs_col.shape[0], d_embs_col.shape[1]) != 0
+    scores = _ColbertScoreFn.apply(q_embs_col, d_embs_col, keep, int(chunk))
+    return scores.view(q_num, -1)
+
+
+def lead_col_distill_loss(q_db, c_db, q_col, c_col, doc_mask, cls_q_db=None, cls_c_db=None, hid_q_col=None, hid_c_col=None, *,
+                          selected_db: Sequence[int] = (), selected_col: Sequence[int] = (), temperature: float = 1.0,
+                          layer_temperature: float = 1.0, para_db: float = 1.0, para_col: float = 1.0, para_dis: float = 1.0,
+                          para_layer: float = 1.0, reweight: bool = True, train_col: bool = True, gather: bool = True):
+    """ColBERT-teacher -> DB-student branch of LEAD's distill_loss (/root/reference/LEAD/util.py:581-585 gather, :594-615
+    student scores, :647-664 teacher scores, :730-735 + :772-794 loss sum, :539-559 layer re-weighting) — the two shipped
+    scripts distillation/distill_from_12cb_to_6de.sh and distill_from_24cb_to_12de.sh.
+
+    q_db / c_db: the student's final embeddings [n, H]; q_col / c_col: the teacher's normalised token embeddings
+    [n, S, 768] (HFColBertEncoder output 0); doc_mask [n_docs, S_d]; cls_*_db [n, L_s, H] the student's per-layer [CLS]
+    rows; hid_*_col [n, L_t, S, H] the teacher's per-layer hidden states (HFColBertEncoder output 1).  The score matrices
+    are small ([GQ, GC]); the arithmetic on them is the reference's, term by term, with NO detach (targets carry gradient
+    to whichever model produced them).  Only the selected teacher layers are gathered.  Returns (loss, dict of parts)."""
+    import torch.nn.functional as F
+
+    g = gather_tensor if gather else (lambda t: t)
+    q_db, c_db, q_col, c_col, doc_mask = g(q_db), g(c_db), g(q_col), g(c_col), g(doc_mask)
+    q_num = q_db.shape[0]
+    sample_num = c_db.shape[0] // q_num
+    target = torch.arange(0, q_num * sample_num, sample_num, device=q_db.device, dtype=torch.long)
+    T = float(temperature)
+
+    def views(scores):
+        return F.log_softmax(scores, dim=-1), F.softmax(scores / T, dim=-1)
+
+    lsm_db, tgt_db = views(torch.matmul(q_db, c_db.t()).view(q_num, -1))
+    lsm_col, tgt_col = views(colbert_score(q_col, c_col, doc_mask, q_num))
+    parts = {}
+    loss_db = F.nll_loss(lsm_db, target)
+    loss = para_db * loss_db
+    parts["loss_db"] = loss_db.detach()
+    if train_col:
+        loss_col = F.nll_loss(lsm_col, target)
+        loss = loss + para_col * loss_col
+        parts["loss_col"] = loss_col.detach()
+    loss_col_db_dis = F.kl_div(lsm_db, tgt_col, reduction="batchmean")
+    loss_db_col_dis = F.kl_div(lsm_col, tgt_db, reduction="batchmean")
+    loss = loss + para_dis * ((loss_col_db_dis + loss_db_col_dis) if train_col else loss_col_db_dis)
+    parts["loss_col_db_dis"], parts["loss_db_col_dis"] = loss_col_db_dis.detach(), loss_db_col_dis.detach()
+    if len(selected_db):
+        kls, lams = [], []
+        for ls, lt in zip(selected_db, selected_col):
+            lsm_s, _ = views(torch.matmul(g(cls_q_db[:, ls]), g(cls_c_db[:, ls]).t()).view(q_num, -1))
+            lsm_t, tgt_t = views(colbert_score(g(hid_q_col[:, lt]), g(hid_c_col[:, lt]), doc_mask, q_num))
+            kls.append(F.kl_div(lsm_s, tgt_t, reduction="batchmean"))
+            lams.append(-F.nll_loss(lsm_t, target).detach() / layer_temperature)  # torch.tensor([...]) in the reference: detached
+        lam = torch.softmax(torch.stack(lams), dim=0) if reweight else torch.full((len(kls),), float(para_layer),
+                                                                                  device=loss.device)
+        layer_loss = sum(l * k for l, k in zip(lam, kls))
+        loss = loss + layer_loss
+        parts["loss_col_db_layer_dis"] = layer_loss.detach()
+    return loss, parts
+
+
 def select_layer(args):
     """LEAD's choice of the layer pairs whose [CLS] scores are distilled (/root/reference/LEAD/util.py:206-254), re-drawn
     every `save_steps` by run_LEAD.py.  Returns (selected_index_list_db, selected_index_list_teacher) for

@@ -1,0 +1,118 @@
+"""B200 (`-m gpu`): every depth's FULL hidden state as a differentiable output of the tower — HF `output_hidden_states`,
+LEAD's `all_layer_hidden [B, L, S, H]` (LEAD/models.py:125-138, :184-196) — through simx_encoder_hidden_state (forward)
+and simx_encoder_add_cotangent between the layer slices of the backward pass.
+
+  * against the numpy oracle with a random cotangent on EVERY depth (plus [CLS] rows and the sequence output), both
+    architectures, dropout, checkpointing, both gradient-delivery modes;
+  * against the reference's own HFColBertEncoder (tests/golden/lead_colbert_tiny.npz, oracle/make_golden.py): token
+    embeddings, per-layer states, colbert_score on the output and on an intermediate layer, and the parameter gradients
+    of the resulting loss."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import bert_numpy as bn
+from simxns_b200 import _lib
+from simxns_b200 import lead_models
+from simxns_b200.losses import colbert_score
+from test_gpu_parity import X3, BF16, assert_grads, build, cu, ec_from, max_rel
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module", autouse=True)
+def _device():
+    assert torch.cuda.is_available(), "gpu tests need a CUDA device"
+    torch.cuda.set_device(0)
+    _lib.require_device()
+
+
+@pytest.mark.parametrize("arch,B,S,drop,ckpt,delivery", [
+    ("bert", 3, 40, False, False, "tower"), ("bert", 2, 130, True, False, "layer"), ("distilbert", 4, 24, True, True, "tower"),
+    ("bert", 1, 300, False, True, "layer"), ("distilbert", 2, 77, False, False, "layer")])
+def test_hidden_states_forward_backward_vs_oracle(arch, B, S, drop, ckpt, delivery):
+    cfg = bn.bert_config(num_layers=3, hidden=128, heads=2, intermediate=192, vocab=300, max_pos=512, arch=arch)
+    params = bn.synth_params(cfg, seed=5 + S)
+    ids, mask = bn.synth_tokens(B, S, cfg["vocab"], seed=S, ragged=True, min_len=3)
+    dr = dict(p_hidden=0.1, p_attn=0.1, seed=424242) if drop else None
+    ora = bn.EncoderOracle(cfg, params)
+    out = ora.forward(ids, mask, dropout=dr) if drop else ora.forward(ids, mask)
+    want_hidden = np.stack(out["hidden"], axis=1)                      # [B, L+1, S, H]
+    rng = np.random.RandomState(S)
+    d_hidden = rng.standard_normal(want_hidden.shape) * mask[:, None, :, None]
+    d_cls = rng.standard_normal(out["cls"].shape)
+    d_seq = rng.standard_normal(out["seq"].shape) * mask[:, :, None]
+    ref = ora.backward(d_cls=d_cls, d_seq=d_seq, d_hidden=d_hidden)
+    m4 = mask[:, None, :, None]
+    for precision, tol_h, tol_g in ((X3, 2e-5, 3e-4), (BF16, 6e-2, 1.2e-1)):
+        model = build(cfg, params, precision)
+        model.grad_delivery = delivery
+        if drop:
+            model.hidden_dropout_prob, model.attention_probs_dropout_prob, model.forced_dropout_seed = 0.1, 0.1, 424242
+        model.train()
+        if ckpt:
+            model.gradient_checkpointing_enable()
+        cls, seq, hidden = model.encode(cu(ids), cu(mask), want_sequence=True, want_hidden=True)
+        assert tuple(hidden.shape) == want_hidden.shape
+        assert max_rel(hidden.detach().cpu().numpy() * m4, want_hidden * m4) < tol_h, (precision, "hidden")
+        assert torch.equal(hidden[:, -1], seq) and torch.equal(hidden[:, :, 0], cls)
+        loss = (hidden * cu(d_hidden, torch.float32)).sum() + (cls * cu(d_cls, torch.float32)).sum() + \
+            (seq * cu(d_seq, torch.float32)).sum()
+        loss.backward()
+        assert_grads(model, ref, tol_g)
+        # the same states without autograd (a frozen teacher): only the layer inputs are kept during that forward
+        with torch.no_grad():
+            _, _, h2 = model.encode(cu(ids), cu(mask), want_hidden=True)
+        assert torch.equal(h2, hidden)
+
+
+def test_only_an_intermediate_depth_carries_gradient():
+    """no cotangent on the outputs at all — the pass is seeded by hidden state 1 alone; layers above it get exact zeros"""
+    cfg = bn.bert_config(num_layers=3, hidden=64, heads=1, intermediate=128, vocab=200, max_pos=64)
+    params = bn.synth_params(cfg, seed=2)
+    ids, mask = bn.synth_tokens(3, 20, cfg["vocab"], seed=8, ragged=True)
+    ora = bn.EncoderOracle(cfg, params)
+    out = ora.forward(ids, mask)
+    d_hidden = np.zeros((3, 4, 20, 64))
+    d_hidden[:, 1] = np.random.RandomState(0).standard_normal((3, 20, 64)) * mask[:, :, None]
+    ref = ora.backward(d_hidden=d_hidden)
+    model = build(cfg, params, X3).train()
+    _, _, hidden = model.encode(cu(ids), cu(mask), want_hidden=True)
+    (hidden[:, 1] * cu(d_hidden[:, 1], torch.float32)).sum().backward()
+    zero_true = tuple(n for n, _ in model.named_parameters() if "layer.1." in n or "layer.2." in n or "pooler" in n)
+    assert_grads(model, ref, 3e-4, zero_true=zero_true)
+    for n, p in model.named_parameters():
+        if n in zero_true:
+            assert float(p.grad.abs().max()) == 0.0, n
+
+
+def test_colbert_tower_vs_reference_golden(golden_dir):
+    g = np.load(golden_dir / "lead_colbert_tiny.npz")
+    cfg = bn.bert_config(num_layers=3, hidden=128, heads=2, intermediate=256, vocab=512, max_pos=64)
+    params = bn.synth_params(cfg, seed=int(g["seed"][0]))
+    layer = int(g["layer"][0])
+    for precision, tol_h, tol_s, tol_g in ((X3, 2e-5, 1e-4, 3e-4), (BF16, 5e-2, 5e-2, 1.5e-1)):
+        model = lead_models.HFColBertEncoder(ec_from(cfg), precision=precision)
+        model.load_state_dict({k: torch.from_numpy(v) for k, v in params.items()}, strict=True)
+        model = model.cuda().eval()
+        q_out, q_hid, _ = model("colbert_query", "cuda", input_ids=cu(g["q_ids"]), attention_mask=cu(g["q_mask"]))
+        d_out, d_hid, _ = model("colbert_doc", "cuda", input_ids=cu(g["d_ids"]), attention_mask=cu(g["d_mask"]))
+        assert tuple(q_hid.shape) == g["q_hid"].shape and tuple(d_hid.shape) == g["d_hid"].shape
+        mq, md = g["q_mask"][:, None, :, None], g["d_mask"][:, None, :, None]
+        assert max_rel(q_hid.detach().cpu().numpy() * mq, g["q_hid"] * mq) < tol_h
+        assert max_rel(d_hid.detach().cpu().numpy() * md, g["d_hid"] * md) < tol_h
+        assert max_rel(d_out.detach().cpu().numpy() * md[:, 0], g["d_out"] * md[:, 0]) < tol_h
+        # padded QUERY positions take part in the reference's sum (util.py:459-465), so their states matter too
+        assert max_rel(q_out.detach().cpu().numpy(), g["q_out"]) < tol_h
+        scores = colbert_score(q_out, d_out, cu(g["d_mask"]), 2)
+        layer_scores = colbert_score(q_hid[:, layer], d_hid[:, layer], cu(g["d_mask"]), 2) / 64.0
+        assert max_rel(scores.detach().cpu().numpy(), g["scores"]) < tol_s
+        assert max_rel(layer_scores.detach().cpu().numpy(), g["layer_scores"]) < tol_s
+        target = torch.tensor([0, 3], device="cuda")
+        lsm = torch.nn.functional.log_softmax
+        loss = torch.nn.functional.nll_loss(lsm(scores, dim=-1), target) + \
+            0.5 * torch.nn.functional.nll_loss(lsm(layer_scores, dim=-1), target)
+        assert abs(loss.item() - float(g["loss"][0])) < (1e-4 if precision == X3 else 5e-2)
+        loss.backward()
+        ref = {k[5:]: g[k] for k in g.files if k.startswith("grad/")}
+        assert_grads(model, ref, tol_g, zero_true=("pooler.dense.weight", "pooler.dense.bias"))

@@ -1,0 +1,57 @@
+"""CPU: LEAD's ColBERT-teacher distillation arithmetic (losses.colbert_score, losses.lead_col_distill_loss) against the
+reference's own `distill_loss` / `colbert_score` run on the same tensors (tests/golden/lead_col_distill.npz, written by
+oracle/make_golden.py from /root/reference/LEAD/util.py:459-465, :561-664, :730-735, :772-794).  These are plain tensor
+ops on [GQ, GC]-sized score matrices, so the pin runs without a GPU; the tower that feeds them (HFColBertEncoder on the
+CUDA kernels) is checked in tests/test_gpu_hidden_states.py."""
+import numpy as np
+import pytest
+import torch
+
+from simxns_b200.losses import colbert_score, lead_col_distill_loss
+
+
+@pytest.fixture(scope="module")
+def gold(golden_dir):
+    return np.load(golden_dir / "lead_col_distill.npz")
+
+
+@pytest.mark.parametrize("tag", ["both", "frozen"])
+def test_col_branch_loss_and_every_gradient_vs_reference(gold, tag):
+    names = ("q_db", "c_db", "q_col", "c_col", "qL_db", "cL_db", "qL_col", "cL_col")
+    t = {n: torch.from_numpy(gold[n].copy()).requires_grad_(True) for n in names}
+    train_col, reweight, T, layer_T, p_db, p_col, p_dis, p_layer = [float(x) for x in gold[tag + "_cfg"]]
+    loss, parts = lead_col_distill_loss(
+        t["q_db"], t["c_db"], t["q_col"], t["c_col"], torch.from_numpy(gold["doc_mask"]), t["qL_db"][:, :, 0], t["cL_db"][:, :, 0],
+        t["qL_col"], t["cL_col"], selected_db=gold["sel_db"].tolist(), selected_col=gold["sel_col"].tolist(), temperature=T,
+        layer_temperature=layer_T, para_db=p_db, para_col=p_col, para_dis=p_dis, para_layer=p_layer, reweight=bool(reweight),
+        train_col=bool(train_col), gather=False)
+    assert abs(loss.item() - float(gold[tag + "_loss"][0])) < 1e-5
+    loss.backward()
+    for n in names:
+        want = gold[f"{tag}_d_{n}"]
+        got = t[n].grad.numpy() if t[n].grad is not None else np.zeros_like(want)
+        assert np.abs(got - want).max() <= 1e-6 + 1e-4 * np.abs(want).max(), n
+    assert set(parts) >= {"loss_db", "loss_col_db_dis", "loss_db_col_dis", "loss_col_db_layer_dis"}
+
+
+def test_colbert_score_chunking_and_masked_documents(gold):
+    q = torch.from_numpy(gold["q_col"].copy()).requires_grad_(True)
+    d = torch.from_numpy(gold["c_col"].copy()).requires_grad_(True)
+    mask = torch.from_numpy(gold["doc_mask"].copy())
+    mask[2] = 0  # a document with no kept token: every pair scores -9e9 per query position and passes no gradient
+    whole = colbert_score(q, d, mask, q.shape[0], chunk=1 << 20)
+    g = torch.randn(whole.shape, generator=torch.Generator().manual_seed(3))
+    (whole * g).sum().backward()
+    gq, gd = q.grad.clone(), d.grad.clone()
+    q.grad = d.grad = None
+    parts = colbert_score(q, d, mask, q.shape[0], chunk=5)     # 12 documents in chunks of 5, 5, 2
+    (parts * g).sum().backward()
+    assert torch.allclose(whole, parts, rtol=1e-6, atol=1e-6)   # BLAS blocks the chunked products differently
+    assert torch.allclose(q.grad, gq, atol=1e-6) and torch.allclose(d.grad, gd, atol=1e-6)
+    assert torch.all(whole[:, 2] == -9e9 * q.shape[1]) and torch.all(d.grad[2] == 0)
+    # padded document tokens never receive gradient
+    assert torch.all(d.grad[mask == 0] == 0)
+    # the straightforward formulation (util.py:459-465) on the same inputs
+    with torch.no_grad():
+        logits = torch.einsum("qih,djh->qidj", q, d).masked_fill(mask[None, None] == 0, -9e9)
+        assert torch.allclose(whole, logits.max(3).values.sum(1), atol=1e-5)
