@@ -647,6 +647,33 @@ def golden_lead_col_distill():
     np.savez_compressed(GOLD / "lead_col_distill.npz", **res)
 
 
+def golden_lead_virt():
+    """LEAD/util.py:504-537 query_doc_attention_map + virt_loss, the reference functions themselves, on synthetic per-layer
+    hidden states of a teacher and a student: maps, loss and the gradients with respect to all four inputs"""
+    lead_shim()
+    util = sys.modules.get("util") or import_from(REF / "LEAD", "util")
+    rng = np.random.RandomState(47)
+    Q, D, Sq, Sd, H = 3, 6, 5, 9, 16
+    mk = lambda *shape: (rng.standard_normal(shape) * 0.7).astype(np.float32)
+    arrs = dict(q_t=mk(Q, 12, Sq, H), d_t=mk(D, 12, Sd, H), q_s=mk(Q, 6, Sq, H), d_s=mk(D, 6, Sd, H))
+    query_len = rng.randint(2, Sq + 1, size=Q).tolist()
+    doc_len = rng.randint(3, Sd + 1, size=D).tolist()
+    sel_s, sel_t = [1, 4], [3, 10]
+    t = {n: torch.from_numpy(v.copy()).requires_grad_(True) for n, v in arrs.items()}
+    args = types.SimpleNamespace(device="cpu", temperature=2.0)
+    maps_t, _, tgt_t = util.query_doc_attention_map(args, t["q_t"], t["d_t"], query_len, doc_len, sel_t)
+    maps_s, lsm_s, _ = util.query_doc_attention_map(args, t["q_s"], t["d_s"], query_len, doc_len, sel_s)
+    loss = util.virt_loss(maps_t, maps_s, 0.7)
+    loss.backward()
+    res = dict(arrs, query_len=np.array(query_len), doc_len=np.array(doc_len), sel_s=np.array(sel_s), sel_t=np.array(sel_t),
+               loss=np.array([loss.item()]), map_t0=maps_t[0].detach().numpy(), lsm_s1=lsm_s[1].detach().numpy(),
+               tgt_t1=tgt_t[1].detach().numpy())
+    for n, v in t.items():
+        res["d_" + n] = v.grad.numpy().copy()
+    np.savez_compressed(GOLD / "lead_virt.npz", **res)
+    print("lead_virt loss", loss.item())
+
+
 def golden_lead_colbert():
     """LEAD/models.py HFColBertEncoder (the ColBERT teacher tower) on a tiny BERT: normalised token embeddings, every
     layer's FULL hidden state, and the gradients of a loss built from the reference's own colbert_score on the final
@@ -693,6 +720,7 @@ def main():
     if only == ["lead_col"]:
         golden_lead_col_distill()
         golden_lead_colbert()
+        golden_lead_virt()
         return
     if only == ["lead"]:
         GOLD.mkdir(parents=True, exist_ok=True)
@@ -735,6 +763,7 @@ def main():
     golden_lead_select_layer()
     golden_lead_col_distill()
     golden_lead_colbert()
+    golden_lead_virt()
 
 
 if __name__ == "__main__":

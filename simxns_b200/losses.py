@@ -558,6 +558,38 @@ def lead_col_distill_loss(q_db, c_db, q_col, c_col, doc_mask, cls_q_db=None, cls
     return loss, parts
 
 
+def query_doc_attention_map(args, q_all_layer_hidden, d_all_layer_hidden, query_len, doc_len, selected_index_list):
+    """LEAD/util.py:504-529 (VIRT): per selected layer the token-level map softmax_over_doc_tokens(q_i . d_j) for every
+    (query, document) pair, positions beyond query_len[i] / doc_len[j] filled with -1e9 before the softmax.
+    q_all_layer_hidden [Q, L, Sq, H], d_all_layer_hidden [D, L, Sd, H] (towers with `full_layer_hidden = True`) ->
+    (maps, log-maps, maps at args.temperature), each a list of [Q, D, Sq, Sd].  Same values as the reference; the mask is
+    built from two comparisons instead of a Python loop over Q x D."""
+    import torch.nn.functional as F
+
+    dev = q_all_layer_hidden.device
+    Sq, Sd = q_all_layer_hidden.shape[2], d_all_layer_hidden.shape[2]
+    qv = torch.arange(Sq, device=dev)[None, :] < torch.as_tensor(query_len, device=dev)[:, None]   # [Q, Sq]
+    dv = torch.arange(Sd, device=dev)[None, :] < torch.as_tensor(doc_len, device=dev)[:, None]     # [D, Sd]
+    masked = ~(qv[:, None, :, None] & dv[None, :, None, :])                                          # [Q, D, Sq, Sd]
+    maps, scores, targets = [], [], []
+    for l in selected_index_list:
+        att = torch.einsum("ijk,mnk->imjn", q_all_layer_hidden[:, l], d_all_layer_hidden[:, l])     # [Q, D, Sq, Sd]
+        att = att.masked_fill(masked, -1e9)
+        scores.append(F.log_softmax(att, dim=-1))
+        targets.append(F.softmax(att / args.temperature, dim=-1))
+        maps.append(F.softmax(att, dim=-1))
+    return maps, scores, targets
+
+
+def virt_loss(query_doc_attention_t, query_doc_attention_s, distill_para):
+    """LEAD/util.py:531-537: sum of squared differences of the teacher's and the student's maps, averaged over layers,
+    queries and documents (NOT over token positions), times distill_para"""
+    total = 0
+    for t, s_ in zip(query_doc_attention_t, query_doc_attention_s):
+        total = total + ((s_ - t) ** 2).sum()
+    return total / len(query_doc_attention_t) / query_doc_attention_t[0].shape[0] / query_doc_attention_t[0].shape[1] * distill_para
+
+
 def select_layer(args):
     """LEAD's choice of the layer pairs whose [CLS] scores are distilled (/root/reference/LEAD/util.py:206-254), re-drawn
     every `save_steps` by run_LEAD.py.  Returns (selected_index_list_db, selected_index_list_teacher) for

@@ -116,3 +116,65 @@ def test_colbert_tower_vs_reference_golden(golden_dir):
         loss.backward()
         ref = {k[5:]: g[k] for k in g.files if k.startswith("grad/")}
         assert_grads(model, ref, tol_g, zero_true=("pooler.dense.weight", "pooler.dense.bias"))
+
+
+def test_virt_attention_distillation_through_both_towers():
+    """DE teacher (BERT) -> DB student (DistilBERT) with the token-level attention-map loss (--distill_de_db_attention,
+    LEAD/util.py:617-618, :643-644, :766-769): LEAD's towers with full_layer_hidden, losses.query_doc_attention_map /
+    virt_loss on the CUDA tensors; expected gradients = the same loss evaluated on the oracle's hidden states (float64) and
+    pushed through the oracle's backward."""
+    import types
+
+    from simxns_b200.losses import query_doc_attention_map, virt_loss
+
+    Q, D, Sq, Sd = 2, 4, 10, 20
+    args = types.SimpleNamespace(device="cuda", temperature=1.0)
+    sel_s, sel_t = [0, 1], [1, 3]
+    towers = {}
+    for name, arch, layers, seed in (("t", "bert", 4, 61), ("s", "distilbert", 2, 62)):
+        cfg = bn.bert_config(num_layers=layers, hidden=128, heads=2, intermediate=192, vocab=300, max_pos=64, arch=arch)
+        towers[name] = (cfg, bn.synth_params(cfg, seed=seed))
+    q_ids, q_mask = bn.synth_tokens(Q, Sq, 300, seed=63, ragged=True, min_len=3)
+    d_ids, d_mask = bn.synth_tokens(D, Sd, 300, seed=64, ragged=True, min_len=5)
+    qlen, dlen = q_mask.sum(1).tolist(), d_mask.sum(1).tolist()
+
+    # oracle side: hidden states in float64 -> torch leaf tensors -> the same loss -> d_hidden -> oracle backward
+    want, leaves, oracles = {}, {}, {}
+    for name, (cfg, params) in towers.items():
+        for side, ids, mask in (("q", q_ids, q_mask), ("d", d_ids, d_mask)):
+            o = bn.EncoderOracle(cfg, params)
+            h = np.stack(o.forward(ids, mask)["hidden"], axis=1)
+            oracles[name, side] = o
+            leaves[name, side] = torch.from_numpy(h).requires_grad_(True)
+    a64 = types.SimpleNamespace(device="cpu", temperature=1.0)
+    mt, _, _ = query_doc_attention_map(a64, leaves["t", "q"][:, 1:], leaves["t", "d"][:, 1:], qlen, dlen, sel_t)
+    ms, _, _ = query_doc_attention_map(a64, leaves["s", "q"][:, 1:], leaves["s", "d"][:, 1:], qlen, dlen, sel_s)
+    loss64 = virt_loss(mt, ms, 3.0)
+    loss64.backward()
+    for name in towers:
+        gq = oracles[name, "q"].backward(d_hidden=leaves[name, "q"].grad.numpy())
+        gd = oracles[name, "d"].backward(d_hidden=leaves[name, "d"].grad.numpy())
+        want[name] = {k: gq[k] + gd[k] for k in gq}           # one shared tower encodes queries and documents
+
+    models = {}
+    for name, (cfg, params) in towers.items():
+        cls_ = lead_models.HFBertEncoder if cfg["arch"] == "bert" else lead_models.HFDistilBertEncoder
+        m = cls_(ec_from(cfg), precision=X3)
+        m.load_state_dict({k: torch.from_numpy(v) for k, v in params.items()}, strict=True)
+        m.full_layer_hidden = True
+        models[name] = m.cuda().eval()
+    hid = {}
+    for name, m in models.items():
+        hid[name, "q"] = m(input_ids=cu(q_ids), attention_mask=cu(q_mask))[4]
+        hid[name, "d"] = m(input_ids=cu(d_ids), attention_mask=cu(d_mask))[4]
+        assert tuple(hid[name, "d"].shape) == (D, towers[name][0]["num_layers"], Sd, 128)
+    mt, _, _ = query_doc_attention_map(args, hid["t", "q"], hid["t", "d"], qlen, dlen, sel_t)
+    ms, _, _ = query_doc_attention_map(args, hid["s", "q"], hid["s", "d"], qlen, dlen, sel_s)
+    loss = virt_loss(mt, ms, 3.0)
+    assert abs(loss.item() - loss64.item()) < 1e-4 * max(1.0, abs(loss64.item()))
+    loss.backward()
+    for name, m in models.items():
+        top = towers[name][0]["num_layers"] - 1
+        dead = tuple(n for n, _ in m.named_parameters() if "pooler" in n or
+                     any(f"layer.{l}." in n for l in range(max(sel_t if name == "t" else sel_s) + 1, top + 1)))
+        assert_grads(m, want[name], 1e-3, zero_true=dead)   # north_star gradient tolerance (the maps exponentiate |logits| ~ 30)

@@ -55,3 +55,26 @@ def test_colbert_score_chunking_and_masked_documents(gold):
     with torch.no_grad():
         logits = torch.einsum("qih,djh->qidj", q, d).masked_fill(mask[None, None] == 0, -9e9)
         assert torch.allclose(whole, logits.max(3).values.sum(1), atol=1e-5)
+
+
+def test_virt_attention_maps_and_loss_vs_reference(golden_dir):
+    """LEAD/util.py:504-537 run by oracle/make_golden.py (tests/golden/lead_virt.npz)"""
+    import types
+
+    from simxns_b200.losses import query_doc_attention_map, virt_loss
+
+    g = np.load(golden_dir / "lead_virt.npz")
+    t = {n: torch.from_numpy(g[n].copy()).requires_grad_(True) for n in ("q_t", "d_t", "q_s", "d_s")}
+    args = types.SimpleNamespace(device="cpu", temperature=2.0)
+    ql, dl = g["query_len"].tolist(), g["doc_len"].tolist()
+    maps_t, _, tgt_t = query_doc_attention_map(args, t["q_t"], t["d_t"], ql, dl, g["sel_t"].tolist())
+    maps_s, lsm_s, _ = query_doc_attention_map(args, t["q_s"], t["d_s"], ql, dl, g["sel_s"].tolist())
+    assert np.allclose(maps_t[0].detach().numpy(), g["map_t0"], atol=1e-6)
+    assert np.allclose(tgt_t[1].detach().numpy(), g["tgt_t1"], atol=1e-6)
+    assert np.allclose(lsm_s[1].detach().numpy(), g["lsm_s1"], rtol=1e-5, atol=1e-3)   # entries are ~ -1e9 where masked
+    loss = virt_loss(maps_t, maps_s, 0.7)
+    assert abs(loss.item() - float(g["loss"][0])) < 1e-5
+    loss.backward()
+    for n in t:
+        want = g["d_" + n]
+        assert np.abs(t[n].grad.numpy() - want).max() <= 1e-7 + 1e-4 * np.abs(want).max(), n
