@@ -8,6 +8,7 @@
                              frozen initial student scores the batch for LwF, the student (DDP, dropout 0.1) takes
                              CrossBERTKDLoss (hard NLL + T^2 KL + LwF) forward + backward.
   lead           configs[4]  LEAD 12-layer BERT dual-encoder teacher / 6-layer DistilBERT student, both trained
+  lead_col       LEAD 12-layer ColBERT teacher / 6-layer DistilBERT student (distill_from_12cb_to_6de.sh), late interaction
                              (LEAD/distillation/distill_from_12de_to_6de.sh: --share_weight --distill_de --train_de --distill_db
                              --train_db --distill_de_db_layer_score --layer_score_reweight, 5 layer pairs): four tower passes,
                              all-gathered [CLS] rows of 1 + 5 layers, mutual KL + per-layer re-weighted KL, backward through
@@ -219,6 +220,60 @@ def bench_lead(R: Runner, args):
     return out
 
 
+def bench_lead_col(R: Runner, args):
+    """LEAD distillation/distill_from_12cb_to_6de.sh: 12-layer ColBERT teacher (trained) -> 6-layer DistilBERT student, late
+    interaction on the final token embeddings and on 5 selected teacher layers (full hidden states with gradients)"""
+    torch = R.torch
+    from simxns_b200 import _lib, lead_models
+    from simxns_b200.encoder import EncoderConfig
+    from simxns_b200.losses import lead_col_distill_loss
+
+    out = []
+    for nq in args.queries:
+        torch.manual_seed(0)
+        group, q_len, p_len = 16, 32, 128
+        t_cfg = EncoderConfig(num_layers=12)
+        s_cfg = EncoderConfig(arch="distilbert", num_layers=6, type_vocab=0)
+        col = lead_models.BiBertEncoder(types.SimpleNamespace(model_type="colbert"),
+                                        question_model=lead_models.HFColBertEncoder(t_cfg, precision=_lib.PREC_BF16)).to(R.dev)
+        db = lead_models.BiBertEncoder(None, question_model=lead_models.HFDistilBertEncoder(s_cfg, precision=_lib.PREC_BF16)).to(R.dev)
+        set_dropout(col, args.dropout)
+        set_dropout(db, args.dropout)
+        col.train()
+        db.train()
+        col_step, db_step = R.ddp(col), R.ddp(db)
+        q, qm = R.tokens(nq, q_len, t_cfg.vocab, 1)
+        p, pm = R.tokens(nq * group, p_len, t_cfg.vocab, 2)
+        sel_db, sel_col = [1, 2, 3, 4, 5], [7, 8, 9, 10, 11]
+
+        def step():
+            q_col, c_col, qh_col, ch_col, _ = col_step(q, qm, p, pm)
+            q_db, c_db, ql_db, cl_db, _ = db_step(q, qm, p, pm)
+            loss, _ = lead_col_distill_loss(q_db, c_db, q_col, c_col, pm, ql_db[:, :, 0], cl_db[:, :, 0], qh_col, ch_col,
+                                            selected_db=sel_db, selected_col=sel_col, temperature=1.0, layer_temperature=10.0,
+                                            reweight=True, train_col=True, gather=True)
+            loss.backward()
+            col.zero_grad(set_to_none=True)
+            db.zero_grad(set_to_none=True)
+            return loss
+
+        ms = R.timed(step, args.steps)
+        pairs = nq * group * R.world / (ms * 1e-3)
+        gq, gd = nq * R.world, nq * group * R.world
+        late = 6 * 3 * 2.0 * gq * q_len * gd * p_len * 768           # 6 score matrices, forward + two backward products
+        fl = 3 * (nq * fwd_flops(12, q_len) + nq * group * fwd_flops(12, p_len)) + \
+            3 * (nq * fwd_flops(6, q_len) + nq * group * fwd_flops(6, p_len)) + late
+        out.append(R.line(workload=f"lead_col (distill_from_12cb_to_6de.sh): 12L ColBERT teacher + 6L DistilBERT student, both "
+                                   f"trained (share_weight), MaxSim on final + 5 teacher layers (full hidden states), "
+                                   f"{nq} queries/GPU x 16, q_len {q_len}, p_len {p_len}, dropout {args.dropout}",
+                          metric="query+passage pairs/sec", value=pairs, unit="pairs/s", ms_per_step=ms, steps=args.steps,
+                          queries_per_gpu=nq, model_tflops_per_gpu=fl / (ms * 1e-3) / 1e12,
+                          late_interaction_tflop_per_step=late / 1e12))
+        del col, db, col_step, db_step
+        torch.cuda.empty_cache()
+    return out
+
+
 def bench_teacher_large(R: Runner, args):
     torch = R.torch
     from simxns_b200 import _lib
@@ -265,19 +320,19 @@ def bench_teacher_large(R: Runner, args):
 
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("--workload", required=True, choices=["prod_kd", "lead", "teacher_large"])
+    ap.add_argument("--workload", required=True, choices=["prod_kd", "lead", "lead_col", "teacher_large"])
     ap.add_argument("--queries", default="", help="comma-separated queries per GPU (defaults per workload)")
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--dropout", type=float, default=0.1, help="the reference recipes train with 0.1")
     ap.add_argument("--out", default="")
     args = ap.parse_args()
-    defaults = dict(prod_kd="8,64", lead="128", teacher_large="16,64")
+    defaults = dict(prod_kd="8,64", lead="128", lead_col="16", teacher_large="16,64")
     args.queries = [int(x) for x in (args.queries or defaults[args.workload]).split(",")]
     R = Runner()
     from simxns_b200 import _lib
 
     _lib.require_device()
-    res = dict(prod_kd=bench_prod_kd, lead=bench_lead, teacher_large=bench_teacher_large)[args.workload](R, args)
+    res = dict(prod_kd=bench_prod_kd, lead=bench_lead, lead_col=bench_lead_col, teacher_large=bench_teacher_large)[args.workload](R, args)
     if R.rank == 0 and args.out:
         Path(args.out).parent.mkdir(parents=True, exist_ok=True)
         with open(args.out, "a") as f:
