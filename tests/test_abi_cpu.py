@@ -105,6 +105,22 @@ def test_buffer_size_queries_and_invalid_configs():
     assert "hidden" in _lib.last_error()
 
 
+def test_hidden_state_entry_points_validate_their_arguments():
+    """simx_encoder_hidden_state / simx_encoder_add_cotangent reject a depth outside [0, L], a batch stride smaller than one
+    sequence and null buffers before touching any memory (checked here with dummy non-null addresses, no GPU involved)"""
+    lib = _lib.lib()
+    cfg = EncoderConfig(num_layers=2, hidden=64, heads=1, intermediate=64, vocab=32, max_pos=16).c_struct(_lib.PREC_BF16)
+    fake = 4096
+    assert lib.simx_encoder_hidden_state(C.byref(cfg), fake, 2, 8, 3, fake, 8 * 64, None) != 0
+    assert "index 3" in _lib.last_error()
+    assert lib.simx_encoder_hidden_state(C.byref(cfg), fake, 2, 8, 1, fake, 8 * 64 - 4, None) != 0
+    assert "out_stride_b" in _lib.last_error()
+    assert lib.simx_encoder_hidden_state(C.byref(cfg), None, 2, 8, 1, fake, 8 * 64, None) != 0
+    assert lib.simx_encoder_add_cotangent(C.byref(cfg), fake, 2, 8, None, 8 * 64, None) != 0
+    assert lib.simx_encoder_add_cotangent(C.byref(cfg), fake, 2, 8, fake, 8, None) != 0
+    assert "d_stride_b" in _lib.last_error()
+
+
 def test_forward_without_cuda_fails_loudly():
     """no CPU fallback: parameters on the CPU are an error, not a slow path"""
     ec = EncoderConfig(num_layers=1, hidden=64, heads=1, intermediate=64, vocab=32, max_pos=16)
