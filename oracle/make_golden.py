@@ -644,6 +644,18 @@ def golden_lead_col_distill():
         for n, v in t.items():
             res[f"{tag}_d_{n}"] = (v.grad if v.grad is not None else torch.zeros_like(v)).numpy().copy()
         print("lead_col_distill", tag, loss.item(), {k_: round(float(v_), 5) for k_, v_ in loss_dict.items()})
+    # ---- warm-up loss of the ColBERT tower: get_loss_dual's late-interaction branch (util.py:416-451, fill -1e4) ----
+    t = {n: torch.from_numpy(arrs[n].copy()).requires_grad_(True) for n in ("q_col", "c_col")}
+    args = types.SimpleNamespace(device="cpu", local_rank=-1, model_type="colbert")
+    loss = util.get_loss_dual(args, t["q_col"], t["c_col"], torch.from_numpy(doc_mask))
+    loss.backward()
+    res["warm_loss"] = np.array([loss.item()])
+    res["warm_d_q_col"], res["warm_d_c_col"] = t["q_col"].grad.numpy().copy(), t["c_col"].grad.numpy().copy()
+    ce_logits = mk(GQ, group)
+    tl = torch.from_numpy(ce_logits.copy()).requires_grad_(True)
+    lc = util.get_loss_cross(args, tl)
+    lc.backward()
+    res.update(ce_logits=ce_logits, ce_warm_loss=np.array([lc.item()]), ce_warm_d=tl.grad.numpy().copy())
     np.savez_compressed(GOLD / "lead_col_distill.npz", **res)
 
 

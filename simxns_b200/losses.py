@@ -459,7 +459,7 @@ class _ColbertScoreFn(torch.autograd.Function):
     routing of each chunk from the saved arg-max positions"""
 
     @staticmethod
-    def forward(ctx, q, d, keep, chunk):
+    def forward(ctx, q, d, keep, chunk, fill=-9e9):
         Q, Sq, H = q.shape
         D, Sd, _ = d.shape
         qf = q.reshape(Q * Sq, H)
@@ -468,7 +468,7 @@ class _ColbertScoreFn(torch.autograd.Function):
         for lo in range(0, D, chunk):
             hi = min(lo + chunk, D)
             logits = torch.matmul(qf, d[lo:hi].reshape(-1, H).t()).view(Q, Sq, hi - lo, Sd)
-            logits.masked_fill_(~keep[lo:hi][None, None], -9e9)
+            logits.masked_fill_(~keep[lo:hi][None, None], fill)
             mx, ix = logits.max(3)
             out[:, lo:hi] = mx.sum(1)
             idx[:, :, lo:hi] = ix
@@ -492,16 +492,41 @@ class _ColbertScoreFn(torch.autograd.Function):
             wf = w.view(Q * Sq, (hi - lo) * Sd)
             dq.addmm_(wf, d[lo:hi].reshape(-1, H))
             dd[lo:hi] = torch.matmul(wf.t(), qf).view(hi - lo, Sd, H)
-        return dq.view(Q, Sq, H), dd, None, None
+        return dq.view(Q, Sq, H), dd, None, None, None
 
 
-def colbert_score(q_embs_col, d_embs_col, attention_mask, q_num, chunk: int = 256):
+def colbert_score(q_embs_col, d_embs_col, attention_mask, q_num, chunk: int = 256, fill: float = -9e9):
     """LEAD/util.py:459-465: MaxSim late interaction.  q_embs_col [Q, Sq, H], d_embs_col [D, Sd, H], attention_mask [D, Sd]
     of the documents -> scores [q_num, D * Q / q_num]: sum over ALL query positions (padded ones included, as in the
     reference) of the maximum over the un-masked document tokens of q_i . d_j."""
     keep = attention_mask.reshape(d_embs_col.shape[0], d_embs_col.shape[1]) != 0
-    scores = _ColbertScoreFn.apply(q_embs_col, d_embs_col, keep, int(chunk))
+    scores = _ColbertScoreFn.apply(q_embs_col, d_embs_col, keep, int(chunk), float(fill))
     return scores.view(q_num, -1)
+
+
+def get_loss_cross(args, relevance_logits):
+    """LEAD/util.py:410-414: cross-entropy of the cross-encoder's [B, 1+n] relevance logits, positive in column 0"""
+    target = torch.zeros(relevance_logits.size(0), dtype=torch.long, device=relevance_logits.device)
+    return torch.nn.functional.cross_entropy(relevance_logits, target)
+
+
+def get_loss_dual(args, local_q_vector, local_ctx_vectors, attention_mask, reduction='mean'):
+    """LEAD/util.py:416-451 (run_single_model.py warm-up of every tower type): in-batch InfoNCE over the embeddings of all
+    ranks, positives at `i * (1+n)`.  Dual encoders: the fused global kernel on the all-gathered [CLS] embeddings.
+    `'colbert' in args.model_type`: late-interaction scores (masked document tokens filled with -1e4, as there) on the
+    all-gathered token embeddings.  The reference gathers the embeddings but not `attention_mask`; here the mask travels
+    with them."""
+    if reduction != 'mean':
+        raise NotImplementedError("get_loss_dual: only reduction='mean' (the only value the reference's callers pass)")
+    if 'colbert' in getattr(args, "model_type", ""):
+        q, c, m = gather_tensor(local_q_vector.contiguous()), gather_tensor(local_ctx_vectors.contiguous()), gather_tensor(attention_mask)
+        q_num = q.size(0)
+        scores = colbert_score(q, c, m, q_num, fill=-1e4)
+        target = torch.arange(0, c.size(0), c.size(0) // q_num, device=scores.device, dtype=torch.long)
+        return torch.nn.functional.nll_loss(torch.nn.functional.log_softmax(scores, dim=1), target)
+    group = local_ctx_vectors.shape[0] // local_q_vector.shape[0]
+    loss, _ = fused_score_loss(local_q_vector, local_ctx_vectors, ["nll_global"], group_size=group, gather=True)
+    return loss
 
 
 def lead_col_distill_loss(q_db, c_db, q_col, c_col, doc_mask, cls_q_db=None, cls_c_db=None, hid_q_col=None, hid_c_col=None, *,

@@ -178,3 +178,23 @@ def test_virt_attention_distillation_through_both_towers():
         dead = tuple(n for n, _ in m.named_parameters() if "pooler" in n or
                      any(f"layer.{l}." in n for l in range(max(sel_t if name == "t" else sel_s) + 1, top + 1)))
         assert_grads(m, want[name], 1e-3, zero_true=dead)   # north_star gradient tolerance (the maps exponentiate |logits| ~ 30)
+
+
+def test_get_loss_dual_dense_branch_is_the_fused_global_kernel():
+    """LEAD/util.py:416-451 for dual encoders: log-softmax over all passages, positives at i * (1+n); loss and gradients
+    against the same formula in torch (float64)"""
+    import types
+
+    from simxns_b200.losses import get_loss_dual
+
+    g = torch.Generator().manual_seed(5)
+    q = torch.randn(6, 128, generator=g).cuda().requires_grad_(True)
+    c = torch.randn(24, 128, generator=g).cuda().requires_grad_(True)
+    loss = get_loss_dual(types.SimpleNamespace(model_type="dual_encoder"), q, c, None)
+    loss.backward()
+    q64, c64 = q.detach().double().requires_grad_(True), c.detach().double().requires_grad_(True)
+    want = torch.nn.functional.nll_loss(torch.log_softmax(q64 @ c64.t(), dim=1), torch.arange(0, 24, 4, device="cuda"))
+    want.backward()
+    assert abs(loss.item() - want.item()) < 1e-4
+    assert torch.allclose(q.grad.double(), q64.grad, atol=1e-4, rtol=1e-3)
+    assert torch.allclose(c.grad.double(), c64.grad, atol=1e-4, rtol=1e-3)

@@ -78,3 +78,25 @@ def test_virt_attention_maps_and_loss_vs_reference(golden_dir):
     for n in t:
         want = g["d_" + n]
         assert np.abs(t[n].grad.numpy() - want).max() <= 1e-7 + 1e-4 * np.abs(want).max(), n
+
+
+def test_warm_up_losses_vs_reference(gold):
+    """get_loss_dual's late-interaction branch and get_loss_cross (LEAD/util.py:410-451), reference values in the fixture"""
+    import types
+
+    from simxns_b200.losses import get_loss_cross, get_loss_dual
+
+    args = types.SimpleNamespace(device="cpu", local_rank=-1, model_type="colbert")
+    q = torch.from_numpy(gold["q_col"].copy()).requires_grad_(True)
+    c = torch.from_numpy(gold["c_col"].copy()).requires_grad_(True)
+    loss = get_loss_dual(args, q, c, torch.from_numpy(gold["doc_mask"]))
+    assert abs(loss.item() - float(gold["warm_loss"][0])) < 1e-6
+    loss.backward()
+    assert np.allclose(q.grad.numpy(), gold["warm_d_q_col"], atol=1e-7, rtol=1e-4)
+    assert np.allclose(c.grad.numpy(), gold["warm_d_c_col"], atol=1e-7, rtol=1e-4)
+    t = torch.from_numpy(gold["ce_logits"].copy()).requires_grad_(True)
+    lc = get_loss_cross(args, t)
+    lc.backward()
+    assert abs(lc.item() - float(gold["ce_warm_loss"][0])) < 1e-6 and np.allclose(t.grad.numpy(), gold["ce_warm_d"], atol=1e-7)
+    with pytest.raises(RuntimeError, match="CUDA"):      # the dual-encoder branch is the fused kernel: no CPU path
+        get_loss_dual(types.SimpleNamespace(model_type="dual_encoder"), q[:, 0], c[:, 0], None)
