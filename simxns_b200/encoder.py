@@ -429,7 +429,7 @@ class _TowerPass:
                                                              Lh * S * ec.hidden, stream), "simx_encoder_hidden_state")
                 if not needs_grad:
                     saved = None
-        self.hidden, self.d_hidden = hidden, None
+        self.hidden, self.d_hidden, self.has_hidden = hidden, None, hidden is not None
         self.module, self.cfg, self.dev = module, cfg, dev
         self.ids, self.mask, self.pos_ids, self.shape = ids, mask, pos_ids, (B, S)
         self.embeds = embeds is not None  # backward also produces d(loss)/d(inputs_embeds)
@@ -443,12 +443,16 @@ class _TowerPass:
         self.monolithic = False
         self.sink = module._grad_sink if needs_grad else None
 
+    def token(self) -> torch.Tensor:
+        """the empty tensor that chains the autograd nodes of one pass"""
+        return torch.empty(0, dtype=torch.float32, device=self.dev)
+
     def begin_backward(self, d_cls, d_seq, d_hidden=None) -> bool:
         """called by the top node; False when no cotangent reaches the tower"""
         if self.saved is None:
             raise RuntimeError("encoder backward without saved activations (already freed by an earlier backward, or the "
                                "forward ran under no_grad)")
-        if d_hidden is not None and self.hidden is None:
+        if d_hidden is not None and not self.has_hidden:
             d_hidden = None
         if d_cls is None and (d_seq is None or not self.want_seq) and d_hidden is None:
             return False
@@ -542,7 +546,7 @@ class _EmbedNode(torch.autograd.Function):
     @staticmethod
     def forward(ctx, st: _TowerPass, *params):
         ctx.st, ctx.params = st, params
-        return st.cls.new_empty(0)
+        return st.token()
 
     @staticmethod
     @torch.autograd.function.once_differentiable
@@ -559,7 +563,7 @@ class _LayerNode(torch.autograd.Function):
     @staticmethod
     def forward(ctx, st: _TowerPass, layer: int, token, *params):
         ctx.st, ctx.layer, ctx.params = st, layer, params
-        return st.cls.new_empty(0)
+        return st.token()
 
     @staticmethod
     @torch.autograd.function.once_differentiable
@@ -568,7 +572,7 @@ class _LayerNode(torch.autograd.Function):
         l = ctx.layer
         if st.flat is not None:
             st.run_slice(l, st.next_hi)  # normally [l, l+1); wider when the nodes above were pruned
-        token_grad = st.cls.new_empty(0) if ctx.needs_input_grad[2] else None
+        token_grad = st.token() if ctx.needs_input_grad[2] else None
         if token_grad is None:  # nothing trainable below: this node is the bottom of the chain
             st.finish()
         return (None, None, token_grad) + st.grads_for(ctx.params, ctx.needs_input_grad[3:])
@@ -581,17 +585,20 @@ class _TopNode(torch.autograd.Function):
     def forward(ctx, st: _TowerPass, token, *params):
         ctx.st, ctx.params = st, params
         ctx.set_materialize_grads(False)
-        seq, hidden = st.seq, st.hidden
+        # the pass state must not keep the tensors it hands out: output.grad_fn -> this node -> ctx.st -> output would be a
+        # reference cycle, and the saved activations / gradient buffer of every step would wait for the cyclic collector
+        cls, seq, hidden = st.cls, st.seq, st.hidden
+        st.cls = st.seq = st.hidden = None
         dead = []
         if seq is None:
-            seq = st.cls.new_empty(0)
+            seq = st.token()
             dead.append(seq)
         if hidden is None:
-            hidden = st.cls.new_empty(0)
+            hidden = st.token()
             dead.append(hidden)
         if dead:
             ctx.mark_non_differentiable(*dead)
-        return st.cls, seq, hidden
+        return cls, seq, hidden
 
     @staticmethod
     @torch.autograd.function.once_differentiable
@@ -604,7 +611,7 @@ class _TopNode(torch.autograd.Function):
                 st.finish()
             d_in = st.d_embeds if (st.embeds and ctx.needs_input_grad[1]) else None  # `token` slot = inputs_embeds here
             return (None, d_in) + st.grads_for(ctx.params, ctx.needs_input_grad[2:])
-        token_grad = st.cls.new_empty(0) if (live and ctx.needs_input_grad[1]) else None
+        token_grad = st.token() if (live and ctx.needs_input_grad[1]) else None
         # pooler parameters: dead math in the reference (multiplied by 0), dense zero gradients.  Their slice of
         # the flat buffer is zeroed by the first backward slice, which has not run yet — hand out fresh zeros instead.
         grads = tuple(torch.zeros_like(p) if (live and need and st.sink is None) else None

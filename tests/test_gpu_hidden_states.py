@@ -198,3 +198,29 @@ def test_get_loss_dual_dense_branch_is_the_fused_global_kernel():
     assert abs(loss.item() - want.item()) < 1e-4
     assert torch.allclose(q.grad.double(), q64.grad, atol=1e-4, rtol=1e-3)
     assert torch.allclose(c.grad.double(), c64.grad, atol=1e-4, rtol=1e-3)
+
+
+def test_pass_state_is_released_by_reference_counting():
+    """outputs -> grad_fn -> pass state must not loop back to the outputs: with the cyclic collector switched off the memory
+    in use after each step (saved activations, hidden states, the flat gradient buffer) has to return to the same level"""
+    import gc
+
+    cfg = bn.bert_config(num_layers=2, hidden=128, heads=2, intermediate=256, vocab=300, max_pos=128)
+    model = build(cfg, bn.synth_params(cfg, seed=1), BF16).train()
+    ids, mask = bn.synth_tokens(64, 128, cfg["vocab"], seed=3)
+    ids, mask = cu(ids), cu(mask)
+    gc.collect()
+    gc.disable()
+    try:
+        levels = []
+        for _ in range(4):
+            cls, seq, hidden = model.encode(ids, mask, want_sequence=True, want_hidden=True)
+            (cls.sum() + seq.sum() + hidden[:, 1].sum()).backward()
+            model.zero_grad(set_to_none=True)
+            del cls, seq, hidden
+            model.last_cls_layers = None
+            torch.cuda.synchronize()
+            levels.append(torch.cuda.memory_allocated())
+        assert levels[1] == levels[2] == levels[3], levels
+    finally:
+        gc.enable()

@@ -61,6 +61,10 @@ def main():
         qe.grad = de.grad = None
 
     res["colbert_score_fwd_bwd_ms"] = timed(score)
+    res["peak_before_step_gb"] = torch.cuda.max_memory_allocated() / 2**30
+    del qe, de
+    torch.cuda.empty_cache()
+    torch.cuda.reset_peak_memory_stats()
 
     # the whole step, phase by phase (host clock around synchronised phases: includes launch / Python overhead)
     import time
@@ -75,12 +79,19 @@ def main():
         q_col, c_col, qh_col, ch_col, _ = colm(q, qm, p, pm)
         q_db, c_db, ql_db, cl_db, _ = db(q, qm, p, pm)
         torch.cuda.synchronize(); t1 = time.perf_counter()
+        if it == 3:
+            res["mem_after_towers_fwd_gb"] = torch.cuda.memory_allocated() / 2**30
         loss, _ = lead_col_distill_loss(q_db, c_db, q_col, c_col, pm, ql_db[:, :, 0], cl_db[:, :, 0], qh_col, ch_col,
                                         selected_db=sel_db, selected_col=sel_col, temperature=1.0, layer_temperature=10.0,
                                         reweight=True, train_col=True, gather=False)
         torch.cuda.synchronize(); t2 = time.perf_counter()
+        if it == 3:
+            res["mem_after_loss_fwd_gb"] = torch.cuda.memory_allocated() / 2**30
+            torch.cuda.reset_peak_memory_stats()
         loss.backward()
         torch.cuda.synchronize(); t3 = time.perf_counter()
+        if it == 3:
+            res["peak_during_backward_gb"] = torch.cuda.max_memory_allocated() / 2**30
         colm.zero_grad(set_to_none=True); db.zero_grad(set_to_none=True)
         if it >= 3:
             phases["towers_fwd"] += (t1 - t0) * 1e3 / n
