@@ -115,6 +115,7 @@ attn_fwd_tc_kernel(const AttnTcParams p, const __grid_constant__ CUtensorMap map
   const int row = warp * 32 + lane;
   const uint32_t taddr = tmem + (static_cast<uint32_t>(warp * 32) << 16);
   const float sl2 = 0.125f * TC_LOG2E;
+  const float2 sl22 = make_float2(sl2, sl2);
   float m = TC_NEG;
 #pragma unroll 1
   for (int c = 0; c < 4; ++c) {
@@ -122,9 +123,14 @@ attn_fwd_tc_kernel(const AttnTcParams p, const __grid_constant__ CUtensorMap map
     tmem_ld_32x32(taddr + c * 32, v);
     tmem_ld_wait();
 #pragma unroll
-    for (int i = 0; i < 32; ++i) m = fmaxf(m, fmaf(__uint_as_float(v[i]), sl2, bias[c * 32 + i]));
+    for (int i = 0; i < 16; ++i) {  // packed fp32: one FFMA2 per key pair
+      const float2 e = __ffma2_rn(make_float2(__uint_as_float(v[2 * i]), __uint_as_float(v[2 * i + 1])), sl22,
+                                  *reinterpret_cast<const float2*>(&bias[c * 32 + 2 * i]));
+      m = fmaxf(m, fmaxf(e.x, e.y));
+    }
   }
-  float l = 0.f;
+  float2 lp = make_float2(0.f, 0.f);
+  const float2 nm2 = make_float2(-m, -m);
 #pragma unroll 1
   for (int c = 0; c < 4; ++c) {
     uint32_t v[32];
@@ -138,9 +144,10 @@ attn_fwd_tc_kernel(const AttnTcParams p, const __grid_constant__ CUtensorMap map
 #pragma unroll
       for (int ii = 0; ii < 4; ++ii) {
         const int i = g8 * 4 + ii;
-        float p0 = ex2(fmaf(__uint_as_float(v[2 * i]), sl2, bias[c * 32 + 2 * i]) - m);
-        float p1 = ex2(fmaf(__uint_as_float(v[2 * i + 1]), sl2, bias[c * 32 + 2 * i + 1]) - m);
-        l += p0 + p1;  // the softmax normaliser is that of the un-dropped probabilities
+        const float2 e = __fadd2_rn(__ffma2_rn(make_float2(__uint_as_float(v[2 * i]), __uint_as_float(v[2 * i + 1])), sl22,
+                                               *reinterpret_cast<const float2*>(&bias[c * 32 + 2 * i])), nm2);
+        float p0 = ex2(e.x), p1 = ex2(e.y);
+        lp = __fadd2_rn(lp, make_float2(p0, p1));  // the softmax normaliser is that of the un-dropped probabilities
         if constexpr (DROP) drop_pair(p0, p1, u4_word(rb, ii), p.drop.thr_hi);
         pk[i] = pack_bf16x2(p0, p1);
       }
@@ -150,6 +157,7 @@ attn_fwd_tc_kernel(const AttnTcParams p, const __grid_constant__ CUtensorMap map
     for (int g = 0; g < 4; ++g)
       st_shared_v4(sQ + p_off(row, c * 4 + g), make_uint4(pk[4 * g], pk[4 * g + 1], pk[4 * g + 2], pk[4 * g + 3]));
   }
+  const float l = lp.x + lp.y;
   if (row < S && p.lse2 != nullptr) p.lse2[((long)b * p.heads + h) * S + row] = m + log2f(l);
   fence_proxy_async_smem();
   tc_fence_before();
@@ -170,14 +178,16 @@ attn_fwd_tc_kernel(const AttnTcParams p, const __grid_constant__ CUtensorMap map
     uint32_t v[32];
     tmem_ld_32x32(taddr + c * 32, v);
     tmem_ld_wait();
+    const float2 inv2 = make_float2(inv, inv);
 #pragma unroll
     for (int g = 0; g < 4; ++g) {
-      uint4 o;
-      o.x = pack_bf16x2(__uint_as_float(v[8 * g]) * inv, __uint_as_float(v[8 * g + 1]) * inv);
-      o.y = pack_bf16x2(__uint_as_float(v[8 * g + 2]) * inv, __uint_as_float(v[8 * g + 3]) * inv);
-      o.z = pack_bf16x2(__uint_as_float(v[8 * g + 4]) * inv, __uint_as_float(v[8 * g + 5]) * inv);
-      o.w = pack_bf16x2(__uint_as_float(v[8 * g + 6]) * inv, __uint_as_float(v[8 * g + 7]) * inv);
-      st_shared_v4(sV + p_off(row, c * 4 + g), o);  // V is dead after the second MMA group; j < 8 stays in this tile
+      uint32_t w[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const float2 f = __fmul2_rn(make_float2(__uint_as_float(v[8 * g + 2 * k]), __uint_as_float(v[8 * g + 2 * k + 1])), inv2);
+        w[k] = pack_bf16x2(f.x, f.y);
+      }
+      st_shared_v4(sV + p_off(row, c * 4 + g), make_uint4(w[0], w[1], w[2], w[3]));  // V is dead after the second MMA group
     }
   }
   fence_proxy_async_smem();
@@ -411,17 +421,15 @@ attn_bwd_tc_kernel(const AttnTcParams p, const __grid_constant__ CUtensorMap map
   const int row = quarter * 32 + lane;
   mbar_wait(&bars[0], 0);
   SIMX_STAMP(2);
-  float delta = 0.f;
+  float2 dacc = make_float2(0.f, 0.f);
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
     const uint4 x = ld_shared_v4(sdO + p_off(row, j)), y = ld_shared_v4(sO + p_off(row, j));
     const uint32_t xs[4] = {x.x, x.y, x.z, x.w}, ys[4] = {y.x, y.y, y.z, y.w};
 #pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      const float2 fx = unpack_bf16x2(xs[k]), fy = unpack_bf16x2(ys[k]);
-      delta += fx.x * fy.x + fx.y * fy.y;
-    }
+    for (int k = 0; k < 4; ++k) dacc = __ffma2_rn(unpack_bf16x2(xs[k]), unpack_bf16x2(ys[k]), dacc);
   }
+  const float delta = dacc.x + dacc.y;
   const float lse = q0 + row < S ? p.lse2[((long)b * p.heads + h) * S + q0 + row] : 0.f;
   __syncthreads();  // both column-halves have read their O row before anyone overwrites that tile with dS
   mbar_wait(&bars[1], 0);
@@ -430,6 +438,7 @@ attn_bwd_tc_kernel(const AttnTcParams p, const __grid_constant__ CUtensorMap map
 
   const uint32_t taddr = tmem + (static_cast<uint32_t>(quarter * 32) << 16);
   const float sl2 = 0.125f * TC_LOG2E;
+  const float2 sl22 = make_float2(sl2, sl2), nlse2 = make_float2(-lse, -lse), ndelta2 = make_float2(-delta, -delta);
   const bool rv = q0 + row < S;
 #pragma unroll 1
   for (int c = half * 2; c < half * 2 + 2; ++c) {
@@ -445,18 +454,24 @@ attn_bwd_tc_kernel(const AttnTcParams p, const __grid_constant__ CUtensorMap map
 #pragma unroll
       for (int ii = 0; ii < 4; ++ii) {
         const int i = g8 * 4 + ii;
-        float p0 = ex2(fmaf(__uint_as_float(s[2 * i]), sl2, bias[c * 32 + 2 * i]) - lse);
-        float p1 = ex2(fmaf(__uint_as_float(s[2 * i + 1]), sl2, bias[c * 32 + 2 * i + 1]) - lse);
-        if (!rv) { p0 = 0.f; p1 = 0.f; }
+        // packed fp32 (FFMA2 / FADD2 / FMUL2): one instruction per key PAIR
+        const float2 sv = make_float2(__uint_as_float(s[2 * i]), __uint_as_float(s[2 * i + 1]));
+        const float2 dv = make_float2(__uint_as_float(d[2 * i]), __uint_as_float(d[2 * i + 1]));
+        const float2 e = __fadd2_rn(__ffma2_rn(sv, sl22, *reinterpret_cast<const float2*>(&bias[c * 32 + 2 * i])), nlse2);
+        float2 pp = make_float2(ex2(e.x), ex2(e.y));
+        if (!rv) pp = make_float2(0.f, 0.f);
         if constexpr (DROP) {
           // forward used P~ = P o mask * scale: dV = P~^T dO, dS = P o (mask * scale * dP - delta), delta = rowsum(dO o O)
-          float m0 = p.drop.scale, m1 = p.drop.scale;
-          drop_pair(m0, m1, u4_word(rb, ii), p.drop.thr_hi);
-          pk[i] = pack_bf16x2(p0 * m0, p1 * m1);
-          dk[i] = pack_bf16x2(p0 * (m0 * __uint_as_float(d[2 * i]) - delta), p1 * (m1 * __uint_as_float(d[2 * i + 1]) - delta));
+          float2 m = make_float2(p.drop.scale, p.drop.scale);
+          drop_pair(m.x, m.y, u4_word(rb, ii), p.drop.thr_hi);
+          const float2 pm = __fmul2_rn(pp, m);
+          const float2 ds = __fmul2_rn(pp, __ffma2_rn(m, dv, ndelta2));
+          pk[i] = pack_bf16x2(pm.x, pm.y);
+          dk[i] = pack_bf16x2(ds.x, ds.y);
         } else {
-          pk[i] = pack_bf16x2(p0, p1);
-          dk[i] = pack_bf16x2(p0 * (__uint_as_float(d[2 * i]) - delta), p1 * (__uint_as_float(d[2 * i + 1]) - delta));
+          const float2 ds = __fmul2_rn(pp, __fadd2_rn(dv, ndelta2));
+          pk[i] = pack_bf16x2(pp.x, pp.y);
+          dk[i] = pack_bf16x2(ds.x, ds.y);
         }
       }
     }
@@ -500,13 +515,16 @@ attn_bwd_tc_kernel(const AttnTcParams p, const __grid_constant__ CUtensorMap map
       tmem_ld_32x32(taddr + t * 64 + c * 32, v);
       tmem_ld_wait();
 #pragma unroll
+      const float2 sc2 = make_float2(sc, sc);
+#pragma unroll
       for (int g = 0; g < 4; ++g) {
-        uint4 o;
-        o.x = pack_bf16x2(__uint_as_float(v[8 * g]) * sc, __uint_as_float(v[8 * g + 1]) * sc);
-        o.y = pack_bf16x2(__uint_as_float(v[8 * g + 2]) * sc, __uint_as_float(v[8 * g + 3]) * sc);
-        o.z = pack_bf16x2(__uint_as_float(v[8 * g + 4]) * sc, __uint_as_float(v[8 * g + 5]) * sc);
-        o.w = pack_bf16x2(__uint_as_float(v[8 * g + 6]) * sc, __uint_as_float(v[8 * g + 7]) * sc);
-        st_shared_v4(sQ + t * TILE + p_off(row, c * 4 + g), o);
+        uint32_t w[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const float2 f = __fmul2_rn(make_float2(__uint_as_float(v[8 * g + 2 * k]), __uint_as_float(v[8 * g + 2 * k + 1])), sc2);
+          w[k] = pack_bf16x2(f.x, f.y);
+        }
+        st_shared_v4(sQ + t * TILE + p_off(row, c * 4 + g), make_uint4(w[0], w[1], w[2], w[3]));
       }
     }
   }

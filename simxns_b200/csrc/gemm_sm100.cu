@@ -142,37 +142,39 @@ __device__ __forceinline__ void gelu_exact(float x, float& g, float& dg) {
 template <int EPI, int NP>
 __device__ __forceinline__ void epi_values(const GemmParams& p, int row, int col, const uint32_t* acc8,
                                            const EpiPre<EPI, NP>& pre, int g, const float* sbias, float (&v)[8]) {
+  // packed fp32 arithmetic (sm_100 FADD2 / FMUL2: two values per instruction): the epilogue competes with the MMA issue
+  // for ~24 issue slots per output element, and a 3-register scalar FADD only issues every other cycle per scheduler
+  float2(&v2)[4] = reinterpret_cast<float2(&)[4]>(v);
 #pragma unroll
-  for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(acc8[i]);
+  for (int i = 0; i < 4; ++i) v2[i] = make_float2(__uint_as_float(acc8[2 * i]), __uint_as_float(acc8[2 * i + 1]));
   if constexpr (EpiPre<EPI, NP>::kBias) {
     // bias from shared memory (the epilogue's own store traffic keeps evicting it from the small L1)
     const float* bsrc = sbias != nullptr ? sbias + col : p.bias + col;
     const float4 b0 = *reinterpret_cast<const float4*>(bsrc);
     const float4 b1 = *reinterpret_cast<const float4*>(bsrc + 4);
-    v[0] += b0.x; v[1] += b0.y; v[2] += b0.z; v[3] += b0.w;
-    v[4] += b1.x; v[5] += b1.y; v[6] += b1.z; v[7] += b1.w;
+    v2[0] = __fadd2_rn(v2[0], make_float2(b0.x, b0.y));
+    v2[1] = __fadd2_rn(v2[1], make_float2(b0.z, b0.w));
+    v2[2] = __fadd2_rn(v2[2], make_float2(b1.x, b1.y));
+    v2[3] = __fadd2_rn(v2[3], make_float2(b1.z, b1.w));
   }
   if constexpr (EPI == EPI_BIAS_DROP_ADD)  // dropout sits between the dense layer and the residual add
     drop_apply8(v, drop_bits(p.drop, static_cast<uint32_t>(col) >> 3, static_cast<uint32_t>(row), 0u), p.drop.thr_hi,
                 p.drop.scale);
   if constexpr (EpiPre<EPI, NP>::kAux) {
-    float a[8];
-#pragma unroll
-    for (int i = 0; i < 8; ++i) a[i] = 0.f;
+    float2 a[4];
 #pragma unroll
     for (int q = 0; q < NP; ++q) {
       const uint32_t w[4] = {pre.aux[q][g].x, pre.aux[q][g].y, pre.aux[q][g].z, pre.aux[q][g].w};
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
         const float2 f = unpack_bf16x2(w[i]);
-        a[2 * i] += f.x;
-        a[2 * i + 1] += f.y;
+        a[i] = q == 0 ? f : __fadd2_rn(a[i], f);
       }
     }
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      if constexpr (EPI == SIMX_EPI_MUL) v[i] *= a[i];
-      else v[i] += a[i];
+    for (int i = 0; i < 4; ++i) {
+      if constexpr (EPI == SIMX_EPI_MUL) v2[i] = __fmul2_rn(v2[i], a[i]);
+      else v2[i] = __fadd2_rn(v2[i], a[i]);
     }
   }
 }
@@ -512,14 +514,13 @@ gemm_kernel(const GemmParams p, const __grid_constant__ CUtensorMap mapA, const 
               // half-warps start one row apart so that their 64-byte rows fall into different bank halves)
               const int pr = lane & 15, hsel = lane >> 4;
               const uint32_t sb = smem_u32(box) + ((pr & 3) << 2);
-              float s0 = 0.f, s1 = 0.f;
+              float2 sp = make_float2(0.f, 0.f);
 #pragma unroll 8
               for (int k = 0; k < 16; ++k) {
                 const int r = hsel * 16 + ((k + hsel) & 15);
-                const float2 f2 = unpack_bf16x2(ld_shared_u32(sb + r * 64 + ((((pr >> 2) ^ (r >> 1)) & 3) << 4)));
-                s0 += f2.x;
-                s1 += f2.y;
+                sp = __fadd2_rn(sp, unpack_bf16x2(ld_shared_u32(sb + r * 64 + ((((pr >> 2) ^ (r >> 1)) & 3) << 4))));
               }
+              float s0 = sp.x, s1 = sp.y;
               s0 += __shfl_xor_sync(0xffffffffu, s0, 16);
               s1 += __shfl_xor_sync(0xffffffffu, s1, 16);
               const int col = col_base + c * 32 + 2 * pr;

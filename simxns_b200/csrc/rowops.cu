@@ -20,6 +20,9 @@ __device__ __forceinline__ void ld8f(const float* p, float (&v)[8]) {
   v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
 }
 
+// four packed pairs seen as the eight floats the load / store / dropout helpers take
+__device__ __forceinline__ float (&as8(float2 (&v)[4]))[8] { return reinterpret_cast<float (&)[8]>(v); }
+
 // normalise the row held in v (NC chunks of 8 per lane), write y = xhat * g + b
 template <int NP>
 __device__ __forceinline__ void ln_row_store(float (&v)[MAXC][8], int H, int lane, const float* gamma,
@@ -131,13 +134,13 @@ __global__ void __launch_bounds__(ROW_THREADS)
 ln_fwd_kernel(const bf16* __restrict__ z, int T, int H, const float* __restrict__ gamma,
               const float* __restrict__ beta, float eps, bf16* x, long ps, int rpw) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  float g[NC][8], b[NC][8];
+  float2 g[NC][4], b[NC][4];
 #pragma unroll
   for (int c = 0; c < NC; ++c) {
     const int col = c * 256 + lane * 8;
     if (col < H) {
-      ld8f(gamma + col, g[c]);
-      ld8f(beta + col, b[c]);
+      ld8f(gamma + col, as8(g[c]));
+      ld8f(beta + col, as8(b[c]));
     }
   }
   uint4 nxt[NC][NP];
@@ -160,36 +163,38 @@ ln_fwd_kernel(const bf16* __restrict__ z, int T, int H, const float* __restrict_
   for (; r0 < T; r0 += stride) {
     const long r1 = min((long)T, r0 + rpw);
     for (long r = r0; r < r1; ++r) {
-      float v[NC][8];
-      float s = 0.f;
+      float2 v[NC][4];                       // packed fp32 (FADD2 / FFMA2 / FMUL2): half the issue slots of the scalar form
+      float2 sp = make_float2(0.f, 0.f);
 #pragma unroll
       for (int c = 0; c < NC; ++c)
         if (c * 256 + lane * 8 < H) {
-          unpack8<NP>(nxt[c], v[c]);
+          unpack8<NP>(nxt[c], as8(v[c]));
 #pragma unroll
-          for (int i = 0; i < 8; ++i) s += v[c][i];
+          for (int i = 0; i < 4; ++i) sp = __fadd2_rn(sp, v[c][i]);
         }
       if (r + 1 < r1) fetch(r + 1);
       else if (r0 + stride < T) fetch(r0 + stride);
-      const float mean = warp_sum(s) * invH;
-      float q2 = 0.f;
+      const float mean = warp_sum(sp.x + sp.y) * invH;
+      const float2 nmean = make_float2(-mean, -mean);
+      float2 qp = make_float2(0.f, 0.f);
 #pragma unroll
       for (int c = 0; c < NC; ++c)
         if (c * 256 + lane * 8 < H)
 #pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            v[c][i] -= mean;
-            q2 += v[c][i] * v[c][i];
+          for (int i = 0; i < 4; ++i) {
+            v[c][i] = __fadd2_rn(v[c][i], nmean);
+            qp = __ffma2_rn(v[c][i], v[c][i], qp);
           }
-      const float rstd = rsqrtf(warp_sum(q2) * invH + eps);
+      const float rstd = rsqrtf(warp_sum(qp.x + qp.y) * invH + eps);
+      const float2 rstd2 = make_float2(rstd, rstd);
 #pragma unroll
       for (int c = 0; c < NC; ++c) {
         const int col = c * 256 + lane * 8;
         if (col < H) {
-          float y[8];
+          float2 y[4];
 #pragma unroll
-          for (int i = 0; i < 8; ++i) y[i] = v[c][i] * rstd * g[c][i] + b[c][i];
-          split_store8<NP>(x + r * H + col, ps, y);
+          for (int i = 0; i < 4; ++i) y[i] = __ffma2_rn(__fmul2_rn(v[c][i], rstd2), g[c][i], b[c][i]);
+          split_store8<NP>(x + r * H + col, ps, as8(y));
         }
       }
     }
@@ -215,11 +220,11 @@ ln_bwd_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ z, int T, in
               float eps, bf16* dz, long ps, float* dgamma, float* dbeta, float* dbias, bf16* dzm, const DropSpec drop) {
   __shared__ float red[LNB_WARPS][32 * 8 + 8];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  float ag[NC][8], ab[NC][8], ad[NC][8];
+  float2 ag[NC][4], ab[NC][4], ad[NC][4];
 #pragma unroll
   for (int c = 0; c < NC; ++c)
 #pragma unroll
-    for (int i = 0; i < 8; ++i) ag[c][i] = ab[c][i] = ad[c][i] = 0.f;
+    for (int i = 0; i < 4; ++i) ag[c][i] = ab[c][i] = ad[c][i] = make_float2(0.f, 0.f);
   const float invH = 1.f / H;
   const int stride = gridDim.x * LNB_WARPS;
   int row = blockIdx.x * LNB_WARPS + warp;
@@ -238,68 +243,75 @@ ln_bwd_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ z, int T, in
     }
   };
   if (row < T) fetch(row);
+  // The arithmetic below is packed: sm_100's FFMA2 / FADD2 / FMUL2 (__ffma2_rn ...) work on two fp32 values per
+  // instruction.  With scalar FFMA this kernel sat on the fma pipe (ncu r02j: issue active 62 % at 64 % of DRAM, ~13 fp32
+  // operations per element against a 3-register FFMA rate of one warp instruction per two cycles per scheduler).
   for (; row < T; row += stride) {
-    float v[NC][8], g[NC][8];
-    float s = 0.f;
+    float2 v[NC][4], g[NC][4];
+    float2 sp = make_float2(0.f, 0.f);
 #pragma unroll
     for (int c = 0; c < NC; ++c) {
       if (c * 256 + lane * 8 < H) {
-        unpack8<NP>(zr[c], v[c]);
-        unpack8<NP>(dr[c], g[c]);
+        unpack8<NP>(zr[c], as8(v[c]));
+        unpack8<NP>(dr[c], as8(g[c]));
         if constexpr (DM == 1)
-          drop_apply8(g[c], drop_bits(drop, (c * 256 + lane * 8) >> 3, row, 0u), drop.thr_hi, drop.scale);
+          drop_apply8(as8(g[c]), drop_bits(drop, (c * 256 + lane * 8) >> 3, row, 0u), drop.thr_hi, drop.scale);
 #pragma unroll
-        for (int i = 0; i < 8; ++i) s += v[c][i];
+        for (int i = 0; i < 4; ++i) sp = __fadd2_rn(sp, v[c][i]);
       }
     }
     if (row + stride < T) fetch(row + stride);
-    const float mean = warp_sum(s) * invH;
-    float q2 = 0.f;
+    const float mean = warp_sum(sp.x + sp.y) * invH;
+    const float2 nmean = make_float2(-mean, -mean);
+    float2 qp = make_float2(0.f, 0.f);
 #pragma unroll
     for (int c = 0; c < NC; ++c)
       if (c * 256 + lane * 8 < H)
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          v[c][i] -= mean;
-          q2 += v[c][i] * v[c][i];
+        for (int i = 0; i < 4; ++i) {
+          v[c][i] = __fadd2_rn(v[c][i], nmean);
+          qp = __ffma2_rn(v[c][i], v[c][i], qp);
         }
-    const float rstd = rsqrtf(warp_sum(q2) * invH + eps);
-    float s1 = 0.f, s2 = 0.f;
+    const float rstd = rsqrtf(warp_sum(qp.x + qp.y) * invH + eps);
+    const float2 rstd2 = make_float2(rstd, rstd);
+    float2 s1p = make_float2(0.f, 0.f), s2p = make_float2(0.f, 0.f);
 #pragma unroll
     for (int c = 0; c < NC; ++c) {
       const int col = c * 256 + lane * 8;
       if (col < H) {
-        float gm[8];
-        ld8f(gamma + col, gm);
+        float2 gm[4];
+        ld8f(gamma + col, as8(gm));
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const float xh = v[c][i] * rstd;
-          const float d = g[c][i];
+        for (int i = 0; i < 4; ++i) {
+          const float2 xh = __fmul2_rn(v[c][i], rstd2);
+          const float2 d = g[c][i];
           v[c][i] = xh;
-          ag[c][i] += d * xh;
-          ab[c][i] += d;
-          g[c][i] = d * gm[i];
-          s1 += g[c][i];
-          s2 += g[c][i] * xh;
+          ag[c][i] = __ffma2_rn(d, xh, ag[c][i]);
+          ab[c][i] = __fadd2_rn(ab[c][i], d);
+          g[c][i] = __fmul2_rn(d, gm[i]);
+          s1p = __fadd2_rn(s1p, g[c][i]);
+          s2p = __ffma2_rn(g[c][i], xh, s2p);
         }
       }
     }
-    s1 = warp_sum(s1) * invH;
-    s2 = warp_sum(s2) * invH;
+    const float s1 = warp_sum(s1p.x + s1p.y) * invH;
+    const float s2 = warp_sum(s2p.x + s2p.y) * invH;
+    // dz = rstd * (g - s1 - xhat * s2) = g * rstd + (xhat * (-rstd s2) + (-rstd s1))
+    const float2 kb = make_float2(-rstd * s1, -rstd * s1), kc = make_float2(-rstd * s2, -rstd * s2);
 #pragma unroll
     for (int c = 0; c < NC; ++c) {
       const int col = c * 256 + lane * 8;
       if (col < H) {
-        float o[8];
+        float2 o[4];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) o[i] = rstd * (g[c][i] - s1 - v[c][i] * s2);
-        split_store8<NP>(dz + (long)row * H + col, ps, o);
+        for (int i = 0; i < 4; ++i) o[i] = __ffma2_rn(g[c][i], rstd2, __ffma2_rn(v[c][i], kc, kb));
+        split_store8<NP>(dz + (long)row * H + col, ps, as8(o));
         if constexpr (DM == 2) {
-          drop_apply8(o, drop_bits(drop, col >> 3, row, 0u), drop.thr_hi, drop.scale);
-          split_store8<NP>(dzm + (long)row * H + col, ps, o);
+          drop_apply8(as8(o), drop_bits(drop, col >> 3, row, 0u), drop.thr_hi, drop.scale);
+          split_store8<NP>(dzm + (long)row * H + col, ps, as8(o));
         }
 #pragma unroll
-        for (int i = 0; i < 8; ++i) ad[c][i] += o[i];
+        for (int i = 0; i < 4; ++i) ad[c][i] = __fadd2_rn(ad[c][i], o[i]);
       }
     }
   }
@@ -314,7 +326,7 @@ ln_bwd_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ z, int T, in
       __syncthreads();
 #pragma unroll
       for (int i = 0; i < 8; ++i)
-        red[warp][lane * 8 + i] = which == 0 ? ag[c][i] : (which == 1 ? ab[c][i] : ad[c][i]);
+        red[warp][lane * 8 + i] = which == 0 ? as8(ag[c])[i] : (which == 1 ? as8(ab[c])[i] : as8(ad[c])[i]);
       __syncthreads();
       const int col = c * 256 + threadIdx.x;
       if (threadIdx.x < 256 && col < H) {

@@ -1,0 +1,11 @@
+cp simxns_b200/libsimx_b200.so /tmp/new.so
+cp simxns_b200/libsimx_b200_old.so /tmp/old.so
+for rep in 1 2; do
+for lib in old new; do
+  cp /tmp/$lib.so simxns_b200/libsimx_b200.so
+  for c in qkv_fwd attnout_fwd ffn1_fwd ffn2_fwd ffn2_dgrad ffn1_dgrad qkv_dgrad; do
+    echo -n "$lib "; python tools/profile_gemm.py $c --tokens 262144 --iters 20 2>&1 | tail -1
+  done
+done
+done
+cp /tmp/new.so simxns_b200/libsimx_b200.so
