@@ -127,6 +127,13 @@ __device__ __forceinline__ void tma_load_2d_2sm(const CUtensorMap* d, uint64_t* 
       "l"(reinterpret_cast<uint64_t>(d)), "r"(mbar), "r"(c0), "r"(c1)
       : "memory");
 }
+// 1-D bulk copy global -> shared (no tensor map): `bytes` and both addresses are multiples of 16; completion is counted
+// on the mbarrier like a tensor load
+__device__ __forceinline__ void bulk_load_1d(uint32_t smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_dst),
+               "l"(gsrc), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
 __device__ __forceinline__ void tma_store_2d(const CUtensorMap* d, const void* smem, int32_t c0, int32_t c1) {
   asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(
                    reinterpret_cast<uint64_t>(d)),
