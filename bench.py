@@ -423,6 +423,16 @@ def run_b200(args):
                             step_share=dom["share"],
                             all_gemm_tflops=sum(k["flops"] for k in gemms) / sum(k["ms"] for k in gemms) / 1e9,
                             all_gemm_step_share=sum(k["ms"] for k in gemms) / tot)
+            wp = ROOT / "profiles" / "r02_hbm_write_probe.json"
+            if dom["name"] == "ffn1_fwd" and wp.exists():
+                # the FFN-up GEMM stores gelu and gelu' ([tokens, I] bf16 each): its second bound is the WRITE side of HBM
+                # (pure stores peak well below the copy figure; DESIGN §5 "What bounds ffn1_fwd")
+                tokens = nq * args.q_len + nq * group * args.p_len
+                written = 2.0 * tokens * 3072 * 2 * args.layers  # bytes per step
+                wpeak = json.loads(wp.read_text())["write_gbs_fill"]
+                roofline["store_path"] = dict(written_bytes_per_step=written, achieved_gbs=written / dom["ms"] / 1e6,
+                                              peak_gbs=wpeak, frac=written / dom["ms"] / 1e6 / wpeak,
+                                              peak_source="profiles/r02_hbm_write_probe.json (torch fill_ over 4 GiB)")
 
     # ---------------- CPU baseline (rank 0, N = 1 only) ----------------
     cpu_baseline = None
