@@ -389,10 +389,14 @@ def run_b200(args):
     if not args.no_profile:
         barrier()
         prof_steps = 6  # several steps: one step's per-kernel times swing +-10 % with the power-capped clock
+        overlap = model.overlap_towers
+        model.overlap_towers = False  # per-kernel times of kernels that run alone (the timed steps overlap the two towers)
+        torch.cuda.synchronize()
         _lib.profile_begin()
         for i in range(prof_steps):
             step(resident[i % n_batches])
         kernels = _lib.profile_end()
+        model.overlap_towers = overlap
         for k in kernels:
             k["launches"] //= prof_steps
             k["ms"] /= prof_steps
@@ -459,7 +463,9 @@ def run_b200(args):
         fpp = flops_per_pair(args.layers, args.q_len, args.p_len, group)
         line = dict(metric=METRIC, value=value, unit=UNIT, n_gpus=world, steps=args.steps, warmup=args.warmup,
                     ms_per_step=ms_step, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="bf16",
-                    data="synthetic", config=dict(workload_config(args, nq), gradient_exchange=exchange), e2e=e2e,
+                    data="synthetic", config=dict(workload_config(args, nq), gradient_exchange=exchange,
+                                                    tower_overlap="query tower on a second CUDA stream" if model.overlap_towers
+                                                    else "off"), e2e=e2e,
                     gpu_launches=(launches_per_step * args.steps if launches_per_step else None), clocks=clocks,
                     roofline=roofline, cpu_baseline=cpu_baseline, dropout=dropout, rank_compute=rank_compute,
                     parity_mode=parity_mode,

@@ -168,3 +168,39 @@ def test_data_style_optimizer_updates_reach_the_kernels():
         _, want, _ = fresh(input_ids=ids, attention_mask=mask)
     assert (after - pooled.detach()).abs().max().item() > 1e-3  # the step moved the output ...
     assert torch.equal(after, want)                              # ... exactly to what the new weights give
+
+
+def test_two_stream_tower_overlap_changes_nothing_but_the_schedule():
+    """BiBertEncoder issues the query tower on a second CUDA stream (models.BiBertEncoder._towers).  Same kernels, same
+    inputs: embeddings bit-identical, gradients identical up to the order of the split-K / column-sum atomics; weight
+    updates made on the main stream between two calls are seen by the side stream; and outputs consumed on the main stream
+    right away (loss, backward) are complete.  (Several optimizer steps are NOT compared: Adam turns the atomics' rounding
+    noise on true-zero gradients into +-lr updates, so two runs of the SAME schedule drift apart as well.)"""
+    from simxns_b200.losses import simans_distill_loss
+    from test_gpu_parity import BF16, build, cu
+
+    cfg = bn.bert_config(num_layers=2, hidden=128, heads=2, intermediate=256, vocab=400, max_pos=160)
+    pq, pc = bn.synth_params(cfg, seed=3), bn.synth_params(cfg, seed=4)
+    q_ids, q_mask = bn.synth_tokens(16, 32, cfg["vocab"], seed=5, ragged=True)
+    p_ids, p_mask = bn.synth_tokens(64, 128, cfg["vocab"], seed=6, ragged=True)
+    teacher = torch.randn(16, 4, generator=torch.Generator().manual_seed(7)).cuda()
+    outs = []
+    for overlap in (False, True):
+        model = BiBertEncoder(None, question_model=build(cfg, pq, BF16), ctx_model=build(cfg, pc, BF16)).train()
+        model.overlap_towers = overlap
+        q, a = model(cu(q_ids), cu(q_mask), cu(p_ids), cu(p_mask))
+        loss = simans_distill_loss(q, a, teacher, temperature_distill=1.0)
+        loss.backward()
+        grads = {n: p.grad.clone() for n, p in model.named_parameters()}
+        with torch.no_grad():  # an in-place update of every master weight, issued on the main stream
+            for p in model.parameters():
+                p.mul_(1.01)
+            q2, a2 = model(cu(q_ids), cu(q_mask), cu(p_ids), cu(p_mask))
+        outs.append((loss.item(), q.detach().clone(), a.detach().clone(), grads, q2.clone(), a2.clone()))
+    (l0, q0, a0, g0, q20, a20), (l1, q1, a1, g1, q21, a21) = outs
+    assert torch.equal(q0, q1) and torch.equal(a0, a1) and abs(l0 - l1) < 1e-6
+    assert torch.equal(q20, q21) and torch.equal(a20, a21) and not torch.equal(q20, q0)
+    gmax = max(float(g.abs().max()) for g in g0.values())
+    for n in g0:
+        err = float((g0[n] - g1[n]).abs().max())
+        assert err <= 2e-3 * max(float(g0[n].abs().max()), 1e-2 * gmax), (n, err)
