@@ -244,6 +244,7 @@ def run_b200(args):
     model = BiBertEncoder(None, question_model=HFBertEncoder(ec, precision=_lib.PREC_BF16),
                           ctx_model=HFBertEncoder(ec, precision=_lib.PREC_BF16)).to(dev)
     step_model = model
+    overlap_desc = "query tower on a second CUDA stream" if model.overlap_towers else "off"
     exchange = "none"
     if world > 1 and os.environ.get("SIMX_BENCH_DDP", "0") == "1":
         # the reference's wrap (co_training_marco_train.py:109-114) plus bucket views: .grad aliases the all-reduce
@@ -464,8 +465,7 @@ def run_b200(args):
         line = dict(metric=METRIC, value=value, unit=UNIT, n_gpus=world, steps=args.steps, warmup=args.warmup,
                     ms_per_step=ms_step, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="bf16",
                     data="synthetic", config=dict(workload_config(args, nq), gradient_exchange=exchange,
-                                                    tower_overlap="query tower on a second CUDA stream" if model.overlap_towers
-                                                    else "off"), e2e=e2e,
+                                                    tower_overlap=overlap_desc), e2e=e2e,
                     gpu_launches=(launches_per_step * args.steps if launches_per_step else None), clocks=clocks,
                     roofline=roofline, cpu_baseline=cpu_baseline, dropout=dropout, rank_compute=rank_compute,
                     parity_mode=parity_mode,

@@ -254,6 +254,10 @@ def _side_stream(device: torch.device) -> "torch.cuda.Stream":
     idx = device.index if device.index is not None else torch.cuda.current_device()
     if idx not in _SIDE_STREAMS:
         _SIDE_STREAMS[idx] = torch.cuda.Stream(device=idx)
+        # parameters live on the default stream, the query tower's gradients are produced on the side stream: intended
+        quiet = getattr(torch.autograd.graph, "set_warn_on_accumulate_grad_stream_mismatch", None)
+        if quiet is not None:
+            quiet(False)
     return _SIDE_STREAMS[idx]
 
 
