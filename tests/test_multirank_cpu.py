@@ -166,3 +166,55 @@ def test_two_rank_flat_gradsync_layout(tmp_path):
         (lo0, hi0, chunk, numel), (lo1, hi1, _, _) = r[0][f"range{i}"], r[1][f"range{i}"]
         assert lo0 == 0 and hi0 == lo1 and hi1 == numel              # the two chunks tile [0, numel)
     assert r[0]["sum"] == r[1]["sum"]
+
+
+def _col_worker(rank, world, port, out_dir):
+    """losses.gather_tensor + lead_col_distill_loss(gather=True) across ranks (pure tensor code: runs on gloo / CPU)"""
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from simxns_b200.losses import gather_tensor, lead_col_distill_loss
+
+    g = np.load(os.path.join(out_dir, "inputs.npz"))
+    nq, group = 2, 3                                       # per rank
+    sl_q, sl_c = slice(rank * nq, (rank + 1) * nq), slice(rank * nq * group, (rank + 1) * nq * group)
+    t = {k: torch.from_numpy(g[k][sl_q if k.startswith("q") else sl_c].copy()).requires_grad_(True)
+         for k in ("q_db", "c_db", "q_col", "c_col", "qL_db", "cL_db", "qL_col", "cL_col")}
+    mask = torch.from_numpy(g["doc_mask"][sl_c].copy())
+    full = gather_tensor(t["q_db"])
+    assert full.shape[0] == world * nq and torch.equal(full[sl_q], t["q_db"])
+    loss, _ = lead_col_distill_loss(t["q_db"], t["c_db"], t["q_col"], t["c_col"], mask, t["qL_db"], t["cL_db"], t["qL_col"],
+                                    t["cL_col"], selected_db=[0, 2], selected_col=[1, 3], temperature=2.0,
+                                    layer_temperature=0.5, para_dis=1.3, reweight=True, train_col=True, gather=True)
+    loss.backward()
+    np.savez(os.path.join(out_dir, f"c{rank}.npz"), loss=np.array([loss.item()]), **{k: v.grad.numpy() for k, v in t.items()})
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_two_rank_col_distill_equals_single_process(tmp_path):
+    """every rank evaluates the SAME global loss; its local gradients are the matching slices of the single-process
+    gradients (remote rows are constants: LEAD/util.py:200-204)"""
+    from simxns_b200.losses import lead_col_distill_loss
+
+    rng = np.random.RandomState(5)
+    GQ, group, H, Sq, Sd = 4, 3, 16, 4, 6
+    mk = lambda *s: (rng.standard_normal(s) * 0.5).astype(np.float32)
+    arrs = dict(q_db=mk(GQ, H), c_db=mk(GQ * group, H), q_col=mk(GQ, Sq, H), c_col=mk(GQ * group, Sd, H), qL_db=mk(GQ, 3, H),
+                cL_db=mk(GQ * group, 3, H), qL_col=mk(GQ, 4, Sq, H), cL_col=mk(GQ * group, 4, Sd, H))
+    doc_mask = (np.arange(Sd)[None] < rng.randint(2, Sd + 1, size=GQ * group)[:, None]).astype(np.int64)
+    np.savez(tmp_path / "inputs.npz", doc_mask=doc_mask, **arrs)
+    world = 2
+    mp.spawn(_col_worker, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
+    t = {k: torch.from_numpy(v.copy()).requires_grad_(True) for k, v in arrs.items()}
+    loss, _ = lead_col_distill_loss(t["q_db"], t["c_db"], t["q_col"], t["c_col"], torch.from_numpy(doc_mask), t["qL_db"],
+                                    t["cL_db"], t["qL_col"], t["cL_col"], selected_db=[0, 2], selected_col=[1, 3],
+                                    temperature=2.0, layer_temperature=0.5, para_dis=1.3, reweight=True, train_col=True,
+                                    gather=False)
+    loss.backward()
+    for r in range(world):
+        got = np.load(tmp_path / f"c{r}.npz")
+        assert abs(float(got["loss"][0]) - loss.item()) < 1e-5
+        for k, v in t.items():
+            n = v.shape[0] // world
+            assert np.allclose(got[k], v.grad.numpy()[r * n:(r + 1) * n], atol=1e-6, rtol=1e-4), (r, k)
