@@ -100,3 +100,27 @@ def test_warm_up_losses_vs_reference(gold):
     assert abs(lc.item() - float(gold["ce_warm_loss"][0])) < 1e-6 and np.allclose(t.grad.numpy(), gold["ce_warm_d"], atol=1e-7)
     with pytest.raises(RuntimeError, match="CUDA"):      # the dual-encoder branch is the fused kernel: no CPU path
         get_loss_dual(types.SimpleNamespace(model_type="dual_encoder"), q[:, 0], c[:, 0], None)
+
+
+def test_colbert_score_random_shapes_vs_direct_formula():
+    """seeded sweep over (queries, documents, lengths, width, chunk): forward and both gradients against the direct
+    einsum / max / sum formulation under autograd"""
+    rng = np.random.RandomState(11)
+    for _ in range(12):
+        Q, D, Sq, Sd, H = (int(rng.randint(1, 5)), int(rng.randint(1, 9)), int(rng.randint(1, 6)), int(rng.randint(1, 9)),
+                           int(rng.choice([4, 16, 32])))
+        chunk = int(rng.randint(1, D + 2))
+        q = torch.from_numpy(rng.standard_normal((Q, Sq, H)).astype(np.float32)).requires_grad_(True)
+        d = torch.from_numpy(rng.standard_normal((D, Sd, H)).astype(np.float32)).requires_grad_(True)
+        mask = torch.from_numpy((rng.rand(D, Sd) < 0.7).astype(np.int64))
+        mask[:, 0] = 1                                            # at least one kept token per document
+        w = torch.from_numpy(rng.standard_normal((Q, D)).astype(np.float32))
+        got = colbert_score(q, d, mask, Q, chunk=chunk)
+        (got * w).sum().backward()
+        gq, gd = q.grad.clone(), d.grad.clone()
+        q.grad = d.grad = None
+        logits = torch.einsum("qih,djh->qidj", q, d).masked_fill(mask[None, None] == 0, -9e9)
+        want = logits.max(3).values.sum(1)
+        (want * w).sum().backward()
+        assert torch.allclose(got, want, atol=1e-5, rtol=1e-5)
+        assert torch.allclose(gq, q.grad, atol=1e-5, rtol=1e-4) and torch.allclose(gd, d.grad, atol=1e-5, rtol=1e-4)
