@@ -206,7 +206,15 @@ ln_fwd_kernel(const bf16* __restrict__ z, int T, int H, const float* __restrict_
 // gamma / beta copies already use.  Here each warp owns a ring of LNF_SLOTS shared-memory slots of LNF_G consecutive rows;
 // lane 0 keeps LNF_SLOTS - 1 bulk copies (cp.async.bulk, completion on an mbarrier per slot) ahead of the row being
 // normalised, so bytes in flight no longer depend on registers: 16 warps x 2 slots x 3 KB = 96 KB per SM.
-constexpr int LNF_SLOTS = 3, LNF_G = 2;
+// (slots, rows per slot) swept on one box at 4 layers: (3,2) 5.5-5.6 TB/s, (4,2) 5.4, (2,4) 5.3, (4,1) 4.9, (3,4) 4.2 —
+// tools/sweep_ln_fwd.sh builds the variants with -DSIMX_LNF_SLOTS / -DSIMX_LNF_G
+#ifndef SIMX_LNF_SLOTS
+#define SIMX_LNF_SLOTS 3
+#endif
+#ifndef SIMX_LNF_G
+#define SIMX_LNF_G 2
+#endif
+constexpr int LNF_SLOTS = SIMX_LNF_SLOTS, LNF_G = SIMX_LNF_G;
 template <int NC>
 __global__ void __launch_bounds__(ROW_THREADS, 2)
 ln_fwd_bulk_kernel(const bf16* __restrict__ z, int T, int H, const float* __restrict__ gamma, const float* __restrict__ beta,
