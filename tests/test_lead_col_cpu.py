@@ -124,3 +124,40 @@ def test_colbert_score_random_shapes_vs_direct_formula():
         (want * w).sum().backward()
         assert torch.allclose(got, want, atol=1e-5, rtol=1e-5)
         assert torch.allclose(gq, q.grad, atol=1e-5, rtol=1e-4) and torch.allclose(gd, d.grad, atol=1e-5, rtol=1e-4)
+
+
+def test_oracle_hidden_state_backward_vs_reference_colbert_tower(golden_dir):
+    """pins the oracle's `backward(d_hidden=)` (the checker of simx_encoder_add_cotangent) to the reference itself: the numpy
+    tower's per-layer states equal those of LEAD's HFColBertEncoder, and pushing the cotangents of the reference's loss
+    (colbert_score on the normalised output and on layer 1) through the oracle reproduces the reference's parameter
+    gradients (tests/golden/lead_colbert_tiny.npz)"""
+    from oracle import bert_numpy as bn
+
+    g = np.load(golden_dir / "lead_colbert_tiny.npz")
+    cfg = bn.bert_config(num_layers=3, hidden=128, heads=2, intermediate=256, vocab=512, max_pos=64)
+    params = bn.synth_params(cfg, seed=int(g["seed"][0]))
+    layer = int(g["layer"][0])
+    oq, od = bn.EncoderOracle(cfg, params), bn.EncoderOracle(cfg, params)
+    hq = np.stack(oq.forward(g["q_ids"], g["q_mask"])["hidden"], axis=1)
+    hd = np.stack(od.forward(g["d_ids"], g["d_mask"])["hidden"], axis=1)
+    assert np.abs(hq[:, 1:] - g["q_hid"]).max() < 2e-5 and np.abs(hd[:, 1:] - g["d_hid"]).max() < 2e-5
+    tq = torch.from_numpy(hq).requires_grad_(True)
+    td = torch.from_numpy(hd).requires_grad_(True)
+    mask = torch.from_numpy(g["d_mask"])
+    norm = torch.nn.functional.normalize
+    scores = colbert_score(norm(tq[:, -1], p=2, dim=2), norm(td[:, -1], p=2, dim=2), mask, 2)
+    layer_scores = colbert_score(tq[:, layer + 1], td[:, layer + 1], mask, 2) / 64.0
+    assert np.abs(scores.detach().numpy() - g["scores"]).max() < 1e-4
+    target = torch.tensor([0, 3])
+    lsm = torch.nn.functional.log_softmax
+    loss = torch.nn.functional.nll_loss(lsm(scores, dim=-1), target) + 0.5 * torch.nn.functional.nll_loss(lsm(layer_scores, dim=-1), target)
+    assert abs(loss.item() - float(g["loss"][0])) < 1e-5
+    loss.backward()
+    gq, gd = oq.backward(d_hidden=tq.grad.numpy()), od.backward(d_hidden=td.grad.numpy())
+    worst = 0.0
+    scale = max(np.abs(g[k]).max() for k in g.files if k.startswith("grad/"))
+    for k in g.files:
+        if k.startswith("grad/"):
+            n = k[5:]
+            worst = max(worst, np.abs(gq[n] + gd[n] - g[k]).max() / max(np.abs(g[k]).max(), 1e-3 * scale))
+    assert worst < 2e-4, worst
