@@ -41,3 +41,26 @@ def test_missing_library_fails_loudly():
             "    print('raised')\n") % str(ROOT)
     out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True)
     assert out.stdout.strip() == "raised", out.stderr[-500:]
+
+
+def test_reference_arm_prints_the_contract_line():
+    """`bench.py --impl reference` (the CPU arm the driver times next to the GPU arm): ONE JSON line with the metric / unit of
+    BASELINE.json, `impl`, a `cpu_baseline` describing the run and an `e2e` that moves no bytes"""
+    import json
+    import subprocess
+    import sys
+
+    out = subprocess.run([sys.executable, str(ROOT / "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0",
+                          "--layers", "1", "--ref-queries", "1"], capture_output=True, text=True, timeout=600, cwd=str(ROOT))
+    assert out.returncode == 0, out.stderr[-2000:]
+    lines = [l for l in out.stdout.strip().splitlines() if l.startswith("{")]
+    assert len(lines) == 1, out.stdout
+    d = json.loads(lines[0])
+    base = json.loads((ROOT / "BASELINE.json").read_text())
+    assert d["impl"] == "reference" and d["unit"] == "pairs/s" and d["higher_is_better"] is True
+    assert d["metric"].startswith("query+passage pairs/sec") and base["metric"].startswith("query+passage pairs/sec")
+    assert d["value"] > 0 and d["steps"] == 1 and d["n_gpus"] == 1 and d["vs_baseline"] is None
+    assert d["cpu_baseline"]["kind"] in ("port", "reference") and d["cpu_baseline"]["cores"] >= 1
+    assert abs(d["cpu_baseline"]["value"] - d["value"]) < 1e-9
+    assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0 and d["e2e"]["value"] == d["value"]
+    assert "workload" in d["config"]
